@@ -1,0 +1,106 @@
+/*
+ * vtrace_oracle.h — CPU ORACLE for the vtrace voxel ray-traversal hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the shipped product (vtrace_b200/,
+ * include/, librender) may include, link or call this.  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * use it, and only as the checker / CPU baseline.
+ *
+ * What it is: a C restatement of the reference's GPU programs
+ *   shaders/trace.vert:32-47, shaders/trace.frag:41-90
+ * plus the fixed-function state that decides which fragment wins
+ *   lib/pipeline.c:114-152 (cull/depth/blend), lib/command.c:56-102 (clear,
+ *   viewport h = w, scissor), lib/descriptor.c:97-117 (NEAREST, clamp),
+ *   lib/memory.c:317 (R8G8B8A8_SRGB), lib/memory.c:22-40 (unit cube proxy).
+ *
+ * Pinning status: the reference ships no golden vectors for this path
+ *  and cannot be built or run here (no Vulkan/GLFW/rustc).
+ * The traversal core (vo_frag_main) is pinned instead against the reference's
+ * own compiled shader binary shaders/trace.frag.spv, executed by
+ * tools/spirv_interp.py; the resulting vectors live in tests/golden/.  The
+ * .vox loader restatement is pinned by the SHA-256s of SURVEY.md §A.4.
+ * The rasteriser (pixel -> proxy-face point) and everything path-tracing
+ * (bounces, RNG, accumulation) have no reference counterpart: "parity
+ * unpinned" for those parts; they are DEFINED here.
+ */
+#ifndef VTRACE_ORACLE_H
+#define VTRACE_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VO_MISS 0xFFFFFFFFu
+
+/* flags */
+#define VO_FLAG_VIEWPORT_H_IS_W 1u /* reference-faithful viewport (lib/command.c:80-81) */
+
+/* Per-pixel derived hit record. 16 bytes. */
+typedef struct vo_hit_record {
+    uint32_t hit_voxel; /* X + W*(Y + H*Z) of model_ray_voxel at the hit, VO_MISS otherwise   */
+    uint32_t packed;    /* bits 0-15 steps at hit, bits 16-18 mask of last executed step,     */
+                        /* bits 19-21 (step<0) per axis; 0 on miss                            */
+    uint32_t instance;  /* gl_InstanceIndex of the winning fragment, VO_MISS otherwise        */
+    uint32_t iters;     /* DDA loop iterations executed by ALL fragments covering this pixel  */
+} vo_hit_record;
+
+typedef struct vo_scene vo_scene;
+
+vo_scene* vo_scene_create(void);
+void vo_scene_destroy(vo_scene*);
+/* mirrors add_texture (lib/memory.c:286): copies 4*w*h*d bytes, returns id or -1 */
+int32_t vo_add_texture(vo_scene*, const uint8_t* rgba, uint32_t w, uint32_t h, uint32_t d);
+/* mirrors start/end_update_instances (lib/memory.c:235-267): n x 16 floats, column-major,
+ * texture id bit-cast into element [3][3] (src/render.rs:74-78). n == 0 is coerced to 1. */
+void vo_set_instances(vo_scene*, const float* mats, uint32_t n);
+
+/* One frame of primary rays = one vkCmdDrawIndexed (lib/command.c:102).
+ * P, V: 16 floats column-major (push constants, lib/command.c:97-98).
+ * Any output pointer may be NULL.  rgba8 is R,G,B,A byte order, sRGB-encoded.
+ * Returns total DDA iterations (sum of records[].iters). */
+uint64_t vo_render_primary(const vo_scene*, const float* P, const float* V, int width, int height,
+                           uint32_t flags, vo_hit_record* records, uint8_t* rgba8, float* depth,
+                           int num_threads);
+
+/* Path-tracing extension (not in the reference; defined in DESIGN.md §3).
+ * Renders samples s = sample_first + k*sample_stride, k in [0, sample_count).
+ * accum: 3 x uint64 per pixel, fixed-point 2^-24 radiance sums (added to, not cleared).
+ * stats[0] += ray segments traced, stats[1] += DDA iterations. */
+void vo_render_paths(const vo_scene*, const float* P, const float* V, int width, int height,
+                     uint32_t flags, uint32_t bounces, uint32_t seed, uint32_t sample_first,
+                     uint32_t sample_stride, uint32_t sample_count, uint64_t* accum,
+                     uint64_t* stats, int num_threads);
+
+/* accum -> RGBA8 (sRGB-encoded), dividing by total_spp */
+void vo_resolve(const uint64_t* accum, int width, int height, uint32_t total_spp, uint8_t* rgba8);
+
+/* Run ONLY trace.frag's main() (shaders/trace.frag:41-90) for one fragment with explicit
+ * varyings; used to pin the restatement against the SPIR-V interpreter's vectors.
+ * out[0]=hit(0/1) out[1..3]=voxel out[4]=steps out[5]=last mask bits; color: 4 floats. */
+void vo_frag_main(const float* P, const float* V, const float* M, const float* screen_position,
+                  const float* model_position, const uint8_t* rgba, uint32_t w, uint32_t h,
+                  uint32_t d, int32_t* out, float* color, float* frag_depth);
+
+/* Uniform matrices derived per frame / per instance; exposed so tests can compare the
+ * product's host-side derivation bit for bit. out: 16 floats. */
+void vo_mat4_inverse(const float* m, float* out);
+void vo_mat4_mul(const float* a, const float* b, float* out);
+
+/* .vox loader restatement (src/voxel/magica_voxel.rs:18-44 over dot_vox 4.1.0).
+ * Writes the first model as the reference's RawDynamicChunk<Color> bytes (z fastest,
+ * src/voxel/rawchunk.rs:292) = exactly what add_texture receives.  Returns 0 on success.
+ * Call with out == NULL to query dims only. */
+int vo_load_vox(const char* path, uint32_t dims[3], uint8_t* out, uint64_t out_capacity);
+
+/* sRGB helpers shared by resolve and blend (exposed for tests) */
+float vo_srgb_decode(uint8_t c);
+uint8_t vo_srgb_encode(float linear);
+
+int vo_max_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
