@@ -1,0 +1,167 @@
+/*
+ * vtrace_abi.h — C ABI of librender (B200 / CUDA backend for vtrace's voxel tracing path).
+ *
+ * Part 1 is EXACTLY the surface the reference's Rust engine binds in
+ * src/render.rs:110-128 and today links from lib/entry.c + lib/memory.c (static librender.a,
+ * build.rs:71-72,96-97).  Same symbol names, argument meaning, return conventions, ownership
+ * and threading rules, so this library is a drop-in for that path.  The Vulkan window,
+ * swapchain and present are replaced by a headless framebuffer that Part 2 reads back.
+ *
+ * Part 2 (vt_*) are extension symbols the Rust engine does not know about: headless
+ * configuration, framebuffer read-back, statistics and the hooks a multi-process launcher
+ * (one process per GPU) needs to reduce the accumulation buffers with NCCL.
+ *
+ * Plain C: fixed-width integers, raw pointers and sizes only.  No CUDA, torch or C++ types.
+ * Every entry point is callable from any OS thread (the reference calls from two,
+ * src/main.rs:40-50), never concurrently; each one selects its CUDA device itself.
+ * Nothing unwinds across the boundary; errors are return codes.
+ */
+#ifndef VTRACE_ABI_H
+#define VTRACE_ABI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ======================================================================================== */
+/* Part 1 — the reference's FFI, unchanged                                                   */
+
+/* lib/common.h:89-92  <->  RenderTickInfo, src/render.rs:177-181.
+ * Both point at 16 floats, column-major mat4 (glm-rs layout): projection then camera,
+ * the two push constants of lib/command.c:97-98.  Valid only during the call. */
+typedef struct render_tick_info {
+    void* perspective;
+    void* camera;
+} render_tick_info;
+
+/* lib/common.h:145-151  <->  UserInput, src/render.rs:37-51 (40 bytes). */
+typedef struct user_input {
+    uint8_t keys[6]; /* w a s d space lshift */
+    double mouse_x;
+    double mouse_y;
+    double last_mouse_x;
+    double last_mouse_y;
+} user_input;
+
+/* replaces lib/entry.c:54-57 (+ init, :59-98).  One-time initialisation: selects the CUDA
+ * device, creates the stream, framebuffers and tables, reads VT_* environment overrides
+ * (see vt_config).  Returns 0 on success; non-zero = (cudaError << 32) | custom code, which
+ * the Rust side turns into a panic (src/render.rs:185-188). */
+uint64_t entry(void);
+
+/* replaces lib/entry.c:150-248.  Renders one frame with the given projection / camera into
+ * the headless framebuffer, then writes the framebuffer size to `*window_width` and `*window_height`
+ * (lib/entry.c:244-245; the engine derives its aspect ratio from them, src/render.rs:282-292).
+ * Returns 0 = keep going, -1 = stop (configured frame budget exhausted) or error. */
+int32_t render_tick(int32_t* window_width, int32_t* window_height, const render_tick_info* info);
+
+/* replaces lib/entry.c:146-148.  Pointer into library-owned static storage, valid for the
+ * life of the process.  Headless: all zero unless scripted through vt_set_user_input. */
+user_input* get_input_data_pointer(void);
+
+/* replaces lib/memory.c:286-385.  Copies 4*width*height*depth bytes of RGBA8 (`Color`,
+ * src/voxel/common.rs:65-72; x fastest as the Vulkan copy reads it, lib/memory.c:353-366)
+ * before returning, uploads them and builds the volume's traversal masks (the slot that
+ * lib/raytrace.c's never-consumed BLAS build occupies).  Returns the dense texture id
+ * (0, 1, 2, ... lib/memory.c:292,384) or -1 (MAX_TEXTURES reached, lib/memory.c:287-290,
+ * or device error). */
+int32_t add_texture(const uint8_t* data, uint32_t width, uint32_t height, uint32_t depth);
+
+/* replaces lib/memory.c:235-248.  Returns a write pointer with room for max(instance_count,1)
+ * 64-byte column-major mat4s (texture id bit-cast into element [3][3], src/render.rs:74-78),
+ * valid until end_update_instances; NULL on failure. */
+float* start_update_instances(uint32_t instance_count);
+
+/* replaces lib/memory.c:250-267.  Commits the first instance_count instances (0 is coerced
+ * to 1, lib/memory.c:251).  0 = ok, -1 = error. */
+int32_t end_update_instances(uint32_t instance_count);
+
+/* replaces lib/entry.c:100-144.  Waits for the device, frees everything. */
+void cleanup(void);
+
+/* ======================================================================================== */
+/* Part 2 — headless extensions (new symbols; the Rust engine never calls them)              */
+
+#define VT_MISS 0xFFFFFFFFu
+
+/* render modes */
+#define VT_MODE_PRIMARY 0u /* the reference's pass: one DDA per covered fragment (trace.frag)  */
+#define VT_MODE_PATHS 1u   /* extension: spp jittered paths per pixel, diffuse bounces, sky     */
+
+/* flags */
+#define VT_FLAG_VIEWPORT_H_IS_W 1u /* reproduce lib/command.c:80-81 (viewport height = width)  */
+#define VT_FLAG_NO_HIT_RECORDS 2u  /* do not write the per-pixel hit records                    */
+#define VT_FLAG_FORCE_GLOBAL_MASKS 4u /* keep traversal masks in global memory (no smem staging) */
+
+/* Per-pixel derived hit record (not an output of the reference). 16 bytes. */
+typedef struct vt_hit_record {
+    uint32_t hit_voxel; /* X + W*(Y + H*Z) of model_ray_voxel (trace.frag:68,85) at the hit; VT_MISS  */
+    uint32_t packed;    /* bits 0-15: `steps` (trace.frag:73,86) at the hit; bits 16-18: axes advanced */
+                        /* by the last executed iteration (`mask`, :83), or the proxy-entry axis when  */
+                        /* steps == 0; bits 19-21: model_ray_step < 0 per axis (:69); 0 on miss        */
+    uint32_t instance;  /* gl_InstanceIndex (trace.vert:37) of the winning fragment; VT_MISS          */
+    uint32_t iters;     /* DDA iterations executed by all fragments covering the pixel (late-Z)        */
+} vt_hit_record;
+
+typedef struct vt_config {
+    uint32_t width, height;   /* framebuffer; the reference hard-codes 1000x1000, lib/entry.c:62 */
+    uint32_t mode;            /* VT_MODE_*                                                        */
+    uint32_t flags;           /* VT_FLAG_*                                                        */
+    uint32_t spp;             /* PATHS: samples per pixel rendered BY THIS PROCESS per frame      */
+    uint32_t bounces;         /* PATHS: diffuse bounces after the primary segment                 */
+    uint32_t seed;            /* PATHS: RNG seed                                                  */
+    uint32_t sample_first;    /* PATHS: global index of this process's first sample (= rank)      */
+    uint32_t sample_stride;   /* PATHS: distance between its samples (= number of ranks)          */
+    uint32_t total_spp;       /* PATHS: spp over all ranks, the divisor used by vt_resolve        */
+    int32_t max_frames;       /* render_tick returns -1 after this many frames; <= 0: never       */
+    int32_t device;           /* CUDA device ordinal; < 0: keep (LOCAL_RANK, else 0)              */
+} vt_config;
+
+typedef struct vt_stats {
+    uint64_t frames;          /* frames rendered since entry()                                    */
+    uint64_t rays;            /* last frame: ray segments traced (primary fragments + bounces)    */
+    uint64_t iterations;      /* last frame: DDA loop iterations (= sum of `steps`)               */
+    uint64_t launches;        /* kernels launched since entry()                                   */
+    float last_trace_ms;      /* last frame: device time of the trace kernel (CUDA events)        */
+    float last_frame_ms;      /* last frame: device time of everything render_tick enqueued       */
+    uint32_t masks_in_smem;   /* 1 when the traversal masks were staged in shared memory          */
+    uint32_t reserved;
+} vt_stats;
+
+/* Current configuration (defaults: 1000x1000, PRIMARY, as lib/entry.c:62). */
+int32_t vt_get_config(vt_config* out);
+/* Applies a configuration; (re)allocates framebuffers.  0 = ok, -1 = error. */
+int32_t vt_configure(const vt_config* cfg);
+
+/* Enqueue one frame without host synchronisation or read-back (device-resident measurement);
+ * projection / camera as in render_tick_info.  0 = ok. */
+int32_t vt_render_async(const float* projection, const float* camera);
+/* Block until everything enqueued so far has finished.  0 = ok. */
+int32_t vt_synchronize(void);
+
+/* Read back the last frame.  `capacity` in bytes; returns bytes written or -1. */
+int64_t vt_read_hits(vt_hit_record* out, size_t capacity);
+int64_t vt_read_color(uint8_t* rgba8, size_t capacity); /* R,G,B,A bytes, sRGB-encoded         */
+int64_t vt_read_depth(float* depth, size_t capacity);   /* D32 depth buffer (proxy-face depth) */
+int64_t vt_read_accum(uint64_t* accum, size_t capacity); /* PATHS: 3 x u64 per pixel, 2^-24 fixed point */
+
+/* PATHS multi-process plumbing: the accumulation buffer lives in device memory; a launcher
+ * reduces it across ranks (NCCL sum over 3*w*h uint64) and then resolves it to colour. */
+void* vt_accum_device_ptr(void);
+int32_t vt_clear_accum(void);
+int32_t vt_resolve(void);
+/* Run on a caller-provided cudaStream_t (e.g. the launcher's current stream); NULL = own. */
+int32_t vt_set_stream(void* cuda_stream);
+
+int32_t vt_get_stats(vt_stats* out);
+int32_t vt_set_user_input(const user_input* in);
+/* Last error as text (static storage). */
+const char* vt_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VTRACE_ABI_H */

@@ -1,0 +1,265 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (librender.so), against the
+CPU oracle on the same inputs.  Integer outputs (hit voxel, face, steps, instance, iteration
+counts, colour bytes, fixed-point radiance sums) must be BIT-EXACT; depth is compared bit-exact
+too because both sides execute the same IEEE operations.
+
+Run on the B200 box:  python -m pytest tests -m gpu -x -q
+"""
+import numpy as np
+import pytest
+
+from conftest import RawVolume, make_volume
+from tools import scenes
+from vtrace_b200 import abi, glm
+
+pytestmark = pytest.mark.gpu
+
+
+def _assert_records_equal(got, want, what=""):
+    for field in ("hit_voxel", "packed", "instance", "iters"):
+        g, w = got[field], want[field]
+        if not np.array_equal(g, w):
+            bad = np.argwhere(g != w)
+            y, x = bad[0]
+            raise AssertionError(
+                f"{what}: {field} differs at {len(bad)} pixels; first (x={x}, y={y}): cuda={g[y, x]:#x} oracle={w[y, x]:#x}")
+
+
+class Scene:
+    """Feeds the same textures / instances to librender and to the oracle."""
+
+    _next_tex = 0  # librender's texture table only grows (as the reference's does)
+
+    def __init__(self, renderer, oracle):
+        self.r = renderer
+        self.o = oracle.OracleScene()
+        self.tex_map = {}
+
+    def add(self, chunk):
+        rid = self.r.add_texture(chunk)
+        oid = self.o.add_texture(chunk.get_raw(), *chunk.dims())
+        self.tex_map[oid] = rid
+        return oid
+
+    def set_instances(self, models_and_tex):
+        """models_and_tex: list of (mat4, oracle-side texture id)"""
+        if len(models_and_tex):
+            o_m = np.stack([glm.with_texture_id(m, t).reshape(16) for m, t in models_and_tex])
+            r_m = np.stack([glm.with_texture_id(m, self.tex_map.get(t, 60000 + t)).reshape(16) for m, t in models_and_tex])
+        else:
+            o_m = r_m = np.zeros((0, 16), dtype=np.float32)
+        self.o.set_instances(o_m)
+        self.r.update_instances_raw(r_m)
+
+    def check_primary(self, P, V, w, h, flags=0, what=""):
+        self.r.configure(width=w, height=h, mode=abi.MODE_PRIMARY, flags=flags, max_frames=0)
+        assert self.r.render_tick_raw(P, V)
+        assert (self.r.window_width, self.r.window_height) == (w, h)
+        got, color, depth = self.r.read_hits(), self.r.read_color(), self.r.read_depth()
+        want, wcolor, wdepth, iters = self.o.render_primary(P, V, w, h, flags=flags & 1, want_depth=True)
+        _assert_records_equal(got, want, what)
+        assert np.array_equal(color, wcolor), f"{what}: colour bytes differ"
+        assert np.array_equal(depth.view(np.uint32), wdepth.view(np.uint32)), f"{what}: depth bits differ"
+        st = self.r.stats()
+        assert st.iterations == iters, f"{what}: iteration counter {st.iterations} != {iters}"
+        assert st.rays == w * h
+        return got, st
+
+    def check_paths(self, P, V, w, h, spp, bounces=4, seed=0x5EED, flags=0, what=""):
+        self.r.configure(width=w, height=h, mode=abi.MODE_PATHS, flags=flags, spp=spp, bounces=bounces, seed=seed,
+                         sample_first=0, sample_stride=1, total_spp=spp, max_frames=0)
+        assert self.r.render_tick_raw(P, V)
+        got = self.r.read_accum()
+        color = self.r.read_color()
+        want, rays, iters = self.o.render_paths(P, V, w, h, spp=spp, bounces=bounces, seed=seed, flags=flags & 1)
+        if not np.array_equal(got, want):
+            bad = np.argwhere((got != want).any(axis=2))
+            y, x = bad[0]
+            raise AssertionError(f"{what}: radiance sums differ at {len(bad)} pixels; first (x={x}, y={y}): "
+                                 f"cuda={got[y, x]} oracle={want[y, x]}")
+        st = self.r.stats()
+        assert st.rays == rays and st.iterations == iters, f"{what}: counters {st.rays},{st.iterations} != {rays},{iters}"
+        import oracle_lib
+        assert np.array_equal(color, oracle_lib.resolve(want, spp)), f"{what}: resolved colour differs"
+        # the tolerance the north star states for radiance, on top of the exact check above
+        scale = 1.0 / (spp * 2.0**24)
+        diff = (got.astype(np.float64) - want.astype(np.float64)) * scale
+        assert np.sqrt((diff**2).mean()) <= 1e-4 and np.abs(diff).max() <= 1e-3
+        return got, st
+
+
+@pytest.fixture()
+def scene(renderer, oracle):
+    renderer.reset()  # fresh texture table / mask arena for every test
+    return Scene(renderer, oracle)
+
+
+# ---- BASELINE.json configs[0] and configs[1] ------------------------------------------------
+
+def test_config0_treasure_640x480_primary(scene, assets):
+    t = scene.add(assets["Treasure"])
+    scene.set_instances([(glm.identity(), t)])
+    P, V = scenes.camera(640, 480)
+    got, st = scene.check_primary(P, V, 640, 480, what="Treasure 640x480")
+    assert (got["hit_voxel"] != abi.VT_MISS).sum() > 10000
+    assert st.masks_in_smem == 1
+
+
+@pytest.mark.parametrize("flags", [0, abi.FLAG_VIEWPORT_H_IS_W])
+def test_config1_temple_1080p_primary(scene, assets, flags):
+    t = scene.add(assets["AncientTemple"])
+    scene.set_instances([(glm.identity(), t)])
+    P, V = scenes.camera(1920, 1080)
+    got, _ = scene.check_primary(P, V, 1920, 1080, flags=flags, what=f"Temple 1080p flags={flags}")
+    assert (got["hit_voxel"] != abi.VT_MISS).sum() > 20000
+
+
+def test_closeup_cameras(scene, assets):
+    t = scene.add(assets["AncientTemple"])
+    scene.set_instances([(glm.identity(), t)])
+    for eye in [(0.8, -0.45, 0.6), (-0.7, 0.2, 0.9), (0.0, -1.2, 0.05), (0.55, 0.55, 0.55)]:
+        P, V = scenes.camera(512, 288, eye=eye)
+        scene.check_primary(P, V, 512, 288, what=f"closeup {eye}")
+
+
+def test_global_mask_path_matches(scene, assets):
+    t = scene.add(assets["Treasure"])
+    scene.set_instances([(glm.identity(), t)])
+    P, V = scenes.camera(640, 480, eye=(0.9, -0.5, 0.7))
+    _, st = scene.check_primary(P, V, 640, 480, flags=abi.FLAG_FORCE_GLOBAL_MASKS, what="global masks")
+    assert st.masks_in_smem == 0
+
+
+# ---- edge cases -----------------------------------------------------------------------------
+
+def test_camera_inside_volume_draws_nothing(scene, assets):
+    t = scene.add(assets["Treasure"])
+    scene.set_instances([(glm.identity(), t)])
+    P, V = scenes.camera(320, 240, eye=(0.1, 0.2, -0.1), center=(1.0, 0.3, 0.2))
+    got, _ = scene.check_primary(P, V, 320, 240, what="camera inside")
+    assert (got["hit_voxel"] == abi.VT_MISS).all()  # back faces only -> culled (lib/pipeline.c:120-121)
+
+
+def test_axis_aligned_rays(scene, assets):
+    """Zero direction components: delta = inf, 0*inf = NaN inside the loop (SURVEY §7 hard parts)."""
+    t = scene.add(assets["AncientTemple"])
+    scene.set_instances([(glm.identity(), t)])
+    for eye, center in [((0.0, 0.0, 2.0), (0.0, 0.0, 0.0)), ((2.0, 0.0, 0.0), (0.0, 0.0, 0.0)),
+                        ((0.0, 0.0, -1.5), (0.0, 0.0, 0.0))]:
+        # odd sizes put a pixel centre exactly on the optical axis
+        P, V = scenes.camera(321, 241, eye=eye, center=center)
+        scene.check_primary(P, V, 321, 241, what=f"axis aligned {eye}")
+
+
+def test_empty_scene_and_bad_texture_id(scene, assets):
+    P, V = scenes.camera(160, 120)
+    scene.set_instances([])  # coerced to one stale instance (lib/memory.c:236,251)
+    got, _ = scene.check_primary(P, V, 160, 120, what="empty scene")
+    assert (got["hit_voxel"] == abi.VT_MISS).all()
+    scene.set_instances([(glm.identity(), 40000)])  # texture id out of range
+    scene.check_primary(P, V, 160, 120, what="bad texture id")
+
+
+def test_ragged_and_noncubic_volumes(scene):
+    """Sizes where floor(fl(v/s)*s) != v (texel remap) and W != H != D (reference quirk: dir not scaled)."""
+    rng = np.random.default_rng(7)
+    for (w, h, d) in [(22, 23, 29), (1, 1, 1), (3, 50, 7), (41, 41, 41), (64, 16, 33)]:
+        t = scene.add(RawVolume(make_volume(rng, w, h, d, fill=0.15), w, h, d))
+        scene.set_instances([(glm.identity(), t)])
+        P, V = scenes.camera(400, 300, eye=(0.9, -0.6, 0.8))
+        scene.check_primary(P, V, 400, 300, what=f"volume {w}x{h}x{d}")
+
+
+def test_transparent_voxels_blend(scene):
+    rng = np.random.default_rng(11)
+    w = h = d = 24
+    t = scene.add(RawVolume(make_volume(rng, w, h, d, fill=0.2, alpha_choices=(255, 128, 1, 77)), w, h, d))
+    models = [(glm.translate(glm.identity(), (0.0, 0.0, -0.8 * k)), t) for k in range(3)]
+    scene.set_instances(models)
+    P, V = scenes.camera(480, 360, eye=(0.3, -0.4, 1.6))
+    scene.check_primary(P, V, 480, 360, what="alpha blending across instances")
+
+
+def test_multi_instance_grid(scene, assets):
+    """The 11x11 entity grid of src/world.rs:143-161 (rank 1 of SURVEY §8f)."""
+    a = scene.add(assets["Treasure"])
+    b = scene.add(assets["AncientTemple"])
+    grid = scenes.entity_grid(a, b)
+    models = []
+    for m in grid:
+        m = m.reshape(4, 4).copy()
+        tid = int(m.reshape(16).view(np.uint32)[15])
+        m[3][3] = 1.0
+        models.append((m, tid))
+    scene.set_instances(models)
+    P = glm.perspective(glm.REFERENCE_FOV, 640 / 360, glm.REFERENCE_NEAR, glm.REFERENCE_FAR)
+    V = glm.look_at((0.0, -2.0, 0.0), (3.0, -5.0, 2.0), (0.0, 1.0, 0.0))
+    got, _ = scene.check_primary(P, V, 640, 360, what="entity grid")
+    assert len(np.unique(got["instance"])) > 10
+
+
+def test_rotated_scaled_instances(scene, assets):
+    t = scene.add(assets["Treasure"])
+    m1 = glm.scale(glm.rotate(glm.translate(glm.identity(), (0.4, 0.1, -0.3)), 0.7, (0.3, 1.0, 0.2)), (1.3, 0.7, 1.9))
+    m2 = glm.rotate(glm.translate(glm.identity(), (-0.9, 0.0, 0.5)), -1.1, (1.0, 0.2, 0.0))
+    scene.set_instances([(m1, t), (m2, t)])
+    P, V = scenes.camera(512, 384, eye=(1.8, -1.1, 1.5))
+    scene.check_primary(P, V, 512, 384, what="rotated/scaled")
+
+
+# ---- path-tracing extension -----------------------------------------------------------------
+
+def test_paths_single_instance_exact(scene, assets):
+    t = scene.add(assets["AncientTemple"])
+    scene.set_instances([(glm.identity(), t)])
+    P, V = scenes.camera(320, 180, eye=(0.8, -0.45, 0.6))
+    got, st = scene.check_paths(P, V, 320, 180, spp=4, what="paths temple")
+    assert st.rays > 320 * 180 * 4
+
+
+def test_paths_multi_instance_exact(scene, assets):
+    a = scene.add(assets["Treasure"])
+    b = scene.add(assets["AncientTemple"])
+    models = [(glm.translate(glm.identity(), (1.2 * i - 1.2, 0.0, 1.1 * j - 0.5)), a if (i + j) % 2 else b)
+              for i in range(3) for j in range(2)]
+    scene.set_instances(models)
+    P, V = scenes.camera(240, 160, eye=(2.2, -1.4, 2.4))
+    scene.check_paths(P, V, 240, 160, spp=3, bounces=3, what="paths multi")
+
+
+def test_paths_sample_sharding_is_exact(renderer, scene, assets):
+    """spp split over ranks: integer accumulation makes 1-rank == sum of N ranks."""
+    t = scene.add(assets["AncientTemple"])
+    scene.set_instances([(glm.identity(), t)])
+    w, h, spp, n = 200, 120, 8, 4
+    P, V = scenes.camera(w, h, eye=(0.8, -0.45, 0.6))
+    whole, _ = scene.check_paths(P, V, w, h, spp=spp, what="whole")
+    total = np.zeros_like(whole)
+    for rank in range(n):
+        renderer.configure(width=w, height=h, mode=abi.MODE_PATHS, spp=spp // n, bounces=4, seed=0x5EED,
+                           sample_first=rank, sample_stride=n, total_spp=spp)
+        renderer.clear_accum()
+        renderer.render_async(P, V)
+        total += renderer.read_accum()
+    assert np.array_equal(total, whole)
+
+
+def test_config2_full_size_properties(renderer, scene, assets):
+    """configs[2] at full size (1080p, 64 spp, 4 bounces): too big for the oracle, so check the
+    size-independent properties: determinism, ray-count bounds, energy bound, sky pixels exact."""
+    t = scene.add(assets["AncientTemple"])
+    scene.set_instances([(glm.identity(), t)])
+    w, h, spp = 1920, 1080, 64
+    P, V = scenes.camera(w, h)
+    renderer.configure(width=w, height=h, mode=abi.MODE_PATHS, flags=0, spp=spp, bounces=4, seed=0x5EED,
+                       sample_first=0, sample_stride=1, total_spp=spp)
+    assert renderer.render_tick_raw(P, V)
+    a1, st1 = renderer.read_accum(), renderer.stats()
+    assert renderer.render_tick_raw(P, V)
+    a2, st2 = renderer.read_accum(), renderer.stats()
+    assert np.array_equal(a1, a2) and st1.rays == st2.rays and st1.iterations == st2.iterations
+    n = w * h * spp
+    assert n <= st1.rays <= 5 * n
+    sky = np.array([int(np.float32(c) / np.float32(100.0) * np.float32(16777216.0)) for c in (53.0, 81.0, 92.0)], dtype=np.uint64)
+    assert (a1 <= sky * np.uint64(spp)).all()           # albedo <= 1: nothing brighter than the sky
+    assert np.array_equal(a1[0, 0], sky * np.uint64(spp))  # a corner pixel sees only sky

@@ -1,0 +1,855 @@
+// kernels.cu — sm_100a kernels for vtrace's voxel ray-traversal path.
+//
+// What runs here replaces the GPU programs of the reference:
+//   instance_setup_kernel  <- shaders/trace.vert:32-47 (per-instance part) + the uniform
+//                             inverse() calls trace.frag repeats per fragment (:48,49,59,65)
+//   trace_primary_kernel   <- rasteriser + shaders/trace.frag:41-90 + depth/blend state
+//                             (lib/pipeline.c:114-152, lib/command.c:56-102)
+//   trace_paths_kernel     <- extension: jittered paths with diffuse bounces
+//   build_mask_kernel      <- takes the slot of lib/raytrace.c's acceleration-structure build
+//
+// Arithmetic contract: compiled with --fmad=false, IEEE div/sqrt, no fast-math.  Every
+// float op that can influence a traversal decision is a separately rounded binary32 op in
+// the same order as oracle/vtrace_oracle.c, so hit voxel / face / steps are bit-exact.
+//
+// The DDA keeps the reference's per-voxel float stepping (side += delta is a running sum,
+// trace.frag:84 — closed-form skipping would change `steps`), but makes each step cheap:
+// one bit test against a padded "stop mask" (filled OR outside), no coordinate compares,
+// no texel fetch until the hit.  For scenes whose masks fit, the whole mask arena is
+// staged into shared memory with one TMA bulk copy per CTA.
+#include "kernels.h"
+
+#include <cstdint>
+
+namespace vt {
+
+#define VT_FLAG_VIEWPORT_H_IS_W 1u
+#define VT_FLAG_NO_HIT_RECORDS 2u
+#define VT_MISS 0xFFFFFFFFu
+
+static constexpr int kBlockThreads = 256; // 8 warps; each warp owns an 8x4 pixel tile
+static constexpr int kTileW = 32, kTileH = 8; // CTA tile = 4x2 warps
+
+// -------------------------------------------------------------------------------------------
+// dynamic shared memory layout: [0,16) mbarrier | [16, 16+1024) sRGB decode LUT | masks
+static constexpr uint32_t kSmemLutOff = 16;
+static constexpr uint32_t kSmemMaskOff = 16 + 1024;
+
+size_t trace_smem_bytes(uint32_t arena_words, bool masks_in_smem) {
+    return kSmemMaskOff + (masks_in_smem ? size_t(arena_words) * 4 : 0);
+}
+
+// -------------------------------------------------------------------------------------------
+// small helpers
+
+__device__ __forceinline__ float vt_fmin(float a, float b) { // IEEE minNum, as the oracle fixes it
+    if (a != a) return b;
+    if (b != b) return a;
+    return a < b ? a : b;
+}
+
+__device__ __forceinline__ int32_t texel_of(int32_t v, float size, int32_t isize) {
+    // texture(tex, voxel / size), NEAREST, clamp-to-edge (trace.frag:76, lib/descriptor.c:100-115)
+    float u = (float)v / size;
+    int32_t i = __float2int_rz(floorf(u * size));
+    i = i < 0 ? 0 : i;
+    i = i > isize - 1 ? isize - 1 : i;
+    return i;
+}
+
+extern __shared__ __align__(128) unsigned char vt_smem[];
+
+// mbarrier + TMA bulk copy (cp.async.bulk, SASS UBLKCP) -------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// -------------------------------------------------------------------------------------------
+// build_mask_kernel: RGBA8 texels -> padded stop mask.  One thread per 32-bit mask word.
+
+__global__ void build_mask_kernel(const uint8_t* __restrict__ rgba, uint32_t W, uint32_t H, uint32_t D, uint32_t xb,
+                                  uint32_t yb, uint32_t* __restrict__ mask, uint32_t mask_words) {
+    uint32_t word = blockIdx.x * blockDim.x + threadIdx.x;
+    if (word >= mask_words) return;
+    const uint32_t bit0 = word << 5;
+    const uint32_t yq = (bit0 >> xb) & ((1u << yb) - 1u);
+    const uint32_t zq = bit0 >> (xb + yb);
+    const int32_t y = (int32_t)yq - 1, z = (int32_t)zq - 1;
+    uint32_t bits = 0;
+    const bool row_inside = y >= 0 && y < (int32_t)H && z >= 0 && z < (int32_t)D;
+    int32_t ty = 0, tz = 0;
+    if (row_inside) {
+        ty = texel_of(y, (float)(int32_t)H, (int32_t)H);
+        tz = texel_of(z, (float)(int32_t)D, (int32_t)D);
+    }
+    for (uint32_t b = 0; b < 32; ++b) {
+        const uint32_t xq = (bit0 & ((1u << xb) - 1u)) + b;
+        const int32_t x = (int32_t)xq - 1;
+        bool stop = true; // border and unused padding both stop the walk
+        if (row_inside && x >= 0 && x < (int32_t)W) {
+            const int32_t tx = texel_of(x, (float)(int32_t)W, (int32_t)W);
+            const size_t t = (size_t)tx + (size_t)W * ((size_t)ty + (size_t)H * (size_t)tz);
+            stop = rgba[4 * t + 3] > 0; // texSample.w > 0.0, trace.frag:78
+        }
+        bits |= (stop ? 1u : 0u) << b;
+    }
+    mask[word] = bits;
+}
+
+cudaError_t launch_build_mask(const uint8_t* rgba, uint32_t w, uint32_t h, uint32_t d, uint32_t xb, uint32_t yb,
+                              uint32_t* mask, uint32_t mask_words, cudaStream_t stream) {
+    const int threads = 128;
+    build_mask_kernel<<<(mask_words + threads - 1) / threads, threads, 0, stream>>>(rgba, w, h, d, xb, yb, mask, mask_words);
+    return cudaGetLastError();
+}
+
+// -------------------------------------------------------------------------------------------
+// instance_setup_kernel: one thread per instance.
+
+// GLSL inverse(mat4) — same cofactor expansion, same operation order as the oracle.
+__host__ __device__ void mat4_inverse(const float* m, float* r) {
+#define A(r_, c_) m[(c_)*4 + (r_)]
+#define B(r_, c_) r[(c_)*4 + (r_)]
+    float s0 = A(0, 0) * A(1, 1) - A(1, 0) * A(0, 1);
+    float s1 = A(0, 0) * A(1, 2) - A(1, 0) * A(0, 2);
+    float s2 = A(0, 0) * A(1, 3) - A(1, 0) * A(0, 3);
+    float s3 = A(0, 1) * A(1, 2) - A(1, 1) * A(0, 2);
+    float s4 = A(0, 1) * A(1, 3) - A(1, 1) * A(0, 3);
+    float s5 = A(0, 2) * A(1, 3) - A(1, 2) * A(0, 3);
+    float c5 = A(2, 2) * A(3, 3) - A(3, 2) * A(2, 3);
+    float c4 = A(2, 1) * A(3, 3) - A(3, 1) * A(2, 3);
+    float c3 = A(2, 1) * A(3, 2) - A(3, 1) * A(2, 2);
+    float c2 = A(2, 0) * A(3, 3) - A(3, 0) * A(2, 3);
+    float c1 = A(2, 0) * A(3, 2) - A(3, 0) * A(2, 2);
+    float c0 = A(2, 0) * A(3, 1) - A(3, 0) * A(2, 1);
+    float det = ((((s0 * c5 - s1 * c4) + s2 * c3) + s3 * c2) - s4 * c1) + s5 * c0;
+    float id = 1.0f / det;
+    B(0, 0) = ((A(1, 1) * c5 - A(1, 2) * c4) + A(1, 3) * c3) * id;
+    B(0, 1) = ((-A(0, 1) * c5 + A(0, 2) * c4) - A(0, 3) * c3) * id;
+    B(0, 2) = ((A(3, 1) * s5 - A(3, 2) * s4) + A(3, 3) * s3) * id;
+    B(0, 3) = ((-A(2, 1) * s5 + A(2, 2) * s4) - A(2, 3) * s3) * id;
+    B(1, 0) = ((-A(1, 0) * c5 + A(1, 2) * c2) - A(1, 3) * c1) * id;
+    B(1, 1) = ((A(0, 0) * c5 - A(0, 2) * c2) + A(0, 3) * c1) * id;
+    B(1, 2) = ((-A(3, 0) * s5 + A(3, 2) * s2) - A(3, 3) * s1) * id;
+    B(1, 3) = ((A(2, 0) * s5 - A(2, 2) * s2) + A(2, 3) * s1) * id;
+    B(2, 0) = ((A(1, 0) * c4 - A(1, 1) * c2) + A(1, 3) * c0) * id;
+    B(2, 1) = ((-A(0, 0) * c4 + A(0, 1) * c2) - A(0, 3) * c0) * id;
+    B(2, 2) = ((A(3, 0) * s4 - A(3, 1) * s2) + A(3, 3) * s0) * id;
+    B(2, 3) = ((-A(2, 0) * s4 + A(2, 1) * s2) - A(2, 3) * s0) * id;
+    B(3, 0) = ((-A(1, 0) * c3 + A(1, 1) * c1) - A(1, 2) * c0) * id;
+    B(3, 1) = ((A(0, 0) * c3 - A(0, 1) * c1) + A(0, 2) * c0) * id;
+    B(3, 2) = ((-A(3, 0) * s3 + A(3, 1) * s1) - A(3, 2) * s0) * id;
+    B(3, 3) = ((A(2, 0) * s3 - A(2, 1) * s1) + A(2, 2) * s0) * id;
+#undef A
+#undef B
+}
+
+__global__ void instance_setup_kernel(const float* __restrict__ instances, uint32_t n,
+                                      const VolumeDesc* __restrict__ volumes, const FrameParams fp,
+                                      InstUniforms* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float M[16], Mi[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) M[k] = instances[(size_t)i * 16 + k];
+    InstUniforms I;
+    I.tex = __float_as_uint(M[15]); // trace.vert:38 floatBitsToInt(model[3][3])
+    M[15] = 1.0f;                   // trace.vert:39-40
+    I.valid = I.tex < fp.n_volumes ? 1u : 0u;
+    I.pad[0] = I.pad[1] = I.pad[2] = 0;
+    I.pad2 = 0;
+    if (!I.valid) {
+        I.w = I.h = I.d = I.xb = I.yb = I.mask_off = 0;
+        I.rgba = nullptr;
+        for (int k = 0; k < 16; ++k) I.MVP[k] = 0.0f;
+        for (int k = 0; k < 12; ++k) I.Mi[k] = I.M[k] = I.dirm[k] = 0.0f;
+        I.eye_m[0] = I.eye_m[1] = I.eye_m[2] = 0.0f;
+        out[i] = I;
+        return;
+    }
+    const VolumeDesc v = volumes[I.tex];
+    I.w = v.w; I.h = v.h; I.d = v.d; I.xb = v.xb; I.yb = v.yb; I.mask_off = v.mask_off; I.rgba = v.rgba;
+    mat4_inverse(M, Mi); // trace.frag:65
+    // MVP = (P V) * M
+    for (int j = 0; j < 4; ++j)
+        for (int r = 0; r < 4; ++r)
+            I.MVP[j * 4 + r] = ((fp.PV[0 * 4 + r] * M[j * 4 + 0] + fp.PV[1 * 4 + r] * M[j * 4 + 1]) + fp.PV[2 * 4 + r] * M[j * 4 + 2]) +
+                               fp.PV[3 * 4 + r] * M[j * 4 + 3];
+    for (int c = 0; c < 4; ++c)
+        for (int r = 0; r < 3; ++r) {
+            I.Mi[c * 3 + r] = Mi[c * 4 + r];
+            I.M[c * 3 + r] = M[c * 4 + r];
+            I.dirm[c * 3 + r] = (Mi[0 * 4 + r] * fp.RD[c * 4 + 0] + Mi[1 * 4 + r] * fp.RD[c * 4 + 1]) + Mi[2 * 4 + r] * fp.RD[c * 4 + 2];
+        }
+    for (int r = 0; r < 3; ++r)
+        I.eye_m[r] = ((Mi[0 * 4 + r] * fp.eye[0] + Mi[1 * 4 + r] * fp.eye[1]) + Mi[2 * 4 + r] * fp.eye[2]) + Mi[3 * 4 + r] * 1.0f;
+    out[i] = I;
+}
+
+cudaError_t launch_instance_setup(const float* instances, uint32_t n, const VolumeDesc* volumes, FrameParams fp,
+                                  InstUniforms* out, cudaStream_t stream) {
+    const int threads = 64;
+    instance_setup_kernel<<<(n + threads - 1) / threads, threads, 0, stream>>>(instances, n, volumes, fp, out);
+    return cudaGetLastError();
+}
+
+// -------------------------------------------------------------------------------------------
+// rasteriser restatement: which point of the proxy cube's front faces covers the sample
+
+__device__ __forceinline__ bool slab_unit_cube(const float o[3], const float d[3], float& tn_out, int& axis_out) {
+    float tn = -INFINITY, tf = INFINITY;
+    int axis = -1;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (d[k] == 0.0f) {
+            if (o[k] < -0.5f || o[k] > 0.5f) return false;
+            continue;
+        }
+        const float inv = 1.0f / d[k];
+        const float t1 = (-0.5f - o[k]) * inv;
+        const float t2 = (0.5f - o[k]) * inv;
+        const float lo = t1 < t2 ? t1 : t2;
+        const float hi = t1 < t2 ? t2 : t1;
+        if (lo > tn) { tn = lo; axis = k; }
+        if (hi < tf) tf = hi;
+    }
+    if (axis < 0) return false;
+    if (!(tn <= tf)) return false;
+    if (!(tn > 0.0f)) return false; // inside / behind: only back faces -> culled (lib/pipeline.c:120-121)
+    tn_out = tn;
+    axis_out = axis;
+    return true;
+}
+
+__device__ __forceinline__ void entry_point(const float o[3], const float d[3], float tn, int axis, float mp[3]) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float p = o[k] + tn * d[k];
+        p = p < -0.5f ? -0.5f : p;
+        p = p > 0.5f ? 0.5f : p;
+        mp[k] = (k == axis) ? (d[k] > 0.0f ? -0.5f : 0.5f) : p;
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// the DDA (trace.frag:63-89)
+
+struct Dda {
+    bool hit;
+    int32_t v[3];       // model_ray_voxel at exit
+    uint32_t steps;
+    uint32_t last_mask; // axes advanced by the last executed iteration
+    int32_t step[3];
+    float side[3], delta[3], dir[3], pos[3], len;
+};
+
+// Volume view used by the march
+struct Vol {
+    uint32_t w, h, d, xb, yb;
+    uint32_t mask_off;          // word offset of this volume's mask inside the arena
+    const uint32_t* arena;      // global arena (used when the masks are not staged)
+};
+
+template <bool kSmem>
+__device__ __forceinline__ uint32_t mask_word(const Vol& vol, uint32_t word) {
+    if (kSmem) // indexing the __shared__ symbol directly keeps this an LDS, not a generic load
+        return reinterpret_cast<const uint32_t*>(vt_smem + kSmemMaskOff)[vol.mask_off + word];
+    else
+        return __ldg(vol.arena + vol.mask_off + word);
+}
+
+template <bool kSmem>
+__device__ __forceinline__ void dda_march(const Vol& vol, const float pos[3], const float dir[3], bool has_start,
+                                          const int32_t sv[3], Dda& r) {
+    const int32_t isz[3] = {(int32_t)vol.w, (int32_t)vol.h, (int32_t)vol.d};
+    const float size[3] = {(float)isz[0], (float)isz[1], (float)isz[2]};
+    float sgn[3];
+    r.len = sqrtf((dir[0] * dir[0] + dir[1] * dir[1]) + dir[2] * dir[2]); // length(), :70
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        r.pos[k] = pos[k];
+        r.dir[k] = dir[k];
+        r.v[k] = has_start ? sv[k] : __float2int_rz(floorf(vt_fmin(pos[k], size[k] - 1.0f))); // :68
+        sgn[k] = dir[k] > 0.0f ? 1.0f : (dir[k] < 0.0f ? -1.0f : 0.0f);                       // :69
+        r.step[k] = (int32_t)sgn[k];
+        r.delta[k] = fabsf(r.len / dir[k]);                                                   // :70
+        r.side[k] = ((sgn[k] * ((float)r.v[k] - pos[k]) + sgn[k] * 0.5f) + 0.5f) * r.delta[k]; // :71
+    }
+    r.steps = 0;
+    r.last_mask = 0;
+    r.hit = false;
+    const uint32_t xb = vol.xb, zb = vol.xb + vol.yb;
+    // the start voxel must lie inside the padded mask (true for every caller: primary rays start
+    // inside the volume, bounce rays start at most one voxel outside it)
+    const bool in_pad = r.v[0] >= -1 && r.v[0] <= isz[0] && r.v[1] >= -1 && r.v[1] <= isz[1] && r.v[2] >= -1 && r.v[2] <= isz[2];
+    if (!in_pad) return;
+    uint32_t idx = (uint32_t)(r.v[0] + 1) | ((uint32_t)(r.v[1] + 1) << xb) | ((uint32_t)(r.v[2] + 1) << zb);
+    const bool finite = isfinite(r.delta[0]) && isfinite(r.delta[1]) && isfinite(r.delta[2]) && isfinite(r.side[0]) &&
+                        isfinite(r.side[1]) && isfinite(r.side[2]);
+    if (finite) {
+        // Fast path.  No NaN/inf anywhere, so `side <= min(other two)` is two ordered compares,
+        // `vec3(mask) * delta` is a predicated add, every iteration advances >= 1 voxel (so the
+        // steps < W+H+D bound of :74-75 can never bind), and leaving the volume lands on a set
+        // border bit of the stop mask — no coordinate compares inside the loop.
+        float sx = r.side[0], sy = r.side[1], sz = r.side[2];
+        const float dx = r.delta[0], dy = r.delta[1], dz = r.delta[2];
+        const uint32_t ix = (uint32_t)r.step[0], iy = (uint32_t)r.step[1] << xb, iz = (uint32_t)r.step[2] << zb;
+        uint32_t prev = idx, steps = 0;
+        for (;;) {
+            const uint32_t wv = mask_word<kSmem>(vol, idx >> 5);
+            if ((wv >> (idx & 31u)) & 1u) break;
+            const bool mx = (sx <= sy) && (sx <= sz); // :83
+            const bool my = (sy <= sz) && (sy <= sx);
+            const bool mz = (sz <= sx) && (sz <= sy);
+            prev = idx;
+            if (mx) { sx += dx; idx += ix; } // :84-85
+            if (my) { sy += dy; idx += iy; }
+            if (mz) { sz += dz; idx += iz; }
+            ++steps; // :86
+        }
+        r.side[0] = sx; r.side[1] = sy; r.side[2] = sz;
+        r.steps = steps;
+        r.v[0] = (int32_t)(idx & ((1u << xb) - 1u)) - 1;
+        r.v[1] = (int32_t)((idx >> xb) & ((1u << vol.yb) - 1u)) - 1;
+        r.v[2] = (int32_t)(idx >> zb) - 1;
+        r.hit = r.v[0] >= 0 && r.v[0] < isz[0] && r.v[1] >= 0 && r.v[1] < isz[1] && r.v[2] >= 0 && r.v[2] < isz[2];
+        if (steps) {
+            // axes advanced by the last iteration, recovered from the index delta
+            const int32_t diff = (int32_t)(idx - prev);
+            const int32_t qz = (diff + (1 << (zb - 1))) >> zb;
+            const int32_t rem = diff - (qz << zb);
+            const int32_t qy = (rem + (1 << (xb - 1))) >> xb;
+            const int32_t qx = rem - (qy << xb);
+            r.last_mask = (qx != 0 ? 1u : 0u) | (qy != 0 ? 2u : 0u) | (qz != 0 ? 4u : 0u);
+        }
+        return;
+    }
+    // Slow path: a direction component is exactly 0 (delta = inf, and 0 * inf = NaN from the first
+    // non-advancing iteration on) or something is NaN.  Literal transcription, including the
+    // steps < max_steps bound which CAN bind here.
+    const uint32_t max_steps = vol.w + vol.h + vol.d; // :74
+    while (r.steps < max_steps && r.v[0] >= 0 && r.v[1] >= 0 && r.v[2] >= 0 && r.v[0] < isz[0] && r.v[1] < isz[1] &&
+           r.v[2] < isz[2]) { // :75
+        idx = (uint32_t)(r.v[0] + 1) | ((uint32_t)(r.v[1] + 1) << xb) | ((uint32_t)(r.v[2] + 1) << zb);
+        const uint32_t wv = mask_word<kSmem>(vol, idx >> 5);
+        if ((wv >> (idx & 31u)) & 1u) { r.hit = true; return; } // :78-80
+        const bool m0 = r.side[0] <= vt_fmin(r.side[1], r.side[2]); // :83
+        const bool m1 = r.side[1] <= vt_fmin(r.side[2], r.side[0]);
+        const bool m2 = r.side[2] <= vt_fmin(r.side[0], r.side[1]);
+        r.side[0] += (m0 ? 1.0f : 0.0f) * r.delta[0]; // :84
+        r.side[1] += (m1 ? 1.0f : 0.0f) * r.delta[1];
+        r.side[2] += (m2 ? 1.0f : 0.0f) * r.delta[2];
+        r.v[0] += m0 ? r.step[0] : 0; // :85
+        r.v[1] += m1 ? r.step[1] : 0;
+        r.v[2] += m2 ? r.step[2] : 0;
+        r.last_mask = (m0 ? 1u : 0u) | (m1 ? 2u : 0u) | (m2 ? 4u : 0u);
+        ++r.steps; // :86
+    }
+}
+
+// texel colour at the hit voxel (the only volume-texel read of a ray)
+__device__ __forceinline__ uchar4 fetch_texel(const uint8_t* rgba, uint32_t W, uint32_t H, uint32_t D, const int32_t v[3]) {
+    const int32_t tx = texel_of(v[0], (float)(int32_t)W, (int32_t)W);
+    const int32_t ty = texel_of(v[1], (float)(int32_t)H, (int32_t)H);
+    const int32_t tz = texel_of(v[2], (float)(int32_t)D, (int32_t)D);
+    const size_t t = (size_t)tx + (size_t)W * ((size_t)ty + (size_t)H * (size_t)tz);
+    return __ldg(reinterpret_cast<const uchar4*>(rgba) + t);
+}
+
+// -------------------------------------------------------------------------------------------
+// one fragment = rasteriser restatement + trace.frag prologue + DDA
+
+struct Fragment {
+    bool covered;
+    float depth;
+    int entry_axis;
+    Dda dda;
+};
+
+template <bool kSmem>
+__device__ __forceinline__ void run_fragment(const FrameParams& fp, const InstUniforms* __restrict__ Ip, const uint32_t* mask_base,
+                                             float fx, float fy, Fragment& f) {
+    f.covered = false;
+    f.dda.hit = false;
+    f.dda.steps = 0;
+    if (!Ip->valid) return;
+    // SURVEY.md §A.2 step 1a
+    const float x_ndc = (fx * 2.0f) / fp.vw - 1.0f;
+    const float y_ndc = (fy * 2.0f) / fp.vh - 1.0f;
+    float d[3], o[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        d[k] = (Ip->dirm[0 * 3 + k] * x_ndc + Ip->dirm[1 * 3 + k] * y_ndc) + Ip->dirm[3 * 3 + k];
+        o[k] = Ip->eye_m[k];
+    }
+    float tn;
+    int axis;
+    if (!slab_unit_cube(o, d, tn, axis)) return;
+    float mp[3];
+    entry_point(o, d, tn, axis, mp);
+    // trace.vert:43-45 at the covered point
+    float sp[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        sp[i] = ((Ip->MVP[0 * 4 + i] * mp[0] + Ip->MVP[1 * 4 + i] * mp[1]) + Ip->MVP[2 * 4 + i] * mp[2]) + Ip->MVP[3 * 4 + i];
+    if (!(sp[3] > 0.0f && sp[2] >= 0.0f && sp[2] <= sp[3])) return; // Vulkan clip volume
+    f.covered = true;
+    f.entry_axis = axis;
+    f.depth = sp[2] / sp[3]; // trace.frag:46
+    // trace.frag:59 ray_dir = normalize((RD * sp).xyz)
+    float rr[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        rr[k] = ((fp.RD[0 * 4 + k] * sp[0] + fp.RD[1 * 4 + k] * sp[1]) + fp.RD[2 * 4 + k] * sp[2]) + fp.RD[3 * 4 + k] * sp[3];
+    const float len = sqrtf((rr[0] * rr[0] + rr[1] * rr[1]) + rr[2] * rr[2]);
+    const float rd[3] = {rr[0] / len, rr[1] / len, rr[2] / len};
+    // trace.frag:65 model_ray_dir = (inverse(M) * vec4(ray_dir, 0)).xyz ; :66 model_ray_pos
+    float dir[3], pos[3];
+    const float size[3] = {(float)(int32_t)Ip->w, (float)(int32_t)Ip->h, (float)(int32_t)Ip->d};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        dir[k] = ((Ip->Mi[0 * 3 + k] * rd[0] + Ip->Mi[1 * 3 + k] * rd[1]) + Ip->Mi[2 * 3 + k] * rd[2]) + Ip->Mi[3 * 3 + k] * 0.0f;
+        pos[k] = (mp[k] + 0.5f) * size[k];
+    }
+    Vol vol{Ip->w, Ip->h, Ip->d, Ip->xb, Ip->yb, Ip->mask_off, mask_base};
+    const int32_t none[3] = {0, 0, 0};
+    dda_march<kSmem>(vol, pos, dir, false, none, f.dda);
+}
+
+__device__ __forceinline__ uint32_t face_bits(const Dda& r, int entry_axis) {
+    const uint32_t mask = r.steps ? r.last_mask : (1u << entry_axis);
+    const uint32_t neg = (r.step[0] < 0 ? 1u : 0u) | (r.step[1] < 0 ? 2u : 0u) | (r.step[2] < 0 ? 4u : 0u);
+    return mask | (neg << 3);
+}
+
+__device__ __forceinline__ uint32_t srgb_encode(const float* __restrict__ thr, float x) {
+    uint32_t k = 0;
+#pragma unroll
+    for (uint32_t bit = 128; bit; bit >>= 1)
+        if (x >= __ldg(thr + (k | bit))) k |= bit;
+    return k;
+}
+
+// CTA prologue shared by both trace kernels: stage the decode LUT and (optionally) the whole
+// mask arena into shared memory.  Returns the base pointer masks are addressed from.
+template <bool kSmem>
+__device__ __forceinline__ void stage_tables(const uint32_t* mask_arena, uint32_t arena_words, const float* __restrict__ decode) {
+    uint64_t* bar = reinterpret_cast<uint64_t*>(vt_smem);
+    float* lut = reinterpret_cast<float*>(vt_smem + kSmemLutOff);
+    uint32_t* smask = reinterpret_cast<uint32_t*>(vt_smem + kSmemMaskOff);
+    if (kSmem) {
+        if (threadIdx.x == 0) {
+            mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t bytes = arena_words * 4u;
+            mbar_expect_tx(bar, bytes);
+            // one TMA bulk copy per <= 64 KiB chunk
+            for (uint32_t off = 0; off < bytes; off += 65536u) {
+                const uint32_t n = bytes - off < 65536u ? bytes - off : 65536u;
+                bulk_g2s(reinterpret_cast<unsigned char*>(smask) + off, reinterpret_cast<const unsigned char*>(mask_arena) + off, n, bar);
+            }
+        }
+    }
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = __ldg(decode + i);
+    if (kSmem) mbar_wait(bar, 0);
+    __syncthreads();
+}
+
+// -------------------------------------------------------------------------------------------
+// trace_primary_kernel: persistent CTAs over 32x8 pixel tiles; one thread per pixel,
+// lanes of a warp form an 8x4 block so neighbouring rays stay coherent.
+
+template <bool kSmem>
+__global__ void __launch_bounds__(kBlockThreads) trace_primary_kernel(const __grid_constant__ FrameParams fp,
+                                                                      const InstUniforms* __restrict__ inst,
+                                                                      const uint32_t* __restrict__ mask_arena,
+                                                                      uint32_t arena_words, SrgbTables lut, FrameBuffers fb) {
+    stage_tables<kSmem>(mask_arena, arena_words, lut.decode);
+    const uint32_t* mask_base = mask_arena;
+    const float* dec = reinterpret_cast<const float*>(vt_smem + kSmemLutOff);
+
+    const int tiles_x = (fp.width + kTileW - 1) / kTileW;
+    const int tiles_y = (fp.height + kTileH - 1) / kTileH;
+    const int n_tiles = tiles_x * tiles_y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lx = (warp & 3) * 8 + (lane & 7);
+    const int ly = (warp >> 2) * 4 + (lane >> 3);
+
+    // clear values, lib/command.c:56-61, as stored by the sRGB target
+    const uint32_t clear_r = srgb_encode(lut.threshold, 53.0f / 100.0f);
+    const uint32_t clear_g = srgb_encode(lut.threshold, 81.0f / 100.0f);
+    const uint32_t clear_b = srgb_encode(lut.threshold, 92.0f / 100.0f);
+
+    unsigned long long iter_sum = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int px = (tile % tiles_x) * kTileW + lx;
+        const int py = (tile / tiles_x) * kTileH + ly;
+        if (px >= fp.width || py >= fp.height) continue;
+        const float fx = (float)px + 0.5f, fy = (float)py + 0.5f;
+        uint32_t dst[4] = {clear_r, clear_g, clear_b, 255u};
+        float zbuf = 1.0f; // lib/command.c:60
+        HitRecord rec{VT_MISS, 0u, VT_MISS, 0u};
+        for (uint32_t i = 0; i < fp.n_inst; ++i) { // draw order = instance order, lib/command.c:102
+            Fragment f;
+            run_fragment<kSmem>(fp, inst + i, mask_base, fx, fy, f);
+            if (!f.covered) continue;
+            rec.iters += f.dda.steps;
+            if (!f.dda.hit) continue;        // discard, trace.frag:89
+            if (!(f.depth < zbuf)) continue; // VK_COMPARE_OP_LESS, lib/pipeline.c:148-150
+            zbuf = f.depth;
+            const InstUniforms* Ip = inst + i;
+            const uchar4 s = fetch_texel(Ip->rgba, Ip->w, Ip->h, Ip->d, f.dda.v);
+            if (s.w == 255) {
+                // a == 1: src*1 + dst*0 == src exactly and encode(decode(c)) == c by construction
+                dst[0] = s.x; dst[1] = s.y; dst[2] = s.z; dst[3] = 255u;
+            } else {
+                // blend, lib/pipeline.c:129-137
+                const float a = (float)s.w / 255.0f;
+                const uint32_t sc[3] = {s.x, s.y, s.z};
+#pragma unroll
+                for (int c = 0; c < 3; ++c) dst[c] = srgb_encode(lut.threshold, dec[sc[c]] * a + dec[dst[c]] * (1.0f - a));
+                dst[3] = (uint32_t)__float2int_rz(floorf(a * 255.0f + 0.5f));
+            }
+            rec.hit_voxel = (uint32_t)f.dda.v[0] + Ip->w * ((uint32_t)f.dda.v[1] + Ip->h * (uint32_t)f.dda.v[2]);
+            rec.packed = (f.dda.steps & 0xFFFFu) | (face_bits(f.dda, f.entry_axis) << 16);
+            rec.instance = i;
+        }
+        const size_t p = (size_t)py * (size_t)fp.width + (size_t)px;
+        if (fb.records) *reinterpret_cast<uint4*>(fb.records + p) = make_uint4(rec.hit_voxel, rec.packed, rec.instance, rec.iters);
+        fb.color[p] = make_uchar4((unsigned char)dst[0], (unsigned char)dst[1], (unsigned char)dst[2], (unsigned char)dst[3]);
+        if (fb.depth) fb.depth[p] = zbuf;
+        iter_sum += rec.iters;
+    }
+    // one atomic per warp
+#pragma unroll
+    for (int o = 16; o; o >>= 1) iter_sum += __shfl_xor_sync(0xffffffffu, iter_sum, o);
+    if (lane == 0 && iter_sum) atomicAdd(fb.stats + 1, iter_sum);
+}
+
+// -------------------------------------------------------------------------------------------
+// path-tracing extension
+
+__device__ __forceinline__ uint32_t vt_mix(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+struct Rng { uint32_t key, ctr; };
+__device__ __forceinline__ void rng_init(Rng& r, uint32_t seed, uint32_t pixel, uint32_t sample) {
+    const uint32_t k = vt_mix(seed ^ vt_mix(pixel * 0x9E3779B9u + 0x85EBCA6Bu));
+    r.key = vt_mix(k ^ vt_mix(sample + 0xC2B2AE35u));
+    r.ctr = 0;
+}
+__device__ __forceinline__ float rng_u01(Rng& r) {
+    const uint32_t x = vt_mix(r.key + (r.ctr++) * 0x9E3779B9u);
+    return (float)(x >> 8) * (1.0f / 16777216.0f);
+}
+__device__ __forceinline__ void rng_sphere(Rng& r, float s[3]) {
+    float a = 0.0f, b = 0.0f, q = 0.0f;
+    bool ok = false;
+    for (int attempt = 0; attempt < 16 && !ok; ++attempt) {
+        a = rng_u01(r) * 2.0f - 1.0f;
+        b = rng_u01(r) * 2.0f - 1.0f;
+        q = a * a + b * b;
+        ok = q < 1.0f;
+    }
+    if (!ok) { a = 0.0f; b = 0.0f; q = 0.0f; }
+    const float w = sqrtf(1.0f - q);
+    s[0] = (2.0f * a) * w;
+    s[1] = (2.0f * b) * w;
+    s[2] = 1.0f - 2.0f * q;
+}
+
+struct PathHit {
+    bool hit;
+    uint32_t instance;
+    int entry_axis;
+    Dda dda;
+};
+
+template <bool kSmem>
+__device__ void trace_world(const FrameParams& fp, const InstUniforms* __restrict__ inst, const uint32_t* mask_base, uint32_t skip,
+                            const float ow[3], const float dw[3], PathHit& out, unsigned long long& iters) {
+    out.hit = false;
+    float last_t = -INFINITY;
+    uint32_t last_j = 0;
+    bool have_last = false;
+    for (;;) {
+        bool found = false;
+        float best_t = 0.0f;
+        uint32_t best_j = 0;
+        int best_axis = 0;
+        float bo[3] = {0, 0, 0}, bd[3] = {0, 0, 0};
+        for (uint32_t j = 0; j < fp.n_inst; ++j) {
+            const InstUniforms* J = inst + j;
+            if (j == skip || !J->valid) continue;
+            float o[3], d[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                o[k] = ((J->Mi[0 * 3 + k] * ow[0] + J->Mi[1 * 3 + k] * ow[1]) + J->Mi[2 * 3 + k] * ow[2]) + J->Mi[3 * 3 + k];
+                d[k] = (J->Mi[0 * 3 + k] * dw[0] + J->Mi[1 * 3 + k] * dw[1]) + J->Mi[2 * 3 + k] * dw[2];
+            }
+            float tn;
+            int axis;
+            if (!slab_unit_cube(o, d, tn, axis)) continue;
+            if (have_last && !(tn > last_t || (tn == last_t && j > last_j))) continue;
+            if (!found || tn < best_t) {
+                found = true; best_t = tn; best_j = j; best_axis = axis;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { bo[k] = o[k]; bd[k] = d[k]; }
+            }
+        }
+        if (!found) return;
+        float mp[3], pos[3];
+        entry_point(bo, bd, best_t, best_axis, mp);
+        const InstUniforms* J = inst + best_j;
+        const float size[3] = {(float)(int32_t)J->w, (float)(int32_t)J->h, (float)(int32_t)J->d};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) pos[k] = (mp[k] + 0.5f) * size[k];
+        Vol vol{J->w, J->h, J->d, J->xb, J->yb, J->mask_off, mask_base};
+        const int32_t none[3] = {0, 0, 0};
+        dda_march<kSmem>(vol, pos, bd, false, none, out.dda);
+        iters += out.dda.steps;
+        if (out.dda.hit) {
+            out.hit = true; out.instance = best_j; out.entry_axis = best_axis;
+            return;
+        }
+        last_t = best_t; last_j = best_j; have_last = true;
+    }
+}
+
+template <bool kSmem>
+__device__ void trace_path(const FrameParams& fp, const InstUniforms* __restrict__ inst, const uint32_t* mask_base,
+                           const float* __restrict__ dec, int px, int py, uint32_t sample, float L[3],
+                           unsigned long long& rays, unsigned long long& iters) {
+    Rng rng;
+    rng_init(rng, fp.seed, (uint32_t)py * (uint32_t)fp.width + (uint32_t)px, sample);
+    const float jx = rng_u01(rng), jy = rng_u01(rng);
+    const float fx = (float)px + jx, fy = (float)py + jy;
+    PathHit cur;
+    cur.hit = false;
+    float zbuf = 1.0f;
+    for (uint32_t i = 0; i < fp.n_inst; ++i) {
+        Fragment f;
+        run_fragment<kSmem>(fp, inst + i, mask_base, fx, fy, f);
+        if (!f.covered) continue;
+        iters += f.dda.steps;
+        if (!f.dda.hit || !(f.depth < zbuf)) continue;
+        zbuf = f.depth;
+        cur.hit = true; cur.instance = i; cur.entry_axis = f.entry_axis; cur.dda = f.dda;
+    }
+    rays += 1;
+    const float sky[3] = {53.0f / 100.0f, 81.0f / 100.0f, 92.0f / 100.0f}; // lib/command.c:57-59
+    float thr[3] = {1.0f, 1.0f, 1.0f};
+    L[0] = L[1] = L[2] = 0.0f;
+    for (uint32_t b = 0;; ++b) {
+        if (!cur.hit) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) L[c] = thr[c] * sky[c];
+            return;
+        }
+        const InstUniforms* J = inst + cur.instance;
+        const Dda& r = cur.dda;
+        const uchar4 s = fetch_texel(J->rgba, J->w, J->h, J->d, r.v);
+        thr[0] = thr[0] * dec[s.x];
+        thr[1] = thr[1] * dec[s.y];
+        thr[2] = thr[2] * dec[s.z];
+        if (b == fp.bounces) return;
+        const float size[3] = {(float)(int32_t)J->w, (float)(int32_t)J->h, (float)(int32_t)J->d};
+        const uint32_t lm = r.steps ? r.last_mask : (1u << cur.entry_axis);
+        const int a = (lm & 1u) ? 0 : ((lm & 2u) ? 1 : 2);
+        float p0[3], dn[3];
+        int32_t sv[3];
+        rng_sphere(rng, dn);
+        int nsign = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            // the per-axis quantities of the hit face are selected without dynamic indexing
+            const float t = r.steps ? ((a == 0 ? r.side[0] : (a == 1 ? r.side[1] : r.side[2])) -
+                                       (a == 0 ? r.delta[0] : (a == 1 ? r.delta[1] : r.delta[2])))
+                                    : 0.0f;
+            float p = r.pos[k] + (r.dir[k] / r.len) * t;
+            const float lo = (float)r.v[k], hi = (float)(r.v[k] + 1);
+            p = p < lo ? lo : p;
+            p = p > hi ? hi : p;
+            p0[k] = p;
+            sv[k] = r.v[k];
+            if (k == a) {
+                nsign = r.step[k] != 0 ? -r.step[k] : (r.pos[k] <= 0.5f * size[k] ? -1 : 1);
+                p0[k] = (float)(r.v[k] + (nsign > 0 ? 1 : 0));
+                sv[k] += nsign;
+                dn[k] += (float)nsign;
+            }
+        }
+        const float l2 = (dn[0] * dn[0] + dn[1] * dn[1]) + dn[2] * dn[2];
+        if (l2 < 1e-6f) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) dn[k] = (k == a) ? (float)nsign : 0.0f;
+        } else {
+            const float l = sqrtf(l2);
+            dn[0] /= l; dn[1] /= l; dn[2] /= l;
+        }
+        rays += 1;
+        PathHit next;
+        next.hit = false;
+        next.instance = cur.instance;
+        next.entry_axis = a;
+        Vol vol{J->w, J->h, J->d, J->xb, J->yb, J->mask_off, mask_base};
+        dda_march<kSmem>(vol, p0, dn, true, sv, next.dda);
+        iters += next.dda.steps;
+        next.hit = next.dda.hit;
+        if (!next.hit && fp.n_inst > 1) {
+            float pm[3], dm[3], ow[3], dw[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { pm[k] = p0[k] / size[k] - 0.5f; dm[k] = dn[k] / size[k]; }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                ow[k] = ((J->M[0 * 3 + k] * pm[0] + J->M[1 * 3 + k] * pm[1]) + J->M[2 * 3 + k] * pm[2]) + J->M[3 * 3 + k];
+                dw[k] = (J->M[0 * 3 + k] * dm[0] + J->M[1 * 3 + k] * dm[1]) + J->M[2 * 3 + k] * dm[2];
+            }
+            trace_world<kSmem>(fp, inst, mask_base, cur.instance, ow, dw, next, iters);
+        }
+        cur = next;
+    }
+}
+
+template <bool kSmem>
+__global__ void __launch_bounds__(kBlockThreads) trace_paths_kernel(const __grid_constant__ FrameParams fp,
+                                                                    const InstUniforms* __restrict__ inst,
+                                                                    const uint32_t* __restrict__ mask_arena,
+                                                                    uint32_t arena_words, SrgbTables lut, FrameBuffers fb) {
+    stage_tables<kSmem>(mask_arena, arena_words, lut.decode);
+    const uint32_t* mask_base = mask_arena;
+    const float* dec = reinterpret_cast<const float*>(vt_smem + kSmemLutOff);
+
+    const int tiles_x = (fp.width + kTileW - 1) / kTileW;
+    const int tiles_y = (fp.height + kTileH - 1) / kTileH;
+    const int n_tiles = tiles_x * tiles_y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lx = (warp & 3) * 8 + (lane & 7);
+    const int ly = (warp >> 2) * 4 + (lane >> 3);
+
+    unsigned long long rays = 0, iters = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int px = (tile % tiles_x) * kTileW + lx;
+        const int py = (tile / tiles_x) * kTileH + ly;
+        if (px >= fp.width || py >= fp.height) continue;
+        unsigned long long acc[3] = {0, 0, 0};
+        for (uint32_t k = 0; k < fp.spp; ++k) {
+            float L[3];
+            trace_path<kSmem>(fp, inst, mask_base, dec, px, py, fp.sample_first + k * fp.sample_stride, L, rays, iters);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float q = L[c] * 16777216.0f;
+                acc[c] += (q == q && q > 0.0f) ? __float2ull_rz(q) : 0ull;
+            }
+        }
+        const size_t p = (size_t)py * (size_t)fp.width + (size_t)px;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) fb.accum[3 * p + c] += acc[c];
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        rays += __shfl_xor_sync(0xffffffffu, rays, o);
+        iters += __shfl_xor_sync(0xffffffffu, iters, o);
+    }
+    if (lane == 0) {
+        if (rays) atomicAdd(fb.stats + 0, rays);
+        if (iters) atomicAdd(fb.stats + 1, iters);
+    }
+}
+
+__global__ void resolve_kernel(const unsigned long long* __restrict__ accum, uint32_t n_pixels, uint32_t total_spp, SrgbTables lut,
+                               uchar4* __restrict__ color) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pixels) return;
+    const float scale = 1.0f / ((float)total_spp * 16777216.0f);
+    uint32_t c[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) c[k] = srgb_encode(lut.threshold, __ull2float_rn(accum[3 * (size_t)p + k]) * scale);
+    color[p] = make_uchar4((unsigned char)c[0], (unsigned char)c[1], (unsigned char)c[2], 255);
+}
+
+// -------------------------------------------------------------------------------------------
+// launch wrappers
+
+
+cudaError_t configure_kernels(int max_smem_optin) {
+    cudaError_t e;
+    e = cudaFuncSetAttribute(trace_primary_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(trace_paths_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    return e;
+}
+
+template <class K>
+static int persistent_grid(K kernel, size_t smem, int sm_count, int n_tiles) {
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlockThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    long grid = (long)per_sm * sm_count; // whole number of CTAs per SM: one resident wave
+    if (grid > n_tiles) grid = n_tiles;
+    return (int)(grid < 1 ? 1 : grid);
+}
+
+cudaError_t launch_trace_primary(const FrameParams& fp, const InstUniforms* inst, const uint32_t* mask_arena, uint32_t arena_words,
+                                 bool masks_in_smem, SrgbTables lut, FrameBuffers fb, int sm_count, cudaStream_t stream) {
+    const int n_tiles = ((fp.width + kTileW - 1) / kTileW) * ((fp.height + kTileH - 1) / kTileH);
+    const size_t smem = trace_smem_bytes(arena_words, masks_in_smem);
+    if (masks_in_smem) {
+        const int grid = persistent_grid(trace_primary_kernel<true>, smem, sm_count, n_tiles);
+        trace_primary_kernel<true><<<grid, kBlockThreads, smem, stream>>>(fp, inst, mask_arena, arena_words, lut, fb);
+    } else {
+        const int grid = persistent_grid(trace_primary_kernel<false>, smem, sm_count, n_tiles);
+        trace_primary_kernel<false><<<grid, kBlockThreads, smem, stream>>>(fp, inst, mask_arena, arena_words, lut, fb);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_trace_paths(const FrameParams& fp, const InstUniforms* inst, const uint32_t* mask_arena, uint32_t arena_words,
+                               bool masks_in_smem, SrgbTables lut, FrameBuffers fb, int sm_count, cudaStream_t stream) {
+    const int n_tiles = ((fp.width + kTileW - 1) / kTileW) * ((fp.height + kTileH - 1) / kTileH);
+    const size_t smem = trace_smem_bytes(arena_words, masks_in_smem);
+    if (masks_in_smem) {
+        const int grid = persistent_grid(trace_paths_kernel<true>, smem, sm_count, n_tiles);
+        trace_paths_kernel<true><<<grid, kBlockThreads, smem, stream>>>(fp, inst, mask_arena, arena_words, lut, fb);
+    } else {
+        const int grid = persistent_grid(trace_paths_kernel<false>, smem, sm_count, n_tiles);
+        trace_paths_kernel<false><<<grid, kBlockThreads, smem, stream>>>(fp, inst, mask_arena, arena_words, lut, fb);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_resolve(const unsigned long long* accum, uint32_t n_pixels, uint32_t total_spp, SrgbTables lut, uchar4* color,
+                           cudaStream_t stream) {
+    const int threads = 256;
+    resolve_kernel<<<(n_pixels + threads - 1) / threads, threads, 0, stream>>>(accum, n_pixels, total_spp, lut, color);
+    return cudaGetLastError();
+}
+
+} // namespace vt

@@ -1,0 +1,100 @@
+// kernels.h — device-side data layout and the launch wrappers render_abi.cu calls.
+//
+// Data layout in HBM:
+//   * volume texels : dense RGBA8, x fastest, exactly the bytes add_texture received
+//                     (lib/memory.c:353-366).  Read ONCE per ray, at the hit.
+//   * stop masks    : one bit per voxel of the volume padded by a one-voxel border,
+//                     bit = 1 when the DDA must stop there (texel alpha > 0, or border =
+//                     the ray left the volume).  Row / plane strides are powers of two so
+//                     a voxel's bit index is x' | y' << xb | z' << (xb + yb).  All volumes
+//                     live in ONE arena so a single TMA bulk copy stages every mask of a
+//                     small scene into shared memory.
+//   * instance table: per-instance uniforms produced by the instance-setup kernel (the
+//                     trace.vert replacement).
+//   * framebuffer   : 16-byte hit records, RGBA8 colour, D32 depth, 3 x u64 accumulators.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace vt {
+
+struct VolumeDesc {
+    const uint8_t* rgba; // dense W*H*D RGBA8
+    uint32_t w, h, d;
+    uint32_t xb, yb;     // log2(row bits), log2(rows per plane) of the padded stop mask
+    uint32_t mask_off;   // word offset of this volume's mask inside the arena
+    uint32_t mask_words; // multiple of 4 (16-byte granules for the bulk copy)
+    uint32_t pad;
+};
+
+// Per-frame uniforms, passed by value as a kernel parameter (constant bank, no loads).
+struct FrameParams {
+    float RD[16]; // inverse(centered camera) * inverse(projection), trace.frag:59
+    float PV[16]; // projection * camera, trace.vert:45
+    float eye[3]; // inverse(camera) * (0,0,0,1), trace.frag:51
+    float vw, vh; // viewport, lib/command.c:80-81
+    int32_t width, height;
+    uint32_t n_inst;
+    uint32_t n_volumes;
+    uint32_t flags;
+    // path-tracing extension
+    uint32_t spp, bounces, seed, sample_first, sample_stride;
+};
+
+// Per-instance uniforms (trace.vert outputs that are flat per instance + derived matrices).
+struct __align__(16) InstUniforms {
+    float MVP[16];   // (P V) M           column-major
+    float Mi[12];    // inverse(M), rows 0-2 of columns 0-3: Mi[c*3 + r]
+    float M[12];     // M,          rows 0-2 of columns 0-3
+    float dirm[12];  // inverse(M)3x3 * RD rows 0-2: clip point -> model-space ray direction
+    float eye_m[3];  // camera position in model space
+    uint32_t valid;  // texture id in range
+    uint32_t tex;
+    uint32_t w, h, d;
+    uint32_t xb, yb;
+    uint32_t mask_off;
+    uint32_t pad[3];
+    const uint8_t* rgba;
+    uint64_t pad2;
+};
+
+struct HitRecord { uint32_t hit_voxel, packed, instance, iters; };
+
+struct FrameBuffers {
+    HitRecord* records;   // may be null
+    uchar4* color;
+    float* depth;         // may be null
+    unsigned long long* accum; // 3 per pixel
+    unsigned long long* stats; // [0] rays, [1] iterations
+};
+
+struct SrgbTables {
+    const float* decode;    // 256
+    const float* threshold; // 256
+};
+
+// GLSL inverse(mat4) (cofactor expansion, fixed operation order); 16 floats column-major.
+// One source for host and device so the per-frame (host) and per-instance (device) inverses
+// follow the same operation order as the oracle.
+__host__ __device__ void mat4_inverse(const float* m, float* out);
+
+// launch wrappers (all asynchronous on `stream`); return cudaError_t
+cudaError_t launch_build_mask(const uint8_t* rgba, uint32_t w, uint32_t h, uint32_t d, uint32_t xb, uint32_t yb,
+                              uint32_t* mask, uint32_t mask_words, cudaStream_t stream);
+cudaError_t launch_instance_setup(const float* instances, uint32_t n, const VolumeDesc* volumes, FrameParams fp,
+                                  InstUniforms* out, cudaStream_t stream);
+cudaError_t launch_trace_primary(const FrameParams& fp, const InstUniforms* inst, const uint32_t* mask_arena,
+                                 uint32_t arena_words, bool masks_in_smem, SrgbTables lut, FrameBuffers fb,
+                                 int sm_count, cudaStream_t stream);
+cudaError_t launch_trace_paths(const FrameParams& fp, const InstUniforms* inst, const uint32_t* mask_arena,
+                               uint32_t arena_words, bool masks_in_smem, SrgbTables lut, FrameBuffers fb,
+                               int sm_count, cudaStream_t stream);
+cudaError_t launch_resolve(const unsigned long long* accum, uint32_t n_pixels, uint32_t total_spp, SrgbTables lut,
+                           uchar4* color, cudaStream_t stream);
+// one-time: opt in to large dynamic shared memory
+cudaError_t configure_kernels(int max_smem_optin);
+// bytes of dynamic shared memory the trace kernels need for a given arena size
+size_t trace_smem_bytes(uint32_t arena_words, bool masks_in_smem);
+
+} // namespace vt

@@ -1,0 +1,566 @@
+// render_abi.cu — the C ABI of librender (include/vtrace_abi.h): the reference's seven FFI
+// symbols (src/render.rs:110-128; lib/entry.c, lib/memory.c) implemented on CUDA, plus the
+// vt_* headless extensions.  Global singleton state like the reference's `renderer glbl`
+// (lib/entry.c:21).  No CPU fallback: every path either runs the CUDA kernels or fails.
+#include "../../include/vtrace_abi.h"
+#include "kernels.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+using namespace vt;
+
+constexpr uint32_t kMaxTextures = 65536; // MAX_TEXTURES, lib/common.h:35
+constexpr size_t kSmemMaskBudget = 160 * 1024; // masks up to this size are staged in shared memory
+
+struct State {
+    bool inited = false;
+    int device = 0;
+    int sm_count = 148;
+    int max_smem_optin = 48 * 1024;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    vt_config cfg{};
+
+    // volumes ("textures")
+    std::vector<VolumeDesc> vols;
+    VolumeDesc* d_vols = nullptr;
+    size_t d_vols_cap = 0;
+    bool vols_dirty = false;
+    uint32_t* d_arena = nullptr; // all stop masks, contiguous
+    uint32_t arena_words = 0, arena_cap = 0;
+    uint8_t* h_tex_staging = nullptr; // pinned; grows to the next power of two (lib/memory.c:297-302)
+    size_t tex_staging_size = 0;
+
+    // instances
+    float* h_inst = nullptr; // pinned staging the engine writes into (lib/memory.c:245-247)
+    float* d_inst = nullptr;
+    InstUniforms* d_iu = nullptr;
+    uint32_t inst_cap = 0, inst_count = 1;
+
+    // tables
+    float* d_dec = nullptr;
+    float* d_thr = nullptr;
+
+    // framebuffer
+    uint32_t fb_w = 0, fb_h = 0;
+    HitRecord* d_rec = nullptr;
+    uchar4* d_color = nullptr;
+    float* d_depth = nullptr;
+    unsigned long long* d_accum = nullptr;
+    unsigned long long* d_stats = nullptr;
+    unsigned long long* h_stats = nullptr; // pinned
+    void* h_readback = nullptr;            // pinned staging for vt_read_*
+    size_t readback_size = 0;
+
+    cudaEvent_t ev_begin = nullptr, ev_trace0 = nullptr, ev_trace1 = nullptr, ev_end = nullptr;
+    bool frame_pending = false;
+
+    vt_stats stats{};
+    user_input input{};
+    char err[512] = {0};
+};
+
+State g;
+
+int fail(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g.err, sizeof g.err, fmt, ap);
+    va_end(ap);
+    fprintf(stderr, "ERROR: %s\n", g.err); // the reference logs the same way, e.g. lib/memory.c:288
+    return -1;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail("%s -> %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+uint32_t env_u32(const char* name, uint32_t dflt) {
+    const char* v = getenv(name);
+    return v && *v ? (uint32_t)strtoul(v, nullptr, 0) : dflt;
+}
+
+uint32_t ceil_log2(uint32_t x) {
+    uint32_t b = 0;
+    while ((1u << b) < x) ++b;
+    return b;
+}
+
+size_t round_up_p2(size_t x) { // lib/memory.c round_up_p2
+    size_t p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+// host-side mat4 helpers, same operation order as the oracle / the device code
+void mat4_mul(const float* a, const float* b, float* r) {
+    for (int j = 0; j < 4; ++j)
+        for (int i = 0; i < 4; ++i)
+            r[j * 4 + i] = ((a[0 * 4 + i] * b[j * 4 + 0] + a[1 * 4 + i] * b[j * 4 + 1]) + a[2 * 4 + i] * b[j * 4 + 2]) + a[3 * 4 + i] * b[j * 4 + 3];
+}
+
+double srgb_to_linear(double c) { return c <= 0.04045 ? c / 12.92 : pow((c + 0.055) / 1.055, 2.4); }
+
+int alloc_framebuffer() {
+    const uint32_t w = g.cfg.width, h = g.cfg.height;
+    if (w == g.fb_w && h == g.fb_h && g.d_color) return 0;
+    CK(cudaStreamSynchronize(g.stream));
+    cudaFree(g.d_rec); cudaFree(g.d_color); cudaFree(g.d_depth); cudaFree(g.d_accum);
+    g.d_rec = nullptr; g.d_color = nullptr; g.d_depth = nullptr; g.d_accum = nullptr;
+    const size_t n = (size_t)w * h;
+    CK(cudaMalloc(&g.d_rec, n * sizeof(HitRecord)));
+    CK(cudaMalloc(&g.d_color, n * sizeof(uchar4)));
+    CK(cudaMalloc(&g.d_depth, n * sizeof(float)));
+    CK(cudaMalloc(&g.d_accum, n * 3 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(g.d_rec, 0xFF, n * sizeof(HitRecord), g.stream));
+    CK(cudaMemsetAsync(g.d_color, 0, n * sizeof(uchar4), g.stream));
+    CK(cudaMemsetAsync(g.d_depth, 0, n * sizeof(float), g.stream));
+    CK(cudaMemsetAsync(g.d_accum, 0, n * 3 * sizeof(unsigned long long), g.stream));
+    g.fb_w = w; g.fb_h = h;
+    return 0;
+}
+
+int ensure_readback(size_t bytes) {
+    if (bytes <= g.readback_size) return 0;
+    if (g.h_readback) cudaFreeHost(g.h_readback);
+    g.h_readback = nullptr;
+    g.readback_size = 0;
+    CK(cudaMallocHost(&g.h_readback, bytes));
+    g.readback_size = bytes;
+    return 0;
+}
+
+int ensure_instances(uint32_t n) {
+    if (n <= g.inst_cap) return 0;
+    // lib/memory.c:239-243: the instance buffers are re-created at the next power of two
+    const uint32_t cap = (uint32_t)round_up_p2(n);
+    CK(cudaStreamSynchronize(g.stream));
+    float* h_new = nullptr;
+    CK(cudaMallocHost(&h_new, (size_t)cap * 64));
+    memset(h_new, 0, (size_t)cap * 64);
+    if (g.h_inst) {
+        memcpy(h_new, g.h_inst, (size_t)g.inst_cap * 64);
+        cudaFreeHost(g.h_inst);
+    }
+    g.h_inst = h_new;
+    cudaFree(g.d_inst); cudaFree(g.d_iu);
+    g.d_inst = nullptr; g.d_iu = nullptr;
+    CK(cudaMalloc(&g.d_inst, (size_t)cap * 64));
+    CK(cudaMalloc(&g.d_iu, (size_t)cap * sizeof(InstUniforms)));
+    CK(cudaMemcpyAsync(g.d_inst, g.h_inst, (size_t)cap * 64, cudaMemcpyHostToDevice, g.stream));
+    g.inst_cap = cap;
+    return 0;
+}
+
+int finish_frame() {
+    if (!g.frame_pending) return 0;
+    CK(cudaStreamSynchronize(g.stream));
+    g.frame_pending = false;
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, g.ev_trace0, g.ev_trace1) == cudaSuccess) g.stats.last_trace_ms = ms;
+    if (cudaEventElapsedTime(&ms, g.ev_begin, g.ev_end) == cudaSuccess) g.stats.last_frame_ms = ms;
+    if (g.cfg.mode == VT_MODE_PRIMARY) {
+        g.stats.rays = (uint64_t)g.cfg.width * g.cfg.height;
+        g.stats.iterations = g.h_stats[1];
+    } else {
+        g.stats.rays = g.h_stats[0];
+        g.stats.iterations = g.h_stats[1];
+    }
+    return 0;
+}
+
+int render_async(const float* P, const float* V, bool clear_accum, bool resolve) {
+    if (!g.inited) return fail("render before entry()");
+    CK(cudaSetDevice(g.device));
+    if (alloc_framebuffer()) return -1;
+    if (g.frame_pending && finish_frame()) return -1;
+
+    FrameParams fp{};
+    float Pi[16], Vi[16], Vc[16], Vci[16];
+    mat4_inverse(P, Pi);                 // trace.frag:48
+    mat4_inverse(V, Vi);                 // trace.frag:49
+    memcpy(Vc, V, sizeof Vc);            // trace.frag:54-57
+    Vc[12] = 0.0f; Vc[13] = 0.0f; Vc[14] = 0.0f;
+    mat4_inverse(Vc, Vci);               // trace.frag:59
+    mat4_mul(Vci, Pi, fp.RD);            // (inverse(Vc) * inverse(P)) * sp
+    mat4_mul(P, V, fp.PV);               // trace.vert:45
+    const float origin[4] = {0.0f, 0.0f, 0.0f, 1.0f};
+    for (int i = 0; i < 3; ++i)          // trace.frag:51 cam_pos
+        fp.eye[i] = ((Vi[0 * 4 + i] * origin[0] + Vi[1 * 4 + i] * origin[1]) + Vi[2 * 4 + i] * origin[2]) + Vi[3 * 4 + i] * origin[3];
+    fp.width = (int32_t)g.cfg.width;
+    fp.height = (int32_t)g.cfg.height;
+    fp.vw = (float)g.cfg.width;                                                              // lib/command.c:80
+    fp.vh = (g.cfg.flags & VT_FLAG_VIEWPORT_H_IS_W) ? (float)g.cfg.width : (float)g.cfg.height; // lib/command.c:81
+    fp.n_inst = g.inst_count;
+    fp.n_volumes = (uint32_t)g.vols.size();
+    fp.flags = g.cfg.flags;
+    fp.spp = g.cfg.spp;
+    fp.bounces = g.cfg.bounces;
+    fp.seed = g.cfg.seed;
+    fp.sample_first = g.cfg.sample_first;
+    fp.sample_stride = g.cfg.sample_stride ? g.cfg.sample_stride : 1;
+
+    if (g.vols_dirty) {
+        if (g.vols.size() > g.d_vols_cap) {
+            cudaFree(g.d_vols);
+            g.d_vols = nullptr;
+            g.d_vols_cap = round_up_p2(g.vols.size());
+            CK(cudaMalloc(&g.d_vols, g.d_vols_cap * sizeof(VolumeDesc)));
+        }
+        CK(cudaMemcpyAsync(g.d_vols, g.vols.data(), g.vols.size() * sizeof(VolumeDesc), cudaMemcpyHostToDevice, g.stream));
+        CK(cudaStreamSynchronize(g.stream)); // g.vols may reallocate before the copy would run
+        g.vols_dirty = false;
+    }
+    if (ensure_instances(g.inst_count)) return -1;
+
+    CK(cudaEventRecord(g.ev_begin, g.stream));
+    CK(cudaMemsetAsync(g.d_stats, 0, 2 * sizeof(unsigned long long), g.stream));
+    CK(launch_instance_setup(g.d_inst, g.inst_count, g.d_vols, fp, g.d_iu, g.stream));
+    g.stats.launches += 1;
+
+    const bool in_smem = !(g.cfg.flags & VT_FLAG_FORCE_GLOBAL_MASKS) && g.arena_words > 0 &&
+                         (size_t)g.arena_words * 4 <= kSmemMaskBudget &&
+                         trace_smem_bytes(g.arena_words, true) <= (size_t)g.max_smem_optin;
+    g.stats.masks_in_smem = in_smem ? 1u : 0u;
+    FrameBuffers fb{};
+    fb.records = (g.cfg.flags & VT_FLAG_NO_HIT_RECORDS) ? nullptr : g.d_rec;
+    fb.color = g.d_color;
+    fb.depth = g.d_depth;
+    fb.accum = g.d_accum;
+    fb.stats = g.d_stats;
+    SrgbTables lut{g.d_dec, g.d_thr};
+
+    if (g.cfg.mode == VT_MODE_PRIMARY) {
+        CK(cudaEventRecord(g.ev_trace0, g.stream));
+        CK(launch_trace_primary(fp, g.d_iu, g.d_arena, g.arena_words, in_smem, lut, fb, g.sm_count, g.stream));
+        CK(cudaEventRecord(g.ev_trace1, g.stream));
+        g.stats.launches += 1;
+    } else {
+        if (clear_accum)
+            CK(cudaMemsetAsync(g.d_accum, 0, (size_t)g.cfg.width * g.cfg.height * 3 * sizeof(unsigned long long), g.stream));
+        CK(cudaEventRecord(g.ev_trace0, g.stream));
+        CK(launch_trace_paths(fp, g.d_iu, g.d_arena, g.arena_words, in_smem, lut, fb, g.sm_count, g.stream));
+        CK(cudaEventRecord(g.ev_trace1, g.stream));
+        g.stats.launches += 1;
+        if (resolve) {
+            const uint32_t total = g.cfg.total_spp ? g.cfg.total_spp : g.cfg.spp;
+            CK(launch_resolve(g.d_accum, g.cfg.width * g.cfg.height, total ? total : 1, lut, g.d_color, g.stream));
+            g.stats.launches += 1;
+        }
+    }
+    CK(cudaMemcpyAsync(g.h_stats, g.d_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaEventRecord(g.ev_end, g.stream));
+    g.frame_pending = true;
+    g.stats.frames += 1;
+    return 0;
+}
+
+int64_t read_back(const void* d_src, size_t bytes, void* out, size_t capacity) {
+    if (!g.inited) return fail("read before entry()");
+    if (!out || capacity < bytes) return fail("read-back buffer too small: need %zu bytes, have %zu", bytes, capacity);
+    if (cudaSetDevice(g.device) != cudaSuccess) return fail("cudaSetDevice failed");
+    if (ensure_readback(bytes)) return -1;
+    if (cudaMemcpyAsync(g.h_readback, d_src, bytes, cudaMemcpyDeviceToHost, g.stream) != cudaSuccess) return fail("read-back copy failed");
+    if (finish_frame()) return -1;
+    if (cudaStreamSynchronize(g.stream) != cudaSuccess) return fail("read-back sync failed");
+    memcpy(out, g.h_readback, bytes);
+    return (int64_t)bytes;
+}
+
+} // namespace
+
+// ============================================================================================
+// Part 1 — the reference's FFI
+
+extern "C" uint64_t entry(void) {
+    if (g.inited) return 0;
+    int dev = (int)env_u32("VT_DEVICE", env_u32("LOCAL_RANK", 0));
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        fail("no CUDA device: %s", cudaGetErrorString(e));
+        return ((uint64_t)(uint32_t)e << 32) | 1u;
+    }
+    if (dev >= count) dev = 0;
+    g.device = dev;
+#define CKE(call)                                                                     \
+    do {                                                                              \
+        cudaError_t e_ = (call);                                                      \
+        if (e_ != cudaSuccess) {                                                      \
+            fail("%s -> %s", #call, cudaGetErrorString(e_));                          \
+            return ((uint64_t)(uint32_t)e_ << 32) | 2u;                               \
+        }                                                                             \
+    } while (0)
+    CKE(cudaSetDevice(dev));
+    cudaDeviceProp prop{};
+    CKE(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10) {
+        fail("librender is built for sm_100a only; device %d is sm_%d%d", dev, prop.major, prop.minor);
+        return 3u;
+    }
+    g.sm_count = prop.multiProcessorCount;
+    g.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    CKE(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
+    g.stream = g.own_stream;
+    CKE(cudaEventCreate(&g.ev_begin));
+    CKE(cudaEventCreate(&g.ev_trace0));
+    CKE(cudaEventCreate(&g.ev_trace1));
+    CKE(cudaEventCreate(&g.ev_end));
+    CKE(configure_kernels(g.max_smem_optin));
+
+    // sRGB tables (VK_FORMAT_R8G8B8A8_SRGB textures, lib/memory.c:317; B8G8R8A8_SRGB target, lib/swapchain.c:88)
+    float dec[256], thr[256];
+    for (int k = 0; k < 256; ++k) {
+        dec[k] = (float)srgb_to_linear((double)k / 255.0);
+        thr[k] = k == 0 ? 0.0f : (float)srgb_to_linear(((double)k - 0.5) / 255.0);
+    }
+    CKE(cudaMalloc(&g.d_dec, sizeof dec));
+    CKE(cudaMalloc(&g.d_thr, sizeof thr));
+    CKE(cudaMemcpy(g.d_dec, dec, sizeof dec, cudaMemcpyHostToDevice));
+    CKE(cudaMemcpy(g.d_thr, thr, sizeof thr, cudaMemcpyHostToDevice));
+    CKE(cudaMalloc(&g.d_stats, 2 * sizeof(unsigned long long)));
+    CKE(cudaMallocHost(&g.h_stats, 2 * sizeof(unsigned long long)));
+    g.h_stats[0] = g.h_stats[1] = 0;
+
+    // defaults: the reference's fixed 1000x1000 window (lib/entry.c:62), overridable from the
+    // environment so the unmodified Rust engine can be configured without new calls
+    g.cfg = vt_config{};
+    g.cfg.width = env_u32("VT_WIDTH", 1000);
+    g.cfg.height = env_u32("VT_HEIGHT", 1000);
+    g.cfg.mode = env_u32("VT_MODE", VT_MODE_PRIMARY);
+    g.cfg.flags = env_u32("VT_FLAGS", 0);
+    g.cfg.spp = env_u32("VT_SPP", 1);
+    g.cfg.bounces = env_u32("VT_BOUNCES", 4);
+    g.cfg.seed = env_u32("VT_SEED", 0x5EED);
+    g.cfg.sample_first = env_u32("VT_SAMPLE_FIRST", 0);
+    g.cfg.sample_stride = env_u32("VT_SAMPLE_STRIDE", 1);
+    g.cfg.total_spp = env_u32("VT_TOTAL_SPP", 0);
+    g.cfg.max_frames = (int32_t)env_u32("VT_MAX_FRAMES", 0);
+    g.cfg.device = dev;
+
+    g.inited = true;
+    g.inst_count = 1; // lib/memory.c:236,251: an empty scene still draws one (stale, zeroed) instance
+    if (ensure_instances(1)) { g.inited = false; return 4u; }
+    if (alloc_framebuffer()) { g.inited = false; return 5u; }
+    CKE(cudaStreamSynchronize(g.stream));
+#undef CKE
+    return 0;
+}
+
+extern "C" int32_t render_tick(int32_t* window_width, int32_t* window_height, const render_tick_info* info) {
+    if (!g.inited) return -1;
+    // lib/entry.c:151-153: the window-close check comes first; headless = frame budget
+    if (g.cfg.max_frames > 0 && g.stats.frames >= (uint64_t)g.cfg.max_frames) return -1;
+    if (!info || !info->perspective || !info->camera) return -1;
+    if (render_async((const float*)info->perspective, (const float*)info->camera, true, true)) return -1;
+    if (finish_frame()) return -1;
+    if (window_width) *window_width = (int32_t)g.cfg.width;   // lib/entry.c:244
+    if (window_height) *window_height = (int32_t)g.cfg.height; // lib/entry.c:245
+    return 0;
+}
+
+extern "C" user_input* get_input_data_pointer(void) { return &g.input; }
+
+extern "C" int32_t add_texture(const uint8_t* data, uint32_t width, uint32_t height, uint32_t depth) {
+    if (!g.inited) return fail("add_texture before entry()");
+    if (g.vols.size() >= kMaxTextures) return fail("Tried allocating too many textures"); // lib/memory.c:287-290
+    if (!data || !width || !height || !depth) return fail("add_texture: empty volume");
+    CK(cudaSetDevice(g.device));
+    const uint32_t xb = ceil_log2(width + 2) < 5 ? 5 : ceil_log2(width + 2);
+    const uint32_t yb = ceil_log2(height + 2) < 2 ? 2 : ceil_log2(height + 2);
+    const uint32_t zbits = ceil_log2(depth + 2);
+    if (xb + yb + zbits > 31) return fail("add_texture: %ux%ux%u does not fit the 31-bit stop-mask index", width, height, depth);
+    const size_t bytes = (size_t)4 * width * height * depth;
+    const uint32_t mask_words = ((1u << (xb - 5)) << yb) * (depth + 2);
+    const uint32_t mask_words_padded = (mask_words + 3u) & ~3u;
+
+    // staging grows to the next power of two and the bytes are copied before returning
+    // (lib/memory.c:297-307: `data` is only borrowed for the call)
+    if (bytes > g.tex_staging_size) {
+        CK(cudaStreamSynchronize(g.stream));
+        if (g.h_tex_staging) cudaFreeHost(g.h_tex_staging);
+        g.h_tex_staging = nullptr;
+        g.tex_staging_size = round_up_p2(bytes);
+        CK(cudaMallocHost(&g.h_tex_staging, g.tex_staging_size));
+    }
+    CK(cudaStreamSynchronize(g.stream)); // the previous upload may still read the staging buffer
+    memcpy(g.h_tex_staging, data, bytes);
+
+    uint8_t* d_rgba = nullptr;
+    CK(cudaMalloc(&d_rgba, bytes));
+    CK(cudaMemcpyAsync(d_rgba, g.h_tex_staging, bytes, cudaMemcpyHostToDevice, g.stream));
+
+    // the arena doubles like the reference's texture memory blocks (lib/memory.c:278-284)
+    if (g.arena_words + mask_words_padded > g.arena_cap) {
+        uint32_t cap = g.arena_cap ? g.arena_cap : 8192;
+        while (cap < g.arena_words + mask_words_padded) cap *= 2;
+        uint32_t* d_new = nullptr;
+        CK(cudaMalloc(&d_new, (size_t)cap * 4));
+        if (g.arena_words) CK(cudaMemcpyAsync(d_new, g.d_arena, (size_t)g.arena_words * 4, cudaMemcpyDeviceToDevice, g.stream));
+        CK(cudaStreamSynchronize(g.stream));
+        cudaFree(g.d_arena);
+        g.d_arena = d_new;
+        g.arena_cap = cap;
+    }
+    VolumeDesc v{};
+    v.rgba = d_rgba;
+    v.w = width; v.h = height; v.d = depth;
+    v.xb = xb; v.yb = yb;
+    v.mask_off = g.arena_words;
+    v.mask_words = mask_words_padded;
+    if (mask_words_padded > mask_words)
+        CK(cudaMemsetAsync(g.d_arena + g.arena_words + mask_words, 0xFF, (size_t)(mask_words_padded - mask_words) * 4, g.stream));
+    CK(launch_build_mask(d_rgba, width, height, depth, xb, yb, g.d_arena + g.arena_words, mask_words, g.stream));
+    g.stats.launches += 1;
+    g.arena_words += mask_words_padded;
+    g.vols.push_back(v);
+    g.vols_dirty = true;
+    return (int32_t)(g.vols.size() - 1); // lib/memory.c:292,384
+}
+
+extern "C" float* start_update_instances(uint32_t instance_count) {
+    if (!g.inited) { fail("start_update_instances before entry()"); return nullptr; }
+    if (instance_count == 0) instance_count = 1; // lib/memory.c:236
+    if (cudaSetDevice(g.device) != cudaSuccess) return nullptr;
+    // the previous frame's upload must have consumed the staging buffer before it is rewritten
+    if (cudaStreamSynchronize(g.stream) != cudaSuccess) return nullptr;
+    if (ensure_instances(instance_count)) return nullptr;
+    g.inst_count = instance_count;
+    return g.h_inst;
+}
+
+extern "C" int32_t end_update_instances(uint32_t instance_count) {
+    if (!g.inited) return fail("end_update_instances before entry()");
+    if (instance_count == 0) instance_count = 1; // lib/memory.c:251
+    if (instance_count > g.inst_cap) return fail("end_update_instances: %u > capacity %u", instance_count, g.inst_cap);
+    CK(cudaSetDevice(g.device));
+    g.inst_count = instance_count;
+    // lib/memory.c:257-264: staging -> device copy
+    CK(cudaMemcpyAsync(g.d_inst, g.h_inst, (size_t)instance_count * 64, cudaMemcpyHostToDevice, g.stream));
+    return 0;
+}
+
+extern "C" void cleanup(void) {
+    if (!g.inited) return;
+    cudaSetDevice(g.device);
+    cudaDeviceSynchronize(); // vkDeviceWaitIdle, lib/entry.c:101
+    for (auto& v : g.vols) cudaFree(const_cast<uint8_t*>(v.rgba));
+    g.vols.clear();
+    cudaFree(g.d_vols); cudaFree(g.d_arena); cudaFree(g.d_inst); cudaFree(g.d_iu); cudaFree(g.d_dec); cudaFree(g.d_thr);
+    cudaFree(g.d_rec); cudaFree(g.d_color); cudaFree(g.d_depth); cudaFree(g.d_accum); cudaFree(g.d_stats);
+    if (g.h_inst) cudaFreeHost(g.h_inst);
+    if (g.h_tex_staging) cudaFreeHost(g.h_tex_staging);
+    if (g.h_stats) cudaFreeHost(g.h_stats);
+    if (g.h_readback) cudaFreeHost(g.h_readback);
+    cudaEventDestroy(g.ev_begin); cudaEventDestroy(g.ev_trace0); cudaEventDestroy(g.ev_trace1); cudaEventDestroy(g.ev_end);
+    if (g.own_stream) cudaStreamDestroy(g.own_stream);
+    const user_input keep = g.input;
+    g = State{};
+    g.input = keep;
+}
+
+// ============================================================================================
+// Part 2 — headless extensions
+
+extern "C" int32_t vt_get_config(vt_config* out) {
+    if (!g.inited || !out) return -1;
+    *out = g.cfg;
+    return 0;
+}
+
+extern "C" int32_t vt_configure(const vt_config* cfg) {
+    if (!g.inited) return fail("vt_configure before entry()");
+    if (!cfg || !cfg->width || !cfg->height) return fail("vt_configure: bad size");
+    if (cfg->mode > VT_MODE_PATHS) return fail("vt_configure: unknown mode %u", cfg->mode);
+    if ((uint64_t)cfg->width * cfg->height > (1ull << 28)) return fail("vt_configure: framebuffer too large");
+    CK(cudaSetDevice(g.device));
+    if (finish_frame()) return -1;
+    const int32_t dev = g.cfg.device;
+    g.cfg = *cfg;
+    g.cfg.device = dev; // the device is fixed at entry()
+    if (!g.cfg.sample_stride) g.cfg.sample_stride = 1;
+    return alloc_framebuffer();
+}
+
+extern "C" int32_t vt_render_async(const float* projection, const float* camera) {
+    if (!projection || !camera) return -1;
+    // PATHS: adds this process's samples into the accumulators; clearing / resolving is the
+    // launcher's job (vt_clear_accum / vt_resolve) because a cross-rank reduction sits between.
+    return render_async(projection, camera, false, false);
+}
+
+extern "C" int32_t vt_synchronize(void) {
+    if (!g.inited) return -1;
+    CK(cudaSetDevice(g.device));
+    if (finish_frame()) return -1;
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+extern "C" int64_t vt_read_hits(vt_hit_record* out, size_t capacity) {
+    static_assert(sizeof(vt_hit_record) == sizeof(HitRecord), "hit record layout");
+    return read_back(g.d_rec, (size_t)g.cfg.width * g.cfg.height * sizeof(HitRecord), out, capacity);
+}
+extern "C" int64_t vt_read_color(uint8_t* rgba8, size_t capacity) {
+    return read_back(g.d_color, (size_t)g.cfg.width * g.cfg.height * 4, rgba8, capacity);
+}
+extern "C" int64_t vt_read_depth(float* depth, size_t capacity) {
+    return read_back(g.d_depth, (size_t)g.cfg.width * g.cfg.height * 4, depth, capacity);
+}
+extern "C" int64_t vt_read_accum(uint64_t* accum, size_t capacity) {
+    return read_back(g.d_accum, (size_t)g.cfg.width * g.cfg.height * 24, accum, capacity);
+}
+
+extern "C" void* vt_accum_device_ptr(void) { return g.inited ? (void*)g.d_accum : nullptr; }
+
+extern "C" int32_t vt_clear_accum(void) {
+    if (!g.inited) return -1;
+    CK(cudaSetDevice(g.device));
+    CK(cudaMemsetAsync(g.d_accum, 0, (size_t)g.cfg.width * g.cfg.height * 24, g.stream));
+    return 0;
+}
+
+extern "C" int32_t vt_resolve(void) {
+    if (!g.inited) return -1;
+    CK(cudaSetDevice(g.device));
+    const uint32_t total = g.cfg.total_spp ? g.cfg.total_spp : g.cfg.spp;
+    SrgbTables lut{g.d_dec, g.d_thr};
+    CK(launch_resolve(g.d_accum, g.cfg.width * g.cfg.height, total ? total : 1, lut, g.d_color, g.stream));
+    g.stats.launches += 1;
+    return 0;
+}
+
+extern "C" int32_t vt_set_stream(void* cuda_stream) {
+    if (!g.inited) return -1;
+    CK(cudaSetDevice(g.device));
+    if (finish_frame()) return -1;
+    CK(cudaStreamSynchronize(g.stream));
+    g.stream = cuda_stream ? (cudaStream_t)cuda_stream : g.own_stream;
+    return 0;
+}
+
+extern "C" int32_t vt_get_stats(vt_stats* out) {
+    if (!g.inited || !out) return -1;
+    *out = g.stats;
+    return 0;
+}
+
+extern "C" int32_t vt_set_user_input(const user_input* in) {
+    if (!in) return -1;
+    g.input = *in;
+    return 0;
+}
+
+extern "C" const char* vt_last_error(void) { return g.err; }
+
+static_assert(sizeof(user_input) == 40, "UserInput is 40 bytes (src/render.rs:37-51)");
+static_assert(sizeof(render_tick_info) == 2 * sizeof(void*), "RenderTickInfo is two pointers (src/render.rs:177-181)");
+static_assert(sizeof(vt_hit_record) == 16, "hit record is 16 bytes");
