@@ -95,6 +95,7 @@ void cleanup(void);
 #define VT_FLAG_VIEWPORT_H_IS_W 1u /* reproduce lib/command.c:80-81 (viewport height = width)  */
 #define VT_FLAG_NO_HIT_RECORDS 2u  /* do not write the per-pixel hit records                    */
 #define VT_FLAG_FORCE_GLOBAL_MASKS 4u /* keep traversal masks in global memory (no smem staging) */
+#define VT_FLAG_GENERIC_PATHS 8u   /* PATHS: use the general (multi-instance) kernel even for one instance */
 
 /* Per-pixel derived hit record (not an output of the reference). 16 bytes. */
 typedef struct vt_hit_record {
@@ -117,7 +118,7 @@ typedef struct vt_config {
     uint32_t sample_stride;   /* PATHS: distance between its samples (= number of ranks)          */
     uint32_t total_spp;       /* PATHS: spp over all ranks, the divisor used by vt_resolve        */
     int32_t max_frames;       /* render_tick returns -1 after this many frames; <= 0: never       */
-    int32_t device;           /* CUDA device ordinal; < 0: keep (LOCAL_RANK, else 0)              */
+    int32_t device;           /* read-only: CUDA device chosen by entry() (VT_DEVICE, LOCAL_RANK, 0) */
 } vt_config;
 
 typedef struct vt_stats {
@@ -151,6 +152,9 @@ int64_t vt_read_accum(uint64_t* accum, size_t capacity); /* PATHS: 3 x u64 per p
 /* PATHS multi-process plumbing: the accumulation buffer lives in device memory; a launcher
  * reduces it across ranks (NCCL sum over 3*w*h uint64) and then resolves it to colour. */
 void* vt_accum_device_ptr(void);
+/* Use caller-owned device memory (3 * width * height uint64, e.g. a launcher's tensor that it
+ * hands to NCCL) as the accumulation buffer; NULL returns to the library's own. */
+int32_t vt_set_accum_buffer(void* device_ptr);
 int32_t vt_clear_accum(void);
 int32_t vt_resolve(void);
 /* Run on a caller-provided cudaStream_t (e.g. the launcher's current stream); NULL = own. */

@@ -198,6 +198,7 @@ typedef struct {
     mat4 P, V, Pi, Vi, Vci, RD, PV;
     float eye[3];
     float vw, vh;
+    float sxn, syn; /* 2/vw, 2/vh: pixel -> NDC scale */
     int width, height;
 } frame_uniforms;
 
@@ -227,6 +228,8 @@ static void frame_setup(frame_uniforms* F, const float* P, const float* V, int w
     F->width = width; F->height = height;
     F->vw = (float)width;                     /* lib/command.c:80 */
     F->vh = (flags & VO_FLAG_VIEWPORT_H_IS_W) ? (float)width : (float)height; /* lib/command.c:81 */
+    F->sxn = 2.0f / F->vw;
+    F->syn = 2.0f / F->vh;
 }
 
 static void inst_setup(inst_uniforms* I, const frame_uniforms* F, const vo_scene* s, const float* m16) {
@@ -419,8 +422,8 @@ static void run_fragment(const frame_uniforms* F, const inst_uniforms* I, float 
     f->dda.steps = 0;
     if (!I->valid) return;
     /* NDC of the sample point, no Y flip anywhere */
-    float x_ndc = (fx * 2.0f) / F->vw - 1.0f;
-    float y_ndc = (fy * 2.0f) / F->vh - 1.0f;
+    float x_ndc = fx * F->sxn - 1.0f;
+    float y_ndc = fy * F->syn - 1.0f;
     float d[3];
     for (int k = 0; k < 3; ++k) d[k] = (I->dirm[0][k] * x_ndc + I->dirm[1][k] * y_ndc) + I->dirm[3][k];
     float tn;
@@ -627,10 +630,11 @@ static void trace_path(const frame_uniforms* F, const inst_uniforms* I, uint32_t
         int a = (lm & 1u) ? 0 : ((lm & 2u) ? 1 : 2);
         float t = r->steps ? r->side[a] - r->delta[a] : 0.0f;
         int nsign = r->step[a] != 0 ? -r->step[a] : (r->pos[a] <= 0.5f * size[a] ? -1 : 1);
+        float tl = t / r->len;
         float p0[3];
         int32_t sv[3];
         for (int k = 0; k < 3; ++k) {
-            float p = r->pos[k] + (r->dir[k] / r->len) * t;
+            float p = r->pos[k] + r->dir[k] * tl;
             float lo = (float)r->voxel[k], hi = (float)(r->voxel[k] + 1);
             p = p < lo ? lo : p;
             p = p > hi ? hi : p;
@@ -648,8 +652,8 @@ static void trace_path(const frame_uniforms* F, const inst_uniforms* I, uint32_t
             dn[0] = dn[1] = dn[2] = 0.0f;
             dn[a] = (float)nsign;
         } else {
-            float l = sqrtf(l2);
-            dn[0] /= l; dn[1] /= l; dn[2] /= l;
+            float rl = 1.0f / sqrtf(l2);
+            dn[0] *= rl; dn[1] *= rl; dn[2] *= rl;
         }
         *rays += 1;
         path_hit next;

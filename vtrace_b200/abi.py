@@ -14,7 +14,7 @@ from . import build as _build
 
 VT_MISS = 0xFFFFFFFF
 MODE_PRIMARY, MODE_PATHS = 0, 1
-FLAG_VIEWPORT_H_IS_W, FLAG_NO_HIT_RECORDS, FLAG_FORCE_GLOBAL_MASKS = 1, 2, 4
+FLAG_VIEWPORT_H_IS_W, FLAG_NO_HIT_RECORDS, FLAG_FORCE_GLOBAL_MASKS, FLAG_GENERIC_PATHS = 1, 2, 4, 8
 
 HIT_DTYPE = np.dtype([("hit_voxel", "<u4"), ("packed", "<u4"), ("instance", "<u4"), ("iters", "<u4")])
 
@@ -62,6 +62,7 @@ SYMBOLS = {
     "vt_read_depth": (_i64, [_vp, _sz]),
     "vt_read_accum": (_i64, [_vp, _sz]),
     "vt_accum_device_ptr": (_vp, []),
+    "vt_set_accum_buffer": (_i32, [_vp]),
     "vt_clear_accum": (_i32, []),
     "vt_resolve": (_i32, []),
     "vt_set_stream": (_i32, [_vp]),

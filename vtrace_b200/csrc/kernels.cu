@@ -25,15 +25,19 @@ namespace vt {
 
 #define VT_FLAG_VIEWPORT_H_IS_W 1u
 #define VT_FLAG_NO_HIT_RECORDS 2u
+#define VT_FLAG_GENERIC_PATHS 8u
 #define VT_MISS 0xFFFFFFFFu
 
-static constexpr int kBlockThreads = 256; // 8 warps; each warp owns an 8x4 pixel tile
-static constexpr int kTileW = 32, kTileH = 8; // CTA tile = 4x2 warps
+static constexpr int kBlockThreads = 256; // 8 warps
+static constexpr int kTileW = 8, kTileH = 4; // one warp = one 8x4 pixel tile, so neighbouring lanes trace neighbouring rays
 
 // -------------------------------------------------------------------------------------------
-// dynamic shared memory layout: [0,16) mbarrier | [16, 16+1024) sRGB decode LUT | masks
+// dynamic shared memory layout:
+//   [0,16) mbarrier | [16,1040) sRGB decode LUT | [1040,4112) per-warp radiance accumulators | masks
 static constexpr uint32_t kSmemLutOff = 16;
-static constexpr uint32_t kSmemMaskOff = 16 + 1024;
+static constexpr uint32_t kSmemAccOff = 16 + 1024;
+static constexpr uint32_t kSmemMaskOff = kSmemAccOff + (kBlockThreads / 32) * 32 * 3 * 4;
+static_assert(kSmemMaskOff % 16 == 0, "bulk copy destination must be 16-byte aligned");
 
 size_t trace_smem_bytes(uint32_t arena_words, bool masks_in_smem) {
     return kSmemMaskOff + (masks_in_smem ? size_t(arena_words) * 4 : 0);
@@ -180,19 +184,20 @@ __global__ void instance_setup_kernel(const float* __restrict__ instances, uint3
     I.tex = __float_as_uint(M[15]); // trace.vert:38 floatBitsToInt(model[3][3])
     M[15] = 1.0f;                   // trace.vert:39-40
     I.valid = I.tex < fp.n_volumes ? 1u : 0u;
-    I.pad[0] = I.pad[1] = I.pad[2] = 0;
-    I.pad2 = 0;
+    I.pad = 0;
     if (!I.valid) {
-        I.w = I.h = I.d = I.xb = I.yb = I.mask_off = 0;
+        I.w = I.h = I.d = I.xb = I.yb = I.mask_off = I.remap_identity = 0;
         I.rgba = nullptr;
         for (int k = 0; k < 16; ++k) I.MVP[k] = 0.0f;
         for (int k = 0; k < 12; ++k) I.Mi[k] = I.M[k] = I.dirm[k] = 0.0f;
-        I.eye_m[0] = I.eye_m[1] = I.eye_m[2] = 0.0f;
+        for (int k = 0; k < 3; ++k) I.eye_m[k] = I.slab_lo[k] = I.slab_hi[k] = 0.0f;
+        I.bounds[0] = 1; I.bounds[1] = 0; I.bounds[2] = 1; I.bounds[3] = 0; // empty
         out[i] = I;
         return;
     }
     const VolumeDesc v = volumes[I.tex];
     I.w = v.w; I.h = v.h; I.d = v.d; I.xb = v.xb; I.yb = v.yb; I.mask_off = v.mask_off; I.rgba = v.rgba;
+    I.remap_identity = v.remap_identity;
     mat4_inverse(M, Mi); // trace.frag:65
     // MVP = (P V) * M
     for (int j = 0; j < 4; ++j)
@@ -205,8 +210,40 @@ __global__ void instance_setup_kernel(const float* __restrict__ instances, uint3
             I.M[c * 3 + r] = M[c * 4 + r];
             I.dirm[c * 3 + r] = (Mi[0 * 4 + r] * fp.RD[c * 4 + 0] + Mi[1 * 4 + r] * fp.RD[c * 4 + 1]) + Mi[2 * 4 + r] * fp.RD[c * 4 + 2];
         }
-    for (int r = 0; r < 3; ++r)
+    for (int r = 0; r < 3; ++r) {
         I.eye_m[r] = ((Mi[0 * 4 + r] * fp.eye[0] + Mi[1 * 4 + r] * fp.eye[1]) + Mi[2 * 4 + r] * fp.eye[2]) + Mi[3 * 4 + r] * 1.0f;
+        I.slab_lo[r] = -0.5f - I.eye_m[r];
+        I.slab_hi[r] = 0.5f - I.eye_m[r];
+    }
+    // Conservative screen rectangle of the proxy cube (what the rasteriser would bin): project the 8
+    // corners, +-2 pixels of slack.  Any corner at or behind the eye plane -> whole screen.  A pixel
+    // outside the rectangle cannot be covered for any sample position inside it, so the trace kernels
+    // may skip the instance (and, when no instance remains, the pixel) without changing any result.
+    float minx = INFINITY, maxx = -INFINITY, miny = INFINITY, maxy = -INFINITY;
+    bool whole = false;
+    for (int c = 0; c < 8; ++c) {
+        const float cx = (c & 1) ? 0.5f : -0.5f, cy = (c & 2) ? 0.5f : -0.5f, cz = (c & 4) ? 0.5f : -0.5f;
+        const float X = ((I.MVP[0] * cx + I.MVP[4] * cy) + I.MVP[8] * cz) + I.MVP[12];
+        const float Y = ((I.MVP[1] * cx + I.MVP[5] * cy) + I.MVP[9] * cz) + I.MVP[13];
+        const float W = ((I.MVP[3] * cx + I.MVP[7] * cy) + I.MVP[11] * cz) + I.MVP[15];
+        if (!(W > 1e-6f)) { whole = true; break; }
+        const float fx = (X / W + 1.0f) / fp.sxn, fy = (Y / W + 1.0f) / fp.syn;
+        if (!(fx == fx) || !(fy == fy)) { whole = true; break; }
+        minx = fminf(minx, fx); maxx = fmaxf(maxx, fx);
+        miny = fminf(miny, fy); maxy = fmaxf(maxy, fy);
+    }
+    if (whole) {
+        I.bounds[0] = 0; I.bounds[1] = fp.width - 1; I.bounds[2] = 0; I.bounds[3] = fp.height - 1;
+    } else {
+        const float lim = 1.0e9f;
+        minx = fmaxf(minx, -lim); maxx = fminf(maxx, lim); miny = fmaxf(miny, -lim); maxy = fminf(maxy, lim);
+        int x0 = __float2int_rd(minx) - 2, x1 = __float2int_rd(maxx) + 2;
+        int y0 = __float2int_rd(miny) - 2, y1 = __float2int_rd(maxy) + 2;
+        I.bounds[0] = x0 < 0 ? 0 : x0;
+        I.bounds[1] = x1 > fp.width - 1 ? fp.width - 1 : x1;
+        I.bounds[2] = y0 < 0 ? 0 : y0;
+        I.bounds[3] = y1 > fp.height - 1 ? fp.height - 1 : y1;
+    }
     out[i] = I;
 }
 
@@ -220,7 +257,9 @@ cudaError_t launch_instance_setup(const float* instances, uint32_t n, const Volu
 // -------------------------------------------------------------------------------------------
 // rasteriser restatement: which point of the proxy cube's front faces covers the sample
 
-__device__ __forceinline__ bool slab_unit_cube(const float o[3], const float d[3], float& tn_out, int& axis_out) {
+// lo[k] = -0.5 - o[k], hi[k] = 0.5 - o[k] (precomputed per instance for camera rays)
+__device__ __forceinline__ bool slab_unit_cube(const float o[3], const float lo3[3], const float hi3[3], const float d[3],
+                                               float& tn_out, int& axis_out) {
     float tn = -INFINITY, tf = INFINITY;
     int axis = -1;
 #pragma unroll
@@ -230,8 +269,8 @@ __device__ __forceinline__ bool slab_unit_cube(const float o[3], const float d[3
             continue;
         }
         const float inv = 1.0f / d[k];
-        const float t1 = (-0.5f - o[k]) * inv;
-        const float t2 = (0.5f - o[k]) * inv;
+        const float t1 = lo3[k] * inv;
+        const float t2 = hi3[k] * inv;
         const float lo = t1 < t2 ? t1 : t2;
         const float hi = t1 < t2 ? t2 : t1;
         if (lo > tn) { tn = lo; axis = k; }
@@ -282,9 +321,11 @@ __device__ __forceinline__ uint32_t mask_word(const Vol& vol, uint32_t word) {
         return __ldg(vol.arena + vol.mask_off + word);
 }
 
-template <bool kSmem>
-__device__ __forceinline__ void dda_march(const Vol& vol, const float pos[3], const float dir[3], bool has_start,
-                                          const int32_t sv[3], Dda& r) {
+enum DdaMode { kDdaDone = 0, kDdaFast = 1, kDdaSlow = 2 };
+
+// trace.frag:63-71: ray state.  Returns how the march has to run and the start voxel's bit index.
+__device__ __forceinline__ DdaMode dda_init(const Vol& vol, const float pos[3], const float dir[3], bool has_start,
+                                            const int32_t sv[3], Dda& r, uint32_t& idx) {
     const int32_t isz[3] = {(int32_t)vol.w, (int32_t)vol.h, (int32_t)vol.d};
     const float size[3] = {(float)isz[0], (float)isz[1], (float)isz[2]};
     float sgn[3];
@@ -302,59 +343,69 @@ __device__ __forceinline__ void dda_march(const Vol& vol, const float pos[3], co
     r.steps = 0;
     r.last_mask = 0;
     r.hit = false;
-    const uint32_t xb = vol.xb, zb = vol.xb + vol.yb;
+    idx = 0;
     // the start voxel must lie inside the padded mask (true for every caller: primary rays start
     // inside the volume, bounce rays start at most one voxel outside it)
     const bool in_pad = r.v[0] >= -1 && r.v[0] <= isz[0] && r.v[1] >= -1 && r.v[1] <= isz[1] && r.v[2] >= -1 && r.v[2] <= isz[2];
-    if (!in_pad) return;
-    uint32_t idx = (uint32_t)(r.v[0] + 1) | ((uint32_t)(r.v[1] + 1) << xb) | ((uint32_t)(r.v[2] + 1) << zb);
+    if (!in_pad) return kDdaDone;
+    idx = (uint32_t)(r.v[0] + 1) | ((uint32_t)(r.v[1] + 1) << vol.xb) | ((uint32_t)(r.v[2] + 1) << (vol.xb + vol.yb));
     const bool finite = isfinite(r.delta[0]) && isfinite(r.delta[1]) && isfinite(r.delta[2]) && isfinite(r.side[0]) &&
                         isfinite(r.side[1]) && isfinite(r.side[2]);
-    if (finite) {
-        // Fast path.  No NaN/inf anywhere, so `side <= min(other two)` is two ordered compares,
-        // `vec3(mask) * delta` is a predicated add, every iteration advances >= 1 voxel (so the
-        // steps < W+H+D bound of :74-75 can never bind), and leaving the volume lands on a set
-        // border bit of the stop mask — no coordinate compares inside the loop.
-        float sx = r.side[0], sy = r.side[1], sz = r.side[2];
-        const float dx = r.delta[0], dy = r.delta[1], dz = r.delta[2];
-        const uint32_t ix = (uint32_t)r.step[0], iy = (uint32_t)r.step[1] << xb, iz = (uint32_t)r.step[2] << zb;
-        uint32_t prev = idx, steps = 0;
-        for (;;) {
-            const uint32_t wv = mask_word<kSmem>(vol, idx >> 5);
-            if ((wv >> (idx & 31u)) & 1u) break;
-            const bool mx = (sx <= sy) && (sx <= sz); // :83
-            const bool my = (sy <= sz) && (sy <= sx);
-            const bool mz = (sz <= sx) && (sz <= sy);
-            prev = idx;
-            if (mx) { sx += dx; idx += ix; } // :84-85
-            if (my) { sy += dy; idx += iy; }
-            if (mz) { sz += dz; idx += iz; }
-            ++steps; // :86
-        }
-        r.side[0] = sx; r.side[1] = sy; r.side[2] = sz;
-        r.steps = steps;
-        r.v[0] = (int32_t)(idx & ((1u << xb) - 1u)) - 1;
-        r.v[1] = (int32_t)((idx >> xb) & ((1u << vol.yb) - 1u)) - 1;
-        r.v[2] = (int32_t)(idx >> zb) - 1;
-        r.hit = r.v[0] >= 0 && r.v[0] < isz[0] && r.v[1] >= 0 && r.v[1] < isz[1] && r.v[2] >= 0 && r.v[2] < isz[2];
-        if (steps) {
-            // axes advanced by the last iteration, recovered from the index delta
-            const int32_t diff = (int32_t)(idx - prev);
-            const int32_t qz = (diff + (1 << (zb - 1))) >> zb;
-            const int32_t rem = diff - (qz << zb);
-            const int32_t qy = (rem + (1 << (xb - 1))) >> xb;
-            const int32_t qx = rem - (qy << xb);
-            r.last_mask = (qx != 0 ? 1u : 0u) | (qy != 0 ? 2u : 0u) | (qz != 0 ? 4u : 0u);
-        }
-        return;
+    return finite ? kDdaFast : kDdaSlow;
+}
+
+// One fast-path iteration (trace.frag:76-86) on scalar state; returns false when the walk stops.
+// Fast path = no NaN/inf anywhere, so `side <= min(other two)` is two ordered compares,
+// `vec3(mask) * delta` is a predicated add, every iteration advances >= 1 voxel (so the
+// steps < W+H+D bound of :74-75 can never bind), and leaving the volume lands on a set border
+// bit of the stop mask — no coordinate compares inside the loop.
+template <bool kSmem>
+__device__ __forceinline__ bool dda_step(const Vol& vol, float& sx, float& sy, float& sz, float dx, float dy, float dz,
+                                         uint32_t& idx, uint32_t& prev, uint32_t& steps, uint32_t ix, uint32_t iy, uint32_t iz) {
+    const uint32_t wv = mask_word<kSmem>(vol, idx >> 5);
+    if ((wv >> (idx & 31u)) & 1u) return false;
+    // :83 mask = side <= min(other two).  Without NaNs that is side == min(all three).
+    const float m = fminf(fminf(sx, sy), sz);
+    const bool mx = sx == m, my = sy == m, mz = sz == m;
+    prev = idx;
+    if (mx) { sx += dx; idx += ix; } // :84-85
+    if (my) { sy += dy; idx += iy; }
+    if (mz) { sz += dz; idx += iz; }
+    ++steps; // :86
+    return true;
+}
+
+// After the fast walk stopped at bit index `idx`: exit voxel, hit flag, axes of the last iteration.
+__device__ __forceinline__ void dda_finish_fast(const Vol& vol, Dda& r, uint32_t idx, uint32_t prev, uint32_t steps) {
+    const uint32_t xb = vol.xb, zb = vol.xb + vol.yb;
+    r.steps = steps;
+    r.v[0] = (int32_t)(idx & ((1u << xb) - 1u)) - 1;
+    r.v[1] = (int32_t)((idx >> xb) & ((1u << vol.yb) - 1u)) - 1;
+    r.v[2] = (int32_t)(idx >> zb) - 1;
+    r.hit = r.v[0] >= 0 && r.v[0] < (int32_t)vol.w && r.v[1] >= 0 && r.v[1] < (int32_t)vol.h && r.v[2] >= 0 && r.v[2] < (int32_t)vol.d;
+    r.last_mask = 0;
+    if (steps) {
+        // axes advanced by the last iteration, recovered from the index delta
+        const int32_t diff = (int32_t)(idx - prev);
+        const int32_t qz = (diff + (1 << (zb - 1))) >> zb;
+        const int32_t rem = diff - (qz << zb);
+        const int32_t qy = (rem + (1 << (xb - 1))) >> xb;
+        const int32_t qx = rem - (qy << xb);
+        r.last_mask = (qx != 0 ? 1u : 0u) | (qy != 0 ? 2u : 0u) | (qz != 0 ? 4u : 0u);
     }
-    // Slow path: a direction component is exactly 0 (delta = inf, and 0 * inf = NaN from the first
-    // non-advancing iteration on) or something is NaN.  Literal transcription, including the
-    // steps < max_steps bound which CAN bind here.
+}
+
+// Slow path: a direction component is exactly 0 (delta = inf, and 0 * inf = NaN from the first
+// non-advancing iteration on) or something is NaN.  Literal transcription, including the
+// steps < max_steps bound which CAN bind here.
+template <bool kSmem>
+__device__ __noinline__ void dda_slow_impl(const Vol& vol, Dda& r) {
+    const int32_t isz[3] = {(int32_t)vol.w, (int32_t)vol.h, (int32_t)vol.d};
+    const uint32_t xb = vol.xb, zb = vol.xb + vol.yb;
     const uint32_t max_steps = vol.w + vol.h + vol.d; // :74
     while (r.steps < max_steps && r.v[0] >= 0 && r.v[1] >= 0 && r.v[2] >= 0 && r.v[0] < isz[0] && r.v[1] < isz[1] &&
            r.v[2] < isz[2]) { // :75
-        idx = (uint32_t)(r.v[0] + 1) | ((uint32_t)(r.v[1] + 1) << xb) | ((uint32_t)(r.v[2] + 1) << zb);
+        const uint32_t idx = (uint32_t)(r.v[0] + 1) | ((uint32_t)(r.v[1] + 1) << xb) | ((uint32_t)(r.v[2] + 1) << zb);
         const uint32_t wv = mask_word<kSmem>(vol, idx >> 5);
         if ((wv >> (idx & 31u)) & 1u) { r.hit = true; return; } // :78-80
         const bool m0 = r.side[0] <= vt_fmin(r.side[1], r.side[2]); // :83
@@ -371,11 +422,42 @@ __device__ __forceinline__ void dda_march(const Vol& vol, const float pos[3], co
     }
 }
 
+// Out-of-line so the rare slow path costs the callers no registers; it works on stack copies so the
+// callers' own ray state never has its address taken (and stays in registers).
+template <bool kSmem>
+__device__ __forceinline__ void dda_slow(const Vol& vol, Dda& r) {
+    Dda tmp = r;
+    Vol v = vol;
+    dda_slow_impl<kSmem>(v, tmp);
+    r = tmp;
+}
+
+template <bool kSmem>
+__device__ __forceinline__ void dda_march(const Vol& vol, const float pos[3], const float dir[3], bool has_start,
+                                          const int32_t sv[3], Dda& r) {
+    uint32_t idx;
+    const DdaMode mode = dda_init(vol, pos, dir, has_start, sv, r, idx);
+    if (mode == kDdaFast) {
+        float sx = r.side[0], sy = r.side[1], sz = r.side[2];
+        const uint32_t ix = (uint32_t)r.step[0], iy = (uint32_t)r.step[1] << vol.xb, iz = (uint32_t)r.step[2] << (vol.xb + vol.yb);
+        uint32_t prev = idx, steps = 0;
+        while (dda_step<kSmem>(vol, sx, sy, sz, r.delta[0], r.delta[1], r.delta[2], idx, prev, steps, ix, iy, iz)) {}
+        r.side[0] = sx; r.side[1] = sy; r.side[2] = sz;
+        dda_finish_fast(vol, r, idx, prev, steps);
+    } else if (mode == kDdaSlow) {
+        dda_slow<kSmem>(vol, r);
+    }
+}
+
 // texel colour at the hit voxel (the only volume-texel read of a ray)
-__device__ __forceinline__ uchar4 fetch_texel(const uint8_t* rgba, uint32_t W, uint32_t H, uint32_t D, const int32_t v[3]) {
-    const int32_t tx = texel_of(v[0], (float)(int32_t)W, (int32_t)W);
-    const int32_t ty = texel_of(v[1], (float)(int32_t)H, (int32_t)H);
-    const int32_t tz = texel_of(v[2], (float)(int32_t)D, (int32_t)D);
+__device__ __forceinline__ uchar4 fetch_texel(const uint8_t* rgba, uint32_t W, uint32_t H, uint32_t D, bool identity,
+                                              const int32_t v[3]) {
+    int32_t tx = v[0], ty = v[1], tz = v[2];
+    if (!identity) { // sizes where floor(fl(v/s)*s) != v for some v: apply the reference's coordinate round trip
+        tx = texel_of(v[0], (float)(int32_t)W, (int32_t)W);
+        ty = texel_of(v[1], (float)(int32_t)H, (int32_t)H);
+        tz = texel_of(v[2], (float)(int32_t)D, (int32_t)D);
+    }
     const size_t t = (size_t)tx + (size_t)W * ((size_t)ty + (size_t)H * (size_t)tz);
     return __ldg(reinterpret_cast<const uchar4*>(rgba) + t);
 }
@@ -392,23 +474,26 @@ struct Fragment {
 
 template <bool kSmem>
 __device__ __forceinline__ void run_fragment(const FrameParams& fp, const InstUniforms* __restrict__ Ip, const uint32_t* mask_base,
-                                             float fx, float fy, Fragment& f) {
+                                             int px, int py, float fx, float fy, Fragment& f) {
     f.covered = false;
     f.dda.hit = false;
     f.dda.steps = 0;
-    if (!Ip->valid) return;
+    // outside the instance's conservative screen rectangle (also empty for invalid instances)
+    if (px < Ip->bounds[0] || px > Ip->bounds[1] || py < Ip->bounds[2] || py > Ip->bounds[3]) return;
     // SURVEY.md §A.2 step 1a
-    const float x_ndc = (fx * 2.0f) / fp.vw - 1.0f;
-    const float y_ndc = (fy * 2.0f) / fp.vh - 1.0f;
-    float d[3], o[3];
+    const float x_ndc = fx * fp.sxn - 1.0f;
+    const float y_ndc = fy * fp.syn - 1.0f;
+    float d[3], o[3], lo3[3], hi3[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         d[k] = (Ip->dirm[0 * 3 + k] * x_ndc + Ip->dirm[1 * 3 + k] * y_ndc) + Ip->dirm[3 * 3 + k];
         o[k] = Ip->eye_m[k];
+        lo3[k] = Ip->slab_lo[k];
+        hi3[k] = Ip->slab_hi[k];
     }
     float tn;
     int axis;
-    if (!slab_unit_cube(o, d, tn, axis)) return;
+    if (!slab_unit_cube(o, lo3, hi3, d, tn, axis)) return;
     float mp[3];
     entry_point(o, d, tn, axis, mp);
     // trace.vert:43-45 at the covered point
@@ -482,9 +567,17 @@ __device__ __forceinline__ void stage_tables(const uint32_t* mask_arena, uint32_
     __syncthreads();
 }
 
+// Persistent warps pull work from a global counter (reset by the host before every launch):
+// tile cost varies by orders of magnitude (sky vs. volume), static striding left SMs idle.
+__device__ __forceinline__ int claim_tiles(unsigned long long* counter, int lane, int chunk) {
+    unsigned long long c = 0;
+    if (lane == 0) c = atomicAdd(counter, 1ull);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    return (int)c * chunk;
+}
+
 // -------------------------------------------------------------------------------------------
-// trace_primary_kernel: persistent CTAs over 32x8 pixel tiles; one thread per pixel,
-// lanes of a warp form an 8x4 block so neighbouring rays stay coherent.
+// trace_primary_kernel: persistent warps over 8x4 pixel tiles; one thread per pixel.
 
 template <bool kSmem>
 __global__ void __launch_bounds__(kBlockThreads) trace_primary_kernel(const __grid_constant__ FrameParams fp,
@@ -498,9 +591,8 @@ __global__ void __launch_bounds__(kBlockThreads) trace_primary_kernel(const __gr
     const int tiles_x = (fp.width + kTileW - 1) / kTileW;
     const int tiles_y = (fp.height + kTileH - 1) / kTileH;
     const int n_tiles = tiles_x * tiles_y;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int lx = (warp & 3) * 8 + (lane & 7);
-    const int ly = (warp >> 2) * 4 + (lane >> 3);
+    const int lane = threadIdx.x & 31;
+    const int lx = lane & 7, ly = lane >> 3;
 
     // clear values, lib/command.c:56-61, as stored by the sRGB target
     const uint32_t clear_r = srgb_encode(lut.threshold, 53.0f / 100.0f);
@@ -508,44 +600,50 @@ __global__ void __launch_bounds__(kBlockThreads) trace_primary_kernel(const __gr
     const uint32_t clear_b = srgb_encode(lut.threshold, 92.0f / 100.0f);
 
     unsigned long long iter_sum = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int px = (tile % tiles_x) * kTileW + lx;
-        const int py = (tile / tiles_x) * kTileH + ly;
-        if (px >= fp.width || py >= fp.height) continue;
-        const float fx = (float)px + 0.5f, fy = (float)py + 0.5f;
-        uint32_t dst[4] = {clear_r, clear_g, clear_b, 255u};
-        float zbuf = 1.0f; // lib/command.c:60
-        HitRecord rec{VT_MISS, 0u, VT_MISS, 0u};
-        for (uint32_t i = 0; i < fp.n_inst; ++i) { // draw order = instance order, lib/command.c:102
-            Fragment f;
-            run_fragment<kSmem>(fp, inst + i, mask_base, fx, fy, f);
-            if (!f.covered) continue;
-            rec.iters += f.dda.steps;
-            if (!f.dda.hit) continue;        // discard, trace.frag:89
-            if (!(f.depth < zbuf)) continue; // VK_COMPARE_OP_LESS, lib/pipeline.c:148-150
-            zbuf = f.depth;
-            const InstUniforms* Ip = inst + i;
-            const uchar4 s = fetch_texel(Ip->rgba, Ip->w, Ip->h, Ip->d, f.dda.v);
-            if (s.w == 255) {
-                // a == 1: src*1 + dst*0 == src exactly and encode(decode(c)) == c by construction
-                dst[0] = s.x; dst[1] = s.y; dst[2] = s.z; dst[3] = 255u;
-            } else {
-                // blend, lib/pipeline.c:129-137
-                const float a = (float)s.w / 255.0f;
-                const uint32_t sc[3] = {s.x, s.y, s.z};
+    // Primary rays are cheap (tens of microseconds for the whole frame), so tiles are dealt
+    // round-robin over all resident warps instead of through a scheduler atomic: neighbouring
+    // tiles (similar cost) land on different SMs, which balances as well and costs nothing.
+    const int n_warps = gridDim.x * (kBlockThreads / 32);
+    {
+        for (int tile = blockIdx.x * (kBlockThreads / 32) + (threadIdx.x >> 5); tile < n_tiles; tile += n_warps) {
+            const int px = (tile % tiles_x) * kTileW + lx;
+            const int py = (tile / tiles_x) * kTileH + ly;
+            if (px >= fp.width || py >= fp.height) continue;
+            const float fx = (float)px + 0.5f, fy = (float)py + 0.5f;
+            uint32_t dst[4] = {clear_r, clear_g, clear_b, 255u};
+            float zbuf = 1.0f; // lib/command.c:60
+            HitRecord rec{VT_MISS, 0u, VT_MISS, 0u};
+            for (uint32_t i = 0; i < fp.n_inst; ++i) { // draw order = instance order, lib/command.c:102
+                Fragment f;
+                run_fragment<kSmem>(fp, inst + i, mask_base, px, py, fx, fy, f);
+                if (!f.covered) continue;
+                rec.iters += f.dda.steps;
+                if (!f.dda.hit) continue;        // discard, trace.frag:89
+                if (!(f.depth < zbuf)) continue; // VK_COMPARE_OP_LESS, lib/pipeline.c:148-150
+                zbuf = f.depth;
+                const InstUniforms* Ip = inst + i;
+                const uchar4 s = fetch_texel(Ip->rgba, Ip->w, Ip->h, Ip->d, Ip->remap_identity != 0, f.dda.v);
+                if (s.w == 255) {
+                    // a == 1: src*1 + dst*0 == src exactly and encode(decode(c)) == c by construction
+                    dst[0] = s.x; dst[1] = s.y; dst[2] = s.z; dst[3] = 255u;
+                } else {
+                    // blend, lib/pipeline.c:129-137
+                    const float a = (float)s.w / 255.0f;
+                    const uint32_t sc[3] = {s.x, s.y, s.z};
 #pragma unroll
-                for (int c = 0; c < 3; ++c) dst[c] = srgb_encode(lut.threshold, dec[sc[c]] * a + dec[dst[c]] * (1.0f - a));
-                dst[3] = (uint32_t)__float2int_rz(floorf(a * 255.0f + 0.5f));
+                    for (int c = 0; c < 3; ++c) dst[c] = srgb_encode(lut.threshold, dec[sc[c]] * a + dec[dst[c]] * (1.0f - a));
+                    dst[3] = (uint32_t)__float2int_rz(floorf(a * 255.0f + 0.5f));
+                }
+                rec.hit_voxel = (uint32_t)f.dda.v[0] + Ip->w * ((uint32_t)f.dda.v[1] + Ip->h * (uint32_t)f.dda.v[2]);
+                rec.packed = (f.dda.steps & 0xFFFFu) | (face_bits(f.dda, f.entry_axis) << 16);
+                rec.instance = i;
             }
-            rec.hit_voxel = (uint32_t)f.dda.v[0] + Ip->w * ((uint32_t)f.dda.v[1] + Ip->h * (uint32_t)f.dda.v[2]);
-            rec.packed = (f.dda.steps & 0xFFFFu) | (face_bits(f.dda, f.entry_axis) << 16);
-            rec.instance = i;
+            const size_t p = (size_t)py * (size_t)fp.width + (size_t)px;
+            if (fb.records) *reinterpret_cast<uint4*>(fb.records + p) = make_uint4(rec.hit_voxel, rec.packed, rec.instance, rec.iters);
+            fb.color[p] = make_uchar4((unsigned char)dst[0], (unsigned char)dst[1], (unsigned char)dst[2], (unsigned char)dst[3]);
+            if (fb.depth) fb.depth[p] = zbuf;
+            iter_sum += rec.iters;
         }
-        const size_t p = (size_t)py * (size_t)fp.width + (size_t)px;
-        if (fb.records) *reinterpret_cast<uint4*>(fb.records + p) = make_uint4(rec.hit_voxel, rec.packed, rec.instance, rec.iters);
-        fb.color[p] = make_uchar4((unsigned char)dst[0], (unsigned char)dst[1], (unsigned char)dst[2], (unsigned char)dst[3]);
-        if (fb.depth) fb.depth[p] = zbuf;
-        iter_sum += rec.iters;
     }
     // one atomic per warp
 #pragma unroll
@@ -615,9 +713,11 @@ __device__ void trace_world(const FrameParams& fp, const InstUniforms* __restric
                 o[k] = ((J->Mi[0 * 3 + k] * ow[0] + J->Mi[1 * 3 + k] * ow[1]) + J->Mi[2 * 3 + k] * ow[2]) + J->Mi[3 * 3 + k];
                 d[k] = (J->Mi[0 * 3 + k] * dw[0] + J->Mi[1 * 3 + k] * dw[1]) + J->Mi[2 * 3 + k] * dw[2];
             }
+            const float lo3[3] = {-0.5f - o[0], -0.5f - o[1], -0.5f - o[2]};
+            const float hi3[3] = {0.5f - o[0], 0.5f - o[1], 0.5f - o[2]};
             float tn;
             int axis;
-            if (!slab_unit_cube(o, d, tn, axis)) continue;
+            if (!slab_unit_cube(o, lo3, hi3, d, tn, axis)) continue;
             if (have_last && !(tn > last_t || (tn == last_t && j > last_j))) continue;
             if (!found || tn < best_t) {
                 found = true; best_t = tn; best_j = j; best_axis = axis;
@@ -657,7 +757,7 @@ __device__ void trace_path(const FrameParams& fp, const InstUniforms* __restrict
     float zbuf = 1.0f;
     for (uint32_t i = 0; i < fp.n_inst; ++i) {
         Fragment f;
-        run_fragment<kSmem>(fp, inst + i, mask_base, fx, fy, f);
+        run_fragment<kSmem>(fp, inst + i, mask_base, px, py, fx, fy, f);
         if (!f.covered) continue;
         iters += f.dda.steps;
         if (!f.dda.hit || !(f.depth < zbuf)) continue;
@@ -676,7 +776,7 @@ __device__ void trace_path(const FrameParams& fp, const InstUniforms* __restrict
         }
         const InstUniforms* J = inst + cur.instance;
         const Dda& r = cur.dda;
-        const uchar4 s = fetch_texel(J->rgba, J->w, J->h, J->d, r.v);
+        const uchar4 s = fetch_texel(J->rgba, J->w, J->h, J->d, J->remap_identity != 0, r.v);
         thr[0] = thr[0] * dec[s.x];
         thr[1] = thr[1] * dec[s.y];
         thr[2] = thr[2] * dec[s.z];
@@ -688,13 +788,14 @@ __device__ void trace_path(const FrameParams& fp, const InstUniforms* __restrict
         int32_t sv[3];
         rng_sphere(rng, dn);
         int nsign = 0;
+        // the per-axis quantities of the hit face are selected without dynamic indexing
+        const float t = r.steps ? ((a == 0 ? r.side[0] : (a == 1 ? r.side[1] : r.side[2])) -
+                                   (a == 0 ? r.delta[0] : (a == 1 ? r.delta[1] : r.delta[2])))
+                                : 0.0f;
+        const float tl = t / r.len;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            // the per-axis quantities of the hit face are selected without dynamic indexing
-            const float t = r.steps ? ((a == 0 ? r.side[0] : (a == 1 ? r.side[1] : r.side[2])) -
-                                       (a == 0 ? r.delta[0] : (a == 1 ? r.delta[1] : r.delta[2])))
-                                    : 0.0f;
-            float p = r.pos[k] + (r.dir[k] / r.len) * t;
+            float p = r.pos[k] + r.dir[k] * tl;
             const float lo = (float)r.v[k], hi = (float)(r.v[k] + 1);
             p = p < lo ? lo : p;
             p = p > hi ? hi : p;
@@ -712,8 +813,8 @@ __device__ void trace_path(const FrameParams& fp, const InstUniforms* __restrict
 #pragma unroll
             for (int k = 0; k < 3; ++k) dn[k] = (k == a) ? (float)nsign : 0.0f;
         } else {
-            const float l = sqrtf(l2);
-            dn[0] /= l; dn[1] /= l; dn[2] /= l;
+            const float rl = 1.0f / sqrtf(l2);
+            dn[0] *= rl; dn[1] *= rl; dn[2] *= rl;
         }
         rays += 1;
         PathHit next;
@@ -751,28 +852,321 @@ __global__ void __launch_bounds__(kBlockThreads) trace_paths_kernel(const __grid
     const int tiles_x = (fp.width + kTileW - 1) / kTileW;
     const int tiles_y = (fp.height + kTileH - 1) / kTileH;
     const int n_tiles = tiles_x * tiles_y;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int lx = (warp & 3) * 8 + (lane & 7);
-    const int ly = (warp >> 2) * 4 + (lane >> 3);
+    const int lane = threadIdx.x & 31;
+    const int lx = lane & 7, ly = lane >> 3;
+
+    // radiance of a path that sees only sky: thr (1,1,1) * clear colour, in 2^-24 fixed point
+    unsigned long long sky_q[3];
+    {
+        const float sky[3] = {53.0f / 100.0f, 81.0f / 100.0f, 92.0f / 100.0f};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sky_q[c] = __float2ull_rz((1.0f * sky[c]) * 16777216.0f);
+    }
 
     unsigned long long rays = 0, iters = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (;;) {
+        const int tile = claim_tiles(fb.stats + 2, lane, 1);
+        if (tile >= n_tiles) break;
         const int px = (tile % tiles_x) * kTileW + lx;
         const int py = (tile / tiles_x) * kTileH + ly;
         if (px >= fp.width || py >= fp.height) continue;
+        // Pixels outside every instance's screen rectangle: all spp paths leave through the sky after
+        // the primary segment; their sum is known without tracing them (they still count as rays).
+        bool may_hit = false;
+        for (uint32_t i = 0; i < fp.n_inst; ++i) {
+            const InstUniforms* Ip = inst + i;
+            may_hit = may_hit || !(px < Ip->bounds[0] || px > Ip->bounds[1] || py < Ip->bounds[2] || py > Ip->bounds[3]);
+        }
         unsigned long long acc[3] = {0, 0, 0};
-        for (uint32_t k = 0; k < fp.spp; ++k) {
-            float L[3];
-            trace_path<kSmem>(fp, inst, mask_base, dec, px, py, fp.sample_first + k * fp.sample_stride, L, rays, iters);
+        if (!may_hit) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float q = L[c] * 16777216.0f;
-                acc[c] += (q == q && q > 0.0f) ? __float2ull_rz(q) : 0ull;
+            for (int c = 0; c < 3; ++c) acc[c] = sky_q[c] * fp.spp;
+            rays += fp.spp;
+        } else {
+            for (uint32_t k = 0; k < fp.spp; ++k) {
+                float L[3];
+                trace_path<kSmem>(fp, inst, mask_base, dec, px, py, fp.sample_first + k * fp.sample_stride, L, rays, iters);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float q = L[c] * 16777216.0f;
+                    acc[c] += (q == q && q > 0.0f) ? __float2ull_rz(q) : 0ull;
+                }
             }
         }
         const size_t p = (size_t)py * (size_t)fp.width + (size_t)px;
 #pragma unroll
         for (int c = 0; c < 3; ++c) fb.accum[3 * p + c] += acc[c];
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        rays += __shfl_xor_sync(0xffffffffu, rays, o);
+        iters += __shfl_xor_sync(0xffffffffu, iters, o);
+    }
+    if (lane == 0) {
+        if (rays) atomicAdd(fb.stats + 0, rays);
+        if (iters) atomicAdd(fb.stats + 1, iters);
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// trace_paths_single_kernel: the path tracer for single-instance scenes (BASELINE configs[2]).
+//
+// Same paths, same arithmetic, same results as trace_path() above — but scheduled for SIMT
+// efficiency.  In the per-pixel kernel a warp's lanes spend most of the DDA loop masked off
+// (rays of one warp need 0..100+ iterations; ncu: 11.5 of 32 lanes active).  Here a warp owns an
+// 8x4 tile and a pool of jobs = (covered pixel, sample); lanes are persistent workers:
+//   * lanes whose ray stopped wait (masked) until fewer than `refill_threshold` lanes are still
+//     marching — i.e. until most of the warp is idle; then all stopped lanes shade, bounce or fetch their next job
+//     (ballot + popc hand out consecutive job numbers) and the warp re-enters the loop packed;
+//   * radiance goes to per-warp shared-memory accumulators with integer atomics — fixed point,
+//     so the order in which lanes finish cannot change a single bit of the result;
+//   * everything stays in the instance's voxel space (one instance: a ray that leaves the
+//     volume can only see the sky).
+// RNG streams are keyed by (pixel, sample) only, so results do not depend on which lane ran what.
+static constexpr uint32_t kSppChunk = 128;  // samples per pool: keeps 2^-24 fixed-point sums inside u32
+
+template <bool kSmem>
+__global__ void __launch_bounds__(kBlockThreads, 2) trace_paths_single_kernel(const __grid_constant__ FrameParams fp,
+                                                                            const InstUniforms* __restrict__ inst,
+                                                                            const uint32_t* __restrict__ mask_arena,
+                                                                            uint32_t arena_words, SrgbTables lut, FrameBuffers fb) {
+    stage_tables<kSmem>(mask_arena, arena_words, lut.decode);
+    const float* dec = reinterpret_cast<const float*>(vt_smem + kSmemLutOff);
+    const InstUniforms* Ip = inst; // the one instance
+    const Vol vol{Ip->w, Ip->h, Ip->d, Ip->xb, Ip->yb, Ip->mask_off, mask_arena};
+    const float size[3] = {(float)(int32_t)Ip->w, (float)(int32_t)Ip->h, (float)(int32_t)Ip->d};
+    const uint32_t xb = vol.xb, zb = vol.xb + vol.yb;
+
+    const int tiles_x = (fp.width + kTileW - 1) / kTileW;
+    const int tiles_y = (fp.height + kTileH - 1) / kTileH;
+    const int n_tiles = tiles_x * tiles_y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t* wacc = reinterpret_cast<uint32_t*>(vt_smem + kSmemAccOff) + warp * 96;
+
+    const float sky[3] = {53.0f / 100.0f, 81.0f / 100.0f, 92.0f / 100.0f}; // lib/command.c:57-59
+    unsigned long long rays = 0, iters = 0;
+
+    for (;;) {
+        const int tile = claim_tiles(fb.stats + 2, lane, 1);
+        if (tile >= n_tiles) break;
+        const int tx0 = (tile % tiles_x) * kTileW, ty0 = (tile / tiles_x) * kTileH;
+        const int my_px = tx0 + (lane & 7), my_py = ty0 + (lane >> 3);
+        const bool in_frame = my_px < fp.width && my_py < fp.height;
+        const bool may_hit = in_frame && !(my_px < Ip->bounds[0] || my_px > Ip->bounds[1] || my_py < Ip->bounds[2] || my_py > Ip->bounds[3]);
+        const uint32_t cov = __ballot_sync(0xffffffffu, may_hit);
+        if (in_frame && !may_hit) { // sees only sky, for every sample
+            const size_t p = (size_t)my_py * (size_t)fp.width + (size_t)my_px;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) fb.accum[3 * p + c] += __float2ull_rz((1.0f * sky[c]) * 16777216.0f) * fp.spp;
+            rays += fp.spp;
+        }
+        if (!cov) continue;
+        const uint32_t ncov = __popc(cov);
+
+        for (uint32_t s0 = 0; s0 < fp.spp; s0 += kSppChunk) {
+            const uint32_t ns = fp.spp - s0 < kSppChunk ? fp.spp - s0 : kSppChunk;
+            const uint32_t njobs = ncov * ns;
+            uint32_t next = 0;
+            wacc[lane * 3 + 0] = 0; wacc[lane * 3 + 1] = 0; wacc[lane * 3 + 2] = 0;
+            __syncwarp();
+
+            // ---- per-lane worker state ----
+            bool has_path = false;   // a path is in flight on this lane
+            bool pending = false;    // its current ray has stopped (or never walked) and awaits shading
+            bool fast = false;       // ... and it stopped inside the fast walk (exit state still to be decoded)
+            bool walking = false;    // the fast walk is still going (the lane is NOT ready for shading)
+            bool reject = false;     // primary fragment that cannot pass the depth test
+            uint32_t pix = 0;        // tile-local pixel (= lane that owns it) of the current path
+            Rng rng{0, 0};
+            float thr[3] = {1.0f, 1.0f, 1.0f};
+            uint32_t bounce = 0;
+            int entry_axis = 0;
+            Dda r;                   // ray state (registers)
+            r.hit = false; r.steps = 0; r.last_mask = 0; r.len = 1.0f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { r.v[k] = 0; r.step[k] = 0; r.side[k] = r.delta[k] = r.dir[k] = r.pos[k] = 0.0f; }
+            // Walk registers.  idx == 0 is a border bit (always set), so a lane without a live ray can
+            // execute the step below as a no-op: the march loop needs no per-lane branch.
+            uint32_t idx = 0, prev = 0, steps = 0, ix = 0, iy = 0, iz = 0;
+            float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+
+            for (;;) {
+                float npos[3] = {0.0f, 0.0f, 0.0f}, ndir[3] = {0.0f, 0.0f, 0.0f};
+                int32_t nsv[3] = {0, 0, 0};
+                bool new_ray = false, new_has_start = false;
+
+                // ---- (i) lanes whose ray stopped: shade, then bounce or end the path -------------
+                if (has_path && pending && !walking) {
+                    if (fast) {
+                        r.side[0] = sx; r.side[1] = sy; r.side[2] = sz;
+                        dda_finish_fast(vol, r, idx, prev, steps);
+                        iters += steps;
+                        idx = 0; // parks the lane on a stop bit
+                    }
+                    pending = false;
+                    if (!r.hit || reject) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const float q = (thr[c] * sky[c]) * 16777216.0f;
+                            if (q == q && q > 0.0f) atomicAdd(&wacc[pix * 3 + c], (uint32_t)__float2ull_rz(q));
+                        }
+                        has_path = false;
+                    } else {
+                        const uchar4 s = fetch_texel(Ip->rgba, Ip->w, Ip->h, Ip->d, Ip->remap_identity != 0, r.v);
+                        thr[0] = thr[0] * dec[s.x];
+                        thr[1] = thr[1] * dec[s.y];
+                        thr[2] = thr[2] * dec[s.z];
+                        if (bounce == fp.bounces) {
+                            has_path = false; // path length exhausted: contributes nothing
+                        } else {
+                            ++bounce;
+                            const uint32_t lm = r.steps ? r.last_mask : (1u << entry_axis);
+                            const int a = (lm & 1u) ? 0 : ((lm & 2u) ? 1 : 2);
+                            rng_sphere(rng, ndir);
+                            int nsign = 0;
+                            const float t = r.steps ? ((a == 0 ? r.side[0] : (a == 1 ? r.side[1] : r.side[2])) -
+                                                       (a == 0 ? r.delta[0] : (a == 1 ? r.delta[1] : r.delta[2])))
+                                                    : 0.0f;
+                            const float tl = t / r.len;
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) {
+                                float p = r.pos[k] + r.dir[k] * tl;
+                                const float lo = (float)r.v[k], hi = (float)(r.v[k] + 1);
+                                p = p < lo ? lo : p;
+                                p = p > hi ? hi : p;
+                                npos[k] = p;
+                                nsv[k] = r.v[k];
+                                if (k == a) {
+                                    nsign = r.step[k] != 0 ? -r.step[k] : (r.pos[k] <= 0.5f * size[k] ? -1 : 1);
+                                    npos[k] = (float)(r.v[k] + (nsign > 0 ? 1 : 0));
+                                    nsv[k] += nsign;
+                                    ndir[k] += (float)nsign;
+                                }
+                            }
+                            const float l2 = (ndir[0] * ndir[0] + ndir[1] * ndir[1]) + ndir[2] * ndir[2];
+                            if (l2 < 1e-6f) {
+#pragma unroll
+                                for (int k = 0; k < 3; ++k) ndir[k] = (k == a) ? (float)nsign : 0.0f;
+                            } else {
+                                const float rl = 1.0f / sqrtf(l2);
+                                ndir[0] *= rl; ndir[1] *= rl; ndir[2] *= rl;
+                            }
+                            rays += 1;
+                            entry_axis = a;
+                            reject = false;
+                            new_ray = true;
+                            new_has_start = true;
+                        }
+                    }
+                }
+                // ---- (ii) lanes without a path take the next jobs of the pool --------------------
+                for (;;) {
+                    const bool need = !has_path;
+                    const uint32_t m = __ballot_sync(0xffffffffu, need);
+                    if (!m || next >= njobs) break;
+                    const uint32_t avail = njobs - next;
+                    const uint32_t rank = __popc(m & lt_mask);
+                    if (need && rank < avail) {
+                        const uint32_t job = next + rank;          // sample-major: neighbouring lanes get neighbouring pixels
+                        const uint32_t si = job / ncov, ci = job - si * ncov;
+                        pix = __fns(cov, 0, ci + 1);                // ci-th covered pixel of the tile
+                        const int px = tx0 + (int)(pix & 7u), py = ty0 + (int)(pix >> 3);
+                        const uint32_t sample = fp.sample_first + (s0 + si) * fp.sample_stride;
+                        rng_init(rng, fp.seed, (uint32_t)py * (uint32_t)fp.width + (uint32_t)px, sample);
+                        const float jx = rng_u01(rng), jy = rng_u01(rng);
+                        const float fx = (float)px + jx, fy = (float)py + jy;
+                        rays += 1;
+                        // rasteriser restatement + trace.frag prologue (same operations as run_fragment)
+                        const float x_ndc = fx * fp.sxn - 1.0f;
+                        const float y_ndc = fy * fp.syn - 1.0f;
+                        float d[3], o[3], lo3[3], hi3[3];
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            d[k] = (Ip->dirm[0 * 3 + k] * x_ndc + Ip->dirm[1 * 3 + k] * y_ndc) + Ip->dirm[3 * 3 + k];
+                            o[k] = Ip->eye_m[k];
+                            lo3[k] = Ip->slab_lo[k];
+                            hi3[k] = Ip->slab_hi[k];
+                        }
+                        float tn;
+                        int axis;
+                        bool covered = slab_unit_cube(o, lo3, hi3, d, tn, axis);
+                        float mp[3], sp[4];
+                        if (covered) {
+                            entry_point(o, d, tn, axis, mp);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                sp[i] = ((Ip->MVP[0 * 4 + i] * mp[0] + Ip->MVP[1 * 4 + i] * mp[1]) + Ip->MVP[2 * 4 + i] * mp[2]) + Ip->MVP[3 * 4 + i];
+                            covered = sp[3] > 0.0f && sp[2] >= 0.0f && sp[2] <= sp[3];
+                        }
+                        if (!covered) { // primary ray leaves through the sky
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) atomicAdd(&wacc[pix * 3 + c], (uint32_t)__float2ull_rz((1.0f * sky[c]) * 16777216.0f));
+                        } else {
+                            const float depth = sp[2] / sp[3]; // trace.frag:46
+                            float rr[3];
+#pragma unroll
+                            for (int k = 0; k < 3; ++k)
+                                rr[k] = ((fp.RD[0 * 4 + k] * sp[0] + fp.RD[1 * 4 + k] * sp[1]) + fp.RD[2 * 4 + k] * sp[2]) + fp.RD[3 * 4 + k] * sp[3];
+                            const float len = sqrtf((rr[0] * rr[0] + rr[1] * rr[1]) + rr[2] * rr[2]);
+                            const float rd[3] = {rr[0] / len, rr[1] / len, rr[2] / len};
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) {
+                                ndir[k] = ((Ip->Mi[0 * 3 + k] * rd[0] + Ip->Mi[1 * 3 + k] * rd[1]) + Ip->Mi[2 * 3 + k] * rd[2]) + Ip->Mi[3 * 3 + k] * 0.0f;
+                                npos[k] = (mp[k] + 0.5f) * size[k];
+                            }
+                            has_path = true;
+                            bounce = 0;
+                            thr[0] = thr[1] = thr[2] = 1.0f;
+                            entry_axis = axis;
+                            // VK_COMPARE_OP_LESS against the cleared 1.0: a fragment exactly on the far plane
+                            // still walks (late-Z) but cannot win
+                            reject = !(depth < 1.0f);
+                            new_ray = true;
+                            new_has_start = false;
+                        }
+                    }
+                    next += __popc(m) < avail ? __popc(m) : avail;
+                }
+                // ---- (iii) bounce rays and new primaries start their walk together (trace.frag:63-71) ---
+                if (new_ray) {
+                    const DdaMode mode = dda_init(vol, npos, ndir, new_has_start, nsv, r, idx);
+                    prev = idx; steps = 0;
+                    sx = r.side[0]; sy = r.side[1]; sz = r.side[2];
+                    ix = (uint32_t)r.step[0]; iy = (uint32_t)r.step[1] << xb; iz = (uint32_t)r.step[2] << zb;
+                    pending = true;
+                    fast = mode == kDdaFast;
+                    walking = fast;
+                    if (mode == kDdaSlow) {
+                        dda_slow<kSmem>(vol, r); // rare: runs to completion here; r.hit / r.steps / r.last_mask final
+                        iters += r.steps;
+                    }
+                    if (!fast) idx = 0;
+                }
+                // ---- done when nobody holds a path (the pool is exhausted then) -------------------
+                if (!__ballot_sync(0xffffffffu, has_path)) break;
+                // ---- (iv) march: every lane executes the step; parked lanes sit on a stop bit --------
+                {
+                    const int n0 = __popc(__ballot_sync(0xffffffffu, walking));
+                    const int thresh = n0 < (int)fp.refill_threshold ? n0 : (int)fp.refill_threshold;
+                    if (n0) {
+                        do {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                walking = dda_step<kSmem>(vol, sx, sy, sz, r.delta[0], r.delta[1], r.delta[2], idx, prev, steps, ix, iy, iz);
+                        } while (__popc(__ballot_sync(0xffffffffu, walking)) >= thresh);
+                    }
+                }
+            }
+            // ---- pool drained: add the tile's sums to the frame accumulators ---------------------
+            __syncwarp();
+            if (may_hit) {
+                const size_t p = (size_t)my_py * (size_t)fp.width + (size_t)my_px;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) fb.accum[3 * p + c] += (unsigned long long)wacc[lane * 3 + c];
+            }
+            __syncwarp();
+        }
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
@@ -805,6 +1199,8 @@ cudaError_t configure_kernels(int max_smem_optin) {
     e = cudaFuncSetAttribute(trace_primary_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(trace_paths_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(trace_paths_single_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     return e;
 }
 
@@ -835,6 +1231,16 @@ cudaError_t launch_trace_paths(const FrameParams& fp, const InstUniforms* inst, 
                                bool masks_in_smem, SrgbTables lut, FrameBuffers fb, int sm_count, cudaStream_t stream) {
     const int n_tiles = ((fp.width + kTileW - 1) / kTileW) * ((fp.height + kTileH - 1) / kTileH);
     const size_t smem = trace_smem_bytes(arena_words, masks_in_smem);
+    if (fp.n_inst == 1 && !(fp.flags & VT_FLAG_GENERIC_PATHS)) { // persistent-lane kernel for single-instance scenes
+        if (masks_in_smem) {
+            const int grid = persistent_grid(trace_paths_single_kernel<true>, smem, sm_count, n_tiles);
+            trace_paths_single_kernel<true><<<grid, kBlockThreads, smem, stream>>>(fp, inst, mask_arena, arena_words, lut, fb);
+        } else {
+            const int grid = persistent_grid(trace_paths_single_kernel<false>, smem, sm_count, n_tiles);
+            trace_paths_single_kernel<false><<<grid, kBlockThreads, smem, stream>>>(fp, inst, mask_arena, arena_words, lut, fb);
+        }
+        return cudaGetLastError();
+    }
     if (masks_in_smem) {
         const int grid = persistent_grid(trace_paths_kernel<true>, smem, sm_count, n_tiles);
         trace_paths_kernel<true><<<grid, kBlockThreads, smem, stream>>>(fp, inst, mask_arena, arena_words, lut, fb);

@@ -25,7 +25,7 @@ struct VolumeDesc {
     uint32_t xb, yb;     // log2(row bits), log2(rows per plane) of the padded stop mask
     uint32_t mask_off;   // word offset of this volume's mask inside the arena
     uint32_t mask_words; // multiple of 4 (16-byte granules for the bulk copy)
-    uint32_t pad;
+    uint32_t remap_identity; // 1 when floor(fl(v/s)*s) == v on all three axes (texel == voxel)
 };
 
 // Per-frame uniforms, passed by value as a kernel parameter (constant bank, no loads).
@@ -34,12 +34,14 @@ struct FrameParams {
     float PV[16]; // projection * camera, trace.vert:45
     float eye[3]; // inverse(camera) * (0,0,0,1), trace.frag:51
     float vw, vh; // viewport, lib/command.c:80-81
+    float sxn, syn; // 2/vw, 2/vh: pixel -> NDC scale
     int32_t width, height;
     uint32_t n_inst;
     uint32_t n_volumes;
     uint32_t flags;
     // path-tracing extension
     uint32_t spp, bounces, seed, sample_first, sample_stride;
+    uint32_t refill_threshold; // persistent-lane kernel: refill when fewer lanes than this still march
 };
 
 // Per-instance uniforms (trace.vert outputs that are flat per instance + derived matrices).
@@ -50,13 +52,16 @@ struct __align__(16) InstUniforms {
     float dirm[12];  // inverse(M)3x3 * RD rows 0-2: clip point -> model-space ray direction
     float eye_m[3];  // camera position in model space
     uint32_t valid;  // texture id in range
+    float slab_lo[3]; // -0.5 - eye_m
+    float slab_hi[3]; //  0.5 - eye_m
+    int32_t bounds[4]; // conservative screen rectangle of the proxy cube: x0, x1, y0, y1 (inclusive)
     uint32_t tex;
     uint32_t w, h, d;
     uint32_t xb, yb;
     uint32_t mask_off;
-    uint32_t pad[3];
+    uint32_t remap_identity;
+    uint32_t pad;
     const uint8_t* rgba;
-    uint64_t pad2;
 };
 
 struct HitRecord { uint32_t hit_voxel, packed, instance, iters; };
@@ -66,7 +71,7 @@ struct FrameBuffers {
     uchar4* color;
     float* depth;         // may be null
     unsigned long long* accum; // 3 per pixel
-    unsigned long long* stats; // [0] rays, [1] iterations
+    unsigned long long* stats; // [0] rays, [1] iterations, [2] tile-scheduler counter, [3] spare
 };
 
 struct SrgbTables {

@@ -52,7 +52,8 @@ struct State {
     HitRecord* d_rec = nullptr;
     uchar4* d_color = nullptr;
     float* d_depth = nullptr;
-    unsigned long long* d_accum = nullptr;
+    unsigned long long* d_accum = nullptr;     // in use (own or caller-provided)
+    unsigned long long* d_accum_own = nullptr; // the library's allocation
     unsigned long long* d_stats = nullptr;
     unsigned long long* h_stats = nullptr; // pinned
     void* h_readback = nullptr;            // pinned staging for vt_read_*
@@ -60,6 +61,7 @@ struct State {
 
     cudaEvent_t ev_begin = nullptr, ev_trace0 = nullptr, ev_trace1 = nullptr, ev_end = nullptr;
     bool frame_pending = false;
+    uint32_t refill_threshold = 8; // tuning knob of the persistent-lane kernel (VT_REFILL)
 
     vt_stats stats{};
     user_input input{};
@@ -113,13 +115,14 @@ int alloc_framebuffer() {
     const uint32_t w = g.cfg.width, h = g.cfg.height;
     if (w == g.fb_w && h == g.fb_h && g.d_color) return 0;
     CK(cudaStreamSynchronize(g.stream));
-    cudaFree(g.d_rec); cudaFree(g.d_color); cudaFree(g.d_depth); cudaFree(g.d_accum);
-    g.d_rec = nullptr; g.d_color = nullptr; g.d_depth = nullptr; g.d_accum = nullptr;
+    cudaFree(g.d_rec); cudaFree(g.d_color); cudaFree(g.d_depth); cudaFree(g.d_accum_own);
+    g.d_rec = nullptr; g.d_color = nullptr; g.d_depth = nullptr; g.d_accum = nullptr; g.d_accum_own = nullptr;
     const size_t n = (size_t)w * h;
     CK(cudaMalloc(&g.d_rec, n * sizeof(HitRecord)));
     CK(cudaMalloc(&g.d_color, n * sizeof(uchar4)));
     CK(cudaMalloc(&g.d_depth, n * sizeof(float)));
-    CK(cudaMalloc(&g.d_accum, n * 3 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&g.d_accum_own, n * 3 * sizeof(unsigned long long)));
+    g.d_accum = g.d_accum_own; // a caller-provided buffer does not survive a resize
     CK(cudaMemsetAsync(g.d_rec, 0xFF, n * sizeof(HitRecord), g.stream));
     CK(cudaMemsetAsync(g.d_color, 0, n * sizeof(uchar4), g.stream));
     CK(cudaMemsetAsync(g.d_depth, 0, n * sizeof(float), g.stream));
@@ -199,6 +202,8 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
     fp.height = (int32_t)g.cfg.height;
     fp.vw = (float)g.cfg.width;                                                              // lib/command.c:80
     fp.vh = (g.cfg.flags & VT_FLAG_VIEWPORT_H_IS_W) ? (float)g.cfg.width : (float)g.cfg.height; // lib/command.c:81
+    fp.sxn = 2.0f / fp.vw;
+    fp.syn = 2.0f / fp.vh;
     fp.n_inst = g.inst_count;
     fp.n_volumes = (uint32_t)g.vols.size();
     fp.flags = g.cfg.flags;
@@ -207,6 +212,7 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
     fp.seed = g.cfg.seed;
     fp.sample_first = g.cfg.sample_first;
     fp.sample_stride = g.cfg.sample_stride ? g.cfg.sample_stride : 1;
+    fp.refill_threshold = g.refill_threshold;
 
     if (g.vols_dirty) {
         if (g.vols.size() > g.d_vols_cap) {
@@ -222,7 +228,7 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
     if (ensure_instances(g.inst_count)) return -1;
 
     CK(cudaEventRecord(g.ev_begin, g.stream));
-    CK(cudaMemsetAsync(g.d_stats, 0, 2 * sizeof(unsigned long long), g.stream));
+    CK(cudaMemsetAsync(g.d_stats, 0, 4 * sizeof(unsigned long long), g.stream));
     CK(launch_instance_setup(g.d_inst, g.inst_count, g.d_vols, fp, g.d_iu, g.stream));
     g.stats.launches += 1;
 
@@ -326,7 +332,7 @@ extern "C" uint64_t entry(void) {
     CKE(cudaMalloc(&g.d_thr, sizeof thr));
     CKE(cudaMemcpy(g.d_dec, dec, sizeof dec, cudaMemcpyHostToDevice));
     CKE(cudaMemcpy(g.d_thr, thr, sizeof thr, cudaMemcpyHostToDevice));
-    CKE(cudaMalloc(&g.d_stats, 2 * sizeof(unsigned long long)));
+    CKE(cudaMalloc(&g.d_stats, 4 * sizeof(unsigned long long)));
     CKE(cudaMallocHost(&g.h_stats, 2 * sizeof(unsigned long long)));
     g.h_stats[0] = g.h_stats[1] = 0;
 
@@ -345,6 +351,9 @@ extern "C" uint64_t entry(void) {
     g.cfg.total_spp = env_u32("VT_TOTAL_SPP", 0);
     g.cfg.max_frames = (int32_t)env_u32("VT_MAX_FRAMES", 0);
     g.cfg.device = dev;
+    g.refill_threshold = env_u32("VT_REFILL", 8);
+    if (g.refill_threshold < 1) g.refill_threshold = 1;
+    if (g.refill_threshold > 32) g.refill_threshold = 32;
 
     g.inited = true;
     g.inst_count = 1; // lib/memory.c:236,251: an empty scene still draws one (stale, zeroed) instance
@@ -416,6 +425,19 @@ extern "C" int32_t add_texture(const uint8_t* data, uint32_t width, uint32_t hei
     v.xb = xb; v.yb = yb;
     v.mask_off = g.arena_words;
     v.mask_words = mask_words_padded;
+    // texel == voxel when the reference's coordinate round trip floor(fl(v/s)*s) is the identity
+    // (true for 16, 40, 50, 64, ...; false e.g. for 22 or 41) — lets the kernels skip three divisions per hit
+    v.remap_identity = 1;
+    {
+        const uint32_t dims[3] = {width, height, depth};
+        for (int a = 0; a < 3 && v.remap_identity; ++a) {
+            const float sz = (float)(int32_t)dims[a];
+            for (uint32_t x = 0; x < dims[a]; ++x) {
+                const float u = (float)(int32_t)x / sz;
+                if ((int32_t)floorf(u * sz) != (int32_t)x) { v.remap_identity = 0; break; }
+            }
+        }
+    }
     if (mask_words_padded > mask_words)
         CK(cudaMemsetAsync(g.d_arena + g.arena_words + mask_words, 0xFF, (size_t)(mask_words_padded - mask_words) * 4, g.stream));
     CK(launch_build_mask(d_rgba, width, height, depth, xb, yb, g.d_arena + g.arena_words, mask_words, g.stream));
@@ -455,7 +477,7 @@ extern "C" void cleanup(void) {
     for (auto& v : g.vols) cudaFree(const_cast<uint8_t*>(v.rgba));
     g.vols.clear();
     cudaFree(g.d_vols); cudaFree(g.d_arena); cudaFree(g.d_inst); cudaFree(g.d_iu); cudaFree(g.d_dec); cudaFree(g.d_thr);
-    cudaFree(g.d_rec); cudaFree(g.d_color); cudaFree(g.d_depth); cudaFree(g.d_accum); cudaFree(g.d_stats);
+    cudaFree(g.d_rec); cudaFree(g.d_color); cudaFree(g.d_depth); cudaFree(g.d_accum_own); cudaFree(g.d_stats);
     if (g.h_inst) cudaFreeHost(g.h_inst);
     if (g.h_tex_staging) cudaFreeHost(g.h_tex_staging);
     if (g.h_stats) cudaFreeHost(g.h_stats);
@@ -520,6 +542,15 @@ extern "C" int64_t vt_read_accum(uint64_t* accum, size_t capacity) {
 }
 
 extern "C" void* vt_accum_device_ptr(void) { return g.inited ? (void*)g.d_accum : nullptr; }
+
+extern "C" int32_t vt_set_accum_buffer(void* device_ptr) {
+    if (!g.inited) return -1;
+    CK(cudaSetDevice(g.device));
+    if (finish_frame()) return -1;
+    CK(cudaStreamSynchronize(g.stream));
+    g.d_accum = device_ptr ? (unsigned long long*)device_ptr : g.d_accum_own;
+    return 0;
+}
 
 extern "C" int32_t vt_clear_accum(void) {
     if (!g.inited) return -1;

@@ -199,6 +199,10 @@ class Renderer:
         if self._lib.vt_set_stream(C.c_void_p(cuda_stream_handle or 0)) != 0:
             raise RuntimeError("vt_set_stream failed: " + abi.last_error())
 
+    def set_accum_buffer(self, device_ptr: int | None):
+        if self._lib.vt_set_accum_buffer(C.c_void_p(device_ptr or 0)) != 0:
+            raise RuntimeError("vt_set_accum_buffer failed: " + abi.last_error())
+
     def accum_device_ptr(self) -> int:
         return int(self._lib.vt_accum_device_ptr() or 0)
 
