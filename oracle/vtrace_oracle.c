@@ -545,9 +545,12 @@ typedef struct {
     dda_state dda;
 } path_hit;
 
-/* nearest instance along a world-space ray, by box-entry parameter (ties: lower index);
- * the first instance in that order whose DDA hits wins.  `skip` is excluded. */
-static void trace_world(const inst_uniforms* I, uint32_t ninst, uint32_t skip, const float ow[3],
+/* nearest instance along a ray, by box-entry parameter (ties: lower index); the first instance in
+ * that order whose DDA hits wins.  `skip` is excluded.  Two kinds of ray:
+ *   camera (cam != NULL): per instance o = eye in model space, d = dirm * (x_ndc, y_ndc, 1) — the
+ *     same model-space ray the rasteriser restatement uses; cam = {x_ndc, y_ndc};
+ *   world  (cam == NULL): o = Mi * (ow,1), d = Mi * (dw,0). */
+static void trace_world(const inst_uniforms* I, uint32_t ninst, uint32_t skip, const float* cam, const float ow[3],
                         const float dw[3], path_hit* out, uint64_t* iters) {
     out->hit = 0;
     float last_t = -INFINITY;
@@ -563,8 +566,13 @@ static void trace_world(const inst_uniforms* I, uint32_t ninst, uint32_t skip, c
             if (j == skip || !I[j].valid) continue;
             float o[3], d[3];
             for (int k = 0; k < 3; ++k) {
-                o[k] = ((I[j].Mi.c[0][k] * ow[0] + I[j].Mi.c[1][k] * ow[1]) + I[j].Mi.c[2][k] * ow[2]) + I[j].Mi.c[3][k];
-                d[k] = (I[j].Mi.c[0][k] * dw[0] + I[j].Mi.c[1][k] * dw[1]) + I[j].Mi.c[2][k] * dw[2];
+                if (cam) {
+                    o[k] = I[j].eye_m[k];
+                    d[k] = (I[j].dirm[0][k] * cam[0] + I[j].dirm[1][k] * cam[1]) + I[j].dirm[3][k];
+                } else {
+                    o[k] = ((I[j].Mi.c[0][k] * ow[0] + I[j].Mi.c[1][k] * ow[1]) + I[j].Mi.c[2][k] * ow[2]) + I[j].Mi.c[3][k];
+                    d[k] = (I[j].Mi.c[0][k] * dw[0] + I[j].Mi.c[1][k] * dw[1]) + I[j].Mi.c[2][k] * dw[2];
+                }
             }
             float tn;
             int axis;
@@ -598,19 +606,12 @@ static void trace_path(const frame_uniforms* F, const inst_uniforms* I, uint32_t
     rng_init(&rng, seed, (uint32_t)py * (uint32_t)F->width + (uint32_t)px, sample);
     float jx = rng_u01(&rng), jy = rng_u01(&rng);
     float fx = (float)px + jx, fy = (float)py + jy;
-    /* primary segment: same fixed-function winner rule as the raster pass, alpha > 0 = opaque */
+    /* camera segment: the ray from the eye through the jittered sample position, traced with the
+     * same visibility rule as every later segment (nearest box entry first, alpha > 0 = opaque;
+     * a path tracer has no near/far clip planes and no proxy-depth test) */
     path_hit cur;
-    cur.hit = 0;
-    float zbuf = 1.0f;
-    for (uint32_t i = 0; i < ninst; ++i) {
-        fragment f;
-        run_fragment(F, &I[i], fx, fy, &f);
-        if (!f.covered) continue;
-        *iters += f.dda.steps;
-        if (!f.dda.hit || !(f.depth < zbuf)) continue;
-        zbuf = f.depth;
-        cur.hit = 1; cur.instance = i; cur.entry_axis = f.entry_axis; cur.dda = f.dda;
-    }
+    const float cam[2] = {fx * F->sxn - 1.0f, fy * F->syn - 1.0f};
+    trace_world(I, ninst, 0xFFFFFFFFu, cam, NULL, NULL, &cur, iters);
     *rays += 1;
     const float sky[3] = {53.0f / 100.0f, 81.0f / 100.0f, 92.0f / 100.0f}; /* lib/command.c:57-59 */
     float thr[3] = {1.0f, 1.0f, 1.0f};
@@ -670,7 +671,7 @@ static void trace_path(const frame_uniforms* F, const inst_uniforms* I, uint32_t
                 ow[k] = ((J->M.c[0][k] * pm[0] + J->M.c[1][k] * pm[1]) + J->M.c[2][k] * pm[2]) + J->M.c[3][k];
                 dw[k] = (J->M.c[0][k] * dm[0] + J->M.c[1][k] * dm[1]) + J->M.c[2][k] * dm[2];
             }
-            trace_world(I, ninst, cur.instance, ow, dw, &next, iters);
+            trace_world(I, ninst, cur.instance, NULL, ow, dw, &next, iters);
         }
         cur = next;
     }

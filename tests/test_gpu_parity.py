@@ -223,9 +223,10 @@ def test_paths_generic_kernel_on_single_instance(scene, assets):
     t = scene.add(assets["Treasure"])
     scene.set_instances([(glm.identity(), t)])
     P, V = scenes.camera(256, 160, eye=(0.9, -0.5, 0.7))
-    a, _ = scene.check_paths(P, V, 256, 160, spp=5, flags=abi.FLAG_GENERIC_PATHS, what="generic kernel")
-    b, _ = scene.check_paths(P, V, 256, 160, spp=5, flags=0, what="persistent-lane kernel")
-    c, _ = scene.check_paths(P, V, 256, 160, spp=5, flags=abi.FLAG_FORCE_GLOBAL_MASKS, what="persistent-lane kernel, global masks")
+    a, _ = scene.check_paths(P, V, 256, 160, spp=5, flags=0, what="general kernel")
+    b, _ = scene.check_paths(P, V, 256, 160, spp=5, flags=abi.FLAG_PERSISTENT_LANES, what="persistent-lane kernel")
+    c, _ = scene.check_paths(P, V, 256, 160, spp=5, flags=abi.FLAG_PERSISTENT_LANES | abi.FLAG_FORCE_GLOBAL_MASKS,
+                             what="persistent-lane kernel, global masks")
     assert np.array_equal(a, b) and np.array_equal(b, c)
 
 
@@ -234,6 +235,7 @@ def test_paths_many_samples_chunking(scene, assets):
     t = scene.add(assets["AncientTemple"])
     scene.set_instances([(glm.identity(), t)])
     P, V = scenes.camera(96, 64, eye=(0.8, -0.45, 0.6))
+    scene.check_paths(P, V, 96, 64, spp=150, bounces=2, flags=abi.FLAG_PERSISTENT_LANES, what="150 spp, persistent lanes")
     scene.check_paths(P, V, 96, 64, spp=150, bounces=2, what="150 spp")
 
 
@@ -242,6 +244,7 @@ def test_paths_axis_aligned_and_inside(scene, assets):
     scene.set_instances([(glm.identity(), t)])
     P, V = scenes.camera(161, 121, eye=(0.0, 0.0, 2.0))
     scene.check_paths(P, V, 161, 121, spp=2, what="paths axis aligned")
+    scene.check_paths(P, V, 161, 121, spp=2, flags=abi.FLAG_PERSISTENT_LANES, what="paths axis aligned, persistent lanes")
     P, V = scenes.camera(160, 120, eye=(0.1, 0.2, -0.1), center=(1.0, 0.3, 0.2))
     scene.check_paths(P, V, 160, 120, spp=2, what="paths camera inside")
 

@@ -25,7 +25,7 @@ namespace vt {
 
 #define VT_FLAG_VIEWPORT_H_IS_W 1u
 #define VT_FLAG_NO_HIT_RECORDS 2u
-#define VT_FLAG_GENERIC_PATHS 8u
+#define VT_FLAG_PERSISTENT_LANES 8u
 #define VT_MISS 0xFFFFFFFFu
 
 static constexpr int kBlockThreads = 256; // 8 warps
@@ -363,14 +363,40 @@ template <bool kSmem>
 __device__ __forceinline__ bool dda_step(const Vol& vol, float& sx, float& sy, float& sz, float dx, float dy, float dz,
                                          uint32_t& idx, uint32_t& prev, uint32_t& steps, uint32_t ix, uint32_t iy, uint32_t iz) {
     const uint32_t wv = mask_word<kSmem>(vol, idx >> 5);
-    if ((wv >> (idx & 31u)) & 1u) return false;
-    // :83 mask = side <= min(other two).  Without NaNs that is side == min(all three).
-    const float m = fminf(fminf(sx, sy), sz);
-    const bool mx = sx == m, my = sy == m, mz = sz == m;
+    // Written in PTX so the instruction selection stays put: the single-bit mask is built while the
+    // load is in flight (one LOP3 with predicate output after it), and the per-axis updates are three
+    // predicated add pairs instead of select + 3-input add chains.
+    uint32_t stop;
+    asm("{\n"
+        ".reg .u32 b;\n"
+        ".reg .pred p;\n"
+        "shf.l.wrap.b32 b, 0, 1, %2;\n"
+        "and.b32 b, b, %1;\n"
+        "setp.ne.u32 p, b, 0;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(stop)
+        : "r"(wv), "r"(idx));
+    if (stop) return false;
     prev = idx;
-    if (mx) { sx += dx; idx += ix; } // :84-85
-    if (my) { sy += dy; idx += iy; }
-    if (mz) { sz += dz; idx += iz; }
+    // :83 mask = side <= min(other two); without NaNs that is side == min(all three).  :84-85 updates.
+    asm("{\n"
+        ".reg .pred px, py, pz;\n"
+        ".reg .f32 m;\n"
+        "min.f32 m, %0, %1;\n"
+        "min.f32 m, m, %2;\n"
+        "setp.eq.f32 px, %0, m;\n"
+        "setp.eq.f32 py, %1, m;\n"
+        "setp.eq.f32 pz, %2, m;\n"
+        "@px add.rn.f32 %0, %0, %4;\n"
+        "@py add.rn.f32 %1, %1, %5;\n"
+        "@pz add.rn.f32 %2, %2, %6;\n"
+        "@px add.s32 %3, %3, %7;\n"
+        "@py add.s32 %3, %3, %8;\n"
+        "@pz add.s32 %3, %3, %9;\n"
+        "}\n"
+        : "+f"(sx), "+f"(sy), "+f"(sz), "+r"(idx)
+        : "f"(dx), "f"(dy), "f"(dz), "r"(ix), "r"(iy), "r"(iz));
     ++steps; // :86
     return true;
 }
@@ -691,9 +717,13 @@ struct PathHit {
     Dda dda;
 };
 
+// Nearest instance along a ray by box-entry parameter (ties: lower index); the first instance in
+// that order whose DDA hits wins.  cam != nullptr: camera ray (o = eye in model space,
+// d = dirm * (x_ndc, y_ndc, 1)); else world ray (o = Mi*(ow,1), d = Mi*(dw,0)).
 template <bool kSmem>
 __device__ void trace_world(const FrameParams& fp, const InstUniforms* __restrict__ inst, const uint32_t* mask_base, uint32_t skip,
-                            const float ow[3], const float dw[3], PathHit& out, unsigned long long& iters) {
+                            const float* cam, int px, int py, const float ow[3], const float dw[3], PathHit& out,
+                            unsigned long long& iters) {
     out.hit = false;
     float last_t = -INFINITY;
     uint32_t last_j = 0;
@@ -708,10 +738,20 @@ __device__ void trace_world(const FrameParams& fp, const InstUniforms* __restric
             const InstUniforms* J = inst + j;
             if (j == skip || !J->valid) continue;
             float o[3], d[3];
+            if (cam) {
+                // camera rays: the conservative screen rectangle rejects most instances without arithmetic
+                if (px < J->bounds[0] || px > J->bounds[1] || py < J->bounds[2] || py > J->bounds[3]) continue;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                o[k] = ((J->Mi[0 * 3 + k] * ow[0] + J->Mi[1 * 3 + k] * ow[1]) + J->Mi[2 * 3 + k] * ow[2]) + J->Mi[3 * 3 + k];
-                d[k] = (J->Mi[0 * 3 + k] * dw[0] + J->Mi[1 * 3 + k] * dw[1]) + J->Mi[2 * 3 + k] * dw[2];
+                for (int k = 0; k < 3; ++k) {
+                    o[k] = J->eye_m[k];
+                    d[k] = (J->dirm[0 * 3 + k] * cam[0] + J->dirm[1 * 3 + k] * cam[1]) + J->dirm[3 * 3 + k];
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    o[k] = ((J->Mi[0 * 3 + k] * ow[0] + J->Mi[1 * 3 + k] * ow[1]) + J->Mi[2 * 3 + k] * ow[2]) + J->Mi[3 * 3 + k];
+                    d[k] = (J->Mi[0 * 3 + k] * dw[0] + J->Mi[1 * 3 + k] * dw[1]) + J->Mi[2 * 3 + k] * dw[2];
+                }
             }
             const float lo3[3] = {-0.5f - o[0], -0.5f - o[1], -0.5f - o[2]};
             const float hi3[3] = {0.5f - o[0], 0.5f - o[1], 0.5f - o[2]};
@@ -752,18 +792,11 @@ __device__ void trace_path(const FrameParams& fp, const InstUniforms* __restrict
     rng_init(rng, fp.seed, (uint32_t)py * (uint32_t)fp.width + (uint32_t)px, sample);
     const float jx = rng_u01(rng), jy = rng_u01(rng);
     const float fx = (float)px + jx, fy = (float)py + jy;
+    // camera segment: same visibility rule as every later segment
     PathHit cur;
-    cur.hit = false;
-    float zbuf = 1.0f;
-    for (uint32_t i = 0; i < fp.n_inst; ++i) {
-        Fragment f;
-        run_fragment<kSmem>(fp, inst + i, mask_base, px, py, fx, fy, f);
-        if (!f.covered) continue;
-        iters += f.dda.steps;
-        if (!f.dda.hit || !(f.depth < zbuf)) continue;
-        zbuf = f.depth;
-        cur.hit = true; cur.instance = i; cur.entry_axis = f.entry_axis; cur.dda = f.dda;
-    }
+    const float cam[2] = {fx * fp.sxn - 1.0f, fy * fp.syn - 1.0f};
+    const float zero3[3] = {0.0f, 0.0f, 0.0f};
+    trace_world<kSmem>(fp, inst, mask_base, 0xFFFFFFFFu, cam, px, py, zero3, zero3, cur, iters);
     rays += 1;
     const float sky[3] = {53.0f / 100.0f, 81.0f / 100.0f, 92.0f / 100.0f}; // lib/command.c:57-59
     float thr[3] = {1.0f, 1.0f, 1.0f};
@@ -834,7 +867,7 @@ __device__ void trace_path(const FrameParams& fp, const InstUniforms* __restrict
                 ow[k] = ((J->M[0 * 3 + k] * pm[0] + J->M[1 * 3 + k] * pm[1]) + J->M[2 * 3 + k] * pm[2]) + J->M[3 * 3 + k];
                 dw[k] = (J->M[0 * 3 + k] * dm[0] + J->M[1 * 3 + k] * dm[1]) + J->M[2 * 3 + k] * dm[2];
             }
-            trace_world<kSmem>(fp, inst, mask_base, cur.instance, ow, dw, next, iters);
+            trace_world<kSmem>(fp, inst, mask_base, cur.instance, nullptr, 0, 0, ow, dw, next, iters);
         }
         cur = next;
     }
@@ -976,7 +1009,6 @@ __global__ void __launch_bounds__(kBlockThreads, 2) trace_paths_single_kernel(co
             bool pending = false;    // its current ray has stopped (or never walked) and awaits shading
             bool fast = false;       // ... and it stopped inside the fast walk (exit state still to be decoded)
             bool walking = false;    // the fast walk is still going (the lane is NOT ready for shading)
-            bool reject = false;     // primary fragment that cannot pass the depth test
             uint32_t pix = 0;        // tile-local pixel (= lane that owns it) of the current path
             Rng rng{0, 0};
             float thr[3] = {1.0f, 1.0f, 1.0f};
@@ -1005,7 +1037,7 @@ __global__ void __launch_bounds__(kBlockThreads, 2) trace_paths_single_kernel(co
                         idx = 0; // parks the lane on a stop bit
                     }
                     pending = false;
-                    if (!r.hit || reject) {
+                    if (!r.hit) {
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
                             const float q = (thr[c] * sky[c]) * 16777216.0f;
@@ -1054,7 +1086,6 @@ __global__ void __launch_bounds__(kBlockThreads, 2) trace_paths_single_kernel(co
                             }
                             rays += 1;
                             entry_axis = a;
-                            reject = false;
                             new_ray = true;
                             new_has_start = true;
                         }
@@ -1077,7 +1108,7 @@ __global__ void __launch_bounds__(kBlockThreads, 2) trace_paths_single_kernel(co
                         const float jx = rng_u01(rng), jy = rng_u01(rng);
                         const float fx = (float)px + jx, fy = (float)py + jy;
                         rays += 1;
-                        // rasteriser restatement + trace.frag prologue (same operations as run_fragment)
+                        // camera ray in the instance's model space: o = eye, d = dirm * (x_ndc, y_ndc, 1)
                         const float x_ndc = fx * fp.sxn - 1.0f;
                         const float y_ndc = fy * fp.syn - 1.0f;
                         float d[3], o[3], lo3[3], hi3[3];
@@ -1090,38 +1121,21 @@ __global__ void __launch_bounds__(kBlockThreads, 2) trace_paths_single_kernel(co
                         }
                         float tn;
                         int axis;
-                        bool covered = slab_unit_cube(o, lo3, hi3, d, tn, axis);
-                        float mp[3], sp[4];
-                        if (covered) {
-                            entry_point(o, d, tn, axis, mp);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i)
-                                sp[i] = ((Ip->MVP[0 * 4 + i] * mp[0] + Ip->MVP[1 * 4 + i] * mp[1]) + Ip->MVP[2 * 4 + i] * mp[2]) + Ip->MVP[3 * 4 + i];
-                            covered = sp[3] > 0.0f && sp[2] >= 0.0f && sp[2] <= sp[3];
-                        }
-                        if (!covered) { // primary ray leaves through the sky
+                        if (!slab_unit_cube(o, lo3, hi3, d, tn, axis)) { // leaves through the sky
 #pragma unroll
                             for (int c = 0; c < 3; ++c) atomicAdd(&wacc[pix * 3 + c], (uint32_t)__float2ull_rz((1.0f * sky[c]) * 16777216.0f));
                         } else {
-                            const float depth = sp[2] / sp[3]; // trace.frag:46
-                            float rr[3];
-#pragma unroll
-                            for (int k = 0; k < 3; ++k)
-                                rr[k] = ((fp.RD[0 * 4 + k] * sp[0] + fp.RD[1 * 4 + k] * sp[1]) + fp.RD[2 * 4 + k] * sp[2]) + fp.RD[3 * 4 + k] * sp[3];
-                            const float len = sqrtf((rr[0] * rr[0] + rr[1] * rr[1]) + rr[2] * rr[2]);
-                            const float rd[3] = {rr[0] / len, rr[1] / len, rr[2] / len};
+                            float mp[3];
+                            entry_point(o, d, tn, axis, mp);
 #pragma unroll
                             for (int k = 0; k < 3; ++k) {
-                                ndir[k] = ((Ip->Mi[0 * 3 + k] * rd[0] + Ip->Mi[1 * 3 + k] * rd[1]) + Ip->Mi[2 * 3 + k] * rd[2]) + Ip->Mi[3 * 3 + k] * 0.0f;
+                                ndir[k] = d[k];
                                 npos[k] = (mp[k] + 0.5f) * size[k];
                             }
                             has_path = true;
                             bounce = 0;
                             thr[0] = thr[1] = thr[2] = 1.0f;
                             entry_axis = axis;
-                            // VK_COMPARE_OP_LESS against the cleared 1.0: a fragment exactly on the far plane
-                            // still walks (late-Z) but cannot win
-                            reject = !(depth < 1.0f);
                             new_ray = true;
                             new_has_start = false;
                         }
@@ -1231,7 +1245,7 @@ cudaError_t launch_trace_paths(const FrameParams& fp, const InstUniforms* inst, 
                                bool masks_in_smem, SrgbTables lut, FrameBuffers fb, int sm_count, cudaStream_t stream) {
     const int n_tiles = ((fp.width + kTileW - 1) / kTileW) * ((fp.height + kTileH - 1) / kTileH);
     const size_t smem = trace_smem_bytes(arena_words, masks_in_smem);
-    if (fp.n_inst == 1 && !(fp.flags & VT_FLAG_GENERIC_PATHS)) { // persistent-lane kernel for single-instance scenes
+    if (fp.n_inst == 1 && (fp.flags & VT_FLAG_PERSISTENT_LANES)) { // opt-in persistent-lane schedule (single-instance scenes)
         if (masks_in_smem) {
             const int grid = persistent_grid(trace_paths_single_kernel<true>, smem, sm_count, n_tiles);
             trace_paths_single_kernel<true><<<grid, kBlockThreads, smem, stream>>>(fp, inst, mask_arena, arena_words, lut, fb);
