@@ -1,0 +1,74 @@
+"""CPU tests of the host-side mirrors of the reference's Rust facade (glm builders, .vox loader,
+texture upload queue, scene helpers)."""
+import os
+
+import numpy as np
+
+from tools import scenes
+from vtrace_b200 import glm, voxel
+from vtrace_b200.distributed import shard_samples
+from vtrace_b200.renderer import TextureUploadQueue
+
+
+def test_perspective_matches_the_gl_formula():
+    P = glm.perspective(glm.REFERENCE_FOV, 16 / 9, 0.01, 10000.0)
+    ys = 1.0 / np.tan(float(glm.REFERENCE_FOV) / 2.0)
+    assert np.isclose(P[1][1], ys, rtol=1e-6) and np.isclose(P[0][0], ys / (16 / 9), rtol=1e-6)
+    assert P[2][3] == -1.0 and P[3][3] == 0.0
+    assert np.isclose(P[2][2], -(10000.0 + 0.01) / (10000.0 - 0.01), rtol=1e-6)
+    assert np.isclose(P[3][2], -2 * 10000.0 * 0.01 / (10000.0 - 0.01), rtol=1e-6)
+
+
+def test_look_at_is_a_rigid_transform():
+    V = glm.look_at(scenes.EYE, scenes.CENTER, scenes.UP)
+    R = V[:3, :3]
+    assert np.allclose(R @ R.T, np.eye(3), atol=1e-6)
+    eye_h = np.append(np.asarray(scenes.EYE, dtype=np.float32), 1.0)
+    assert np.allclose(V.T @ eye_h, [0, 0, 0, 1], atol=1e-6)           # the eye maps to the origin
+    c = V.T @ np.array([0, 0, 0, 1], dtype=np.float32)
+    assert c[2] < 0 and abs(c[0]) < 1e-6 and abs(c[1]) < 1e-6          # looks down -Z at the centre
+
+
+def test_texture_id_is_bit_cast_into_m33():
+    m = glm.with_texture_id(glm.translate(glm.identity(), (1, 2, 3)), 0xBEEF)
+    assert m.reshape(16).view(np.uint32)[15] == 0xBEEF and tuple(m[3][:3]) == (1, 2, 3)
+
+
+def test_python_loader_matches_oracle_loader(oracle):
+    for name in ("Treasure", "AncientTemple"):
+        path = os.path.join(scenes.ASSETS, f"{name}.vox")
+        raw, dims = oracle.load_vox(path)
+        chunk = voxel.load_magica_voxel(path)[0]
+        assert chunk.dims() == dims and np.array_equal(chunk.get_raw(), raw)
+
+
+def test_chunk_layout_is_z_fastest():
+    c = voxel.RawDynamicChunk(2, 3, 4)
+    c.at_mut(1, 2, 3)[:] = (9, 8, 7, 6)
+    flat = c.get_raw().reshape(-1, 4)
+    assert tuple(flat[3 + 4 * (2 + 3 * 1)]) == (9, 8, 7, 6)   # z + dz*(y + dy*x), src/voxel/rawchunk.rs:292
+    assert c.at_mut(2, 0, 0) is None
+
+
+def test_texture_upload_queue_is_fifo_with_dense_handles():
+    q = TextureUploadQueue()
+    assert [q.add_texture(x) for x in "abc"] == [0, 1, 2]
+    assert q.pop() == ("a", 0) and q.pop() == ("b", 1) and q.pop() == ("c", 2) and q.pop() is None
+
+
+def test_entity_grid_is_the_reference_world():
+    g = scenes.entity_grid(3, 7)
+    assert g.shape == (121, 16)                                            # 11 x 11, src/world.rs:143-161
+    ids = g.view(np.uint32)[:, 15]
+    assert set(ids.tolist()) == {3, 7} and (ids == 3).sum() == 61
+    assert np.allclose(g[:, 13], -5.0) and np.isclose(g[:, 12].min(), -7.5) and np.isclose(g[:, 14].max(), 7.5)
+
+
+def test_shard_samples_partitions_every_sample_once():
+    for total in (0, 1, 7, 64, 65):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for rank in range(world):
+                first, stride, count = shard_samples(total, rank, world)
+                seen += [first + k * stride for k in range(count)]
+            assert sorted(seen) == list(range(total))

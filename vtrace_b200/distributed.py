@@ -1,0 +1,29 @@
+"""Multi-GPU plumbing for the path-tracing extension: one process per GPU, the
+scene replicated, the samples of every pixel sharded over the ranks, the fixed-point accumulation
+buffers summed with ONE all-reduce (NCCL on GPUs; gloo in the CPU tests).  No other collective:
+rays never cross ranks.
+
+Because the accumulators are integers (2^-24 fixed point), the reduced image is bit-identical for
+any number of ranks and any reduction order.
+"""
+from __future__ import annotations
+
+
+def shard_samples(total_spp: int, rank: int, world: int) -> tuple[int, int, int]:
+    """(sample_first, sample_stride, sample_count) of `rank`: global samples s = rank (mod world).
+
+    Works for any total_spp >= 0: the first total_spp % world ranks render one extra sample.
+    """
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world of {world}")
+    count = total_spp // world + (1 if rank < total_spp % world else 0)
+    return rank, world, count
+
+
+def reduce_accum(accum, group=None):
+    """Sum the (h, w, 3) int64 accumulation tensor over all ranks, in place; returns it."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(accum, op=dist.ReduceOp.SUM, group=group)
+    return accum
