@@ -111,6 +111,14 @@ def scene_inputs():
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port on the host's cores
 
+def host_threads() -> int:
+    """All host threads this process may use (torchrun pins OMP_NUM_THREADS=1; the CPU arm ignores that)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_sample(threads: int, spp: int):
     """Times `spp` samples/pixel of the full 1080p workload on the oracle; returns (Mrays/s, s, rays)."""
     import oracle_lib
@@ -128,8 +136,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0  # the CPU arm runs once, on rank 0; other ranks exit without work
-    import oracle_lib
-    threads = oracle_lib.max_threads()
+    threads = host_threads()
     spp = args.ref_spp
     for _ in range(args.warmup):
         cpu_sample(threads, 1)
@@ -164,6 +171,7 @@ def run_cuda(args):
     import torch.distributed as dist
 
     from vtrace_b200 import abi
+    from vtrace_b200.distributed import reduce_accum, shard_samples
     from vtrace_b200.renderer import Renderer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -183,8 +191,9 @@ def run_cuda(args):
     r = Renderer()  # entry(): picks LOCAL_RANK's device
     r.add_texture(chunk)
     r.update_instances_raw(inst)
-    r.configure(width=WIDTH, height=HEIGHT, mode=abi.MODE_PATHS, flags=abi.FLAG_NO_HIT_RECORDS, spp=SPP // world,
-                bounces=BOUNCES, seed=SEED, sample_first=rank, sample_stride=world, total_spp=SPP, max_frames=0)
+    first, stride, count = shard_samples(SPP, rank, world)
+    r.configure(width=WIDTH, height=HEIGHT, mode=abi.MODE_PATHS, flags=abi.FLAG_NO_HIT_RECORDS, spp=count,
+                bounces=BOUNCES, seed=SEED, sample_first=first, sample_stride=stride, total_spp=SPP, max_frames=0)
     # a non-default torch stream becomes the current stream; the library enqueues on it too, so torch
     # CUDA events bracket the library's kernels and NCCL is ordered with them
     stream = torch.cuda.Stream(device=dev)
@@ -201,8 +210,7 @@ def run_cuda(args):
         """One frame, everything device-resident, no host copies."""
         accum.zero_()
         r.render_async(P, V)
-        if world > 1:
-            dist.all_reduce(accum, op=dist.ReduceOp.SUM)
+        reduce_accum(accum)
         r.resolve()
 
     def step_e2e():
@@ -213,7 +221,7 @@ def run_cuda(args):
         else:
             accum.zero_()
             r.render_async(P, V)
-            dist.all_reduce(accum, op=dist.ReduceOp.SUM)
+            reduce_accum(accum)
             r.resolve()
         n = lib.vt_read_color(frame_host.ctypes.data, frame_host.nbytes)  # finished frame -> host
         assert n == frame_host.nbytes
@@ -283,8 +291,7 @@ def run_cuda(args):
         achieved = alg_bytes / kernel_s / 1e9
         cpu = None
         if world == 1 and not args.no_cpu:
-            import oracle_lib
-            threads = oracle_lib.max_threads()
+            threads = host_threads()
             v, dt, _, _ = cpu_sample(threads, args.cpu_spp)
             cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"{args.cpu_spp} of the {SPP} spp of the same 1080p frame (samples 0..{args.cpu_spp - 1}), "
