@@ -223,7 +223,10 @@ def test_paths_generic_kernel_on_single_instance(scene, assets):
     t = scene.add(assets["Treasure"])
     scene.set_instances([(glm.identity(), t)])
     P, V = scenes.camera(256, 160, eye=(0.9, -0.5, 0.7))
-    a, _ = scene.check_paths(P, V, 256, 160, spp=5, flags=0, what="general kernel")
+    a, _ = scene.check_paths(P, V, 256, 160, spp=5, flags=abi.FLAG_PER_PIXEL_PATHS, what="general per-pixel kernel")
+    w, _ = scene.check_paths(P, V, 256, 160, spp=5, flags=0, what="wavefront kernel")
+    g, _ = scene.check_paths(P, V, 256, 160, spp=5, flags=abi.FLAG_FORCE_GLOBAL_MASKS, what="wavefront kernel, global masks")
+    assert np.array_equal(a, w) and np.array_equal(a, g)
     b, _ = scene.check_paths(P, V, 256, 160, spp=5, flags=abi.FLAG_PERSISTENT_LANES, what="persistent-lane kernel")
     c, _ = scene.check_paths(P, V, 256, 160, spp=5, flags=abi.FLAG_PERSISTENT_LANES | abi.FLAG_FORCE_GLOBAL_MASKS,
                              what="persistent-lane kernel, global masks")

@@ -26,6 +26,7 @@ namespace vt {
 #define VT_FLAG_VIEWPORT_H_IS_W 1u
 #define VT_FLAG_NO_HIT_RECORDS 2u
 #define VT_FLAG_PERSISTENT_LANES 8u
+#define VT_FLAG_PER_PIXEL_PATHS 16u
 #define VT_MISS 0xFFFFFFFFu
 
 static constexpr int kBlockThreads = 256; // 8 warps
@@ -1193,6 +1194,8 @@ __global__ void __launch_bounds__(kBlockThreads, 2) trace_paths_single_kernel(co
     }
 }
 
+#include "paths_wave.cuh"
+
 __global__ void resolve_kernel(const unsigned long long* __restrict__ accum, uint32_t n_pixels, uint32_t total_spp, SrgbTables lut,
                                uchar4* __restrict__ color) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1215,13 +1218,17 @@ cudaError_t configure_kernels(int max_smem_optin) {
     e = cudaFuncSetAttribute(trace_paths_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(trace_paths_single_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(trace_paths_wave_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(trace_paths_wave_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     return e;
 }
 
 template <class K>
-static int persistent_grid(K kernel, size_t smem, int sm_count, int n_tiles) {
+static int persistent_grid(K kernel, size_t smem, int sm_count, int n_tiles, int block_threads = kBlockThreads) {
     int per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlockThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block_threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     long grid = (long)per_sm * sm_count; // whole number of CTAs per SM: one resident wave
     if (grid > n_tiles) grid = n_tiles;
     return (int)(grid < 1 ? 1 : grid);
@@ -1245,6 +1252,20 @@ cudaError_t launch_trace_paths(const FrameParams& fp, const InstUniforms* inst, 
                                bool masks_in_smem, SrgbTables lut, FrameBuffers fb, int sm_count, cudaStream_t stream) {
     const int n_tiles = ((fp.width + kTileW - 1) / kTileW) * ((fp.height + kTileH - 1) / kTileH);
     const size_t smem = trace_smem_bytes(arena_words, masks_in_smem);
+    if (fp.n_inst == 1 && !(fp.flags & (VT_FLAG_PERSISTENT_LANES | VT_FLAG_PER_PIXEL_PATHS))) {
+        // single-instance scenes: warp-local wavefront engine (paths_wave.cuh)
+        const size_t wsmem = wave_smem_bytes(arena_words, masks_in_smem);
+        const int n_items = n_tiles * (int)((fp.spp + kItemSpp - 1) / kItemSpp);
+        const int max_warps = (n_items + 0) > 0 ? n_items : 1;
+        if (masks_in_smem) {
+            int grid = persistent_grid(trace_paths_wave_kernel<true>, wsmem, sm_count, max_warps, kWaveThreads);
+            trace_paths_wave_kernel<true><<<grid, kWaveThreads, wsmem, stream>>>(fp, inst, mask_arena, arena_words, lut, fb);
+        } else {
+            int grid = persistent_grid(trace_paths_wave_kernel<false>, wsmem, sm_count, max_warps, kWaveThreads);
+            trace_paths_wave_kernel<false><<<grid, kWaveThreads, wsmem, stream>>>(fp, inst, mask_arena, arena_words, lut, fb);
+        }
+        return cudaGetLastError();
+    }
     if (fp.n_inst == 1 && (fp.flags & VT_FLAG_PERSISTENT_LANES)) { // opt-in persistent-lane schedule (single-instance scenes)
         if (masks_in_smem) {
             const int grid = persistent_grid(trace_paths_single_kernel<true>, smem, sm_count, n_tiles);

@@ -1,0 +1,408 @@
+// paths_wave.cuh — trace_paths_wave_kernel: the path tracer for single-instance scenes
+// (BASELINE configs[2]) as a warp-local wavefront engine.  Included from kernels.cu (namespace vt).
+//
+// Same paths, same arithmetic, same integer sums as trace_path() — only the schedule differs.
+// The per-pixel kernel runs at ~47 % SIMT efficiency (ncu: 15 of 32 lanes): rays of one warp need
+// 0..150 DDA iterations, paths end after 1..5 segments, and regenerating a ray (shade + bounce, or
+// a new camera ray) is as expensive as marching it.  Here every warp owns a pool of kSlots paths in
+// shared memory and only ever runs one kind of work at a time, on full batches:
+//
+//   classify : slot owners decode rays that stopped -> HIT (wait for a bounce batch) or MISS
+//              (sky radiance is added with integer atomics, slot freed);
+//   primary  : when >= 32 slots are free, 32 lanes start 32 new camera rays (jobs = covered
+//              pixel x sample, claimed per (tile, 16-sample) item from a global counter);
+//   bounce   : when >= 32 slots hold hits, 32 lanes shade and bounce them;
+//   march    : lanes pull READY rays from the pool, step them together (parked lanes sit on a
+//              stop bit, so the loop has no per-lane branch), write the exit state back when a
+//              ray stops and immediately pull the next one; when the READY list is empty and fewer
+//              than `refill_threshold` lanes still walk, the rest is parked back into the pool.
+//
+// Everything is warp-local (__syncwarp only): no inter-warp queues, no block barriers after the
+// prologue.  Radiance is 2^-24 fixed point added with integer atomics, RNG streams are keyed by
+// (pixel, sample): the result is bit-identical to the per-pixel kernel and to the CPU oracle.
+//
+// Slot layout (96 bytes, 3 + 3 uint4; the 48-byte stride makes 128-bit accesses of consecutive
+// slots bank-conflict-free):
+//   ray  q0 = side.xyz, idx      q1 = delta.xyz, step signs      q2 = prev, steps, state, pixel
+//   path p0 = thr.rgb, rng key   p1 = pos.xyz, len               p2 = dir.xyz, meta
+#pragma once
+
+static constexpr int kWaveWarps = 12;
+static constexpr int kWaveThreads = kWaveWarps * 32;
+static constexpr int kSlots = 64;        // paths in flight per warp
+static constexpr int kSlotGroups = kSlots / 32;
+static constexpr uint32_t kItemSpp = 16; // samples per work item (tile x 16 samples)
+static constexpr uint32_t kPoolBytes = kSlots * 96 + kSlots + 32; // slots + one byte list + the item's covered-pixel table
+static_assert(kPoolBytes % 16 == 0, "pool alignment");
+
+enum SlotState : uint32_t { kFree = 0, kReady = 1, kDone = 3, kHit = 4 };
+
+size_t wave_smem_bytes(uint32_t arena_words, bool masks_in_smem) {
+    return trace_smem_bytes(arena_words, masks_in_smem) + size_t(kWaveWarps) * kPoolBytes;
+}
+
+__device__ __forceinline__ uint32_t pack_signs(const int32_t step[3]) {
+    return (uint32_t)(step[0] + 1) | ((uint32_t)(step[1] + 1) << 2) | ((uint32_t)(step[2] + 1) << 4);
+}
+
+template <bool kSmem>
+__global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const __grid_constant__ FrameParams fp,
+                                                                          const InstUniforms* __restrict__ inst,
+                                                                          const uint32_t* __restrict__ mask_arena,
+                                                                          uint32_t arena_words, SrgbTables lut, FrameBuffers fb) {
+    stage_tables<kSmem>(mask_arena, arena_words, lut.decode);
+    const float* dec = reinterpret_cast<const float*>(vt_smem + kSmemLutOff);
+    const InstUniforms* Ip = inst; // the one instance
+    const Vol vol{Ip->w, Ip->h, Ip->d, Ip->xb, Ip->yb, Ip->mask_off, mask_arena};
+    const float size[3] = {(float)(int32_t)Ip->w, (float)(int32_t)Ip->h, (float)(int32_t)Ip->d};
+    const uint32_t xb = vol.xb, zb = vol.xb + vol.yb;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t pool_off = kSmemMaskOff + (kSmem ? arena_words * 4u : 0u);
+    uint4* ray = reinterpret_cast<uint4*>(vt_smem + pool_off + warp * kPoolBytes);
+    uint4* path = ray + kSlots * 3;
+    uint8_t* list = reinterpret_cast<uint8_t*>(path + kSlots * 3);
+    uint8_t* cov_pix = list + kSlots; // cov_pix[c] = tile-local index of the item's c-th covered pixel
+
+    const int tiles_x = (fp.width + kTileW - 1) / kTileW;
+    const int tiles_y = (fp.height + kTileH - 1) / kTileH;
+    const int n_tiles = tiles_x * tiles_y;
+    const int n_chunks = (int)((fp.spp + kItemSpp - 1) / kItemSpp);
+    const int n_items = n_tiles * n_chunks;
+
+    const float sky[3] = {53.0f / 100.0f, 81.0f / 100.0f, 92.0f / 100.0f}; // lib/command.c:57-59
+    unsigned long long sky_q[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) sky_q[c] = __float2ull_rz((1.0f * sky[c]) * 16777216.0f);
+    unsigned long long rays = 0, iters = 0;
+
+#pragma unroll
+    for (int g = 0; g < kSlotGroups; ++g) ray[(lane + 32 * g) * 3 + 2] = make_uint4(0u, 0u, kFree, 0u);
+    __syncwarp();
+    int n_free = kSlots, n_ready = 0, n_hit = 0;
+
+    // current work item (warp-uniform)
+    bool work_left = true;
+    int it_x0 = 0, it_y0 = 0;
+    uint32_t it_ncov = 1, it_magic = 0, it_next = 0, it_njobs = 0, it_s0 = 0;
+
+    // adds one finished path's radiance (thr * sky, or nothing) to the frame accumulators
+    auto add_sky = [&](uint32_t pixel, float t0, float t1, float t2) {
+        const float thr[3] = {t0, t1, t2};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float q = (thr[c] * sky[c]) * 16777216.0f;
+            if (q == q && q > 0.0f) atomicAdd(fb.accum + 3 * (size_t)pixel + c, __float2ull_rz(q));
+        }
+    };
+    // writes a ray that is about to walk (or whose slow-path result is final) into its slot
+    auto store_ray = [&](uint32_t slot, const Dda& r, uint32_t idx, uint32_t prev, uint32_t steps, uint32_t state, uint32_t pixel) {
+        ray[slot * 3 + 0] = make_uint4(__float_as_uint(r.side[0]), __float_as_uint(r.side[1]), __float_as_uint(r.side[2]), idx);
+        ray[slot * 3 + 1] = make_uint4(__float_as_uint(r.delta[0]), __float_as_uint(r.delta[1]), __float_as_uint(r.delta[2]), pack_signs(r.step));
+        ray[slot * 3 + 2] = make_uint4(prev, steps, state, pixel);
+    };
+    // Starts the walk of a fresh ray (pos, dir[, start voxel]) that belongs to `slot`.
+    // Returns the slot's new state: kReady (fast walk pending), kHit (slow path hit), kFree (slow path miss).
+    auto launch_ray = [&](uint32_t slot, uint32_t pixel, const float pos[3], const float dir[3], bool has_start, const int32_t sv[3],
+                          const float thr[3], uint32_t key, uint32_t meta) -> uint32_t {
+        Dda r;
+        uint32_t idx;
+        const DdaMode mode = dda_init(vol, pos, dir, has_start, sv, r, idx);
+        path[slot * 3 + 0] = make_uint4(__float_as_uint(thr[0]), __float_as_uint(thr[1]), __float_as_uint(thr[2]), key);
+        path[slot * 3 + 1] = make_uint4(__float_as_uint(pos[0]), __float_as_uint(pos[1]), __float_as_uint(pos[2]), __float_as_uint(r.len));
+        path[slot * 3 + 2] = make_uint4(__float_as_uint(dir[0]), __float_as_uint(dir[1]), __float_as_uint(dir[2]), meta);
+        if (mode == kDdaFast) {
+            store_ray(slot, r, idx, idx, 0u, kReady, pixel);
+            return kReady;
+        }
+        if (mode == kDdaSlow) {
+            dda_slow<kSmem>(vol, r); // rare: a direction component is exactly 0; runs to completion here
+            iters += r.steps;
+            if (r.hit) {
+                // re-express the result in the fast walk's exit format (bit index, previous index, steps)
+                const uint32_t hidx = (uint32_t)(r.v[0] + 1) | ((uint32_t)(r.v[1] + 1) << xb) | ((uint32_t)(r.v[2] + 1) << zb);
+                const uint32_t ix = (uint32_t)r.step[0], iy = (uint32_t)r.step[1] << xb, iz = (uint32_t)r.step[2] << zb;
+                const uint32_t lm = r.steps ? r.last_mask : 0u;
+                const uint32_t hprev = hidx - ((lm & 1u) ? ix : 0u) - ((lm & 2u) ? iy : 0u) - ((lm & 4u) ? iz : 0u);
+                store_ray(slot, r, hidx, hprev, r.steps, kHit, pixel);
+                return kHit;
+            }
+        }
+        add_sky(pixel, thr[0], thr[1], thr[2]); // missed (or never entered the padded volume)
+        ray[slot * 3 + 2] = make_uint4(0u, 0u, kFree, pixel);
+        return kFree;
+    };
+    // compacts the slots in `state` into list[0..), returns how many there are
+    auto build_list = [&](uint32_t state) -> int {
+        int base = 0;
+#pragma unroll
+        for (int g = 0; g < kSlotGroups; ++g) {
+            const uint32_t slot = lane + 32 * g;
+            const bool f = ray[slot * 3 + 2].z == state;
+            const uint32_t m = __ballot_sync(0xffffffffu, f);
+            if (f) list[base + __popc(m & lt_mask)] = (uint8_t)slot;
+            base += __popc(m);
+        }
+        __syncwarp();
+        return base;
+    };
+
+    for (;;) {
+        // ---- classify: owners decode the rays that stopped -------------------------------------
+#pragma unroll
+        for (int g = 0; g < kSlotGroups; ++g) {
+            const uint32_t slot = lane + 32 * g;
+            const uint4 q2 = ray[slot * 3 + 2];
+            const bool done = q2.z == kDone;
+            bool hit = false;
+            if (done) {
+                const uint32_t idx = ray[slot * 3 + 0].w;
+                const int32_t vx = (int32_t)(idx & ((1u << xb) - 1u)) - 1;
+                const int32_t vy = (int32_t)((idx >> xb) & ((1u << vol.yb) - 1u)) - 1;
+                const int32_t vz = (int32_t)(idx >> zb) - 1;
+                hit = vx >= 0 && vx < (int32_t)vol.w && vy >= 0 && vy < (int32_t)vol.h && vz >= 0 && vz < (int32_t)vol.d;
+                iters += q2.y;
+                if (hit) {
+                    ray[slot * 3 + 2].z = kHit;
+                } else {
+                    const uint4 p0 = path[slot * 3 + 0];
+                    add_sky(q2.w, __uint_as_float(p0.x), __uint_as_float(p0.y), __uint_as_float(p0.z));
+                    ray[slot * 3 + 2].z = kFree;
+                }
+            }
+            n_hit += __popc(__ballot_sync(0xffffffffu, done && hit));
+            n_free += __popc(__ballot_sync(0xffffffffu, done && !hit));
+        }
+        __syncwarp();
+
+        // ---- make sure there is a work item with jobs (or learn that the frame is exhausted) ------
+        while (work_left && it_next >= it_njobs) {
+            const int item = claim_tiles(fb.stats + 2, lane, 1);
+            if (item >= n_items) { work_left = false; break; }
+            const int chunk = item / n_tiles, tile = item - chunk * n_tiles;
+            it_x0 = (tile % tiles_x) * kTileW;
+            it_y0 = (tile / tiles_x) * kTileH;
+            const int my_px = it_x0 + (lane & 7), my_py = it_y0 + (lane >> 3);
+            const bool in_frame = my_px < fp.width && my_py < fp.height;
+            const bool may_hit = in_frame && !(my_px < Ip->bounds[0] || my_px > Ip->bounds[1] || my_py < Ip->bounds[2] || my_py > Ip->bounds[3]);
+            const uint32_t cov = __ballot_sync(0xffffffffu, may_hit);
+            it_ncov = __popc(cov);
+            if (may_hit) cov_pix[__popc(cov & lt_mask)] = (uint8_t)lane;
+            it_s0 = (uint32_t)chunk * kItemSpp;
+            const uint32_t ns = fp.spp - it_s0 < kItemSpp ? fp.spp - it_s0 : kItemSpp;
+            it_njobs = it_ncov * ns;
+            it_next = 0;
+            if (chunk == 0 && in_frame && !may_hit) { // pixels outside the screen rectangle see only sky, for every sample
+                const size_t p = (size_t)my_py * (size_t)fp.width + (size_t)my_px;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) atomicAdd(fb.accum + 3 * p + c, sky_q[c] * fp.spp);
+                rays += fp.spp;
+            }
+            if (it_ncov == 0) it_ncov = 1; // (no jobs; keeps the division below defined)
+            it_magic = 0xFFFFFFFFu / it_ncov + 1u; // floor(job / ncov) == umulhi(job, magic) for job * ncov < 2^32
+            __syncwarp();
+        }
+        const bool jobs = work_left && it_next < it_njobs;
+
+        // ---- pick the next full batch (or the best partial one when the pool runs dry) -----------
+        int action; // 0 primary, 1 bounce, 2 march, 3 stop
+        const int low = (int)fp.refill_threshold;
+        if (n_hit >= 32) action = 1;
+        else if (n_free >= 32 && jobs) action = 0;
+        else if (n_ready >= low) action = 2;
+        else if (n_hit > 0 && (!jobs || n_hit >= n_free)) action = 1;
+        else if (jobs && n_free > 0) action = 0;
+        else if (n_ready > 0) action = 2;
+        else action = 3;
+        if (action == 3) break;
+
+        if (action == 0) {
+            // ---- primary batch: new camera rays --------------------------------------------------
+            build_list(kFree);
+            const uint32_t avail = it_njobs - it_next;
+            uint32_t n = n_free < 32 ? (uint32_t)n_free : 32u;
+            n = n < avail ? n : avail;
+            uint32_t st = kFree;
+            if ((uint32_t)lane < n) {
+                const uint32_t slot = list[lane];
+                const uint32_t job = it_next + lane; // sample-major: neighbouring lanes get neighbouring pixels
+                const uint32_t si = __umulhi(job, it_magic), ci = job - si * it_ncov;
+                const uint32_t pix = cov_pix[ci];
+                const int px = it_x0 + (int)(pix & 7u), py = it_y0 + (int)(pix >> 3);
+                const uint32_t pixel = (uint32_t)py * (uint32_t)fp.width + (uint32_t)px;
+                Rng rng;
+                rng_init(rng, fp.seed, pixel, fp.sample_first + (it_s0 + si) * fp.sample_stride);
+                const float jx = rng_u01(rng), jy = rng_u01(rng);
+                const float fx = (float)px + jx, fy = (float)py + jy;
+                rays += 1;
+                // camera ray in the instance's model space: o = eye, d = dirm * (x_ndc, y_ndc, 1)
+                const float x_ndc = fx * fp.sxn - 1.0f;
+                const float y_ndc = fy * fp.syn - 1.0f;
+                float d[3], o[3], lo3[3], hi3[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    d[k] = (Ip->dirm[0 * 3 + k] * x_ndc + Ip->dirm[1 * 3 + k] * y_ndc) + Ip->dirm[3 * 3 + k];
+                    o[k] = Ip->eye_m[k];
+                    lo3[k] = Ip->slab_lo[k];
+                    hi3[k] = Ip->slab_hi[k];
+                }
+                float tn;
+                int axis;
+                if (!slab_unit_cube(o, lo3, hi3, d, tn, axis)) { // leaves through the sky; the slot stays free
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) atomicAdd(fb.accum + 3 * (size_t)pixel + c, sky_q[c]);
+                } else {
+                    float mp[3], pos[3];
+                    entry_point(o, d, tn, axis, mp);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) pos[k] = (mp[k] + 0.5f) * size[k];
+                    const float one[3] = {1.0f, 1.0f, 1.0f};
+                    const int32_t none[3] = {0, 0, 0};
+                    st = launch_ray(slot, pixel, pos, d, false, none, one, rng.key, (uint32_t)axis << 4 | rng.ctr << 8);
+                }
+            }
+            it_next += n;
+            const int nr = __popc(__ballot_sync(0xffffffffu, st == kReady)), nh = __popc(__ballot_sync(0xffffffffu, st == kHit));
+            n_ready += nr; n_hit += nh; n_free -= nr + nh;
+            __syncwarp();
+        } else if (action == 1) {
+            // ---- bounce batch: shade the hits, start the next segment ---------------------------
+            const int have = build_list(kHit);
+            const int n = have < 32 ? have : 32;
+            uint32_t st = kHit; // lanes without work report "unchanged"
+            if (lane < n) {
+                const uint32_t slot = list[lane];
+                const uint4 q0 = ray[slot * 3 + 0], q1 = ray[slot * 3 + 1], q2 = ray[slot * 3 + 2];
+                const uint4 p0 = path[slot * 3 + 0], p1 = path[slot * 3 + 1], p2 = path[slot * 3 + 2];
+                Dda r;
+                r.side[0] = __uint_as_float(q0.x); r.side[1] = __uint_as_float(q0.y); r.side[2] = __uint_as_float(q0.z);
+                r.delta[0] = __uint_as_float(q1.x); r.delta[1] = __uint_as_float(q1.y); r.delta[2] = __uint_as_float(q1.z);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) r.step[k] = (int32_t)((q1.w >> (2 * k)) & 3u) - 1;
+                r.pos[0] = __uint_as_float(p1.x); r.pos[1] = __uint_as_float(p1.y); r.pos[2] = __uint_as_float(p1.z);
+                r.len = __uint_as_float(p1.w);
+                r.dir[0] = __uint_as_float(p2.x); r.dir[1] = __uint_as_float(p2.y); r.dir[2] = __uint_as_float(p2.z);
+                dda_finish_fast(vol, r, q0.w, q2.x, q2.y);
+                const uint32_t pixel = q2.w;
+                uint32_t bounce = p2.w & 15u;
+                const int entry_axis = (int)((p2.w >> 4) & 3u);
+                Rng rng{p0.w, p2.w >> 8};
+                float thr[3] = {__uint_as_float(p0.x), __uint_as_float(p0.y), __uint_as_float(p0.z)};
+                const uchar4 s = fetch_texel(Ip->rgba, Ip->w, Ip->h, Ip->d, Ip->remap_identity != 0, r.v);
+                thr[0] = thr[0] * dec[s.x];
+                thr[1] = thr[1] * dec[s.y];
+                thr[2] = thr[2] * dec[s.z];
+                if (bounce == fp.bounces) {
+                    ray[slot * 3 + 2].z = kFree; // path length exhausted: contributes nothing
+                    st = kFree;
+                } else {
+                    ++bounce;
+                    const uint32_t lm = r.steps ? r.last_mask : (1u << entry_axis);
+                    const int a = (lm & 1u) ? 0 : ((lm & 2u) ? 1 : 2);
+                    float npos[3], ndir[3];
+                    int32_t nsv[3];
+                    rng_sphere(rng, ndir);
+                    int nsign = 0;
+                    const float t = r.steps ? ((a == 0 ? r.side[0] : (a == 1 ? r.side[1] : r.side[2])) -
+                                               (a == 0 ? r.delta[0] : (a == 1 ? r.delta[1] : r.delta[2])))
+                                            : 0.0f;
+                    const float tl = t / r.len;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        float p = r.pos[k] + r.dir[k] * tl;
+                        const float lo = (float)r.v[k], hi = (float)(r.v[k] + 1);
+                        p = p < lo ? lo : p;
+                        p = p > hi ? hi : p;
+                        npos[k] = p;
+                        nsv[k] = r.v[k];
+                        if (k == a) {
+                            nsign = r.step[k] != 0 ? -r.step[k] : (r.pos[k] <= 0.5f * size[k] ? -1 : 1);
+                            npos[k] = (float)(r.v[k] + (nsign > 0 ? 1 : 0));
+                            nsv[k] += nsign;
+                            ndir[k] += (float)nsign;
+                        }
+                    }
+                    const float l2 = (ndir[0] * ndir[0] + ndir[1] * ndir[1]) + ndir[2] * ndir[2];
+                    if (l2 < 1e-6f) {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) ndir[k] = (k == a) ? (float)nsign : 0.0f;
+                    } else {
+                        const float rl = 1.0f / sqrtf(l2);
+                        ndir[0] *= rl; ndir[1] *= rl; ndir[2] *= rl;
+                    }
+                    rays += 1;
+                    st = launch_ray(slot, pixel, npos, ndir, true, nsv, thr, rng.key, bounce | (uint32_t)a << 4 | rng.ctr << 8);
+                }
+            }
+            const int nr = __popc(__ballot_sync(0xffffffffu, st == kReady)), nf = __popc(__ballot_sync(0xffffffffu, st == kFree));
+            n_ready += nr; n_free += nf; n_hit -= nr + nf;
+            __syncwarp();
+        } else {
+            // ---- march: pull READY rays, step them packed, write exits back --------------------------
+            const int total = build_list(kReady); // == n_ready
+            int rc = 0;
+            int my_slot = -1;
+            uint32_t my_pixel = 0;
+            uint32_t idx = 0, prev = 0, steps = 0, ix = 0, iy = 0, iz = 0; // idx 0 = border bit: a parked lane's step is a no-op
+            float sx = 0.0f, sy = 0.0f, sz = 0.0f, dx = 0.0f, dy = 0.0f, dz = 0.0f;
+            int thresh = -1;
+            uint32_t idle_mask = 0xffffffffu; // lanes without a ray
+            for (;;) {
+                if (idle_mask && rc < total) { // hand the next READY rays to the idle lanes
+                    const bool idle = (idle_mask >> lane) & 1u;
+                    const int rank = __popc(idle_mask & lt_mask);
+                    if (idle && rc + rank < total) {
+                        my_slot = list[rc + rank];
+                        const uint4 q0 = ray[my_slot * 3 + 0], q1 = ray[my_slot * 3 + 1], q2 = ray[my_slot * 3 + 2];
+                        sx = __uint_as_float(q0.x); sy = __uint_as_float(q0.y); sz = __uint_as_float(q0.z); idx = q0.w;
+                        dx = __uint_as_float(q1.x); dy = __uint_as_float(q1.y); dz = __uint_as_float(q1.z);
+                        ix = (uint32_t)((int32_t)(q1.w & 3u) - 1);
+                        iy = (uint32_t)((int32_t)((q1.w >> 2) & 3u) - 1) << xb;
+                        iz = (uint32_t)((int32_t)((q1.w >> 4) & 3u) - 1) << zb;
+                        prev = q2.x; steps = q2.y; my_pixel = q2.w;
+                    }
+                    const int want = __popc(idle_mask);
+                    rc += want < total - rc ? want : total - rc;
+                    idle_mask = __ballot_sync(0xffffffffu, my_slot < 0);
+                }
+                const int nact = 32 - __popc(idle_mask);
+                if (!nact) { n_ready = 0; break; }
+                if (thresh < 0) thresh = nact < low ? nact : low;
+                if (rc >= total && nact < thresh) {
+                    // too few lanes left: park them back into the pool and go generate more rays
+                    if (my_slot >= 0) {
+                        ray[my_slot * 3 + 0] = make_uint4(__float_as_uint(sx), __float_as_uint(sy), __float_as_uint(sz), idx);
+                        ray[my_slot * 3 + 2] = make_uint4(prev, steps, kReady, my_pixel);
+                    }
+                    n_ready = nact;
+                    break;
+                }
+                // step until some lane stops (checked every 4 steps); idle lanes sit on a stop bit
+                bool walking;
+                do {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) walking = dda_step<kSmem>(vol, sx, sy, sz, dx, dy, dz, idx, prev, steps, ix, iy, iz);
+                } while (__ballot_sync(0xffffffffu, walking) == ~idle_mask);
+                if (my_slot >= 0 && !walking) { // stopped: filled voxel or border
+                    ray[my_slot * 3 + 0] = make_uint4(__float_as_uint(sx), __float_as_uint(sy), __float_as_uint(sz), idx);
+                    ray[my_slot * 3 + 2] = make_uint4(prev, steps, kDone, my_pixel);
+                    my_slot = -1;
+                    idx = 0;
+                }
+                idle_mask = __ballot_sync(0xffffffffu, my_slot < 0);
+            }
+            __syncwarp();
+        }
+    }
+
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        rays += __shfl_xor_sync(0xffffffffu, rays, o);
+        iters += __shfl_xor_sync(0xffffffffu, iters, o);
+    }
+    if (lane == 0) {
+        if (rays) atomicAdd(fb.stats + 0, rays);
+        if (iters) atomicAdd(fb.stats + 1, iters);
+    }
+}
