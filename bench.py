@@ -281,7 +281,7 @@ def run_cuda(args):
         steps = args.steps
         value = rays_all / (t_res * 1e-3) / 1e6
         e2e_value = rays_e_all / (t_e2e * 1e-3) / 1e6
-        # roofline of the dominant kernel (trace_paths_kernel), per launch on THIS rank:
+        # roofline of the dominant kernel (trace_paths_wave_kernel), per launch on THIS rank:
         # algorithmic bytes = 4 B per DDA iteration (one RGBA8 voxel record, trace.frag:76) +
         # 16 B per pixel of accumulator read-modify-write
         st = r.stats()
@@ -308,7 +308,7 @@ def run_cuda(args):
                     "d2h_bytes_per_step": int(frame_host.nbytes + 16), "ms_per_step": t_e2e / steps},
             "gpu_launches": launches_all,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": recorded_traffic(), "kernel": "trace_paths_kernel", "kernel_ms": kernel_s * 1e3,
+                         "traffic": recorded_traffic(), "kernel": "trace_paths_wave_kernel", "kernel_ms": kernel_s * 1e3,
                          "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                          "dda_iterations_per_launch": iters / steps,
                          "dda_iterations_per_s": (iters / steps) / kernel_s},

@@ -71,6 +71,8 @@ def main():
     ap.add_argument("--so", default=os.path.join(ROOT, "vtrace_b200", "librender.so"))
     ap.add_argument("--top", type=int, default=40)
     ap.add_argument("--regex", default=None, help="ncu -k regex when the report holds several kernels")
+    ap.add_argument("--buckets", action="store_true",
+                    help="aggregate per code region: a region starts at a '// ----' banner comment or a function definition")
     args = ap.parse_args()
 
     sass = sass_lines(args.so, args.kernel)
@@ -111,6 +113,38 @@ def main():
         ls = lines_cache[path]
         return ls[line - 1].strip()[:90] if line and 0 < line <= len(ls) else ""
 
+    if args.buckets:
+        import bisect
+        bounds = {}
+
+        def region(fname, line):
+            path = os.path.join(ROOT, "vtrace_b200", "csrc", fname)
+            if fname not in bounds:
+                try:
+                    ls = open(path).read().splitlines()
+                except OSError:
+                    ls = []
+                marks = [(i + 1, l.strip()) for i, l in enumerate(ls)
+                         if re.match(r"\s*// ----", l) or re.match(r"(template|__device__|__global__|static|inline|auto \w+ = \[)", l.strip())
+                         or re.match(r"\s*auto \w+ = \[&\]", l)]
+                bounds[fname] = marks
+            marks = bounds[fname]
+            k = bisect.bisect_right([m[0] for m in marks], line or 0) - 1
+            if k < 0:
+                return fname
+            # a template line is followed by the real signature: prefer that
+            name = marks[k][1]
+            if name.startswith("template") and k + 1 < len(marks) and marks[k + 1][0] <= (line or 0) + 0:
+                name = marks[k + 1][1]
+            return f"{fname}:{marks[k][0]} {name[:70]}"
+        bagg = collections.defaultdict(lambda: [0, 0, 0])
+        for (fname, line), a in agg.items():
+            b = bagg[region(fname, line)]
+            b[0] += a[0]; b[1] += a[1]; b[2] += a[2]
+        print(f"{'inst%':>7}{'samp%':>7}{'lanes':>7}  region")
+        for name, a in sorted(bagg.items(), key=lambda kv: -kv[1][0])[: args.top]:
+            print(f"{100 * a[0] / max(tot_inst, 1):7.2f}{100 * a[2] / max(tot_samp, 1):7.2f}{a[1] / max(a[0], 1):7.1f}  {name}")
+        return
     print(f"{'file:line':<22}{'inst%':>7}{'samp%':>7}{'thr/inst':>9}  source")
     for (fname, line), a in sorted(agg.items(), key=lambda kv: -kv[1][0])[: args.top]:
         print(f"{fname + ':' + str(line):<22}{100 * a[0] / max(tot_inst, 1):7.2f}{100 * a[2] / max(tot_samp, 1):7.2f}"

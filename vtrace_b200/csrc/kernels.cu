@@ -1255,8 +1255,7 @@ cudaError_t launch_trace_paths(const FrameParams& fp, const InstUniforms* inst, 
     if (fp.n_inst == 1 && !(fp.flags & (VT_FLAG_PERSISTENT_LANES | VT_FLAG_PER_PIXEL_PATHS))) {
         // single-instance scenes: warp-local wavefront engine (paths_wave.cuh)
         const size_t wsmem = wave_smem_bytes(arena_words, masks_in_smem);
-        const int n_items = n_tiles * (int)((fp.spp + kItemSpp - 1) / kItemSpp);
-        const int max_warps = (n_items + 0) > 0 ? n_items : 1;
+        const int max_warps = 1 << 30; // persistent: one resident wave, work is claimed dynamically
         if (masks_in_smem) {
             int grid = persistent_grid(trace_paths_wave_kernel<true>, wsmem, sm_count, max_warps, kWaveThreads);
             trace_paths_wave_kernel<true><<<grid, kWaveThreads, wsmem, stream>>>(fp, inst, mask_arena, arena_words, lut, fb);

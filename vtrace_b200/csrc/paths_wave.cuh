@@ -32,7 +32,7 @@ static constexpr int kWaveThreads = kWaveWarps * 32;
 static constexpr int kSlots = 64;        // paths in flight per warp
 static constexpr int kSlotGroups = kSlots / 32;
 static constexpr uint32_t kItemSpp = 16; // samples per work item (tile x 16 samples)
-static constexpr uint32_t kPoolBytes = kSlots * 96 + kSlots + 32; // slots + one byte list + the item's covered-pixel table
+static constexpr uint32_t kPoolBytes = kSlots * 96 + kSlots + 32 + 32 * 3 * 4; // slots + byte list + covered-pixel table + tile accumulators
 static_assert(kPoolBytes % 16 == 0, "pool alignment");
 
 enum SlotState : uint32_t { kFree = 0, kReady = 1, kDone = 3, kHit = 4 };
@@ -64,12 +64,19 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
     uint4* path = ray + kSlots * 3;
     uint8_t* list = reinterpret_cast<uint8_t*>(path + kSlots * 3);
     uint8_t* cov_pix = list + kSlots; // cov_pix[c] = tile-local index of the item's c-th covered pixel
+    uint32_t* wacc = reinterpret_cast<uint32_t*>(cov_pix + 32); // radiance sums of the current item's tile (2^-24 fixed point)
 
     const int tiles_x = (fp.width + kTileW - 1) / kTileW;
     const int tiles_y = (fp.height + kTileH - 1) / kTileH;
     const int n_tiles = tiles_x * tiles_y;
     const int n_chunks = (int)((fp.spp + kItemSpp - 1) / kItemSpp);
-    const int n_items = n_tiles * n_chunks;
+    // Only tiles that touch the instance's screen rectangle become work items; every other pixel sees
+    // nothing but sky and is written by the prologue below.
+    const bool any_cov = Ip->bounds[0] <= Ip->bounds[1] && Ip->bounds[2] <= Ip->bounds[3];
+    const int ctx0 = any_cov ? Ip->bounds[0] / kTileW : 0, ctx1 = any_cov ? Ip->bounds[1] / kTileW : -1;
+    const int cty0 = any_cov ? Ip->bounds[2] / kTileH : 0, cty1 = any_cov ? Ip->bounds[3] / kTileH : -1;
+    const int cov_w = ctx1 - ctx0 + 1, cov_tiles = cov_w * (cty1 - cty0 + 1);
+    const int n_items = cov_tiles * n_chunks;
 
     const float sky[3] = {53.0f / 100.0f, 81.0f / 100.0f, 92.0f / 100.0f}; // lib/command.c:57-59
     unsigned long long sky_q[3];
@@ -77,24 +84,71 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
     for (int c = 0; c < 3; ++c) sky_q[c] = __float2ull_rz((1.0f * sky[c]) * 16777216.0f);
     unsigned long long rays = 0, iters = 0;
 
+    // ---- prologue: pixels outside the screen rectangle see only sky, for every sample.  No other
+    // warp ever touches them, so a plain read-modify-write is enough (they still count as rays).
+    {
+        const int gw = blockIdx.x * kWaveWarps + warp, nw = gridDim.x * kWaveWarps;
+        for (int tile = gw; tile < n_tiles; tile += nw) {
+            const int tx = tile % tiles_x, ty = tile / tiles_x;
+            const int px = tx * kTileW + (lane & 7), py = ty * kTileH + (lane >> 3);
+            const bool in_frame = px < fp.width && py < fp.height;
+            const bool may_hit = !(px < Ip->bounds[0] || px > Ip->bounds[1] || py < Ip->bounds[2] || py > Ip->bounds[3]);
+            if (in_frame && !may_hit) {
+                const size_t p = (size_t)py * (size_t)fp.width + (size_t)px;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) fb.accum[3 * p + c] += sky_q[c] * fp.spp;
+                rays += fp.spp;
+            }
+        }
+    }
+
 #pragma unroll
     for (int g = 0; g < kSlotGroups; ++g) ray[(lane + 32 * g) * 3 + 2] = make_uint4(0u, 0u, kFree, 0u);
+    wacc[lane * 3 + 0] = 0u; wacc[lane * 3 + 1] = 0u; wacc[lane * 3 + 2] = 0u;
     __syncwarp();
     int n_free = kSlots, n_ready = 0, n_hit = 0;
 
     // current work item (warp-uniform)
     bool work_left = true;
     int it_x0 = 0, it_y0 = 0;
-    uint32_t it_ncov = 1, it_magic = 0, it_next = 0, it_njobs = 0, it_s0 = 0;
+    uint32_t it_tile = 0xFFFFFFFFu, it_ncov = 1, it_magic = 0, it_next = 0, it_njobs = 0, it_s0 = 0;
 
-    // adds one finished path's radiance (thr * sky, or nothing) to the frame accumulators
-    auto add_sky = [&](uint32_t pixel, float t0, float t1, float t2) {
+    // A path is identified by its pixel handle = tile << 5 | tile-local pixel.  Radiance of paths that
+    // belong to the warp's current tile goes to shared-memory accumulators (flushed once per item);
+    // stragglers of earlier items go straight to the frame accumulators.  Integer adds: order-free.
+    auto add_sky = [&](uint32_t handle, float t0, float t1, float t2) {
         const float thr[3] = {t0, t1, t2};
+        if ((handle >> 5) == it_tile) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float q = (thr[c] * sky[c]) * 16777216.0f;
-            if (q == q && q > 0.0f) atomicAdd(fb.accum + 3 * (size_t)pixel + c, __float2ull_rz(q));
+            for (int c = 0; c < 3; ++c) {
+                const float q = (thr[c] * sky[c]) * 16777216.0f;
+                if (q == q && q > 0.0f) atomicAdd(&wacc[(handle & 31u) * 3 + c], (uint32_t)__float2ull_rz(q));
+            }
+        } else {
+            const uint32_t tile = handle >> 5, pix = handle & 31u;
+            const uint32_t ty = tile / (uint32_t)tiles_x, tx = tile - ty * (uint32_t)tiles_x;
+            const size_t p = (size_t)(ty * kTileH + (pix >> 3)) * (size_t)fp.width + (size_t)(tx * kTileW + (pix & 7u));
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float q = (thr[c] * sky[c]) * 16777216.0f;
+                if (q == q && q > 0.0f) atomicAdd(fb.accum + 3 * p + c, __float2ull_rz(q));
+            }
         }
+    };
+    // moves the current tile's sums to the frame accumulators (lane = tile-local pixel)
+    auto flush_tile = [&]() {
+        __syncwarp();
+        const int my_px = it_x0 + (lane & 7), my_py = it_y0 + (lane >> 3);
+        if (it_tile != 0xFFFFFFFFu && my_px < fp.width && my_py < fp.height) {
+            const size_t p = (size_t)my_py * (size_t)fp.width + (size_t)my_px;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const uint32_t v = wacc[lane * 3 + c];
+                if (v) atomicAdd(fb.accum + 3 * p + c, (unsigned long long)v);
+                wacc[lane * 3 + c] = 0u;
+            }
+        }
+        __syncwarp();
     };
     // writes a ray that is about to walk (or whose slow-path result is final) into its slot
     auto store_ray = [&](uint32_t slot, const Dda& r, uint32_t idx, uint32_t prev, uint32_t steps, uint32_t state, uint32_t pixel) {
@@ -180,9 +234,13 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
         while (work_left && it_next >= it_njobs) {
             const int item = claim_tiles(fb.stats + 2, lane, 1);
             if (item >= n_items) { work_left = false; break; }
-            const int chunk = item / n_tiles, tile = item - chunk * n_tiles;
-            it_x0 = (tile % tiles_x) * kTileW;
-            it_y0 = (tile / tiles_x) * kTileH;
+            flush_tile();
+            const int chunk = item / cov_tiles, ct = item - chunk * cov_tiles; // chunk-major: a tile's chunks are spread in time
+            const int cy = ct / cov_w, cx = ct - cy * cov_w;
+            const int tile = (cty0 + cy) * tiles_x + (ctx0 + cx);
+            it_tile = (uint32_t)tile;
+            it_x0 = (ctx0 + cx) * kTileW;
+            it_y0 = (cty0 + cy) * kTileH;
             const int my_px = it_x0 + (lane & 7), my_py = it_y0 + (lane >> 3);
             const bool in_frame = my_px < fp.width && my_py < fp.height;
             const bool may_hit = in_frame && !(my_px < Ip->bounds[0] || my_px > Ip->bounds[1] || my_py < Ip->bounds[2] || my_py > Ip->bounds[3]);
@@ -193,12 +251,6 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
             const uint32_t ns = fp.spp - it_s0 < kItemSpp ? fp.spp - it_s0 : kItemSpp;
             it_njobs = it_ncov * ns;
             it_next = 0;
-            if (chunk == 0 && in_frame && !may_hit) { // pixels outside the screen rectangle see only sky, for every sample
-                const size_t p = (size_t)my_py * (size_t)fp.width + (size_t)my_px;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) atomicAdd(fb.accum + 3 * p + c, sky_q[c] * fp.spp);
-                rays += fp.spp;
-            }
             if (it_ncov == 0) it_ncov = 1; // (no jobs; keeps the division below defined)
             it_magic = 0xFFFFFFFFu / it_ncov + 1u; // floor(job / ncov) == umulhi(job, magic) for job * ncov < 2^32
             __syncwarp();
@@ -208,12 +260,15 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
         // ---- pick the next full batch (or the best partial one when the pool runs dry) -----------
         int action; // 0 primary, 1 bounce, 2 march, 3 stop
         const int low = (int)fp.refill_threshold;
-        if (n_hit >= 32) action = 1;
-        else if (n_free >= 32 && jobs) action = 0;
-        else if (n_ready >= low) action = 2;
-        else if (n_hit > 0 && (!jobs || n_hit >= n_free)) action = 1;
-        else if (jobs && n_free > 0) action = 0;
+        const int can_primary = jobs ? n_free : 0;
+        if (n_hit >= 32) action = 1;                          // full bounce batch
+        else if (can_primary >= 32) action = 0;               // full camera batch
+        else if (n_ready >= 32) action = 2;                   // a full warp of rays is waiting
+        else if (n_hit >= low && n_hit >= can_primary) action = 1; // otherwise top the pool up with the better partial batch
+        else if (can_primary >= low) action = 0;
         else if (n_ready > 0) action = 2;
+        else if (n_hit > 0) action = 1;
+        else if (can_primary > 0) action = 0;
         else action = 3;
         if (action == 3) break;
 
@@ -235,6 +290,7 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
                 rng_init(rng, fp.seed, pixel, fp.sample_first + (it_s0 + si) * fp.sample_stride);
                 const float jx = rng_u01(rng), jy = rng_u01(rng);
                 const float fx = (float)px + jx, fy = (float)py + jy;
+                const uint32_t handle = it_tile << 5 | pix;
                 rays += 1;
                 // camera ray in the instance's model space: o = eye, d = dirm * (x_ndc, y_ndc, 1)
                 const float x_ndc = fx * fp.sxn - 1.0f;
@@ -251,7 +307,7 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
                 int axis;
                 if (!slab_unit_cube(o, lo3, hi3, d, tn, axis)) { // leaves through the sky; the slot stays free
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) atomicAdd(fb.accum + 3 * (size_t)pixel + c, sky_q[c]);
+                    for (int c = 0; c < 3; ++c) atomicAdd(&wacc[pix * 3 + c], (uint32_t)sky_q[c]);
                 } else {
                     float mp[3], pos[3];
                     entry_point(o, d, tn, axis, mp);
@@ -259,7 +315,7 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
                     for (int k = 0; k < 3; ++k) pos[k] = (mp[k] + 0.5f) * size[k];
                     const float one[3] = {1.0f, 1.0f, 1.0f};
                     const int32_t none[3] = {0, 0, 0};
-                    st = launch_ray(slot, pixel, pos, d, false, none, one, rng.key, (uint32_t)axis << 4 | rng.ctr << 8);
+                    st = launch_ray(slot, handle, pos, d, false, none, one, rng.key, (uint32_t)axis << 4 | rng.ctr << 8);
                 }
             }
             it_next += n;
@@ -396,6 +452,7 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
         }
     }
 
+    flush_tile();
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
         rays += __shfl_xor_sync(0xffffffffu, rays, o);

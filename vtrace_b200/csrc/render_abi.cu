@@ -61,7 +61,7 @@ struct State {
 
     cudaEvent_t ev_begin = nullptr, ev_trace0 = nullptr, ev_trace1 = nullptr, ev_end = nullptr;
     bool frame_pending = false;
-    uint32_t refill_threshold = 8; // tuning knob of the persistent-lane kernel (VT_REFILL)
+    uint32_t refill_threshold = 16; // tuning knob of the wavefront / persistent-lane kernels (VT_REFILL)
 
     vt_stats stats{};
     user_input input{};
@@ -351,7 +351,7 @@ extern "C" uint64_t entry(void) {
     g.cfg.total_spp = env_u32("VT_TOTAL_SPP", 0);
     g.cfg.max_frames = (int32_t)env_u32("VT_MAX_FRAMES", 0);
     g.cfg.device = dev;
-    g.refill_threshold = env_u32("VT_REFILL", 8);
+    g.refill_threshold = env_u32("VT_REFILL", 16);
     if (g.refill_threshold < 1) g.refill_threshold = 1;
     if (g.refill_threshold > 32) g.refill_threshold = 32;
 
