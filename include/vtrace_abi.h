@@ -96,6 +96,7 @@ void cleanup(void);
 #define VT_FLAG_NO_HIT_RECORDS 2u  /* do not write the per-pixel hit records                    */
 #define VT_FLAG_FORCE_GLOBAL_MASKS 4u /* keep traversal masks in global memory (no smem staging) */
 #define VT_FLAG_PERSISTENT_LANES 8u /* PATHS, one instance: persistent-lane schedule (job pool per warp tile) */
+#define VT_FLAG_NO_BINNING 32u      /* visit every instance per pixel instead of the screen-space bins (testing) */
 #define VT_FLAG_PER_PIXEL_PATHS 16u /* PATHS, one instance: the general per-pixel kernel instead of the wavefront engine */
 
 /* Per-pixel derived hit record (not an output of the reference). 16 bytes. */

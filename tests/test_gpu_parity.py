@@ -198,6 +198,42 @@ def test_multi_instance_grid(scene, assets):
     assert len(np.unique(got["instance"])) > 10
 
 
+def test_many_instances_binned(renderer, scene, monkeypatch):
+    """1000 chunk instances (the shape of the reference's paged terrain, src/world.rs:163-198): the
+    screen-space bins must give exactly what visiting every instance gives — and what the oracle gives."""
+    rng = np.random.default_rng(3)
+    t = scene.add(RawVolume(make_volume(rng, 16, 16, 16, fill=0.35), 16, 16, 16))
+    models = [(glm.scale(glm.translate(glm.identity(), (2.2 * x, 2.2 * y - 9.0, 2.2 * z)), (2.0, 2.0, 2.0)), t)
+              for x in range(-5, 5) for y in range(-5, 5) for z in range(-5, 5)]
+    scene.set_instances(models)
+    P = glm.perspective(glm.REFERENCE_FOV, 640 / 360, glm.REFERENCE_NEAR, glm.REFERENCE_FAR)
+    V = glm.look_at((14.0, 4.0, 17.0), (0.0, -9.0, 0.0), (0.0, 1.0, 0.0))
+    got, st = scene.check_primary(P, V, 640, 360, what="1000 instances, binned")
+    assert len(np.unique(got["instance"])) > 100
+    unbinned, _ = scene.check_primary(P, V, 640, 360, flags=abi.FLAG_NO_BINNING, what="1000 instances, unbinned")
+    assert np.array_equal(got, unbinned)
+
+
+def test_bin_list_overflow_grows_and_retries(renderer, oracle, assets, monkeypatch):
+    monkeypatch.setenv("VT_BIN_CAP", "1000")  # far too small: the first attempt overflows
+    renderer.reset()
+    sc = Scene(renderer, oracle)
+    a = sc.add(assets["Treasure"])
+    b = sc.add(assets["AncientTemple"])
+    grid = scenes.entity_grid(a, b)
+    models = []
+    for m in grid:
+        m = m.reshape(4, 4).copy()
+        tid = int(m.reshape(16).view(np.uint32)[15])
+        m[3][3] = 1.0
+        models.append((m, tid))
+    sc.set_instances(models)
+    P = glm.perspective(glm.REFERENCE_FOV, 640 / 360, glm.REFERENCE_NEAR, glm.REFERENCE_FAR)
+    V = glm.look_at((0.0, -2.0, 0.0), (3.0, -5.0, 2.0), (0.0, 1.0, 0.0))
+    sc.check_primary(P, V, 640, 360, what="bin overflow retry")
+    sc.check_paths(P, V, 160, 90, spp=2, bounces=2, what="bin overflow retry, paths")
+
+
 def test_rotated_scaled_instances(scene, assets):
     t = scene.add(assets["Treasure"])
     m1 = glm.scale(glm.rotate(glm.translate(glm.identity(), (0.4, 0.1, -0.3)), 0.7, (0.3, 1.0, 0.2)), (1.3, 0.7, 1.9))

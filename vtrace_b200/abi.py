@@ -14,7 +14,7 @@ from . import build as _build
 
 VT_MISS = 0xFFFFFFFF
 MODE_PRIMARY, MODE_PATHS = 0, 1
-FLAG_VIEWPORT_H_IS_W, FLAG_NO_HIT_RECORDS, FLAG_FORCE_GLOBAL_MASKS, FLAG_PERSISTENT_LANES, FLAG_PER_PIXEL_PATHS = 1, 2, 4, 8, 16
+FLAG_VIEWPORT_H_IS_W, FLAG_NO_HIT_RECORDS, FLAG_FORCE_GLOBAL_MASKS, FLAG_PERSISTENT_LANES, FLAG_PER_PIXEL_PATHS, FLAG_NO_BINNING = 1, 2, 4, 8, 16, 32
 
 HIT_DTYPE = np.dtype([("hit_voxel", "<u4"), ("packed", "<u4"), ("instance", "<u4"), ("iters", "<u4")])
 

@@ -256,6 +256,56 @@ cudaError_t launch_instance_setup(const float* instances, uint32_t n, const Volu
 }
 
 // -------------------------------------------------------------------------------------------
+// bin_instances_kernel: one warp per 16x16-pixel bin.  Pass 1 counts the instances whose screen
+// rectangle touches the bin, one atomic reserves the bin's segment of the list, pass 2 writes the
+// instance indices in ascending order (= draw order, which the depth/blend rule depends on).
+__global__ void bin_instances_kernel(const InstUniforms* __restrict__ inst, uint32_t n_inst, uint32_t bins_x, uint32_t bins_y,
+                                     uint32_t* __restrict__ offset, uint32_t* __restrict__ count, uint32_t* __restrict__ list,
+                                     uint32_t capacity, uint32_t* __restrict__ cursor) {
+    const uint32_t bin = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+    if (bin >= bins_x * bins_y) return;
+    const int bx0 = (int)((bin % bins_x) << kBinShift), by0 = (int)((bin / bins_x) << kBinShift);
+    const int bx1 = bx0 + (1 << kBinShift) - 1, by1 = by0 + (1 << kBinShift) - 1;
+    uint32_t n = 0;
+    for (uint32_t i0 = 0; i0 < n_inst; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        bool t = false;
+        if (i < n_inst) {
+            const int4 b = *reinterpret_cast<const int4*>(inst[i].bounds);
+            t = !(b.y < bx0 || b.x > bx1 || b.w < by0 || b.z > by1);
+        }
+        n += __popc(__ballot_sync(0xffffffffu, t));
+    }
+    uint32_t base = 0;
+    if (lane == 0) base = n ? atomicAdd(cursor, n) : 0u;
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (lane == 0) { offset[bin] = base; count[bin] = (base + n <= capacity) ? n : 0xFFFFFFFFu; }
+    if (base + n > capacity) return; // overflow: the host sees cursor > capacity and retries with a larger list
+    uint32_t w = base;
+    for (uint32_t i0 = 0; i0 < n_inst; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        bool t = false;
+        if (i < n_inst) {
+            const int4 b = *reinterpret_cast<const int4*>(inst[i].bounds);
+            t = !(b.y < bx0 || b.x > bx1 || b.w < by0 || b.z > by1);
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, t);
+        if (t) list[w + __popc(m & ((1u << lane) - 1u))] = i;
+        w += __popc(m);
+    }
+}
+
+cudaError_t launch_bin_instances(const InstUniforms* inst, uint32_t n_inst, uint32_t bins_x, uint32_t bins_y, uint32_t* offset,
+                                 uint32_t* count, uint32_t* list, uint32_t capacity, uint32_t* cursor, cudaStream_t stream) {
+    const uint32_t warps = bins_x * bins_y;
+    const int threads = 256;
+    bin_instances_kernel<<<(warps * 32 + threads - 1) / threads, threads, 0, stream>>>(inst, n_inst, bins_x, bins_y, offset, count, list,
+                                                                                     capacity, cursor);
+    return cudaGetLastError();
+}
+
+// -------------------------------------------------------------------------------------------
 // rasteriser restatement: which point of the proxy cube's front faces covers the sample
 
 // lo[k] = -0.5 - o[k], hi[k] = 0.5 - o[k] (precomputed per instance for camera rays)
@@ -608,7 +658,7 @@ __device__ __forceinline__ int claim_tiles(unsigned long long* counter, int lane
 
 template <bool kSmem>
 __global__ void __launch_bounds__(kBlockThreads) trace_primary_kernel(const __grid_constant__ FrameParams fp,
-                                                                      const InstUniforms* __restrict__ inst,
+                                                                      const InstUniforms* __restrict__ inst, const BinTable bins,
                                                                       const uint32_t* __restrict__ mask_arena,
                                                                       uint32_t arena_words, SrgbTables lut, FrameBuffers fb) {
     stage_tables<kSmem>(mask_arena, arena_words, lut.decode);
@@ -640,7 +690,16 @@ __global__ void __launch_bounds__(kBlockThreads) trace_primary_kernel(const __gr
             uint32_t dst[4] = {clear_r, clear_g, clear_b, 255u};
             float zbuf = 1.0f; // lib/command.c:60
             HitRecord rec{VT_MISS, 0u, VT_MISS, 0u};
-            for (uint32_t i = 0; i < fp.n_inst; ++i) { // draw order = instance order, lib/command.c:102
+            // draw order = instance order (lib/command.c:102); with bins, only the instances whose screen
+            // rectangle touches this pixel's 16x16 bin are visited (same order, same results)
+            uint32_t k_begin = 0, k_end = fp.n_inst;
+            if (bins.enabled) {
+                const uint32_t bin = ((uint32_t)py >> kBinShift) * bins.bins_x + ((uint32_t)px >> kBinShift);
+                k_begin = __ldg(bins.offset + bin);
+                k_end = k_begin + __ldg(bins.count + bin);
+            }
+            for (uint32_t k = k_begin; k < k_end; ++k) {
+                const uint32_t i = bins.enabled ? __ldg(bins.list + k) : k;
                 Fragment f;
                 run_fragment<kSmem>(fp, inst + i, mask_base, px, py, fx, fy, f);
                 if (!f.covered) continue;
@@ -722,9 +781,9 @@ struct PathHit {
 // that order whose DDA hits wins.  cam != nullptr: camera ray (o = eye in model space,
 // d = dirm * (x_ndc, y_ndc, 1)); else world ray (o = Mi*(ow,1), d = Mi*(dw,0)).
 template <bool kSmem>
-__device__ void trace_world(const FrameParams& fp, const InstUniforms* __restrict__ inst, const uint32_t* mask_base, uint32_t skip,
-                            const float* cam, int px, int py, const float ow[3], const float dw[3], PathHit& out,
-                            unsigned long long& iters) {
+__device__ void trace_world(const FrameParams& fp, const InstUniforms* __restrict__ inst, const BinTable& bins,
+                            const uint32_t* mask_base, uint32_t skip, const float* cam, int px, int py, const float ow[3],
+                            const float dw[3], PathHit& out, unsigned long long& iters) {
     out.hit = false;
     float last_t = -INFINITY;
     uint32_t last_j = 0;
@@ -735,7 +794,16 @@ __device__ void trace_world(const FrameParams& fp, const InstUniforms* __restric
         uint32_t best_j = 0;
         int best_axis = 0;
         float bo[3] = {0, 0, 0}, bd[3] = {0, 0, 0};
-        for (uint32_t j = 0; j < fp.n_inst; ++j) {
+        // camera rays only need the instances binned to their pixel; world rays visit every instance
+        uint32_t k_begin = 0, k_end = fp.n_inst;
+        const bool binned = cam && bins.enabled;
+        if (binned) {
+            const uint32_t bin = ((uint32_t)py >> kBinShift) * bins.bins_x + ((uint32_t)px >> kBinShift);
+            k_begin = __ldg(bins.offset + bin);
+            k_end = k_begin + __ldg(bins.count + bin);
+        }
+        for (uint32_t k = k_begin; k < k_end; ++k) {
+            const uint32_t j = binned ? __ldg(bins.list + k) : k;
             const InstUniforms* J = inst + j;
             if (j == skip || !J->valid) continue;
             float o[3], d[3];
@@ -786,8 +854,8 @@ __device__ void trace_world(const FrameParams& fp, const InstUniforms* __restric
 }
 
 template <bool kSmem>
-__device__ void trace_path(const FrameParams& fp, const InstUniforms* __restrict__ inst, const uint32_t* mask_base,
-                           const float* __restrict__ dec, int px, int py, uint32_t sample, float L[3],
+__device__ void trace_path(const FrameParams& fp, const InstUniforms* __restrict__ inst, const BinTable& bins,
+                           const uint32_t* mask_base, const float* __restrict__ dec, int px, int py, uint32_t sample, float L[3],
                            unsigned long long& rays, unsigned long long& iters) {
     Rng rng;
     rng_init(rng, fp.seed, (uint32_t)py * (uint32_t)fp.width + (uint32_t)px, sample);
@@ -797,7 +865,7 @@ __device__ void trace_path(const FrameParams& fp, const InstUniforms* __restrict
     PathHit cur;
     const float cam[2] = {fx * fp.sxn - 1.0f, fy * fp.syn - 1.0f};
     const float zero3[3] = {0.0f, 0.0f, 0.0f};
-    trace_world<kSmem>(fp, inst, mask_base, 0xFFFFFFFFu, cam, px, py, zero3, zero3, cur, iters);
+    trace_world<kSmem>(fp, inst, bins, mask_base, 0xFFFFFFFFu, cam, px, py, zero3, zero3, cur, iters);
     rays += 1;
     const float sky[3] = {53.0f / 100.0f, 81.0f / 100.0f, 92.0f / 100.0f}; // lib/command.c:57-59
     float thr[3] = {1.0f, 1.0f, 1.0f};
@@ -868,7 +936,7 @@ __device__ void trace_path(const FrameParams& fp, const InstUniforms* __restrict
                 ow[k] = ((J->M[0 * 3 + k] * pm[0] + J->M[1 * 3 + k] * pm[1]) + J->M[2 * 3 + k] * pm[2]) + J->M[3 * 3 + k];
                 dw[k] = (J->M[0 * 3 + k] * dm[0] + J->M[1 * 3 + k] * dm[1]) + J->M[2 * 3 + k] * dm[2];
             }
-            trace_world<kSmem>(fp, inst, mask_base, cur.instance, nullptr, 0, 0, ow, dw, next, iters);
+            trace_world<kSmem>(fp, inst, bins, mask_base, cur.instance, nullptr, 0, 0, ow, dw, next, iters);
         }
         cur = next;
     }
@@ -876,7 +944,7 @@ __device__ void trace_path(const FrameParams& fp, const InstUniforms* __restrict
 
 template <bool kSmem>
 __global__ void __launch_bounds__(kBlockThreads) trace_paths_kernel(const __grid_constant__ FrameParams fp,
-                                                                    const InstUniforms* __restrict__ inst,
+                                                                    const InstUniforms* __restrict__ inst, const BinTable bins,
                                                                     const uint32_t* __restrict__ mask_arena,
                                                                     uint32_t arena_words, SrgbTables lut, FrameBuffers fb) {
     stage_tables<kSmem>(mask_arena, arena_words, lut.decode);
@@ -907,9 +975,17 @@ __global__ void __launch_bounds__(kBlockThreads) trace_paths_kernel(const __grid
         // Pixels outside every instance's screen rectangle: all spp paths leave through the sky after
         // the primary segment; their sum is known without tracing them (they still count as rays).
         bool may_hit = false;
-        for (uint32_t i = 0; i < fp.n_inst; ++i) {
-            const InstUniforms* Ip = inst + i;
-            may_hit = may_hit || !(px < Ip->bounds[0] || px > Ip->bounds[1] || py < Ip->bounds[2] || py > Ip->bounds[3]);
+        {
+            uint32_t k_begin = 0, k_end = fp.n_inst;
+            if (bins.enabled) {
+                const uint32_t bin = ((uint32_t)py >> kBinShift) * bins.bins_x + ((uint32_t)px >> kBinShift);
+                k_begin = __ldg(bins.offset + bin);
+                k_end = k_begin + __ldg(bins.count + bin);
+            }
+            for (uint32_t k = k_begin; k < k_end; ++k) {
+                const InstUniforms* Ip = inst + (bins.enabled ? __ldg(bins.list + k) : k);
+                may_hit = may_hit || !(px < Ip->bounds[0] || px > Ip->bounds[1] || py < Ip->bounds[2] || py > Ip->bounds[3]);
+            }
         }
         unsigned long long acc[3] = {0, 0, 0};
         if (!may_hit) {
@@ -919,7 +995,7 @@ __global__ void __launch_bounds__(kBlockThreads) trace_paths_kernel(const __grid
         } else {
             for (uint32_t k = 0; k < fp.spp; ++k) {
                 float L[3];
-                trace_path<kSmem>(fp, inst, mask_base, dec, px, py, fp.sample_first + k * fp.sample_stride, L, rays, iters);
+                trace_path<kSmem>(fp, inst, bins, mask_base, dec, px, py, fp.sample_first + k * fp.sample_stride, L, rays, iters);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const float q = L[c] * 16777216.0f;
@@ -1234,22 +1310,24 @@ static int persistent_grid(K kernel, size_t smem, int sm_count, int n_tiles, int
     return (int)(grid < 1 ? 1 : grid);
 }
 
-cudaError_t launch_trace_primary(const FrameParams& fp, const InstUniforms* inst, const uint32_t* mask_arena, uint32_t arena_words,
-                                 bool masks_in_smem, SrgbTables lut, FrameBuffers fb, int sm_count, cudaStream_t stream) {
+cudaError_t launch_trace_primary(const FrameParams& fp, const InstUniforms* inst, BinTable bins, const uint32_t* mask_arena,
+                                 uint32_t arena_words, bool masks_in_smem, SrgbTables lut, FrameBuffers fb, int sm_count,
+                                 cudaStream_t stream) {
     const int n_tiles = ((fp.width + kTileW - 1) / kTileW) * ((fp.height + kTileH - 1) / kTileH);
     const size_t smem = trace_smem_bytes(arena_words, masks_in_smem);
     if (masks_in_smem) {
         const int grid = persistent_grid(trace_primary_kernel<true>, smem, sm_count, n_tiles);
-        trace_primary_kernel<true><<<grid, kBlockThreads, smem, stream>>>(fp, inst, mask_arena, arena_words, lut, fb);
+        trace_primary_kernel<true><<<grid, kBlockThreads, smem, stream>>>(fp, inst, bins, mask_arena, arena_words, lut, fb);
     } else {
         const int grid = persistent_grid(trace_primary_kernel<false>, smem, sm_count, n_tiles);
-        trace_primary_kernel<false><<<grid, kBlockThreads, smem, stream>>>(fp, inst, mask_arena, arena_words, lut, fb);
+        trace_primary_kernel<false><<<grid, kBlockThreads, smem, stream>>>(fp, inst, bins, mask_arena, arena_words, lut, fb);
     }
     return cudaGetLastError();
 }
 
-cudaError_t launch_trace_paths(const FrameParams& fp, const InstUniforms* inst, const uint32_t* mask_arena, uint32_t arena_words,
-                               bool masks_in_smem, SrgbTables lut, FrameBuffers fb, int sm_count, cudaStream_t stream) {
+cudaError_t launch_trace_paths(const FrameParams& fp, const InstUniforms* inst, BinTable bins, const uint32_t* mask_arena,
+                               uint32_t arena_words, bool masks_in_smem, SrgbTables lut, FrameBuffers fb, int sm_count,
+                               cudaStream_t stream) {
     const int n_tiles = ((fp.width + kTileW - 1) / kTileW) * ((fp.height + kTileH - 1) / kTileH);
     const size_t smem = trace_smem_bytes(arena_words, masks_in_smem);
     if (fp.n_inst == 1 && !(fp.flags & (VT_FLAG_PERSISTENT_LANES | VT_FLAG_PER_PIXEL_PATHS))) {
@@ -1277,10 +1355,10 @@ cudaError_t launch_trace_paths(const FrameParams& fp, const InstUniforms* inst, 
     }
     if (masks_in_smem) {
         const int grid = persistent_grid(trace_paths_kernel<true>, smem, sm_count, n_tiles);
-        trace_paths_kernel<true><<<grid, kBlockThreads, smem, stream>>>(fp, inst, mask_arena, arena_words, lut, fb);
+        trace_paths_kernel<true><<<grid, kBlockThreads, smem, stream>>>(fp, inst, bins, mask_arena, arena_words, lut, fb);
     } else {
         const int grid = persistent_grid(trace_paths_kernel<false>, smem, sm_count, n_tiles);
-        trace_paths_kernel<false><<<grid, kBlockThreads, smem, stream>>>(fp, inst, mask_arena, arena_words, lut, fb);
+        trace_paths_kernel<false><<<grid, kBlockThreads, smem, stream>>>(fp, inst, bins, mask_arena, arena_words, lut, fb);
     }
     return cudaGetLastError();
 }

@@ -14,6 +14,7 @@
 //   * framebuffer   : 16-byte hit records, RGBA8 colour, D32 depth, 3 x u64 accumulators.
 #pragma once
 
+#include <cstddef>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -52,9 +53,9 @@ struct __align__(16) InstUniforms {
     float dirm[12];  // inverse(M)3x3 * RD rows 0-2: clip point -> model-space ray direction
     float eye_m[3];  // camera position in model space
     uint32_t valid;  // texture id in range
+    int32_t bounds[4]; // conservative screen rectangle of the proxy cube: x0, x1, y0, y1 (inclusive); 16-byte aligned
     float slab_lo[3]; // -0.5 - eye_m
     float slab_hi[3]; //  0.5 - eye_m
-    int32_t bounds[4]; // conservative screen rectangle of the proxy cube: x0, x1, y0, y1 (inclusive)
     uint32_t tex;
     uint32_t w, h, d;
     uint32_t xb, yb;
@@ -63,6 +64,9 @@ struct __align__(16) InstUniforms {
     uint32_t pad;
     const uint8_t* rgba;
 };
+
+static_assert(offsetof(InstUniforms, bounds) % 16 == 0, "bounds are loaded as one int4");
+static_assert(sizeof(InstUniforms) % 16 == 0, "instance table stride");
 
 struct HitRecord { uint32_t hit_voxel, packed, instance, iters; };
 
@@ -73,6 +77,18 @@ struct FrameBuffers {
     unsigned long long* accum; // 3 per pixel
     unsigned long long* stats; // [0] rays, [1] iterations, [2] tile-scheduler counter, [3] spare
 };
+
+// Screen-space instance bins (what a tiling rasteriser's binner produces): for every 16x16-pixel
+// bin the instances whose conservative screen rectangle touches it, ascending = draw order.
+struct BinTable {
+    const uint32_t* offset; // per bin: first entry in `list`
+    const uint32_t* count;  // per bin: number of entries
+    const uint32_t* list;   // instance indices
+    uint32_t bins_x, bins_y;
+    uint32_t enabled;       // 0: loop over all instances
+    uint32_t pad;
+};
+static constexpr uint32_t kBinShift = 4; // 16x16 pixels
 
 struct SrgbTables {
     const float* decode;    // 256
@@ -89,10 +105,14 @@ cudaError_t launch_build_mask(const uint8_t* rgba, uint32_t w, uint32_t h, uint3
                               uint32_t* mask, uint32_t mask_words, cudaStream_t stream);
 cudaError_t launch_instance_setup(const float* instances, uint32_t n, const VolumeDesc* volumes, FrameParams fp,
                                   InstUniforms* out, cudaStream_t stream);
-cudaError_t launch_trace_primary(const FrameParams& fp, const InstUniforms* inst, const uint32_t* mask_arena,
+// bins the instances' screen rectangles; *cursor (device) ends up holding the number of list entries
+// needed — if it exceeds `capacity` the lists are incomplete and the caller must retry with more room
+cudaError_t launch_bin_instances(const InstUniforms* inst, uint32_t n_inst, uint32_t bins_x, uint32_t bins_y, uint32_t* offset,
+                                 uint32_t* count, uint32_t* list, uint32_t capacity, uint32_t* cursor, cudaStream_t stream);
+cudaError_t launch_trace_primary(const FrameParams& fp, const InstUniforms* inst, BinTable bins, const uint32_t* mask_arena,
                                  uint32_t arena_words, bool masks_in_smem, SrgbTables lut, FrameBuffers fb,
                                  int sm_count, cudaStream_t stream);
-cudaError_t launch_trace_paths(const FrameParams& fp, const InstUniforms* inst, const uint32_t* mask_arena,
+cudaError_t launch_trace_paths(const FrameParams& fp, const InstUniforms* inst, BinTable bins, const uint32_t* mask_arena,
                                uint32_t arena_words, bool masks_in_smem, SrgbTables lut, FrameBuffers fb,
                                int sm_count, cudaStream_t stream);
 cudaError_t launch_resolve(const unsigned long long* accum, uint32_t n_pixels, uint32_t total_spp, SrgbTables lut,

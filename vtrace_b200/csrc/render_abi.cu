@@ -18,6 +18,7 @@ using namespace vt;
 
 constexpr uint32_t kMaxTextures = 65536; // MAX_TEXTURES, lib/common.h:35
 constexpr size_t kSmemMaskBudget = 160 * 1024; // masks up to this size are staged in shared memory
+constexpr uint32_t kBinMinInstances = 16;       // below this the per-pixel loop over all instances is cheaper than binning
 
 struct State {
     bool inited = false;
@@ -42,6 +43,17 @@ struct State {
     float* d_inst = nullptr;
     InstUniforms* d_iu = nullptr;
     uint32_t inst_cap = 0, inst_count = 1;
+
+    // screen-space instance bins (used when the scene has more than kBinMinInstances instances)
+    uint32_t* d_bin_offset = nullptr;
+    uint32_t* d_bin_count = nullptr;
+    uint32_t* d_bin_list = nullptr;
+    uint32_t* d_bin_cursor = nullptr;
+    uint32_t* h_bin_cursor = nullptr; // pinned
+    uint32_t bin_cap_bins = 0, bin_cap_list = 0;
+    bool bins_used = false;
+    float last_P[16] = {0}, last_V[16] = {0};
+    bool last_clear = false, last_resolve = false;
 
     // tables
     float* d_dec = nullptr;
@@ -163,10 +175,29 @@ int ensure_instances(uint32_t n) {
     return 0;
 }
 
+int render_async(const float* P, const float* V, bool clear_accum, bool resolve);
+
 int finish_frame() {
     if (!g.frame_pending) return 0;
     CK(cudaStreamSynchronize(g.stream));
     g.frame_pending = false;
+    // the binner reports how many list entries it needed; if they did not fit, the frame is incomplete:
+    // grow the list and render it again
+    for (int attempt = 0; g.bins_used && *g.h_bin_cursor > g.bin_cap_list && attempt < 4; ++attempt) {
+        const uint32_t need = *g.h_bin_cursor + *g.h_bin_cursor / 2;
+        cudaFree(g.d_bin_list);
+        g.d_bin_list = nullptr;
+        g.bin_cap_list = 0;
+        CK(cudaMalloc(&g.d_bin_list, (size_t)need * 4));
+        g.bin_cap_list = need;
+        g.stats.frames -= 1;
+        float P[16], V[16];
+        memcpy(P, g.last_P, sizeof P);
+        memcpy(V, g.last_V, sizeof V);
+        if (render_async(P, V, g.last_clear, g.last_resolve)) return -1;
+        CK(cudaStreamSynchronize(g.stream));
+        g.frame_pending = false;
+    }
     float ms = 0.0f;
     if (cudaEventElapsedTime(&ms, g.ev_trace0, g.ev_trace1) == cudaSuccess) g.stats.last_trace_ms = ms;
     if (cudaEventElapsedTime(&ms, g.ev_begin, g.ev_end) == cudaSuccess) g.stats.last_frame_ms = ms;
@@ -227,10 +258,43 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
     }
     if (ensure_instances(g.inst_count)) return -1;
 
+    memcpy(g.last_P, P, sizeof g.last_P);
+    memcpy(g.last_V, V, sizeof g.last_V);
+    g.last_clear = clear_accum;
+    g.last_resolve = resolve;
+
     CK(cudaEventRecord(g.ev_begin, g.stream));
     CK(cudaMemsetAsync(g.d_stats, 0, 4 * sizeof(unsigned long long), g.stream));
     CK(launch_instance_setup(g.d_inst, g.inst_count, g.d_vols, fp, g.d_iu, g.stream));
     g.stats.launches += 1;
+
+    // many instances: bin their screen rectangles (16x16-pixel bins) so a pixel only visits its own
+    BinTable bins{};
+    g.bins_used = g.inst_count > kBinMinInstances && !(g.cfg.flags & VT_FLAG_NO_BINNING);
+    if (g.bins_used) {
+        const uint32_t bx = (g.cfg.width + (1u << kBinShift) - 1) >> kBinShift, by = (g.cfg.height + (1u << kBinShift) - 1) >> kBinShift;
+        if (bx * by > g.bin_cap_bins) {
+            CK(cudaStreamSynchronize(g.stream));
+            cudaFree(g.d_bin_offset); cudaFree(g.d_bin_count);
+            g.d_bin_offset = g.d_bin_count = nullptr;
+            CK(cudaMalloc(&g.d_bin_offset, (size_t)bx * by * 4));
+            CK(cudaMalloc(&g.d_bin_count, (size_t)bx * by * 4));
+            g.bin_cap_bins = bx * by;
+        }
+        if (!g.d_bin_list) {
+            size_t cap = (size_t)g.inst_count * 64 > (1u << 20) ? (size_t)g.inst_count * 64 : (1u << 20);
+            cap = env_u32("VT_BIN_CAP", (uint32_t)cap); // (tests shrink it to exercise the grow-and-retry path)
+            CK(cudaMalloc(&g.d_bin_list, cap * 4));
+            g.bin_cap_list = (uint32_t)cap;
+        }
+        CK(cudaMemsetAsync(g.d_bin_cursor, 0, 4, g.stream));
+        CK(launch_bin_instances(g.d_iu, g.inst_count, bx, by, g.d_bin_offset, g.d_bin_count, g.d_bin_list, g.bin_cap_list,
+                                g.d_bin_cursor, g.stream));
+        CK(cudaMemcpyAsync(g.h_bin_cursor, g.d_bin_cursor, 4, cudaMemcpyDeviceToHost, g.stream));
+        g.stats.launches += 1;
+        bins.offset = g.d_bin_offset; bins.count = g.d_bin_count; bins.list = g.d_bin_list;
+        bins.bins_x = bx; bins.bins_y = by; bins.enabled = 1;
+    }
 
     const bool in_smem = !(g.cfg.flags & VT_FLAG_FORCE_GLOBAL_MASKS) && g.arena_words > 0 &&
                          (size_t)g.arena_words * 4 <= kSmemMaskBudget &&
@@ -246,14 +310,14 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
 
     if (g.cfg.mode == VT_MODE_PRIMARY) {
         CK(cudaEventRecord(g.ev_trace0, g.stream));
-        CK(launch_trace_primary(fp, g.d_iu, g.d_arena, g.arena_words, in_smem, lut, fb, g.sm_count, g.stream));
+        CK(launch_trace_primary(fp, g.d_iu, bins, g.d_arena, g.arena_words, in_smem, lut, fb, g.sm_count, g.stream));
         CK(cudaEventRecord(g.ev_trace1, g.stream));
         g.stats.launches += 1;
     } else {
         if (clear_accum)
             CK(cudaMemsetAsync(g.d_accum, 0, (size_t)g.cfg.width * g.cfg.height * 3 * sizeof(unsigned long long), g.stream));
         CK(cudaEventRecord(g.ev_trace0, g.stream));
-        CK(launch_trace_paths(fp, g.d_iu, g.d_arena, g.arena_words, in_smem, lut, fb, g.sm_count, g.stream));
+        CK(launch_trace_paths(fp, g.d_iu, bins, g.d_arena, g.arena_words, in_smem, lut, fb, g.sm_count, g.stream));
         CK(cudaEventRecord(g.ev_trace1, g.stream));
         g.stats.launches += 1;
         if (resolve) {
@@ -333,6 +397,9 @@ extern "C" uint64_t entry(void) {
     CKE(cudaMemcpy(g.d_dec, dec, sizeof dec, cudaMemcpyHostToDevice));
     CKE(cudaMemcpy(g.d_thr, thr, sizeof thr, cudaMemcpyHostToDevice));
     CKE(cudaMalloc(&g.d_stats, 4 * sizeof(unsigned long long)));
+    CKE(cudaMalloc(&g.d_bin_cursor, 4));
+    CKE(cudaMallocHost(&g.h_bin_cursor, 4));
+    *g.h_bin_cursor = 0;
     CKE(cudaMallocHost(&g.h_stats, 2 * sizeof(unsigned long long)));
     g.h_stats[0] = g.h_stats[1] = 0;
 
@@ -478,6 +545,8 @@ extern "C" void cleanup(void) {
     g.vols.clear();
     cudaFree(g.d_vols); cudaFree(g.d_arena); cudaFree(g.d_inst); cudaFree(g.d_iu); cudaFree(g.d_dec); cudaFree(g.d_thr);
     cudaFree(g.d_rec); cudaFree(g.d_color); cudaFree(g.d_depth); cudaFree(g.d_accum_own); cudaFree(g.d_stats);
+    cudaFree(g.d_bin_offset); cudaFree(g.d_bin_count); cudaFree(g.d_bin_list); cudaFree(g.d_bin_cursor);
+    if (g.h_bin_cursor) cudaFreeHost(g.h_bin_cursor);
     if (g.h_inst) cudaFreeHost(g.h_inst);
     if (g.h_tex_staging) cudaFreeHost(g.h_tex_staging);
     if (g.h_stats) cudaFreeHost(g.h_stats);
