@@ -83,3 +83,14 @@ def test_fails_loudly_without_a_gpu():
     from vtrace_b200.renderer import Renderer
     with pytest.raises(RuntimeError):
         Renderer()
+
+
+def test_compiled_host_builds_and_links_the_seven_symbols():
+    """host/vtrace_headless.cpp (C++ mirror of the Rust engine's host side) links against librender.so."""
+    abi.load()  # makes sure librender.so exists
+    subprocess.run(["make", "-C", os.path.join(ROOT, "host")], check=True, capture_output=True)
+    exe = os.path.join(ROOT, "host", "vtrace_headless")
+    undefined = subprocess.run(["nm", "-D", "--undefined-only", exe], capture_output=True, text=True, check=True).stdout
+    for ref in ("entry", "render_tick", "get_input_data_pointer", "add_texture", "start_update_instances",
+                "end_update_instances", "cleanup"):
+        assert re.search(rf"\bU {ref}\b", undefined), ref

@@ -334,3 +334,36 @@ def test_config2_full_size_properties(renderer, scene, assets):
     sky = np.array([int(np.float32(c) / np.float32(100.0) * np.float32(16777216.0)) for c in (53.0, 81.0, 92.0)], dtype=np.uint64)
     assert (a1 <= sky * np.uint64(spp)).all()           # albedo <= 1: nothing brighter than the sky
     assert np.array_equal(a1[0, 0], sky * np.uint64(spp))  # a corner pixel sees only sky
+
+
+# ---- compiled host over the C ABI ----------------------------------------------------------------
+
+def test_compiled_host_drives_the_abi_like_the_engine(oracle, assets, tmp_path):
+    """host/vtrace_headless (C++ mirror of src/main.rs + src/render.rs + src/world.rs' entity grid) runs
+    as its own process against librender.so: one texture upload per tick, instances skipped until their
+    texture is resident, frame k rendered with frame k-1's pose.  Its last frame must hash to what the
+    oracle renders from the same matrices."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-C", os.path.join(root, "host")], check=True, capture_output=True)
+    env = dict(os.environ, VT_WIDTH="640", VT_HEIGHT="360", VT_MAX_FRAMES="5", VT_MODE="0", VT_FLAGS="0")
+    ppm = str(tmp_path / "frame.ppm")
+    out = subprocess.run([os.path.join(root, "host", "vtrace_headless"), scenes.ASSETS, ppm], env=env, capture_output=True,
+                         text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    fields = dict(line.split("=", 1) for line in out.stdout.replace(" ", "\n").splitlines() if "=" in line)
+    assert fields["frames"] == "6" and fields["size"] == "640x360"  # 5 rendered + the tick that returned -1
+    P = np.array([int(x, 16) for x in fields["P"].split(",")], dtype=np.uint32).view(np.float32)
+    V = np.array([int(x, 16) for x in fields["V"].split(",")], dtype=np.uint32).view(np.float32)
+    sc = oracle.OracleScene()
+    temple = sc.add_texture(assets["AncientTemple"].get_raw(), *assets["AncientTemple"].dims())   # uploaded first
+    treasure = sc.add_texture(assets["Treasure"].get_raw(), *assets["Treasure"].dims())
+    sc.set_instances(scenes.entity_grid(treasure, temple))
+    rec, rgba, _, iters = sc.render_primary(P, V, 640, 360)
+    h = 1469598103934665603
+    for b in rgba.tobytes():
+        h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    assert int(fields["iterations"]) == iters
+    assert fields["fnv1a"] == f"{h:016x}"
+    assert os.path.getsize(ppm) == len("P6\n640 360\n255\n") + 640 * 360 * 3
