@@ -26,8 +26,10 @@ struct WorldState { // src/world.rs:28-76 (camera + entity registry; terrain pag
     Vec3 get_camera_direction() const { // src/world.rs:75-81
         return {std::cos(camera_theta) * std::sin(camera_phi), std::cos(camera_phi), std::sin(camera_theta) * std::sin(camera_phi)};
     }
-    SceneGraph update(float dt) { // src/world.rs:136-161
-        camera_theta += 0.01f * dt;
+    SceneGraph update(float dt, const user_input& in) { // src/world.rs:88-161
+        camera_theta += 0.002f * float(in.mouse_x - in.last_mouse_x); // SENSITIVITY * mouse delta (zero when headless)
+        camera_phi -= 0.002f * float(in.mouse_y - in.last_mouse_y);
+        camera_theta += 0.01f * dt;                                   // scripted pan so consecutive frames differ
         SceneGraph scene, scene_entities;
         for (int x = -5; x <= 5; ++x)
             for (int z = -5; z <= 5; ++z) {
@@ -45,13 +47,14 @@ int main(int argc, char** argv) {
         Renderer renderer;
         TextureUploadQueue queue;
         WorldState world(queue, assets);
-        SceneGraph scene = world.update(0.0f);
+        const user_input* input_ptr = renderer.get_input_data_pointer(); // src/main.rs:31
+        SceneGraph scene = world.update(0.0f, *input_ptr);
         bool code = true;
         while (code) { // src/main.rs:36-55 (the render thread is joined every frame, so this is the same order)
             const Vec3 pos = world.camera_position, dir = world.get_camera_direction();
             renderer.update_instances(scene);
             code = renderer.render_tick(pos, dir, queue);
-            scene = world.update(1.0f);
+            scene = world.update(1.0f, *input_ptr); // src/main.rs:52
         }
         const int w = renderer.window_width(), h = renderer.window_height();
         std::vector<uint8_t> rgba(size_t(w) * h * 4);
