@@ -70,6 +70,14 @@ user_input* get_input_data_pointer(void);
  * or device error). */
 int32_t add_texture(const uint8_t* data, uint32_t width, uint32_t height, uint32_t depth);
 
+/* Extension (no reference counterpart): volumes too large for add_texture's
+ * dense RGBA8 upload (its u32 byte count overflows at 1024^3, lib/memory.c:297) are generated on the
+ * device from a procedural definition and stored as sparse 8^3 occupancy bricks.  Returns a texture
+ * id usable in instances exactly like add_texture's, or -1.  Dimensions: multiples of 8, <= 8192. */
+#define VT_VOLUME_HEIGHTMAP 1u      /* terrain: altitude <= H/2 + H/4 * fbm(value noise, 5 octaves)          */
+#define VT_VOLUME_SPARSE_BRICKS 2u  /* 2 % of the 8^3 bricks non-empty (hash), half of their voxels filled */
+int32_t vt_add_volume_procedural(uint32_t kind, uint32_t width, uint32_t height, uint32_t depth, uint32_t seed);
+
 /* replaces lib/memory.c:235-248.  Returns a write pointer with room for max(instance_count,1)
  * 64-byte column-major mat4s (texture id bit-cast into element [3][3], src/render.rs:74-78),
  * valid until end_update_instances; NULL on failure. */
@@ -90,12 +98,14 @@ void cleanup(void);
 /* render modes */
 #define VT_MODE_PRIMARY 0u /* the reference's pass: one DDA per covered fragment (trace.frag)  */
 #define VT_MODE_PATHS 1u   /* extension: spp jittered paths per pixel, diffuse bounces, sky     */
+#define VT_MODE_RAYS 2u    /* extension: width*height incoherent rays through instance 0's volume (config 4) */
 
 /* flags */
 #define VT_FLAG_VIEWPORT_H_IS_W 1u /* reproduce lib/command.c:80-81 (viewport height = width)  */
 #define VT_FLAG_NO_HIT_RECORDS 2u  /* do not write the per-pixel hit records                    */
 #define VT_FLAG_FORCE_GLOBAL_MASKS 4u /* keep traversal masks in global memory (no smem staging) */
 #define VT_FLAG_PERSISTENT_LANES 8u /* PATHS, one instance: persistent-lane schedule (job pool per warp tile) */
+#define VT_FLAG_SHADOW_RAYS 64u     /* PRIMARY: one shadow ray towards the sun (0.4,-0.8,0.45) per winning fragment  */
 #define VT_FLAG_NO_BINNING 32u      /* visit every instance per pixel instead of the screen-space bins (testing) */
 #define VT_FLAG_PER_PIXEL_PATHS 16u /* PATHS, one instance: the general per-pixel kernel instead of the wavefront engine */
 
@@ -116,7 +126,8 @@ typedef struct vt_config {
     uint32_t spp;             /* PATHS: samples per pixel rendered BY THIS PROCESS per frame      */
     uint32_t bounces;         /* PATHS: diffuse bounces after the primary segment                 */
     uint32_t seed;            /* PATHS: RNG seed                                                  */
-    uint32_t sample_first;    /* PATHS: global index of this process's first sample (= rank)      */
+    uint32_t sample_first;    /* PATHS: global index of this process's first sample (= rank);     */
+                              /* RAYS: this process traces rays [sample_first*w*h, (sample_first+1)*w*h) */
     uint32_t sample_stride;   /* PATHS: distance between its samples (= number of ranks)          */
     uint32_t total_spp;       /* PATHS: spp over all ranks, the divisor used by vt_resolve        */
     int32_t max_frames;       /* render_tick returns -1 after this many frames; <= 0: never       */

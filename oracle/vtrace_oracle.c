@@ -141,7 +141,72 @@ uint8_t vo_srgb_encode(float x) {
 /* ------------------------------------------------------------------------------------------ */
 /* scene state = what crosses the C ABI                                       */
 
-typedef struct { uint32_t w, h, d; uint8_t* rgba; } vo_texture;
+typedef struct { uint32_t w, h, d; uint8_t* rgba; uint32_t kind, seed; float* heights; } vo_texture;
+
+/* what the traversal needs to know about a volume.  kind 0 = dense RGBA8 texels (add_texture);
+ * kinds 1/2 = procedural volumes of the large-scene extension (no reference counterpart). */
+typedef struct { uint32_t kind, w, h, d, seed; const uint8_t* rgba; const float* heights; } vol_view;
+
+static inline uint32_t vo_mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+static inline uint32_t vo_hash3(uint32_t x, uint32_t y, uint32_t z, uint32_t seed) {
+    uint32_t h = vo_mix32(x * 0x9E3779B1u + seed);
+    h = vo_mix32(h ^ (y * 0x85EBCA77u));
+    h = vo_mix32(h ^ (z * 0xC2B2AE3Du));
+    return h;
+}
+
+/* VO_VOLUME_HEIGHTMAP: height(x,z) = H/2 + H/4 * fbm, fbm = 5 octaves of value noise on lattices of
+ * 128, 64, 32, 16, 8 voxels with amplitudes 1/2 .. 1/32; a voxel is filled iff its altitude
+ * (H - 1 - y, because +Y is down) satisfies (float)altitude <= height. */
+static float heightmap_height(uint32_t x, uint32_t z, uint32_t H, uint32_t seed) {
+    float n = 0.0f, amp = 0.5f;
+    for (uint32_t o = 0; o < 5; ++o) {
+        const uint32_t cell = 128u >> o;
+        const uint32_t ix = x / cell, iz = z / cell;
+        const float fx = (float)(x % cell) / (float)cell, fz = (float)(z % cell) / (float)cell;
+        const float ux = (fx * fx) * (3.0f - 2.0f * fx), uz = (fz * fz) * (3.0f - 2.0f * fz);
+        const float v00 = (float)(vo_hash3(ix, iz, o, seed) >> 8) * (1.0f / 16777216.0f);
+        const float v10 = (float)(vo_hash3(ix + 1, iz, o, seed) >> 8) * (1.0f / 16777216.0f);
+        const float v01 = (float)(vo_hash3(ix, iz + 1, o, seed) >> 8) * (1.0f / 16777216.0f);
+        const float v11 = (float)(vo_hash3(ix + 1, iz + 1, o, seed) >> 8) * (1.0f / 16777216.0f);
+        const float a = v00 + ux * (v10 - v00);
+        const float b = v01 + ux * (v11 - v01);
+        const float v = a + uz * (b - a);
+        n = n + amp * (2.0f * v - 1.0f);
+        amp = amp * 0.5f;
+    }
+    return 0.5f * (float)H + (0.25f * (float)H) * n;
+}
+
+/* texel (x,y,z) of a volume -> RGBA8; alpha 0 = empty */
+static inline void vol_texel(const vol_view* v, int32_t x, int32_t y, int32_t z, uint8_t out[4]) {
+    if (v->kind == 0) {
+        memcpy(out, v->rgba + 4 * ((size_t)x + (size_t)v->w * ((size_t)y + (size_t)v->h * (size_t)z)), 4);
+    } else if (v->kind == VO_VOLUME_HEIGHTMAP) {
+        const float hgt = v->heights[(size_t)z * v->w + (size_t)x];
+        /* world +Y points DOWN on screen in the reference, so the ground fills the high-y side */
+        const uint32_t alt = v->h - 1u - (uint32_t)y;
+        if ((float)alt <= hgt) {
+            const uint32_t band = (alt * 4u) / v->h; /* colour by altitude band */
+            static const uint8_t pal[4][3] = {{72, 60, 50}, {96, 128, 56}, {120, 120, 120}, {240, 240, 245}};
+            out[0] = pal[band][0]; out[1] = pal[band][1]; out[2] = pal[band][2]; out[3] = 255;
+        } else {
+            out[0] = out[1] = out[2] = out[3] = 0;
+        }
+    } else { /* VO_VOLUME_SPARSE_BRICKS: 2 % of the 8^3 bricks are non-empty, half of their voxels filled */
+        const uint32_t ux = (uint32_t)x, uy = (uint32_t)y, uz = (uint32_t)z;
+        const int brick = (vo_hash3(ux >> 3, uy >> 3, uz >> 3, v->seed) & 0xFFFFu) < 1311u;
+        if (brick && (vo_hash3(ux, uy, uz, v->seed ^ 0x5bd1e995u) & 1u)) {
+            const uint32_t c = vo_hash3(ux, uy, uz, v->seed ^ 0x27d4eb2fu);
+            out[0] = (uint8_t)(c | 0x40u); out[1] = (uint8_t)((c >> 8) | 0x40u); out[2] = (uint8_t)((c >> 16) | 0x40u); out[3] = 255;
+        } else {
+            out[0] = out[1] = out[2] = out[3] = 0;
+        }
+    }
+}
 
 struct vo_scene {
     vo_texture* tex;
@@ -160,7 +225,7 @@ vo_scene* vo_scene_create(void) {
 
 void vo_scene_destroy(vo_scene* s) {
     if (!s) return;
-    for (uint32_t i = 0; i < s->ntex; ++i) free(s->tex[i].rgba);
+    for (uint32_t i = 0; i < s->ntex; ++i) { free(s->tex[i].rgba); free(s->tex[i].heights); }
     free(s->tex);
     free(s->inst);
     free(s);
@@ -175,8 +240,28 @@ int32_t vo_add_texture(vo_scene* s, const uint8_t* rgba, uint32_t w, uint32_t h,
     size_t bytes = (size_t)4 * w * h * d;
     vo_texture* t = &s->tex[s->ntex];
     t->w = w; t->h = h; t->d = d;
+    t->kind = 0; t->seed = 0; t->heights = NULL;
     t->rgba = (uint8_t*)malloc(bytes ? bytes : 1);
     memcpy(t->rgba, rgba, bytes); /* lib/memory.c:304-307: data only borrowed for the call */
+    return (int32_t)s->ntex++;
+}
+
+int32_t vo_add_volume_procedural(vo_scene* s, uint32_t kind, uint32_t w, uint32_t h, uint32_t d, uint32_t seed) {
+    if (s->ntex >= 65536u || (kind != VO_VOLUME_HEIGHTMAP && kind != VO_VOLUME_SPARSE_BRICKS)) return -1;
+    if (s->ntex == s->captex) {
+        s->captex = s->captex ? s->captex * 2 : 4;
+        s->tex = (vo_texture*)realloc(s->tex, s->captex * sizeof *s->tex);
+    }
+    vo_texture* t = &s->tex[s->ntex];
+    t->w = w; t->h = h; t->d = d; t->kind = kind; t->seed = seed; t->rgba = NULL; t->heights = NULL;
+    if (kind == VO_VOLUME_HEIGHTMAP) {
+        t->heights = (float*)malloc(sizeof(float) * (size_t)w * d);
+#ifdef _OPENMP
+#pragma omp parallel for
+#endif
+        for (int64_t z = 0; z < (int64_t)d; ++z)
+            for (uint32_t x = 0; x < w; ++x) t->heights[(size_t)z * w + x] = heightmap_height(x, (uint32_t)z, h, seed);
+    }
     return (int32_t)s->ntex++;
 }
 
@@ -199,6 +284,7 @@ typedef struct {
     float eye[3];
     float vw, vh;
     float sxn, syn; /* 2/vw, 2/vh: pixel -> NDC scale */
+    float sun[3];   /* unit vector towards the sun, world space (shadow-ray extension) */
     int width, height;
 } frame_uniforms;
 
@@ -206,9 +292,10 @@ typedef struct {
     mat4 M, Mi, MVP;
     float dirm[4][3]; /* Mi(3x3) * RD(rows 0-2): clip-space point -> model-space ray direction */
     float eye_m[3];
+    float sun_m[3]; /* inverse(M)3x3 * sun: direction of the shadow rays in model space */
     uint32_t tex;
     uint32_t w, h, d;
-    const uint8_t* rgba;
+    vol_view vol;
     int valid;
 } inst_uniforms;
 
@@ -230,6 +317,11 @@ static void frame_setup(frame_uniforms* F, const float* P, const float* V, int w
     F->vh = (flags & VO_FLAG_VIEWPORT_H_IS_W) ? (float)width : (float)height; /* lib/command.c:81 */
     F->sxn = 2.0f / F->vw;
     F->syn = 2.0f / F->vh;
+    {   /* sun direction (0.4, -0.8, 0.45), normalised */
+        const float sx = 0.4f, sy = -0.8f, sz = 0.45f;
+        const float l = sqrtf((sx * sx + sy * sy) + sz * sz);
+        F->sun[0] = sx / l; F->sun[1] = sy / l; F->sun[2] = sz / l;
+    }
 }
 
 static void inst_setup(inst_uniforms* I, const frame_uniforms* F, const vo_scene* s, const float* m16) {
@@ -239,12 +331,15 @@ static void inst_setup(inst_uniforms* I, const frame_uniforms* F, const vo_scene
     I->valid = I->tex < s->ntex;
     if (!I->valid) return;
     I->w = s->tex[I->tex].w; I->h = s->tex[I->tex].h; I->d = s->tex[I->tex].d;
-    I->rgba = s->tex[I->tex].rgba;
+    I->vol.kind = s->tex[I->tex].kind; I->vol.w = I->w; I->vol.h = I->h; I->vol.d = I->d;
+    I->vol.seed = s->tex[I->tex].seed; I->vol.rgba = s->tex[I->tex].rgba; I->vol.heights = s->tex[I->tex].heights;
     I->Mi = mat4_inverse(&I->M);              /* trace.frag:65 */
     I->MVP = mat4_mul(&F->PV, &I->M);
     for (int j = 0; j < 4; ++j)
         for (int i = 0; i < 3; ++i)
             I->dirm[j][i] = (I->Mi.c[0][i] * F->RD.c[j][0] + I->Mi.c[1][i] * F->RD.c[j][1]) + I->Mi.c[2][i] * F->RD.c[j][2];
+    for (int i = 0; i < 3; ++i)
+        I->sun_m[i] = (I->Mi.c[0][i] * F->sun[0] + I->Mi.c[1][i] * F->sun[1]) + I->Mi.c[2][i] * F->sun[2];
     vec4 e = {{F->eye[0], F->eye[1], F->eye[2], 1.0f}};
     vec4 em = mat4_mul_vec4(&I->Mi, e);
     I->eye_m[0] = em.v[0]; I->eye_m[1] = em.v[1]; I->eye_m[2] = em.v[2];
@@ -314,8 +409,9 @@ static inline int32_t texel_of(int32_t v, float size, int32_t isize) {
     return i;
 }
 
-static void dda_march(const uint8_t* rgba, uint32_t W, uint32_t H, uint32_t D, const float pos[3],
-                      const float dir[3], const int32_t* start_voxel, dda_state* r) {
+static void dda_march(const vol_view* vol, const float pos[3], const float dir[3], const int32_t* start_voxel,
+                      dda_state* r) {
+    const uint32_t W = vol->w, H = vol->h, D = vol->d;
     const int32_t isz[3] = {(int32_t)W, (int32_t)H, (int32_t)D};
     const float size[3] = {(float)isz[0], (float)isz[1], (float)isz[2]}; /* :63-64 */
     float sgn[3];
@@ -339,7 +435,8 @@ static void dda_march(const uint8_t* rgba, uint32_t W, uint32_t H, uint32_t D, c
         int32_t tx = texel_of(r->voxel[0], size[0], isz[0]);
         int32_t ty = texel_of(r->voxel[1], size[1], isz[1]);
         int32_t tz = texel_of(r->voxel[2], size[2], isz[2]);
-        const uint8_t* s = rgba + 4 * ((size_t)tx + (size_t)W * ((size_t)ty + (size_t)H * (size_t)tz)); /* :76 */
+        uint8_t s[4];
+        vol_texel(vol, tx, ty, tz, s); /* :76 */
         if (s[3] > 0) { /* :78 texSample.w > 0.0 */
             memcpy(r->rgba, s, 4);
             r->hit = 1;
@@ -390,7 +487,8 @@ void vo_frag_main(const float* P, const float* V, const float* M, const float* s
     float pos[3], dir[3];
     frag_ray(&F.RD, &Mi, sp, model_position, w, h, d, pos, dir);
     dda_state r;
-    dda_march(rgba, w, h, d, pos, dir, NULL, &r);
+    const vol_view vv = {0, w, h, d, 0, rgba, NULL};
+    dda_march(&vv, pos, dir, NULL, &r);
     out[0] = r.hit;
     out[1] = r.voxel[0]; out[2] = r.voxel[1]; out[3] = r.voxel[2];
     out[4] = (int32_t)r.steps;
@@ -441,7 +539,31 @@ static void run_fragment(const frame_uniforms* F, const inst_uniforms* I, float 
     f->depth = sp.v[2] / sp.v[3]; /* :46 */
     float pos[3], dir[3];
     frag_ray(&F->RD, &I->Mi, sp, f->mp, I->w, I->h, I->d, pos, dir);
-    dda_march(I->rgba, I->w, I->h, I->d, pos, dir, NULL, &f->dda);
+    dda_march(&I->vol, pos, dir, NULL, &f->dda);
+}
+
+/* Where a secondary ray (bounce or shadow) leaves a hit: axis = first axis advanced by the last DDA
+ * iteration (or the box-entry axis when steps == 0), origin = hit point clamped to the hit voxel with
+ * the normal component on the face plane, start voxel = the neighbour across that face. */
+static void leave_hit(const dda_state* r, int entry_axis, const float size[3], int* a_out, int* nsign_out, float p0[3],
+                      int32_t sv[3]) {
+    uint32_t lm = r->steps ? r->last_mask : (1u << entry_axis);
+    int a = (lm & 1u) ? 0 : ((lm & 2u) ? 1 : 2);
+    float t = r->steps ? r->side[a] - r->delta[a] : 0.0f;
+    int nsign = r->step[a] != 0 ? -r->step[a] : (r->pos[a] <= 0.5f * size[a] ? -1 : 1);
+    float tl = t / r->len;
+    for (int k = 0; k < 3; ++k) {
+        float p = r->pos[k] + r->dir[k] * tl;
+        float lo = (float)r->voxel[k], hi = (float)(r->voxel[k] + 1);
+        p = p < lo ? lo : p;
+        p = p > hi ? hi : p;
+        p0[k] = p;
+        sv[k] = r->voxel[k];
+    }
+    p0[a] = (float)(r->voxel[a] + (nsign > 0 ? 1 : 0));
+    sv[a] += nsign;
+    *a_out = a;
+    *nsign_out = nsign;
 }
 
 static inline uint32_t face_bits(const dda_state* r, int entry_axis) {
@@ -449,6 +571,8 @@ static inline uint32_t face_bits(const dda_state* r, int entry_axis) {
     uint32_t neg = (uint32_t)(r->step[0] < 0) | ((uint32_t)(r->step[1] < 0) << 1) | ((uint32_t)(r->step[2] < 0) << 2);
     return mask | (neg << 3);
 }
+
+static uint64_t g_last_shadow_rays = 0;
 
 uint64_t vo_render_primary(const vo_scene* s, const float* P, const float* V, int width, int height,
                            uint32_t flags, vo_hit_record* records, uint8_t* rgba8, float* depth_out,
@@ -461,13 +585,14 @@ uint64_t vo_render_primary(const vo_scene* s, const float* P, const float* V, in
     /* clear values, lib/command.c:56-61, stored through the sRGB target */
     const uint8_t clear[4] = {vo_srgb_encode(53.0f / 100.0f), vo_srgb_encode(81.0f / 100.0f),
                               vo_srgb_encode(92.0f / 100.0f), 255};
-    uint64_t total_iters = 0;
+    uint64_t total_iters = 0, shadow_rays = 0;
 #ifdef _OPENMP
     if (num_threads <= 0) num_threads = omp_get_max_threads();
-#pragma omp parallel for schedule(dynamic, 4) num_threads(num_threads) reduction(+ : total_iters)
+#pragma omp parallel for schedule(dynamic, 4) num_threads(num_threads) reduction(+ : total_iters, shadow_rays)
 #endif
     for (int py = 0; py < height; ++py) {
         for (int px = 0; px < width; ++px) {
+            if ((flags & VO_FLAG_SUBSET_8) && ((px | py) & 7)) continue; /* 1/64 of the pixels (full-size parity checks) */
             float fx = (float)px + 0.5f, fy = (float)py + 0.5f;
             uint8_t dst[4] = {clear[0], clear[1], clear[2], clear[3]};
             float zbuf = 1.0f; /* lib/command.c:60 */
@@ -480,16 +605,36 @@ uint64_t vo_render_primary(const vo_scene* s, const float* P, const float* V, in
                 if (!f.dda.hit) continue;                 /* discard, trace.frag:89 */
                 if (!(f.depth < zbuf)) continue;          /* VK_COMPARE_OP_LESS, lib/pipeline.c:148-150 */
                 zbuf = f.depth;
+                /* extension: one shadow ray towards the sun, inside the fragment's own volume */
+                float shade = 1.0f;
+                uint32_t shadow_bits = 0;
+                if (flags & VO_FLAG_SHADOW_RAYS) {
+                    const float size[3] = {(float)(int32_t)I[i].w, (float)(int32_t)I[i].h, (float)(int32_t)I[i].d};
+                    int ax, nsign;
+                    float p0[3];
+                    int32_t sv[3];
+                    leave_hit(&f.dda, f.entry_axis, size, &ax, &nsign, p0, sv);
+                    int lit = 0;
+                    if ((float)nsign * I[i].sun_m[ax] > 0.0f) { /* the face looks at the sun */
+                        dda_state sh;
+                        dda_march(&I[i].vol, p0, I[i].sun_m, sv, &sh);
+                        rec.iters += sh.steps;
+                        lit = !sh.hit;
+                        shadow_bits = 1u | ((uint32_t)lit << 1);
+                        ++shadow_rays;
+                    }
+                    shade = lit ? 1.0f : 0.35f;
+                }
                 /* blend, lib/pipeline.c:129-137 */
                 float a = (float)f.dda.rgba[3] / 255.0f;
                 for (int c = 0; c < 3; ++c) {
-                    float src = g_srgb_dec[f.dda.rgba[c]];
+                    float src = g_srgb_dec[f.dda.rgba[c]] * shade;
                     float dl = g_srgb_dec[dst[c]];
                     dst[c] = vo_srgb_encode(src * a + dl * (1.0f - a));
                 }
                 dst[3] = (uint8_t)vo_f2i(floorf(a * 255.0f + 0.5f));
                 rec.hit_voxel = (uint32_t)f.dda.voxel[0] + I[i].w * ((uint32_t)f.dda.voxel[1] + I[i].h * (uint32_t)f.dda.voxel[2]);
-                rec.packed = (f.dda.steps & 0xFFFFu) | (face_bits(&f.dda, f.entry_axis) << 16);
+                rec.packed = (f.dda.steps & 0xFFFFu) | (face_bits(&f.dda, f.entry_axis) << 16) | (shadow_bits << 22);
                 rec.instance = i;
             }
             size_t p = (size_t)py * (size_t)width + (size_t)px;
@@ -500,8 +645,11 @@ uint64_t vo_render_primary(const vo_scene* s, const float* P, const float* V, in
         }
     }
     free(I);
+    g_last_shadow_rays = shadow_rays;
     return total_iters;
 }
+
+uint64_t vo_last_shadow_rays(void) { return g_last_shadow_rays; }
 
 /* ------------------------------------------------------------------------------------------ */
 /* path-tracing extension (no reference counterpart)                            */
@@ -589,7 +737,7 @@ static void trace_world(const inst_uniforms* I, uint32_t ninst, uint32_t skip, c
         const inst_uniforms* J = &I[best_j];
         const float size[3] = {(float)(int32_t)J->w, (float)(int32_t)J->h, (float)(int32_t)J->d};
         for (int k = 0; k < 3; ++k) pos[k] = (mp[k] + 0.5f) * size[k];
-        dda_march(J->rgba, J->w, J->h, J->d, pos, bd, NULL, &out->dda);
+        dda_march(&J->vol, pos, bd, NULL, &out->dda);
         *iters += out->dda.steps;
         if (out->dda.hit) {
             out->hit = 1; out->instance = best_j; out->entry_axis = best_axis;
@@ -626,24 +774,10 @@ static void trace_path(const frame_uniforms* F, const inst_uniforms* I, uint32_t
         const inst_uniforms* J = &I[cur.instance];
         const dda_state* r = &cur.dda;
         const float size[3] = {(float)(int32_t)J->w, (float)(int32_t)J->h, (float)(int32_t)J->d};
-        /* hit face: first axis advanced by the last iteration, or the box-entry axis */
-        uint32_t lm = r->steps ? r->last_mask : (1u << cur.entry_axis);
-        int a = (lm & 1u) ? 0 : ((lm & 2u) ? 1 : 2);
-        float t = r->steps ? r->side[a] - r->delta[a] : 0.0f;
-        int nsign = r->step[a] != 0 ? -r->step[a] : (r->pos[a] <= 0.5f * size[a] ? -1 : 1);
-        float tl = t / r->len;
+        int a, nsign;
         float p0[3];
         int32_t sv[3];
-        for (int k = 0; k < 3; ++k) {
-            float p = r->pos[k] + r->dir[k] * tl;
-            float lo = (float)r->voxel[k], hi = (float)(r->voxel[k] + 1);
-            p = p < lo ? lo : p;
-            p = p > hi ? hi : p;
-            p0[k] = p;
-            sv[k] = r->voxel[k];
-        }
-        p0[a] = (float)(r->voxel[a] + (nsign > 0 ? 1 : 0));
-        sv[a] += nsign;
+        leave_hit(r, cur.entry_axis, size, &a, &nsign, p0, sv);
         /* cosine-weighted direction about the face normal: normalize(n + uniform sphere point) */
         float dn[3];
         rng_sphere(&rng, dn);
@@ -661,7 +795,7 @@ static void trace_path(const frame_uniforms* F, const inst_uniforms* I, uint32_t
         next.hit = 0;
         next.instance = cur.instance;
         next.entry_axis = a;
-        dda_march(J->rgba, J->w, J->h, J->d, p0, dn, sv, &next.dda);
+        dda_march(&J->vol, p0, dn, sv, &next.dda);
         *iters += next.dda.steps;
         next.hit = next.dda.hit;
         if (!next.hit && ninst > 1) {
@@ -710,6 +844,49 @@ void vo_render_paths(const vo_scene* s, const float* P, const float* V, int widt
     }
     free(I);
     if (stats) { stats[0] += rays; stats[1] += iters; }
+}
+
+/* Incoherent-ray extension: n rays through the volume of instance 0, in its
+ * voxel space; ray i has origin uniform in the volume and direction uniform on the sphere, both from
+ * the RNG stream keyed (seed, i, 0).  Record: hit_voxel = x | y << 16, instance = z, packed as for
+ * primary rays (entry axis bit = 0 when steps == 0), iters = steps; VO_MISS / 0 / VO_MISS on a miss. */
+uint64_t vo_render_rays(const vo_scene* s, uint64_t n, uint64_t first, uint32_t seed, vo_hit_record* records, uint8_t* rgba8,
+                        int num_threads) {
+    srgb_init();
+    uint32_t tex;
+    memcpy(&tex, s->inst + 15, 4);
+    if (tex >= s->ntex) return 0;
+    const vo_texture* t = &s->tex[tex];
+    const vol_view vol = {t->kind, t->w, t->h, t->d, t->seed, t->rgba, t->heights};
+    const float size[3] = {(float)(int32_t)t->w, (float)(int32_t)t->h, (float)(int32_t)t->d};
+    uint64_t total = 0;
+#ifdef _OPENMP
+    if (num_threads <= 0) num_threads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 256) num_threads(num_threads) reduction(+ : total)
+#endif
+    for (int64_t k = 0; k < (int64_t)n; ++k) {
+        const uint64_t i = first + (uint64_t)k;
+        vo_rng rng;
+        rng_init(&rng, seed, (uint32_t)i, (uint32_t)(i >> 32));
+        float pos[3], dir[3];
+        for (int c = 0; c < 3; ++c) pos[c] = rng_u01(&rng) * size[c];
+        rng_sphere(&rng, dir);
+        dda_state r;
+        dda_march(&vol, pos, dir, NULL, &r);
+        total += r.steps;
+        vo_hit_record rec = {VO_MISS, 0, VO_MISS, r.steps};
+        uint8_t px[4] = {0, 0, 0, 0};
+        if (r.hit) {
+            rec.hit_voxel = (uint32_t)r.voxel[0] | ((uint32_t)r.voxel[1] << 16);
+            rec.instance = (uint32_t)r.voxel[2];
+            const uint32_t neg = (uint32_t)(r.step[0] < 0) | ((uint32_t)(r.step[1] < 0) << 1) | ((uint32_t)(r.step[2] < 0) << 2);
+            rec.packed = (r.steps & 0xFFFFu) | ((r.last_mask | (neg << 3)) << 16);
+            memcpy(px, r.rgba, 4);
+        }
+        if (records) records[k] = rec;
+        if (rgba8) memcpy(rgba8 + 4 * (size_t)k, px, 4);
+    }
+    return total;
 }
 
 void vo_resolve(const uint64_t* accum, int width, int height, uint32_t total_spp, uint8_t* rgba8) {

@@ -36,6 +36,12 @@ extern "C" {
 
 /* flags */
 #define VO_FLAG_VIEWPORT_H_IS_W 1u /* reference-faithful viewport (lib/command.c:80-81) */
+#define VO_FLAG_SHADOW_RAYS 64u    /* extension: one shadow ray towards the sun per primary hit */
+#define VO_FLAG_SUBSET_8 0x10000u  /* oracle only: compute every 8th pixel in x and y, leave the rest untouched */
+
+/* procedural volume kinds of the large-scene extension */
+#define VO_VOLUME_HEIGHTMAP 1u
+#define VO_VOLUME_SPARSE_BRICKS 2u
 
 /* Per-pixel derived hit record. 16 bytes. */
 typedef struct vo_hit_record {
@@ -52,6 +58,8 @@ vo_scene* vo_scene_create(void);
 void vo_scene_destroy(vo_scene*);
 /* mirrors add_texture (lib/memory.c:286): copies 4*w*h*d bytes, returns id or -1 */
 int32_t vo_add_texture(vo_scene*, const uint8_t* rgba, uint32_t w, uint32_t h, uint32_t d);
+/* extension: a procedural volume (no texel storage); returns its texture id or -1 */
+int32_t vo_add_volume_procedural(vo_scene*, uint32_t kind, uint32_t w, uint32_t h, uint32_t d, uint32_t seed);
 /* mirrors start/end_update_instances (lib/memory.c:235-267): n x 16 floats, column-major,
  * texture id bit-cast into element [3][3] (src/render.rs:74-78). n == 0 is coerced to 1. */
 void vo_set_instances(vo_scene*, const float* mats, uint32_t n);
@@ -72,6 +80,14 @@ void vo_render_paths(const vo_scene*, const float* P, const float* V, int width,
                      uint32_t flags, uint32_t bounces, uint32_t seed, uint32_t sample_first,
                      uint32_t sample_stride, uint32_t sample_count, uint64_t* accum,
                      uint64_t* stats, int num_threads);
+
+/* shadow rays traced by the most recent vo_render_primary (VO_FLAG_SHADOW_RAYS) */
+uint64_t vo_last_shadow_rays(void);
+
+/* Incoherent-ray extension (config 4): rays `first` .. `first + n` through instance 0's volume.
+ * Returns the total DDA iterations. */
+uint64_t vo_render_rays(const vo_scene*, uint64_t n, uint64_t first, uint32_t seed, vo_hit_record* records, uint8_t* rgba8,
+                        int num_threads);
 
 /* accum -> RGBA8 (sRGB-encoded), dividing by total_spp */
 void vo_resolve(const uint64_t* accum, int width, int height, uint32_t total_spp, uint8_t* rgba8);

@@ -17,6 +17,9 @@ ORACLE_SO = os.path.join(ORACLE_DIR, "_build", "libvtrace_oracle.so")
 
 VO_MISS = 0xFFFFFFFF
 FLAG_VIEWPORT_H_IS_W = 1
+FLAG_SHADOW_RAYS = 64
+FLAG_SUBSET_8 = 0x10000
+VOLUME_HEIGHTMAP, VOLUME_SPARSE_BRICKS = 1, 2
 
 HIT_DTYPE = np.dtype([("hit_voxel", "<u4"), ("packed", "<u4"), ("instance", "<u4"), ("iters", "<u4")])
 
@@ -43,6 +46,11 @@ def lib() -> C.CDLL:
         L.vo_scene_destroy.argtypes = [vp]
         L.vo_add_texture.argtypes = [vp, vp, u32, u32, u32]
         L.vo_add_texture.restype = i32
+        L.vo_add_volume_procedural.argtypes = [vp, u32, u32, u32, u32, u32]
+        L.vo_add_volume_procedural.restype = i32
+        L.vo_last_shadow_rays.restype = u64
+        L.vo_render_rays.argtypes = [vp, u64, u64, u32, vp, vp, C.c_int]
+        L.vo_render_rays.restype = u64
         L.vo_set_instances.argtypes = [vp, vp, u32]
         L.vo_render_primary.argtypes = [vp, vp, vp, C.c_int, C.c_int, u32, vp, vp, vp, C.c_int]
         L.vo_render_primary.restype = u64
@@ -93,14 +101,26 @@ class OracleScene:
         assert rgba.size == 4 * w * h * d
         return lib().vo_add_texture(self._h, _p(rgba), w, h, d)
 
+    def add_volume_procedural(self, kind: int, w: int, h: int, d: int, seed: int) -> int:
+        return lib().vo_add_volume_procedural(self._h, kind, w, h, d, seed)
+
+    def render_rays(self, n: int, seed: int, first: int = 0, threads=0, want_color=True):
+        rec = np.empty(n, dtype=HIT_DTYPE)
+        rgba = np.empty((n, 4), dtype=np.uint8) if want_color else None
+        iters = lib().vo_render_rays(self._h, n, first, seed, _p(rec), _p(rgba), threads)
+        return rec, rgba, int(iters)
+
+    def last_shadow_rays(self) -> int:
+        return int(lib().vo_last_shadow_rays())
+
     def set_instances(self, mats: np.ndarray):
         mats = np.ascontiguousarray(mats, dtype=np.float32).reshape(-1, 16)
         lib().vo_set_instances(self._h, _p(mats) if len(mats) else None, len(mats))
 
     def render_primary(self, P, V, width, height, flags=0, threads=0, want_color=True, want_depth=False):
-        rec = np.empty(width * height, dtype=HIT_DTYPE)
-        rgba = np.empty((height, width, 4), dtype=np.uint8) if want_color else None
-        depth = np.empty((height, width), dtype=np.float32) if want_depth else None
+        rec = np.zeros(width * height, dtype=HIT_DTYPE)
+        rgba = np.zeros((height, width, 4), dtype=np.uint8) if want_color else None
+        depth = np.zeros((height, width), dtype=np.float32) if want_depth else None
         P, V = _m(P), _m(V)
         iters = lib().vo_render_primary(self._h, _p(P), _p(V), width, height, flags, _p(rec), _p(rgba), _p(depth), threads)
         return rec.reshape(height, width), rgba, depth, int(iters)

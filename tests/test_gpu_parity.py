@@ -51,18 +51,24 @@ class Scene:
         self.o.set_instances(o_m)
         self.r.update_instances_raw(r_m)
 
-    def check_primary(self, P, V, w, h, flags=0, what=""):
+    def check_primary(self, P, V, w, h, flags=0, what="", subset=False):
         self.r.configure(width=w, height=h, mode=abi.MODE_PRIMARY, flags=flags, max_frames=0)
         assert self.r.render_tick_raw(P, V)
         assert (self.r.window_width, self.r.window_height) == (w, h)
         got, color, depth = self.r.read_hits(), self.r.read_color(), self.r.read_depth()
-        want, wcolor, wdepth, iters = self.o.render_primary(P, V, w, h, flags=flags & 1, want_depth=True)
+        oflags = (flags & (1 | abi.FLAG_SHADOW_RAYS)) | (0x10000 if subset else 0)
+        want, wcolor, wdepth, iters = self.o.render_primary(P, V, w, h, flags=oflags, want_depth=True)
+        st = self.r.stats()
+        if subset:  # the oracle computed every 8th pixel in x and y only (full-size configurations)
+            got, color, depth = got[::8, ::8], color[::8, ::8], depth[::8, ::8]
+            want, wcolor, wdepth = want[::8, ::8], wcolor[::8, ::8], wdepth[::8, ::8]
         _assert_records_equal(got, want, what)
         assert np.array_equal(color, wcolor), f"{what}: colour bytes differ"
         assert np.array_equal(depth.view(np.uint32), wdepth.view(np.uint32)), f"{what}: depth bits differ"
-        st = self.r.stats()
-        assert st.iterations == iters, f"{what}: iteration counter {st.iterations} != {iters}"
-        assert st.rays == w * h
+        if not subset:
+            assert st.iterations == iters, f"{what}: iteration counter {st.iterations} != {iters}"
+            shadow = self.o.last_shadow_rays() if flags & abi.FLAG_SHADOW_RAYS else 0
+            assert st.rays == w * h + shadow, f"{what}: ray counter {st.rays} != {w * h} + {shadow}"
         return got, st
 
     def check_paths(self, P, V, w, h, spp, bounces=4, seed=0x5EED, flags=0, what=""):
@@ -241,6 +247,103 @@ def test_rotated_scaled_instances(scene, assets):
     scene.set_instances([(m1, t), (m2, t)])
     P, V = scenes.camera(512, 384, eye=(1.8, -1.1, 1.5))
     scene.check_primary(P, V, 512, 384, what="rotated/scaled")
+
+
+# ---- large-scene extension: shadow rays, procedural brick volumes, incoherent rays --------------
+
+def test_shadow_rays_on_dense_volumes(scene, assets):
+    t = scene.add(assets["AncientTemple"])
+    scene.set_instances([(glm.identity(), t)])
+    P, V = scenes.camera(640, 360, eye=(0.8, -0.45, 0.6))
+    got, st = scene.check_primary(P, V, 640, 360, flags=abi.FLAG_SHADOW_RAYS, what="shadow rays, temple")
+    traced = (got["packed"] >> 22) & 1
+    lit = (got["packed"] >> 23) & 1
+    assert traced.sum() > 1000 and 0 < lit.sum() < traced.sum()
+    a = scene.add(assets["Treasure"])
+    scene.set_instances([(glm.translate(glm.identity(), (0.7 * i - 0.7, 0.0, -0.9 * i)), a if i % 2 else t) for i in range(3)])
+    scene.check_primary(P, V, 640, 360, flags=abi.FLAG_SHADOW_RAYS, what="shadow rays, three instances")
+
+
+class ProcScene(Scene):
+    def add_procedural(self, kind, w, h, d, seed):
+        rid = self.r.add_volume_procedural(kind, w, h, d, seed)
+        oid = self.o.add_volume_procedural(kind, w, h, d, seed)
+        self.tex_map[oid] = rid
+        return oid
+
+    def check_rays(self, w, h, seed, n_check, what=""):
+        self.r.configure(width=w, height=h, mode=abi.MODE_RAYS, flags=0, seed=seed, sample_first=0, max_frames=0)
+        P, V = scenes.camera(w, h)
+        assert self.r.render_tick_raw(P, V)
+        got = self.r.read_hits().reshape(-1)[:n_check]
+        color = self.r.read_color().reshape(-1, 4)[:n_check]
+        want, wcolor, iters = self.o.render_rays(n_check, seed)
+        for field in ("hit_voxel", "packed", "instance", "iters"):
+            bad = np.flatnonzero(got[field] != want[field])
+            assert len(bad) == 0, f"{what}: {field} differs for {len(bad)} rays, first ray {bad[:1]}"
+        assert np.array_equal(color, wcolor), f"{what}: colours differ"
+        st = self.r.stats()
+        if n_check == w * h:
+            assert st.iterations == iters
+        return got, st
+
+
+@pytest.fixture()
+def pscene(renderer, oracle):
+    renderer.reset()
+    return ProcScene(renderer, oracle)
+
+
+def test_heightmap_brick_volume_small(pscene):
+    t = pscene.add_procedural(abi.VOLUME_HEIGHTMAP, 256, 128, 192, 1)
+    pscene.set_instances([(glm.identity(), t)])
+    for eye in [(0.9, -0.8, 0.9), (-0.6, -0.3, 1.1)]:
+        P, V = scenes.camera(480, 270, eye=eye)
+        got, _ = pscene.check_primary(P, V, 480, 270, flags=abi.FLAG_SHADOW_RAYS, what=f"heightmap 256x128x192 {eye}")
+        assert (got["hit_voxel"] != abi.VT_MISS).sum() > 5000
+
+
+def test_brick_and_dense_volumes_in_one_scene(pscene, assets):
+    b = pscene.add_procedural(abi.VOLUME_SPARSE_BRICKS, 64, 64, 64, 2)
+    d = pscene.add(assets["Treasure"])
+    h = pscene.add_procedural(abi.VOLUME_HEIGHTMAP, 128, 128, 128, 9)
+    pscene.set_instances([(glm.translate(glm.identity(), (-1.1, 0.0, 0.0)), b), (glm.identity(), d),
+                          (glm.translate(glm.identity(), (1.1, 0.0, 0.2)), h)])
+    P, V = scenes.camera(640, 360, eye=(0.4, -1.0, 2.4))
+    got, _ = pscene.check_primary(P, V, 640, 360, flags=abi.FLAG_SHADOW_RAYS, what="bricks + dense")
+    assert set(np.unique(got["instance"])) >= {0, 1, 2}
+
+
+def test_incoherent_rays_small(pscene, assets):
+    t = pscene.add_procedural(abi.VOLUME_SPARSE_BRICKS, 512, 512, 512, 2)
+    pscene.set_instances([(glm.identity(), t)])
+    got, st = pscene.check_rays(256, 128, seed=3, n_check=256 * 128, what="sparse 512^3 rays")
+    assert 0.2 < (got["hit_voxel"] != abi.VT_MISS).mean() < 0.8
+    # the same mode over a dense volume (stop mask in global memory)
+    pscene.r.reset()
+    ps = ProcScene(pscene.r, __import__("oracle_lib"))
+    d = ps.add(assets["AncientTemple"])
+    ps.set_instances([(glm.identity(), d)])
+    ps.check_rays(128, 128, seed=7, n_check=128 * 128, what="dense volume rays")
+
+
+def test_config3_heightmap_1024_4k_subset(pscene):
+    """BASELINE configs[3]: 1024^3 heightmap terrain, 3840x2160 primary + shadow rays; oracle parity on a
+    1/64 pixel subset."""
+    t = pscene.add_procedural(abi.VOLUME_HEIGHTMAP, 1024, 1024, 1024, 1)
+    pscene.set_instances([(glm.identity(), t)])
+    P, V = scenes.camera(3840, 2160, eye=(0.9, -0.8, 0.9))
+    got, st = pscene.check_primary(P, V, 3840, 2160, flags=abi.FLAG_SHADOW_RAYS, what="config 3", subset=True)
+    assert (got["hit_voxel"] != abi.VT_MISS).sum() > 2000 and st.rays > 3840 * 2160
+
+
+def test_config4_sparse_4096_first_rays(pscene):
+    """BASELINE configs[4]: sparse 4096^3 brick volume, incoherent rays; oracle parity on the first 2^16
+    rays of a 2^22-ray launch (the full 2^26-ray launch is a benchmark, tools/run_config.py)."""
+    t = pscene.add_procedural(abi.VOLUME_SPARSE_BRICKS, 4096, 4096, 4096, 2)
+    pscene.set_instances([(glm.identity(), t)])
+    got, st = pscene.check_rays(2048, 2048, seed=3, n_check=1 << 16, what="config 4")
+    assert st.rays == 2048 * 2048 and st.iterations > (1 << 22) * 50
 
 
 # ---- path-tracing extension -----------------------------------------------------------------

@@ -13,8 +13,9 @@ import numpy as np
 from . import build as _build
 
 VT_MISS = 0xFFFFFFFF
-MODE_PRIMARY, MODE_PATHS = 0, 1
-FLAG_VIEWPORT_H_IS_W, FLAG_NO_HIT_RECORDS, FLAG_FORCE_GLOBAL_MASKS, FLAG_PERSISTENT_LANES, FLAG_PER_PIXEL_PATHS, FLAG_NO_BINNING = 1, 2, 4, 8, 16, 32
+MODE_PRIMARY, MODE_PATHS, MODE_RAYS = 0, 1, 2
+VOLUME_HEIGHTMAP, VOLUME_SPARSE_BRICKS = 1, 2
+FLAG_VIEWPORT_H_IS_W, FLAG_NO_HIT_RECORDS, FLAG_FORCE_GLOBAL_MASKS, FLAG_PERSISTENT_LANES, FLAG_PER_PIXEL_PATHS, FLAG_NO_BINNING, FLAG_SHADOW_RAYS = 1, 2, 4, 8, 16, 32, 64
 
 HIT_DTYPE = np.dtype([("hit_voxel", "<u4"), ("packed", "<u4"), ("instance", "<u4"), ("iters", "<u4")])
 
@@ -49,6 +50,7 @@ SYMBOLS = {
     "render_tick": (_i32, [C.POINTER(_i32), C.POINTER(_i32), C.POINTER(RenderTickInfo)]),
     "get_input_data_pointer": (C.POINTER(UserInput), []),
     "add_texture": (_i32, [_vp, _u32, _u32, _u32]),
+    "vt_add_volume_procedural": (_i32, [_u32, _u32, _u32, _u32, _u32]),
     "start_update_instances": (_vp, [_u32]),
     "end_update_instances": (_i32, [_u32]),
     "cleanup": (None, []),

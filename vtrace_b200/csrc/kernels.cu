@@ -27,6 +27,7 @@ namespace vt {
 #define VT_FLAG_NO_HIT_RECORDS 2u
 #define VT_FLAG_PERSISTENT_LANES 8u
 #define VT_FLAG_PER_PIXEL_PATHS 16u
+#define VT_FLAG_SHADOW_RAYS 64u
 #define VT_MISS 0xFFFFFFFFu
 
 static constexpr int kBlockThreads = 256; // 8 warps
@@ -186,6 +187,9 @@ __global__ void instance_setup_kernel(const float* __restrict__ instances, uint3
     M[15] = 1.0f;                   // trace.vert:39-40
     I.valid = I.tex < fp.n_volumes ? 1u : 0u;
     I.pad = 0;
+    I.pad0 = 0;
+    I.bricks = nullptr;
+    I.sun_m[0] = I.sun_m[1] = I.sun_m[2] = 0.0f;
     if (!I.valid) {
         I.w = I.h = I.d = I.xb = I.yb = I.mask_off = I.remap_identity = 0;
         I.rgba = nullptr;
@@ -199,6 +203,7 @@ __global__ void instance_setup_kernel(const float* __restrict__ instances, uint3
     const VolumeDesc v = volumes[I.tex];
     I.w = v.w; I.h = v.h; I.d = v.d; I.xb = v.xb; I.yb = v.yb; I.mask_off = v.mask_off; I.rgba = v.rgba;
     I.remap_identity = v.remap_identity;
+    I.bricks = v.bricks;
     mat4_inverse(M, Mi); // trace.frag:65
     // MVP = (P V) * M
     for (int j = 0; j < 4; ++j)
@@ -215,6 +220,7 @@ __global__ void instance_setup_kernel(const float* __restrict__ instances, uint3
         I.eye_m[r] = ((Mi[0 * 4 + r] * fp.eye[0] + Mi[1 * 4 + r] * fp.eye[1]) + Mi[2 * 4 + r] * fp.eye[2]) + Mi[3 * 4 + r] * 1.0f;
         I.slab_lo[r] = -0.5f - I.eye_m[r];
         I.slab_hi[r] = 0.5f - I.eye_m[r];
+        I.sun_m[r] = (Mi[0 * 4 + r] * fp.sun[0] + Mi[1 * 4 + r] * fp.sun[1]) + Mi[2 * 4 + r] * fp.sun[2];
     }
     // Conservative screen rectangle of the proxy cube (what the rasteriser would bin): project the 8
     // corners, +-2 pixels of slack.  Any corner at or behind the eye plane -> whole screen.  A pixel
@@ -526,6 +532,8 @@ __device__ __forceinline__ void dda_march(const Vol& vol, const float pos[3], co
     }
 }
 
+#include "bricks.cuh"
+
 // texel colour at the hit voxel (the only volume-texel read of a ray)
 __device__ __forceinline__ uchar4 fetch_texel(const uint8_t* rgba, uint32_t W, uint32_t H, uint32_t D, bool identity,
                                               const int32_t v[3]) {
@@ -549,7 +557,58 @@ struct Fragment {
     Dda dda;
 };
 
-template <bool kSmem>
+// marches (pos, dir[, start voxel]) through the instance's volume, whatever its kind
+template <bool kSmem, bool kBricks>
+__device__ __forceinline__ void march_instance(const InstUniforms* __restrict__ Ip, const uint32_t* mask_base, const float pos[3],
+                                               const float dir[3], bool has_start, const int32_t sv[3], Dda& r) {
+    if (kBricks && Ip->bricks) {
+        const BrickVolume bv = *Ip->bricks;
+        dda_march_bricks(bv, Ip->w, Ip->h, Ip->d, pos, dir, has_start, sv, r);
+    } else {
+        Vol vol{Ip->w, Ip->h, Ip->d, Ip->xb, Ip->yb, Ip->mask_off, mask_base};
+        dda_march<kSmem>(vol, pos, dir, has_start, sv, r);
+    }
+}
+
+// colour of the instance's voxel v (dense: the texel; brick volumes: procedural)
+template <bool kBricks>
+__device__ __forceinline__ uchar4 instance_texel(const InstUniforms* __restrict__ Ip, const int32_t v[3]) {
+    if (kBricks && Ip->bricks)
+        return proc_color(Ip->bricks->kind, Ip->bricks->seed, Ip->h, (uint32_t)v[0], (uint32_t)v[1], (uint32_t)v[2]);
+    return fetch_texel(Ip->rgba, Ip->w, Ip->h, Ip->d, Ip->remap_identity != 0, v);
+}
+
+// Where a secondary ray (bounce or shadow) leaves a hit: axis = first axis advanced by the last DDA
+// iteration (or the box-entry axis when steps == 0), origin = hit point clamped to the hit voxel with
+// the normal component on the face plane, start voxel = the neighbour across that face.
+__device__ __forceinline__ void leave_hit(const Dda& r, int entry_axis, const float size[3], int& a_out, int& nsign_out, float p0[3],
+                                          int32_t sv[3]) {
+    const uint32_t lm = r.steps ? r.last_mask : (1u << entry_axis);
+    const int a = (lm & 1u) ? 0 : ((lm & 2u) ? 1 : 2);
+    const float t = r.steps ? ((a == 0 ? r.side[0] : (a == 1 ? r.side[1] : r.side[2])) -
+                               (a == 0 ? r.delta[0] : (a == 1 ? r.delta[1] : r.delta[2])))
+                            : 0.0f;
+    const float tl = t / r.len;
+    int nsign = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float p = r.pos[k] + r.dir[k] * tl;
+        const float lo = (float)r.v[k], hi = (float)(r.v[k] + 1);
+        p = p < lo ? lo : p;
+        p = p > hi ? hi : p;
+        p0[k] = p;
+        sv[k] = r.v[k];
+        if (k == a) {
+            nsign = r.step[k] != 0 ? -r.step[k] : (r.pos[k] <= 0.5f * size[k] ? -1 : 1);
+            p0[k] = (float)(r.v[k] + (nsign > 0 ? 1 : 0));
+            sv[k] += nsign;
+        }
+    }
+    a_out = a;
+    nsign_out = nsign;
+}
+
+template <bool kSmem, bool kBricks = false>
 __device__ __forceinline__ void run_fragment(const FrameParams& fp, const InstUniforms* __restrict__ Ip, const uint32_t* mask_base,
                                              int px, int py, float fx, float fy, Fragment& f) {
     f.covered = false;
@@ -597,9 +656,8 @@ __device__ __forceinline__ void run_fragment(const FrameParams& fp, const InstUn
         dir[k] = ((Ip->Mi[0 * 3 + k] * rd[0] + Ip->Mi[1 * 3 + k] * rd[1]) + Ip->Mi[2 * 3 + k] * rd[2]) + Ip->Mi[3 * 3 + k] * 0.0f;
         pos[k] = (mp[k] + 0.5f) * size[k];
     }
-    Vol vol{Ip->w, Ip->h, Ip->d, Ip->xb, Ip->yb, Ip->mask_off, mask_base};
     const int32_t none[3] = {0, 0, 0};
-    dda_march<kSmem>(vol, pos, dir, false, none, f.dda);
+    march_instance<kSmem, kBricks>(Ip, mask_base, pos, dir, false, none, f.dda);
 }
 
 __device__ __forceinline__ uint32_t face_bits(const Dda& r, int entry_axis) {
@@ -656,7 +714,7 @@ __device__ __forceinline__ int claim_tiles(unsigned long long* counter, int lane
 // -------------------------------------------------------------------------------------------
 // trace_primary_kernel: persistent warps over 8x4 pixel tiles; one thread per pixel.
 
-template <bool kSmem>
+template <bool kSmem, bool kBricks>
 __global__ void __launch_bounds__(kBlockThreads) trace_primary_kernel(const __grid_constant__ FrameParams fp,
                                                                       const InstUniforms* __restrict__ inst, const BinTable bins,
                                                                       const uint32_t* __restrict__ mask_arena,
@@ -676,7 +734,7 @@ __global__ void __launch_bounds__(kBlockThreads) trace_primary_kernel(const __gr
     const uint32_t clear_g = srgb_encode(lut.threshold, 81.0f / 100.0f);
     const uint32_t clear_b = srgb_encode(lut.threshold, 92.0f / 100.0f);
 
-    unsigned long long iter_sum = 0;
+    unsigned long long iter_sum = 0, shadow_rays = 0;
     // Primary rays are cheap (tens of microseconds for the whole frame), so tiles are dealt
     // round-robin over all resident warps instead of through a scheduler atomic: neighbouring
     // tiles (similar cost) land on different SMs, which balances as well and costs nothing.
@@ -701,15 +759,36 @@ __global__ void __launch_bounds__(kBlockThreads) trace_primary_kernel(const __gr
             for (uint32_t k = k_begin; k < k_end; ++k) {
                 const uint32_t i = bins.enabled ? __ldg(bins.list + k) : k;
                 Fragment f;
-                run_fragment<kSmem>(fp, inst + i, mask_base, px, py, fx, fy, f);
+                run_fragment<kSmem, kBricks>(fp, inst + i, mask_base, px, py, fx, fy, f);
                 if (!f.covered) continue;
                 rec.iters += f.dda.steps;
                 if (!f.dda.hit) continue;        // discard, trace.frag:89
                 if (!(f.depth < zbuf)) continue; // VK_COMPARE_OP_LESS, lib/pipeline.c:148-150
                 zbuf = f.depth;
                 const InstUniforms* Ip = inst + i;
-                const uchar4 s = fetch_texel(Ip->rgba, Ip->w, Ip->h, Ip->d, Ip->remap_identity != 0, f.dda.v);
-                if (s.w == 255) {
+                const uchar4 s = instance_texel<kBricks>(Ip, f.dda.v);
+                // extension: one shadow ray towards the sun, inside the fragment's own volume
+                float shade = 1.0f;
+                uint32_t shadow_bits = 0;
+                if (fp.flags & VT_FLAG_SHADOW_RAYS) {
+                    const float size[3] = {(float)(int32_t)Ip->w, (float)(int32_t)Ip->h, (float)(int32_t)Ip->d};
+                    int ax, nsign;
+                    float p0[3];
+                    int32_t sv[3];
+                    leave_hit(f.dda, f.entry_axis, size, ax, nsign, p0, sv);
+                    const float sun_m[3] = {Ip->sun_m[0], Ip->sun_m[1], Ip->sun_m[2]};
+                    bool lit = false;
+                    if ((float)nsign * (ax == 0 ? sun_m[0] : (ax == 1 ? sun_m[1] : sun_m[2])) > 0.0f) { // the face looks at the sun
+                        Dda sh;
+                        march_instance<kSmem, kBricks>(Ip, mask_base, p0, sun_m, true, sv, sh);
+                        rec.iters += sh.steps;
+                        lit = !sh.hit;
+                        shadow_bits = 1u | (lit ? 2u : 0u);
+                        shadow_rays += 1;
+                    }
+                    shade = lit ? 1.0f : 0.35f;
+                }
+                if (s.w == 255 && shade == 1.0f) {
                     // a == 1: src*1 + dst*0 == src exactly and encode(decode(c)) == c by construction
                     dst[0] = s.x; dst[1] = s.y; dst[2] = s.z; dst[3] = 255u;
                 } else {
@@ -717,11 +796,11 @@ __global__ void __launch_bounds__(kBlockThreads) trace_primary_kernel(const __gr
                     const float a = (float)s.w / 255.0f;
                     const uint32_t sc[3] = {s.x, s.y, s.z};
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) dst[c] = srgb_encode(lut.threshold, dec[sc[c]] * a + dec[dst[c]] * (1.0f - a));
+                    for (int c = 0; c < 3; ++c) dst[c] = srgb_encode(lut.threshold, (dec[sc[c]] * shade) * a + dec[dst[c]] * (1.0f - a));
                     dst[3] = (uint32_t)__float2int_rz(floorf(a * 255.0f + 0.5f));
                 }
                 rec.hit_voxel = (uint32_t)f.dda.v[0] + Ip->w * ((uint32_t)f.dda.v[1] + Ip->h * (uint32_t)f.dda.v[2]);
-                rec.packed = (f.dda.steps & 0xFFFFu) | (face_bits(f.dda, f.entry_axis) << 16);
+                rec.packed = (f.dda.steps & 0xFFFFu) | (face_bits(f.dda, f.entry_axis) << 16) | (shadow_bits << 22);
                 rec.instance = i;
             }
             const size_t p = (size_t)py * (size_t)fp.width + (size_t)px;
@@ -733,9 +812,14 @@ __global__ void __launch_bounds__(kBlockThreads) trace_primary_kernel(const __gr
     }
     // one atomic per warp
 #pragma unroll
-    for (int o = 16; o; o >>= 1) iter_sum += __shfl_xor_sync(0xffffffffu, iter_sum, o);
+    for (int o = 16; o; o >>= 1) {
+        iter_sum += __shfl_xor_sync(0xffffffffu, iter_sum, o);
+        shadow_rays += __shfl_xor_sync(0xffffffffu, shadow_rays, o);
+    }
     if (lane == 0 && iter_sum) atomicAdd(fb.stats + 1, iter_sum);
+    if (lane == 0 && shadow_rays) atomicAdd(fb.stats + 0, shadow_rays);
 }
+
 
 // -------------------------------------------------------------------------------------------
 // path-tracing extension
@@ -768,6 +852,63 @@ __device__ __forceinline__ void rng_sphere(Rng& r, float s[3]) {
     s[0] = (2.0f * a) * w;
     s[1] = (2.0f * b) * w;
     s[2] = 1.0f - 2.0f * q;
+}
+
+// -------------------------------------------------------------------------------------------
+// trace_rays_kernel (extension): incoherent rays through instance 0's volume,
+// in its voxel space.  Ray i: origin uniform in the volume, direction uniform on the sphere, from the
+// RNG stream keyed (seed, i).  One thread per ray, grid-stride; masks of dense volumes stay in global
+// memory here (the mode exists for volumes far larger than shared memory).
+// Record: hit_voxel = x | y << 16, instance = z, packed = steps | face bits << 16, iters = steps.
+__global__ void __launch_bounds__(kBlockThreads) trace_rays_kernel(const __grid_constant__ FrameParams fp,
+                                                                   const InstUniforms* __restrict__ inst,
+                                                                   const uint32_t* __restrict__ mask_arena, unsigned long long n,
+                                                                   unsigned long long first, FrameBuffers fb) {
+    const InstUniforms* Ip = inst;
+    const float size[3] = {(float)(int32_t)Ip->w, (float)(int32_t)Ip->h, (float)(int32_t)Ip->d};
+    unsigned long long iter_sum = 0;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        const unsigned long long i = first + k;
+        Rng rng;
+        rng_init(rng, fp.seed, (uint32_t)i, (uint32_t)(i >> 32));
+        float pos[3], dir[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) pos[c] = rng_u01(rng) * size[c];
+        rng_sphere(rng, dir);
+        Dda r;
+        const int32_t none[3] = {0, 0, 0};
+        if (Ip->valid) march_instance<false, true>(Ip, mask_arena, pos, dir, false, none, r);
+        else { r.hit = false; r.steps = 0; r.last_mask = 0; r.step[0] = r.step[1] = r.step[2] = 0; r.v[0] = r.v[1] = r.v[2] = 0; }
+        iter_sum += r.steps;
+        uint4 rec = make_uint4(VT_MISS, 0u, VT_MISS, r.steps);
+        uchar4 px = make_uchar4(0, 0, 0, 0);
+        if (r.hit) {
+            const uint32_t neg = (r.step[0] < 0 ? 1u : 0u) | (r.step[1] < 0 ? 2u : 0u) | (r.step[2] < 0 ? 4u : 0u);
+            rec.x = (uint32_t)r.v[0] | ((uint32_t)r.v[1] << 16);
+            rec.y = (r.steps & 0xFFFFu) | ((r.last_mask | (neg << 3)) << 16);
+            rec.z = (uint32_t)r.v[2];
+            px = instance_texel<true>(Ip, r.v);
+        }
+        if (fb.records) *reinterpret_cast<uint4*>(fb.records + k) = rec;
+        fb.color[k] = px;
+    }
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) iter_sum += __shfl_xor_sync(0xffffffffu, iter_sum, o);
+    if (lane == 0 && iter_sum) atomicAdd(fb.stats + 1, iter_sum);
+}
+
+cudaError_t launch_trace_rays(const FrameParams& fp, const InstUniforms* inst, const uint32_t* mask_arena, unsigned long long n,
+                              unsigned long long first, FrameBuffers fb, int sm_count, cudaStream_t stream) {
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_rays_kernel, kBlockThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    unsigned long long blocks = (n + kBlockThreads - 1) / kBlockThreads;
+    const unsigned long long cap = (unsigned long long)per_sm * sm_count * 4; // a few waves: rays differ in length by 100x
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    trace_rays_kernel<<<(unsigned)blocks, kBlockThreads, 0, stream>>>(fp, inst, mask_arena, n, first, fb);
+    return cudaGetLastError();
 }
 
 struct PathHit {
@@ -1289,7 +1430,9 @@ __global__ void resolve_kernel(const unsigned long long* __restrict__ accum, uin
 
 cudaError_t configure_kernels(int max_smem_optin) {
     cudaError_t e;
-    e = cudaFuncSetAttribute(trace_primary_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    e = cudaFuncSetAttribute(trace_primary_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(trace_primary_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(trace_paths_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     if (e != cudaSuccess) return e;
@@ -1315,12 +1458,21 @@ cudaError_t launch_trace_primary(const FrameParams& fp, const InstUniforms* inst
                                  cudaStream_t stream) {
     const int n_tiles = ((fp.width + kTileW - 1) / kTileW) * ((fp.height + kTileH - 1) / kTileH);
     const size_t smem = trace_smem_bytes(arena_words, masks_in_smem);
-    if (masks_in_smem) {
-        const int grid = persistent_grid(trace_primary_kernel<true>, smem, sm_count, n_tiles);
-        trace_primary_kernel<true><<<grid, kBlockThreads, smem, stream>>>(fp, inst, bins, mask_arena, arena_words, lut, fb);
+    const int warps_needed = (n_tiles + 7) / 8;
+    if (fp.any_bricks) { // scenes with procedural brick volumes: the variant that knows both volume kinds
+        if (masks_in_smem) {
+            const int grid = persistent_grid(trace_primary_kernel<true, true>, smem, sm_count, warps_needed);
+            trace_primary_kernel<true, true><<<grid, kBlockThreads, smem, stream>>>(fp, inst, bins, mask_arena, arena_words, lut, fb);
+        } else {
+            const int grid = persistent_grid(trace_primary_kernel<false, true>, smem, sm_count, warps_needed);
+            trace_primary_kernel<false, true><<<grid, kBlockThreads, smem, stream>>>(fp, inst, bins, mask_arena, arena_words, lut, fb);
+        }
+    } else if (masks_in_smem) {
+        const int grid = persistent_grid(trace_primary_kernel<true, false>, smem, sm_count, warps_needed);
+        trace_primary_kernel<true, false><<<grid, kBlockThreads, smem, stream>>>(fp, inst, bins, mask_arena, arena_words, lut, fb);
     } else {
-        const int grid = persistent_grid(trace_primary_kernel<false>, smem, sm_count, n_tiles);
-        trace_primary_kernel<false><<<grid, kBlockThreads, smem, stream>>>(fp, inst, bins, mask_arena, arena_words, lut, fb);
+        const int grid = persistent_grid(trace_primary_kernel<false, false>, smem, sm_count, warps_needed);
+        trace_primary_kernel<false, false><<<grid, kBlockThreads, smem, stream>>>(fp, inst, bins, mask_arena, arena_words, lut, fb);
     }
     return cudaGetLastError();
 }

@@ -20,6 +20,8 @@
 
 namespace vt {
 
+struct BrickVolume;
+
 struct VolumeDesc {
     const uint8_t* rgba; // dense W*H*D RGBA8
     uint32_t w, h, d;
@@ -27,7 +29,25 @@ struct VolumeDesc {
     uint32_t mask_off;   // word offset of this volume's mask inside the arena
     uint32_t mask_words; // multiple of 4 (16-byte granules for the bulk copy)
     uint32_t remap_identity; // 1 when floor(fl(v/s)*s) == v on all three axes (texel == voxel)
+    const BrickVolume* bricks; // non-null: a procedural brick volume (rgba / mask fields unused)
 };
+
+// Large procedural volumes (extension; §8f rank 2): occupancy only, as a
+// two-level sparse structure; colours are a function of the voxel position.
+//   l1    : one bit per 8^3 brick (set = the brick has at least one filled voxel)
+//   table : per brick, its slot in `pool` (only meaningful where the l1 bit is set)
+//   pool  : 16 words per non-empty brick; voxel (x,y,z) of a brick is bit (x | (y&3) << 3) of
+//           word ((z&7) << 1 | (y&7) >> 2)
+struct BrickVolume {
+    const uint32_t* l1;
+    const uint32_t* table;
+    const uint32_t* pool;
+    const float* heights;  // heightmap kind: w*d column heights
+    uint32_t kind, seed;   // VT_VOLUME_*
+    uint32_t bx, by, bz;   // brick grid dimensions
+    uint32_t n_bricks;     // non-empty bricks in the pool
+};
+static constexpr uint32_t kVolumeDense = 0, kVolumeHeightmap = 1, kVolumeSparseBricks = 2;
 
 // Per-frame uniforms, passed by value as a kernel parameter (constant bank, no loads).
 struct FrameParams {
@@ -43,6 +63,8 @@ struct FrameParams {
     // path-tracing extension
     uint32_t spp, bounces, seed, sample_first, sample_stride;
     uint32_t refill_threshold; // persistent-lane kernel: refill when fewer lanes than this still march
+    float sun[3];              // unit vector towards the sun, world space (shadow-ray extension)
+    uint32_t any_bricks;       // the scene contains a procedural brick volume
 };
 
 // Per-instance uniforms (trace.vert outputs that are flat per instance + derived matrices).
@@ -53,6 +75,8 @@ struct __align__(16) InstUniforms {
     float dirm[12];  // inverse(M)3x3 * RD rows 0-2: clip point -> model-space ray direction
     float eye_m[3];  // camera position in model space
     uint32_t valid;  // texture id in range
+    float sun_m[3];  // inverse(M)3x3 * sun: shadow-ray direction in model space
+    uint32_t pad0;
     int32_t bounds[4]; // conservative screen rectangle of the proxy cube: x0, x1, y0, y1 (inclusive); 16-byte aligned
     float slab_lo[3]; // -0.5 - eye_m
     float slab_hi[3]; //  0.5 - eye_m
@@ -63,6 +87,7 @@ struct __align__(16) InstUniforms {
     uint32_t remap_identity;
     uint32_t pad;
     const uint8_t* rgba;
+    const BrickVolume* bricks; // non-null: procedural brick volume
 };
 
 static_assert(offsetof(InstUniforms, bounds) % 16 == 0, "bounds are loaded as one int4");
@@ -115,6 +140,13 @@ cudaError_t launch_trace_primary(const FrameParams& fp, const InstUniforms* inst
 cudaError_t launch_trace_paths(const FrameParams& fp, const InstUniforms* inst, BinTable bins, const uint32_t* mask_arena,
                                uint32_t arena_words, bool masks_in_smem, SrgbTables lut, FrameBuffers fb,
                                int sm_count, cudaStream_t stream);
+// procedural brick volumes: column heights, then count / fill passes over all bricks
+cudaError_t launch_heightmap(float* heights, uint32_t w, uint32_t h, uint32_t d, uint32_t seed, cudaStream_t stream);
+cudaError_t launch_brick_build(uint32_t kind, uint32_t seed, uint32_t w, uint32_t h, uint32_t d, const float* heights, uint32_t* l1,
+                               uint32_t* table, uint32_t* pool, uint32_t pool_capacity, uint32_t* counter, cudaStream_t stream);
+// incoherent-ray mode: rays [first, first + n) through instance 0's volume
+cudaError_t launch_trace_rays(const FrameParams& fp, const InstUniforms* inst, const uint32_t* mask_arena, unsigned long long n,
+                              unsigned long long first, FrameBuffers fb, int sm_count, cudaStream_t stream);
 cudaError_t launch_resolve(const unsigned long long* accum, uint32_t n_pixels, uint32_t total_spp, SrgbTables lut,
                            uchar4* color, cudaStream_t stream);
 // one-time: opt in to large dynamic shared memory

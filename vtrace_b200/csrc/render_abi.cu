@@ -35,6 +35,9 @@ struct State {
     bool vols_dirty = false;
     uint32_t* d_arena = nullptr; // all stop masks, contiguous
     uint32_t arena_words = 0, arena_cap = 0;
+    struct BrickAlloc { uint32_t* l1; uint32_t* table; uint32_t* pool; float* heights; BrickVolume* d_desc; };
+    std::vector<BrickAlloc> brick_allocs; // procedural volumes (extension)
+    bool any_bricks = false;
     uint8_t* h_tex_staging = nullptr; // pinned; grows to the next power of two (lib/memory.c:297-302)
     size_t tex_staging_size = 0;
 
@@ -201,8 +204,8 @@ int finish_frame() {
     float ms = 0.0f;
     if (cudaEventElapsedTime(&ms, g.ev_trace0, g.ev_trace1) == cudaSuccess) g.stats.last_trace_ms = ms;
     if (cudaEventElapsedTime(&ms, g.ev_begin, g.ev_end) == cudaSuccess) g.stats.last_frame_ms = ms;
-    if (g.cfg.mode == VT_MODE_PRIMARY) {
-        g.stats.rays = (uint64_t)g.cfg.width * g.cfg.height;
+    if (g.cfg.mode == VT_MODE_PRIMARY || g.cfg.mode == VT_MODE_RAYS) {
+        g.stats.rays = (uint64_t)g.cfg.width * g.cfg.height + g.h_stats[0]; // + shadow rays
         g.stats.iterations = g.h_stats[1];
     } else {
         g.stats.rays = g.h_stats[0];
@@ -244,6 +247,13 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
     fp.sample_first = g.cfg.sample_first;
     fp.sample_stride = g.cfg.sample_stride ? g.cfg.sample_stride : 1;
     fp.refill_threshold = g.refill_threshold;
+    {   // sun direction (0.4, -0.8, 0.45), normalised (same float operations as the oracle)
+        const float sx = 0.4f, sy = -0.8f, sz = 0.45f;
+        const float l = sqrtf((sx * sx + sy * sy) + sz * sz);
+        fp.sun[0] = sx / l; fp.sun[1] = sy / l; fp.sun[2] = sz / l;
+    }
+    fp.any_bricks = g.any_bricks ? 1u : 0u;
+    if (g.cfg.mode == VT_MODE_PATHS && g.any_bricks) return fail("path tracing over procedural brick volumes is not implemented");
 
     if (g.vols_dirty) {
         if (g.vols.size() > g.d_vols_cap) {
@@ -308,7 +318,13 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
     fb.stats = g.d_stats;
     SrgbTables lut{g.d_dec, g.d_thr};
 
-    if (g.cfg.mode == VT_MODE_PRIMARY) {
+    if (g.cfg.mode == VT_MODE_RAYS) {
+        const unsigned long long n = (unsigned long long)g.cfg.width * g.cfg.height;
+        CK(cudaEventRecord(g.ev_trace0, g.stream));
+        CK(launch_trace_rays(fp, g.d_iu, g.d_arena, n, (unsigned long long)g.cfg.sample_first * n, fb, g.sm_count, g.stream));
+        CK(cudaEventRecord(g.ev_trace1, g.stream));
+        g.stats.launches += 1;
+    } else if (g.cfg.mode == VT_MODE_PRIMARY) {
         CK(cudaEventRecord(g.ev_trace0, g.stream));
         CK(launch_trace_primary(fp, g.d_iu, bins, g.d_arena, g.arena_words, in_smem, lut, fb, g.sm_count, g.stream));
         CK(cudaEventRecord(g.ev_trace1, g.stream));
@@ -492,6 +508,7 @@ extern "C" int32_t add_texture(const uint8_t* data, uint32_t width, uint32_t hei
     v.xb = xb; v.yb = yb;
     v.mask_off = g.arena_words;
     v.mask_words = mask_words_padded;
+    v.bricks = nullptr;
     // texel == voxel when the reference's coordinate round trip floor(fl(v/s)*s) is the identity
     // (true for 16, 40, 50, 64, ...; false e.g. for 22 or 41) — lets the kernels skip three divisions per hit
     v.remap_identity = 1;
@@ -513,6 +530,68 @@ extern "C" int32_t add_texture(const uint8_t* data, uint32_t width, uint32_t hei
     g.vols.push_back(v);
     g.vols_dirty = true;
     return (int32_t)(g.vols.size() - 1); // lib/memory.c:292,384
+}
+
+// extension: a large procedural volume generated on the device as sparse bricks.
+extern "C" int32_t vt_add_volume_procedural(uint32_t kind, uint32_t width, uint32_t height, uint32_t depth, uint32_t seed) {
+    if (!g.inited) return fail("vt_add_volume_procedural before entry()");
+    if (g.vols.size() >= kMaxTextures) return fail("Tried allocating too many textures");
+    if (kind != kVolumeHeightmap && kind != kVolumeSparseBricks) return fail("vt_add_volume_procedural: unknown kind %u", kind);
+    if (!width || !height || !depth || (width | height | depth) & 7u || width > 8192 || height > 8192 || depth > 8192)
+        return fail("vt_add_volume_procedural: dimensions must be multiples of 8, at most 8192");
+    {   // brick volumes assume texel == voxel (true for powers of two; checked like add_texture does)
+        const uint32_t dims[3] = {width, height, depth};
+        for (int a = 0; a < 3; ++a) {
+            const float sz = (float)(int32_t)dims[a];
+            for (uint32_t x = 0; x < dims[a]; ++x)
+                if ((int32_t)floorf(((float)(int32_t)x / sz) * sz) != (int32_t)x)
+                    return fail("vt_add_volume_procedural: size %u does not map voxels to texels one to one", dims[a]);
+        }
+    }
+    CK(cudaSetDevice(g.device));
+    const size_t bricks = (size_t)(width >> 3) * (height >> 3) * (depth >> 3);
+    if (bricks >= (1ull << 31)) return fail("vt_add_volume_procedural: too many bricks");
+    State::BrickAlloc a{};
+    uint32_t* d_counter = nullptr;
+    uint32_t n = 0;
+    CK(cudaMalloc(&d_counter, 4));
+    if (kind == kVolumeHeightmap) {
+        CK(cudaMalloc(&a.heights, (size_t)width * depth * sizeof(float)));
+        CK(launch_heightmap(a.heights, width, height, depth, seed, g.stream));
+        g.stats.launches += 1;
+    }
+    CK(cudaMalloc(&a.l1, ((bricks + 31) / 32) * 4));
+    CK(cudaMalloc(&a.table, bricks * 4));
+    CK(cudaMemsetAsync(a.l1, 0, ((bricks + 31) / 32) * 4, g.stream));
+    // pass 1 counts the non-empty bricks, pass 2 fills the pool
+    CK(cudaMemsetAsync(d_counter, 0, 4, g.stream));
+    CK(launch_brick_build(kind, seed, width, height, depth, a.heights, a.l1, a.table, nullptr, 0, d_counter, g.stream));
+    CK(cudaMemcpyAsync(&n, d_counter, 4, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaMalloc(&a.pool, (size_t)(n ? n : 1) * 64));
+    CK(cudaMemsetAsync(d_counter, 0, 4, g.stream));
+    CK(launch_brick_build(kind, seed, width, height, depth, a.heights, a.l1, a.table, a.pool, n, d_counter, g.stream));
+    g.stats.launches += 2;
+    BrickVolume bv{};
+    bv.l1 = a.l1; bv.table = a.table; bv.pool = a.pool; bv.heights = a.heights;
+    bv.kind = kind; bv.seed = seed;
+    bv.bx = width >> 3; bv.by = height >> 3; bv.bz = depth >> 3;
+    bv.n_bricks = n;
+    CK(cudaMalloc(&a.d_desc, sizeof(BrickVolume)));
+    CK(cudaMemcpyAsync(a.d_desc, &bv, sizeof bv, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    cudaFree(d_counter);
+    g.brick_allocs.push_back(a);
+    VolumeDesc v{};
+    v.rgba = nullptr;
+    v.w = width; v.h = height; v.d = depth;
+    v.xb = 5; v.yb = 2; v.mask_off = 0; v.mask_words = 0;
+    v.remap_identity = 1;
+    v.bricks = a.d_desc;
+    g.vols.push_back(v);
+    g.vols_dirty = true;
+    g.any_bricks = true;
+    return (int32_t)(g.vols.size() - 1);
 }
 
 extern "C" float* start_update_instances(uint32_t instance_count) {
@@ -543,6 +622,8 @@ extern "C" void cleanup(void) {
     cudaDeviceSynchronize(); // vkDeviceWaitIdle, lib/entry.c:101
     for (auto& v : g.vols) cudaFree(const_cast<uint8_t*>(v.rgba));
     g.vols.clear();
+    for (auto& b : g.brick_allocs) { cudaFree(b.l1); cudaFree(b.table); cudaFree(b.pool); cudaFree(b.heights); cudaFree(b.d_desc); }
+    g.brick_allocs.clear();
     cudaFree(g.d_vols); cudaFree(g.d_arena); cudaFree(g.d_inst); cudaFree(g.d_iu); cudaFree(g.d_dec); cudaFree(g.d_thr);
     cudaFree(g.d_rec); cudaFree(g.d_color); cudaFree(g.d_depth); cudaFree(g.d_accum_own); cudaFree(g.d_stats);
     cudaFree(g.d_bin_offset); cudaFree(g.d_bin_count); cudaFree(g.d_bin_list); cudaFree(g.d_bin_cursor);
@@ -570,7 +651,7 @@ extern "C" int32_t vt_get_config(vt_config* out) {
 extern "C" int32_t vt_configure(const vt_config* cfg) {
     if (!g.inited) return fail("vt_configure before entry()");
     if (!cfg || !cfg->width || !cfg->height) return fail("vt_configure: bad size");
-    if (cfg->mode > VT_MODE_PATHS) return fail("vt_configure: unknown mode %u", cfg->mode);
+    if (cfg->mode > VT_MODE_RAYS) return fail("vt_configure: unknown mode %u", cfg->mode);
     if ((uint64_t)cfg->width * cfg->height > (1ull << 28)) return fail("vt_configure: framebuffer too large");
     CK(cudaSetDevice(g.device));
     if (finish_frame()) return -1;

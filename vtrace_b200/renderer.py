@@ -134,6 +134,12 @@ class Renderer:
             raise RuntimeError("ERROR: Adding texture failed: " + abi.last_error())
         return tex_id
 
+    def add_volume_procedural(self, kind: int, w: int, h: int, d: int, seed: int) -> int:
+        tex_id = self._lib.vt_add_volume_procedural(kind, w, h, d, seed)
+        if tex_id < 0:
+            raise RuntimeError("ERROR: Adding procedural volume failed: " + abi.last_error())
+        return tex_id
+
     # -- headless extensions -------------------------------------------------------------------
     def get_config(self) -> abi.VtConfig:
         cfg = abi.VtConfig()
