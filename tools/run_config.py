@@ -29,6 +29,9 @@ CONFIGS = {
     "temple_primary": ("AncientTemple", 1920, 1080, abi.MODE_PRIMARY, 0),     # configs[1]
     "temple_paths": ("AncientTemple", 1920, 1080, abi.MODE_PATHS, 64),        # configs[2]
     "treasure_paths": ("Treasure", 1920, 1080, abi.MODE_PATHS, 64),
+    # extension scenes (procedural brick volumes)
+    "heightmap_4k": ("heightmap1024", 3840, 2160, abi.MODE_PRIMARY, 0),        # configs[3]: primary + shadow rays
+    "sparse_rays": ("sparse4096", 8192, 8192, abi.MODE_RAYS, 0),               # configs[4]: 2^26 incoherent rays
 }
 
 
@@ -53,11 +56,20 @@ def main():
             from vtrace_b200 import glm
             P = glm.perspective(glm.REFERENCE_FOV, np.float32(w) / np.float32(h), glm.REFERENCE_NEAR, glm.REFERENCE_FAR)
             V = glm.look_at((0.0, -2.0, 0.0), (3.0, -5.0, 2.0), (0.0, 1.0, 0.0))
+        elif asset == "heightmap1024":
+            r.add_volume_procedural(abi.VOLUME_HEIGHTMAP, 1024, 1024, 1024, 1)
+            r.update_instances_raw(scenes.single_instance(0))
+            P, V = scenes.camera(w, h, eye=(0.9, -0.8, 0.9))
+            args.flags |= abi.FLAG_SHADOW_RAYS | abi.FLAG_NO_HIT_RECORDS * 0
+        elif asset == "sparse4096":
+            r.add_volume_procedural(abi.VOLUME_SPARSE_BRICKS, 4096, 4096, 4096, 2)
+            r.update_instances_raw(scenes.single_instance(0))
+            P, V = scenes.camera(w, h)
         else:
             r.add_texture(scenes.load_asset(asset))
             r.update_instances_raw(scenes.single_instance(0))
             P, V = scenes.camera(w, h, eye=CLOSEUP_EYE if args.closeup else scenes.EYE)
-        r.configure(width=w, height=h, mode=mode, flags=args.flags, spp=max(spp, 1), bounces=4, seed=0x5EED,
+        r.configure(width=w, height=h, mode=mode, flags=args.flags, spp=max(spp, 1), bounces=4, seed=3 if mode == abi.MODE_RAYS else 0x5EED,
                     sample_first=0, sample_stride=1, total_spp=max(spp, 1), max_frames=0)
         trace_ms, frame_ms = [], []
         for i in range(args.warmup + args.frames):

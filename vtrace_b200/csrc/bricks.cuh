@@ -122,70 +122,95 @@ cudaError_t launch_brick_build(uint32_t kind, uint32_t seed, uint32_t w, uint32_
     return cudaGetLastError();
 }
 
-// The reference's DDA (trace.frag:63-89) over a brick volume.  Same state, same float operations in
-// the same order as dda_init / dda_step / dda_slow_impl — only the occupancy test differs.
-__device__ __forceinline__ void dda_march_bricks(const BrickVolume& bv, uint32_t W, uint32_t H, uint32_t D, const float pos[3],
-                                                 const float dir[3], bool has_start, const int32_t sv[3], Dda& r) {
-    const int32_t isz[3] = {(int32_t)W, (int32_t)H, (int32_t)D};
-    const float size[3] = {(float)isz[0], (float)isz[1], (float)isz[2]};
+// The reference's DDA (trace.frag:63-89) over a brick volume, as a resumable walk: same state, same
+// float operations in the same order as dda_init / dda_step / dda_slow_impl — only the occupancy
+// test differs.  brick_walk_step() runs ONE loop iteration; the persistent-lane ray kernel interleaves
+// the walks of 32 lanes and refills lanes whose ray ended.
+struct BrickWalk {
+    int32_t vx, vy, vz;
+    float sx, sy, sz;
+    uint32_t steps, last;
+    uint32_t cur_key, cur_slot;
+    bool finite;
+};
+
+__device__ __forceinline__ void brick_walk_init(uint32_t W, uint32_t H, uint32_t D, const float pos[3], const float dir[3],
+                                                bool has_start, const int32_t sv[3], Dda& r, BrickWalk& k) {
+    const float size[3] = {(float)(int32_t)W, (float)(int32_t)H, (float)(int32_t)D};
     float sgn[3];
     r.len = sqrtf((dir[0] * dir[0] + dir[1] * dir[1]) + dir[2] * dir[2]); // length(), :70
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        r.pos[k] = pos[k];
-        r.dir[k] = dir[k];
-        r.v[k] = has_start ? sv[k] : __float2int_rz(floorf(vt_fmin(pos[k], size[k] - 1.0f))); // :68
-        sgn[k] = dir[k] > 0.0f ? 1.0f : (dir[k] < 0.0f ? -1.0f : 0.0f);                       // :69
-        r.step[k] = (int32_t)sgn[k];
-        r.delta[k] = fabsf(r.len / dir[k]);                                                   // :70
-        r.side[k] = ((sgn[k] * ((float)r.v[k] - pos[k]) + sgn[k] * 0.5f) + 0.5f) * r.delta[k]; // :71
+    for (int c = 0; c < 3; ++c) {
+        r.pos[c] = pos[c];
+        r.dir[c] = dir[c];
+        r.v[c] = has_start ? sv[c] : __float2int_rz(floorf(vt_fmin(pos[c], size[c] - 1.0f))); // :68
+        sgn[c] = dir[c] > 0.0f ? 1.0f : (dir[c] < 0.0f ? -1.0f : 0.0f);                       // :69
+        r.step[c] = (int32_t)sgn[c];
+        r.delta[c] = fabsf(r.len / dir[c]);                                                   // :70
+        r.side[c] = ((sgn[c] * ((float)r.v[c] - pos[c]) + sgn[c] * 0.5f) + 0.5f) * r.delta[c]; // :71
     }
     r.steps = 0;
     r.last_mask = 0;
     r.hit = false;
-    const bool finite = isfinite(r.delta[0]) && isfinite(r.delta[1]) && isfinite(r.delta[2]) && isfinite(r.side[0]) &&
-                        isfinite(r.side[1]) && isfinite(r.side[2]);
-    const uint32_t max_steps = W + H + D; // :74
-    uint32_t cur_key = 0xFFFFFFFFu, cur_slot = 0xFFFFFFFFu;
-    int32_t vx = r.v[0], vy = r.v[1], vz = r.v[2];
-    float sx = r.side[0], sy = r.side[1], sz = r.side[2];
-    uint32_t steps = 0, last = 0;
-    while (steps < max_steps && (uint32_t)vx < W && (uint32_t)vy < H && (uint32_t)vz < D) { // :75
-        // texture(tex, voxel / size): brick volumes only exist for sizes where the texel IS the voxel
-        const uint32_t key = ((uint32_t)vx >> 3) | (((uint32_t)vy >> 3) << 10) | (((uint32_t)vz >> 3) << 20);
-        if (key != cur_key) { // entered a new brick: one l1 bit, and the slot if it is set
-            cur_key = key;
-            const size_t b = ((size_t)((uint32_t)vz >> 3) * bv.by + ((uint32_t)vy >> 3)) * bv.bx + ((uint32_t)vx >> 3);
-            const uint32_t bit = (__ldg(bv.l1 + (b >> 5)) >> (b & 31)) & 1u;
-            cur_slot = bit ? __ldg(bv.table + b) : 0xFFFFFFFFu;
-        }
-        if (cur_slot != 0xFFFFFFFFu) {
-            const uint32_t wv = __ldg(bv.pool + (size_t)cur_slot * 16 + ((((uint32_t)vz & 7u) << 1) | (((uint32_t)vy & 7u) >> 2)));
-            if ((wv >> (((uint32_t)vx & 7u) | (((uint32_t)vy & 3u) << 3))) & 1u) { r.hit = true; break; } // :78-80
-        }
-        bool m0, m1, m2;
-        if (finite) { // no NaN: side <= min(other two) is side == min(all three); vec3(mask) * delta is a predicated add
-            const float m = fminf(fminf(sx, sy), sz);
-            m0 = sx == m; m1 = sy == m; m2 = sz == m;
-            if (m0) sx += r.delta[0];
-            if (m1) sy += r.delta[1];
-            if (m2) sz += r.delta[2];
-        } else {
-            m0 = sx <= vt_fmin(sy, sz); // :83
-            m1 = sy <= vt_fmin(sz, sx);
-            m2 = sz <= vt_fmin(sx, sy);
-            sx += (m0 ? 1.0f : 0.0f) * r.delta[0]; // :84
-            sy += (m1 ? 1.0f : 0.0f) * r.delta[1];
-            sz += (m2 ? 1.0f : 0.0f) * r.delta[2];
-        }
-        vx += m0 ? r.step[0] : 0; // :85
-        vy += m1 ? r.step[1] : 0;
-        vz += m2 ? r.step[2] : 0;
-        last = (m0 ? 1u : 0u) | (m1 ? 2u : 0u) | (m2 ? 4u : 0u);
-        ++steps; // :86
+    k.finite = isfinite(r.delta[0]) && isfinite(r.delta[1]) && isfinite(r.delta[2]) && isfinite(r.side[0]) &&
+               isfinite(r.side[1]) && isfinite(r.side[2]);
+    k.vx = r.v[0]; k.vy = r.v[1]; k.vz = r.v[2];
+    k.sx = r.side[0]; k.sy = r.side[1]; k.sz = r.side[2];
+    k.steps = 0; k.last = 0;
+    k.cur_key = 0xFFFFFFFFu; k.cur_slot = 0xFFFFFFFFu;
+}
+
+// one iteration of the while loop of trace.frag:75-87; returns 0 = keep walking, 1 = hit, 2 = left / out of steps
+__device__ __forceinline__ int brick_walk_step(const BrickVolume& bv, uint32_t W, uint32_t H, uint32_t D, const Dda& r, BrickWalk& k) {
+    if (!(k.steps < W + H + D && (uint32_t)k.vx < W && (uint32_t)k.vy < H && (uint32_t)k.vz < D)) return 2; // :74-75
+    // texture(tex, voxel / size): brick volumes only exist for sizes where the texel IS the voxel
+    const uint32_t key = ((uint32_t)k.vx >> 3) | (((uint32_t)k.vy >> 3) << 10) | (((uint32_t)k.vz >> 3) << 20);
+    if (key != k.cur_key) { // entered a new brick: one l1 bit, and the slot if it is set
+        k.cur_key = key;
+        const size_t b = ((size_t)((uint32_t)k.vz >> 3) * bv.by + ((uint32_t)k.vy >> 3)) * bv.bx + ((uint32_t)k.vx >> 3);
+        const uint32_t bit = (__ldg(bv.l1 + (b >> 5)) >> (b & 31)) & 1u;
+        k.cur_slot = bit ? __ldg(bv.table + b) : 0xFFFFFFFFu;
     }
-    r.v[0] = vx; r.v[1] = vy; r.v[2] = vz;
-    r.side[0] = sx; r.side[1] = sy; r.side[2] = sz;
-    r.steps = steps;
-    r.last_mask = last;
+    if (k.cur_slot != 0xFFFFFFFFu) {
+        const uint32_t wv = __ldg(bv.pool + (size_t)k.cur_slot * 16 + ((((uint32_t)k.vz & 7u) << 1) | (((uint32_t)k.vy & 7u) >> 2)));
+        if ((wv >> (((uint32_t)k.vx & 7u) | (((uint32_t)k.vy & 3u) << 3))) & 1u) return 1; // :78-80
+    }
+    bool m0, m1, m2;
+    if (k.finite) { // no NaN: side <= min(other two) is side == min(all three); vec3(mask) * delta is a predicated add
+        const float m = fminf(fminf(k.sx, k.sy), k.sz);
+        m0 = k.sx == m; m1 = k.sy == m; m2 = k.sz == m;
+        if (m0) k.sx += r.delta[0];
+        if (m1) k.sy += r.delta[1];
+        if (m2) k.sz += r.delta[2];
+    } else {
+        m0 = k.sx <= vt_fmin(k.sy, k.sz); // :83
+        m1 = k.sy <= vt_fmin(k.sz, k.sx);
+        m2 = k.sz <= vt_fmin(k.sx, k.sy);
+        k.sx += (m0 ? 1.0f : 0.0f) * r.delta[0]; // :84
+        k.sy += (m1 ? 1.0f : 0.0f) * r.delta[1];
+        k.sz += (m2 ? 1.0f : 0.0f) * r.delta[2];
+    }
+    k.vx += m0 ? r.step[0] : 0; // :85
+    k.vy += m1 ? r.step[1] : 0;
+    k.vz += m2 ? r.step[2] : 0;
+    k.last = (m0 ? 1u : 0u) | (m1 ? 2u : 0u) | (m2 ? 4u : 0u);
+    ++k.steps; // :86
+    return 0;
+}
+
+__device__ __forceinline__ void brick_walk_finish(const BrickWalk& k, bool hit, Dda& r) {
+    r.v[0] = k.vx; r.v[1] = k.vy; r.v[2] = k.vz;
+    r.side[0] = k.sx; r.side[1] = k.sy; r.side[2] = k.sz;
+    r.steps = k.steps;
+    r.last_mask = k.last;
+    r.hit = hit;
+}
+
+__device__ __forceinline__ void dda_march_bricks(const BrickVolume& bv, uint32_t W, uint32_t H, uint32_t D, const float pos[3],
+                                                 const float dir[3], bool has_start, const int32_t sv[3], Dda& r) {
+    BrickWalk k;
+    brick_walk_init(W, H, D, pos, dir, has_start, sv, r, k);
+    int status;
+    while ((status = brick_walk_step(bv, W, H, D, r, k)) == 0) {}
+    brick_walk_finish(k, status == 1, r);
 }

@@ -866,21 +866,18 @@ __global__ void __launch_bounds__(kBlockThreads) trace_rays_kernel(const __grid_
                                                                    unsigned long long first, FrameBuffers fb) {
     const InstUniforms* Ip = inst;
     const float size[3] = {(float)(int32_t)Ip->w, (float)(int32_t)Ip->h, (float)(int32_t)Ip->d};
+    const int lane = threadIdx.x & 31;
     unsigned long long iter_sum = 0;
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+
+    auto make_ray = [&](unsigned long long k, float pos[3], float dir[3]) {
         const unsigned long long i = first + k;
         Rng rng;
         rng_init(rng, fp.seed, (uint32_t)i, (uint32_t)(i >> 32));
-        float pos[3], dir[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) pos[c] = rng_u01(rng) * size[c];
         rng_sphere(rng, dir);
-        Dda r;
-        const int32_t none[3] = {0, 0, 0};
-        if (Ip->valid) march_instance<false, true>(Ip, mask_arena, pos, dir, false, none, r);
-        else { r.hit = false; r.steps = 0; r.last_mask = 0; r.step[0] = r.step[1] = r.step[2] = 0; r.v[0] = r.v[1] = r.v[2] = 0; }
-        iter_sum += r.steps;
+    };
+    auto write_ray = [&](unsigned long long k, const Dda& r) {
         uint4 rec = make_uint4(VT_MISS, 0u, VT_MISS, r.steps);
         uchar4 px = make_uchar4(0, 0, 0, 0);
         if (r.hit) {
@@ -892,8 +889,87 @@ __global__ void __launch_bounds__(kBlockThreads) trace_rays_kernel(const __grid_
         }
         if (fb.records) *reinterpret_cast<uint4*>(fb.records + k) = rec;
         fb.color[k] = px;
+    };
+
+    if (!Ip->valid || !Ip->bricks) {
+        // dense volumes (or no volume): one ray per thread, grid-stride
+        const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+        for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+            float pos[3], dir[3];
+            make_ray(k, pos, dir);
+            Dda r;
+            const int32_t none[3] = {0, 0, 0};
+            if (Ip->valid) march_instance<false, false>(Ip, mask_arena, pos, dir, false, none, r);
+            else { r.hit = false; r.steps = 0; r.last_mask = 0; r.step[0] = r.step[1] = r.step[2] = 0; r.v[0] = r.v[1] = r.v[2] = 0; }
+            iter_sum += r.steps;
+            write_ray(k, r);
+        }
+    } else {
+        // Brick volumes: rays differ in length by three orders of magnitude, so lanes are persistent
+        // workers — a warp claims 2048 consecutive ray ids at a time; a lane whose ray ended writes its
+        // record and starts the next id as soon as a quarter of the warp is idle.
+        const BrickVolume bv = *Ip->bricks;
+        const uint32_t W = Ip->w, H = Ip->h, D = Ip->d;
+        constexpr unsigned long long kChunk = 2048;
+        const unsigned long long n_chunks = (n + kChunk - 1) / kChunk;
+        unsigned long long chunk_next = 0, chunk_end = 0; // the warp's current range of ray ids
+        bool more = true;
+        bool active = false;
+        unsigned long long my_ray = 0;
+        Dda r;
+        BrickWalk k;
+        r.hit = false; r.steps = 0; r.last_mask = 0; r.len = 1.0f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { r.v[c] = 0; r.step[c] = 0; r.side[c] = r.delta[c] = r.dir[c] = r.pos[c] = 0.0f; }
+        k.vx = k.vy = k.vz = 0; k.sx = k.sy = k.sz = 0.0f; k.steps = k.last = 0; k.cur_key = k.cur_slot = 0xFFFFFFFFu; k.finite = true;
+        for (;;) {
+            // ---- refill idle lanes ----
+            uint32_t idle = __ballot_sync(0xffffffffu, !active);
+            while (idle && more) {
+                if (chunk_next >= chunk_end) {
+                    unsigned long long c = 0;
+                    if (lane == 0) c = atomicAdd(fb.stats + 2, 1ull);
+                    c = __shfl_sync(0xffffffffu, c, 0);
+                    if (c >= n_chunks) { more = false; break; }
+                    chunk_next = c * kChunk;
+                    chunk_end = chunk_next + kChunk < n ? chunk_next + kChunk : n;
+                }
+                const unsigned long long avail = chunk_end - chunk_next;
+                const uint32_t rank = __popc(idle & ((1u << lane) - 1u));
+                if (!active && rank < avail) {
+                    my_ray = chunk_next + rank;
+                    float pos[3], dir[3];
+                    make_ray(my_ray, pos, dir);
+                    const int32_t none[3] = {0, 0, 0};
+                    brick_walk_init(W, H, D, pos, dir, false, none, r, k);
+                    active = true;
+                }
+                const unsigned long long want = __popc(idle);
+                chunk_next += want < avail ? want : avail;
+                idle = __ballot_sync(0xffffffffu, !active);
+            }
+            const uint32_t act = __ballot_sync(0xffffffffu, active);
+            if (!act) break;
+            // ---- walk until a quarter of the warp has ended (or everything, when no rays are left) ----
+            const int stop_at = more ? 8 : 32;
+            for (;;) {
+#pragma unroll 1
+                for (int u = 0; u < 8; ++u) {
+                    if (active) {
+                        const int status = brick_walk_step(bv, W, H, D, r, k);
+                        if (status) {
+                            brick_walk_finish(k, status == 1, r);
+                            iter_sum += r.steps;
+                            write_ray(my_ray, r);
+                            active = false;
+                        }
+                    }
+                }
+                const int n_idle = __popc(__ballot_sync(0xffffffffu, !active));
+                if (n_idle >= stop_at || n_idle == 32) break;
+            }
+        }
     }
-    const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int o = 16; o; o >>= 1) iter_sum += __shfl_xor_sync(0xffffffffu, iter_sum, o);
     if (lane == 0 && iter_sum) atomicAdd(fb.stats + 1, iter_sum);
@@ -904,7 +980,7 @@ cudaError_t launch_trace_rays(const FrameParams& fp, const InstUniforms* inst, c
     int per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_rays_kernel, kBlockThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
     unsigned long long blocks = (n + kBlockThreads - 1) / kBlockThreads;
-    const unsigned long long cap = (unsigned long long)per_sm * sm_count * 4; // a few waves: rays differ in length by 100x
+    const unsigned long long cap = (unsigned long long)per_sm * sm_count; // persistent: one resident wave
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     trace_rays_kernel<<<(unsigned)blocks, kBlockThreads, 0, stream>>>(fp, inst, mask_arena, n, first, fb);
