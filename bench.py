@@ -171,7 +171,7 @@ def run_cuda(args):
     import torch.distributed as dist
 
     from vtrace_b200 import abi
-    from vtrace_b200.distributed import reduce_accum, shard_samples
+    from vtrace_b200.distributed import reduce_accum, setup_fused_reduce, shard_samples, stream_barrier
     from vtrace_b200.renderer import Renderer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -200,18 +200,36 @@ def run_cuda(args):
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     r.set_stream(stream.cuda_stream)
-    accum = torch.zeros((HEIGHT, WIDTH, 3), dtype=torch.int64, device=dev)  # 2^-24 fixed-point radiance sums
-    r.set_accum_buffer(accum.data_ptr())
+    # N > 1: by default every rank's trace kernel adds its sums straight into rank 0's buffer with NVLink
+    # atomics (vt_fused_reduce_*); --reduce allreduce keeps a per-rank buffer and sums them with NCCL
+    fused = world > 1 and args.reduce == "fused"
+    accum = None
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    if fused:
+        setup_fused_reduce(r, rank, world, dev)
+    else:
+        accum = torch.zeros((HEIGHT, WIDTH, 3), dtype=torch.int64, device=dev)  # 2^-24 fixed-point radiance sums
+        r.set_accum_buffer(accum.data_ptr())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     frame_host = np.empty((HEIGHT, WIDTH, 4), dtype=np.uint8)
     lib = abi.load()
 
+    def trace_and_reduce():
+        if fused:
+            r.fused_reduce_next_frame()
+            r.render_async(P, V)
+            stream_barrier(flag)   # all ranks' kernels (and their remote atomics) are done after this
+            if rank == 0:
+                r.resolve()        # also clears the buffer for its next use
+        else:
+            accum.zero_()
+            r.render_async(P, V)
+            reduce_accum(accum)
+            r.resolve()
+
     def step_resident():
         """One frame, everything device-resident, no host copies."""
-        accum.zero_()
-        r.render_async(P, V)
-        reduce_accum(accum)
-        r.resolve()
+        trace_and_reduce()
 
     def step_e2e():
         """One frame through the reference-facing ABI with host buffers."""
@@ -219,12 +237,10 @@ def run_cuda(args):
         if world == 1:
             assert r.render_tick_raw(P, V)    # projection/camera by host pointer; clear + trace + resolve
         else:
-            accum.zero_()
-            r.render_async(P, V)
-            reduce_accum(accum)
-            r.resolve()
-        n = lib.vt_read_color(frame_host.ctypes.data, frame_host.nbytes)  # finished frame -> host
-        assert n == frame_host.nbytes
+            trace_and_reduce()
+        if rank == 0 or not fused:
+            n = lib.vt_read_color(frame_host.ctypes.data, frame_host.nbytes)  # finished frame -> host
+            assert n == frame_host.nbytes
 
     def barrier():
         if world > 1:
@@ -318,7 +334,8 @@ def run_cuda(args):
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
-    r.set_accum_buffer(None)
+    if not fused:
+        r.set_accum_buffer(None)
     r.close()
     if world > 1:
         dist.destroy_process_group()
@@ -334,6 +351,7 @@ def main():
     ap.add_argument("--cpu-spp", type=int, default=64, help="spp of the bounded cpu_baseline sample (64 = the whole frame)")
     ap.add_argument("--ref-spp", type=int, default=64, help="spp per step of the --impl reference arm (64 = the whole frame)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--reduce", default="fused", choices=["fused", "allreduce"], help="cross-GPU accumulation for N > 1")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

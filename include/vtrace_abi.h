@@ -170,6 +170,18 @@ void* vt_accum_device_ptr(void);
 int32_t vt_set_accum_buffer(void* device_ptr);
 int32_t vt_clear_accum(void);
 int32_t vt_resolve(void);
+/* Fused cross-GPU accumulation (one process per GPU, one node): instead of every rank summing into
+ * its own buffer and an all-reduce afterwards, the ROOT rank exports its (double-buffered)
+ * accumulation buffer as a 64-byte CUDA IPC handle, the other ranks import it, and every rank's trace
+ * kernel adds its tiles' sums straight into the root's memory with NVLink atomics — integer adds, so
+ * the result is bit-identical to the all-reduce.  Per frame, on every rank: vt_fused_reduce_next_frame,
+ * vt_render_async, then a stream-ordered barrier supplied by the launcher; then the root calls
+ * vt_resolve (which also clears the buffer for its next use).  Single-instance PATHS scenes only. */
+int32_t vt_fused_reduce_export(uint8_t handle[64]);
+int32_t vt_fused_reduce_import(const uint8_t handle[64]);
+int32_t vt_fused_reduce_next_frame(void);
+int32_t vt_fused_reduce_disable(void);
+
 /* Run on a caller-provided cudaStream_t (e.g. the launcher's current stream); NULL = own. */
 int32_t vt_set_stream(void* cuda_stream);
 

@@ -67,6 +67,10 @@ SYMBOLS = {
     "vt_set_accum_buffer": (_i32, [_vp]),
     "vt_clear_accum": (_i32, []),
     "vt_resolve": (_i32, []),
+    "vt_fused_reduce_export": (_i32, [_vp]),
+    "vt_fused_reduce_import": (_i32, [_vp]),
+    "vt_fused_reduce_next_frame": (_i32, []),
+    "vt_fused_reduce_disable": (_i32, []),
     "vt_set_stream": (_i32, [_vp]),
     "vt_get_stats": (_i32, [C.POINTER(VtStats)]),
     "vt_set_user_input": (_i32, [C.POINTER(UserInput)]),

@@ -25,6 +25,10 @@
 // slots bank-conflict-free):
 //   ray  q0 = side.xyz, idx      q1 = delta.xyz, step signs      q2 = prev, steps, state, pixel
 //   path p0 = thr.rgb, rng key   p1 = pos.xyz, len               p2 = dir.xyz, meta
+//
+// Multi-GPU: fb.accum may point at ANOTHER GPU's accumulation buffer (CUDA IPC mapping over NVLink,
+// see vt_fused_reduce_*): the per-tile flushes below are integer atomics, which work on peer memory
+// and commute, so N ranks tracing disjoint samples add into one buffer with no separate all-reduce.
 #pragma once
 
 static constexpr int kWaveWarps = 12;
@@ -96,7 +100,8 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
             if (in_frame && !may_hit) {
                 const size_t p = (size_t)py * (size_t)fp.width + (size_t)px;
 #pragma unroll
-                for (int c = 0; c < 3; ++c) fb.accum[3 * p + c] += sky_q[c] * fp.spp;
+                if (fp.sky_spp)
+                    for (int c = 0; c < 3; ++c) fb.accum[3 * p + c] += sky_q[c] * fp.sky_spp;
                 rays += fp.spp;
             }
         }

@@ -69,6 +69,11 @@ struct State {
     float* d_depth = nullptr;
     unsigned long long* d_accum = nullptr;     // in use (own or caller-provided)
     unsigned long long* d_accum_own = nullptr; // the library's allocation
+    // fused cross-GPU accumulation (vt_fused_reduce_*): 0 off, 1 root (owns the double buffer), 2 peer (maps it)
+    int fused_mode = 0;
+    unsigned long long* fused_base = nullptr; // two accumulation buffers back to back
+    size_t fused_stride = 0;                  // elements per buffer
+    uint32_t fused_index = 0;
     unsigned long long* d_stats = nullptr;
     unsigned long long* h_stats = nullptr; // pinned
     void* h_readback = nullptr;            // pinned staging for vt_read_*
@@ -253,6 +258,13 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
         fp.sun[0] = sx / l; fp.sun[1] = sy / l; fp.sun[2] = sz / l;
     }
     fp.any_bricks = g.any_bricks ? 1u : 0u;
+    fp.sky_spp = g.cfg.spp;
+    if (g.fused_mode && g.cfg.mode == VT_MODE_PATHS) {
+        if (g.inst_count != 1 || (g.cfg.flags & (VT_FLAG_PERSISTENT_LANES | VT_FLAG_PER_PIXEL_PATHS)))
+            return fail("fused cross-GPU accumulation needs the single-instance wavefront kernel");
+        if (g.fused_stride != (size_t)g.cfg.width * g.cfg.height * 3) return fail("fused accumulation buffer does not match the framebuffer size");
+        fp.sky_spp = g.fused_mode == 1 ? (g.cfg.total_spp ? g.cfg.total_spp : g.cfg.spp) : 0u;
+    }
     if (g.cfg.mode == VT_MODE_PATHS && g.any_bricks) return fail("path tracing over procedural brick volumes is not implemented");
 
     if (g.vols_dirty) {
@@ -314,7 +326,7 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
     fb.records = (g.cfg.flags & VT_FLAG_NO_HIT_RECORDS) ? nullptr : g.d_rec;
     fb.color = g.d_color;
     fb.depth = g.d_depth;
-    fb.accum = g.d_accum;
+    fb.accum = (g.fused_mode && g.cfg.mode == VT_MODE_PATHS) ? g.fused_base + g.fused_index * g.fused_stride : g.d_accum;
     fb.stats = g.d_stats;
     SrgbTables lut{g.d_dec, g.d_thr};
 
@@ -620,6 +632,10 @@ extern "C" void cleanup(void) {
     if (!g.inited) return;
     cudaSetDevice(g.device);
     cudaDeviceSynchronize(); // vkDeviceWaitIdle, lib/entry.c:101
+    if (g.fused_mode == 1) cudaFree(g.fused_base);
+    if (g.fused_mode == 2) cudaIpcCloseMemHandle(g.fused_base);
+    g.fused_base = nullptr;
+    g.fused_mode = 0;
     for (auto& v : g.vols) cudaFree(const_cast<uint8_t*>(v.rgba));
     g.vols.clear();
     for (auto& b : g.brick_allocs) { cudaFree(b.l1); cudaFree(b.table); cudaFree(b.pool); cudaFree(b.heights); cudaFree(b.d_desc); }
@@ -688,7 +704,8 @@ extern "C" int64_t vt_read_depth(float* depth, size_t capacity) {
     return read_back(g.d_depth, (size_t)g.cfg.width * g.cfg.height * 4, depth, capacity);
 }
 extern "C" int64_t vt_read_accum(uint64_t* accum, size_t capacity) {
-    return read_back(g.d_accum, (size_t)g.cfg.width * g.cfg.height * 24, accum, capacity);
+    const unsigned long long* src = g.fused_mode == 1 ? g.fused_base + g.fused_index * g.fused_stride : g.d_accum;
+    return read_back(src, (size_t)g.cfg.width * g.cfg.height * 24, accum, capacity);
 }
 
 extern "C" void* vt_accum_device_ptr(void) { return g.inited ? (void*)g.d_accum : nullptr; }
@@ -714,8 +731,65 @@ extern "C" int32_t vt_resolve(void) {
     CK(cudaSetDevice(g.device));
     const uint32_t total = g.cfg.total_spp ? g.cfg.total_spp : g.cfg.spp;
     SrgbTables lut{g.d_dec, g.d_thr};
-    CK(launch_resolve(g.d_accum, g.cfg.width * g.cfg.height, total ? total : 1, lut, g.d_color, g.stream));
+    if (g.fused_mode == 2) return fail("vt_resolve: only the root of a fused reduction holds the sums");
+    unsigned long long* src = g.fused_mode == 1 ? g.fused_base + g.fused_index * g.fused_stride : g.d_accum;
+    CK(launch_resolve(src, g.cfg.width * g.cfg.height, total ? total : 1, lut, g.d_color, g.stream));
     g.stats.launches += 1;
+    // fused: the buffer is next written two frames from now; clear it behind the resolve
+    if (g.fused_mode == 1) CK(cudaMemsetAsync(src, 0, g.fused_stride * sizeof(unsigned long long), g.stream));
+    return 0;
+}
+
+// ---- fused cross-GPU accumulation over NVLink peer memory (one process per GPU, one node) -----------
+extern "C" int32_t vt_fused_reduce_export(uint8_t handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    if (!g.inited || !handle) return -1;
+    CK(cudaSetDevice(g.device));
+    if (finish_frame()) return -1;
+    if (g.fused_mode) return fail("fused reduction already set up");
+    const size_t stride = (size_t)g.cfg.width * g.cfg.height * 3;
+    CK(cudaMalloc(&g.fused_base, 2 * stride * sizeof(unsigned long long)));
+    CK(cudaMemset(g.fused_base, 0, 2 * stride * sizeof(unsigned long long)));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, g.fused_base));
+    memcpy(handle, &h, 64);
+    g.fused_stride = stride;
+    g.fused_index = 0;
+    g.fused_mode = 1;
+    return 0;
+}
+
+extern "C" int32_t vt_fused_reduce_import(const uint8_t handle[64]) {
+    if (!g.inited || !handle) return -1;
+    CK(cudaSetDevice(g.device));
+    if (finish_frame()) return -1;
+    if (g.fused_mode) return fail("fused reduction already set up");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void* p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    g.fused_base = (unsigned long long*)p;
+    g.fused_stride = (size_t)g.cfg.width * g.cfg.height * 3;
+    g.fused_index = 0;
+    g.fused_mode = 2;
+    return 0;
+}
+
+extern "C" int32_t vt_fused_reduce_next_frame(void) {
+    if (!g.inited || !g.fused_mode) return -1;
+    g.fused_index ^= 1u;
+    return 0;
+}
+
+extern "C" int32_t vt_fused_reduce_disable(void) {
+    if (!g.inited) return -1;
+    CK(cudaSetDevice(g.device));
+    if (finish_frame()) return -1;
+    CK(cudaStreamSynchronize(g.stream));
+    if (g.fused_mode == 1) cudaFree(g.fused_base);
+    if (g.fused_mode == 2) cudaIpcCloseMemHandle(g.fused_base);
+    g.fused_base = nullptr;
+    g.fused_mode = 0;
     return 0;
 }
 

@@ -27,3 +27,27 @@ def reduce_accum(accum, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(accum, op=dist.ReduceOp.SUM, group=group)
     return accum
+
+
+def setup_fused_reduce(renderer, rank: int, world: int, device, root: int = 0):
+    """Wires the library's fused cross-GPU accumulation: the root exports the CUDA IPC handle of its
+    accumulation buffers, torch.distributed broadcasts the 64 bytes, every other rank maps them.  After
+    this, each rank's trace kernel adds its radiance straight into the root's memory over NVLink."""
+    import torch
+    import torch.distributed as dist
+
+    handle = torch.zeros(64, dtype=torch.uint8, device=device)
+    if rank == root:
+        handle.copy_(torch.frombuffer(bytearray(renderer.fused_reduce_export()), dtype=torch.uint8))
+    dist.broadcast(handle, src=root)
+    if rank != root:
+        renderer.fused_reduce_import(bytes(handle.cpu().numpy().tobytes()))
+    dist.barrier()
+
+
+def stream_barrier(flag):
+    """A stream-ordered barrier: a one-element all-reduce completes on a rank only after every rank's
+    stream reached it, i.e. after every rank's trace kernel (and its remote atomics) finished."""
+    import torch.distributed as dist
+
+    dist.all_reduce(flag)

@@ -205,6 +205,21 @@ class Renderer:
         if self._lib.vt_set_stream(C.c_void_p(cuda_stream_handle or 0)) != 0:
             raise RuntimeError("vt_set_stream failed: " + abi.last_error())
 
+    def fused_reduce_export(self) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        if self._lib.vt_fused_reduce_export(buf) != 0:
+            raise RuntimeError("vt_fused_reduce_export failed: " + abi.last_error())
+        return bytes(buf)
+
+    def fused_reduce_import(self, handle: bytes):
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        if self._lib.vt_fused_reduce_import(buf) != 0:
+            raise RuntimeError("vt_fused_reduce_import failed: " + abi.last_error())
+
+    def fused_reduce_next_frame(self):
+        if self._lib.vt_fused_reduce_next_frame() != 0:
+            raise RuntimeError("vt_fused_reduce_next_frame failed: " + abi.last_error())
+
     def set_accum_buffer(self, device_ptr: int | None):
         if self._lib.vt_set_accum_buffer(C.c_void_p(device_ptr or 0)) != 0:
             raise RuntimeError("vt_set_accum_buffer failed: " + abi.last_error())
