@@ -200,8 +200,8 @@ def run_cuda(args):
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     r.set_stream(stream.cuda_stream)
-    # N > 1: by default every rank's trace kernel adds its sums straight into rank 0's buffer with NVLink
-    # atomics (vt_fused_reduce_*); --reduce allreduce keeps a per-rank buffer and sums them with NCCL
+    # N > 1: by default every rank pushes its sums of the covered rectangle straight into rank 0's memory over
+    # NVLink (vt_fused_reduce_*); --reduce allreduce keeps a per-rank buffer and sums them with NCCL
     fused = world > 1 and args.reduce == "fused"
     accum = None
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -326,6 +326,7 @@ def run_cuda(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": recorded_traffic(), "kernel": "trace_paths_wave_kernel", "kernel_ms": kernel_s * 1e3,
                          "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                         "kernel_ms_max_over_ranks": t_trace / steps,
                          "dda_iterations_per_launch": iters / steps,
                          "dda_iterations_per_s": (iters / steps) / kernel_s},
             "clocks": clocks,

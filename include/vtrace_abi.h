@@ -170,15 +170,18 @@ void* vt_accum_device_ptr(void);
 int32_t vt_set_accum_buffer(void* device_ptr);
 int32_t vt_clear_accum(void);
 int32_t vt_resolve(void);
-/* Fused cross-GPU accumulation (one process per GPU, one node): instead of every rank summing into
- * its own buffer and an all-reduce afterwards, the ROOT rank exports its (double-buffered)
- * accumulation buffer as a 64-byte CUDA IPC handle, the other ranks import it, and every rank's trace
- * kernel adds its tiles' sums straight into the root's memory with NVLink atomics — integer adds, so
- * the result is bit-identical to the all-reduce.  Per frame, on every rank: vt_fused_reduce_next_frame,
- * vt_render_async, then a stream-ordered barrier supplied by the launcher; then the root calls
- * vt_resolve (which also clears the buffer for its next use).  Single-instance PATHS scenes only. */
-int32_t vt_fused_reduce_export(uint8_t handle[64]);
-int32_t vt_fused_reduce_import(const uint8_t handle[64]);
+/* Fused cross-GPU accumulation (one process per GPU, one node) — replaces the all-reduce of the
+ * accumulation buffers.  Rank 0 (the root) allocates a partial-sum buffer with one slot per rank and
+ * exports it as a 64-byte CUDA IPC handle; the other ranks import it.  Each frame every rank traces
+ * its samples into its own accumulators, then a small kernel streams the pixels of the instance's
+ * screen rectangle — the only ones that can differ from "spp x sky" — into the rank's slot in the
+ * root's memory with 32-byte vector stores over NVLink (and clears them locally).  After a
+ * stream-ordered barrier supplied by the launcher, the root's vt_resolve sums the slots (integers:
+ * bit-identical to an all-reduce) and encodes the frame.  Per frame, on every rank:
+ * vt_fused_reduce_next_frame (double buffering), vt_render_async, barrier; then vt_resolve on the root.
+ * Single-instance PATHS scenes only. */
+int32_t vt_fused_reduce_export(uint8_t handle[64], uint32_t world);
+int32_t vt_fused_reduce_import(const uint8_t handle[64], uint32_t rank, uint32_t world);
 int32_t vt_fused_reduce_next_frame(void);
 int32_t vt_fused_reduce_disable(void);
 

@@ -67,8 +67,8 @@ SYMBOLS = {
     "vt_set_accum_buffer": (_i32, [_vp]),
     "vt_clear_accum": (_i32, []),
     "vt_resolve": (_i32, []),
-    "vt_fused_reduce_export": (_i32, [_vp]),
-    "vt_fused_reduce_import": (_i32, [_vp]),
+    "vt_fused_reduce_export": (_i32, [_vp, _u32]),
+    "vt_fused_reduce_import": (_i32, [_vp, _u32, _u32]),
     "vt_fused_reduce_next_frame": (_i32, []),
     "vt_fused_reduce_disable": (_i32, []),
     "vt_set_stream": (_i32, [_vp]),

@@ -1501,6 +1501,70 @@ __global__ void resolve_kernel(const unsigned long long* __restrict__ accum, uin
 }
 
 // -------------------------------------------------------------------------------------------
+// Fused multi-GPU reduction (single-instance scenes).  Every rank accumulates its own samples locally;
+// only the tiles that touch the instance's screen rectangle can differ from "spp x sky".  push_partial
+// streams exactly those pixels — 32-byte vector stores, coalesced — into this rank's slot of a buffer
+// that lives in the ROOT GPU's memory (CUDA IPC mapping, NVLink), clearing the local sums behind it.
+// After a stream barrier the root's resolve_partials adds the slots up (integers: order-free, bit-exact)
+// and encodes the frame; pixels outside the rectangle are resolved analytically.
+// pixels for which paths are traced at all: inside the instance's conservative screen rectangle
+__device__ __forceinline__ bool covered_region(const InstUniforms* __restrict__ Ip, int px, int py) {
+    return !(px < Ip->bounds[0] || px > Ip->bounds[1] || py < Ip->bounds[2] || py > Ip->bounds[3]);
+}
+
+__global__ void push_partial_kernel(const InstUniforms* __restrict__ inst, unsigned long long* __restrict__ local_accum,
+                                    uint4* __restrict__ slot, uint32_t width, uint32_t height) {
+    const uint32_t px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y;
+    if (px >= width || py >= height || !covered_region(inst, (int)px, (int)py)) return;
+    const size_t p = (size_t)py * width + px;
+    const unsigned long long r = local_accum[3 * p + 0], g = local_accum[3 * p + 1], b = local_accum[3 * p + 2];
+    local_accum[3 * p + 0] = 0ull; local_accum[3 * p + 1] = 0ull; local_accum[3 * p + 2] = 0ull;
+    slot[2 * p + 0] = make_uint4((uint32_t)r, (uint32_t)(r >> 32), (uint32_t)g, (uint32_t)(g >> 32));
+    slot[2 * p + 1] = make_uint4((uint32_t)b, (uint32_t)(b >> 32), 0u, 0u);
+}
+
+__global__ void resolve_partials_kernel(const InstUniforms* __restrict__ inst, const uint4* __restrict__ partials, uint32_t world,
+                                        uint32_t width, uint32_t height, uint32_t total_spp, SrgbTables lut, uchar4* __restrict__ color,
+                                        unsigned long long* __restrict__ accum_out) {
+    const uint32_t px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y;
+    if (px >= width || py >= height) return;
+    const size_t p = (size_t)py * width + px, n_pix = (size_t)width * height;
+    unsigned long long sum[3];
+    if (covered_region(inst, (int)px, (int)py)) {
+        sum[0] = sum[1] = sum[2] = 0ull;
+        for (uint32_t r = 0; r < world; ++r) {
+            const uint4 a = partials[(r * n_pix + p) * 2 + 0], b = partials[(r * n_pix + p) * 2 + 1];
+            sum[0] += (unsigned long long)a.x | ((unsigned long long)a.y << 32);
+            sum[1] += (unsigned long long)a.z | ((unsigned long long)a.w << 32);
+            sum[2] += (unsigned long long)b.x | ((unsigned long long)b.y << 32);
+        }
+    } else { // sees only sky, for every sample of every rank
+        const float sky[3] = {53.0f / 100.0f, 81.0f / 100.0f, 92.0f / 100.0f};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sum[c] = __float2ull_rz((1.0f * sky[c]) * 16777216.0f) * total_spp;
+    }
+    const float scale = 1.0f / ((float)total_spp * 16777216.0f);
+    uint32_t c[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) c[k] = srgb_encode(lut.threshold, __ull2float_rn(sum[k]) * scale);
+    color[p] = make_uchar4((unsigned char)c[0], (unsigned char)c[1], (unsigned char)c[2], 255);
+    if (accum_out) { accum_out[3 * p + 0] = sum[0]; accum_out[3 * p + 1] = sum[1]; accum_out[3 * p + 2] = sum[2]; }
+}
+
+cudaError_t launch_push_partial(const InstUniforms* inst, unsigned long long* local_accum, uint4* slot, uint32_t width, uint32_t height,
+                                cudaStream_t stream) {
+    push_partial_kernel<<<dim3((width + 127) / 128, height), 128, 0, stream>>>(inst, local_accum, slot, width, height);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_resolve_partials(const InstUniforms* inst, const uint4* partials, uint32_t world, uint32_t width, uint32_t height,
+                                    uint32_t total_spp, SrgbTables lut, uchar4* color, unsigned long long* accum_out, cudaStream_t stream) {
+    resolve_partials_kernel<<<dim3((width + 127) / 128, height), 128, 0, stream>>>(inst, partials, world, width, height, total_spp, lut,
+                                                                                   color, accum_out);
+    return cudaGetLastError();
+}
+
+// -------------------------------------------------------------------------------------------
 // launch wrappers
 
 

@@ -149,6 +149,12 @@ cudaError_t launch_brick_build(uint32_t kind, uint32_t seed, uint32_t w, uint32_
 // incoherent-ray mode: rays [first, first + n) through instance 0's volume
 cudaError_t launch_trace_rays(const FrameParams& fp, const InstUniforms* inst, const uint32_t* mask_arena, unsigned long long n,
                               unsigned long long first, FrameBuffers fb, int sm_count, cudaStream_t stream);
+// fused multi-GPU reduction: move this rank's sums of the covered rectangle into its slot of the root's
+// partial buffer (peer memory) and clear them locally; then, on the root, sum all slots and resolve
+cudaError_t launch_push_partial(const InstUniforms* inst, unsigned long long* local_accum, uint4* slot, uint32_t width, uint32_t height,
+                                cudaStream_t stream);
+cudaError_t launch_resolve_partials(const InstUniforms* inst, const uint4* partials, uint32_t world, uint32_t width, uint32_t height,
+                                    uint32_t total_spp, SrgbTables lut, uchar4* color, unsigned long long* accum_out, cudaStream_t stream);
 cudaError_t launch_resolve(const unsigned long long* accum, uint32_t n_pixels, uint32_t total_spp, SrgbTables lut,
                            uchar4* color, cudaStream_t stream);
 // one-time: opt in to large dynamic shared memory

@@ -35,7 +35,7 @@ static constexpr int kWaveWarps = 12;
 static constexpr int kWaveThreads = kWaveWarps * 32;
 static constexpr int kSlots = 64;        // paths in flight per warp
 static constexpr int kSlotGroups = kSlots / 32;
-static constexpr uint32_t kItemSpp = 16; // samples per work item (tile x 16 samples)
+static constexpr uint32_t kItemSpp = 16; // most samples per work item (tile x samples)
 static constexpr uint32_t kPoolBytes = kSlots * 96 + kSlots + 32 + 32 * 3 * 4; // slots + byte list + covered-pixel table + tile accumulators
 static_assert(kPoolBytes % 16 == 0, "pool alignment");
 
@@ -73,13 +73,25 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
     const int tiles_x = (fp.width + kTileW - 1) / kTileW;
     const int tiles_y = (fp.height + kTileH - 1) / kTileH;
     const int n_tiles = tiles_x * tiles_y;
-    const int n_chunks = (int)((fp.spp + kItemSpp - 1) / kItemSpp);
     // Only tiles that touch the instance's screen rectangle become work items; every other pixel sees
     // nothing but sky and is written by the prologue below.
     const bool any_cov = Ip->bounds[0] <= Ip->bounds[1] && Ip->bounds[2] <= Ip->bounds[3];
     const int ctx0 = any_cov ? Ip->bounds[0] / kTileW : 0, ctx1 = any_cov ? Ip->bounds[1] / kTileW : -1;
     const int cty0 = any_cov ? Ip->bounds[2] / kTileH : 0, cty1 = any_cov ? Ip->bounds[3] / kTileH : -1;
     const int cov_w = ctx1 - ctx0 + 1, cov_tiles = cov_w * (cty1 - cty0 + 1);
+    // Work item = one tile x `item_spp` samples.  Items are sized so that there are several per resident
+    // warp even when a rank only has a few samples per pixel (multi-GPU), otherwise the tail dominates.
+    uint32_t item_spp = kItemSpp;
+    {
+        const long long want_items = 6ll * gridDim.x * kWaveWarps;
+        long long chunks = cov_tiles > 0 ? (want_items + cov_tiles - 1) / cov_tiles : 1;
+        if (chunks < (long long)((fp.spp + kItemSpp - 1) / kItemSpp)) chunks = (fp.spp + kItemSpp - 1) / kItemSpp;
+        if (chunks > (long long)fp.spp) chunks = fp.spp;
+        if (chunks < 1) chunks = 1;
+        item_spp = (fp.spp + (uint32_t)chunks - 1) / (uint32_t)chunks;
+        if (item_spp < 1) item_spp = 1;
+    }
+    const int n_chunks = (int)((fp.spp + item_spp - 1) / item_spp);
     const int n_items = cov_tiles * n_chunks;
 
     const float sky[3] = {53.0f / 100.0f, 81.0f / 100.0f, 92.0f / 100.0f}; // lib/command.c:57-59
@@ -252,8 +264,8 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
             const uint32_t cov = __ballot_sync(0xffffffffu, may_hit);
             it_ncov = __popc(cov);
             if (may_hit) cov_pix[__popc(cov & lt_mask)] = (uint8_t)lane;
-            it_s0 = (uint32_t)chunk * kItemSpp;
-            const uint32_t ns = fp.spp - it_s0 < kItemSpp ? fp.spp - it_s0 : kItemSpp;
+            it_s0 = (uint32_t)chunk * item_spp;
+            const uint32_t ns = fp.spp - it_s0 < item_spp ? fp.spp - it_s0 : item_spp;
             it_njobs = it_ncov * ns;
             it_next = 0;
             if (it_ncov == 0) it_ncov = 1; // (no jobs; keeps the division below defined)

@@ -71,9 +71,10 @@ struct State {
     unsigned long long* d_accum_own = nullptr; // the library's allocation
     // fused cross-GPU accumulation (vt_fused_reduce_*): 0 off, 1 root (owns the double buffer), 2 peer (maps it)
     int fused_mode = 0;
-    unsigned long long* fused_base = nullptr; // two accumulation buffers back to back
-    size_t fused_stride = 0;                  // elements per buffer
-    uint32_t fused_index = 0;
+    uint4* fused_base = nullptr;     // root memory: [2 buffers][world ranks][pixels][2] partial sums (32 B per pixel)
+    size_t fused_pixels = 0;         // pixels per slot
+    uint32_t fused_index = 0, fused_rank = 0, fused_world = 1;
+    unsigned long long* fused_sum = nullptr; // root, on demand: materialised sums for vt_read_accum
     unsigned long long* d_stats = nullptr;
     unsigned long long* h_stats = nullptr; // pinned
     void* h_readback = nullptr;            // pinned staging for vt_read_*
@@ -262,8 +263,8 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
     if (g.fused_mode && g.cfg.mode == VT_MODE_PATHS) {
         if (g.inst_count != 1 || (g.cfg.flags & (VT_FLAG_PERSISTENT_LANES | VT_FLAG_PER_PIXEL_PATHS)))
             return fail("fused cross-GPU accumulation needs the single-instance wavefront kernel");
-        if (g.fused_stride != (size_t)g.cfg.width * g.cfg.height * 3) return fail("fused accumulation buffer does not match the framebuffer size");
-        fp.sky_spp = g.fused_mode == 1 ? (g.cfg.total_spp ? g.cfg.total_spp : g.cfg.spp) : 0u;
+        if (g.fused_pixels != (size_t)g.cfg.width * g.cfg.height) return fail("fused accumulation buffer does not match the framebuffer size");
+        fp.sky_spp = 0u; // pixels outside the screen rectangle are resolved analytically on the root
     }
     if (g.cfg.mode == VT_MODE_PATHS && g.any_bricks) return fail("path tracing over procedural brick volumes is not implemented");
 
@@ -326,7 +327,8 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
     fb.records = (g.cfg.flags & VT_FLAG_NO_HIT_RECORDS) ? nullptr : g.d_rec;
     fb.color = g.d_color;
     fb.depth = g.d_depth;
-    fb.accum = (g.fused_mode && g.cfg.mode == VT_MODE_PATHS) ? g.fused_base + g.fused_index * g.fused_stride : g.d_accum;
+    const bool fused = g.fused_mode && g.cfg.mode == VT_MODE_PATHS;
+    fb.accum = fused ? g.d_accum_own : g.d_accum;
     fb.stats = g.d_stats;
     SrgbTables lut{g.d_dec, g.d_thr};
 
@@ -348,7 +350,12 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
         CK(launch_trace_paths(fp, g.d_iu, bins, g.d_arena, g.arena_words, in_smem, lut, fb, g.sm_count, g.stream));
         CK(cudaEventRecord(g.ev_trace1, g.stream));
         g.stats.launches += 1;
-        if (resolve) {
+        if (fused) { // stream this rank's sums of the covered rectangle into its slot in the root's memory
+            uint4* slot = g.fused_base + ((size_t)g.fused_index * g.fused_world + g.fused_rank) * g.fused_pixels * 2;
+            CK(launch_push_partial(g.d_iu, g.d_accum_own, slot, g.cfg.width, g.cfg.height, g.stream));
+            g.stats.launches += 1;
+        }
+        if (resolve && !fused) {
             const uint32_t total = g.cfg.total_spp ? g.cfg.total_spp : g.cfg.spp;
             CK(launch_resolve(g.d_accum, g.cfg.width * g.cfg.height, total ? total : 1, lut, g.d_color, g.stream));
             g.stats.launches += 1;
@@ -704,8 +711,17 @@ extern "C" int64_t vt_read_depth(float* depth, size_t capacity) {
     return read_back(g.d_depth, (size_t)g.cfg.width * g.cfg.height * 4, depth, capacity);
 }
 extern "C" int64_t vt_read_accum(uint64_t* accum, size_t capacity) {
-    const unsigned long long* src = g.fused_mode == 1 ? g.fused_base + g.fused_index * g.fused_stride : g.d_accum;
-    return read_back(src, (size_t)g.cfg.width * g.cfg.height * 24, accum, capacity);
+    if (g.inited && g.fused_mode == 1) { // materialise the sum of all ranks' partial sums
+        if (cudaSetDevice(g.device) != cudaSuccess) return -1;
+        if (!g.fused_sum && cudaMalloc(&g.fused_sum, g.fused_pixels * 24) != cudaSuccess) return fail("vt_read_accum: out of memory");
+        const uint32_t total = g.cfg.total_spp ? g.cfg.total_spp : g.cfg.spp;
+        SrgbTables lut{g.d_dec, g.d_thr};
+        const uint4* partials = g.fused_base + (size_t)g.fused_index * g.fused_world * g.fused_pixels * 2;
+        if (launch_resolve_partials(g.d_iu, partials, g.fused_world, g.cfg.width, g.cfg.height, total ? total : 1, lut, g.d_color, g.fused_sum,
+                                    g.stream) != cudaSuccess) return fail("vt_read_accum: resolve failed");
+        return read_back(g.fused_sum, g.fused_pixels * 24, accum, capacity);
+    }
+    return read_back(g.d_accum, (size_t)g.cfg.width * g.cfg.height * 24, accum, capacity);
 }
 
 extern "C" void* vt_accum_device_ptr(void) { return g.inited ? (void*)g.d_accum : nullptr; }
@@ -732,45 +748,59 @@ extern "C" int32_t vt_resolve(void) {
     const uint32_t total = g.cfg.total_spp ? g.cfg.total_spp : g.cfg.spp;
     SrgbTables lut{g.d_dec, g.d_thr};
     if (g.fused_mode == 2) return fail("vt_resolve: only the root of a fused reduction holds the sums");
-    unsigned long long* src = g.fused_mode == 1 ? g.fused_base + g.fused_index * g.fused_stride : g.d_accum;
-    CK(launch_resolve(src, g.cfg.width * g.cfg.height, total ? total : 1, lut, g.d_color, g.stream));
+    if (g.fused_mode == 1) {
+        const uint4* partials = g.fused_base + (size_t)g.fused_index * g.fused_world * g.fused_pixels * 2;
+        CK(launch_resolve_partials(g.d_iu, partials, g.fused_world, g.cfg.width, g.cfg.height, total ? total : 1, lut, g.d_color, nullptr,
+                                   g.stream));
+    } else {
+        CK(launch_resolve(g.d_accum, g.cfg.width * g.cfg.height, total ? total : 1, lut, g.d_color, g.stream));
+    }
     g.stats.launches += 1;
-    // fused: the buffer is next written two frames from now; clear it behind the resolve
-    if (g.fused_mode == 1) CK(cudaMemsetAsync(src, 0, g.fused_stride * sizeof(unsigned long long), g.stream));
     return 0;
 }
 
 // ---- fused cross-GPU accumulation over NVLink peer memory (one process per GPU, one node) -----------
-extern "C" int32_t vt_fused_reduce_export(uint8_t handle[64]) {
+static int fused_common(uint32_t rank, uint32_t world) {
+    if (world < 1 || rank >= world) return fail("fused reduction: bad rank %u of %u", rank, world);
+    g.fused_pixels = (size_t)g.cfg.width * g.cfg.height;
+    g.fused_rank = rank;
+    g.fused_world = world;
+    g.fused_index = 0;
+    // the local accumulators must start (and, thanks to push_partial, stay) clear
+    CK(cudaMemsetAsync(g.d_accum_own, 0, g.fused_pixels * 3 * sizeof(unsigned long long), g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+extern "C" int32_t vt_fused_reduce_export(uint8_t handle[64], uint32_t world) {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
     if (!g.inited || !handle) return -1;
     CK(cudaSetDevice(g.device));
     if (finish_frame()) return -1;
     if (g.fused_mode) return fail("fused reduction already set up");
-    const size_t stride = (size_t)g.cfg.width * g.cfg.height * 3;
-    CK(cudaMalloc(&g.fused_base, 2 * stride * sizeof(unsigned long long)));
-    CK(cudaMemset(g.fused_base, 0, 2 * stride * sizeof(unsigned long long)));
+    if (fused_common(0, world)) return -1;
+    const size_t bytes = 2 * (size_t)world * g.fused_pixels * 2 * sizeof(uint4);
+    CK(cudaMalloc(&g.fused_base, bytes));
+    CK(cudaMemset(g.fused_base, 0, bytes));
     cudaIpcMemHandle_t h;
     CK(cudaIpcGetMemHandle(&h, g.fused_base));
     memcpy(handle, &h, 64);
-    g.fused_stride = stride;
-    g.fused_index = 0;
     g.fused_mode = 1;
     return 0;
 }
 
-extern "C" int32_t vt_fused_reduce_import(const uint8_t handle[64]) {
+extern "C" int32_t vt_fused_reduce_import(const uint8_t handle[64], uint32_t rank, uint32_t world) {
     if (!g.inited || !handle) return -1;
     CK(cudaSetDevice(g.device));
     if (finish_frame()) return -1;
     if (g.fused_mode) return fail("fused reduction already set up");
+    if (rank == 0) return fail("vt_fused_reduce_import: rank 0 is the root (it exports)");
+    if (fused_common(rank, world)) return -1;
     cudaIpcMemHandle_t h;
     memcpy(&h, handle, 64);
     void* p = nullptr;
     CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-    g.fused_base = (unsigned long long*)p;
-    g.fused_stride = (size_t)g.cfg.width * g.cfg.height * 3;
-    g.fused_index = 0;
+    g.fused_base = (uint4*)p;
     g.fused_mode = 2;
     return 0;
 }
@@ -788,6 +818,8 @@ extern "C" int32_t vt_fused_reduce_disable(void) {
     CK(cudaStreamSynchronize(g.stream));
     if (g.fused_mode == 1) cudaFree(g.fused_base);
     if (g.fused_mode == 2) cudaIpcCloseMemHandle(g.fused_base);
+    cudaFree(g.fused_sum);
+    g.fused_sum = nullptr;
     g.fused_base = nullptr;
     g.fused_mode = 0;
     return 0;

@@ -31,17 +31,20 @@ def reduce_accum(accum, group=None):
 
 def setup_fused_reduce(renderer, rank: int, world: int, device, root: int = 0):
     """Wires the library's fused cross-GPU accumulation: the root exports the CUDA IPC handle of its
-    accumulation buffers, torch.distributed broadcasts the 64 bytes, every other rank maps them.  After
-    this, each rank's trace kernel adds its radiance straight into the root's memory over NVLink."""
+    partial-sum buffer, torch.distributed broadcasts the 64 bytes, every other rank maps it.  After
+    this, each rank streams its sums of the covered rectangle straight into the root's memory over
+    NVLink and the root's resolve adds the slots up; no all-reduce of the accumulators."""
+    if root != 0:
+        raise ValueError("the library's fused reduction uses rank 0 as the root")
     import torch
     import torch.distributed as dist
 
     handle = torch.zeros(64, dtype=torch.uint8, device=device)
     if rank == root:
-        handle.copy_(torch.frombuffer(bytearray(renderer.fused_reduce_export()), dtype=torch.uint8))
+        handle.copy_(torch.frombuffer(bytearray(renderer.fused_reduce_export(world)), dtype=torch.uint8))
     dist.broadcast(handle, src=root)
     if rank != root:
-        renderer.fused_reduce_import(bytes(handle.cpu().numpy().tobytes()))
+        renderer.fused_reduce_import(bytes(handle.cpu().numpy().tobytes()), rank, world)
     dist.barrier()
 
 

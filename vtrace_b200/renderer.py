@@ -205,15 +205,15 @@ class Renderer:
         if self._lib.vt_set_stream(C.c_void_p(cuda_stream_handle or 0)) != 0:
             raise RuntimeError("vt_set_stream failed: " + abi.last_error())
 
-    def fused_reduce_export(self) -> bytes:
+    def fused_reduce_export(self, world: int) -> bytes:
         buf = (C.c_uint8 * 64)()
-        if self._lib.vt_fused_reduce_export(buf) != 0:
+        if self._lib.vt_fused_reduce_export(buf, world) != 0:
             raise RuntimeError("vt_fused_reduce_export failed: " + abi.last_error())
         return bytes(buf)
 
-    def fused_reduce_import(self, handle: bytes):
+    def fused_reduce_import(self, handle: bytes, rank: int, world: int):
         buf = (C.c_uint8 * 64).from_buffer_copy(handle)
-        if self._lib.vt_fused_reduce_import(buf) != 0:
+        if self._lib.vt_fused_reduce_import(buf, rank, world) != 0:
             raise RuntimeError("vt_fused_reduce_import failed: " + abi.last_error())
 
     def fused_reduce_next_frame(self):
