@@ -142,6 +142,8 @@ typedef struct vt_stats {
     float last_trace_ms;      /* last frame: device time of the trace kernel (CUDA events)        */
     float last_frame_ms;      /* last frame: device time of everything render_tick enqueued       */
     uint32_t masks_in_smem;   /* 1 when the traversal masks were staged in shared memory          */
+    uint32_t trace_frames;    /* frames folded into trace_ms_sum since the previous vt_get_stats  */
+    float trace_ms_sum;       /* sum of the trace kernel's device time over those frames          */
     uint32_t reserved;
 } vt_stats;
 
@@ -151,7 +153,8 @@ int32_t vt_get_config(vt_config* out);
 int32_t vt_configure(const vt_config* cfg);
 
 /* Enqueue one frame without host synchronisation or read-back (device-resident measurement);
- * projection / camera as in render_tick_info.  0 = ok. */
+ * projection / camera as in render_tick_info.  Up to 64 frames may be in flight; their counters and
+ * kernel timings are folded into vt_stats at the next synchronising call.  0 = ok. */
 int32_t vt_render_async(const float* projection, const float* camera);
 /* Block until everything enqueued so far has finished.  0 = ok. */
 int32_t vt_synchronize(void);

@@ -58,7 +58,7 @@ def test_struct_layouts_match_the_rust_side():
     assert abi.UserInput.mouse_x.offset == 8 and abi.UserInput.last_mouse_y.offset == 32
     assert C.sizeof(abi.RenderTickInfo) == 2 * C.sizeof(C.c_void_p)  # src/render.rs:177-181
     assert abi.HIT_DTYPE.itemsize == 16
-    assert C.sizeof(abi.VtConfig) == 48 and C.sizeof(abi.VtStats) == 48
+    assert C.sizeof(abi.VtConfig) == 48 and C.sizeof(abi.VtStats) == 56
 
 
 def test_sass_is_sm100a_with_tma_bulk_copy():

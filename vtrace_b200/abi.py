@@ -39,7 +39,7 @@ class VtConfig(C.Structure):
 class VtStats(C.Structure):
     _fields_ = [("frames", C.c_uint64), ("rays", C.c_uint64), ("iterations", C.c_uint64), ("launches", C.c_uint64),
                 ("last_trace_ms", C.c_float), ("last_frame_ms", C.c_float), ("masks_in_smem", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("trace_frames", C.c_uint32), ("trace_ms_sum", C.c_float), ("reserved", C.c_uint32)]
 
 
 # every symbol include/vtrace_abi.h declares: name -> (restype, argtypes)

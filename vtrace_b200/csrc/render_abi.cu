@@ -76,11 +76,15 @@ struct State {
     uint32_t fused_index = 0, fused_rank = 0, fused_world = 1;
     unsigned long long* fused_sum = nullptr; // root, on demand: materialised sums for vt_read_accum
     unsigned long long* d_stats = nullptr;
-    unsigned long long* h_stats = nullptr; // pinned
+    unsigned long long* h_stats = nullptr; // pinned: kRing slots of 2 counters
     void* h_readback = nullptr;            // pinned staging for vt_read_*
     size_t readback_size = 0;
 
-    cudaEvent_t ev_begin = nullptr, ev_trace0 = nullptr, ev_trace1 = nullptr, ev_end = nullptr;
+    // Frames can be enqueued back to back without a host synchronisation (vt_render_async); their
+    // timing events and counters live in a ring and are folded into `stats` at the next synchronisation.
+    static constexpr uint32_t kRing = 64;
+    cudaEvent_t ev_begin[kRing] = {}, ev_trace0[kRing] = {}, ev_trace1[kRing] = {}, ev_end[kRing] = {};
+    uint64_t ring_head = 0, ring_done = 0; // frames enqueued / frames folded into stats
     bool frame_pending = false;
     uint32_t refill_threshold = 16; // tuning knob of the wavefront / persistent-lane kernels (VT_REFILL)
 
@@ -207,15 +211,23 @@ int finish_frame() {
         CK(cudaStreamSynchronize(g.stream));
         g.frame_pending = false;
     }
-    float ms = 0.0f;
-    if (cudaEventElapsedTime(&ms, g.ev_trace0, g.ev_trace1) == cudaSuccess) g.stats.last_trace_ms = ms;
-    if (cudaEventElapsedTime(&ms, g.ev_begin, g.ev_end) == cudaSuccess) g.stats.last_frame_ms = ms;
-    if (g.cfg.mode == VT_MODE_PRIMARY || g.cfg.mode == VT_MODE_RAYS) {
-        g.stats.rays = (uint64_t)g.cfg.width * g.cfg.height + g.h_stats[0]; // + shadow rays
-        g.stats.iterations = g.h_stats[1];
-    } else {
-        g.stats.rays = g.h_stats[0];
-        g.stats.iterations = g.h_stats[1];
+    for (; g.ring_done < g.ring_head; ++g.ring_done) {
+        const uint32_t slot = (uint32_t)(g.ring_done % State::kRing);
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, g.ev_trace0[slot], g.ev_trace1[slot]) == cudaSuccess) {
+            g.stats.last_trace_ms = ms;
+            g.stats.trace_ms_sum += ms;
+            g.stats.trace_frames += 1;
+        }
+        if (cudaEventElapsedTime(&ms, g.ev_begin[slot], g.ev_end[slot]) == cudaSuccess) g.stats.last_frame_ms = ms;
+        const unsigned long long* hs = g.h_stats + 2 * slot;
+        if (g.cfg.mode == VT_MODE_PRIMARY || g.cfg.mode == VT_MODE_RAYS) {
+            g.stats.rays = (uint64_t)g.cfg.width * g.cfg.height + hs[0]; // + shadow rays
+            g.stats.iterations = hs[1];
+        } else {
+            g.stats.rays = hs[0];
+            g.stats.iterations = hs[1];
+        }
     }
     return 0;
 }
@@ -224,7 +236,10 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
     if (!g.inited) return fail("render before entry()");
     CK(cudaSetDevice(g.device));
     if (alloc_framebuffer()) return -1;
-    if (g.frame_pending && finish_frame()) return -1;
+    // A frame that used the instance bins must be checked for list overflow before the next one; otherwise
+    // frames may queue up (their events/counters live in a ring of kRing slots).
+    if (g.frame_pending && (g.bins_used || g.ring_head - g.ring_done >= State::kRing) && finish_frame()) return -1;
+    const uint32_t slot = (uint32_t)(g.ring_head % State::kRing);
 
     FrameParams fp{};
     float Pi[16], Vi[16], Vc[16], Vci[16];
@@ -286,7 +301,7 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
     g.last_clear = clear_accum;
     g.last_resolve = resolve;
 
-    CK(cudaEventRecord(g.ev_begin, g.stream));
+    CK(cudaEventRecord(g.ev_begin[slot], g.stream));
     CK(cudaMemsetAsync(g.d_stats, 0, 4 * sizeof(unsigned long long), g.stream));
     CK(launch_instance_setup(g.d_inst, g.inst_count, g.d_vols, fp, g.d_iu, g.stream));
     g.stats.launches += 1;
@@ -334,21 +349,21 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
 
     if (g.cfg.mode == VT_MODE_RAYS) {
         const unsigned long long n = (unsigned long long)g.cfg.width * g.cfg.height;
-        CK(cudaEventRecord(g.ev_trace0, g.stream));
+        CK(cudaEventRecord(g.ev_trace0[slot], g.stream));
         CK(launch_trace_rays(fp, g.d_iu, g.d_arena, n, (unsigned long long)g.cfg.sample_first * n, fb, g.sm_count, g.stream));
-        CK(cudaEventRecord(g.ev_trace1, g.stream));
+        CK(cudaEventRecord(g.ev_trace1[slot], g.stream));
         g.stats.launches += 1;
     } else if (g.cfg.mode == VT_MODE_PRIMARY) {
-        CK(cudaEventRecord(g.ev_trace0, g.stream));
+        CK(cudaEventRecord(g.ev_trace0[slot], g.stream));
         CK(launch_trace_primary(fp, g.d_iu, bins, g.d_arena, g.arena_words, in_smem, lut, fb, g.sm_count, g.stream));
-        CK(cudaEventRecord(g.ev_trace1, g.stream));
+        CK(cudaEventRecord(g.ev_trace1[slot], g.stream));
         g.stats.launches += 1;
     } else {
         if (clear_accum)
             CK(cudaMemsetAsync(g.d_accum, 0, (size_t)g.cfg.width * g.cfg.height * 3 * sizeof(unsigned long long), g.stream));
-        CK(cudaEventRecord(g.ev_trace0, g.stream));
+        CK(cudaEventRecord(g.ev_trace0[slot], g.stream));
         CK(launch_trace_paths(fp, g.d_iu, bins, g.d_arena, g.arena_words, in_smem, lut, fb, g.sm_count, g.stream));
-        CK(cudaEventRecord(g.ev_trace1, g.stream));
+        CK(cudaEventRecord(g.ev_trace1[slot], g.stream));
         g.stats.launches += 1;
         if (fused) { // stream this rank's sums of the covered rectangle into its slot in the root's memory
             uint4* slot = g.fused_base + ((size_t)g.fused_index * g.fused_world + g.fused_rank) * g.fused_pixels * 2;
@@ -361,8 +376,9 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
             g.stats.launches += 1;
         }
     }
-    CK(cudaMemcpyAsync(g.h_stats, g.d_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g.stream));
-    CK(cudaEventRecord(g.ev_end, g.stream));
+    CK(cudaMemcpyAsync(g.h_stats + 2 * slot, g.d_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaEventRecord(g.ev_end[slot], g.stream));
+    g.ring_head += 1;
     g.frame_pending = true;
     g.stats.frames += 1;
     return 0;
@@ -415,10 +431,12 @@ extern "C" uint64_t entry(void) {
     g.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     CKE(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
     g.stream = g.own_stream;
-    CKE(cudaEventCreate(&g.ev_begin));
-    CKE(cudaEventCreate(&g.ev_trace0));
-    CKE(cudaEventCreate(&g.ev_trace1));
-    CKE(cudaEventCreate(&g.ev_end));
+    for (uint32_t k = 0; k < State::kRing; ++k) {
+        CKE(cudaEventCreate(&g.ev_begin[k]));
+        CKE(cudaEventCreate(&g.ev_trace0[k]));
+        CKE(cudaEventCreate(&g.ev_trace1[k]));
+        CKE(cudaEventCreate(&g.ev_end[k]));
+    }
     CKE(configure_kernels(g.max_smem_optin));
 
     // sRGB tables (VK_FORMAT_R8G8B8A8_SRGB textures, lib/memory.c:317; B8G8R8A8_SRGB target, lib/swapchain.c:88)
@@ -435,8 +453,8 @@ extern "C" uint64_t entry(void) {
     CKE(cudaMalloc(&g.d_bin_cursor, 4));
     CKE(cudaMallocHost(&g.h_bin_cursor, 4));
     *g.h_bin_cursor = 0;
-    CKE(cudaMallocHost(&g.h_stats, 2 * sizeof(unsigned long long)));
-    g.h_stats[0] = g.h_stats[1] = 0;
+    CKE(cudaMallocHost(&g.h_stats, 2 * State::kRing * sizeof(unsigned long long)));
+    memset(g.h_stats, 0, 2 * State::kRing * sizeof(unsigned long long));
 
     // defaults: the reference's fixed 1000x1000 window (lib/entry.c:62), overridable from the
     // environment so the unmodified Rust engine can be configured without new calls
@@ -655,7 +673,9 @@ extern "C" void cleanup(void) {
     if (g.h_tex_staging) cudaFreeHost(g.h_tex_staging);
     if (g.h_stats) cudaFreeHost(g.h_stats);
     if (g.h_readback) cudaFreeHost(g.h_readback);
-    cudaEventDestroy(g.ev_begin); cudaEventDestroy(g.ev_trace0); cudaEventDestroy(g.ev_trace1); cudaEventDestroy(g.ev_end);
+    for (uint32_t k = 0; k < State::kRing; ++k) {
+        cudaEventDestroy(g.ev_begin[k]); cudaEventDestroy(g.ev_trace0[k]); cudaEventDestroy(g.ev_trace1[k]); cudaEventDestroy(g.ev_end[k]);
+    }
     if (g.own_stream) cudaStreamDestroy(g.own_stream);
     const user_input keep = g.input;
     g = State{};
@@ -836,7 +856,12 @@ extern "C" int32_t vt_set_stream(void* cuda_stream) {
 
 extern "C" int32_t vt_get_stats(vt_stats* out) {
     if (!g.inited || !out) return -1;
+    if (g.frame_pending) {
+        if (cudaSetDevice(g.device) != cudaSuccess || finish_frame()) return -1;
+    }
     *out = g.stats;
+    g.stats.trace_ms_sum = 0.0f; // the sums cover the frames since the previous call
+    g.stats.trace_frames = 0;
     return 0;
 }
 
