@@ -659,14 +659,19 @@ static inline uint32_t vo_mix(uint32_t x) {
     return x;
 }
 typedef struct { uint32_t key, ctr; } vo_rng;
+/* counter-based stream keyed by (seed, pixel, sample): draw k is mix(key + k * phi) */
 static inline void rng_init(vo_rng* r, uint32_t seed, uint32_t pixel, uint32_t sample) {
-    uint32_t k = vo_mix(seed ^ vo_mix(pixel * 0x9E3779B9u + 0x85EBCA6Bu));
-    r->key = vo_mix(k ^ vo_mix(sample + 0xC2B2AE35u));
+    uint32_t k = vo_mix(seed + pixel * 0x9E3779B9u);
+    r->key = vo_mix(k ^ (sample * 0x85EBCA6Bu + 0xC2B2AE35u));
     r->ctr = 0;
 }
+/* uniform in [0,1) with 23 random mantissa bits: as_float(0x3f800000 | bits) - 1 (no int->float conversion) */
 static inline float rng_u01(vo_rng* r) {
     uint32_t x = vo_mix(r->key + (r->ctr++) * 0x9E3779B9u);
-    return (float)(x >> 8) * (1.0f / 16777216.0f);
+    uint32_t u = 0x3f800000u | (x >> 9);
+    float f;
+    memcpy(&f, &u, 4);
+    return f - 1.0f;
 }
 
 /* uniform point on the unit sphere, Marsaglia (1972): only + - * sqrt, so it is bit-reproducible */

@@ -829,14 +829,16 @@ __device__ __forceinline__ uint32_t vt_mix(uint32_t x) {
     return x;
 }
 struct Rng { uint32_t key, ctr; };
+// counter-based stream keyed by (seed, pixel, sample): draw k is mix(key + k * phi)
 __device__ __forceinline__ void rng_init(Rng& r, uint32_t seed, uint32_t pixel, uint32_t sample) {
-    const uint32_t k = vt_mix(seed ^ vt_mix(pixel * 0x9E3779B9u + 0x85EBCA6Bu));
-    r.key = vt_mix(k ^ vt_mix(sample + 0xC2B2AE35u));
+    const uint32_t k = vt_mix(seed + pixel * 0x9E3779B9u);
+    r.key = vt_mix(k ^ (sample * 0x85EBCA6Bu + 0xC2B2AE35u));
     r.ctr = 0;
 }
+// uniform in [0,1) with 23 random mantissa bits: as_float(0x3f800000 | bits) - 1 (no int->float conversion)
 __device__ __forceinline__ float rng_u01(Rng& r) {
     const uint32_t x = vt_mix(r.key + (r.ctr++) * 0x9E3779B9u);
-    return (float)(x >> 8) * (1.0f / 16777216.0f);
+    return __uint_as_float(0x3f800000u | (x >> 9)) - 1.0f;
 }
 __device__ __forceinline__ void rng_sphere(Rng& r, float s[3]) {
     float a = 0.0f, b = 0.0f, q = 0.0f;

@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
     for (int g = 0; g < kSlotGroups; ++g) ray[(lane + 32 * g) * 3 + 2] = make_uint4(0u, 0u, kFree, 0u);
     wacc[lane * 3 + 0] = 0u; wacc[lane * 3 + 1] = 0u; wacc[lane * 3 + 2] = 0u;
     __syncwarp();
-    int n_free = kSlots, n_ready = 0, n_hit = 0;
+    int n_free = kSlots, n_ready = 0, n_hit = 0, n_done = 0; // n_done: rays that stopped in the last march, not yet classified
 
     // current work item (warp-uniform)
     bool work_left = true;
@@ -221,6 +221,8 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
 
     for (;;) {
         // ---- classify: owners decode the rays that stopped -------------------------------------
+        if (n_done) {
+        n_done = 0;
 #pragma unroll
         for (int g = 0; g < kSlotGroups; ++g) {
             const uint32_t slot = lane + 32 * g;
@@ -246,6 +248,7 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
             n_free += __popc(__ballot_sync(0xffffffffu, done && !hit));
         }
         __syncwarp();
+        }
 
         // ---- make sure there is a work item with jobs (or learn that the frame is exhausted) ------
         while (work_left && it_next >= it_njobs) {
@@ -463,7 +466,9 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
                     my_slot = -1;
                     idx = 0;
                 }
-                idle_mask = __ballot_sync(0xffffffffu, my_slot < 0);
+                const uint32_t now_idle = __ballot_sync(0xffffffffu, my_slot < 0);
+                n_done += __popc(now_idle & ~idle_mask);
+                idle_mask = now_idle;
             }
             __syncwarp();
         }
