@@ -211,7 +211,8 @@ def run_cuda(args):
         accum = torch.zeros((HEIGHT, WIDTH, 3), dtype=torch.int64, device=dev)  # 2^-24 fixed-point radiance sums
         r.set_accum_buffer(accum.data_ptr())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    frame_host = np.empty((HEIGHT, WIDTH, 4), dtype=np.uint8)
+    frame_pinned = torch.empty((HEIGHT, WIDTH, 4), dtype=torch.uint8, pin_memory=True)  # the host-side frame buffer
+    frame_host = frame_pinned.numpy()
     lib = abi.load()
 
     def trace_and_reduce():

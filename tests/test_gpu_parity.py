@@ -391,6 +391,21 @@ def test_paths_axis_aligned_and_inside(scene, assets):
     scene.check_paths(P, V, 160, 120, spp=2, what="paths camera inside")
 
 
+def test_paths_degenerate_scenes(scene, assets):
+    """No instance, an out-of-range texture id, zero bounces, one sample: every path kernel must agree with the oracle."""
+    P, V = scenes.camera(96, 64)
+    scene.set_instances([])
+    scene.check_paths(P, V, 96, 64, spp=2, what="paths, empty scene")
+    scene.set_instances([(glm.identity(), 40000)])
+    scene.check_paths(P, V, 96, 64, spp=2, what="paths, bad texture id")
+    t = scene.add(assets["Treasure"])
+    scene.set_instances([(glm.identity(), t)])
+    P, V = scenes.camera(96, 64, eye=(0.9, -0.5, 0.7))
+    for flags in (0, abi.FLAG_PER_PIXEL_PATHS, abi.FLAG_PERSISTENT_LANES):
+        scene.check_paths(P, V, 96, 64, spp=1, bounces=0, flags=flags, what=f"paths, 0 bounces, flags {flags}")
+        scene.check_paths(P, V, 97, 63, spp=3, bounces=1, flags=flags, what=f"paths, odd size, flags {flags}")
+
+
 def test_paths_multi_instance_exact(scene, assets):
     a = scene.add(assets["Treasure"])
     b = scene.add(assets["AncientTemple"])

@@ -729,10 +729,9 @@ __global__ void __launch_bounds__(kBlockThreads) trace_primary_kernel(const __gr
     const int lane = threadIdx.x & 31;
     const int lx = lane & 7, ly = lane >> 3;
 
-    // clear values, lib/command.c:56-61, as stored by the sRGB target
-    const uint32_t clear_r = srgb_encode(lut.threshold, 53.0f / 100.0f);
-    const uint32_t clear_g = srgb_encode(lut.threshold, 81.0f / 100.0f);
-    const uint32_t clear_b = srgb_encode(lut.threshold, 92.0f / 100.0f);
+    // clear values, lib/command.c:56-61, as stored by the sRGB target (encoded once on the host)
+    const uint32_t clear_r = fp.clear_rgba & 255u, clear_g = (fp.clear_rgba >> 8) & 255u, clear_b = (fp.clear_rgba >> 16) & 255u;
+    const uint32_t tiles_x_magic = 0xFFFFFFFFu / (uint32_t)tiles_x + 1u; // tile / tiles_x == umulhi(tile, magic) for these sizes
 
     unsigned long long iter_sum = 0, shadow_rays = 0;
     // Primary rays are cheap (tens of microseconds for the whole frame), so tiles are dealt
@@ -741,8 +740,9 @@ __global__ void __launch_bounds__(kBlockThreads) trace_primary_kernel(const __gr
     const int n_warps = gridDim.x * (kBlockThreads / 32);
     {
         for (int tile = blockIdx.x * (kBlockThreads / 32) + (threadIdx.x >> 5); tile < n_tiles; tile += n_warps) {
-            const int px = (tile % tiles_x) * kTileW + lx;
-            const int py = (tile / tiles_x) * kTileH + ly;
+            const int tile_y = (int)__umulhi((uint32_t)tile, tiles_x_magic), tile_x = tile - tile_y * tiles_x;
+            const int px = tile_x * kTileW + lx;
+            const int py = tile_y * kTileH + ly;
             if (px >= fp.width || py >= fp.height) continue;
             const float fx = (float)px + 0.5f, fy = (float)py + 0.5f;
             uint32_t dst[4] = {clear_r, clear_g, clear_b, 255u};

@@ -59,6 +59,7 @@ struct State {
     bool last_clear = false, last_resolve = false;
 
     // tables
+    uint32_t clear_rgba = 0;
     float* d_dec = nullptr;
     float* d_thr = nullptr;
 
@@ -274,6 +275,7 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
         fp.sun[0] = sx / l; fp.sun[1] = sy / l; fp.sun[2] = sz / l;
     }
     fp.any_bricks = g.any_bricks ? 1u : 0u;
+    fp.clear_rgba = g.clear_rgba;
     fp.sky_spp = g.cfg.spp;
     if (g.fused_mode && g.cfg.mode == VT_MODE_PATHS) {
         if (g.inst_count != 1 || (g.cfg.flags & (VT_FLAG_PERSISTENT_LANES | VT_FLAG_PER_PIXEL_PATHS)))
@@ -388,11 +390,17 @@ int64_t read_back(const void* d_src, size_t bytes, void* out, size_t capacity) {
     if (!g.inited) return fail("read before entry()");
     if (!out || capacity < bytes) return fail("read-back buffer too small: need %zu bytes, have %zu", bytes, capacity);
     if (cudaSetDevice(g.device) != cudaSuccess) return fail("cudaSetDevice failed");
-    if (ensure_readback(bytes)) return -1;
-    if (cudaMemcpyAsync(g.h_readback, d_src, bytes, cudaMemcpyDeviceToHost, g.stream) != cudaSuccess) return fail("read-back copy failed");
+    // a page-locked destination (cudaHostAlloc / cudaHostRegister / a pinned torch tensor) is written by the
+    // copy engine directly; pageable memory goes through the library's pinned staging buffer
+    cudaPointerAttributes attr{};
+    const bool pinned = cudaPointerGetAttributes(&attr, out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    if (!pinned) (void)cudaGetLastError();
+    if (!pinned && ensure_readback(bytes)) return -1;
+    void* dst = pinned ? out : g.h_readback;
+    if (cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, g.stream) != cudaSuccess) return fail("read-back copy failed");
     if (finish_frame()) return -1;
     if (cudaStreamSynchronize(g.stream) != cudaSuccess) return fail("read-back sync failed");
-    memcpy(out, g.h_readback, bytes);
+    if (!pinned) memcpy(out, g.h_readback, bytes);
     return (int64_t)bytes;
 }
 
@@ -444,6 +452,16 @@ extern "C" uint64_t entry(void) {
     for (int k = 0; k < 256; ++k) {
         dec[k] = (float)srgb_to_linear((double)k / 255.0);
         thr[k] = k == 0 ? 0.0f : (float)srgb_to_linear(((double)k - 0.5) / 255.0);
+    }
+    {   // clear values (lib/command.c:56-61) pushed through the sRGB target's encoding once, here
+        const float clear[3] = {53.0f / 100.0f, 81.0f / 100.0f, 92.0f / 100.0f};
+        g.clear_rgba = 255u << 24;
+        for (int c = 0; c < 3; ++c) {
+            uint32_t k = 0;
+            for (uint32_t bit = 128; bit; bit >>= 1)
+                if (clear[c] >= thr[k | bit]) k |= bit;
+            g.clear_rgba |= k << (8 * c);
+        }
     }
     CKE(cudaMalloc(&g.d_dec, sizeof dec));
     CKE(cudaMalloc(&g.d_thr, sizeof thr));
