@@ -62,7 +62,8 @@ struct FrameParams {
     uint32_t flags;
     // path-tracing extension
     uint32_t spp, bounces, seed, sample_first, sample_stride;
-    uint32_t refill_threshold; // persistent-lane kernel: refill when fewer lanes than this still march
+    uint32_t refill_threshold; // wavefront / persistent-lane kernels: park the walkers when fewer than this many are left
+    uint32_t refill_batch;     // wavefront kernel: hand out new rays once this many lanes have stopped
     float sun[3];              // unit vector towards the sun, world space (shadow-ray extension)
     uint32_t any_bricks;       // the scene contains a procedural brick volume
     uint32_t clear_rgba;       // clear colour (lib/command.c:56-61) as stored by the sRGB target: r | g<<8 | b<<16 | a<<24

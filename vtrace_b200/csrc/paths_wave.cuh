@@ -454,12 +454,17 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
                     n_ready = nact;
                     break;
                 }
-                // step until some lane stops (checked every 4 steps); idle lanes sit on a stop bit
+                // Step (4 iterations between checks; idle lanes sit on a stop bit) until it pays to look at the
+                // stopped lanes: while READY rays remain, once `refill_batch` lanes can be refilled together;
+                // afterwards, once fewer than `thresh` lanes are left and the rest gets parked.
                 bool walking;
+                int nwalk;
+                const bool can_refill = rc < total;
                 do {
 #pragma unroll
                     for (int u = 0; u < 4; ++u) walking = dda_step<kSmem>(vol, sx, sy, sz, dx, dy, dz, idx, prev, steps, ix, iy, iz);
-                } while (__ballot_sync(0xffffffffu, walking) == ~idle_mask);
+                    nwalk = __popc(__ballot_sync(0xffffffffu, walking));
+                } while (nwalk > 0 && (can_refill ? (nact - nwalk < (int)fp.refill_batch) : (nwalk >= thresh)));
                 if (my_slot >= 0 && !walking) { // stopped: filled voxel or border
                     ray[my_slot * 3 + 0] = make_uint4(__float_as_uint(sx), __float_as_uint(sy), __float_as_uint(sz), idx);
                     ray[my_slot * 3 + 2] = make_uint4(prev, steps, kDone, my_pixel);
