@@ -78,6 +78,13 @@ int32_t add_texture(const uint8_t* data, uint32_t width, uint32_t height, uint32
 #define VT_VOLUME_SPARSE_BRICKS 2u  /* 2 % of the 8^3 bricks non-empty (hash), half of their voxels filled */
 int32_t vt_add_volume_procedural(uint32_t kind, uint32_t width, uint32_t height, uint32_t depth, uint32_t seed);
 
+/* Extension: a caller-supplied sparse volume.  n_bricks bricks of 8^3 voxels: brick_coords = n x 3
+ * uint32 (voxel coordinate / 8), masks = n x 16 uint32 (voxel (x,y,z) of a brick is bit
+ * (x | (y&3) << 3) of word ((z&7) << 1 | (y&7) >> 2)), colors = n x RGBA8 (one colour per brick; filled
+ * voxels are opaque).  The arrays are only borrowed for the call.  Returns a texture id or -1. */
+int32_t vt_add_volume_bricks(const uint32_t* brick_coords, const uint32_t* masks, const uint8_t* colors, size_t n_bricks,
+                             uint32_t width, uint32_t height, uint32_t depth);
+
 /* replaces lib/memory.c:235-248.  Returns a write pointer with room for max(instance_count,1)
  * 64-byte column-major mat4s (texture id bit-cast into element [3][3], src/render.rs:74-78),
  * valid until end_update_instances; NULL on failure. */
@@ -162,6 +169,10 @@ int32_t vt_synchronize(void);
 /* Read back the last frame.  `capacity` in bytes; returns bytes written or -1. */
 int64_t vt_read_hits(vt_hit_record* out, size_t capacity);
 int64_t vt_read_color(uint8_t* rgba8, size_t capacity); /* R,G,B,A bytes, sRGB-encoded         */
+/* The same frame in the reference swapchain's byte order, VK_FORMAT_B8G8R8A8_SRGB (lib/swapchain.c:88). */
+int64_t vt_read_color_bgra(uint8_t* bgra8, size_t capacity);
+/* Writes the last frame as a binary PPM (P6, RGB); 0 = ok.  For eyeballing / diffing against a real run of the reference. */
+int32_t vt_write_ppm(const char* path);
 int64_t vt_read_depth(float* depth, size_t capacity);   /* D32 depth buffer (proxy-face depth) */
 int64_t vt_read_accum(uint64_t* accum, size_t capacity); /* PATHS: 3 x u64 per pixel, 2^-24 fixed point */
 

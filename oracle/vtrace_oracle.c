@@ -141,11 +141,17 @@ uint8_t vo_srgb_encode(float x) {
 /* ------------------------------------------------------------------------------------------ */
 /* scene state = what crosses the C ABI                                       */
 
-typedef struct { uint32_t w, h, d; uint8_t* rgba; uint32_t kind, seed; float* heights; } vo_texture;
+typedef struct {
+    uint32_t w, h, d; uint8_t* rgba; uint32_t kind, seed; float* heights;
+    uint32_t* btable; uint32_t* bmasks; uint8_t* bcolors; /* VO_VOLUME_BRICKS: slot per brick (or ~0), 16 words + RGBA per slot */
+} vo_texture;
 
 /* what the traversal needs to know about a volume.  kind 0 = dense RGBA8 texels (add_texture);
  * kinds 1/2 = procedural volumes of the large-scene extension (no reference counterpart). */
-typedef struct { uint32_t kind, w, h, d, seed; const uint8_t* rgba; const float* heights; } vol_view;
+typedef struct {
+    uint32_t kind, w, h, d, seed; const uint8_t* rgba; const float* heights;
+    const uint32_t* btable; const uint32_t* bmasks; const uint8_t* bcolors;
+} vol_view;
 
 static inline uint32_t vo_mix32(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
@@ -196,6 +202,18 @@ static inline void vol_texel(const vol_view* v, int32_t x, int32_t y, int32_t z,
         } else {
             out[0] = out[1] = out[2] = out[3] = 0;
         }
+    } else if (v->kind == VO_VOLUME_BRICKS) { /* caller-supplied 8^3 bricks: occupancy bits + one colour per brick */
+        const uint32_t ux = (uint32_t)x, uy = (uint32_t)y, uz = (uint32_t)z;
+        const size_t b = ((size_t)(uz >> 3) * (v->h >> 3) + (uy >> 3)) * (v->w >> 3) + (ux >> 3);
+        const uint32_t slot = v->btable[b];
+        out[0] = out[1] = out[2] = out[3] = 0;
+        if (slot != 0xFFFFFFFFu) {
+            const uint32_t wv = v->bmasks[(size_t)slot * 16 + (((uz & 7u) << 1) | ((uy & 7u) >> 2))];
+            if ((wv >> ((ux & 7u) | ((uy & 3u) << 3))) & 1u) {
+                memcpy(out, v->bcolors + 4 * (size_t)slot, 3);
+                out[3] = 255;
+            }
+        }
     } else { /* VO_VOLUME_SPARSE_BRICKS: 2 % of the 8^3 bricks are non-empty, half of their voxels filled */
         const uint32_t ux = (uint32_t)x, uy = (uint32_t)y, uz = (uint32_t)z;
         const int brick = (vo_hash3(ux >> 3, uy >> 3, uz >> 3, v->seed) & 0xFFFFu) < 1311u;
@@ -225,7 +243,9 @@ vo_scene* vo_scene_create(void) {
 
 void vo_scene_destroy(vo_scene* s) {
     if (!s) return;
-    for (uint32_t i = 0; i < s->ntex; ++i) { free(s->tex[i].rgba); free(s->tex[i].heights); }
+    for (uint32_t i = 0; i < s->ntex; ++i) {
+        free(s->tex[i].rgba); free(s->tex[i].heights); free(s->tex[i].btable); free(s->tex[i].bmasks); free(s->tex[i].bcolors);
+    }
     free(s->tex);
     free(s->inst);
     free(s);
@@ -240,7 +260,7 @@ int32_t vo_add_texture(vo_scene* s, const uint8_t* rgba, uint32_t w, uint32_t h,
     size_t bytes = (size_t)4 * w * h * d;
     vo_texture* t = &s->tex[s->ntex];
     t->w = w; t->h = h; t->d = d;
-    t->kind = 0; t->seed = 0; t->heights = NULL;
+    t->kind = 0; t->seed = 0; t->heights = NULL; t->btable = NULL; t->bmasks = NULL; t->bcolors = NULL;
     t->rgba = (uint8_t*)malloc(bytes ? bytes : 1);
     memcpy(t->rgba, rgba, bytes); /* lib/memory.c:304-307: data only borrowed for the call */
     return (int32_t)s->ntex++;
@@ -254,6 +274,7 @@ int32_t vo_add_volume_procedural(vo_scene* s, uint32_t kind, uint32_t w, uint32_
     }
     vo_texture* t = &s->tex[s->ntex];
     t->w = w; t->h = h; t->d = d; t->kind = kind; t->seed = seed; t->rgba = NULL; t->heights = NULL;
+    t->btable = NULL; t->bmasks = NULL; t->bcolors = NULL;
     if (kind == VO_VOLUME_HEIGHTMAP) {
         t->heights = (float*)malloc(sizeof(float) * (size_t)w * d);
 #ifdef _OPENMP
@@ -261,6 +282,31 @@ int32_t vo_add_volume_procedural(vo_scene* s, uint32_t kind, uint32_t w, uint32_
 #endif
         for (int64_t z = 0; z < (int64_t)d; ++z)
             for (uint32_t x = 0; x < w; ++x) t->heights[(size_t)z * w + x] = heightmap_height(x, (uint32_t)z, h, seed);
+    }
+    return (int32_t)s->ntex++;
+}
+
+int32_t vo_add_volume_bricks(vo_scene* s, const uint32_t* coords, const uint32_t* masks, const uint8_t* colors, uint64_t n,
+                             uint32_t w, uint32_t h, uint32_t d) {
+    if (s->ntex >= 65536u || !w || !h || !d || ((w | h | d) & 7u)) return -1;
+    if (s->ntex == s->captex) {
+        s->captex = s->captex ? s->captex * 2 : 4;
+        s->tex = (vo_texture*)realloc(s->tex, s->captex * sizeof *s->tex);
+    }
+    vo_texture* t = &s->tex[s->ntex];
+    memset(t, 0, sizeof *t);
+    t->w = w; t->h = h; t->d = d; t->kind = VO_VOLUME_BRICKS;
+    const size_t nb = (size_t)(w >> 3) * (h >> 3) * (d >> 3);
+    t->btable = (uint32_t*)malloc(nb * 4);
+    memset(t->btable, 0xFF, nb * 4);
+    t->bmasks = (uint32_t*)malloc((size_t)(n ? n : 1) * 64);
+    t->bcolors = (uint8_t*)malloc((size_t)(n ? n : 1) * 4);
+    memcpy(t->bmasks, masks, (size_t)n * 64);
+    memcpy(t->bcolors, colors, (size_t)n * 4);
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint32_t bx = coords[3 * i], by = coords[3 * i + 1], bz = coords[3 * i + 2];
+        if (bx >= (w >> 3) || by >= (h >> 3) || bz >= (d >> 3)) return -1;
+        t->btable[((size_t)bz * (h >> 3) + by) * (w >> 3) + bx] = (uint32_t)i;
     }
     return (int32_t)s->ntex++;
 }
@@ -333,6 +379,7 @@ static void inst_setup(inst_uniforms* I, const frame_uniforms* F, const vo_scene
     I->w = s->tex[I->tex].w; I->h = s->tex[I->tex].h; I->d = s->tex[I->tex].d;
     I->vol.kind = s->tex[I->tex].kind; I->vol.w = I->w; I->vol.h = I->h; I->vol.d = I->d;
     I->vol.seed = s->tex[I->tex].seed; I->vol.rgba = s->tex[I->tex].rgba; I->vol.heights = s->tex[I->tex].heights;
+    I->vol.btable = s->tex[I->tex].btable; I->vol.bmasks = s->tex[I->tex].bmasks; I->vol.bcolors = s->tex[I->tex].bcolors;
     I->Mi = mat4_inverse(&I->M);              /* trace.frag:65 */
     I->MVP = mat4_mul(&F->PV, &I->M);
     for (int j = 0; j < 4; ++j)
@@ -487,7 +534,7 @@ void vo_frag_main(const float* P, const float* V, const float* M, const float* s
     float pos[3], dir[3];
     frag_ray(&F.RD, &Mi, sp, model_position, w, h, d, pos, dir);
     dda_state r;
-    const vol_view vv = {0, w, h, d, 0, rgba, NULL};
+    const vol_view vv = {0, w, h, d, 0, rgba, NULL, NULL, NULL, NULL};
     dda_march(&vv, pos, dir, NULL, &r);
     out[0] = r.hit;
     out[1] = r.voxel[0]; out[2] = r.voxel[1]; out[3] = r.voxel[2];
@@ -862,7 +909,7 @@ uint64_t vo_render_rays(const vo_scene* s, uint64_t n, uint64_t first, uint32_t 
     memcpy(&tex, s->inst + 15, 4);
     if (tex >= s->ntex) return 0;
     const vo_texture* t = &s->tex[tex];
-    const vol_view vol = {t->kind, t->w, t->h, t->d, t->seed, t->rgba, t->heights};
+    const vol_view vol = {t->kind, t->w, t->h, t->d, t->seed, t->rgba, t->heights, t->btable, t->bmasks, t->bcolors};
     const float size[3] = {(float)(int32_t)t->w, (float)(int32_t)t->h, (float)(int32_t)t->d};
     uint64_t total = 0;
 #ifdef _OPENMP

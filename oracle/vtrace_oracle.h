@@ -42,6 +42,7 @@ extern "C" {
 /* procedural volume kinds of the large-scene extension */
 #define VO_VOLUME_HEIGHTMAP 1u
 #define VO_VOLUME_SPARSE_BRICKS 2u
+#define VO_VOLUME_BRICKS 3u /* caller-supplied bricks */
 
 /* Per-pixel derived hit record. 16 bytes. */
 typedef struct vo_hit_record {
@@ -60,6 +61,9 @@ void vo_scene_destroy(vo_scene*);
 int32_t vo_add_texture(vo_scene*, const uint8_t* rgba, uint32_t w, uint32_t h, uint32_t d);
 /* extension: a procedural volume (no texel storage); returns its texture id or -1 */
 int32_t vo_add_volume_procedural(vo_scene*, uint32_t kind, uint32_t w, uint32_t h, uint32_t d, uint32_t seed);
+/* extension: caller-supplied sparse volume: n bricks with coordinates (voxel / 8), 16 occupancy words and one RGBA colour each */
+int32_t vo_add_volume_bricks(vo_scene*, const uint32_t* coords, const uint32_t* masks, const uint8_t* colors, uint64_t n,
+                             uint32_t w, uint32_t h, uint32_t d);
 /* mirrors start/end_update_instances (lib/memory.c:235-267): n x 16 floats, column-major,
  * texture id bit-cast into element [3][3] (src/render.rs:74-78). n == 0 is coerced to 1. */
 void vo_set_instances(vo_scene*, const float* mats, uint32_t n);

@@ -48,6 +48,8 @@ def lib() -> C.CDLL:
         L.vo_add_texture.restype = i32
         L.vo_add_volume_procedural.argtypes = [vp, u32, u32, u32, u32, u32]
         L.vo_add_volume_procedural.restype = i32
+        L.vo_add_volume_bricks.argtypes = [vp, vp, vp, vp, u64, u32, u32, u32]
+        L.vo_add_volume_bricks.restype = i32
         L.vo_last_shadow_rays.restype = u64
         L.vo_render_rays.argtypes = [vp, u64, u64, u32, vp, vp, C.c_int]
         L.vo_render_rays.restype = u64
@@ -103,6 +105,12 @@ class OracleScene:
 
     def add_volume_procedural(self, kind: int, w: int, h: int, d: int, seed: int) -> int:
         return lib().vo_add_volume_procedural(self._h, kind, w, h, d, seed)
+
+    def add_volume_bricks(self, coords, masks, colors, w: int, h: int, d: int) -> int:
+        coords = np.ascontiguousarray(coords, dtype=np.uint32).reshape(-1, 3)
+        masks = np.ascontiguousarray(masks, dtype=np.uint32).reshape(-1, 16)
+        colors = np.ascontiguousarray(colors, dtype=np.uint8).reshape(-1, 4)
+        return lib().vo_add_volume_bricks(self._h, _p(coords), _p(masks), _p(colors), len(coords), w, h, d)
 
     def render_rays(self, n: int, seed: int, first: int = 0, threads=0, want_color=True):
         rec = np.empty(n, dtype=HIT_DTYPE)

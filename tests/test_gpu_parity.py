@@ -120,6 +120,20 @@ def test_config1_temple_1080p_primary(scene, assets, flags):
     assert (got["hit_voxel"] != abi.VT_MISS).sum() > 20000
 
 
+def test_bgra_and_ppm_readback(renderer, scene, assets, tmp_path):
+    t = scene.add(assets["Treasure"])
+    scene.set_instances([(glm.identity(), t)])
+    P, V = scenes.camera(160, 120, eye=(0.9, -0.5, 0.7))
+    scene.check_primary(P, V, 160, 120, what="readback formats")
+    rgba, bgra = renderer.read_color(), renderer.read_color_bgra()
+    assert np.array_equal(rgba[..., [2, 1, 0, 3]], bgra)  # VK_FORMAT_B8G8R8A8_SRGB byte order, lib/swapchain.c:88
+    path = str(tmp_path / "f.ppm")
+    renderer.write_ppm(path)
+    data = open(path, "rb").read()
+    head = b"P6\n160 120\n255\n"
+    assert data.startswith(head) and np.array_equal(np.frombuffer(data[len(head):], dtype=np.uint8).reshape(120, 160, 3), rgba[..., :3])
+
+
 def test_closeup_cameras(scene, assets):
     t = scene.add(assets["AncientTemple"])
     scene.set_instances([(glm.identity(), t)])
@@ -312,6 +326,28 @@ def test_brick_and_dense_volumes_in_one_scene(pscene, assets):
     P, V = scenes.camera(640, 360, eye=(0.4, -1.0, 2.4))
     got, _ = pscene.check_primary(P, V, 640, 360, flags=abi.FLAG_SHADOW_RAYS, what="bricks + dense")
     assert set(np.unique(got["instance"])) >= {0, 1, 2}
+
+
+def test_uploaded_brick_volume(pscene):
+    """vt_add_volume_bricks: caller-supplied sparse 8^3 bricks (coordinates, 512-bit masks, one colour each)."""
+    rng = np.random.default_rng(5)
+    w, h, d = 128, 64, 96
+    all_coords = np.array([(x, y, z) for z in range(d // 8) for y in range(h // 8) for x in range(w // 8)], dtype=np.uint32)
+    pick = rng.random(len(all_coords)) < 0.12
+    coords = all_coords[pick]
+    masks = rng.integers(0, 2**32, size=(len(coords), 16), dtype=np.uint64).astype(np.uint32) & \
+        rng.integers(0, 2**32, size=(len(coords), 16), dtype=np.uint64).astype(np.uint32)   # ~25 % of the voxels
+    colors = rng.integers(0, 256, size=(len(coords), 4), dtype=np.uint8)
+    rid = pscene.r.add_volume_bricks(coords, masks, colors, w, h, d)
+    oid = pscene.o.add_volume_bricks(coords, masks, colors, w, h, d)
+    pscene.tex_map[oid] = rid
+    pscene.set_instances([(glm.identity(), oid)])
+    P, V = scenes.camera(480, 270, eye=(0.9, -0.7, 0.9))
+    got, _ = pscene.check_primary(P, V, 480, 270, flags=abi.FLAG_SHADOW_RAYS, what="uploaded bricks")
+    assert (got["hit_voxel"] != abi.VT_MISS).sum() > 3000
+    pscene.check_rays(128, 64, seed=11, n_check=128 * 64, what="uploaded bricks, rays")
+    with pytest.raises(RuntimeError):
+        pscene.r.add_volume_bricks(np.array([[99, 0, 0]]), masks[:1], colors[:1], w, h, d)
 
 
 def test_incoherent_rays_small(pscene, assets):

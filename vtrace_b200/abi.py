@@ -51,6 +51,7 @@ SYMBOLS = {
     "get_input_data_pointer": (C.POINTER(UserInput), []),
     "add_texture": (_i32, [_vp, _u32, _u32, _u32]),
     "vt_add_volume_procedural": (_i32, [_u32, _u32, _u32, _u32, _u32]),
+    "vt_add_volume_bricks": (_i32, [_vp, _vp, _vp, _sz, _u32, _u32, _u32]),
     "start_update_instances": (_vp, [_u32]),
     "end_update_instances": (_i32, [_u32]),
     "cleanup": (None, []),
@@ -61,6 +62,8 @@ SYMBOLS = {
     "vt_synchronize": (_i32, []),
     "vt_read_hits": (_i64, [_vp, _sz]),
     "vt_read_color": (_i64, [_vp, _sz]),
+    "vt_read_color_bgra": (_i64, [_vp, _sz]),
+    "vt_write_ppm": (_i32, [C.c_char_p]),
     "vt_read_depth": (_i64, [_vp, _sz]),
     "vt_read_accum": (_i64, [_vp, _sz]),
     "vt_accum_device_ptr": (_vp, []),

@@ -64,7 +64,13 @@ __device__ __forceinline__ bool proc_filled(uint32_t kind, uint32_t seed, const 
     return brick && (vt_hash3(x, y, z, seed ^ 0x5bd1e995u) & 1u);                    // half of their voxels
 }
 
-__device__ __forceinline__ uchar4 proc_color(uint32_t kind, uint32_t seed, uint32_t h, uint32_t x, uint32_t y, uint32_t z) {
+__device__ __forceinline__ uchar4 proc_color(const BrickVolume* __restrict__ bv, uint32_t h, uint32_t x, uint32_t y, uint32_t z) {
+    const uint32_t kind = bv->kind, seed = bv->seed;
+    if (kind == kVolumeUploadedBricks) { // one colour per brick, found through the table again (once per ray)
+        const size_t b = ((size_t)(z >> 3) * bv->by + (y >> 3)) * bv->bx + (x >> 3);
+        const uchar4 c = __ldg(bv->colors + __ldg(bv->table + b));
+        return make_uchar4(c.x, c.y, c.z, 255);
+    }
     if (kind == kVolumeHeightmap) {
         const uint32_t band = ((h - 1u - y) * 4u) / h;
         const uint32_t pal[4] = {0x323c48u, 0x388060u, 0x787878u, 0xf5f0f0u}; // b<<16 | g<<8 | r
@@ -119,6 +125,24 @@ cudaError_t launch_brick_build(uint32_t kind, uint32_t seed, uint32_t w, uint32_
     const int threads = 128;
     brick_build_kernel<<<(unsigned)((bricks + threads - 1) / threads), threads, 0, stream>>>(kind, seed, w, h, d, heights, l1, table, pool,
                                                                                           pool_capacity, counter);
+    return cudaGetLastError();
+}
+
+// caller-supplied bricks: one thread per brick writes its table entry and l1 bit
+__global__ void brick_index_kernel(const uint32_t* __restrict__ coords, uint32_t n, uint32_t bx, uint32_t by, uint32_t bz,
+                                   uint32_t* __restrict__ l1, uint32_t* __restrict__ table, uint32_t* __restrict__ bad) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t x = coords[3 * i], y = coords[3 * i + 1], z = coords[3 * i + 2];
+    if (x >= bx || y >= by || z >= bz) { atomicAdd(bad, 1u); return; }
+    const size_t b = ((size_t)z * by + y) * bx + x;
+    table[b] = i;
+    atomicOr(l1 + (b >> 5), 1u << (b & 31));
+}
+
+cudaError_t launch_brick_index(const uint32_t* coords, uint32_t n, uint32_t bx, uint32_t by, uint32_t bz, uint32_t* l1, uint32_t* table,
+                               uint32_t* bad, cudaStream_t stream) {
+    if (n) brick_index_kernel<<<(n + 127) / 128, 128, 0, stream>>>(coords, n, bx, by, bz, l1, table, bad);
     return cudaGetLastError();
 }
 

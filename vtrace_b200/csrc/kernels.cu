@@ -574,7 +574,7 @@ __device__ __forceinline__ void march_instance(const InstUniforms* __restrict__ 
 template <bool kBricks>
 __device__ __forceinline__ uchar4 instance_texel(const InstUniforms* __restrict__ Ip, const int32_t v[3]) {
     if (kBricks && Ip->bricks)
-        return proc_color(Ip->bricks->kind, Ip->bricks->seed, Ip->h, (uint32_t)v[0], (uint32_t)v[1], (uint32_t)v[2]);
+        return proc_color(Ip->bricks, Ip->h, (uint32_t)v[0], (uint32_t)v[1], (uint32_t)v[2]);
     return fetch_texel(Ip->rgba, Ip->w, Ip->h, Ip->d, Ip->remap_identity != 0, v);
 }
 

@@ -43,11 +43,12 @@ struct BrickVolume {
     const uint32_t* table;
     const uint32_t* pool;
     const float* heights;  // heightmap kind: w*d column heights
+    const uchar4* colors;  // uploaded bricks: one RGBA colour per pool slot
     uint32_t kind, seed;   // VT_VOLUME_*
     uint32_t bx, by, bz;   // brick grid dimensions
     uint32_t n_bricks;     // non-empty bricks in the pool
 };
-static constexpr uint32_t kVolumeDense = 0, kVolumeHeightmap = 1, kVolumeSparseBricks = 2;
+static constexpr uint32_t kVolumeDense = 0, kVolumeHeightmap = 1, kVolumeSparseBricks = 2, kVolumeUploadedBricks = 3;
 
 // Per-frame uniforms, passed by value as a kernel parameter (constant bank, no loads).
 struct FrameParams {
@@ -148,6 +149,9 @@ cudaError_t launch_trace_paths(const FrameParams& fp, const InstUniforms* inst, 
 cudaError_t launch_heightmap(float* heights, uint32_t w, uint32_t h, uint32_t d, uint32_t seed, cudaStream_t stream);
 cudaError_t launch_brick_build(uint32_t kind, uint32_t seed, uint32_t w, uint32_t h, uint32_t d, const float* heights, uint32_t* l1,
                                uint32_t* table, uint32_t* pool, uint32_t pool_capacity, uint32_t* counter, cudaStream_t stream);
+// caller-supplied bricks: coords (n x 3) -> table / l1 entries (the masks are already the pool)
+cudaError_t launch_brick_index(const uint32_t* coords, uint32_t n, uint32_t bx, uint32_t by, uint32_t bz, uint32_t* l1, uint32_t* table,
+                               uint32_t* bad, cudaStream_t stream);
 // incoherent-ray mode: rays [first, first + n) through instance 0's volume
 cudaError_t launch_trace_rays(const FrameParams& fp, const InstUniforms* inst, const uint32_t* mask_arena, unsigned long long n,
                               unsigned long long first, FrameBuffers fb, int sm_count, cudaStream_t stream);

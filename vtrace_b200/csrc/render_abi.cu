@@ -35,7 +35,7 @@ struct State {
     bool vols_dirty = false;
     uint32_t* d_arena = nullptr; // all stop masks, contiguous
     uint32_t arena_words = 0, arena_cap = 0;
-    struct BrickAlloc { uint32_t* l1; uint32_t* table; uint32_t* pool; float* heights; BrickVolume* d_desc; };
+    struct BrickAlloc { uint32_t* l1; uint32_t* table; uint32_t* pool; float* heights; uchar4* colors; BrickVolume* d_desc; };
     std::vector<BrickAlloc> brick_allocs; // procedural volumes (extension)
     bool any_bricks = false;
     uint8_t* h_tex_staging = nullptr; // pinned; grows to the next power of two (lib/memory.c:297-302)
@@ -633,7 +633,7 @@ extern "C" int32_t vt_add_volume_procedural(uint32_t kind, uint32_t width, uint3
     CK(launch_brick_build(kind, seed, width, height, depth, a.heights, a.l1, a.table, a.pool, n, d_counter, g.stream));
     g.stats.launches += 2;
     BrickVolume bv{};
-    bv.l1 = a.l1; bv.table = a.table; bv.pool = a.pool; bv.heights = a.heights;
+    bv.l1 = a.l1; bv.table = a.table; bv.pool = a.pool; bv.heights = a.heights; bv.colors = nullptr;
     bv.kind = kind; bv.seed = seed;
     bv.bx = width >> 3; bv.by = height >> 3; bv.bz = depth >> 3;
     bv.n_bricks = n;
@@ -646,6 +646,72 @@ extern "C" int32_t vt_add_volume_procedural(uint32_t kind, uint32_t width, uint3
     v.rgba = nullptr;
     v.w = width; v.h = height; v.d = depth;
     v.xb = 5; v.yb = 2; v.mask_off = 0; v.mask_words = 0;
+    v.remap_identity = 1;
+    v.bricks = a.d_desc;
+    g.vols.push_back(v);
+    g.vols_dirty = true;
+    g.any_bricks = true;
+    return (int32_t)(g.vols.size() - 1);
+}
+
+// extension: a caller-supplied sparse volume, as 8^3 occupancy bricks with one colour each.
+extern "C" int32_t vt_add_volume_bricks(const uint32_t* brick_coords, const uint32_t* masks, const uint8_t* colors, size_t n_bricks,
+                                        uint32_t width, uint32_t height, uint32_t depth) {
+    if (!g.inited) return fail("vt_add_volume_bricks before entry()");
+    if (g.vols.size() >= kMaxTextures) return fail("Tried allocating too many textures");
+    if (!width || !height || !depth || (width | height | depth) & 7u || width > 8192 || height > 8192 || depth > 8192)
+        return fail("vt_add_volume_bricks: dimensions must be multiples of 8, at most 8192");
+    if (n_bricks && (!brick_coords || !masks || !colors)) return fail("vt_add_volume_bricks: null input");
+    if (n_bricks >= (1ull << 31)) return fail("vt_add_volume_bricks: too many bricks");
+    {
+        const uint32_t dims[3] = {width, height, depth};
+        for (int a = 0; a < 3; ++a) {
+            const float sz = (float)(int32_t)dims[a];
+            for (uint32_t x = 0; x < dims[a]; ++x)
+                if ((int32_t)floorf(((float)(int32_t)x / sz) * sz) != (int32_t)x)
+                    return fail("vt_add_volume_bricks: size %u does not map voxels to texels one to one", dims[a]);
+        }
+    }
+    CK(cudaSetDevice(g.device));
+    const size_t bricks = (size_t)(width >> 3) * (height >> 3) * (depth >> 3);
+    const size_t n1 = n_bricks ? n_bricks : 1;
+    State::BrickAlloc a{};
+    uint32_t* d_coords = nullptr;
+    uint32_t* d_bad = nullptr;
+    uint32_t bad = 0;
+    CK(cudaMalloc(&a.l1, ((bricks + 31) / 32) * 4));
+    CK(cudaMalloc(&a.table, bricks * 4));
+    CK(cudaMalloc(&a.pool, n1 * 64));
+    CK(cudaMalloc(&a.colors, n1 * 4));
+    CK(cudaMalloc(&d_coords, n1 * 12));
+    CK(cudaMalloc(&d_bad, 4));
+    CK(cudaMemsetAsync(a.l1, 0, ((bricks + 31) / 32) * 4, g.stream));
+    CK(cudaMemsetAsync(d_bad, 0, 4, g.stream));
+    // the inputs are only borrowed for the call (like add_texture's): synchronous copies
+    CK(cudaMemcpy(a.pool, masks, n_bricks * 64, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(a.colors, colors, n_bricks * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_coords, brick_coords, n_bricks * 12, cudaMemcpyHostToDevice));
+    CK(launch_brick_index(d_coords, (uint32_t)n_bricks, width >> 3, height >> 3, depth >> 3, a.l1, a.table, d_bad, g.stream));
+    CK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    cudaFree(d_coords);
+    cudaFree(d_bad);
+    g.stats.launches += 1;
+    if (bad) {
+        cudaFree(a.l1); cudaFree(a.table); cudaFree(a.pool); cudaFree(a.colors);
+        return fail("vt_add_volume_bricks: %u brick coordinates outside the volume", bad);
+    }
+    BrickVolume bv{};
+    bv.l1 = a.l1; bv.table = a.table; bv.pool = a.pool; bv.heights = nullptr; bv.colors = a.colors;
+    bv.kind = kVolumeUploadedBricks; bv.seed = 0;
+    bv.bx = width >> 3; bv.by = height >> 3; bv.bz = depth >> 3;
+    bv.n_bricks = (uint32_t)n_bricks;
+    CK(cudaMalloc(&a.d_desc, sizeof(BrickVolume)));
+    CK(cudaMemcpy(a.d_desc, &bv, sizeof bv, cudaMemcpyHostToDevice));
+    g.brick_allocs.push_back(a);
+    VolumeDesc v{};
+    v.w = width; v.h = height; v.d = depth;
+    v.xb = 5; v.yb = 2;
     v.remap_identity = 1;
     v.bricks = a.d_desc;
     g.vols.push_back(v);
@@ -686,7 +752,7 @@ extern "C" void cleanup(void) {
     g.fused_mode = 0;
     for (auto& v : g.vols) cudaFree(const_cast<uint8_t*>(v.rgba));
     g.vols.clear();
-    for (auto& b : g.brick_allocs) { cudaFree(b.l1); cudaFree(b.table); cudaFree(b.pool); cudaFree(b.heights); cudaFree(b.d_desc); }
+    for (auto& b : g.brick_allocs) { cudaFree(b.l1); cudaFree(b.table); cudaFree(b.pool); cudaFree(b.heights); cudaFree(b.colors); cudaFree(b.d_desc); }
     g.brick_allocs.clear();
     cudaFree(g.d_vols); cudaFree(g.d_arena); cudaFree(g.d_inst); cudaFree(g.d_iu); cudaFree(g.d_dec); cudaFree(g.d_thr);
     cudaFree(g.d_rec); cudaFree(g.d_color); cudaFree(g.d_depth); cudaFree(g.d_accum_own); cudaFree(g.d_stats);
@@ -750,6 +816,27 @@ extern "C" int64_t vt_read_hits(vt_hit_record* out, size_t capacity) {
 extern "C" int64_t vt_read_color(uint8_t* rgba8, size_t capacity) {
     return read_back(g.d_color, (size_t)g.cfg.width * g.cfg.height * 4, rgba8, capacity);
 }
+extern "C" int64_t vt_read_color_bgra(uint8_t* bgra8, size_t capacity) {
+    const int64_t n = read_back(g.d_color, (size_t)g.cfg.width * g.cfg.height * 4, bgra8, capacity);
+    for (int64_t p = 0; p + 3 < n; p += 4) { const uint8_t r = bgra8[p]; bgra8[p] = bgra8[p + 2]; bgra8[p + 2] = r; }
+    return n;
+}
+
+extern "C" int32_t vt_write_ppm(const char* path) {
+    if (!g.inited || !path) return -1;
+    const size_t n = (size_t)g.cfg.width * g.cfg.height;
+    std::vector<uint8_t> rgba(n * 4);
+    if (read_back(g.d_color, n * 4, rgba.data(), rgba.size()) < 0) return -1;
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail("vt_write_ppm: cannot open %s", path);
+    fprintf(f, "P6\n%u %u\n255\n", g.cfg.width, g.cfg.height);
+    std::vector<uint8_t> rgb(n * 3);
+    for (size_t p = 0; p < n; ++p) { rgb[3 * p] = rgba[4 * p]; rgb[3 * p + 1] = rgba[4 * p + 1]; rgb[3 * p + 2] = rgba[4 * p + 2]; }
+    const bool ok = fwrite(rgb.data(), 1, rgb.size(), f) == rgb.size();
+    fclose(f);
+    return ok ? 0 : fail("vt_write_ppm: short write to %s", path);
+}
+
 extern "C" int64_t vt_read_depth(float* depth, size_t capacity) {
     return read_back(g.d_depth, (size_t)g.cfg.width * g.cfg.height * 4, depth, capacity);
 }

@@ -140,6 +140,16 @@ class Renderer:
             raise RuntimeError("ERROR: Adding procedural volume failed: " + abi.last_error())
         return tex_id
 
+    def add_volume_bricks(self, coords, masks, colors, w: int, h: int, d: int) -> int:
+        coords = np.ascontiguousarray(coords, dtype=np.uint32).reshape(-1, 3)
+        masks = np.ascontiguousarray(masks, dtype=np.uint32).reshape(-1, 16)
+        colors = np.ascontiguousarray(colors, dtype=np.uint8).reshape(-1, 4)
+        assert len(coords) == len(masks) == len(colors)
+        tex_id = self._lib.vt_add_volume_bricks(coords.ctypes.data, masks.ctypes.data, colors.ctypes.data, len(coords), w, h, d)
+        if tex_id < 0:
+            raise RuntimeError("ERROR: Adding brick volume failed: " + abi.last_error())
+        return tex_id
+
     # -- headless extensions -------------------------------------------------------------------
     def get_config(self) -> abi.VtConfig:
         cfg = abi.VtConfig()
@@ -174,6 +184,14 @@ class Renderer:
     def read_color(self) -> np.ndarray:
         w, h = self._size()
         return self._read(self._lib.vt_read_color, np.empty((h, w, 4), dtype=np.uint8))
+
+    def read_color_bgra(self) -> np.ndarray:
+        w, h = self._size()
+        return self._read(self._lib.vt_read_color_bgra, np.empty((h, w, 4), dtype=np.uint8))
+
+    def write_ppm(self, path: str):
+        if self._lib.vt_write_ppm(path.encode()) != 0:
+            raise RuntimeError("vt_write_ppm failed: " + abi.last_error())
 
     def read_depth(self) -> np.ndarray:
         w, h = self._size()
