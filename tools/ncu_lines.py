@@ -75,7 +75,7 @@ def main():
                     help="aggregate per code region: a region starts at a '// ----' banner comment or a function definition")
     args = ap.parse_args()
 
-    sass = sass_lines(args.so, args.kernel)
+    sass = sass_lines(os.path.abspath(args.so), args.kernel)
     hdr, body = ncu_sass(args.report, args.regex)
     col = {h: i for i, h in enumerate(hdr)}
     if len(body) != len(sass):

@@ -191,12 +191,12 @@ __device__ __forceinline__ int brick_walk_step(const BrickVolume& bv, uint32_t W
     const uint32_t key = ((uint32_t)k.vx >> 3) | (((uint32_t)k.vy >> 3) << 10) | (((uint32_t)k.vz >> 3) << 20);
     if (key != k.cur_key) { // entered a new brick: one l1 bit, and the slot if it is set
         k.cur_key = key;
-        const size_t b = ((size_t)((uint32_t)k.vz >> 3) * bv.by + ((uint32_t)k.vy >> 3)) * bv.bx + ((uint32_t)k.vx >> 3);
+        const uint32_t b = (((uint32_t)k.vz >> 3) * bv.by + ((uint32_t)k.vy >> 3)) * bv.bx + ((uint32_t)k.vx >> 3); // < 2^31 bricks
         const uint32_t bit = (__ldg(bv.l1 + (b >> 5)) >> (b & 31)) & 1u;
         k.cur_slot = bit ? __ldg(bv.table + b) : 0xFFFFFFFFu;
     }
     if (k.cur_slot != 0xFFFFFFFFu) {
-        const uint32_t wv = __ldg(bv.pool + (size_t)k.cur_slot * 16 + ((((uint32_t)k.vz & 7u) << 1) | (((uint32_t)k.vy & 7u) >> 2)));
+        const uint32_t wv = __ldg(bv.pool + ((size_t)k.cur_slot << 4) + ((((uint32_t)k.vz & 7u) << 1) | (((uint32_t)k.vy & 7u) >> 2)));
         if ((wv >> (((uint32_t)k.vx & 7u) | (((uint32_t)k.vy & 3u) << 3))) & 1u) return 1; // :78-80
     }
     bool m0, m1, m2;

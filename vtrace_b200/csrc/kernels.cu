@@ -714,7 +714,7 @@ __device__ __forceinline__ int claim_tiles(unsigned long long* counter, int lane
 // -------------------------------------------------------------------------------------------
 // trace_primary_kernel: persistent warps over 8x4 pixel tiles; one thread per pixel.
 
-template <bool kSmem, bool kBricks>
+template <bool kSmem, bool kBricks, bool kShadow>
 __global__ void __launch_bounds__(kBlockThreads) trace_primary_kernel(const __grid_constant__ FrameParams fp,
                                                                       const InstUniforms* __restrict__ inst, const BinTable bins,
                                                                       const uint32_t* __restrict__ mask_arena,
@@ -770,7 +770,7 @@ __global__ void __launch_bounds__(kBlockThreads) trace_primary_kernel(const __gr
                 // extension: one shadow ray towards the sun, inside the fragment's own volume
                 float shade = 1.0f;
                 uint32_t shadow_bits = 0;
-                if (fp.flags & VT_FLAG_SHADOW_RAYS) {
+                if (kShadow) { // compiled in only for VT_FLAG_SHADOW_RAYS frames: the plain pass keeps its 64 registers
                     const float size[3] = {(float)(int32_t)Ip->w, (float)(int32_t)Ip->h, (float)(int32_t)Ip->d};
                     int ax, nsign;
                     float p0[3];
@@ -1572,9 +1572,13 @@ cudaError_t launch_resolve_partials(const InstUniforms* inst, const uint4* parti
 
 cudaError_t configure_kernels(int max_smem_optin) {
     cudaError_t e;
-    e = cudaFuncSetAttribute(trace_primary_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    e = cudaFuncSetAttribute(trace_primary_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(trace_primary_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    e = cudaFuncSetAttribute(trace_primary_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(trace_primary_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(trace_primary_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(trace_paths_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     if (e != cudaSuccess) return e;
@@ -1601,20 +1605,18 @@ cudaError_t launch_trace_primary(const FrameParams& fp, const InstUniforms* inst
     const int n_tiles = ((fp.width + kTileW - 1) / kTileW) * ((fp.height + kTileH - 1) / kTileH);
     const size_t smem = trace_smem_bytes(arena_words, masks_in_smem);
     const int warps_needed = (n_tiles + 7) / 8;
-    if (fp.any_bricks) { // scenes with procedural brick volumes: the variant that knows both volume kinds
-        if (masks_in_smem) {
-            const int grid = persistent_grid(trace_primary_kernel<true, true>, smem, sm_count, warps_needed);
-            trace_primary_kernel<true, true><<<grid, kBlockThreads, smem, stream>>>(fp, inst, bins, mask_arena, arena_words, lut, fb);
-        } else {
-            const int grid = persistent_grid(trace_primary_kernel<false, true>, smem, sm_count, warps_needed);
-            trace_primary_kernel<false, true><<<grid, kBlockThreads, smem, stream>>>(fp, inst, bins, mask_arena, arena_words, lut, fb);
-        }
-    } else if (masks_in_smem) {
-        const int grid = persistent_grid(trace_primary_kernel<true, false>, smem, sm_count, warps_needed);
-        trace_primary_kernel<true, false><<<grid, kBlockThreads, smem, stream>>>(fp, inst, bins, mask_arena, arena_words, lut, fb);
+    // variants: masks in shared memory or not x scenes with procedural brick volumes x shadow rays
+    auto launch = [&](auto kernel) {
+        const int grid = persistent_grid(kernel, smem, sm_count, warps_needed);
+        kernel<<<grid, kBlockThreads, smem, stream>>>(fp, inst, bins, mask_arena, arena_words, lut, fb);
+    };
+    const bool shadow = (fp.flags & VT_FLAG_SHADOW_RAYS) != 0, bricks = fp.any_bricks != 0;
+    if (masks_in_smem) {
+        if (bricks) { if (shadow) launch(trace_primary_kernel<true, true, true>); else launch(trace_primary_kernel<true, true, false>); }
+        else        { if (shadow) launch(trace_primary_kernel<true, false, true>); else launch(trace_primary_kernel<true, false, false>); }
     } else {
-        const int grid = persistent_grid(trace_primary_kernel<false, false>, smem, sm_count, warps_needed);
-        trace_primary_kernel<false, false><<<grid, kBlockThreads, smem, stream>>>(fp, inst, bins, mask_arena, arena_words, lut, fb);
+        if (bricks) { if (shadow) launch(trace_primary_kernel<false, true, true>); else launch(trace_primary_kernel<false, true, false>); }
+        else        { if (shadow) launch(trace_primary_kernel<false, false, true>); else launch(trace_primary_kernel<false, false, false>); }
     }
     return cudaGetLastError();
 }
