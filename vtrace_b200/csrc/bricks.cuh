@@ -5,11 +5,22 @@
 // overflows its u32 byte count at 1024^3, lib/memory.c:297).  Such volumes are generated on the
 // device from a procedural definition and stored as occupancy only:
 //   l1 bit per 8^3 brick  ->  table[brick] = pool slot  ->  16 words (512 bits) per non-empty brick.
+// The brick grid carries a one-brick border on every side whose entries say "outside" (kSlotExit), so
+// the walk needs no coordinate compares: leaving the volume is found by the same lookup as entering
+// a brick.
 // Traversal keeps the reference's per-voxel float DDA (trace.frag:73-87) bit for bit — same steps,
 // same ties — but touches memory only when the ray enters a new brick (l1 bit, then the slot) and,
 // inside non-empty bricks, one word per step; empty bricks are walked with arithmetic alone.
 // Colour is a function of the voxel position, evaluated at the hit.
 #pragma once
+
+static constexpr uint32_t kSlotEmpty = 0xFFFFFFFFu; // brick without voxels
+static constexpr uint32_t kSlotExit = 0xFFFFFFFEu;  // border brick: outside the volume
+
+// index of brick (x, y, z) in the padded grid (pbx, pby = brick counts + 2)
+__host__ __device__ __forceinline__ uint32_t brick_index(uint32_t pbx, uint32_t pby, uint32_t x, uint32_t y, uint32_t z) {
+    return ((z + 1u) * pby + (y + 1u)) * pbx + (x + 1u);
+}
 
 __host__ __device__ __forceinline__ uint32_t vt_mix32(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
@@ -67,8 +78,7 @@ __device__ __forceinline__ bool proc_filled(uint32_t kind, uint32_t seed, const 
 __device__ __forceinline__ uchar4 proc_color(const BrickVolume* __restrict__ bv, uint32_t h, uint32_t x, uint32_t y, uint32_t z) {
     const uint32_t kind = bv->kind, seed = bv->seed;
     if (kind == kVolumeUploadedBricks) { // one colour per brick, found through the table again (once per ray)
-        const size_t b = ((size_t)(z >> 3) * bv->by + (y >> 3)) * bv->bx + (x >> 3);
-        const uchar4 c = __ldg(bv->colors + __ldg(bv->table + b));
+        const uchar4 c = __ldg(bv->colors + __ldg(bv->table + brick_index(bv->bx, bv->by, x >> 3, y >> 3, z >> 3)));
         return make_uchar4(c.x, c.y, c.z, 255);
     }
     if (kind == kVolumeHeightmap) {
@@ -115,8 +125,26 @@ __global__ void brick_build_kernel(uint32_t kind, uint32_t seed, uint32_t w, uin
     const uint32_t slot = atomicAdd(counter, 1u);
     if (!pool || slot >= pool_capacity) return;
     for (uint32_t wi = 0; wi < 16; ++wi) pool[(size_t)slot * 16 + wi] = words[wi];
-    table[b] = slot;
-    atomicOr(l1 + (b >> 5), 1u << (b & 31));
+    const uint32_t pb = brick_index(bxn + 2, byn + 2, bx, by, bz);
+    table[pb] = slot;
+    atomicOr(l1 + (pb >> 5), 1u << (pb & 31));
+}
+
+// border of the padded brick grid: l1 bit set, table = kSlotExit.  One thread per padded brick.
+__global__ void brick_border_kernel(uint32_t pbx, uint32_t pby, uint32_t pbz, uint32_t* __restrict__ l1, uint32_t* __restrict__ table) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)pbx * pby * pbz) return;
+    const uint32_t x = (uint32_t)(i % pbx), y = (uint32_t)((i / pbx) % pby), z = (uint32_t)(i / ((size_t)pbx * pby));
+    if (x == 0 || y == 0 || z == 0 || x == pbx - 1 || y == pby - 1 || z == pbz - 1) {
+        table[i] = kSlotExit;
+        atomicOr(l1 + (i >> 5), 1u << (i & 31));
+    }
+}
+
+cudaError_t launch_brick_border(uint32_t pbx, uint32_t pby, uint32_t pbz, uint32_t* l1, uint32_t* table, cudaStream_t stream) {
+    const size_t n = (size_t)pbx * pby * pbz;
+    brick_border_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(pbx, pby, pbz, l1, table);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_brick_build(uint32_t kind, uint32_t seed, uint32_t w, uint32_t h, uint32_t d, const float* heights, uint32_t* l1,
@@ -135,7 +163,7 @@ __global__ void brick_index_kernel(const uint32_t* __restrict__ coords, uint32_t
     if (i >= n) return;
     const uint32_t x = coords[3 * i], y = coords[3 * i + 1], z = coords[3 * i + 2];
     if (x >= bx || y >= by || z >= bz) { atomicAdd(bad, 1u); return; }
-    const size_t b = ((size_t)z * by + y) * bx + x;
+    const uint32_t b = brick_index(bx + 2, by + 2, x, y, z);
     table[b] = i;
     atomicOr(l1 + (b >> 5), 1u << (b & 31));
 }
@@ -150,16 +178,93 @@ cudaError_t launch_brick_index(const uint32_t* coords, uint32_t n, uint32_t bx, 
 // float operations in the same order as dda_init / dda_step / dda_slow_impl — only the occupancy
 // test differs.  brick_walk_step() runs ONE loop iteration; the persistent-lane ray kernel interleaves
 // the walks of 32 lanes and refills lanes whose ray ended.
+//
+// Fast path (no NaN/inf in side/delta): the voxel is kept packed in two words, a = (x+8) | (y+8) << 16
+// and b = z+8 (the bias of one brick keeps the border positive), so a step is three predicated adds
+// and "still in the same empty brick?" is three LOP3s against the reference pair (ref_a, ref_b).  Only
+// when that test fails is anything looked up: the l1 bit of the new brick, its slot if the bit is
+// set (kSlotExit in the border = the ray left the volume), one pool word per step inside a brick
+// that has voxels.  For such a brick the reference pair is stored complemented, which makes the test
+// fail on every step without a second compare.  Every fast-path iteration advances >= 1 voxel, so the
+// steps < W+H+D bound of :74 cannot bind before the ray is outside.
 struct BrickWalk {
-    int32_t vx, vy, vz;
     float sx, sy, sz;
+    uint32_t a, b;
+    uint32_t pa, pb;       // (a, b) before the last iteration
+    uint32_t ix, iy, iz;   // packed per-axis increments
+    uint32_t ref_a, ref_b;
+    uint32_t slot;
     uint32_t steps, last;
-    uint32_t cur_key, cur_slot;
-    bool finite;
 };
+static constexpr uint32_t kBrickMaskA = 0xFFF8FFF8u; // brick part of both packed words
 
-__device__ __forceinline__ void brick_walk_init(uint32_t W, uint32_t H, uint32_t D, const float pos[3], const float dir[3],
-                                                bool has_start, const int32_t sv[3], Dda& r, BrickWalk& k) {
+// literal transcription of the loop for rays with a zero direction component (0 * inf = NaN, :84), run to
+// the end.  Out of line and fed by value, so the callers' ray state stays in registers.
+struct BrickSlowState {
+    int32_t v[3];
+    float side[3];
+    uint32_t steps, last;
+};
+__device__ __noinline__ int brick_walk_slow(const uint32_t* __restrict__ l1, const uint32_t* __restrict__ table,
+                                            const uint32_t* __restrict__ pool, uint32_t pbx, uint32_t pby, uint32_t W, uint32_t H,
+                                            uint32_t D, float d0, float d1, float d2, int32_t s0, int32_t s1, int32_t s2,
+                                            BrickSlowState* io) {
+    int32_t vx = io->v[0], vy = io->v[1], vz = io->v[2];
+    float sx = io->side[0], sy = io->side[1], sz = io->side[2];
+    uint32_t steps = 0, last = 0;
+    int status = 2;
+    while (steps < W + H + D && (uint32_t)vx < W && (uint32_t)vy < H && (uint32_t)vz < D) { // :74-75
+        const uint32_t bi = brick_index(pbx, pby, (uint32_t)vx >> 3, (uint32_t)vy >> 3, (uint32_t)vz >> 3);
+        if ((__ldg(l1 + (bi >> 5)) >> (bi & 31)) & 1u) {
+            const uint32_t wv = __ldg(pool + ((size_t)__ldg(table + bi) << 4) + ((((uint32_t)vz & 7u) << 1) | (((uint32_t)vy & 7u) >> 2)));
+            if ((wv >> (((uint32_t)vx & 7u) | (((uint32_t)vy & 3u) << 3))) & 1u) { status = 1; break; } // :78-80
+        }
+        const bool m0 = sx <= vt_fmin(sy, sz); // :83
+        const bool m1 = sy <= vt_fmin(sz, sx);
+        const bool m2 = sz <= vt_fmin(sx, sy);
+        sx += (m0 ? 1.0f : 0.0f) * d0; // :84
+        sy += (m1 ? 1.0f : 0.0f) * d1;
+        sz += (m2 ? 1.0f : 0.0f) * d2;
+        vx += m0 ? s0 : 0; // :85
+        vy += m1 ? s1 : 0;
+        vz += m2 ? s2 : 0;
+        last = (m0 ? 1u : 0u) | (m1 ? 2u : 0u) | (m2 ? 4u : 0u);
+        ++steps; // :86
+    }
+    io->v[0] = vx; io->v[1] = vy; io->v[2] = vz;
+    io->side[0] = sx; io->side[1] = sy; io->side[2] = sz;
+    io->steps = steps; io->last = last;
+    return status;
+}
+
+// The walk left the brick it knew to be empty (or stands in one that has voxels): look at the current
+// voxel.  0 = empty, keep walking; 1 = filled (:78-80); 2 = outside the volume (:75).
+__device__ __forceinline__ int brick_walk_lookup(const BrickVolume& bv, BrickWalk& k) {
+    // ref is stored complemented (flip = ~0) while the current brick has voxels
+    const uint32_t flip = k.slot != kSlotEmpty ? 0xFFFFFFFFu : 0u;
+    if ((((k.a ^ k.ref_a ^ flip) | (k.b ^ k.ref_b ^ flip)) & kBrickMaskA) != 0u) { // entered another brick: one l1 bit, and the slot if it is set
+        const uint32_t bi = ((k.b >> 3) * bv.by + (k.a >> 19)) * bv.bx + ((k.a >> 3) & 0x1FFFu);
+        const uint32_t bit = (__ldg(bv.l1 + (bi >> 5)) >> (bi & 31)) & 1u;
+        k.slot = bit ? __ldg(bv.table + bi) : kSlotEmpty;
+        k.ref_a = bit ? ~k.a : k.a;
+        k.ref_b = bit ? ~k.b : k.b;
+        if (k.slot == kSlotExit) return 2;
+    }
+    if (k.slot != kSlotEmpty) {
+        const uint32_t wv = __ldg(bv.pool + ((size_t)k.slot << 4) + (((k.b & 7u) << 1) | ((k.a >> 18) & 1u)));
+        if ((wv >> ((k.a & 7u) | (((k.a >> 16) & 3u) << 3))) & 1u) {
+            // axes advanced by the last iteration (:83), from the voxel it started at
+            const uint32_t da = k.a ^ k.pa;
+            k.last = ((da & 0xFFFFu) ? 1u : 0u) | ((da >> 16) ? 2u : 0u) | (k.b != k.pb ? 4u : 0u);
+            return 1;
+        }
+    }
+    return 0;
+}
+
+// ray setup (trace.frag:63-71) + the test of the start voxel; returns the walk status (0 = walking)
+__device__ __forceinline__ int brick_walk_begin(const BrickVolume& bv, uint32_t W, uint32_t H, uint32_t D, const float pos[3],
+                                                const float dir[3], bool has_start, const int32_t sv[3], Dda& r, BrickWalk& k) {
     const float size[3] = {(float)(int32_t)W, (float)(int32_t)H, (float)(int32_t)D};
     float sgn[3];
     r.len = sqrtf((dir[0] * dir[0] + dir[1] * dir[1]) + dir[2] * dir[2]); // length(), :70
@@ -176,54 +281,63 @@ __device__ __forceinline__ void brick_walk_init(uint32_t W, uint32_t H, uint32_t
     r.steps = 0;
     r.last_mask = 0;
     r.hit = false;
-    k.finite = isfinite(r.delta[0]) && isfinite(r.delta[1]) && isfinite(r.delta[2]) && isfinite(r.side[0]) &&
-               isfinite(r.side[1]) && isfinite(r.side[2]);
-    k.vx = r.v[0]; k.vy = r.v[1]; k.vz = r.v[2];
-    k.sx = r.side[0]; k.sy = r.side[1]; k.sz = r.side[2];
+    const bool finite = isfinite(r.delta[0]) && isfinite(r.delta[1]) && isfinite(r.delta[2]) && isfinite(r.side[0]) &&
+                        isfinite(r.side[1]) && isfinite(r.side[2]);
+    // the packed walk needs the start voxel within one brick of the volume (true for every caller:
+    // rays start inside, shadow / bounce rays at most one voxel outside)
+    const bool near = r.v[0] >= -8 && r.v[0] < (int32_t)W + 8 && r.v[1] >= -8 && r.v[1] < (int32_t)H + 8 && r.v[2] >= -8 &&
+                      r.v[2] < (int32_t)D + 8;
+    int status = 0;
     k.steps = 0; k.last = 0;
-    k.cur_key = 0xFFFFFFFFu; k.cur_slot = 0xFFFFFFFFu;
+    if (!finite || !near) {
+        BrickSlowState io;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { io.v[c] = r.v[c]; io.side[c] = r.side[c]; }
+        status = brick_walk_slow(bv.l1, bv.table, bv.pool, bv.bx, bv.by, W, H, D, r.delta[0], r.delta[1], r.delta[2], r.step[0],
+                                 r.step[1], r.step[2], &io);
+        // park the finished ray in the packed state (clamped: the voxel of a miss is never read)
+        r.v[0] = max(-8, min(io.v[0], (int32_t)W + 7)); r.v[1] = max(-8, min(io.v[1], (int32_t)H + 7)); r.v[2] = max(-8, min(io.v[2], (int32_t)D + 7));
+        r.side[0] = io.side[0]; r.side[1] = io.side[1]; r.side[2] = io.side[2];
+        k.steps = io.steps; k.last = io.last;
+    }
+    k.a = (uint32_t)(r.v[0] + 8) | ((uint32_t)(r.v[1] + 8) << 16);
+    k.b = (uint32_t)(r.v[2] + 8);
+    k.ix = (uint32_t)r.step[0]; k.iy = (uint32_t)r.step[1] << 16; k.iz = (uint32_t)r.step[2];
+    k.sx = r.side[0]; k.sy = r.side[1]; k.sz = r.side[2];
+    k.pa = k.a; k.pb = k.b;
+    k.slot = kSlotEmpty;
+    k.ref_a = ~k.a; k.ref_b = ~k.b; // no current brick: the first test looks one up
+    if (status == 0) status = brick_walk_lookup(bv, k);
+    return status;
 }
 
-// one iteration of the while loop of trace.frag:75-87; returns 0 = keep walking, 1 = hit, 2 = left / out of steps
-__device__ __forceinline__ int brick_walk_step(const BrickVolume& bv, uint32_t W, uint32_t H, uint32_t D, const Dda& r, BrickWalk& k) {
-    if (!(k.steps < W + H + D && (uint32_t)k.vx < W && (uint32_t)k.vy < H && (uint32_t)k.vz < D)) return 2; // :74-75
-    // texture(tex, voxel / size): brick volumes only exist for sizes where the texel IS the voxel
-    const uint32_t key = ((uint32_t)k.vx >> 3) | (((uint32_t)k.vy >> 3) << 10) | (((uint32_t)k.vz >> 3) << 20);
-    if (key != k.cur_key) { // entered a new brick: one l1 bit, and the slot if it is set
-        k.cur_key = key;
-        const uint32_t b = (((uint32_t)k.vz >> 3) * bv.by + ((uint32_t)k.vy >> 3)) * bv.bx + ((uint32_t)k.vx >> 3); // < 2^31 bricks
-        const uint32_t bit = (__ldg(bv.l1 + (b >> 5)) >> (b & 31)) & 1u;
-        k.cur_slot = bit ? __ldg(bv.table + b) : 0xFFFFFFFFu;
+// Up to kBurst iterations of the while loop of trace.frag:75-87 through the current empty brick, then
+// ONE lookup if the walk left it.  The lanes of a warp run the burst together and meet again for the
+// lookup, so its loads are issued by many lanes at once instead of by whichever lane happens to cross
+// a brick face in a given iteration.
+template <int kBurst>
+__device__ __forceinline__ int brick_walk_burst(const BrickVolume& bv, const Dda& r, BrickWalk& k) {
+    // Branch-free on purpose: a lane that has left its brick idles through the rest of the burst
+    // (predicated off) instead of jumping ahead to a lookup of its own.
+    bool go = true;
+#pragma unroll
+    for (int u = 0; u < kBurst; ++u) {
+        // no NaN: side <= min(other two) is side == min(all three); vec3(mask) * delta is a predicated add
+        const float m = fminf(fminf(k.sx, k.sy), k.sz); // :83
+        const bool m0 = go && k.sx == m, m1 = go && k.sy == m, m2 = go && k.sz == m;
+        if (go) { k.pa = k.a; k.pb = k.b; }
+        if (m0) { k.sx += r.delta[0]; k.a += k.ix; } // :84-85
+        if (m1) { k.sy += r.delta[1]; k.a += k.iy; }
+        if (m2) { k.sz += r.delta[2]; k.b += k.iz; }
+        k.steps += go ? 1u : 0u; // :86
+        // bits 16-18 of b are always 0: one mask serves both words
+        go = go && (((k.a ^ k.ref_a) | (k.b ^ k.ref_b)) & kBrickMaskA) == 0u;
     }
-    if (k.cur_slot != 0xFFFFFFFFu) {
-        const uint32_t wv = __ldg(bv.pool + ((size_t)k.cur_slot << 4) + ((((uint32_t)k.vz & 7u) << 1) | (((uint32_t)k.vy & 7u) >> 2)));
-        if ((wv >> (((uint32_t)k.vx & 7u) | (((uint32_t)k.vy & 3u) << 3))) & 1u) return 1; // :78-80
-    }
-    bool m0, m1, m2;
-    if (k.finite) { // no NaN: side <= min(other two) is side == min(all three); vec3(mask) * delta is a predicated add
-        const float m = fminf(fminf(k.sx, k.sy), k.sz);
-        m0 = k.sx == m; m1 = k.sy == m; m2 = k.sz == m;
-        if (m0) k.sx += r.delta[0];
-        if (m1) k.sy += r.delta[1];
-        if (m2) k.sz += r.delta[2];
-    } else {
-        m0 = k.sx <= vt_fmin(k.sy, k.sz); // :83
-        m1 = k.sy <= vt_fmin(k.sz, k.sx);
-        m2 = k.sz <= vt_fmin(k.sx, k.sy);
-        k.sx += (m0 ? 1.0f : 0.0f) * r.delta[0]; // :84
-        k.sy += (m1 ? 1.0f : 0.0f) * r.delta[1];
-        k.sz += (m2 ? 1.0f : 0.0f) * r.delta[2];
-    }
-    k.vx += m0 ? r.step[0] : 0; // :85
-    k.vy += m1 ? r.step[1] : 0;
-    k.vz += m2 ? r.step[2] : 0;
-    k.last = (m0 ? 1u : 0u) | (m1 ? 2u : 0u) | (m2 ? 4u : 0u);
-    ++k.steps; // :86
-    return 0;
+    return go ? 0 : brick_walk_lookup(bv, k);
 }
 
 __device__ __forceinline__ void brick_walk_finish(const BrickWalk& k, bool hit, Dda& r) {
-    r.v[0] = k.vx; r.v[1] = k.vy; r.v[2] = k.vz;
+    r.v[0] = (int32_t)(k.a & 0xFFFFu) - 8; r.v[1] = (int32_t)(k.a >> 16) - 8; r.v[2] = (int32_t)k.b - 8;
     r.side[0] = k.sx; r.side[1] = k.sy; r.side[2] = k.sz;
     r.steps = k.steps;
     r.last_mask = k.last;
@@ -233,8 +347,7 @@ __device__ __forceinline__ void brick_walk_finish(const BrickWalk& k, bool hit, 
 __device__ __forceinline__ void dda_march_bricks(const BrickVolume& bv, uint32_t W, uint32_t H, uint32_t D, const float pos[3],
                                                  const float dir[3], bool has_start, const int32_t sv[3], Dda& r) {
     BrickWalk k;
-    brick_walk_init(W, H, D, pos, dir, has_start, sv, r, k);
-    int status;
-    while ((status = brick_walk_step(bv, W, H, D, r, k)) == 0) {}
+    int status = brick_walk_begin(bv, W, H, D, pos, dir, has_start, sv, r, k);
+    while (status == 0) status = brick_walk_burst<4>(bv, r, k);
     brick_walk_finish(k, status == 1, r);
 }

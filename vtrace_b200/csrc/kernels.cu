@@ -913,17 +913,19 @@ __global__ void __launch_bounds__(kBlockThreads) trace_rays_kernel(const __grid_
         const BrickVolume bv = *Ip->bricks;
         const uint32_t W = Ip->w, H = Ip->h, D = Ip->d;
         constexpr unsigned long long kChunk = 2048;
+        constexpr int kRayBurst = 4; // DDA iterations between brick lookups (see brick_walk_burst)
         const unsigned long long n_chunks = (n + kChunk - 1) / kChunk;
         unsigned long long chunk_next = 0, chunk_end = 0; // the warp's current range of ray ids
         bool more = true;
         bool active = false;
+        int status = 0; // of the lane's walk: 0 = walking, 1 = hit, 2 = left the volume
         unsigned long long my_ray = 0;
         Dda r;
         BrickWalk k;
         r.hit = false; r.steps = 0; r.last_mask = 0; r.len = 1.0f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) { r.v[c] = 0; r.step[c] = 0; r.side[c] = r.delta[c] = r.dir[c] = r.pos[c] = 0.0f; }
-        k.vx = k.vy = k.vz = 0; k.sx = k.sy = k.sz = 0.0f; k.steps = k.last = 0; k.cur_key = k.cur_slot = 0xFFFFFFFFu; k.finite = true;
+        k.a = k.b = k.pa = k.pb = k.ix = k.iy = k.iz = 0; k.sx = k.sy = k.sz = 0.0f; k.steps = k.last = 0; k.ref_a = k.ref_b = 0; k.slot = kSlotEmpty;
         for (;;) {
             // ---- refill idle lanes ----
             uint32_t idle = __ballot_sync(0xffffffffu, !active);
@@ -943,7 +945,7 @@ __global__ void __launch_bounds__(kBlockThreads) trace_rays_kernel(const __grid_
                     float pos[3], dir[3];
                     make_ray(my_ray, pos, dir);
                     const int32_t none[3] = {0, 0, 0};
-                    brick_walk_init(W, H, D, pos, dir, false, none, r, k);
+                    status = brick_walk_begin(bv, W, H, D, pos, dir, false, none, r, k);
                     active = true;
                 }
                 const unsigned long long want = __popc(idle);
@@ -956,19 +958,19 @@ __global__ void __launch_bounds__(kBlockThreads) trace_rays_kernel(const __grid_
             const int stop_at = more ? 8 : 32;
             for (;;) {
 #pragma unroll 1
-                for (int u = 0; u < 8; ++u) {
-                    if (active) {
-                        const int status = brick_walk_step(bv, W, H, D, r, k);
-                        if (status) {
-                            brick_walk_finish(k, status == 1, r);
-                            iter_sum += r.steps;
-                            write_ray(my_ray, r);
-                            active = false;
-                        }
-                    }
+                for (int u = 0; u < 2; ++u) {
+                    if (status == 0 && active) status = brick_walk_burst<kRayBurst>(bv, r, k);
+                    __syncwarp();
                 }
-                const int n_idle = __popc(__ballot_sync(0xffffffffu, !active));
+                const int n_idle = __popc(__ballot_sync(0xffffffffu, !active || status != 0));
                 if (n_idle >= stop_at || n_idle == 32) break;
+            }
+            // ---- ended rays write their record ----
+            if (active && status != 0) {
+                brick_walk_finish(k, status == 1, r);
+                iter_sum += r.steps;
+                write_ray(my_ray, r);
+                active = false;
             }
         }
     }

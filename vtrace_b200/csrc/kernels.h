@@ -34,8 +34,9 @@ struct VolumeDesc {
 
 // Large procedural volumes (extension; §8f rank 2): occupancy only, as a
 // two-level sparse structure; colours are a function of the voxel position.
-//   l1    : one bit per 8^3 brick (set = the brick has at least one filled voxel)
-//   table : per brick, its slot in `pool` (only meaningful where the l1 bit is set)
+//   l1    : one bit per 8^3 brick (set = the brick has at least one filled voxel, or lies in the border)
+//   table : per brick, its slot in `pool` (only meaningful where the l1 bit is set); 0xFFFFFFFE in the border
+// The brick grid is stored padded by one brick on every side; the border says "outside the volume".
 //   pool  : 16 words per non-empty brick; voxel (x,y,z) of a brick is bit (x | (y&3) << 3) of
 //           word ((z&7) << 1 | (y&7) >> 2)
 struct BrickVolume {
@@ -45,7 +46,7 @@ struct BrickVolume {
     const float* heights;  // heightmap kind: w*d column heights
     const uchar4* colors;  // uploaded bricks: one RGBA colour per pool slot
     uint32_t kind, seed;   // VT_VOLUME_*
-    uint32_t bx, by, bz;   // brick grid dimensions
+    uint32_t bx, by, bz;   // PADDED brick grid dimensions (bricks per axis + 2)
     uint32_t n_bricks;     // non-empty bricks in the pool
 };
 static constexpr uint32_t kVolumeDense = 0, kVolumeHeightmap = 1, kVolumeSparseBricks = 2, kVolumeUploadedBricks = 3;
@@ -150,6 +151,7 @@ cudaError_t launch_heightmap(float* heights, uint32_t w, uint32_t h, uint32_t d,
 cudaError_t launch_brick_build(uint32_t kind, uint32_t seed, uint32_t w, uint32_t h, uint32_t d, const float* heights, uint32_t* l1,
                                uint32_t* table, uint32_t* pool, uint32_t pool_capacity, uint32_t* counter, cudaStream_t stream);
 // caller-supplied bricks: coords (n x 3) -> table / l1 entries (the masks are already the pool)
+cudaError_t launch_brick_border(uint32_t pbx, uint32_t pby, uint32_t pbz, uint32_t* l1, uint32_t* table, cudaStream_t stream);
 cudaError_t launch_brick_index(const uint32_t* coords, uint32_t n, uint32_t bx, uint32_t by, uint32_t bz, uint32_t* l1, uint32_t* table,
                                uint32_t* bad, cudaStream_t stream);
 // incoherent-ray mode: rays [first, first + n) through instance 0's volume

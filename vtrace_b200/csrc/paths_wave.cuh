@@ -111,9 +111,10 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
             const bool may_hit = !(px < Ip->bounds[0] || px > Ip->bounds[1] || py < Ip->bounds[2] || py > Ip->bounds[3]);
             if (in_frame && !may_hit) {
                 const size_t p = (size_t)py * (size_t)fp.width + (size_t)px;
+                if (fp.sky_spp) {
 #pragma unroll
-                if (fp.sky_spp)
                     for (int c = 0; c < 3; ++c) fb.accum[3 * p + c] += sky_q[c] * fp.sky_spp;
+                }
                 rays += fp.spp;
             }
         }

@@ -620,9 +620,14 @@ extern "C" int32_t vt_add_volume_procedural(uint32_t kind, uint32_t width, uint3
         CK(launch_heightmap(a.heights, width, height, depth, seed, g.stream));
         g.stats.launches += 1;
     }
-    CK(cudaMalloc(&a.l1, ((bricks + 31) / 32) * 4));
-    CK(cudaMalloc(&a.table, bricks * 4));
-    CK(cudaMemsetAsync(a.l1, 0, ((bricks + 31) / 32) * 4, g.stream));
+    // the brick grid is stored with a one-brick border that marks "outside" (kernels.h, BrickVolume)
+    const uint32_t pbx = (width >> 3) + 2, pby = (height >> 3) + 2, pbz = (depth >> 3) + 2;
+    const size_t padded = (size_t)pbx * pby * pbz;
+    CK(cudaMalloc(&a.l1, ((padded + 31) / 32) * 4));
+    CK(cudaMalloc(&a.table, padded * 4));
+    CK(cudaMemsetAsync(a.l1, 0, ((padded + 31) / 32) * 4, g.stream));
+    CK(launch_brick_border(pbx, pby, pbz, a.l1, a.table, g.stream));
+    g.stats.launches += 1;
     // pass 1 counts the non-empty bricks, pass 2 fills the pool
     CK(cudaMemsetAsync(d_counter, 0, 4, g.stream));
     CK(launch_brick_build(kind, seed, width, height, depth, a.heights, a.l1, a.table, nullptr, 0, d_counter, g.stream));
@@ -635,7 +640,7 @@ extern "C" int32_t vt_add_volume_procedural(uint32_t kind, uint32_t width, uint3
     BrickVolume bv{};
     bv.l1 = a.l1; bv.table = a.table; bv.pool = a.pool; bv.heights = a.heights; bv.colors = nullptr;
     bv.kind = kind; bv.seed = seed;
-    bv.bx = width >> 3; bv.by = height >> 3; bv.bz = depth >> 3;
+    bv.bx = pbx; bv.by = pby; bv.bz = pbz;
     bv.n_bricks = n;
     CK(cudaMalloc(&a.d_desc, sizeof(BrickVolume)));
     CK(cudaMemcpyAsync(a.d_desc, &bv, sizeof bv, cudaMemcpyHostToDevice, g.stream));
@@ -673,19 +678,21 @@ extern "C" int32_t vt_add_volume_bricks(const uint32_t* brick_coords, const uint
         }
     }
     CK(cudaSetDevice(g.device));
-    const size_t bricks = (size_t)(width >> 3) * (height >> 3) * (depth >> 3);
     const size_t n1 = n_bricks ? n_bricks : 1;
     State::BrickAlloc a{};
     uint32_t* d_coords = nullptr;
     uint32_t* d_bad = nullptr;
     uint32_t bad = 0;
-    CK(cudaMalloc(&a.l1, ((bricks + 31) / 32) * 4));
-    CK(cudaMalloc(&a.table, bricks * 4));
+    const uint32_t pbx = (width >> 3) + 2, pby = (height >> 3) + 2, pbz = (depth >> 3) + 2;
+    const size_t padded = (size_t)pbx * pby * pbz;
+    CK(cudaMalloc(&a.l1, ((padded + 31) / 32) * 4));
+    CK(cudaMalloc(&a.table, padded * 4));
     CK(cudaMalloc(&a.pool, n1 * 64));
     CK(cudaMalloc(&a.colors, n1 * 4));
     CK(cudaMalloc(&d_coords, n1 * 12));
     CK(cudaMalloc(&d_bad, 4));
-    CK(cudaMemsetAsync(a.l1, 0, ((bricks + 31) / 32) * 4, g.stream));
+    CK(cudaMemsetAsync(a.l1, 0, ((padded + 31) / 32) * 4, g.stream));
+    CK(launch_brick_border(pbx, pby, pbz, a.l1, a.table, g.stream));
     CK(cudaMemsetAsync(d_bad, 0, 4, g.stream));
     // the inputs are only borrowed for the call (like add_texture's): synchronous copies
     CK(cudaMemcpy(a.pool, masks, n_bricks * 64, cudaMemcpyHostToDevice));
@@ -696,7 +703,7 @@ extern "C" int32_t vt_add_volume_bricks(const uint32_t* brick_coords, const uint
     CK(cudaStreamSynchronize(g.stream));
     cudaFree(d_coords);
     cudaFree(d_bad);
-    g.stats.launches += 1;
+    g.stats.launches += 2;
     if (bad) {
         cudaFree(a.l1); cudaFree(a.table); cudaFree(a.pool); cudaFree(a.colors);
         return fail("vt_add_volume_bricks: %u brick coordinates outside the volume", bad);
@@ -704,7 +711,7 @@ extern "C" int32_t vt_add_volume_bricks(const uint32_t* brick_coords, const uint
     BrickVolume bv{};
     bv.l1 = a.l1; bv.table = a.table; bv.pool = a.pool; bv.heights = nullptr; bv.colors = a.colors;
     bv.kind = kVolumeUploadedBricks; bv.seed = 0;
-    bv.bx = width >> 3; bv.by = height >> 3; bv.bz = depth >> 3;
+    bv.bx = pbx; bv.by = pby; bv.bz = pbz;
     bv.n_bricks = (uint32_t)n_bricks;
     CK(cudaMalloc(&a.d_desc, sizeof(BrickVolume)));
     CK(cudaMemcpy(a.d_desc, &bv, sizeof bv, cudaMemcpyHostToDevice));
