@@ -196,6 +196,12 @@ struct BrickWalk {
     uint32_t slot;
     uint32_t steps, last;
 };
+#ifndef VT_MARCH_BURST
+#define VT_MARCH_BURST 4 // DDA iterations between brick lookups, coherent rays (primary / shadow); 3, 6, 8 measured slower
+#endif
+#ifndef VT_RAY_BURST
+#define VT_RAY_BURST 6   // same, incoherent rays (trace_rays_kernel); 4 and 8 measured 5 % slower
+#endif
 static constexpr uint32_t kBrickMaskA = 0xFFF8FFF8u; // brick part of both packed words
 
 // literal transcription of the loop for rays with a zero direction component (0 * inf = NaN, :84), run to
@@ -315,25 +321,61 @@ __device__ __forceinline__ int brick_walk_begin(const BrickVolume& bv, uint32_t 
 // ONE lookup if the walk left it.  The lanes of a warp run the burst together and meet again for the
 // lookup, so its loads are issued by many lanes at once instead of by whichever lane happens to cross
 // a brick face in a given iteration.
+// One iteration in PTX (the selection the compiler makes from the C++ below it costs five more
+// instructions per iteration: selects + 3-input adds instead of predicated adds).  g = "this lane is
+// still inside the brick it knows to be empty"; a lane that has left idles through the rest of the
+// burst, predicated off, instead of jumping ahead to a lookup of its own.
+//   %0-2 side, %3-4 packed voxel, %5-6 voxel before the iteration, %7 steps, %8 left (out),
+//   %9-11 delta, %12-14 packed increments, %15-16 reference brick
+#define VT_BRICK_STEP_PTX                        \
+    "min.f32 m, %0, %1;\n"                       \
+    "min.f32 m, m, %2;\n"                        \
+    "setp.eq.and.f32 px, %0, m, g;\n"            \
+    "setp.eq.and.f32 py, %1, m, g;\n"            \
+    "setp.eq.and.f32 pz, %2, m, g;\n"            \
+    "@g mov.u32 %5, %3;\n"                       \
+    "@g mov.u32 %6, %4;\n"                       \
+    "@px add.rn.f32 %0, %0, %9;\n"               \
+    "@py add.rn.f32 %1, %1, %10;\n"              \
+    "@pz add.rn.f32 %2, %2, %11;\n"              \
+    "@px add.u32 %3, %3, %12;\n"                 \
+    "@py add.u32 %3, %3, %13;\n"                 \
+    "@pz add.u32 %4, %4, %14;\n"                 \
+    "@g add.u32 %7, %7, 1;\n"                    \
+    "xor.b32 t, %3, %15;\n"                      \
+    "xor.b32 u, %4, %16;\n"                      \
+    "or.b32 t, t, u;\n"                          \
+    "and.b32 t, t, 0xFFF8FFF8;\n"                \
+    "setp.eq.and.u32 g, t, 0, g;\n"
+#define VT_BRICK_BURST_ASM(STEPS)                                                                                         \
+    asm volatile("{\n"                                                                                                    \
+                 ".reg .pred g, px, py, pz;\n"                                                                            \
+                 ".reg .f32 m;\n"                                                                                         \
+                 ".reg .u32 t, u;\n"                                                                                      \
+                 "setp.eq.u32 g, 0, 0;\n" STEPS "selp.u32 %8, 0, 1, g;\n"                                                 \
+                 "}\n"                                                                                                    \
+                 : "+f"(k.sx), "+f"(k.sy), "+f"(k.sz), "+r"(k.a), "+r"(k.b), "+r"(k.pa), "+r"(k.pb), "+r"(k.steps), "=r"(left) \
+                 : "f"(r.delta[0]), "f"(r.delta[1]), "f"(r.delta[2]), "r"(k.ix), "r"(k.iy), "r"(k.iz), "r"(k.ref_a), "r"(k.ref_b))
+
 template <int kBurst>
 __device__ __forceinline__ int brick_walk_burst(const BrickVolume& bv, const Dda& r, BrickWalk& k) {
-    // Branch-free on purpose: a lane that has left its brick idles through the rest of the burst
-    // (predicated off) instead of jumping ahead to a lookup of its own.
-    bool go = true;
-#pragma unroll
-    for (int u = 0; u < kBurst; ++u) {
-        // no NaN: side <= min(other two) is side == min(all three); vec3(mask) * delta is a predicated add
-        const float m = fminf(fminf(k.sx, k.sy), k.sz); // :83
-        const bool m0 = go && k.sx == m, m1 = go && k.sy == m, m2 = go && k.sz == m;
-        if (go) { k.pa = k.a; k.pb = k.b; }
-        if (m0) { k.sx += r.delta[0]; k.a += k.ix; } // :84-85
-        if (m1) { k.sy += r.delta[1]; k.a += k.iy; }
-        if (m2) { k.sz += r.delta[2]; k.b += k.iz; }
-        k.steps += go ? 1u : 0u; // :86
-        // bits 16-18 of b are always 0: one mask serves both words
-        go = go && (((k.a ^ k.ref_a) | (k.b ^ k.ref_b)) & kBrickMaskA) == 0u;
-    }
-    return go ? 0 : brick_walk_lookup(bv, k);
+    static_assert(kBurst == 3 || kBurst == 4 || kBurst == 6 || kBurst == 8, "burst lengths with a PTX body");
+    // Per iteration (trace.frag:83-86), no NaN: side <= min(other two) is side == min(all three);
+    // vec3(mask) * delta is a predicated add; bits 16-18 of b are always 0, so one mask serves both words:
+    //     m = min(sx, sy, sz); m0 = go && sx == m; ...; if (go) { pa = a; pb = b; }
+    //     if (m0) { sx += delta[0]; a += ix; } ...; steps += go;
+    //     go = go && (((a ^ ref_a) | (b ^ ref_b)) & kBrickMaskA) == 0;
+    // The asm is volatile and `left` comes out of it, so the lookup is reached from ONE branch by all
+    // lanes that need it together.
+    uint32_t left;
+    if (kBurst == 3) VT_BRICK_BURST_ASM(VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX);
+    if (kBurst == 4) VT_BRICK_BURST_ASM(VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX);
+    if (kBurst == 6)
+        VT_BRICK_BURST_ASM(VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX);
+    if (kBurst == 8)
+        VT_BRICK_BURST_ASM(VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX
+                               VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX);
+    return left ? brick_walk_lookup(bv, k) : 0;
 }
 
 __device__ __forceinline__ void brick_walk_finish(const BrickWalk& k, bool hit, Dda& r) {
@@ -348,6 +390,6 @@ __device__ __forceinline__ void dda_march_bricks(const BrickVolume& bv, uint32_t
                                                  const float dir[3], bool has_start, const int32_t sv[3], Dda& r) {
     BrickWalk k;
     int status = brick_walk_begin(bv, W, H, D, pos, dir, has_start, sv, r, k);
-    while (status == 0) status = brick_walk_burst<4>(bv, r, k);
+    while (status == 0) status = brick_walk_burst<VT_MARCH_BURST>(bv, r, k);
     brick_walk_finish(k, status == 1, r);
 }

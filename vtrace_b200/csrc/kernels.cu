@@ -913,7 +913,7 @@ __global__ void __launch_bounds__(kBlockThreads) trace_rays_kernel(const __grid_
         const BrickVolume bv = *Ip->bricks;
         const uint32_t W = Ip->w, H = Ip->h, D = Ip->d;
         constexpr unsigned long long kChunk = 2048;
-        constexpr int kRayBurst = 4; // DDA iterations between brick lookups (see brick_walk_burst)
+        constexpr int kRayBurst = VT_RAY_BURST; // DDA iterations between brick lookups (see brick_walk_burst)
         const unsigned long long n_chunks = (n + kChunk - 1) / kChunk;
         unsigned long long chunk_next = 0, chunk_end = 0; // the warp's current range of ray ids
         bool more = true;
