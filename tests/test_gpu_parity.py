@@ -452,6 +452,68 @@ def test_paths_multi_instance_exact(scene, assets):
     scene.check_paths(P, V, 240, 160, spp=3, bounces=3, what="paths multi")
 
 
+def _grid_models(a, b):
+    models = []
+    for m in scenes.entity_grid(a, b):
+        m = m.reshape(4, 4).copy()
+        tid = int(m.reshape(16).view(np.uint32)[15])
+        m[3][3] = 1.0
+        models.append((m, tid))
+    return models
+
+
+def test_paths_world_grid_entity_grid(scene, assets):
+    """Bounce rays over the 11x11 entity grid go through the world-space instance grid (world_grid.cuh): the
+    result must be what the oracle's loop over every instance gives, and what the same kernel gives with the
+    grid (and the screen bins) switched off."""
+    a = scene.add(assets["Treasure"])
+    b = scene.add(assets["AncientTemple"])
+    scene.set_instances(_grid_models(a, b))
+    P = glm.perspective(glm.REFERENCE_FOV, 240 / 136, glm.REFERENCE_NEAR, glm.REFERENCE_FAR)
+    V = glm.look_at((0.0, -2.0, 0.0), (3.0, -5.0, 2.0), (0.0, 1.0, 0.0))
+    got, st = scene.check_paths(P, V, 240, 136, spp=3, bounces=4, what="entity grid paths, world grid")
+    plain, _ = scene.check_paths(P, V, 240, 136, spp=3, bounces=4, flags=abi.FLAG_NO_BINNING, what="entity grid paths, every instance")
+    assert np.array_equal(got, plain)
+    assert st.rays > 240 * 136 * 3
+
+
+def test_paths_world_grid_mixed_sizes(scene, assets):
+    """Instances of very different sizes, rotated and scaled, touching and overlapping: a large slab spans many
+    cells, small volumes sit on it and inside each other's boxes."""
+    rng = np.random.default_rng(11)
+    t = scene.add(assets["Treasure"])
+    u = scene.add(RawVolume(make_volume(rng, 12, 9, 14, fill=0.45), 12, 9, 14))
+    models = [(glm.scale(glm.translate(glm.identity(), (0.0, 0.9, 0.0)), (9.0, 0.6, 9.0)), u)]  # the slab (+Y is down)
+    for i in range(14):
+        pos = (float(rng.uniform(-3.5, 3.5)), float(rng.uniform(-0.6, 0.3)), float(rng.uniform(-3.5, 3.5)))
+        m = glm.translate(glm.identity(), pos)
+        m = glm.rotate(m, float(rng.uniform(-1.5, 1.5)), (float(rng.uniform(-1, 1)), 1.0, float(rng.uniform(-1, 1))))
+        m = glm.scale(m, (float(rng.uniform(0.4, 1.6)), float(rng.uniform(0.4, 1.6)), float(rng.uniform(0.4, 1.6))))
+        models.append((m, t if i % 2 else u))
+    models.append((glm.translate(glm.identity(), (0.25, -0.2, 0.1)), t))   # overlaps its neighbours' boxes
+    models.append((glm.translate(glm.identity(), (0.25, -0.2, 0.1)), u))   # coincident boxes: ties go to the lower index
+    scene.set_instances(models)
+    P, V = scenes.camera(200, 150, eye=(4.5, -3.0, 5.0))
+    got, _ = scene.check_paths(P, V, 200, 150, spp=3, bounces=4, what="mixed sizes, world grid")
+    plain, _ = scene.check_paths(P, V, 200, 150, spp=3, bounces=4, flags=abi.FLAG_NO_BINNING, what="mixed sizes, every instance")
+    assert np.array_equal(got, plain)
+
+
+def test_paths_world_grid_overflow_falls_back(renderer, oracle, assets, monkeypatch):
+    """A list that is too small makes the frame loop over every instance (still exact); the next frame has room."""
+    monkeypatch.setenv("VT_WORLD_CAP", "50")
+    renderer.reset()
+    sc = Scene(renderer, oracle)
+    a = sc.add(assets["Treasure"])
+    b = sc.add(assets["AncientTemple"])
+    sc.set_instances(_grid_models(a, b))
+    P = glm.perspective(glm.REFERENCE_FOV, 160 / 90, glm.REFERENCE_NEAR, glm.REFERENCE_FAR)
+    V = glm.look_at((0.0, -2.0, 0.0), (3.0, -5.0, 2.0), (0.0, 1.0, 0.0))
+    first, _ = sc.check_paths(P, V, 160, 90, spp=2, bounces=3, what="world grid overflow, first frame")
+    second, _ = sc.check_paths(P, V, 160, 90, spp=2, bounces=3, what="world grid overflow, second frame")
+    assert np.array_equal(first, second)
+
+
 def test_paths_sample_sharding_is_exact(renderer, scene, assets):
     """spp split over ranks: integer accumulation makes 1-rank == sum of N ranks."""
     t = scene.add(assets["AncientTemple"])

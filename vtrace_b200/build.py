@@ -17,7 +17,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "librender.so")
 SOURCES = ["kernels.cu", "render_abi.cu"]
-HEADERS = [os.path.join(CSRC, "kernels.h"), os.path.join(CSRC, "paths_wave.cuh"), os.path.join(CSRC, "bricks.cuh"), os.path.join(ROOT, "include", "vtrace_abi.h")]
+HEADERS = [os.path.join(CSRC, "kernels.h"), os.path.join(CSRC, "paths_wave.cuh"), os.path.join(CSRC, "bricks.cuh"), os.path.join(CSRC, "world_grid.cuh"), os.path.join(ROOT, "include", "vtrace_abi.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -991,6 +991,8 @@ cudaError_t launch_trace_rays(const FrameParams& fp, const InstUniforms* inst, c
     return cudaGetLastError();
 }
 
+#include "world_grid.cuh"
+
 struct PathHit {
     bool hit;
     uint32_t instance;
@@ -1002,29 +1004,45 @@ struct PathHit {
 // that order whose DDA hits wins.  cam != nullptr: camera ray (o = eye in model space,
 // d = dirm * (x_ndc, y_ndc, 1)); else world ray (o = Mi*(ow,1), d = Mi*(dw,0)).
 template <bool kSmem>
-__device__ void trace_world(const FrameParams& fp, const InstUniforms* __restrict__ inst, const BinTable& bins,
+__device__ void trace_world(const FrameParams& fp, const InstUniforms* __restrict__ inst, const BinTable& bins, const WorldGridTable& wg,
                             const uint32_t* mask_base, uint32_t skip, const float* cam, int px, int py, const float ow[3],
                             const float dw[3], PathHit& out, unsigned long long& iters) {
     out.hit = false;
     float last_t = -INFINITY;
     uint32_t last_j = 0;
     bool have_last = false;
+    // camera rays only need the instances binned to their pixel; world rays the ones registered in the grid
+    // cells they pass (world_grid.cuh); without either, every instance is visited
+    const bool binned = cam && bins.enabled;
+    const bool gridded = !cam && wg.enabled && __ldg(&wg.hdr->overflow) == 0u;
+    WorldWalk walk;
+    if (gridded) {
+        const WorldGrid g = *wg.hdr;
+        world_walk_begin(g, ow, dw, walk);
+    }
     for (;;) {
         bool found = false;
         float best_t = 0.0f;
         uint32_t best_j = 0;
         int best_axis = 0;
         float bo[3] = {0, 0, 0}, bd[3] = {0, 0, 0};
-        // camera rays only need the instances binned to their pixel; world rays visit every instance
         uint32_t k_begin = 0, k_end = fp.n_inst;
-        const bool binned = cam && bins.enabled;
+        float t_lim = INFINITY; // grid: candidates entered beyond the current cell wait for their own cell
+        bool last_cell = true;
+        const uint32_t* list = nullptr;
         if (binned) {
             const uint32_t bin = ((uint32_t)py >> kBinShift) * bins.bins_x + ((uint32_t)px >> kBinShift);
             k_begin = __ldg(bins.offset + bin);
             k_end = k_begin + __ldg(bins.count + bin);
+            list = bins.list;
+        } else if (gridded) {
+            const uint32_t cell = world_walk_cell(walk, t_lim, last_cell);
+            k_begin = __ldg(wg.offset + cell);
+            k_end = k_begin + __ldg(wg.count + cell);
+            list = wg.list;
         }
         for (uint32_t k = k_begin; k < k_end; ++k) {
-            const uint32_t j = binned ? __ldg(bins.list + k) : k;
+            const uint32_t j = list ? __ldg(list + k) : k;
             const InstUniforms* J = inst + j;
             if (j == skip || !J->valid) continue;
             float o[3], d[3];
@@ -1049,13 +1067,18 @@ __device__ void trace_world(const FrameParams& fp, const InstUniforms* __restric
             int axis;
             if (!slab_unit_cube(o, lo3, hi3, d, tn, axis)) continue;
             if (have_last && !(tn > last_t || (tn == last_t && j > last_j))) continue;
-            if (!found || tn < best_t) {
+            if (tn > t_lim) continue;
+            if (!found || tn < best_t || (tn == best_t && j < best_j)) { // (grid lists are unordered)
                 found = true; best_t = tn; best_j = j; best_axis = axis;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) { bo[k] = o[k]; bd[k] = d[k]; }
             }
         }
-        if (!found) return;
+        if (!found) {
+            if (last_cell) return;
+            world_walk_next(walk); // nothing (more) entered inside this cell: on to the next one
+            continue;
+        }
         float mp[3], pos[3];
         entry_point(bo, bd, best_t, best_axis, mp);
         const InstUniforms* J = inst + best_j;
@@ -1075,7 +1098,7 @@ __device__ void trace_world(const FrameParams& fp, const InstUniforms* __restric
 }
 
 template <bool kSmem>
-__device__ void trace_path(const FrameParams& fp, const InstUniforms* __restrict__ inst, const BinTable& bins,
+__device__ void trace_path(const FrameParams& fp, const InstUniforms* __restrict__ inst, const BinTable& bins, const WorldGridTable& wg,
                            const uint32_t* mask_base, const float* __restrict__ dec, int px, int py, uint32_t sample, float L[3],
                            unsigned long long& rays, unsigned long long& iters) {
     Rng rng;
@@ -1086,7 +1109,7 @@ __device__ void trace_path(const FrameParams& fp, const InstUniforms* __restrict
     PathHit cur;
     const float cam[2] = {fx * fp.sxn - 1.0f, fy * fp.syn - 1.0f};
     const float zero3[3] = {0.0f, 0.0f, 0.0f};
-    trace_world<kSmem>(fp, inst, bins, mask_base, 0xFFFFFFFFu, cam, px, py, zero3, zero3, cur, iters);
+    trace_world<kSmem>(fp, inst, bins, wg, mask_base, 0xFFFFFFFFu, cam, px, py, zero3, zero3, cur, iters);
     rays += 1;
     const float sky[3] = {53.0f / 100.0f, 81.0f / 100.0f, 92.0f / 100.0f}; // lib/command.c:57-59
     float thr[3] = {1.0f, 1.0f, 1.0f};
@@ -1157,7 +1180,7 @@ __device__ void trace_path(const FrameParams& fp, const InstUniforms* __restrict
                 ow[k] = ((J->M[0 * 3 + k] * pm[0] + J->M[1 * 3 + k] * pm[1]) + J->M[2 * 3 + k] * pm[2]) + J->M[3 * 3 + k];
                 dw[k] = (J->M[0 * 3 + k] * dm[0] + J->M[1 * 3 + k] * dm[1]) + J->M[2 * 3 + k] * dm[2];
             }
-            trace_world<kSmem>(fp, inst, bins, mask_base, cur.instance, nullptr, 0, 0, ow, dw, next, iters);
+            trace_world<kSmem>(fp, inst, bins, wg, mask_base, cur.instance, nullptr, 0, 0, ow, dw, next, iters);
         }
         cur = next;
     }
@@ -1166,7 +1189,7 @@ __device__ void trace_path(const FrameParams& fp, const InstUniforms* __restrict
 template <bool kSmem>
 __global__ void __launch_bounds__(kBlockThreads) trace_paths_kernel(const __grid_constant__ FrameParams fp,
                                                                     const InstUniforms* __restrict__ inst, const BinTable bins,
-                                                                    const uint32_t* __restrict__ mask_arena,
+                                                                    const WorldGridTable wg, const uint32_t* __restrict__ mask_arena,
                                                                     uint32_t arena_words, SrgbTables lut, FrameBuffers fb) {
     stage_tables<kSmem>(mask_arena, arena_words, lut.decode);
     const uint32_t* mask_base = mask_arena;
@@ -1216,7 +1239,7 @@ __global__ void __launch_bounds__(kBlockThreads) trace_paths_kernel(const __grid
         } else {
             for (uint32_t k = 0; k < fp.spp; ++k) {
                 float L[3];
-                trace_path<kSmem>(fp, inst, bins, mask_base, dec, px, py, fp.sample_first + k * fp.sample_stride, L, rays, iters);
+                trace_path<kSmem>(fp, inst, bins, wg, mask_base, dec, px, py, fp.sample_first + k * fp.sample_stride, L, rays, iters);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const float q = L[c] * 16777216.0f;
@@ -1623,7 +1646,7 @@ cudaError_t launch_trace_primary(const FrameParams& fp, const InstUniforms* inst
     return cudaGetLastError();
 }
 
-cudaError_t launch_trace_paths(const FrameParams& fp, const InstUniforms* inst, BinTable bins, const uint32_t* mask_arena,
+cudaError_t launch_trace_paths(const FrameParams& fp, const InstUniforms* inst, BinTable bins, WorldGridTable wg, const uint32_t* mask_arena,
                                uint32_t arena_words, bool masks_in_smem, SrgbTables lut, FrameBuffers fb, int sm_count,
                                cudaStream_t stream) {
     const int n_tiles = ((fp.width + kTileW - 1) / kTileW) * ((fp.height + kTileH - 1) / kTileH);
@@ -1653,10 +1676,10 @@ cudaError_t launch_trace_paths(const FrameParams& fp, const InstUniforms* inst, 
     }
     if (masks_in_smem) {
         const int grid = persistent_grid(trace_paths_kernel<true>, smem, sm_count, n_tiles);
-        trace_paths_kernel<true><<<grid, kBlockThreads, smem, stream>>>(fp, inst, bins, mask_arena, arena_words, lut, fb);
+        trace_paths_kernel<true><<<grid, kBlockThreads, smem, stream>>>(fp, inst, bins, wg, mask_arena, arena_words, lut, fb);
     } else {
         const int grid = persistent_grid(trace_paths_kernel<false>, smem, sm_count, n_tiles);
-        trace_paths_kernel<false><<<grid, kBlockThreads, smem, stream>>>(fp, inst, bins, mask_arena, arena_words, lut, fb);
+        trace_paths_kernel<false><<<grid, kBlockThreads, smem, stream>>>(fp, inst, bins, wg, mask_arena, arena_words, lut, fb);
     }
     return cudaGetLastError();
 }

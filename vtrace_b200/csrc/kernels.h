@@ -121,6 +121,27 @@ struct BinTable {
 };
 static constexpr uint32_t kBinShift = 4; // 16x16 pixels
 
+// World-space uniform grid over the instances' bounding boxes: narrows the instance loop of the path
+// tracer's bounce rays (world_grid.cuh).  The header is written on the device every frame.
+struct WorldGrid {
+    float lo[3], cell[3], inv_cell[3];
+    uint32_t res[3];
+    uint32_t n_cells;
+    uint32_t total;    // list entries needed
+    uint32_t overflow; // 1: the lists did not fit (or a model matrix is not finite) -> full instance loop this frame
+    uint32_t pad;
+};
+struct WorldGridTable {
+    const WorldGrid* hdr;
+    const uint32_t* offset; // per cell: first entry in `list`
+    const uint32_t* count;  // per cell: number of entries
+    const uint32_t* list;   // instance indices
+    uint32_t enabled;       // 0: loop over all instances
+    uint32_t pad;
+};
+static constexpr uint32_t kWorldGridMaxRes = 64, kWorldGridMaxCells = 64 * 64 * 64;
+static constexpr uint32_t kWorldGridMinInstances = 8;
+
 struct SrgbTables {
     const float* decode;    // 256
     const float* threshold; // 256
@@ -143,7 +164,9 @@ cudaError_t launch_bin_instances(const InstUniforms* inst, uint32_t n_inst, uint
 cudaError_t launch_trace_primary(const FrameParams& fp, const InstUniforms* inst, BinTable bins, const uint32_t* mask_arena,
                                  uint32_t arena_words, bool masks_in_smem, SrgbTables lut, FrameBuffers fb,
                                  int sm_count, cudaStream_t stream);
-cudaError_t launch_trace_paths(const FrameParams& fp, const InstUniforms* inst, BinTable bins, const uint32_t* mask_arena,
+cudaError_t launch_world_grid(const InstUniforms* inst, uint32_t n_inst, float* aabb, WorldGrid* hdr, uint32_t* offset, uint32_t* count,
+                              uint32_t* cursor, uint32_t* list, uint32_t capacity, cudaStream_t stream);
+cudaError_t launch_trace_paths(const FrameParams& fp, const InstUniforms* inst, BinTable bins, WorldGridTable wg, const uint32_t* mask_arena,
                                uint32_t arena_words, bool masks_in_smem, SrgbTables lut, FrameBuffers fb,
                                int sm_count, cudaStream_t stream);
 // procedural brick volumes: column heights, then count / fill passes over all bricks

@@ -55,6 +55,15 @@ struct State {
     uint32_t* h_bin_cursor = nullptr; // pinned
     uint32_t bin_cap_bins = 0, bin_cap_list = 0;
     bool bins_used = false;
+    // world-space instance grid for the path tracer's bounce rays (world_grid.cuh)
+    float* d_world_aabb = nullptr;
+    uint32_t world_aabb_cap = 0;
+    WorldGrid* d_world_hdr = nullptr;
+    WorldGrid* h_world_hdr = nullptr; // pinned copy of the last frame's header
+    uint32_t* d_world_cells = nullptr; // offset | count | cursor, kWorldGridMaxCells each
+    uint32_t* d_world_list = nullptr;
+    uint32_t world_list_cap = 0;
+    bool world_used = false;
     float last_P[16] = {0}, last_V[16] = {0};
     bool last_clear = false, last_resolve = false;
 
@@ -213,6 +222,16 @@ int finish_frame() {
         CK(cudaStreamSynchronize(g.stream));
         g.frame_pending = false;
     }
+    // the world grid only reports that its lists did not fit (that frame looped over all instances, which is
+    // exact): give the next frame room
+    if (g.world_used && g.h_world_hdr->total > g.world_list_cap) {
+        const uint32_t need = g.h_world_hdr->total + g.h_world_hdr->total / 2;
+        cudaFree(g.d_world_list);
+        g.d_world_list = nullptr;
+        g.world_list_cap = 0;
+        CK(cudaMalloc(&g.d_world_list, (size_t)need * 4));
+        g.world_list_cap = need;
+    }
     for (; g.ring_done < g.ring_head; ++g.ring_done) {
         const uint32_t slot = (uint32_t)(g.ring_done % State::kRing);
         float ms = 0.0f;
@@ -338,6 +357,34 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
         bins.bins_x = bx; bins.bins_y = by; bins.enabled = 1;
     }
 
+    // path tracing over many instances: a world-space grid so that bounce rays only test the instances near them
+    WorldGridTable wg{};
+    g.world_used = g.cfg.mode == VT_MODE_PATHS && g.inst_count >= kWorldGridMinInstances && !(g.cfg.flags & VT_FLAG_NO_BINNING);
+    if (g.world_used) {
+        if (g.inst_count > g.world_aabb_cap) {
+            CK(cudaStreamSynchronize(g.stream));
+            cudaFree(g.d_world_aabb);
+            g.d_world_aabb = nullptr;
+            g.world_aabb_cap = 0;
+            CK(cudaMalloc(&g.d_world_aabb, (size_t)g.inst_count * 6 * sizeof(float)));
+            g.world_aabb_cap = g.inst_count;
+        }
+        if (!g.d_world_cells) CK(cudaMalloc(&g.d_world_cells, (size_t)kWorldGridMaxCells * 3 * 4));
+        if (!g.d_world_list) {
+            const uint32_t cap = env_u32("VT_WORLD_CAP", g.inst_count * 16 > (1u << 16) ? g.inst_count * 16 : (1u << 16));
+            CK(cudaMalloc(&g.d_world_list, (size_t)cap * 4));
+            g.world_list_cap = cap;
+        }
+        uint32_t* offset = g.d_world_cells;
+        uint32_t* count = g.d_world_cells + kWorldGridMaxCells;
+        uint32_t* cursor = g.d_world_cells + 2 * kWorldGridMaxCells;
+        CK(launch_world_grid(g.d_iu, g.inst_count, g.d_world_aabb, g.d_world_hdr, offset, count, cursor, g.d_world_list,
+                             g.world_list_cap, g.stream));
+        CK(cudaMemcpyAsync(g.h_world_hdr, g.d_world_hdr, sizeof(WorldGrid), cudaMemcpyDeviceToHost, g.stream));
+        g.stats.launches += 4;
+        wg.hdr = g.d_world_hdr; wg.offset = offset; wg.count = count; wg.list = g.d_world_list; wg.enabled = 1;
+    }
+
     const bool in_smem = !(g.cfg.flags & VT_FLAG_FORCE_GLOBAL_MASKS) && g.arena_words > 0 &&
                          (size_t)g.arena_words * 4 <= kSmemMaskBudget &&
                          trace_smem_bytes(g.arena_words, true) <= (size_t)g.max_smem_optin;
@@ -366,7 +413,7 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
         if (clear_accum)
             CK(cudaMemsetAsync(g.d_accum, 0, (size_t)g.cfg.width * g.cfg.height * 3 * sizeof(unsigned long long), g.stream));
         CK(cudaEventRecord(g.ev_trace0[slot], g.stream));
-        CK(launch_trace_paths(fp, g.d_iu, bins, g.d_arena, g.arena_words, in_smem, lut, fb, g.sm_count, g.stream));
+        CK(launch_trace_paths(fp, g.d_iu, bins, wg, g.d_arena, g.arena_words, in_smem, lut, fb, g.sm_count, g.stream));
         CK(cudaEventRecord(g.ev_trace1[slot], g.stream));
         g.stats.launches += 1;
         if (fused) { // stream this rank's sums of the covered rectangle into its slot in the root's memory
@@ -470,6 +517,9 @@ extern "C" uint64_t entry(void) {
     CKE(cudaMemcpy(g.d_dec, dec, sizeof dec, cudaMemcpyHostToDevice));
     CKE(cudaMemcpy(g.d_thr, thr, sizeof thr, cudaMemcpyHostToDevice));
     CKE(cudaMalloc(&g.d_stats, 4 * sizeof(unsigned long long)));
+    CKE(cudaMalloc(&g.d_world_hdr, sizeof(WorldGrid)));
+    CKE(cudaMallocHost(&g.h_world_hdr, sizeof(WorldGrid)));
+    memset(g.h_world_hdr, 0, sizeof(WorldGrid));
     CKE(cudaMalloc(&g.d_bin_cursor, 4));
     CKE(cudaMallocHost(&g.h_bin_cursor, 4));
     *g.h_bin_cursor = 0;
@@ -765,6 +815,10 @@ extern "C" void cleanup(void) {
     cudaFree(g.d_rec); cudaFree(g.d_color); cudaFree(g.d_depth); cudaFree(g.d_accum_own); cudaFree(g.d_stats);
     cudaFree(g.d_bin_offset); cudaFree(g.d_bin_count); cudaFree(g.d_bin_list); cudaFree(g.d_bin_cursor);
     if (g.h_bin_cursor) cudaFreeHost(g.h_bin_cursor);
+    cudaFree(g.d_world_aabb); cudaFree(g.d_world_hdr); cudaFree(g.d_world_cells); cudaFree(g.d_world_list);
+    if (g.h_world_hdr) cudaFreeHost(g.h_world_hdr);
+    g.d_world_aabb = nullptr; g.d_world_hdr = nullptr; g.h_world_hdr = nullptr; g.d_world_cells = g.d_world_list = nullptr;
+    g.world_aabb_cap = g.world_list_cap = 0; g.world_used = false;
     if (g.h_inst) cudaFreeHost(g.h_inst);
     if (g.h_tex_staging) cudaFreeHost(g.h_tex_staging);
     if (g.h_stats) cudaFreeHost(g.h_stats);
