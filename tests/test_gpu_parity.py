@@ -514,6 +514,32 @@ def test_paths_world_grid_overflow_falls_back(renderer, oracle, assets, monkeypa
     assert np.array_equal(first, second)
 
 
+def test_paths_over_brick_volumes(pscene, assets):
+    """Path tracing through procedural / uploaded brick volumes, alone and next to a dense volume (the general
+    path kernel marches every kind of volume through march_instance())."""
+    h = pscene.add_procedural(abi.VOLUME_HEIGHTMAP, 128, 64, 128, 4)
+    pscene.set_instances([(glm.identity(), h)])
+    P, V = scenes.camera(240, 136, eye=(0.9, -0.8, 0.9))
+    got, st = pscene.check_paths(P, V, 240, 136, spp=3, bounces=4, what="paths, heightmap bricks")
+    assert st.iterations > 240 * 136 * 3
+    b = pscene.add_procedural(abi.VOLUME_SPARSE_BRICKS, 64, 64, 64, 2)
+    d = pscene.add(assets["Treasure"])
+    pscene.set_instances([(glm.translate(glm.identity(), (-1.1, 0.0, 0.0)), b), (glm.identity(), d),
+                          (glm.translate(glm.identity(), (1.1, 0.0, 0.2)), h)])
+    P, V = scenes.camera(240, 136, eye=(0.4, -1.0, 2.4))
+    pscene.check_paths(P, V, 240, 136, spp=3, bounces=3, what="paths, bricks + dense + heightmap")
+    rng = np.random.default_rng(8)
+    coords = np.array([(x, y, z) for z in range(4) for y in range(4) for x in range(4)], dtype=np.uint32)[rng.random(64) < 0.4]
+    masks = rng.integers(0, 2**32, size=(len(coords), 16), dtype=np.uint64).astype(np.uint32)
+    colors = rng.integers(0, 256, size=(len(coords), 4), dtype=np.uint8)
+    rid = pscene.r.add_volume_bricks(coords, masks, colors, 32, 32, 32)
+    oid = pscene.o.add_volume_bricks(coords, masks, colors, 32, 32, 32)
+    pscene.tex_map[oid] = rid
+    pscene.set_instances([(glm.identity(), oid)])
+    P, V = scenes.camera(160, 120, eye=(0.9, -0.7, 0.9))
+    pscene.check_paths(P, V, 160, 120, spp=4, bounces=4, what="paths, uploaded bricks")
+
+
 def test_paths_sample_sharding_is_exact(renderer, scene, assets):
     """spp split over ranks: integer accumulation makes 1-rank == sum of N ranks."""
     t = scene.add(assets["AncientTemple"])

@@ -32,6 +32,7 @@ CONFIGS = {
     # extension scenes (procedural brick volumes)
     "heightmap_4k": ("heightmap1024", 3840, 2160, abi.MODE_PRIMARY, 0),        # configs[3]: primary + shadow rays
     "sparse_rays": ("sparse4096", 8192, 8192, abi.MODE_RAYS, 0),               # configs[4]: 2^26 incoherent rays
+    "heightmap_paths": ("heightmap1024", 1920, 1080, abi.MODE_PATHS, 8),       # the configs[3] volume, path traced
 }
 
 
@@ -60,7 +61,8 @@ def main():
             r.add_volume_procedural(abi.VOLUME_HEIGHTMAP, 1024, 1024, 1024, 1)
             r.update_instances_raw(scenes.single_instance(0))
             P, V = scenes.camera(w, h, eye=(0.9, -0.8, 0.9))
-            args.flags |= abi.FLAG_SHADOW_RAYS | abi.FLAG_NO_HIT_RECORDS * 0
+            if mode == abi.MODE_PRIMARY:
+                args.flags |= abi.FLAG_SHADOW_RAYS
         elif asset == "sparse4096":
             r.add_volume_procedural(abi.VOLUME_SPARSE_BRICKS, 4096, 4096, 4096, 2)
             r.update_instances_raw(scenes.single_instance(0))

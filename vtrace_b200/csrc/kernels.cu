@@ -1003,7 +1003,7 @@ struct PathHit {
 // Nearest instance along a ray by box-entry parameter (ties: lower index); the first instance in
 // that order whose DDA hits wins.  cam != nullptr: camera ray (o = eye in model space,
 // d = dirm * (x_ndc, y_ndc, 1)); else world ray (o = Mi*(ow,1), d = Mi*(dw,0)).
-template <bool kSmem>
+template <bool kSmem, bool kBricks>
 __device__ void trace_world(const FrameParams& fp, const InstUniforms* __restrict__ inst, const BinTable& bins, const WorldGridTable& wg,
                             const uint32_t* mask_base, uint32_t skip, const float* cam, int px, int py, const float ow[3],
                             const float dw[3], PathHit& out, unsigned long long& iters) {
@@ -1085,9 +1085,8 @@ __device__ void trace_world(const FrameParams& fp, const InstUniforms* __restric
         const float size[3] = {(float)(int32_t)J->w, (float)(int32_t)J->h, (float)(int32_t)J->d};
 #pragma unroll
         for (int k = 0; k < 3; ++k) pos[k] = (mp[k] + 0.5f) * size[k];
-        Vol vol{J->w, J->h, J->d, J->xb, J->yb, J->mask_off, mask_base};
         const int32_t none[3] = {0, 0, 0};
-        dda_march<kSmem>(vol, pos, bd, false, none, out.dda);
+        march_instance<kSmem, kBricks>(J, mask_base, pos, bd, false, none, out.dda);
         iters += out.dda.steps;
         if (out.dda.hit) {
             out.hit = true; out.instance = best_j; out.entry_axis = best_axis;
@@ -1097,7 +1096,7 @@ __device__ void trace_world(const FrameParams& fp, const InstUniforms* __restric
     }
 }
 
-template <bool kSmem>
+template <bool kSmem, bool kBricks>
 __device__ void trace_path(const FrameParams& fp, const InstUniforms* __restrict__ inst, const BinTable& bins, const WorldGridTable& wg,
                            const uint32_t* mask_base, const float* __restrict__ dec, int px, int py, uint32_t sample, float L[3],
                            unsigned long long& rays, unsigned long long& iters) {
@@ -1109,7 +1108,7 @@ __device__ void trace_path(const FrameParams& fp, const InstUniforms* __restrict
     PathHit cur;
     const float cam[2] = {fx * fp.sxn - 1.0f, fy * fp.syn - 1.0f};
     const float zero3[3] = {0.0f, 0.0f, 0.0f};
-    trace_world<kSmem>(fp, inst, bins, wg, mask_base, 0xFFFFFFFFu, cam, px, py, zero3, zero3, cur, iters);
+    trace_world<kSmem, kBricks>(fp, inst, bins, wg, mask_base, 0xFFFFFFFFu, cam, px, py, zero3, zero3, cur, iters);
     rays += 1;
     const float sky[3] = {53.0f / 100.0f, 81.0f / 100.0f, 92.0f / 100.0f}; // lib/command.c:57-59
     float thr[3] = {1.0f, 1.0f, 1.0f};
@@ -1122,7 +1121,7 @@ __device__ void trace_path(const FrameParams& fp, const InstUniforms* __restrict
         }
         const InstUniforms* J = inst + cur.instance;
         const Dda& r = cur.dda;
-        const uchar4 s = fetch_texel(J->rgba, J->w, J->h, J->d, J->remap_identity != 0, r.v);
+        const uchar4 s = instance_texel<kBricks>(J, r.v);
         thr[0] = thr[0] * dec[s.x];
         thr[1] = thr[1] * dec[s.y];
         thr[2] = thr[2] * dec[s.z];
@@ -1167,8 +1166,7 @@ __device__ void trace_path(const FrameParams& fp, const InstUniforms* __restrict
         next.hit = false;
         next.instance = cur.instance;
         next.entry_axis = a;
-        Vol vol{J->w, J->h, J->d, J->xb, J->yb, J->mask_off, mask_base};
-        dda_march<kSmem>(vol, p0, dn, true, sv, next.dda);
+        march_instance<kSmem, kBricks>(J, mask_base, p0, dn, true, sv, next.dda);
         iters += next.dda.steps;
         next.hit = next.dda.hit;
         if (!next.hit && fp.n_inst > 1) {
@@ -1180,13 +1178,13 @@ __device__ void trace_path(const FrameParams& fp, const InstUniforms* __restrict
                 ow[k] = ((J->M[0 * 3 + k] * pm[0] + J->M[1 * 3 + k] * pm[1]) + J->M[2 * 3 + k] * pm[2]) + J->M[3 * 3 + k];
                 dw[k] = (J->M[0 * 3 + k] * dm[0] + J->M[1 * 3 + k] * dm[1]) + J->M[2 * 3 + k] * dm[2];
             }
-            trace_world<kSmem>(fp, inst, bins, wg, mask_base, cur.instance, nullptr, 0, 0, ow, dw, next, iters);
+            trace_world<kSmem, kBricks>(fp, inst, bins, wg, mask_base, cur.instance, nullptr, 0, 0, ow, dw, next, iters);
         }
         cur = next;
     }
 }
 
-template <bool kSmem>
+template <bool kSmem, bool kBricks>
 __global__ void __launch_bounds__(kBlockThreads) trace_paths_kernel(const __grid_constant__ FrameParams fp,
                                                                     const InstUniforms* __restrict__ inst, const BinTable bins,
                                                                     const WorldGridTable wg, const uint32_t* __restrict__ mask_arena,
@@ -1239,7 +1237,7 @@ __global__ void __launch_bounds__(kBlockThreads) trace_paths_kernel(const __grid
         } else {
             for (uint32_t k = 0; k < fp.spp; ++k) {
                 float L[3];
-                trace_path<kSmem>(fp, inst, bins, wg, mask_base, dec, px, py, fp.sample_first + k * fp.sample_stride, L, rays, iters);
+                trace_path<kSmem, kBricks>(fp, inst, bins, wg, mask_base, dec, px, py, fp.sample_first + k * fp.sample_stride, L, rays, iters);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const float q = L[c] * 16777216.0f;
@@ -1605,7 +1603,9 @@ cudaError_t configure_kernels(int max_smem_optin) {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(trace_primary_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(trace_paths_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    e = cudaFuncSetAttribute(trace_paths_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(trace_paths_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(trace_paths_single_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     if (e != cudaSuccess) return e;
@@ -1651,6 +1651,16 @@ cudaError_t launch_trace_paths(const FrameParams& fp, const InstUniforms* inst, 
                                cudaStream_t stream) {
     const int n_tiles = ((fp.width + kTileW - 1) / kTileW) * ((fp.height + kTileH - 1) / kTileH);
     const size_t smem = trace_smem_bytes(arena_words, masks_in_smem);
+    if (fp.any_bricks) { // scenes with brick volumes: the general kernel, marching through march_instance()
+        if (masks_in_smem) {
+            const int grid = persistent_grid(trace_paths_kernel<true, true>, smem, sm_count, n_tiles);
+            trace_paths_kernel<true, true><<<grid, kBlockThreads, smem, stream>>>(fp, inst, bins, wg, mask_arena, arena_words, lut, fb);
+        } else {
+            const int grid = persistent_grid(trace_paths_kernel<false, true>, smem, sm_count, n_tiles);
+            trace_paths_kernel<false, true><<<grid, kBlockThreads, smem, stream>>>(fp, inst, bins, wg, mask_arena, arena_words, lut, fb);
+        }
+        return cudaGetLastError();
+    }
     if (fp.n_inst == 1 && !(fp.flags & (VT_FLAG_PERSISTENT_LANES | VT_FLAG_PER_PIXEL_PATHS))) {
         // single-instance scenes: warp-local wavefront engine (paths_wave.cuh)
         const size_t wsmem = wave_smem_bytes(arena_words, masks_in_smem);
@@ -1675,11 +1685,11 @@ cudaError_t launch_trace_paths(const FrameParams& fp, const InstUniforms* inst, 
         return cudaGetLastError();
     }
     if (masks_in_smem) {
-        const int grid = persistent_grid(trace_paths_kernel<true>, smem, sm_count, n_tiles);
-        trace_paths_kernel<true><<<grid, kBlockThreads, smem, stream>>>(fp, inst, bins, wg, mask_arena, arena_words, lut, fb);
+        const int grid = persistent_grid(trace_paths_kernel<true, false>, smem, sm_count, n_tiles);
+        trace_paths_kernel<true, false><<<grid, kBlockThreads, smem, stream>>>(fp, inst, bins, wg, mask_arena, arena_words, lut, fb);
     } else {
-        const int grid = persistent_grid(trace_paths_kernel<false>, smem, sm_count, n_tiles);
-        trace_paths_kernel<false><<<grid, kBlockThreads, smem, stream>>>(fp, inst, bins, wg, mask_arena, arena_words, lut, fb);
+        const int grid = persistent_grid(trace_paths_kernel<false, false>, smem, sm_count, n_tiles);
+        trace_paths_kernel<false, false><<<grid, kBlockThreads, smem, stream>>>(fp, inst, bins, wg, mask_arena, arena_words, lut, fb);
     }
     return cudaGetLastError();
 }

@@ -299,12 +299,11 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
     fp.clear_rgba = g.clear_rgba;
     fp.sky_spp = g.cfg.spp;
     if (g.fused_mode && g.cfg.mode == VT_MODE_PATHS) {
-        if (g.inst_count != 1 || (g.cfg.flags & (VT_FLAG_PERSISTENT_LANES | VT_FLAG_PER_PIXEL_PATHS)))
+        if (g.inst_count != 1 || g.any_bricks || (g.cfg.flags & (VT_FLAG_PERSISTENT_LANES | VT_FLAG_PER_PIXEL_PATHS)))
             return fail("fused cross-GPU accumulation needs the single-instance wavefront kernel");
         if (g.fused_pixels != (size_t)g.cfg.width * g.cfg.height) return fail("fused accumulation buffer does not match the framebuffer size");
         fp.sky_spp = 0u; // pixels outside the screen rectangle are resolved analytically on the root
     }
-    if (g.cfg.mode == VT_MODE_PATHS && g.any_bricks) return fail("path tracing over procedural brick volumes is not implemented");
 
     if (g.vols_dirty) {
         if (g.vols.size() > g.d_vols_cap) {
