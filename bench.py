@@ -203,6 +203,7 @@ def run_cuda(args):
     # N > 1: by default every rank pushes its sums of the covered rectangle straight into rank 0's memory over
     # NVLink (vt_fused_reduce_*); --reduce allreduce keeps a per-rank buffer and sums them with NCCL
     fused = world > 1 and args.reduce == "fused"
+    fused_flags = os.environ.get("VT_FUSED_SYNC", "1") != "0"  # the library's own flag synchronisation (default)
     accum = None
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
     if fused:
@@ -218,10 +219,11 @@ def run_cuda(args):
     def trace_and_reduce():
         if fused:
             r.fused_reduce_next_frame()
-            r.render_async(P, V)
-            stream_barrier(flag)   # all ranks' kernels (and their remote atomics) are done after this
+            r.render_async(P, V)   # trace, push the partial sums into rank 0's memory, raise this rank's flag
+            if not fused_flags:
+                stream_barrier(flag)   # VT_FUSED_SYNC=0: order the ranks with a 4-byte NCCL all-reduce instead
             if rank == 0:
-                r.resolve()        # also clears the buffer for its next use
+                r.resolve()        # waits for every rank's flag, sums the slots, encodes the frame
         else:
             accum.zero_()
             r.render_async(P, V)

@@ -4,8 +4,9 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/multi_gpu_check.py
 
 Every rank traces its shard of the samples.  The frame must be bit-identical (a) to rank 0 tracing all
-samples alone, (b) with the NCCL all-reduce of the accumulators, (c) with the fused NVLink-atomic
-accumulation into the root's buffer (vt_fused_reduce_*), over several frames (double buffering).
+samples alone, (b) with the NCCL all-reduce of the accumulators, (c) with the fused accumulation into the
+root's buffer over NVLink peer stores ordered by flags (vt_fused_reduce_*), over several frames (double
+buffering), (d) the same ordered by an external stream barrier.
 """
 import os
 import sys
@@ -61,7 +62,24 @@ def main():
         assert np.array_equal(r.read_color(), whole_color)
     r.set_accum_buffer(None)
 
-    # (c) fused accumulation over NVLink peer atomics, three frames (both buffers, and a reused one)
+    # (c) fused accumulation: every rank pushes its partial sums into rank 0's memory over NVLink and raises a
+    # flag there; the root waits for the flags.  Six frames, no host synchronisation and no collective in
+    # between: both halves of the double buffer get reused, so the "consumed" flags are exercised too.
+    os.environ["VT_FUSED_SYNC"] = "1"
+    setup_fused_reduce(r, rank, world, dev)
+    for frame in range(6):
+        r.fused_reduce_next_frame()
+        r.render_async(P, V)
+        if rank == 0:
+            fused = r.read_accum()
+            assert np.array_equal(fused, whole), f"fused accumulation differs from the single-rank frame (frame {frame})"
+            r.resolve()
+            assert np.array_equal(r.read_color(), whole_color)
+    r.synchronize()
+    dist.barrier()
+    # (d) the same with the ranks ordered by an external stream barrier instead of the flags
+    r.fused_reduce_disable()
+    os.environ["VT_FUSED_SYNC"] = "0"
     setup_fused_reduce(r, rank, world, dev)
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
     for frame in range(3):
@@ -70,13 +88,11 @@ def main():
         stream_barrier(flag)
         if rank == 0:
             fused = r.read_accum()
-            assert np.array_equal(fused, whole), f"fused accumulation differs from the single-rank frame (frame {frame})"
-            r.resolve()
-            assert np.array_equal(r.read_color(), whole_color)
+            assert np.array_equal(fused, whole), f"fused accumulation (external barrier) differs (frame {frame})"
         r.synchronize()
     dist.barrier()
     if rank == 0:
-        print(f"multi-GPU check ok: {world} ranks, all-reduce and fused NVLink accumulation bit-identical to one rank")
+        print(f"multi-GPU check ok: {world} ranks, all-reduce and fused NVLink accumulation (flags, external barrier) bit-identical to one rank")
     r.close()
     dist.destroy_process_group()
 

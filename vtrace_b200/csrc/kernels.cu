@@ -1576,6 +1576,50 @@ __global__ void resolve_partials_kernel(const InstUniforms* __restrict__ inst, c
     if (accum_out) { accum_out[3 * p + 0] = sum[0]; accum_out[3 * p + 1] = sum[1]; accum_out[3 * p + 2] = sum[2]; }
 }
 
+// Cross-GPU ordering of the fused accumulation without a collective: sequence-number flags in the root's
+// memory.  A rank signals "my partial sums of frame s are in place" after its push kernel (kernel
+// boundaries order the stores: the flag is written by a later kernel on the same stream, after a
+// system-scope fence); the root waits for every rank's flag before it sums the slots, and signals
+// "frame s consumed" so that the ranks may reuse that half of the double buffer.  Waits are bounded
+// (~10 s): a rank that never arrives raises *err instead of hanging the GPU.
+static constexpr unsigned long long kFlagWaitLimitNs = 10ull * 1000 * 1000 * 1000;
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void flag_signal_kernel(uint32_t* flag, uint32_t value) {
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t*>(flag) = value;
+    __threadfence_system();
+}
+
+// thread r waits until flags[r] has reached `target` (sequence numbers compared modulo 2^32)
+__global__ void flag_wait_kernel(const uint32_t* flags, uint32_t n, uint32_t target, uint32_t* err) {
+    const uint32_t r = threadIdx.x;
+    if (r < n) {
+        const volatile uint32_t* f = flags + r;
+        const unsigned long long t0 = global_timer_ns();
+        while ((int32_t)(*f - target) < 0) {
+            __nanosleep(256);
+            if (global_timer_ns() - t0 > kFlagWaitLimitNs) { atomicExch(err, 1u); break; }
+        }
+    }
+    __threadfence_system();
+}
+
+cudaError_t launch_flag_signal(uint32_t* flag, uint32_t value, cudaStream_t stream) {
+    flag_signal_kernel<<<1, 1, 0, stream>>>(flag, value);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_flag_wait(const uint32_t* flags, uint32_t n, uint32_t target, uint32_t* err, cudaStream_t stream) {
+    flag_wait_kernel<<<1, 64, 0, stream>>>(flags, n, target, err);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_push_partial(const InstUniforms* inst, unsigned long long* local_accum, uint4* slot, uint32_t width, uint32_t height,
                                 cudaStream_t stream) {
     push_partial_kernel<<<dim3((width + 127) / 128, height), 128, 0, stream>>>(inst, local_accum, slot, width, height);

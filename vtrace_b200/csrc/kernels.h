@@ -182,6 +182,8 @@ cudaError_t launch_trace_rays(const FrameParams& fp, const InstUniforms* inst, c
                               unsigned long long first, FrameBuffers fb, int sm_count, cudaStream_t stream);
 // fused multi-GPU reduction: move this rank's sums of the covered rectangle into its slot of the root's
 // partial buffer (peer memory) and clear them locally; then, on the root, sum all slots and resolve
+cudaError_t launch_flag_signal(uint32_t* flag, uint32_t value, cudaStream_t stream);
+cudaError_t launch_flag_wait(const uint32_t* flags, uint32_t n, uint32_t target, uint32_t* err, cudaStream_t stream);
 cudaError_t launch_push_partial(const InstUniforms* inst, unsigned long long* local_accum, uint4* slot, uint32_t width, uint32_t height,
                                 cudaStream_t stream);
 cudaError_t launch_resolve_partials(const InstUniforms* inst, const uint4* partials, uint32_t world, uint32_t width, uint32_t height,

@@ -84,6 +84,13 @@ struct State {
     uint4* fused_base = nullptr;     // root memory: [2 buffers][world ranks][pixels][2] partial sums (32 B per pixel)
     size_t fused_pixels = 0;         // pixels per slot
     uint32_t fused_index = 0, fused_rank = 0, fused_world = 1;
+    // flag synchronisation of the fused accumulation (kernels.cu, flag_*_kernel): frame sequence number, the
+    // flags in the root's memory (arrive[2][kFusedMaxWorld], consumed[2]), a local error word
+    uint32_t fused_seq = 0;
+    uint32_t* fused_flags = nullptr;
+    uint32_t* d_fused_err = nullptr;
+    uint32_t* h_fused_err = nullptr; // pinned
+    bool fused_sync = true;
     unsigned long long* fused_sum = nullptr; // root, on demand: materialised sums for vt_read_accum
     unsigned long long* d_stats = nullptr;
     unsigned long long* h_stats = nullptr; // pinned: kRing slots of 2 counters
@@ -201,6 +208,10 @@ int ensure_instances(uint32_t n) {
 
 int render_async(const float* P, const float* V, bool clear_accum, bool resolve);
 
+static constexpr uint32_t kFusedMaxWorld = 64;
+static uint32_t* fused_arrive(uint32_t half) { return g.fused_flags + half * kFusedMaxWorld; }
+static uint32_t* fused_consumed(uint32_t half) { return g.fused_flags + 2 * kFusedMaxWorld + half; }
+
 int finish_frame() {
     if (!g.frame_pending) return 0;
     CK(cudaStreamSynchronize(g.stream));
@@ -221,6 +232,11 @@ int finish_frame() {
         if (render_async(P, V, g.last_clear, g.last_resolve)) return -1;
         CK(cudaStreamSynchronize(g.stream));
         g.frame_pending = false;
+    }
+    if (g.fused_mode && g.h_fused_err && *g.h_fused_err) {
+        *g.h_fused_err = 0;
+        cudaMemsetAsync(g.d_fused_err, 0, 4, g.stream);
+        return fail("fused cross-GPU accumulation: timed out waiting for another rank");
     }
     // the world grid only reports that its lists did not fit (that frame looped over all instances, which is
     // exact): give the next frame room
@@ -324,6 +340,14 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
     g.last_resolve = resolve;
 
     CK(cudaEventRecord(g.ev_begin[slot], g.stream));
+    if (g.fused_mode && g.cfg.mode == VT_MODE_PATHS) {
+        if (g.fused_seq == 0) { g.fused_seq = 1; g.fused_index = 1; } // (vt_fused_reduce_next_frame was not called yet)
+        // the root is done with the previous frame once it starts this one: its half may be refilled
+        if (g.fused_sync && g.fused_mode == 1 && g.fused_seq > 1) {
+            CK(launch_flag_signal(fused_consumed((g.fused_seq - 1) & 1u), g.fused_seq - 1, g.stream));
+            g.stats.launches += 1;
+        }
+    }
     CK(cudaMemsetAsync(g.d_stats, 0, 4 * sizeof(unsigned long long), g.stream));
     CK(launch_instance_setup(g.d_inst, g.inst_count, g.d_vols, fp, g.d_iu, g.stream));
     g.stats.launches += 1;
@@ -416,9 +440,19 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
         CK(cudaEventRecord(g.ev_trace1[slot], g.stream));
         g.stats.launches += 1;
         if (fused) { // stream this rank's sums of the covered rectangle into its slot in the root's memory
-            uint4* slot = g.fused_base + ((size_t)g.fused_index * g.fused_world + g.fused_rank) * g.fused_pixels * 2;
+            const uint32_t half = g.fused_index, seq = g.fused_seq;
+            uint4* slot = g.fused_base + ((size_t)half * g.fused_world + g.fused_rank) * g.fused_pixels * 2;
+            if (g.fused_sync && g.fused_rank != 0 && seq > 2) { // the root must be done with the frame that used this half before
+                CK(launch_flag_wait(fused_consumed(half), 1, seq - 2, g.d_fused_err, g.stream));
+                g.stats.launches += 1;
+            }
             CK(launch_push_partial(g.d_iu, g.d_accum_own, slot, g.cfg.width, g.cfg.height, g.stream));
             g.stats.launches += 1;
+            if (g.fused_sync) {
+                CK(launch_flag_signal(fused_arrive(half) + g.fused_rank, seq, g.stream));
+                CK(cudaMemcpyAsync(g.h_fused_err, g.d_fused_err, 4, cudaMemcpyDeviceToHost, g.stream));
+                g.stats.launches += 1;
+            }
         }
         if (resolve && !fused) {
             const uint32_t total = g.cfg.total_spp ? g.cfg.total_spp : g.cfg.spp;
@@ -805,6 +839,10 @@ extern "C" void cleanup(void) {
     if (g.fused_mode == 1) cudaFree(g.fused_base);
     if (g.fused_mode == 2) cudaIpcCloseMemHandle(g.fused_base);
     g.fused_base = nullptr;
+    g.fused_flags = nullptr;
+    cudaFree(g.d_fused_err);
+    if (g.h_fused_err) cudaFreeHost(g.h_fused_err);
+    g.d_fused_err = g.h_fused_err = nullptr;
     g.fused_mode = 0;
     for (auto& v : g.vols) cudaFree(const_cast<uint8_t*>(v.rgba));
     g.vols.clear();
@@ -907,8 +945,11 @@ extern "C" int64_t vt_read_accum(uint64_t* accum, size_t capacity) {
         const uint32_t total = g.cfg.total_spp ? g.cfg.total_spp : g.cfg.spp;
         SrgbTables lut{g.d_dec, g.d_thr};
         const uint4* partials = g.fused_base + (size_t)g.fused_index * g.fused_world * g.fused_pixels * 2;
+        if (g.fused_sync && launch_flag_wait(fused_arrive(g.fused_index), g.fused_world, g.fused_seq, g.d_fused_err, g.stream) != cudaSuccess)
+            return fail("vt_read_accum: wait failed");
         if (launch_resolve_partials(g.d_iu, partials, g.fused_world, g.cfg.width, g.cfg.height, total ? total : 1, lut, g.d_color, g.fused_sum,
                                     g.stream) != cudaSuccess) return fail("vt_read_accum: resolve failed");
+        cudaMemcpyAsync(g.h_fused_err, g.d_fused_err, 4, cudaMemcpyDeviceToHost, g.stream);
         return read_back(g.fused_sum, g.fused_pixels * 24, accum, capacity);
     }
     return read_back(g.d_accum, (size_t)g.cfg.width * g.cfg.height * 24, accum, capacity);
@@ -940,8 +981,13 @@ extern "C" int32_t vt_resolve(void) {
     if (g.fused_mode == 2) return fail("vt_resolve: only the root of a fused reduction holds the sums");
     if (g.fused_mode == 1) {
         const uint4* partials = g.fused_base + (size_t)g.fused_index * g.fused_world * g.fused_pixels * 2;
+        if (g.fused_sync) { // every rank's partial sums of this frame must be in place
+            CK(launch_flag_wait(fused_arrive(g.fused_index), g.fused_world, g.fused_seq, g.d_fused_err, g.stream));
+            g.stats.launches += 1;
+        }
         CK(launch_resolve_partials(g.d_iu, partials, g.fused_world, g.cfg.width, g.cfg.height, total ? total : 1, lut, g.d_color, nullptr,
                                    g.stream));
+        CK(cudaMemcpyAsync(g.h_fused_err, g.d_fused_err, 4, cudaMemcpyDeviceToHost, g.stream));
     } else {
         CK(launch_resolve(g.d_accum, g.cfg.width * g.cfg.height, total ? total : 1, lut, g.d_color, g.stream));
     }
@@ -956,6 +1002,15 @@ static int fused_common(uint32_t rank, uint32_t world) {
     g.fused_rank = rank;
     g.fused_world = world;
     g.fused_index = 0;
+    g.fused_seq = 0;
+    g.fused_sync = env_u32("VT_FUSED_SYNC", 1) != 0; // 0: the caller orders the ranks itself (a stream barrier per frame)
+    if (world > kFusedMaxWorld) return fail("fused reduction: at most %u ranks", kFusedMaxWorld);
+    if (!g.d_fused_err) {
+        CK(cudaMalloc(&g.d_fused_err, 4));
+        CK(cudaMallocHost(&g.h_fused_err, 4));
+    }
+    *g.h_fused_err = 0;
+    CK(cudaMemsetAsync(g.d_fused_err, 0, 4, g.stream));
     // the local accumulators must start (and, thanks to push_partial, stay) clear
     CK(cudaMemsetAsync(g.d_accum_own, 0, g.fused_pixels * 3 * sizeof(unsigned long long), g.stream));
     CK(cudaStreamSynchronize(g.stream));
@@ -969,9 +1024,11 @@ extern "C" int32_t vt_fused_reduce_export(uint8_t handle[64], uint32_t world) {
     if (finish_frame()) return -1;
     if (g.fused_mode) return fail("fused reduction already set up");
     if (fused_common(0, world)) return -1;
-    const size_t bytes = 2 * (size_t)world * g.fused_pixels * 2 * sizeof(uint4);
+    const size_t data = 2 * (size_t)world * g.fused_pixels * 2 * sizeof(uint4);
+    const size_t bytes = data + (2 * kFusedMaxWorld + 2) * sizeof(uint32_t); // partial sums, then the flags
     CK(cudaMalloc(&g.fused_base, bytes));
     CK(cudaMemset(g.fused_base, 0, bytes));
+    g.fused_flags = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(g.fused_base) + data);
     cudaIpcMemHandle_t h;
     CK(cudaIpcGetMemHandle(&h, g.fused_base));
     memcpy(handle, &h, 64);
@@ -991,13 +1048,15 @@ extern "C" int32_t vt_fused_reduce_import(const uint8_t handle[64], uint32_t ran
     void* p = nullptr;
     CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     g.fused_base = (uint4*)p;
+    g.fused_flags = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p) + 2 * (size_t)world * g.fused_pixels * 2 * sizeof(uint4));
     g.fused_mode = 2;
     return 0;
 }
 
 extern "C" int32_t vt_fused_reduce_next_frame(void) {
     if (!g.inited || !g.fused_mode) return -1;
-    g.fused_index ^= 1u;
+    g.fused_seq += 1;
+    g.fused_index = g.fused_seq & 1u;
     return 0;
 }
 

@@ -33,7 +33,9 @@ def setup_fused_reduce(renderer, rank: int, world: int, device, root: int = 0):
     """Wires the library's fused cross-GPU accumulation: the root exports the CUDA IPC handle of its
     partial-sum buffer, torch.distributed broadcasts the 64 bytes, every other rank maps it.  After
     this, each rank streams its sums of the covered rectangle straight into the root's memory over
-    NVLink and the root's resolve adds the slots up; no all-reduce of the accumulators."""
+    NVLink and raises a sequence-number flag there; the root's resolve waits for the flags and adds the
+    slots up.  No collective on the data path (VT_FUSED_SYNC=0 switches the flags off; the caller then
+    orders the ranks itself, e.g. with stream_barrier)."""
     if root != 0:
         raise ValueError("the library's fused reduction uses rank 0 as the root")
     import torch
@@ -50,7 +52,7 @@ def setup_fused_reduce(renderer, rank: int, world: int, device, root: int = 0):
 
 def stream_barrier(flag):
     """A stream-ordered barrier: a one-element all-reduce completes on a rank only after every rank's
-    stream reached it, i.e. after every rank's trace kernel (and its remote atomics) finished."""
+    stream reached it, i.e. after every rank's push kernel finished.  Only needed with VT_FUSED_SYNC=0."""
     import torch.distributed as dist
 
     dist.all_reduce(flag)

@@ -238,6 +238,10 @@ class Renderer:
         if self._lib.vt_fused_reduce_next_frame() != 0:
             raise RuntimeError("vt_fused_reduce_next_frame failed: " + abi.last_error())
 
+    def fused_reduce_disable(self):
+        if self._lib.vt_fused_reduce_disable() != 0:
+            raise RuntimeError("vt_fused_reduce_disable failed: " + abi.last_error())
+
     def set_accum_buffer(self, device_ptr: int | None):
         if self._lib.vt_set_accum_buffer(C.c_void_p(device_ptr or 0)) != 0:
             raise RuntimeError("vt_set_accum_buffer failed: " + abi.last_error())
