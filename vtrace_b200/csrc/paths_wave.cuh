@@ -35,7 +35,6 @@ static constexpr int kWaveWarps = 12;
 static constexpr int kWaveThreads = kWaveWarps * 32;
 static constexpr int kSlots = 64;        // paths in flight per warp
 static constexpr int kSlotGroups = kSlots / 32;
-static constexpr uint32_t kItemSpp = 16; // most samples per work item (tile x samples)
 static constexpr uint32_t kPoolBytes = kSlots * 96 + kSlots + 32 + 32 * 3 * 4; // slots + byte list + covered-pixel table + tile accumulators
 static_assert(kPoolBytes % 16 == 0, "pool alignment");
 
@@ -81,6 +80,7 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
     const int cov_w = ctx1 - ctx0 + 1, cov_tiles = cov_w * (cty1 - cty0 + 1);
     // Work item = one tile x `item_spp` samples.  Items are sized so that there are several per resident
     // warp even when a rank only has a few samples per pixel (multi-GPU), otherwise the tail dominates.
+    const uint32_t kItemSpp = fp.item_spp; // most samples per work item
     uint32_t item_spp = kItemSpp;
     {
         const long long want_items = 6ll * gridDim.x * kWaveWarps;
@@ -91,7 +91,14 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
         item_spp = (fp.spp + (uint32_t)chunks - 1) / (uint32_t)chunks;
         if (item_spp < 1) item_spp = 1;
     }
-    const int n_chunks = (int)((fp.spp + item_spp - 1) / item_spp);
+    // Chunks are handed out in order (chunk-major), so the LAST ones decide how long the slowest warp runs
+    // after the counter is exhausted: the final chunk's samples are split again and again in halves
+    // (8 -> 4, 2, 1, 1), guided-self-scheduling style.
+    const uint32_t n_full = fp.spp ? (fp.spp + item_spp - 1) / item_spp - 1 : 0; // chunks of exactly item_spp samples
+    const uint32_t tail_spp = fp.spp - n_full * item_spp;                        // 1 .. item_spp samples left for the tail chunks
+    uint32_t n_tail = 0;
+    for (uint32_t rem = tail_spp; rem; rem -= (rem + 1) / 2) ++n_tail;
+    const int n_chunks = (int)(n_full + n_tail);
     const int n_items = cov_tiles * n_chunks;
 
     const float sky[3] = {53.0f / 100.0f, 81.0f / 100.0f, 92.0f / 100.0f}; // lib/command.c:57-59
@@ -268,8 +275,14 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
             const uint32_t cov = __ballot_sync(0xffffffffu, may_hit);
             it_ncov = __popc(cov);
             if (may_hit) cov_pix[__popc(cov & lt_mask)] = (uint8_t)lane;
+            uint32_t ns = item_spp;
             it_s0 = (uint32_t)chunk * item_spp;
-            const uint32_t ns = fp.spp - it_s0 < item_spp ? fp.spp - it_s0 : item_spp;
+            if ((uint32_t)chunk >= n_full) { // tail chunk t: what is left after t halvings
+                uint32_t rem = tail_spp;
+                it_s0 = n_full * item_spp;
+                for (uint32_t t = (uint32_t)chunk - n_full; t; --t) { const uint32_t take = (rem + 1) / 2; it_s0 += take; rem -= take; }
+                ns = (rem + 1) / 2;
+            }
             it_njobs = it_ncov * ns;
             it_next = 0;
             if (it_ncov == 0) it_ncov = 1; // (no jobs; keeps the division below defined)

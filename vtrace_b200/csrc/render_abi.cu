@@ -105,6 +105,7 @@ struct State {
     bool frame_pending = false;
     uint32_t refill_threshold = 16; // tuning knob of the wavefront / persistent-lane kernels (VT_REFILL)
     uint32_t refill_batch = 6;      // wavefront kernel: stopped lanes wait until this many can be refilled together (VT_REFILL_BATCH)
+    uint32_t item_spp = 16;         // wavefront kernel: most samples per work item (VT_ITEM_SPP)
 
     vt_stats stats{};
     user_input input{};
@@ -306,6 +307,7 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
     fp.sample_stride = g.cfg.sample_stride ? g.cfg.sample_stride : 1;
     fp.refill_threshold = g.refill_threshold;
     fp.refill_batch = g.refill_batch;
+    fp.item_spp = g.item_spp;
     {   // sun direction (0.4, -0.8, 0.45), normalised (same float operations as the oracle)
         const float sx = 0.4f, sy = -0.8f, sz = 0.45f;
         const float l = sqrtf((sx * sx + sy * sy) + sz * sz);
@@ -576,6 +578,8 @@ extern "C" uint64_t entry(void) {
     g.cfg.device = dev;
     g.refill_threshold = env_u32("VT_REFILL", 16);
     g.refill_batch = env_u32("VT_REFILL_BATCH", 6);
+    g.item_spp = env_u32("VT_ITEM_SPP", 16);
+    if (g.item_spp < 1) g.item_spp = 1;
     if (g.refill_batch < 1) g.refill_batch = 1;
     if (g.refill_batch > 32) g.refill_batch = 32;
     if (g.refill_threshold < 1) g.refill_threshold = 1;
