@@ -67,6 +67,7 @@ struct FrameParams {
     uint32_t refill_threshold; // wavefront / persistent-lane kernels: park the walkers when fewer than this many are left
     uint32_t refill_batch;     // wavefront kernel: hand out new rays once this many lanes have stopped
     uint32_t item_spp;        // wavefront kernel: most samples per work item (tile x samples), VT_ITEM_SPP
+    uint32_t items_per_warp;  // wavefront kernel: work items wanted per resident warp, VT_ITEMS_PER_WARP
     float sun[3];              // unit vector towards the sun, world space (shadow-ray extension)
     uint32_t any_bricks;       // the scene contains a procedural brick volume
     uint32_t clear_rgba;       // clear colour (lib/command.c:56-61) as stored by the sRGB target: r | g<<8 | b<<16 | a<<24

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
     const uint32_t kItemSpp = fp.item_spp; // most samples per work item
     uint32_t item_spp = kItemSpp;
     {
-        const long long want_items = 6ll * gridDim.x * kWaveWarps;
+        const long long want_items = (long long)fp.items_per_warp * gridDim.x * kWaveWarps;
         long long chunks = cov_tiles > 0 ? (want_items + cov_tiles - 1) / cov_tiles : 1;
         if (chunks < (long long)((fp.spp + kItemSpp - 1) / kItemSpp)) chunks = (fp.spp + kItemSpp - 1) / kItemSpp;
         if (chunks > (long long)fp.spp) chunks = fp.spp;

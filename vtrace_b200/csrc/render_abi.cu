@@ -106,6 +106,7 @@ struct State {
     uint32_t refill_threshold = 16; // tuning knob of the wavefront / persistent-lane kernels (VT_REFILL)
     uint32_t refill_batch = 6;      // wavefront kernel: stopped lanes wait until this many can be refilled together (VT_REFILL_BATCH)
     uint32_t item_spp = 16;         // wavefront kernel: most samples per work item (VT_ITEM_SPP)
+    uint32_t items_per_warp = 6;    // wavefront kernel: work items wanted per resident warp (VT_ITEMS_PER_WARP)
 
     vt_stats stats{};
     user_input input{};
@@ -308,6 +309,7 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
     fp.refill_threshold = g.refill_threshold;
     fp.refill_batch = g.refill_batch;
     fp.item_spp = g.item_spp;
+    fp.items_per_warp = g.items_per_warp;
     {   // sun direction (0.4, -0.8, 0.45), normalised (same float operations as the oracle)
         const float sx = 0.4f, sy = -0.8f, sz = 0.45f;
         const float l = sqrtf((sx * sx + sy * sy) + sz * sz);
@@ -580,6 +582,8 @@ extern "C" uint64_t entry(void) {
     g.refill_batch = env_u32("VT_REFILL_BATCH", 6);
     g.item_spp = env_u32("VT_ITEM_SPP", 16);
     if (g.item_spp < 1) g.item_spp = 1;
+    g.items_per_warp = env_u32("VT_ITEMS_PER_WARP", 6);
+    if (g.items_per_warp < 1) g.items_per_warp = 1;
     if (g.refill_batch < 1) g.refill_batch = 1;
     if (g.refill_batch > 32) g.refill_batch = 32;
     if (g.refill_threshold < 1) g.refill_threshold = 1;
