@@ -206,9 +206,9 @@ def run_cuda(args):
     fused_flags = os.environ.get("VT_FUSED_SYNC", "1") != "0"  # the library's own flag synchronisation (default)
     accum = None
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
-    if fused:
-        setup_fused_reduce(r, rank, world, dev)
-    else:
+    if fused and not setup_fused_reduce(r, rank, world, dev):
+        fused = False  # no peer access between the GPUs of this box: sum the accumulators with NCCL instead
+    if not fused:
         accum = torch.zeros((HEIGHT, WIDTH, 3), dtype=torch.int64, device=dev)  # 2^-24 fixed-point radiance sums
         r.set_accum_buffer(accum.data_ptr())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -339,8 +339,10 @@ def run_cuda(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
             "ms_per_step": t_res / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "spp_per_rank": SPP // world, "partition": f"spp sharded over {world} rank(s), "
-                       "NCCL all-reduce of 3*w*h int64" if world > 1 else "single rank",
+            "config": {"workload": WORKLOAD, "spp_per_rank": SPP // world, "partition": (f"spp sharded over {world} rank(s), " + (
+                           ("partial sums pushed into rank 0's memory over NVLink peer stores, ordered by " +
+                            ("flags in peer memory" if fused_flags else "a 4-byte NCCL stream barrier")) if fused
+                           else "NCCL all-reduce of 3*w*h int64")) if world > 1 else "single rank",
                        "l2": "flushed between steps (256 MiB fill, untimed); scene itself is 256 KB and lives in shared memory/L2 by design",
                        "masks_in_smem": bool(st.masks_in_smem)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(inst.nbytes + 128),

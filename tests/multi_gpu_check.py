@@ -66,7 +66,7 @@ def main():
     # flag there; the root waits for the flags.  Six frames, no host synchronisation and no collective in
     # between: both halves of the double buffer get reused, so the "consumed" flags are exercised too.
     os.environ["VT_FUSED_SYNC"] = "1"
-    setup_fused_reduce(r, rank, world, dev)
+    assert setup_fused_reduce(r, rank, world, dev), "fused accumulation could not be set up (no peer access?)"
     for frame in range(6):
         r.fused_reduce_next_frame()
         r.render_async(P, V)
@@ -80,7 +80,7 @@ def main():
     # (d) the same with the ranks ordered by an external stream barrier instead of the flags
     r.fused_reduce_disable()
     os.environ["VT_FUSED_SYNC"] = "0"
-    setup_fused_reduce(r, rank, world, dev)
+    assert setup_fused_reduce(r, rank, world, dev)
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
     for frame in range(3):
         r.fused_reduce_next_frame()

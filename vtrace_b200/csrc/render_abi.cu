@@ -235,10 +235,13 @@ int finish_frame() {
         CK(cudaStreamSynchronize(g.stream));
         g.frame_pending = false;
     }
-    if (g.fused_mode && g.h_fused_err && *g.h_fused_err) {
-        *g.h_fused_err = 0;
-        cudaMemsetAsync(g.d_fused_err, 0, 4, g.stream);
-        return fail("fused cross-GPU accumulation: timed out waiting for another rank");
+    if (g.fused_mode && g.d_fused_err) { // did a flag wait give up?  (the stream is idle here: a blocking 4-byte copy)
+        CK(cudaMemcpy(g.h_fused_err, g.d_fused_err, 4, cudaMemcpyDeviceToHost));
+        if (*g.h_fused_err) {
+            *g.h_fused_err = 0;
+            CK(cudaMemset(g.d_fused_err, 0, 4));
+            return fail("fused cross-GPU accumulation: timed out waiting for another rank");
+        }
     }
     // the world grid only reports that its lists did not fit (that frame looped over all instances, which is
     // exact): give the next frame room
@@ -454,7 +457,6 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
             g.stats.launches += 1;
             if (g.fused_sync) {
                 CK(launch_flag_signal(fused_arrive(half) + g.fused_rank, seq, g.stream));
-                CK(cudaMemcpyAsync(g.h_fused_err, g.d_fused_err, 4, cudaMemcpyDeviceToHost, g.stream));
                 g.stats.launches += 1;
             }
         }
@@ -957,7 +959,6 @@ extern "C" int64_t vt_read_accum(uint64_t* accum, size_t capacity) {
             return fail("vt_read_accum: wait failed");
         if (launch_resolve_partials(g.d_iu, partials, g.fused_world, g.cfg.width, g.cfg.height, total ? total : 1, lut, g.d_color, g.fused_sum,
                                     g.stream) != cudaSuccess) return fail("vt_read_accum: resolve failed");
-        cudaMemcpyAsync(g.h_fused_err, g.d_fused_err, 4, cudaMemcpyDeviceToHost, g.stream);
         return read_back(g.fused_sum, g.fused_pixels * 24, accum, capacity);
     }
     return read_back(g.d_accum, (size_t)g.cfg.width * g.cfg.height * 24, accum, capacity);
@@ -995,7 +996,6 @@ extern "C" int32_t vt_resolve(void) {
         }
         CK(launch_resolve_partials(g.d_iu, partials, g.fused_world, g.cfg.width, g.cfg.height, total ? total : 1, lut, g.d_color, nullptr,
                                    g.stream));
-        CK(cudaMemcpyAsync(g.h_fused_err, g.d_fused_err, 4, cudaMemcpyDeviceToHost, g.stream));
     } else {
         CK(launch_resolve(g.d_accum, g.cfg.width * g.cfg.height, total ? total : 1, lut, g.d_color, g.stream));
     }

@@ -35,19 +35,36 @@ def setup_fused_reduce(renderer, rank: int, world: int, device, root: int = 0):
     this, each rank streams its sums of the covered rectangle straight into the root's memory over
     NVLink and raises a sequence-number flag there; the root's resolve waits for the flags and adds the
     slots up.  No collective on the data path (VT_FUSED_SYNC=0 switches the flags off; the caller then
-    orders the ranks itself, e.g. with stream_barrier)."""
+    orders the ranks itself, e.g. with stream_barrier).
+
+    Returns False (on every rank, with the fused path switched off again) if any rank could not set it up —
+    the caller then falls back to reduce_accum()."""
     if root != 0:
         raise ValueError("the library's fused reduction uses rank 0 as the root")
     import torch
     import torch.distributed as dist
 
     handle = torch.zeros(64, dtype=torch.uint8, device=device)
+    ok = torch.ones(1, dtype=torch.int32, device=device)
+    err = None
     if rank == root:
-        handle.copy_(torch.frombuffer(bytearray(renderer.fused_reduce_export(world)), dtype=torch.uint8))
+        try:
+            handle.copy_(torch.frombuffer(bytearray(renderer.fused_reduce_export(world)), dtype=torch.uint8))
+        except RuntimeError as e:  # e.g. no memory for the partial-sum buffer
+            err, ok[0] = e, 0
     dist.broadcast(handle, src=root)
     if rank != root:
-        renderer.fused_reduce_import(bytes(handle.cpu().numpy().tobytes()), rank, world)
-    dist.barrier()
+        try:
+            renderer.fused_reduce_import(bytes(handle.cpu().numpy().tobytes()), rank, world)
+        except RuntimeError as e:  # e.g. no peer access between this GPU and the root's
+            err, ok[0] = e, 0
+    # all ranks or none: a rank that could not map the buffer must not leave the others waiting for its flag
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok.item()) == 0:
+        if err is None:
+            renderer.fused_reduce_disable()
+        return False
+    return True
 
 
 def stream_barrier(flag):
