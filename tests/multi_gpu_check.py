@@ -91,6 +91,26 @@ def main():
             assert np.array_equal(fused, whole), f"fused accumulation (external barrier) differs (frame {frame})"
         r.synchronize()
     dist.barrier()
+    # (e) more than 255 samples: the partial sums no longer fit 3 x u32 and travel in the wide layout
+    r.fused_reduce_disable()
+    os.environ["VT_FUSED_SYNC"] = "1"
+    w2, h2, spp2 = 320, 180, 264
+    P2, V2 = scenes.camera(w2, h2, eye=(0.8, -0.45, 0.6))
+    if rank == 0:
+        r.configure(width=w2, height=h2, mode=abi.MODE_PATHS, spp=spp2, bounces=4, seed=0x5EED, sample_first=0, sample_stride=1, total_spp=spp2)
+        assert r.render_tick_raw(P2, V2)
+        whole2 = r.read_accum()
+    first, stride, count = shard_samples(spp2, rank, world)
+    r.configure(width=w2, height=h2, mode=abi.MODE_PATHS, spp=count, bounces=4, seed=0x5EED, sample_first=first,
+                sample_stride=stride, total_spp=spp2)
+    assert setup_fused_reduce(r, rank, world, dev)
+    for frame in range(3):
+        r.fused_reduce_next_frame()
+        r.render_async(P2, V2)
+        if rank == 0:
+            assert np.array_equal(r.read_accum(), whole2), f"fused accumulation, wide layout, differs (frame {frame})"
+    r.synchronize()
+    dist.barrier()
     if rank == 0:
         print(f"multi-GPU check ok: {world} ranks, all-reduce and fused NVLink accumulation (flags, external barrier) bit-identical to one rank")
     r.close()

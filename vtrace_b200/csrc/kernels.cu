@@ -1537,6 +1537,9 @@ __device__ __forceinline__ bool covered_region(const InstUniforms* __restrict__ 
     return !(px < Ip->bounds[0] || px > Ip->bounds[1] || py < Ip->bounds[2] || py > Ip->bounds[3]);
 }
 
+// kCompact: a rank's per-channel sums fit 32 bits (at most 255 samples of at most 2^24 each), so a pixel
+// travels as ONE 16-byte store instead of two — the root's NVLink ingress is what limits the step at 8 GPUs.
+template <bool kCompact>
 __global__ void push_partial_kernel(const InstUniforms* __restrict__ inst, unsigned long long* __restrict__ local_accum,
                                     uint4* __restrict__ slot, uint32_t width, uint32_t height) {
     const uint32_t px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y;
@@ -1544,10 +1547,15 @@ __global__ void push_partial_kernel(const InstUniforms* __restrict__ inst, unsig
     const size_t p = (size_t)py * width + px;
     const unsigned long long r = local_accum[3 * p + 0], g = local_accum[3 * p + 1], b = local_accum[3 * p + 2];
     local_accum[3 * p + 0] = 0ull; local_accum[3 * p + 1] = 0ull; local_accum[3 * p + 2] = 0ull;
-    slot[2 * p + 0] = make_uint4((uint32_t)r, (uint32_t)(r >> 32), (uint32_t)g, (uint32_t)(g >> 32));
-    slot[2 * p + 1] = make_uint4((uint32_t)b, (uint32_t)(b >> 32), 0u, 0u);
+    if (kCompact) {
+        slot[p] = make_uint4((uint32_t)r, (uint32_t)g, (uint32_t)b, 0u);
+    } else {
+        slot[2 * p + 0] = make_uint4((uint32_t)r, (uint32_t)(r >> 32), (uint32_t)g, (uint32_t)(g >> 32));
+        slot[2 * p + 1] = make_uint4((uint32_t)b, (uint32_t)(b >> 32), 0u, 0u);
+    }
 }
 
+template <bool kCompact>
 __global__ void resolve_partials_kernel(const InstUniforms* __restrict__ inst, const uint4* __restrict__ partials, uint32_t world,
                                         uint32_t width, uint32_t height, uint32_t total_spp, SrgbTables lut, uchar4* __restrict__ color,
                                         unsigned long long* __restrict__ accum_out) {
@@ -1557,11 +1565,16 @@ __global__ void resolve_partials_kernel(const InstUniforms* __restrict__ inst, c
     unsigned long long sum[3];
     if (covered_region(inst, (int)px, (int)py)) {
         sum[0] = sum[1] = sum[2] = 0ull;
-        for (uint32_t r = 0; r < world; ++r) {
-            const uint4 a = partials[(r * n_pix + p) * 2 + 0], b = partials[(r * n_pix + p) * 2 + 1];
-            sum[0] += (unsigned long long)a.x | ((unsigned long long)a.y << 32);
-            sum[1] += (unsigned long long)a.z | ((unsigned long long)a.w << 32);
-            sum[2] += (unsigned long long)b.x | ((unsigned long long)b.y << 32);
+        for (uint32_t r = 0; r < world; ++r) { // (a slot is n_pix * 32 bytes whatever the layout)
+            if (kCompact) {
+                const uint4 a = partials[r * n_pix * 2 + p];
+                sum[0] += a.x; sum[1] += a.y; sum[2] += a.z;
+            } else {
+                const uint4 a = partials[(r * n_pix + p) * 2 + 0], b = partials[(r * n_pix + p) * 2 + 1];
+                sum[0] += (unsigned long long)a.x | ((unsigned long long)a.y << 32);
+                sum[1] += (unsigned long long)a.z | ((unsigned long long)a.w << 32);
+                sum[2] += (unsigned long long)b.x | ((unsigned long long)b.y << 32);
+            }
         }
     } else { // sees only sky, for every sample of every rank
         const float sky[3] = {53.0f / 100.0f, 81.0f / 100.0f, 92.0f / 100.0f};
@@ -1621,15 +1634,19 @@ cudaError_t launch_flag_wait(const uint32_t* flags, uint32_t n, uint32_t target,
 }
 
 cudaError_t launch_push_partial(const InstUniforms* inst, unsigned long long* local_accum, uint4* slot, uint32_t width, uint32_t height,
-                                cudaStream_t stream) {
-    push_partial_kernel<<<dim3((width + 127) / 128, height), 128, 0, stream>>>(inst, local_accum, slot, width, height);
+                                bool compact, cudaStream_t stream) {
+    const dim3 grid((width + 127) / 128, height);
+    if (compact) push_partial_kernel<true><<<grid, 128, 0, stream>>>(inst, local_accum, slot, width, height);
+    else push_partial_kernel<false><<<grid, 128, 0, stream>>>(inst, local_accum, slot, width, height);
     return cudaGetLastError();
 }
 
 cudaError_t launch_resolve_partials(const InstUniforms* inst, const uint4* partials, uint32_t world, uint32_t width, uint32_t height,
-                                    uint32_t total_spp, SrgbTables lut, uchar4* color, unsigned long long* accum_out, cudaStream_t stream) {
-    resolve_partials_kernel<<<dim3((width + 127) / 128, height), 128, 0, stream>>>(inst, partials, world, width, height, total_spp, lut,
-                                                                                   color, accum_out);
+                                    uint32_t total_spp, SrgbTables lut, uchar4* color, unsigned long long* accum_out, bool compact,
+                                    cudaStream_t stream) {
+    const dim3 grid((width + 127) / 128, height);
+    if (compact) resolve_partials_kernel<true><<<grid, 128, 0, stream>>>(inst, partials, world, width, height, total_spp, lut, color, accum_out);
+    else resolve_partials_kernel<false><<<grid, 128, 0, stream>>>(inst, partials, world, width, height, total_spp, lut, color, accum_out);
     return cudaGetLastError();
 }
 

@@ -187,9 +187,10 @@ cudaError_t launch_trace_rays(const FrameParams& fp, const InstUniforms* inst, c
 cudaError_t launch_flag_signal(uint32_t* flag, uint32_t value, cudaStream_t stream);
 cudaError_t launch_flag_wait(const uint32_t* flags, uint32_t n, uint32_t target, uint32_t* err, cudaStream_t stream);
 cudaError_t launch_push_partial(const InstUniforms* inst, unsigned long long* local_accum, uint4* slot, uint32_t width, uint32_t height,
-                                cudaStream_t stream);
+                                bool compact, cudaStream_t stream);
 cudaError_t launch_resolve_partials(const InstUniforms* inst, const uint4* partials, uint32_t world, uint32_t width, uint32_t height,
-                                    uint32_t total_spp, SrgbTables lut, uchar4* color, unsigned long long* accum_out, cudaStream_t stream);
+                                    uint32_t total_spp, SrgbTables lut, uchar4* color, unsigned long long* accum_out, bool compact,
+                                    cudaStream_t stream);
 cudaError_t launch_resolve(const unsigned long long* accum, uint32_t n_pixels, uint32_t total_spp, SrgbTables lut,
                            uchar4* color, cudaStream_t stream);
 // one-time: opt in to large dynamic shared memory

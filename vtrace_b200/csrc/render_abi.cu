@@ -213,6 +213,9 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
 static constexpr uint32_t kFusedMaxWorld = 64;
 static uint32_t* fused_arrive(uint32_t half) { return g.fused_flags + half * kFusedMaxWorld; }
 static uint32_t* fused_consumed(uint32_t half) { return g.fused_flags + 2 * kFusedMaxWorld + half; }
+// partial sums travel as 3 x u32 when no rank can exceed 32 bits per channel: every rank renders at most
+// total_spp samples of at most 2^24 each (total_spp is the same on all ranks, so they agree on the layout)
+static bool fused_compact() { return (g.cfg.total_spp ? g.cfg.total_spp : g.cfg.spp) <= 255u; }
 
 int finish_frame() {
     if (!g.frame_pending) return 0;
@@ -453,7 +456,7 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
                 CK(launch_flag_wait(fused_consumed(half), 1, seq - 2, g.d_fused_err, g.stream));
                 g.stats.launches += 1;
             }
-            CK(launch_push_partial(g.d_iu, g.d_accum_own, slot, g.cfg.width, g.cfg.height, g.stream));
+            CK(launch_push_partial(g.d_iu, g.d_accum_own, slot, g.cfg.width, g.cfg.height, fused_compact(), g.stream));
             g.stats.launches += 1;
             if (g.fused_sync) {
                 CK(launch_flag_signal(fused_arrive(half) + g.fused_rank, seq, g.stream));
@@ -958,7 +961,7 @@ extern "C" int64_t vt_read_accum(uint64_t* accum, size_t capacity) {
         if (g.fused_sync && launch_flag_wait(fused_arrive(g.fused_index), g.fused_world, g.fused_seq, g.d_fused_err, g.stream) != cudaSuccess)
             return fail("vt_read_accum: wait failed");
         if (launch_resolve_partials(g.d_iu, partials, g.fused_world, g.cfg.width, g.cfg.height, total ? total : 1, lut, g.d_color, g.fused_sum,
-                                    g.stream) != cudaSuccess) return fail("vt_read_accum: resolve failed");
+                                    fused_compact(), g.stream) != cudaSuccess) return fail("vt_read_accum: resolve failed");
         return read_back(g.fused_sum, g.fused_pixels * 24, accum, capacity);
     }
     return read_back(g.d_accum, (size_t)g.cfg.width * g.cfg.height * 24, accum, capacity);
@@ -995,7 +998,7 @@ extern "C" int32_t vt_resolve(void) {
             g.stats.launches += 1;
         }
         CK(launch_resolve_partials(g.d_iu, partials, g.fused_world, g.cfg.width, g.cfg.height, total ? total : 1, lut, g.d_color, nullptr,
-                                   g.stream));
+                                   fused_compact(), g.stream));
     } else {
         CK(launch_resolve(g.d_accum, g.cfg.width * g.cfg.height, total ? total : 1, lut, g.d_color, g.stream));
     }
