@@ -189,11 +189,17 @@ int32_t vt_resolve(void);
  * exports it as a 64-byte CUDA IPC handle; the other ranks import it.  Each frame every rank traces
  * its samples into its own accumulators, then a small kernel streams the pixels of the instance's
  * screen rectangle — the only ones that can differ from "spp x sky" — into the rank's slot in the
- * root's memory with 32-byte vector stores over NVLink (and clears them locally).  After a
- * stream-ordered barrier supplied by the launcher, the root's vt_resolve sums the slots (integers:
- * bit-identical to an all-reduce) and encodes the frame.  Per frame, on every rank:
- * vt_fused_reduce_next_frame (double buffering), vt_render_async, barrier; then vt_resolve on the root.
- * Single-instance PATHS scenes only. */
+ * root's memory with vector stores over NVLink (16 bytes per pixel while a rank's sums fit 32 bits,
+ * i.e. up to 255 samples; 32 bytes otherwise) and clears them locally, and raises the rank's
+ * sequence-number flag in the root's memory.  The root's vt_resolve (or vt_read_accum) waits for every
+ * rank's flag, sums the slots (integers: bit-identical to an all-reduce) and encodes the frame; a rank
+ * reuses a half of the double buffer only after the root has moved on from the frame that used it.
+ * No collective and no host synchronisation between the ranks.  Per frame, on every rank:
+ * vt_fused_reduce_next_frame, vt_render_async; then vt_resolve on the root (every frame: the other
+ * ranks run at most two frames ahead of it).  A rank that does not arrive within 10 s makes the next
+ * synchronising call fail instead of hanging the GPU.  Environment VT_FUSED_SYNC=0 (read at export /
+ * import) turns the flags off; the launcher must then put a stream-ordered barrier between
+ * vt_render_async and the root's vt_resolve.  Single-instance PATHS scenes only. */
 int32_t vt_fused_reduce_export(uint8_t handle[64], uint32_t world);
 int32_t vt_fused_reduce_import(const uint8_t handle[64], uint32_t rank, uint32_t world);
 int32_t vt_fused_reduce_next_frame(void);
