@@ -540,6 +540,34 @@ def test_paths_over_brick_volumes(pscene, assets):
     pscene.check_paths(P, V, 160, 120, spp=4, bounces=4, what="paths, uploaded bricks")
 
 
+@pytest.mark.parametrize("seed", [101, 202, 303, 404, 505, 606, 707, 808])
+def test_random_scenes_primary_and_paths(scene, assets, seed):
+    """Randomised scenes: 1-12 instances with random rotations, non-uniform scales and overlaps, random
+    (non-cubic) volumes next to the assets, random cameras incl. ones inside a volume; primary records,
+    shadow rays and radiance sums must all equal the oracle's."""
+    rng = np.random.default_rng(seed)
+    texs = [scene.add(assets["Treasure"]), scene.add(assets["AncientTemple"])]
+    for _ in range(2):
+        w, h, d = (int(rng.integers(3, 40)) for _ in range(3))
+        texs.append(scene.add(RawVolume(make_volume(rng, w, h, d, fill=float(rng.uniform(0.05, 0.6))), w, h, d)))
+    for trial in range(3):
+        n = int(rng.integers(1, 13))
+        models = []
+        for _ in range(n):
+            m = glm.translate(glm.identity(), tuple(float(x) for x in rng.uniform(-1.6, 1.6, 3)))
+            m = glm.rotate(m, float(rng.uniform(-3.1, 3.1)), tuple(float(x) for x in rng.uniform(-1, 1, 3) + np.array([0, 1.5, 0])))
+            m = glm.scale(m, tuple(float(x) for x in rng.uniform(0.3, 1.8, 3)))
+            models.append((m, texs[int(rng.integers(0, len(texs)))]))
+        scene.set_instances(models)
+        eye = tuple(float(x) for x in rng.uniform(-3.0, 3.0, 3))
+        center = tuple(float(x) for x in rng.uniform(-0.5, 0.5, 3))
+        w, h = int(rng.integers(60, 260)), int(rng.integers(40, 180))
+        P, V = scenes.camera(w, h, eye=eye, center=center)
+        what = f"random scene seed {seed} trial {trial} ({n} instances, {w}x{h})"
+        scene.check_primary(P, V, w, h, flags=abi.FLAG_SHADOW_RAYS if trial == 1 else 0, what=what)
+        scene.check_paths(P, V, w, h, spp=int(rng.integers(1, 5)), bounces=int(rng.integers(0, 5)), what=what + " paths")
+
+
 def test_paths_sample_sharding_is_exact(renderer, scene, assets):
     """spp split over ranks: integer accumulation makes 1-rank == sum of N ranks."""
     t = scene.add(assets["AncientTemple"])
