@@ -195,8 +195,9 @@ int32_t vt_resolve(void);
  * rank's flag, sums the slots (integers: bit-identical to an all-reduce) and encodes the frame; a rank
  * reuses a half of the double buffer only after the root has moved on from the frame that used it.
  * No collective and no host synchronisation between the ranks.  Per frame, on every rank:
- * vt_fused_reduce_next_frame, vt_render_async; then vt_resolve on the root (every frame: the other
- * ranks run at most two frames ahead of it).  A rank that does not arrive within 10 s makes the next
+ * vt_fused_reduce_next_frame, vt_render_async; then vt_resolve on the root — for every frame, and before
+ * the root enqueues its next one (starting a frame is what tells the other ranks, which run at most two
+ * frames ahead, that the previous frame's half of the buffer may be refilled).  A rank that does not arrive within 10 s makes the next
  * synchronising call fail instead of hanging the GPU.  Environment VT_FUSED_SYNC=0 (read at export /
  * import) turns the flags off; the launcher must then put a stream-ordered barrier between
  * vt_render_async and the root's vt_resolve.  Single-instance PATHS scenes only. */
