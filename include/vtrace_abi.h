@@ -197,8 +197,8 @@ int32_t vt_resolve(void);
  * No collective and no host synchronisation between the ranks.  Per frame, on every rank:
  * vt_fused_reduce_next_frame, vt_render_async; then vt_resolve on the root — for every frame, and before
  * the root enqueues its next one (starting a frame is what tells the other ranks, which run at most two
- * frames ahead, that the previous frame's half of the buffer may be refilled).  A rank that does not arrive within 10 s makes the next
- * synchronising call fail instead of hanging the GPU.  Environment VT_FUSED_SYNC=0 (read at export /
+ * frames ahead, that the previous frame's half of the buffer may be refilled).  A rank that does not
+ * arrive within 10 s makes the next synchronising call fail instead of hanging the GPU.  Environment VT_FUSED_SYNC=0 (read at export /
  * import) turns the flags off; the launcher must then put a stream-ordered barrier between
  * vt_render_async and the root's vt_resolve.  Single-instance PATHS scenes only. */
 int32_t vt_fused_reduce_export(uint8_t handle[64], uint32_t world);
