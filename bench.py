@@ -202,11 +202,13 @@ def run_cuda(args):
     r.set_stream(stream.cuda_stream)
     # N > 1: by default every rank pushes its sums of the covered rectangle straight into rank 0's memory over
     # NVLink (vt_fused_reduce_*); --reduce allreduce keeps a per-rank buffer and sums them with NCCL
-    fused = world > 1 and args.reduce == "fused"
+    fused = (world > 1 or args.force_fused) and args.reduce == "fused"
     fused_flags = os.environ.get("VT_FUSED_SYNC", "1") != "0"  # the library's own flag synchronisation (default)
     accum = None
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
-    if fused and not setup_fused_reduce(r, rank, world, dev):
+    if fused and world == 1:
+        r.fused_reduce_export(1)  # (--force-fused: the multi-GPU data path with a single rank, to profile its kernels)
+    elif fused and not setup_fused_reduce(r, rank, world, dev):
         fused = False  # no peer access between the GPUs of this box: sum the accumulators with NCCL instead
     if not fused:
         accum = torch.zeros((HEIGHT, WIDTH, 3), dtype=torch.int64, device=dev)  # 2^-24 fixed-point radiance sums
@@ -237,7 +239,7 @@ def run_cuda(args):
     def step_e2e():
         """One frame through the reference-facing ABI with host buffers."""
         r.update_instances_raw(inst)          # host matrices -> pinned staging -> device
-        if world == 1:
+        if world == 1 and not fused:
             assert r.render_tick_raw(P, V)    # projection/camera by host pointer; clear + trace + resolve
         else:
             trace_and_reduce()
@@ -377,6 +379,7 @@ def main():
     ap.add_argument("--cpu-spp", type=int, default=64, help="spp of the bounded cpu_baseline sample (64 = the whole frame)")
     ap.add_argument("--ref-spp", type=int, default=64, help="spp per step of the --impl reference arm (64 = the whole frame)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--force-fused", action="store_true", help="N=1 only: run the fused multi-GPU data path with one rank (profiling aid)")
     ap.add_argument("--reduce", default="fused", choices=["fused", "allreduce"], help="cross-GPU accumulation for N > 1")
     args = ap.parse_args()
     if args.impl == "reference":

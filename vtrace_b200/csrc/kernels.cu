@@ -176,8 +176,12 @@ __host__ __device__ void mat4_inverse(const float* m, float* r) {
 
 __global__ void instance_setup_kernel(const float* __restrict__ instances, uint32_t n,
                                       const VolumeDesc* __restrict__ volumes, const FrameParams fp,
-                                      InstUniforms* __restrict__ out) {
+                                      InstUniforms* __restrict__ out, uint32_t* flag, uint32_t flag_value) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && flag) { // fused multi-GPU accumulation, root: "the previous frame is consumed" (see flag_wait below)
+        __threadfence_system();
+        *reinterpret_cast<volatile uint32_t*>(flag) = flag_value;
+    }
     if (i >= n) return;
     float M[16], Mi[16];
 #pragma unroll
@@ -255,9 +259,9 @@ __global__ void instance_setup_kernel(const float* __restrict__ instances, uint3
 }
 
 cudaError_t launch_instance_setup(const float* instances, uint32_t n, const VolumeDesc* volumes, FrameParams fp,
-                                  InstUniforms* out, cudaStream_t stream) {
+                                  InstUniforms* out, uint32_t* flag, uint32_t flag_value, cudaStream_t stream) {
     const int threads = 64;
-    instance_setup_kernel<<<(n + threads - 1) / threads, threads, 0, stream>>>(instances, n, volumes, fp, out);
+    instance_setup_kernel<<<(n + threads - 1) / threads, threads, 0, stream>>>(instances, n, volumes, fp, out, flag, flag_value);
     return cudaGetLastError();
 }
 
@@ -1537,63 +1541,11 @@ __device__ __forceinline__ bool covered_region(const InstUniforms* __restrict__ 
     return !(px < Ip->bounds[0] || px > Ip->bounds[1] || py < Ip->bounds[2] || py > Ip->bounds[3]);
 }
 
-// kCompact: a rank's per-channel sums fit 32 bits (at most 255 samples of at most 2^24 each), so a pixel
-// travels as ONE 16-byte store instead of two — the root's NVLink ingress is what limits the step at 8 GPUs.
-template <bool kCompact>
-__global__ void push_partial_kernel(const InstUniforms* __restrict__ inst, unsigned long long* __restrict__ local_accum,
-                                    uint4* __restrict__ slot, uint32_t width, uint32_t height) {
-    const uint32_t px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y;
-    if (px >= width || py >= height || !covered_region(inst, (int)px, (int)py)) return;
-    const size_t p = (size_t)py * width + px;
-    const unsigned long long r = local_accum[3 * p + 0], g = local_accum[3 * p + 1], b = local_accum[3 * p + 2];
-    local_accum[3 * p + 0] = 0ull; local_accum[3 * p + 1] = 0ull; local_accum[3 * p + 2] = 0ull;
-    if (kCompact) {
-        slot[p] = make_uint4((uint32_t)r, (uint32_t)g, (uint32_t)b, 0u);
-    } else {
-        slot[2 * p + 0] = make_uint4((uint32_t)r, (uint32_t)(r >> 32), (uint32_t)g, (uint32_t)(g >> 32));
-        slot[2 * p + 1] = make_uint4((uint32_t)b, (uint32_t)(b >> 32), 0u, 0u);
-    }
-}
-
-template <bool kCompact>
-__global__ void resolve_partials_kernel(const InstUniforms* __restrict__ inst, const uint4* __restrict__ partials, uint32_t world,
-                                        uint32_t width, uint32_t height, uint32_t total_spp, SrgbTables lut, uchar4* __restrict__ color,
-                                        unsigned long long* __restrict__ accum_out) {
-    const uint32_t px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y;
-    if (px >= width || py >= height) return;
-    const size_t p = (size_t)py * width + px, n_pix = (size_t)width * height;
-    unsigned long long sum[3];
-    if (covered_region(inst, (int)px, (int)py)) {
-        sum[0] = sum[1] = sum[2] = 0ull;
-        for (uint32_t r = 0; r < world; ++r) { // (a slot is n_pix * 32 bytes whatever the layout)
-            if (kCompact) {
-                const uint4 a = partials[r * n_pix * 2 + p];
-                sum[0] += a.x; sum[1] += a.y; sum[2] += a.z;
-            } else {
-                const uint4 a = partials[(r * n_pix + p) * 2 + 0], b = partials[(r * n_pix + p) * 2 + 1];
-                sum[0] += (unsigned long long)a.x | ((unsigned long long)a.y << 32);
-                sum[1] += (unsigned long long)a.z | ((unsigned long long)a.w << 32);
-                sum[2] += (unsigned long long)b.x | ((unsigned long long)b.y << 32);
-            }
-        }
-    } else { // sees only sky, for every sample of every rank
-        const float sky[3] = {53.0f / 100.0f, 81.0f / 100.0f, 92.0f / 100.0f};
-#pragma unroll
-        for (int c = 0; c < 3; ++c) sum[c] = __float2ull_rz((1.0f * sky[c]) * 16777216.0f) * total_spp;
-    }
-    const float scale = 1.0f / ((float)total_spp * 16777216.0f);
-    uint32_t c[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) c[k] = srgb_encode(lut.threshold, __ull2float_rn(sum[k]) * scale);
-    color[p] = make_uchar4((unsigned char)c[0], (unsigned char)c[1], (unsigned char)c[2], 255);
-    if (accum_out) { accum_out[3 * p + 0] = sum[0]; accum_out[3 * p + 1] = sum[1]; accum_out[3 * p + 2] = sum[2]; }
-}
-
 // Cross-GPU ordering of the fused accumulation without a collective: sequence-number flags in the root's
-// memory.  A rank signals "my partial sums of frame s are in place" after its push kernel (kernel
-// boundaries order the stores: the flag is written by a later kernel on the same stream, after a
-// system-scope fence); the root waits for every rank's flag before it sums the slots, and signals
-// "frame s consumed" so that the ranks may reuse that half of the double buffer.  Waits are bounded
+// memory.  A rank raises "my partial sums of frame s are in place" from the last block of its push kernel
+// (every block fences its stores at system scope before it counts itself done); the root's summation kernel
+// waits for every rank's flag before it reads the slots, and the root raises "frame s consumed" when it
+// starts its next frame, so that the ranks may reuse that half of the double buffer.  Waits are bounded
 // (~10 s): a rank that never arrives raises *err instead of hanging the GPU.
 static constexpr unsigned long long kFlagWaitLimitNs = 10ull * 1000 * 1000 * 1000;
 
@@ -1603,50 +1555,121 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     return t;
 }
 
-__global__ void flag_signal_kernel(uint32_t* flag, uint32_t value) {
-    __threadfence_system();
-    *reinterpret_cast<volatile uint32_t*>(flag) = value;
-    __threadfence_system();
+// spins until *flag has reached `target` (sequence numbers compared modulo 2^32)
+__device__ __forceinline__ void flag_wait(const uint32_t* flag, uint32_t target, uint32_t* err) {
+    const volatile uint32_t* f = flag;
+    if ((int32_t)(*f - target) >= 0) return;
+    const unsigned long long t0 = global_timer_ns();
+    while ((int32_t)(*f - target) < 0) {
+        __nanosleep(256);
+        if (global_timer_ns() - t0 > kFlagWaitLimitNs) { atomicExch(err, 1u); break; }
+    }
 }
 
-// thread r waits until flags[r] has reached `target` (sequence numbers compared modulo 2^32)
-__global__ void flag_wait_kernel(const uint32_t* flags, uint32_t n, uint32_t target, uint32_t* err) {
-    const uint32_t r = threadIdx.x;
-    if (r < n) {
-        const volatile uint32_t* f = flags + r;
-        const unsigned long long t0 = global_timer_ns();
-        while ((int32_t)(*f - target) < 0) {
-            __nanosleep(256);
-            if (global_timer_ns() - t0 > kFlagWaitLimitNs) { atomicExch(err, 1u); break; }
+__device__ __forceinline__ void fused_sync_begin(const FusedSync& fs) {
+    if (fs.wait_flags) {
+        if (threadIdx.x < fs.wait_count) flag_wait(fs.wait_flags + threadIdx.x, fs.wait_target, fs.err);
+        __syncthreads();
+    }
+}
+__device__ __forceinline__ void fused_sync_end(const FusedSync& fs) {
+    if (fs.signal_flag) {
+        __threadfence_system(); // this thread's stores to the root's memory are visible before the flag can be
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (atomicAdd(fs.done_counter, 1u) == gridDim.x - 1) { // last block
+                *fs.done_counter = 0u;
+                __threadfence_system();
+                *reinterpret_cast<volatile uint32_t*>(fs.signal_flag) = fs.signal_value;
+            }
         }
     }
-    __threadfence_system();
 }
 
-cudaError_t launch_flag_signal(uint32_t* flag, uint32_t value, cudaStream_t stream) {
-    flag_signal_kernel<<<1, 1, 0, stream>>>(flag, value);
-    return cudaGetLastError();
+// kCompact: a rank's per-channel sums fit 32 bits (at most 255 samples of at most 2^24 each), so a pixel
+// travels as ONE 16-byte store instead of two.  Blocks stride over the rows of the instance's screen
+// rectangle only (the other pixels are sky for every rank and never travel).
+template <bool kCompact>
+__global__ void __launch_bounds__(256) push_partial_kernel(const InstUniforms* __restrict__ inst, unsigned long long* __restrict__ local_accum,
+                                                           uint4* __restrict__ slot, uint32_t width, uint32_t height, FusedSync fs) {
+    fused_sync_begin(fs);
+    const int x0 = max(inst->bounds[0], 0), x1 = min(inst->bounds[1], (int)width - 1);
+    const int y0 = max(inst->bounds[2], 0), y1 = min(inst->bounds[3], (int)height - 1);
+    for (int py = y0 + (int)blockIdx.x; py <= y1; py += (int)gridDim.x)
+        for (int px = x0 + (int)threadIdx.x; px <= x1; px += (int)blockDim.x) {
+            const size_t p = (size_t)py * width + (size_t)px;
+            const unsigned long long r = local_accum[3 * p + 0], g = local_accum[3 * p + 1], b = local_accum[3 * p + 2];
+            local_accum[3 * p + 0] = 0ull; local_accum[3 * p + 1] = 0ull; local_accum[3 * p + 2] = 0ull;
+            if (kCompact) {
+                slot[p] = make_uint4((uint32_t)r, (uint32_t)g, (uint32_t)b, 0u);
+            } else {
+                slot[2 * p + 0] = make_uint4((uint32_t)r, (uint32_t)(r >> 32), (uint32_t)g, (uint32_t)(g >> 32));
+                slot[2 * p + 1] = make_uint4((uint32_t)b, (uint32_t)(b >> 32), 0u, 0u);
+            }
+        }
+    fused_sync_end(fs);
 }
 
-cudaError_t launch_flag_wait(const uint32_t* flags, uint32_t n, uint32_t target, uint32_t* err, cudaStream_t stream) {
-    flag_wait_kernel<<<1, 64, 0, stream>>>(flags, n, target, err);
-    return cudaGetLastError();
+template <bool kCompact>
+__global__ void __launch_bounds__(256) resolve_partials_kernel(const InstUniforms* __restrict__ inst, const uint4* __restrict__ partials,
+                                                               uint32_t world, uint32_t width, uint32_t height, uint32_t total_spp,
+                                                               SrgbTables lut, uchar4* __restrict__ color,
+                                                               unsigned long long* __restrict__ accum_out, FusedSync fs) {
+    fused_sync_begin(fs);
+    const size_t n_pix = (size_t)width * height;
+    const float scale = 1.0f / ((float)total_spp * 16777216.0f);
+    const float sky[3] = {53.0f / 100.0f, 81.0f / 100.0f, 92.0f / 100.0f};
+    unsigned long long sky_sum[3];
+    uint32_t sky_c[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { // a pixel outside the rectangle sees only sky, for every sample of every rank
+        sky_sum[c] = __float2ull_rz((1.0f * sky[c]) * 16777216.0f) * total_spp;
+        sky_c[c] = srgb_encode(lut.threshold, __ull2float_rn(sky_sum[c]) * scale);
+    }
+    const uchar4 sky_px = make_uchar4((unsigned char)sky_c[0], (unsigned char)sky_c[1], (unsigned char)sky_c[2], 255);
+    for (uint32_t py = blockIdx.x; py < height; py += gridDim.x)
+        for (uint32_t px = threadIdx.x; px < width; px += blockDim.x) {
+            const size_t p = (size_t)py * width + px;
+            if (!covered_region(inst, (int)px, (int)py)) {
+                color[p] = sky_px;
+                if (accum_out) { accum_out[3 * p + 0] = sky_sum[0]; accum_out[3 * p + 1] = sky_sum[1]; accum_out[3 * p + 2] = sky_sum[2]; }
+                continue;
+            }
+            unsigned long long sum[3] = {0ull, 0ull, 0ull};
+            for (uint32_t r = 0; r < world; ++r) { // (a slot is n_pix * 32 bytes whatever the layout; L1 is bypassed: peers wrote these lines)
+                if (kCompact) {
+                    const uint4 a = __ldcg(partials + r * n_pix * 2 + p);
+                    sum[0] += a.x; sum[1] += a.y; sum[2] += a.z;
+                } else {
+                    const uint4 a = __ldcg(partials + (r * n_pix + p) * 2 + 0), b = __ldcg(partials + (r * n_pix + p) * 2 + 1);
+                    sum[0] += (unsigned long long)a.x | ((unsigned long long)a.y << 32);
+                    sum[1] += (unsigned long long)a.z | ((unsigned long long)a.w << 32);
+                    sum[2] += (unsigned long long)b.x | ((unsigned long long)b.y << 32);
+                }
+            }
+            uint32_t c[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) c[k] = srgb_encode(lut.threshold, __ull2float_rn(sum[k]) * scale);
+            color[p] = make_uchar4((unsigned char)c[0], (unsigned char)c[1], (unsigned char)c[2], 255);
+            if (accum_out) { accum_out[3 * p + 0] = sum[0]; accum_out[3 * p + 1] = sum[1]; accum_out[3 * p + 2] = sum[2]; }
+        }
+    fused_sync_end(fs);
 }
 
 cudaError_t launch_push_partial(const InstUniforms* inst, unsigned long long* local_accum, uint4* slot, uint32_t width, uint32_t height,
-                                bool compact, cudaStream_t stream) {
-    const dim3 grid((width + 127) / 128, height);
-    if (compact) push_partial_kernel<true><<<grid, 128, 0, stream>>>(inst, local_accum, slot, width, height);
-    else push_partial_kernel<false><<<grid, 128, 0, stream>>>(inst, local_accum, slot, width, height);
+                                bool compact, FusedSync fs, int sm_count, cudaStream_t stream) {
+    const int grid = sm_count * 4 < (int)height ? sm_count * 4 : (int)height;
+    if (compact) push_partial_kernel<true><<<grid, 256, 0, stream>>>(inst, local_accum, slot, width, height, fs);
+    else push_partial_kernel<false><<<grid, 256, 0, stream>>>(inst, local_accum, slot, width, height, fs);
     return cudaGetLastError();
 }
 
 cudaError_t launch_resolve_partials(const InstUniforms* inst, const uint4* partials, uint32_t world, uint32_t width, uint32_t height,
                                     uint32_t total_spp, SrgbTables lut, uchar4* color, unsigned long long* accum_out, bool compact,
-                                    cudaStream_t stream) {
-    const dim3 grid((width + 127) / 128, height);
-    if (compact) resolve_partials_kernel<true><<<grid, 128, 0, stream>>>(inst, partials, world, width, height, total_spp, lut, color, accum_out);
-    else resolve_partials_kernel<false><<<grid, 128, 0, stream>>>(inst, partials, world, width, height, total_spp, lut, color, accum_out);
+                                    FusedSync fs, int sm_count, cudaStream_t stream) {
+    const int grid = sm_count * 4 < (int)height ? sm_count * 4 : (int)height;
+    if (compact) resolve_partials_kernel<true><<<grid, 256, 0, stream>>>(inst, partials, world, width, height, total_spp, lut, color, accum_out, fs);
+    else resolve_partials_kernel<false><<<grid, 256, 0, stream>>>(inst, partials, world, width, height, total_spp, lut, color, accum_out, fs);
     return cudaGetLastError();
 }
 

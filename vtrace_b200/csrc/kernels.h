@@ -158,7 +158,7 @@ __host__ __device__ void mat4_inverse(const float* m, float* out);
 cudaError_t launch_build_mask(const uint8_t* rgba, uint32_t w, uint32_t h, uint32_t d, uint32_t xb, uint32_t yb,
                               uint32_t* mask, uint32_t mask_words, cudaStream_t stream);
 cudaError_t launch_instance_setup(const float* instances, uint32_t n, const VolumeDesc* volumes, FrameParams fp,
-                                  InstUniforms* out, cudaStream_t stream);
+                                  InstUniforms* out, uint32_t* flag, uint32_t flag_value, cudaStream_t stream);
 // bins the instances' screen rectangles; *cursor (device) ends up holding the number of list entries
 // needed — if it exceeds `capacity` the lists are incomplete and the caller must retry with more room
 cudaError_t launch_bin_instances(const InstUniforms* inst, uint32_t n_inst, uint32_t bins_x, uint32_t bins_y, uint32_t* offset,
@@ -184,13 +184,21 @@ cudaError_t launch_trace_rays(const FrameParams& fp, const InstUniforms* inst, c
                               unsigned long long first, FrameBuffers fb, int sm_count, cudaStream_t stream);
 // fused multi-GPU reduction: move this rank's sums of the covered rectangle into its slot of the root's
 // partial buffer (peer memory) and clear them locally; then, on the root, sum all slots and resolve
-cudaError_t launch_flag_signal(uint32_t* flag, uint32_t value, cudaStream_t stream);
-cudaError_t launch_flag_wait(const uint32_t* flags, uint32_t n, uint32_t target, uint32_t* err, cudaStream_t stream);
+// What the push and summation kernels do about the flags (all optional: nullptr = nothing).
+struct FusedSync {
+    const uint32_t* wait_flags; // wait until wait_flags[0 .. wait_count) >= wait_target before touching the slots
+    uint32_t wait_count, wait_target;
+    uint32_t* signal_flag;      // once every block is done: *signal_flag = signal_value
+    uint32_t signal_value;
+    uint32_t* done_counter;     // device word, 0 between launches
+    uint32_t* err;
+};
+
 cudaError_t launch_push_partial(const InstUniforms* inst, unsigned long long* local_accum, uint4* slot, uint32_t width, uint32_t height,
-                                bool compact, cudaStream_t stream);
+                                bool compact, FusedSync fs, int sm_count, cudaStream_t stream);
 cudaError_t launch_resolve_partials(const InstUniforms* inst, const uint4* partials, uint32_t world, uint32_t width, uint32_t height,
                                     uint32_t total_spp, SrgbTables lut, uchar4* color, unsigned long long* accum_out, bool compact,
-                                    cudaStream_t stream);
+                                    FusedSync fs, int sm_count, cudaStream_t stream);
 cudaError_t launch_resolve(const unsigned long long* accum, uint32_t n_pixels, uint32_t total_spp, SrgbTables lut,
                            uchar4* color, cudaStream_t stream);
 // one-time: opt in to large dynamic shared memory

@@ -215,6 +215,15 @@ static uint32_t* fused_arrive(uint32_t half) { return g.fused_flags + half * kFu
 static uint32_t* fused_consumed(uint32_t half) { return g.fused_flags + 2 * kFusedMaxWorld + half; }
 // partial sums travel as 3 x u32 when no rank can exceed 32 bits per channel: every rank renders at most
 // total_spp samples of at most 2^24 each (total_spp is the same on all ranks, so they agree on the layout)
+// the root's summation first waits for every rank's "sums of this frame are in place" flag
+static FusedSync fused_wait_all() {
+    FusedSync fs{};
+    if (g.fused_sync) {
+        fs.wait_flags = fused_arrive(g.fused_index); fs.wait_count = g.fused_world; fs.wait_target = g.fused_seq;
+        fs.err = g.d_fused_err;
+    }
+    return fs;
+}
 static bool fused_compact() { return (g.cfg.total_spp ? g.cfg.total_spp : g.cfg.spp) <= 255u; }
 
 int finish_frame() {
@@ -350,16 +359,19 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
     g.last_resolve = resolve;
 
     CK(cudaEventRecord(g.ev_begin[slot], g.stream));
+    uint32_t* consumed_flag = nullptr;
+    uint32_t consumed_value = 0;
     if (g.fused_mode && g.cfg.mode == VT_MODE_PATHS) {
         if (g.fused_seq == 0) { g.fused_seq = 1; g.fused_index = 1; } // (vt_fused_reduce_next_frame was not called yet)
         // the root is done with the previous frame once it starts this one: its half may be refilled
+        // (raised by the instance-setup kernel below, the first kernel of the frame)
         if (g.fused_sync && g.fused_mode == 1 && g.fused_seq > 1) {
-            CK(launch_flag_signal(fused_consumed((g.fused_seq - 1) & 1u), g.fused_seq - 1, g.stream));
-            g.stats.launches += 1;
+            consumed_flag = fused_consumed((g.fused_seq - 1) & 1u);
+            consumed_value = g.fused_seq - 1;
         }
     }
     CK(cudaMemsetAsync(g.d_stats, 0, 4 * sizeof(unsigned long long), g.stream));
-    CK(launch_instance_setup(g.d_inst, g.inst_count, g.d_vols, fp, g.d_iu, g.stream));
+    CK(launch_instance_setup(g.d_inst, g.inst_count, g.d_vols, fp, g.d_iu, consumed_flag, consumed_value, g.stream));
     g.stats.launches += 1;
 
     // many instances: bin their screen rectangles (16x16-pixel bins) so a pixel only visits its own
@@ -452,16 +464,17 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
         if (fused) { // stream this rank's sums of the covered rectangle into its slot in the root's memory
             const uint32_t half = g.fused_index, seq = g.fused_seq;
             uint4* slot = g.fused_base + ((size_t)half * g.fused_world + g.fused_rank) * g.fused_pixels * 2;
-            if (g.fused_sync && g.fused_rank != 0 && seq > 2) { // the root must be done with the frame that used this half before
-                CK(launch_flag_wait(fused_consumed(half), 1, seq - 2, g.d_fused_err, g.stream));
-                g.stats.launches += 1;
-            }
-            CK(launch_push_partial(g.d_iu, g.d_accum_own, slot, g.cfg.width, g.cfg.height, fused_compact(), g.stream));
-            g.stats.launches += 1;
+            FusedSync fs{};
             if (g.fused_sync) {
-                CK(launch_flag_signal(fused_arrive(half) + g.fused_rank, seq, g.stream));
-                g.stats.launches += 1;
+                if (g.fused_rank != 0 && seq > 2) { // the root must be done with the frame that used this half before
+                    fs.wait_flags = fused_consumed(half); fs.wait_count = 1; fs.wait_target = seq - 2;
+                }
+                fs.signal_flag = fused_arrive(half) + g.fused_rank; fs.signal_value = seq; // "my sums of frame seq are in place"
+                fs.done_counter = g.d_fused_err + 1;
+                fs.err = g.d_fused_err;
             }
+            CK(launch_push_partial(g.d_iu, g.d_accum_own, slot, g.cfg.width, g.cfg.height, fused_compact(), fs, g.sm_count, g.stream));
+            g.stats.launches += 1;
         }
         if (resolve && !fused) {
             const uint32_t total = g.cfg.total_spp ? g.cfg.total_spp : g.cfg.spp;
@@ -958,10 +971,9 @@ extern "C" int64_t vt_read_accum(uint64_t* accum, size_t capacity) {
         const uint32_t total = g.cfg.total_spp ? g.cfg.total_spp : g.cfg.spp;
         SrgbTables lut{g.d_dec, g.d_thr};
         const uint4* partials = g.fused_base + (size_t)g.fused_index * g.fused_world * g.fused_pixels * 2;
-        if (g.fused_sync && launch_flag_wait(fused_arrive(g.fused_index), g.fused_world, g.fused_seq, g.d_fused_err, g.stream) != cudaSuccess)
-            return fail("vt_read_accum: wait failed");
         if (launch_resolve_partials(g.d_iu, partials, g.fused_world, g.cfg.width, g.cfg.height, total ? total : 1, lut, g.d_color, g.fused_sum,
-                                    fused_compact(), g.stream) != cudaSuccess) return fail("vt_read_accum: resolve failed");
+                                    fused_compact(), fused_wait_all(), g.sm_count, g.stream) != cudaSuccess)
+            return fail("vt_read_accum: resolve failed");
         return read_back(g.fused_sum, g.fused_pixels * 24, accum, capacity);
     }
     return read_back(g.d_accum, (size_t)g.cfg.width * g.cfg.height * 24, accum, capacity);
@@ -993,12 +1005,8 @@ extern "C" int32_t vt_resolve(void) {
     if (g.fused_mode == 2) return fail("vt_resolve: only the root of a fused reduction holds the sums");
     if (g.fused_mode == 1) {
         const uint4* partials = g.fused_base + (size_t)g.fused_index * g.fused_world * g.fused_pixels * 2;
-        if (g.fused_sync) { // every rank's partial sums of this frame must be in place
-            CK(launch_flag_wait(fused_arrive(g.fused_index), g.fused_world, g.fused_seq, g.d_fused_err, g.stream));
-            g.stats.launches += 1;
-        }
         CK(launch_resolve_partials(g.d_iu, partials, g.fused_world, g.cfg.width, g.cfg.height, total ? total : 1, lut, g.d_color, nullptr,
-                                   fused_compact(), g.stream));
+                                   fused_compact(), fused_wait_all(), g.sm_count, g.stream));
     } else {
         CK(launch_resolve(g.d_accum, g.cfg.width * g.cfg.height, total ? total : 1, lut, g.d_color, g.stream));
     }
@@ -1017,11 +1025,11 @@ static int fused_common(uint32_t rank, uint32_t world) {
     g.fused_sync = env_u32("VT_FUSED_SYNC", 1) != 0; // 0: the caller orders the ranks itself (a stream barrier per frame)
     if (world > kFusedMaxWorld) return fail("fused reduction: at most %u ranks", kFusedMaxWorld);
     if (!g.d_fused_err) {
-        CK(cudaMalloc(&g.d_fused_err, 4));
+        CK(cudaMalloc(&g.d_fused_err, 8)); // [0] error word, [1] the push kernel's done-block counter
         CK(cudaMallocHost(&g.h_fused_err, 4));
     }
     *g.h_fused_err = 0;
-    CK(cudaMemsetAsync(g.d_fused_err, 0, 4, g.stream));
+    CK(cudaMemsetAsync(g.d_fused_err, 0, 8, g.stream));
     // the local accumulators must start (and, thanks to push_partial, stay) clear
     CK(cudaMemsetAsync(g.d_accum_own, 0, g.fused_pixels * 3 * sizeof(unsigned long long), g.stream));
     CK(cudaStreamSynchronize(g.stream));
