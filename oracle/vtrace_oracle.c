@@ -1016,6 +1016,21 @@ done:
     return rc;
 }
 
+/* texels of volume `tex` (any kind) in the box [x0,x0+nx) x [y0,y0+ny) x [z0,z0+nz), x fastest: lets the tests turn a
+ * procedural or brick volume into the equivalent dense texture and check that both traverse identically */
+int vo_read_texels(const vo_scene* s, uint32_t tex, uint32_t x0, uint32_t y0, uint32_t z0, uint32_t nx, uint32_t ny, uint32_t nz,
+                   uint8_t* rgba) {
+    if (tex >= s->ntex) return -1;
+    const vo_texture* t = &s->tex[tex];
+    if (x0 + nx > t->w || y0 + ny > t->h || z0 + nz > t->d) return -1;
+    const vol_view vol = {t->kind, t->w, t->h, t->d, t->seed, t->rgba, t->heights, t->btable, t->bmasks, t->bcolors};
+    for (uint32_t z = 0; z < nz; ++z)
+        for (uint32_t y = 0; y < ny; ++y)
+            for (uint32_t x = 0; x < nx; ++x)
+                vol_texel(&vol, (int32_t)(x0 + x), (int32_t)(y0 + y), (int32_t)(z0 + z), rgba + 4 * ((size_t)(z * ny + y) * nx + x));
+    return 0;
+}
+
 int vo_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -118,6 +118,10 @@ int vo_load_vox(const char* path, uint32_t dims[3], uint8_t* out, uint64_t out_c
 float vo_srgb_decode(uint8_t c);
 uint8_t vo_srgb_encode(float linear);
 
+/* texels of volume `tex` (any kind) in a box, x fastest, 4 bytes each (tests: procedural / brick volume -> dense texture) */
+int vo_read_texels(const vo_scene*, uint32_t tex, uint32_t x0, uint32_t y0, uint32_t z0, uint32_t nx, uint32_t ny, uint32_t nz,
+                   uint8_t* rgba);
+
 int vo_max_threads(void);
 
 #ifdef __cplusplus

@@ -67,6 +67,8 @@ def lib() -> C.CDLL:
         L.vo_srgb_decode.restype = C.c_float
         L.vo_srgb_encode.argtypes = [C.c_float]
         L.vo_srgb_encode.restype = C.c_uint8
+        L.vo_read_texels.argtypes = [vp, u32, u32, u32, u32, u32, u32, u32, vp]
+        L.vo_read_texels.restype = C.c_int
         L.vo_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -117,6 +119,14 @@ class OracleScene:
         rgba = np.empty((n, 4), dtype=np.uint8) if want_color else None
         iters = lib().vo_render_rays(self._h, n, first, seed, _p(rec), _p(rgba), threads)
         return rec, rgba, int(iters)
+
+    def read_texels(self, tex: int, box=None, dims=None) -> np.ndarray:
+        """RGBA8 texels of volume `tex` (any kind), x fastest; box = (x0, y0, z0, nx, ny, nz) or the whole volume (dims)."""
+        x0, y0, z0, nx, ny, nz = box if box is not None else (0, 0, 0, *dims)
+        out = np.empty(4 * nx * ny * nz, dtype=np.uint8)
+        if lib().vo_read_texels(self._h, tex, x0, y0, z0, nx, ny, nz, _p(out)) != 0:
+            raise ValueError("vo_read_texels: bad texture id or box")
+        return out
 
     def last_shadow_rays(self) -> int:
         return int(lib().vo_last_shadow_rays())

@@ -204,3 +204,76 @@ def test_paths_sample_sharding_sums_exactly(oracle, assets):
     # energy bound: albedo <= 1, so nothing is brighter than the sky
     sky = np.array([int(np.float32(c) / np.float32(100.0) * np.float32(16777216.0)) for c in (53.0, 81.0, 92.0)], dtype=np.uint64)
     assert (whole <= sky * np.uint64(spp)).all()
+
+
+def test_brick_volume_walk_equals_dense_walk(oracle):
+    """The oracle's brick-volume occupancy test against its dense one: the same voxels given once as an RGBA8
+    texture and once as uploaded 8^3 bricks must produce identical traversals (hit voxel, steps, face, iterations),
+    for primary rays, shadow rays and path-traced radiance (colours equalised: one colour per brick)."""
+    from conftest import make_volume
+
+    rng = np.random.default_rng(21)
+    w, h, d = 32, 16, 24
+    occ = rng.random((d, h, w)) < 0.18
+    occ[:, :, :8] &= rng.random((d, h, 8)) < 0.3           # a sparser region: some bricks end up empty
+    occ[8:16, 8:16, 16:24] = False                          # an empty brick for sure
+    brick_color = rng.integers(1, 256, size=(d // 8, h // 8, w // 8, 3), dtype=np.uint8)
+    dense = np.zeros((d, h, w, 4), dtype=np.uint8)
+    dense[..., :3] = np.repeat(np.repeat(np.repeat(brick_color, 8, axis=0), 8, axis=1), 8, axis=2)
+    dense[..., 3] = np.where(occ, 255, 0)
+    dense[~occ] = 0
+    coords, masks, colors = [], [], []
+    for bz in range(d // 8):
+        for by in range(h // 8):
+            for bx in range(w // 8):
+                blk = occ[bz * 8:bz * 8 + 8, by * 8:by * 8 + 8, bx * 8:bx * 8 + 8]
+                if not blk.any():
+                    continue
+                words = np.zeros(16, dtype=np.uint32)
+                zz, yy, xx = np.nonzero(blk)
+                for z, y, x in zip(zz, yy, xx):  # bit (x | (y&3) << 3) of word ((z&7) << 1 | (y&7) >> 2), include/vtrace_abi.h
+                    words[(z << 1) | (y >> 2)] |= np.uint32(1) << np.uint32(x | ((y & 3) << 3))
+                coords.append((bx, by, bz)); masks.append(words); colors.append((*brick_color[bz, by, bx], 255))
+    assert 0 < len(coords) < (w // 8) * (h // 8) * (d // 8)
+
+    a, b = oracle.OracleScene(), oracle.OracleScene()
+    ta = a.add_texture(dense.reshape(-1), w, h, d)
+    tb = b.add_volume_bricks(np.array(coords), np.array(masks), np.array(colors, dtype=np.uint8), w, h, d)
+    m = glm.rotate(glm.identity(), 0.4, (0.2, 1.0, 0.1))
+    a.set_instances(np.stack([glm.with_texture_id(m, ta).reshape(16)]))
+    b.set_instances(np.stack([glm.with_texture_id(m, tb).reshape(16)]))
+    for eye in [(1.4, -0.8, 1.1), (-1.0, 0.6, 0.9), (0.0, 0.0, 1.8)]:
+        P, V = scenes.camera(160, 120, eye=eye)
+        ra, ca, _, ia = a.render_primary(P, V, 160, 120, flags=oracle.FLAG_SHADOW_RAYS)
+        rb, cb, _, ib = b.render_primary(P, V, 160, 120, flags=oracle.FLAG_SHADOW_RAYS)
+        assert ia == ib and np.array_equal(ra, rb) and np.array_equal(ca, cb)
+        assert (ra["hit_voxel"] != oracle.VO_MISS).sum() > 500
+        pa, na, ja = a.render_paths(P, V, 160, 120, spp=2, bounces=3)
+        pb, nb, jb = b.render_paths(P, V, 160, 120, spp=2, bounces=3)
+        assert (na, ja) == (nb, jb) and np.array_equal(pa, pb)
+
+
+@pytest.mark.parametrize("kind,dims,seed", [(1, (64, 32, 48), 4), (2, (64, 64, 64), 2)])
+def test_procedural_volume_equals_its_dense_texture(oracle, kind, dims, seed):
+    """A procedural volume (heightmap / sparse bricks) and the dense RGBA8 texture holding the same texels traverse
+    identically: the large-scene kinds add no traversal rule of their own, only another occupancy source."""
+    w, h, d = dims
+    a, b = oracle.OracleScene(), oracle.OracleScene()
+    ta = a.add_volume_procedural(kind, w, h, d, seed)
+    texels = a.read_texels(ta, dims=dims)
+    filled = int((texels.reshape(-1, 4)[:, 3] > 0).sum())
+    assert 0 < filled < w * h * d
+    tb = b.add_texture(texels, w, h, d)
+    a.set_instances(np.stack([glm.with_texture_id(glm.identity(), ta).reshape(16)]))
+    b.set_instances(np.stack([glm.with_texture_id(glm.identity(), tb).reshape(16)]))
+    P, V = scenes.camera(200, 120, eye=(0.9, -0.8, 0.9))
+    ra, ca, _, ia = a.render_primary(P, V, 200, 120, flags=oracle.FLAG_SHADOW_RAYS)
+    rb, cb, _, ib = b.render_primary(P, V, 200, 120, flags=oracle.FLAG_SHADOW_RAYS)
+    assert ia == ib and np.array_equal(ra, rb) and np.array_equal(ca, cb)
+    assert (ra["hit_voxel"] != oracle.VO_MISS).sum() > 200
+    n = 4096
+    qa, _, ja = a.render_rays(n, seed=7)
+    qb, _, jb = b.render_rays(n, seed=7)
+    assert ja == jb and np.array_equal(qa, qb)
+    with pytest.raises(ValueError):
+        a.read_texels(ta, box=(0, 0, 0, w + 1, 1, 1))
