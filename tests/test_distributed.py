@@ -63,3 +63,64 @@ def test_two_ranks_reduce_to_the_single_rank_image(tmp_path, oracle, assets):
         got = np.load(f"{out}.{rank}.npy").view(np.uint64)
         assert np.array_equal(got, whole)
         assert tuple(np.load(f"{out}.{rank}.counters.npy")) == (rays, iters)
+
+
+class _FakeRenderer:
+    """Stands in for vtrace_b200.renderer.Renderer in the fused-setup handshake (no GPU here)."""
+
+    def __init__(self, fail_import):
+        self.fail_import = fail_import
+        self.calls = []
+
+    def fused_reduce_export(self, world):
+        self.calls.append(("export", world))
+        return bytes(range(64))
+
+    def fused_reduce_import(self, handle, rank, world):
+        self.calls.append(("import", bytes(handle), rank, world))
+        if self.fail_import:
+            raise RuntimeError("no peer access")
+
+    def fused_reduce_disable(self):
+        self.calls.append(("disable",))
+
+
+def _handshake_worker(rank, world, port, fail_rank, out_path):
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import json
+
+    import torch
+    import torch.distributed as dist
+
+    from vtrace_b200.distributed import setup_fused_reduce
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    r = _FakeRenderer(fail_import=(rank == fail_rank))
+    ok = setup_fused_reduce(r, rank, world, torch.device("cpu"))
+    with open(f"{out_path}.{rank}.json", "w") as f:
+        json.dump({"ok": bool(ok), "calls": [c[0] for c in r.calls],
+                   "handle_ok": all(c[1] == bytes(range(64)) for c in r.calls if c[0] == "import")}, f)
+    dist.destroy_process_group()
+
+
+def test_fused_setup_handshake_all_ranks_or_none(tmp_path):
+    """The IPC-handle handshake of the fused accumulation: the root's 64 bytes reach every rank; if one rank
+    cannot map the buffer, EVERY rank reports failure (and the ones that succeeded switch the path off again), so
+    no rank is left waiting for a flag that will never be raised."""
+    import json
+    world = 2
+    out = str(tmp_path / "ok")
+    mp.spawn(_handshake_worker, args=(world, _free_port(), -1, out), nprocs=world, join=True)
+    res = [json.load(open(f"{out}.{r}.json")) for r in range(world)]
+    assert all(x["ok"] and x["handle_ok"] for x in res)
+    assert res[0]["calls"] == ["export"] and res[1]["calls"] == ["import"]
+    out = str(tmp_path / "fail")
+    mp.spawn(_handshake_worker, args=(world, _free_port(), 1, out), nprocs=world, join=True)
+    res = [json.load(open(f"{out}.{r}.json")) for r in range(world)]
+    assert not any(x["ok"] for x in res)
+    assert res[0]["calls"] == ["export", "disable"]   # the root had succeeded: it backs out
+    assert res[1]["calls"] == ["import"]              # the failing rank has nothing to undo
