@@ -6,14 +6,20 @@
 
 Workload (BASELINE.json configs[2]): AncientTemple.vox, 1920x1080, path tracing,
 4 bounces, 64 spp per frame; the 64 samples are sharded over the N ranks (rank g renders samples
-s = g mod N), the fixed-point accumulation buffers are summed with one NCCL all-reduce and
-resolved — so the total work is fixed as N grows ("scaling": "strong").  One step = one frame.
+s = g mod N) and the ranks' fixed-point radiance sums are combined over NVLink — so the total work
+is fixed as N grows ("scaling": "strong").  One step = one frame.
 
-Metric: Mrays/s = ray segments traced (primary + bounce) by all ranks / device time, max over
+Metric: Mrays/s = ray segments (primary + bounce) of the frame, all ranks / device time, max over
 ranks.  `value` is measured with everything resident in HBM; `e2e` goes through the
 reference-facing C ABI with HOST buffers every step (instance matrices written into the pinned
 staging returned by start_update_instances, projection/camera passed by host pointer to the
 frame call, the finished RGBA8 frame read back to host memory), copies inside the timed region.
+`traced_rays` / `traced_mrays_per_s` exclude the camera samples of pixels outside the instance's
+screen rectangle, which the kernel resolves analytically (spp x sky) without marching anything.
+
+After the timed regions the line also carries: `parity` (the frame all ranks produced, compared bit for
+bit with the CPU oracle's), `secondary` (the same scene from a frame-filling camera) and `configs` (the other
+BASELINE.json configurations, each timed a few frames; configs[4] on every rank, ray ids sharded).
 
 The reference (Vulkan + GLSL + Rust, needs a window) cannot run on the box; its CPU arm here is
 the oracle = C transcription of trace.frag/trace.vert ("kind": "port"), see DESIGN.md §2.
@@ -36,7 +42,14 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 METRIC = "Mrays/s (primary+bounce) at 1080p"
 UNIT = "Mrays/s"
 WIDTH, HEIGHT, SPP, BOUNCES, SEED = 1920, 1080, 64, 4, 0x5EED
+CLOSEUP_EYE = (0.8, -0.45, 0.6)
 WORKLOAD = "AncientTemple.vox 1920x1080 path tracing, 4 bounces, 64 spp (configs[2]), camera eye=(1.6,-0.9,1.2) fov 80deg"
+DATA = "reference asset AncientTemple.vox (committed fixture) + fixed synthetic camera"
+# identical in both arms (the driver compares the dicts); per-run details live in "run"
+CONFIG = {"workload": WORKLOAD,
+          "l2": "GPU arm: L2 flushed between steps (256 MiB fill, untimed); the scene itself is 256 KB and lives in "
+                "shared memory by design.  CPU arm: n/a"}
+SM_CLOCK_GHZ, SMSP_PER_SM, STEP_INSTRUCTIONS = 1.965, 4, 17  # issue roof: one warp instruction per SMSP per clock
 
 
 def measured_peaks():
@@ -54,6 +67,16 @@ def recorded_traffic():
         with open(path) as f:
             return json.load(f).get("trace_paths_dram_bytes_per_launch")
     return None
+
+
+def fnv1a64(data: bytes) -> str:
+    """64-bit digest of a buffer: FNV-1a 64 (what host/vtrace_headless prints) folded over the buffer's SHA-256.
+    FNV itself is sequential — 8 MB in pure Python takes seconds — so the heavy pass runs at C speed."""
+    import hashlib
+    h = 1469598103934665603
+    for b in hashlib.sha256(data).digest():
+        h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return f"{h:016x}"
 
 
 class ClockSampler:
@@ -119,17 +142,20 @@ def host_threads() -> int:
         return os.cpu_count() or 1
 
 
-def cpu_sample(threads: int, spp: int):
-    """Times `spp` samples/pixel of the full 1080p workload on the oracle; returns (Mrays/s, s, rays)."""
+def cpu_sample(threads: int, spp: int, eye=None):
+    """Times `spp` samples/pixel of the full 1080p workload on the oracle; returns (Mrays/s, s, rays, iters, accum)."""
     import oracle_lib
+    from tools import scenes
     chunk, P, V, inst = scene_inputs()
+    if eye is not None:
+        P, V = scenes.camera(WIDTH, HEIGHT, eye=eye)
     sc = oracle_lib.OracleScene()
     sc.add_texture(chunk.get_raw(), *chunk.dims())
     sc.set_instances(inst)
     t0 = time.perf_counter()
-    _, rays, iters = sc.render_paths(P, V, WIDTH, HEIGHT, spp=spp, bounces=BOUNCES, seed=SEED, threads=threads)
+    accum, rays, iters = sc.render_paths(P, V, WIDTH, HEIGHT, spp=spp, bounces=BOUNCES, seed=SEED, threads=threads)
     dt = time.perf_counter() - t0
-    return rays / dt / 1e6, dt, rays, iters
+    return rays / dt / 1e6, dt, rays, iters, accum
 
 
 def run_reference(args):
@@ -142,7 +168,7 @@ def run_reference(args):
         cpu_sample(threads, 1)
     times, rays_total = [], 0
     for _ in range(args.steps):
-        _, dt, rays, _ = cpu_sample(threads, spp)
+        _, dt, rays, _, _ = cpu_sample(threads, spp)
         times.append(dt)
         rays_total += rays
     total = sum(times)
@@ -151,9 +177,10 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "reference = C transcription of trace.frag/trace.vert on host cores; "
-                                                  "Vulkan/lavapipe/rustc unavailable on the box"},
+        "vs_baseline": None, "dtype": "f32", "data": DATA,
+        "config": CONFIG,
+        "run": {"note": "reference = C transcription of trace.frag/trace.vert on host cores; Vulkan/lavapipe/rustc "
+                        "unavailable on the box"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -166,10 +193,13 @@ def run_reference(args):
 # CUDA arm
 
 def run_cuda(args):
+    import ctypes as C
+
     import numpy as np
     import torch
     import torch.distributed as dist
 
+    from tools import scenes
     from vtrace_b200 import abi
     from vtrace_b200.distributed import reduce_accum, setup_fused_reduce, shard_samples, stream_barrier
     from vtrace_b200.renderer import Renderer
@@ -210,26 +240,31 @@ def run_cuda(args):
         r.fused_reduce_export(1)  # (--force-fused: the multi-GPU data path with a single rank, to profile its kernels)
     elif fused and not setup_fused_reduce(r, rank, world, dev):
         fused = False  # no peer access between the GPUs of this box: sum the accumulators with NCCL instead
-    if not fused:
+    if not fused and world > 1:
         accum = torch.zeros((HEIGHT, WIDTH, 3), dtype=torch.int64, device=dev)  # 2^-24 fixed-point radiance sums
         r.set_accum_buffer(accum.data_ptr())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     frame_pinned = torch.empty((HEIGHT, WIDTH, 4), dtype=torch.uint8, pin_memory=True)  # the host-side frame buffer
     frame_host = frame_pinned.numpy()
     lib = abi.load()
+    cam = {"P": P, "V": V}
 
     def trace_and_reduce():
         if fused:
             r.fused_reduce_next_frame()
-            r.render_async(P, V)   # trace, push the partial sums into rank 0's memory, raise this rank's flag
+            r.render_async(cam["P"], cam["V"])   # trace, push the partial sums into rank 0's memory, raise this rank's flag
             if not fused_flags:
                 stream_barrier(flag)   # VT_FUSED_SYNC=0: order the ranks with a 4-byte NCCL all-reduce instead
             if rank == 0:
                 r.resolve()        # waits for every rank's flag, sums the slots, encodes the frame
-        else:
+        elif world > 1:
             accum.zero_()
-            r.render_async(P, V)
+            r.render_async(cam["P"], cam["V"])
             reduce_accum(accum)
+            r.resolve()
+        else:
+            r.clear_accum()
+            r.render_async(cam["P"], cam["V"])
             r.resolve()
 
     def step_resident():
@@ -240,7 +275,7 @@ def run_cuda(args):
         """One frame through the reference-facing ABI with host buffers."""
         r.update_instances_raw(inst)          # host matrices -> pinned staging -> device
         if world == 1 and not fused:
-            assert r.render_tick_raw(P, V)    # projection/camera by host pointer; clear + trace + resolve
+            assert r.render_tick_raw(cam["P"], cam["V"])    # projection/camera by host pointer; clear + trace + resolve
         else:
             trace_and_reduce()
         if rank == 0 or not fused:
@@ -254,7 +289,8 @@ def run_cuda(args):
 
     def timed(step_fn, steps):
         """K steps, each bracketed by CUDA events on the launching stream; L2 flushed between steps."""
-        ms, trace_ms, rays, iters = [], [], 0, 0
+        ms, rays = [], 0
+        r.stats()
         for _ in range(steps):
             flush.fill_(1)  # untimed: evict the previous frame from L2
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -264,17 +300,16 @@ def run_cuda(args):
             e1.synchronize()
             r.synchronize()
             ms.append(e0.elapsed_time(e1))
-            st = r.stats()
-            trace_ms.append(st.last_trace_ms)
-            rays += st.rays
-            iters += st.iterations
-        return ms, trace_ms, rays, iters
+        st = r.stats()
+        rays = st.rays_sum
+        return ms, rays
 
     def timed_resident(steps):
         """K device-resident steps enqueued back to back (the host never waits inside the timed region, as
         a renderer that pipelines its frames would); each step is bracketed by its own CUDA events on the
-        launching stream, with the L2 flushed in between; one synchronisation at the end."""
-        r.stats()  # folds everything so far; the kernel-time sums restart here
+        launching stream, with the L2 flushed in between; one synchronisation at the end.  The work counters
+        are summed per frame by the library (vt_stats.*_sum), not extrapolated from one frame."""
+        r.stats()  # folds everything so far; the sums restart here
         evs = []
         for _ in range(steps):
             flush.fill_(1)  # untimed: evict the previous frame from L2
@@ -287,9 +322,18 @@ def run_cuda(args):
         st = r.stats()
         assert st.trace_frames == steps, (st.trace_frames, steps)
         ms = [a.elapsed_time(b) for a, b in evs]
-        per_frame_trace = st.trace_ms_sum / steps
-        return ms, [per_frame_trace] * steps, st.rays * steps, st.iterations * steps  # every step renders the same frame
+        return ms, st.trace_ms_sum, st.rays_sum, st.iterations_sum, st.analytic_rays_sum
 
+    def reduce_over_ranks(times, work):
+        """max over ranks of the device times; sum over ranks of the work counters"""
+        t = torch.tensor(times, dtype=torch.float64, device=dev)
+        w = torch.tensor(work, dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(w, op=dist.ReduceOp.SUM)
+        return [float(x) for x in t.tolist()], [int(x) for x in w.tolist()]
+
+    steps = args.steps
     for _ in range(max(args.warmup, 3)):
         step_resident()
         step_e2e()
@@ -300,74 +344,230 @@ def run_cuda(args):
         sampler.start()
     barrier()
     t_wall0 = time.perf_counter()
-    ms, trace_ms, rays, iters = timed_resident(args.steps)
+    ms, trace_ms_sum, rays, iters, analytic = timed_resident(steps)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = r.stats().launches - launches0
     clocks = sampler.stop() if rank == 0 else None
     barrier()
-    ms_e, _, rays_e, _ = timed(step_e2e, args.steps)
+    ms_e, rays_e = timed(step_e2e, steps)
+    barrier()
+    (t_res, t_e2e, t_trace), (rays_all, rays_e_all, iters_all, analytic_all, launches_all) = reduce_over_ranks(
+        [sum(ms), sum(ms_e), trace_ms_sum], [rays, rays_e, iters, analytic, launches])
+
+    # ---- parity of the frame the timed configuration produces (all ranks' samples), against the CPU oracle ----
+    trace_and_reduce()
+    got_accum = got_color = None
+    if rank == 0:
+        if accum is not None:
+            r.synchronize()
+            got_accum = accum.cpu().numpy().view(np.uint64)
+        else:
+            got_accum = r.read_accum()
+        got_color = r.read_color()
     barrier()
 
-    # max over ranks of the device time; sum over ranks of the work
-    t = torch.tensor([sum(ms), sum(ms_e), sum(trace_ms)], dtype=torch.float64, device=dev)
-    w = torch.tensor([rays, rays_e, iters, launches], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(w, op=dist.ReduceOp.SUM)
-    t_res, t_e2e, t_trace = (float(x) for x in t.tolist())
-    rays_all, rays_e_all, iters_all, launches_all = (int(x) for x in w.tolist())
+    # ---- secondary: the same scene from a frame-filling camera (nearly every sample is a marched ray) ----
+    cam["P"], cam["V"] = scenes.camera(WIDTH, HEIGHT, eye=CLOSEUP_EYE)
+    for _ in range(3):
+        step_resident()
+    barrier()
+    sec_steps = max(3, min(steps, 10))
+    ms2, trace2_sum, rays2, iters2, analytic2 = timed_resident(sec_steps)
+    barrier()
+    (t2, t2_trace), (rays2_all, iters2_all, analytic2_all) = reduce_over_ranks([sum(ms2), trace2_sum], [rays2, iters2, analytic2])
+    cam["P"], cam["V"] = P, V
+
+    # ---- measured cache rooflines (plain streaming kernels of the library, untimed region) ----
+    peaks = {}
+    if rank == 0:
+        for kind, name in ((0, "l2_read_gbs"), (1, "smem_read_gbs"), (2, "hbm_read_gbs")):
+            v = C.c_double(0.0)
+            if lib.vt_measure_peak(kind, C.byref(v)) == 0:
+                peaks[name] = v.value
+
+    # ---- the other BASELINE.json configurations ----
+    if fused:
+        r.fused_reduce_disable()
+    if accum is not None:
+        r.set_accum_buffer(None)
+    hbm_peak, peak_src = measured_peaks()
+    configs = [] if args.no_configs else run_other_configs(r, rank, world, stream, flush, reduce_over_ranks, barrier, hbm_peak, peaks, args)
 
     if rank == 0:
-        steps = args.steps
         value = rays_all / (t_res * 1e-3) / 1e6
         e2e_value = rays_e_all / (t_e2e * 1e-3) / 1e6
+        traced = rays_all - analytic_all
         # roofline of the dominant kernel (trace_paths_wave_kernel), per launch on THIS rank:
         # algorithmic bytes = 4 B per DDA iteration (one RGBA8 voxel record, trace.frag:76) +
         # 16 B per pixel of accumulator read-modify-write
-        st = r.stats()
-        peak, peak_src = measured_peaks()
         alg_bytes = 4.0 * (iters / steps) + 16.0 * WIDTH * HEIGHT
-        kernel_s = (sum(trace_ms) / steps) * 1e-3
+        kernel_s = (trace_ms_sum / steps) * 1e-3
         achieved = alg_bytes / kernel_s / 1e9
-        cpu = None
-        if world == 1 and not args.no_cpu:
+        iters_per_s = (iters / steps) / kernel_s
+        sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+        issue_roof = sm_count * SMSP_PER_SM * SM_CLOCK_GHZ * 1e9 * 32 / STEP_INSTRUCTIONS
+        cpu = parity = None
+        if not args.no_cpu:
             threads = host_threads()
-            v, dt, _, _ = cpu_sample(threads, args.cpu_spp)
-            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"{args.cpu_spp} of the {SPP} spp of the same 1080p frame (samples 0..{args.cpu_spp - 1}), "
-                             f"{dt:.2f} s wall on {threads} threads"}
+            v, dt, _, _, want = cpu_sample(threads, args.cpu_spp)
+            if world == 1:
+                cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                       "sample": f"{args.cpu_spp} of the {SPP} spp of the same 1080p frame (samples 0..{args.cpu_spp - 1}), "
+                                 f"{dt:.2f} s wall on {threads} threads"}
+            if args.cpu_spp == SPP:
+                import oracle_lib
+                want_color = oracle_lib.resolve(want, SPP)
+                parity = {"exact": bool(np.array_equal(got_accum, want) and np.array_equal(got_color, want_color)),
+                          "frame_fnv": fnv1a64(got_color.tobytes()), "oracle_frame_fnv": fnv1a64(want_color.tobytes()),
+                          "accum_fnv": fnv1a64(got_accum.tobytes()), "oracle_accum_fnv": fnv1a64(want.tobytes()),
+                          "what": f"full-size frame of all {world} rank(s): 3 x u64 radiance sums per pixel and the RGBA8 "
+                                  "frame vs the CPU oracle, bit for bit (fnv = FNV-1a 64 of the buffer's SHA-256)"}
+        if parity is None:
+            parity = {"exact": None, "frame_fnv": fnv1a64(got_color.tobytes()), "accum_fnv": fnv1a64(got_accum.tobytes()),
+                      "what": "oracle leg skipped (--no-cpu or --cpu-spp != 64): digests only"}
+        kernel2_s = (trace2_sum / sec_steps) * 1e-3
+        secondary = {
+            "workload": f"same scene and settings, frame-filling camera eye={CLOSEUP_EYE}", "steps": sec_steps,
+            "value": rays2_all / (t2 * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": t2 / sec_steps,
+            "traced_rays_per_step": (rays2_all - analytic2_all) / sec_steps,
+            "traced_mrays_per_s": (rays2_all - analytic2_all) / (t2 * 1e-3) / 1e6,
+            "dda_iterations_per_s": (iters2 / sec_steps) / kernel2_s,
+            "roofline_frac_hbm": (4.0 * (iters2 / sec_steps) + 16.0 * WIDTH * HEIGHT) / kernel2_s / 1e9 / hbm_peak,
+            "issue_frac": (iters2 / sec_steps) / kernel2_s / issue_roof,
+        }
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
             "ms_per_step": t_res / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "spp_per_rank": SPP // world, "partition": (f"spp sharded over {world} rank(s), " + (
-                           ("partial sums pushed into rank 0's memory over NVLink peer stores, ordered by " +
-                            ("flags in peer memory" if fused_flags else "a 4-byte NCCL stream barrier")) if fused
-                           else "NCCL all-reduce of 3*w*h int64")) if world > 1 else "single rank",
-                       "l2": "flushed between steps (256 MiB fill, untimed); scene itself is 256 KB and lives in shared memory/L2 by design",
-                       "masks_in_smem": bool(st.masks_in_smem)},
+            "dtype": "f32", "data": DATA,
+            "config": CONFIG,
+            "run": {"spp_per_rank": SPP // world, "partition": (f"spp sharded over {world} rank(s), " + (
+                        ("partial sums pushed into rank 0's memory over NVLink peer stores, ordered by " +
+                         ("flags in peer memory" if fused_flags else "a 4-byte NCCL stream barrier")) if fused
+                        else "NCCL all-reduce of 3*w*h int64")) if world > 1 else "single rank",
+                    "masks_in_smem": bool(r.stats().masks_in_smem), "ms_per_step_min": min(ms), "ms_per_step_median": statistics.median(ms)},
+            "traced_rays_per_step": traced / steps, "traced_mrays_per_s": traced / (t_res * 1e-3) / 1e6,
+            "analytic_sky_samples_per_step": analytic_all / steps,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(inst.nbytes + 128),
-                    "d2h_bytes_per_step": int(frame_host.nbytes + 16), "ms_per_step": t_e2e / steps},
+                    "d2h_bytes_per_step": int(frame_host.nbytes + 32), "ms_per_step": t_e2e / steps,
+                    "traced_mrays_per_s": (rays_e_all - analytic_all) / (t_e2e * 1e-3) / 1e6},
             "gpu_launches": launches_all,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": recorded_traffic(), "kernel": "trace_paths_wave_kernel", "kernel_ms": kernel_s * 1e3,
                          "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                          "kernel_ms_max_over_ranks": t_trace / steps,
                          "dda_iterations_per_launch": iters / steps,
-                         "dda_iterations_per_s": (iters / steps) / kernel_s},
+                         "dda_iterations_per_s": iters_per_s,
+                         # the scene is shared-memory resident: the same algorithmic bytes against the measured cache peaks,
+                         # and the voxel steps against the instruction-issue roof (the limit this kernel actually runs into)
+                         "vs_l2_peak": {"peak": peaks.get("l2_read_gbs"), "frac": achieved / peaks["l2_read_gbs"] if peaks.get("l2_read_gbs") else None},
+                         "vs_smem_peak": {"peak": peaks.get("smem_read_gbs"), "frac": achieved / peaks["smem_read_gbs"] if peaks.get("smem_read_gbs") else None},
+                         "vs_issue_roof": {"peak_steps_per_s": issue_roof, "frac": iters_per_s / issue_roof,
+                                           "how": f"{sm_count} SMs x {SMSP_PER_SM} issue slots x {SM_CLOCK_GHZ} GHz x 32 lanes / {STEP_INSTRUCTIONS} "
+                                                  "SASS instructions per voxel step"},
+                         "hbm_read_gbs_measured_here": peaks.get("hbm_read_gbs")},
+            "parity": parity,
+            "secondary": secondary,
+            "configs": configs,
             "clocks": clocks,
             "wall_s": t_wall,
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
-    if not fused:
-        r.set_accum_buffer(None)
     r.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def run_other_configs(r, rank, world, stream, flush, reduce_over_ranks, barrier, hbm_peak, peaks, args):
+    """configs[0], [1], [3] on rank 0 and configs[4] on every rank (ray ids sharded, no collective): a few frames each,
+    timed on the device by the library's own CUDA events around the trace kernel."""
+    import numpy as np
+
+    import oracle_lib
+    from tools import scenes
+    from vtrace_b200 import abi
+
+    out = []
+    frames = max(3, min(args.steps, 5))
+
+    def fresh():
+        r.reset()
+        r.set_stream(stream.cuda_stream)  # (the L2 flush is enqueued on this stream too: ordered with the frames)
+
+    def timed_frames(P, V):
+        ms = []
+        for i in range(2 + frames):
+            flush.fill_(1)
+            assert r.render_tick_raw(P, V)
+            st = r.stats()
+            if i >= 2:
+                ms.append(st.last_trace_ms)
+        return float(np.median(ms)), st
+
+    def entry(name, st, ms, n_rays_bytes, bytes_per_ray, resident, extra=None):
+        t = ms * 1e-3
+        alg = 4.0 * st.iterations + bytes_per_ray * n_rays_bytes
+        e = {"workload": name, "trace_kernel_ms": ms, "rays": int(st.rays), "mrays_per_s": st.rays / t / 1e6,
+             "giters_per_s": st.iterations / t / 1e9, "algorithmic_gb_per_s": alg / t / 1e9,
+             "roofline_frac_hbm": alg / t / 1e9 / hbm_peak}
+        if resident and peaks.get("l2_read_gbs"):
+            e["roofline_frac_l2"] = alg / t / 1e9 / peaks["l2_read_gbs"]
+        if extra:
+            e.update(extra)
+        return e
+
+    # configs[0], [1]: the reference's own pass on the two assets, checked against the oracle on the spot
+    if rank == 0:
+        for name, asset, w, h in (("configs[0] Treasure.vox 640x480 primary", "Treasure", 640, 480),
+                                  ("configs[1] AncientTemple.vox 1920x1080 primary", "AncientTemple", 1920, 1080)):
+            fresh()
+            chunk = scenes.load_asset(asset)
+            r.add_texture(chunk)
+            r.update_instances_raw(scenes.single_instance(0))
+            P, V = scenes.camera(w, h)
+            r.configure(width=w, height=h, mode=abi.MODE_PRIMARY, flags=0, spp=1, sample_first=0, sample_stride=1, total_spp=1, max_frames=0)
+            ms, st = timed_frames(P, V)
+            exact = None
+            if not args.no_cpu:
+                sc = oracle_lib.OracleScene()
+                sc.add_texture(chunk.get_raw(), *chunk.dims())
+                sc.set_instances(scenes.single_instance(0))
+                want, wcolor, _, witers = sc.render_primary(P, V, w, h)
+                got = r.read_hits()
+                exact = bool(all(np.array_equal(got[f], want[f]) for f in ("hit_voxel", "packed", "instance", "iters"))
+                             and np.array_equal(r.read_color(), wcolor) and st.iterations == witers)
+            out.append(entry(name, st, ms, st.rays, 12.0, True, {"parity_exact": exact}))
+        # configs[3]: 1024^3 heightmap, 4K, primary + shadow rays (parity: tests/test_gpu_parity.py::test_config3_*)
+        fresh()
+        r.add_volume_procedural(abi.VOLUME_HEIGHTMAP, 1024, 1024, 1024, 1)
+        r.update_instances_raw(scenes.single_instance(0))
+        P, V = scenes.camera(3840, 2160, eye=(0.9, -0.8, 0.9))
+        r.configure(width=3840, height=2160, mode=abi.MODE_PRIMARY, flags=abi.FLAG_SHADOW_RAYS, spp=1, sample_first=0, sample_stride=1,
+                    total_spp=1, max_frames=0)
+        ms, st = timed_frames(P, V)
+        out.append(entry("configs[3] heightmap 1024^3, 3840x2160 primary + shadow rays", st, ms, st.rays, 12.0, False))
+    barrier()
+    # configs[4]: 4096^3 sparse bricks, 2^26 incoherent rays PER GPU; rank g traces ray ids [g * 2^26, (g + 1) * 2^26)
+    fresh()
+    r.add_volume_procedural(abi.VOLUME_SPARSE_BRICKS, 4096, 4096, 4096, 2)
+    r.update_instances_raw(scenes.single_instance(0))
+    P, V = scenes.camera(8192, 8192)
+    r.configure(width=8192, height=8192, mode=abi.MODE_RAYS, flags=0, spp=1, seed=3, sample_first=rank, sample_stride=1, total_spp=1, max_frames=0)
+    barrier()
+    ms, st = timed_frames(P, V)
+    (t4,), (rays4, iters4) = reduce_over_ranks([ms], [st.rays, st.iterations])
+    if rank == 0:
+        t = t4 * 1e-3
+        alg = 4.0 * iters4 + 16.0 * rays4
+        out.append({"workload": f"configs[4] sparse 4096^3 bricks, 2^26 incoherent rays per GPU x {world} GPU(s) (ray ids sharded, no collective)",
+                    "trace_kernel_ms": t4, "rays": rays4, "mrays_per_s": rays4 / t / 1e6, "giters_per_s": iters4 / t / 1e9,
+                    "algorithmic_gb_per_s": alg / t / 1e9, "roofline_frac_hbm": alg / t / 1e9 / (hbm_peak * world), "n_gpus": world,
+                    "scaling": "weak"})
+    barrier()
+    return out
 
 
 def main():
@@ -376,9 +576,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--cpu-spp", type=int, default=64, help="spp of the bounded cpu_baseline sample (64 = the whole frame)")
+    ap.add_argument("--cpu-spp", type=int, default=64, help="spp of the bounded cpu_baseline sample (64 = the whole frame; also enables the parity check)")
     ap.add_argument("--ref-spp", type=int, default=64, help="spp per step of the --impl reference arm (64 = the whole frame)")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity legs")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE.json configurations")
     ap.add_argument("--force-fused", action="store_true", help="N=1 only: run the fused multi-GPU data path with one rank (profiling aid)")
     ap.add_argument("--reduce", default="fused", choices=["fused", "allreduce"], help="cross-GPU accumulation for N > 1")
     args = ap.parse_args()

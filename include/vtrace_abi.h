@@ -111,7 +111,7 @@ void cleanup(void);
 #define VT_FLAG_VIEWPORT_H_IS_W 1u /* reproduce lib/command.c:80-81 (viewport height = width)  */
 #define VT_FLAG_NO_HIT_RECORDS 2u  /* do not write the per-pixel hit records                    */
 #define VT_FLAG_FORCE_GLOBAL_MASKS 4u /* keep traversal masks in global memory (no smem staging) */
-#define VT_FLAG_PERSISTENT_LANES 8u /* PATHS, one instance: persistent-lane schedule (job pool per warp tile) */
+/* (bit 8u was the round-1 persistent-lane schedule, removed: the wavefront engine superseded it) */
 #define VT_FLAG_SHADOW_RAYS 64u     /* PRIMARY: one shadow ray towards the sun (0.4,-0.8,0.45) per winning fragment  */
 #define VT_FLAG_NO_BINNING 32u      /* visit every instance per pixel instead of the screen-space bins (testing) */
 #define VT_FLAG_PER_PIXEL_PATHS 16u /* PATHS, one instance: the general per-pixel kernel instead of the wavefront engine */
@@ -151,7 +151,12 @@ typedef struct vt_stats {
     uint32_t masks_in_smem;   /* 1 when the traversal masks were staged in shared memory          */
     uint32_t trace_frames;    /* frames folded into trace_ms_sum since the previous vt_get_stats  */
     float trace_ms_sum;       /* sum of the trace kernel's device time over those frames          */
-    uint32_t reserved;
+    uint32_t bin_list_grown;  /* times the instance-bin list was too small (such a frame is exact but slower) and was grown */
+    uint64_t analytic_rays;   /* last frame, PATHS: the part of `rays` that was never marched — camera samples of  */
+                              /* pixels outside every instance's screen rectangle, resolved as spp x sky           */
+    uint64_t rays_sum;        /* `rays`, `iterations`, `analytic_rays` summed over the frames folded since the     */
+    uint64_t iterations_sum;  /* previous vt_get_stats (frames may differ: the sums are not last-frame x frames)    */
+    uint64_t analytic_rays_sum;
 } vt_stats;
 
 /* Current configuration (defaults: 1000x1000, PRIMARY, as lib/entry.c:62). */
@@ -210,6 +215,11 @@ int32_t vt_fused_reduce_disable(void);
 int32_t vt_set_stream(void* cuda_stream);
 
 int32_t vt_get_stats(vt_stats* out);
+/* Measured roofline denominators on the device entry() chose (streaming kernels, best of 4, CUDA events):
+ * kind 0 = L2 read GB/s (32 MiB resident buffer, L1 bypassed), 1 = shared-memory read GB/s (LDS.128),
+ * 2 = HBM read GB/s (2 GiB buffer).  The .vox scenes are cache-resident: their algorithmic
+ * bandwidth is reported against these next to the HBM figure.  0 = ok. */
+int32_t vt_measure_peak(uint32_t kind, double* gb_per_s);
 int32_t vt_set_user_input(const user_input* in);
 /* Last error as text (static storage). */
 const char* vt_last_error(void);

@@ -58,7 +58,7 @@ def test_struct_layouts_match_the_rust_side():
     assert abi.UserInput.mouse_x.offset == 8 and abi.UserInput.last_mouse_y.offset == 32
     assert C.sizeof(abi.RenderTickInfo) == 2 * C.sizeof(C.c_void_p)  # src/render.rs:177-181
     assert abi.HIT_DTYPE.itemsize == 16
-    assert C.sizeof(abi.VtConfig) == 48 and C.sizeof(abi.VtStats) == 56
+    assert C.sizeof(abi.VtConfig) == 48 and C.sizeof(abi.VtStats) == 88
 
 
 def test_sass_is_sm100a_with_tma_bulk_copy():
@@ -83,6 +83,43 @@ def test_fails_loudly_without_a_gpu():
     from vtrace_b200.renderer import Renderer
     with pytest.raises(RuntimeError):
         Renderer()
+
+
+def test_static_library_defines_the_seven_symbols_and_links_into_a_c_host(tmp_path):
+    """librender.a is what the reference's build script links (`cargo:rustc-link-lib=static=render`,
+    build.rs:96-97): a plain C host must link against it with only the CUDA and C++ runtimes added."""
+    abi.load()
+    from vtrace_b200 import build
+    assert os.path.exists(build.STATIC_LIB)
+    defined = subprocess.run(["nm", "-g", "--defined-only", build.STATIC_LIB], capture_output=True, text=True, check=True).stdout
+    refs = ("entry", "render_tick", "get_input_data_pointer", "add_texture", "start_update_instances", "end_update_instances", "cleanup")
+    for ref in refs:
+        assert re.search(rf"\bT {ref}\b", defined), ref
+    src = tmp_path / "host.c"
+    src.write_text('''#include "vtrace_abi.h"
+#include <stdio.h>
+int main(void) {
+    uint64_t rc = entry();
+    if (rc) { printf("entry failed: %s\\n", vt_last_error()); return 3; }
+    float P[16] = {0}, V[16] = {0}; render_tick_info info = {P, V}; int32_t w = 0, h = 0;
+    (void)get_input_data_pointer();
+    float* m = start_update_instances(1); if (!m || end_update_instances(1)) return 4;
+    (void)add_texture(0, 0, 0, 0); (void)render_tick(&w, &h, &info); cleanup(); return 0;
+}
+''')
+    exe = tmp_path / "host_static"
+    cuda_lib = os.environ.get("CUDA_LIB", "/usr/local/cuda/lib64")
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", os.path.dirname(build.STATIC_LIB),
+                    "-l:librender.a", "-L", cuda_lib, "-lcudart_static", "-lstdc++", "-lm", "-ldl", "-lpthread", "-lrt"],
+                   check=True, capture_output=True)
+    ldd = subprocess.run(["ldd", str(exe)], capture_output=True, text=True).stdout
+    assert "librender" not in ldd  # nothing of the renderer is left to the dynamic loader
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    import torch
+    if torch.cuda.is_available():
+        assert out.returncode == 0, out.stdout + out.stderr
+    else:  # fails loudly, through the statically linked entry()
+        assert out.returncode == 3 and "CUDA" in out.stdout
 
 
 def test_compiled_host_builds_and_links_the_seven_symbols():

@@ -25,8 +25,11 @@ def test_reference_arm_line():
     assert line["impl"] == "reference"
     assert line["metric"].startswith("Mrays/s") and line["unit"] == "Mrays/s"
     assert line["n_gpus"] == 1 and line["steps"] == 1 and line["higher_is_better"] is True
-    assert line["vs_baseline"] is None and line["data"] == "synthetic"
+    assert line["vs_baseline"] is None and "AncientTemple.vox" in line["data"]
     assert "workload" in line["config"] and "configs[2]" in line["config"]["workload"]
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line["config"] == bench.CONFIG  # the two arms carry the same config dict (the driver compares them)
     assert line["value"] > 0 and line["ms_per_step"] > 0
     cb = line["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]

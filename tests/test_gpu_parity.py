@@ -393,7 +393,7 @@ def test_paths_single_instance_exact(scene, assets):
 
 
 def test_paths_generic_kernel_on_single_instance(scene, assets):
-    """The general (multi-instance) kernel and the persistent-lane single-instance kernel are two
+    """The general (multi-instance) kernel and the wavefront single-instance kernel are two
     schedules of the same paths: both must reproduce the oracle bit for bit."""
     t = scene.add(assets["Treasure"])
     scene.set_instances([(glm.identity(), t)])
@@ -402,18 +402,17 @@ def test_paths_generic_kernel_on_single_instance(scene, assets):
     w, _ = scene.check_paths(P, V, 256, 160, spp=5, flags=0, what="wavefront kernel")
     g, _ = scene.check_paths(P, V, 256, 160, spp=5, flags=abi.FLAG_FORCE_GLOBAL_MASKS, what="wavefront kernel, global masks")
     assert np.array_equal(a, w) and np.array_equal(a, g)
-    b, _ = scene.check_paths(P, V, 256, 160, spp=5, flags=abi.FLAG_PERSISTENT_LANES, what="persistent-lane kernel")
-    c, _ = scene.check_paths(P, V, 256, 160, spp=5, flags=abi.FLAG_PERSISTENT_LANES | abi.FLAG_FORCE_GLOBAL_MASKS,
-                             what="persistent-lane kernel, global masks")
-    assert np.array_equal(a, b) and np.array_equal(b, c)
+    b, _ = scene.check_paths(P, V, 256, 160, spp=5, flags=abi.FLAG_PER_PIXEL_PATHS | abi.FLAG_FORCE_GLOBAL_MASKS,
+                             what="general per-pixel kernel, global masks")
+    assert np.array_equal(a, b)
 
 
 def test_paths_many_samples_chunking(scene, assets):
-    """spp > 128 exercises the per-pool sample chunking of the persistent-lane kernel."""
+    """spp > 128: an item's samples are chunked so that its 32-bit per-pixel sums cannot wrap."""
     t = scene.add(assets["AncientTemple"])
     scene.set_instances([(glm.identity(), t)])
     P, V = scenes.camera(96, 64, eye=(0.8, -0.45, 0.6))
-    scene.check_paths(P, V, 96, 64, spp=150, bounces=2, flags=abi.FLAG_PERSISTENT_LANES, what="150 spp, persistent lanes")
+    scene.check_paths(P, V, 96, 64, spp=150, bounces=2, flags=abi.FLAG_PER_PIXEL_PATHS, what="150 spp, per-pixel kernel")
     scene.check_paths(P, V, 96, 64, spp=150, bounces=2, what="150 spp")
 
 
@@ -422,7 +421,7 @@ def test_paths_axis_aligned_and_inside(scene, assets):
     scene.set_instances([(glm.identity(), t)])
     P, V = scenes.camera(161, 121, eye=(0.0, 0.0, 2.0))
     scene.check_paths(P, V, 161, 121, spp=2, what="paths axis aligned")
-    scene.check_paths(P, V, 161, 121, spp=2, flags=abi.FLAG_PERSISTENT_LANES, what="paths axis aligned, persistent lanes")
+    scene.check_paths(P, V, 161, 121, spp=2, flags=abi.FLAG_PER_PIXEL_PATHS, what="paths axis aligned, per-pixel kernel")
     P, V = scenes.camera(160, 120, eye=(0.1, 0.2, -0.1), center=(1.0, 0.3, 0.2))
     scene.check_paths(P, V, 160, 120, spp=2, what="paths camera inside")
 
@@ -437,7 +436,7 @@ def test_paths_degenerate_scenes(scene, assets):
     t = scene.add(assets["Treasure"])
     scene.set_instances([(glm.identity(), t)])
     P, V = scenes.camera(96, 64, eye=(0.9, -0.5, 0.7))
-    for flags in (0, abi.FLAG_PER_PIXEL_PATHS, abi.FLAG_PERSISTENT_LANES):
+    for flags in (0, abi.FLAG_PER_PIXEL_PATHS):
         scene.check_paths(P, V, 96, 64, spp=1, bounces=0, flags=flags, what=f"paths, 0 bounces, flags {flags}")
         scene.check_paths(P, V, 97, 63, spp=3, bounces=1, flags=flags, what=f"paths, odd size, flags {flags}")
 
@@ -585,17 +584,15 @@ def test_paths_sample_sharding_is_exact(renderer, scene, assets):
     assert np.array_equal(total, whole)
 
 
-def test_config2_full_size_properties(renderer, scene, assets):
-    """configs[2] at full size (1080p, 64 spp, 4 bounces): too big for the oracle, so check the
+def test_config2_full_size_exact(renderer, scene, assets):
+    """configs[2] at full size (1080p, 64 spp, 4 bounces) — the bench workload itself — against the
+    oracle bit for bit (radiance sums, ray and iteration counters, resolved colour), plus the
     size-independent properties: determinism, ray-count bounds, energy bound, sky pixels exact."""
     t = scene.add(assets["AncientTemple"])
     scene.set_instances([(glm.identity(), t)])
     w, h, spp = 1920, 1080, 64
     P, V = scenes.camera(w, h)
-    renderer.configure(width=w, height=h, mode=abi.MODE_PATHS, flags=0, spp=spp, bounces=4, seed=0x5EED,
-                       sample_first=0, sample_stride=1, total_spp=spp)
-    assert renderer.render_tick_raw(P, V)
-    a1, st1 = renderer.read_accum(), renderer.stats()
+    a1, st1 = scene.check_paths(P, V, w, h, spp=spp, bounces=4, seed=0x5EED, what="configs[2] full size")
     assert renderer.render_tick_raw(P, V)
     a2, st2 = renderer.read_accum(), renderer.stats()
     assert np.array_equal(a1, a2) and st1.rays == st2.rays and st1.iterations == st2.iterations
@@ -606,11 +603,22 @@ def test_config2_full_size_properties(renderer, scene, assets):
     assert np.array_equal(a1[0, 0], sky * np.uint64(spp))  # a corner pixel sees only sky
 
 
+def test_config2_full_size_closeup_exact(scene, assets):
+    """The frame-filling camera of the bench's `secondary` block, full size, against the oracle."""
+    t = scene.add(assets["AncientTemple"])
+    scene.set_instances([(glm.identity(), t)])
+    w, h = 1920, 1080
+    P, V = scenes.camera(w, h, eye=(0.8, -0.45, 0.6))
+    scene.check_paths(P, V, w, h, spp=16, bounces=4, seed=0x5EED, what="configs[2] close-up, 16 spp")
+
+
 # ---- compiled host over the C ABI ----------------------------------------------------------------
 
-def test_compiled_host_drives_the_abi_like_the_engine(oracle, assets, tmp_path):
+@pytest.mark.parametrize("exe", ["vtrace_headless", "vtrace_headless_static"])
+def test_compiled_host_drives_the_abi_like_the_engine(oracle, assets, tmp_path, exe):
     """host/vtrace_headless (C++ mirror of src/main.rs + src/render.rs + src/world.rs' entity grid) runs
-    as its own process against librender.so: one texture upload per tick, instances skipped until their
+    as its own process against librender.so — and, as vtrace_headless_static, with the static librender.a
+    the reference's build script would link (build.rs:96-97) inside the executable: one texture upload per tick, instances skipped until their
     texture is resident, frame k rendered with frame k-1's pose.  Its last frame must hash to what the
     oracle renders from the same matrices."""
     import os
@@ -619,7 +627,7 @@ def test_compiled_host_drives_the_abi_like_the_engine(oracle, assets, tmp_path):
     subprocess.run(["make", "-C", os.path.join(root, "host")], check=True, capture_output=True)
     env = dict(os.environ, VT_WIDTH="640", VT_HEIGHT="360", VT_MAX_FRAMES="5", VT_MODE="0", VT_FLAGS="0")
     ppm = str(tmp_path / "frame.ppm")
-    out = subprocess.run([os.path.join(root, "host", "vtrace_headless"), scenes.ASSETS, ppm], env=env, capture_output=True,
+    out = subprocess.run([os.path.join(root, "host", exe), scenes.ASSETS, ppm], env=env, capture_output=True,
                          text=True, timeout=120)
     assert out.returncode == 0, out.stderr
     fields = dict(line.split("=", 1) for line in out.stdout.replace(" ", "\n").splitlines() if "=" in line)

@@ -15,7 +15,7 @@ from . import build as _build
 VT_MISS = 0xFFFFFFFF
 MODE_PRIMARY, MODE_PATHS, MODE_RAYS = 0, 1, 2
 VOLUME_HEIGHTMAP, VOLUME_SPARSE_BRICKS = 1, 2
-FLAG_VIEWPORT_H_IS_W, FLAG_NO_HIT_RECORDS, FLAG_FORCE_GLOBAL_MASKS, FLAG_PERSISTENT_LANES, FLAG_PER_PIXEL_PATHS, FLAG_NO_BINNING, FLAG_SHADOW_RAYS = 1, 2, 4, 8, 16, 32, 64
+FLAG_VIEWPORT_H_IS_W, FLAG_NO_HIT_RECORDS, FLAG_FORCE_GLOBAL_MASKS, FLAG_PER_PIXEL_PATHS, FLAG_NO_BINNING, FLAG_SHADOW_RAYS = 1, 2, 4, 16, 32, 64
 
 HIT_DTYPE = np.dtype([("hit_voxel", "<u4"), ("packed", "<u4"), ("instance", "<u4"), ("iters", "<u4")])
 
@@ -39,7 +39,9 @@ class VtConfig(C.Structure):
 class VtStats(C.Structure):
     _fields_ = [("frames", C.c_uint64), ("rays", C.c_uint64), ("iterations", C.c_uint64), ("launches", C.c_uint64),
                 ("last_trace_ms", C.c_float), ("last_frame_ms", C.c_float), ("masks_in_smem", C.c_uint32),
-                ("trace_frames", C.c_uint32), ("trace_ms_sum", C.c_float), ("reserved", C.c_uint32)]
+                ("trace_frames", C.c_uint32), ("trace_ms_sum", C.c_float), ("bin_list_grown", C.c_uint32),
+                ("analytic_rays", C.c_uint64), ("rays_sum", C.c_uint64), ("iterations_sum", C.c_uint64),
+                ("analytic_rays_sum", C.c_uint64)]
 
 
 # every symbol include/vtrace_abi.h declares: name -> (restype, argtypes)
@@ -76,6 +78,7 @@ SYMBOLS = {
     "vt_fused_reduce_disable": (_i32, []),
     "vt_set_stream": (_i32, [_vp]),
     "vt_get_stats": (_i32, [C.POINTER(VtStats)]),
+    "vt_measure_peak": (_i32, [_u32, C.POINTER(C.c_double)]),
     "vt_set_user_input": (_i32, [C.POINTER(UserInput)]),
     "vt_last_error": (C.c_char_p, []),
 }

@@ -1,23 +1,35 @@
-"""Builds vtrace_b200/librender.so (sm_100a only) with nvcc, in-tree.
+"""Builds vtrace_b200/librender.so and vtrace_b200/librender.a (sm_100a only) with nvcc, in-tree.
 
     python -m vtrace_b200.build [--force] [--verbose]
 
 Flags that matter for parity: --fmad=false (no FMA contraction), IEEE
 division / square root, no flush-to-zero, no fast-math; the host compiler gets
 -ffp-contract=off for the per-frame uniform matrices.
+
+Every source is compiled to its own object (in parallel, only when stale); the objects are linked
+into the shared library the ctypes / C++ hosts load, and archived into a static `librender.a` — the
+form the reference's build script links (`cargo:rustc-link-lib=static=render`, build.rs:96-97).
 """
 from __future__ import annotations
 
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
+OBJ = os.path.join(PKG, "_obj")
 LIB = os.path.join(PKG, "librender.so")
-SOURCES = ["kernels.cu", "render_abi.cu"]
-HEADERS = [os.path.join(CSRC, "kernels.h"), os.path.join(CSRC, "paths_wave.cuh"), os.path.join(CSRC, "bricks.cuh"), os.path.join(CSRC, "world_grid.cuh"), os.path.join(ROOT, "include", "vtrace_abi.h")]
+STATIC_LIB = os.path.join(PKG, "librender.a")
+SOURCES = ["kernels.cu", "render_abi.cu", "peaks.cu"]
+
+
+def headers() -> list[str]:
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".h", ".cuh"))] + [
+        os.path.join(ROOT, "include", "vtrace_abi.h")]
+
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -25,7 +37,6 @@ NVCC_FLAGS = [
     "--fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall",
     "-Xptxas", "-v",
-    "-shared",
 ]
 
 
@@ -36,25 +47,64 @@ def nvcc() -> str:
     return "nvcc"
 
 
-def needs_build() -> bool:
-    if not os.path.exists(LIB):
+def _obj(src: str) -> str:
+    return os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
+
+
+def _stale(target: str, deps: list[str]) -> bool:
+    if not os.path.exists(target):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS + [os.path.abspath(__file__)]
+    t = os.path.getmtime(target)
     return any(os.path.getmtime(d) > t for d in deps)
+
+
+def needs_build() -> bool:
+    common = headers() + [os.path.abspath(__file__)]
+    return any(_stale(_obj(s), [os.path.join(CSRC, s)] + common) for s in SOURCES) or \
+        any(_stale(out, [_obj(s) for s in SOURCES if os.path.exists(_obj(s))]) for out in (LIB, STATIC_LIB))
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc(), *NVCC_FLAGS, "-ccbin", "/usr/bin/g++", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or proc.returncode != 0:
-        sys.stderr.write(proc.stdout + proc.stderr)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed building librender.so")
+    os.makedirs(OBJ, exist_ok=True)
+    common = headers() + [os.path.abspath(__file__)]
+    log = []
+
+    def compile_one(src: str):
+        out = _obj(src)
+        if not force and not _stale(out, [os.path.join(CSRC, src)] + common):
+            return 0, f"(up to date) {src}\n"
+        cmd = [nvcc(), *NVCC_FLAGS, "-ccbin", "/usr/bin/g++", "-c", "-o", out, os.path.join(CSRC, src)]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        return proc.returncode, " ".join(cmd) + "\n" + proc.stdout + proc.stderr
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    failed = False
+    for rc, text in results:
+        log.append(text)
+        failed = failed or rc != 0
+    if not failed:
+        objs = [_obj(s) for s in SOURCES]
+        link = [nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++", "-shared", "-o", LIB, *objs]
+        proc = subprocess.run(link, capture_output=True, text=True)
+        log.append(" ".join(link) + "\n" + proc.stdout + proc.stderr)
+        failed = proc.returncode != 0
+        if not failed:
+            if os.path.exists(STATIC_LIB):
+                os.remove(STATIC_LIB)
+            ar = ["ar", "rcs", STATIC_LIB, *objs]
+            proc = subprocess.run(ar, capture_output=True, text=True)
+            log.append(" ".join(ar) + "\n" + proc.stdout + proc.stderr)
+            failed = proc.returncode != 0
+    text = "".join(log)
+    if verbose or failed:
+        sys.stderr.write(text)
+    if failed:
+        raise RuntimeError("nvcc failed building librender")
     with open(os.path.join(PKG, "librender.build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+        f.write(text)
     return LIB
 
 

@@ -25,7 +25,6 @@ namespace vt {
 
 #define VT_FLAG_VIEWPORT_H_IS_W 1u
 #define VT_FLAG_NO_HIT_RECORDS 2u
-#define VT_FLAG_PERSISTENT_LANES 8u
 #define VT_FLAG_PER_PIXEL_PATHS 16u
 #define VT_FLAG_SHADOW_RAYS 64u
 #define VT_MISS 0xFFFFFFFFu
@@ -291,7 +290,7 @@ __global__ void bin_instances_kernel(const InstUniforms* __restrict__ inst, uint
     if (lane == 0) base = n ? atomicAdd(cursor, n) : 0u;
     base = __shfl_sync(0xffffffffu, base, 0);
     if (lane == 0) { offset[bin] = base; count[bin] = (base + n <= capacity) ? n : 0xFFFFFFFFu; }
-    if (base + n > capacity) return; // overflow: the host sees cursor > capacity and retries with a larger list
+    if (base + n > capacity) return; // overflow: this bin's pixels visit every instance (bin_range); the host grows the list
     uint32_t w = base;
     for (uint32_t i0 = 0; i0 < n_inst; i0 += 32) {
         const uint32_t i = i0 + lane;
@@ -313,6 +312,22 @@ cudaError_t launch_bin_instances(const InstUniforms* inst, uint32_t n_inst, uint
     bin_instances_kernel<<<(warps * 32 + threads - 1) / threads, threads, 0, stream>>>(inst, n_inst, bins_x, bins_y, offset, count, list,
                                                                                      capacity, cursor);
     return cudaGetLastError();
+}
+
+// Instances a pixel has to visit, in draw order: its 16x16 bin's segment of the binned list, or every instance when
+// the scene is not binned — or when the bin's segment did not fit the list (count == 0xFFFFFFFF, see
+// bin_instances_kernel): such a frame is still exact, only slower; the host grows the list for the next one.
+__device__ __forceinline__ const uint32_t* bin_range(const BinTable& bins, int px, int py, uint32_t n_inst, uint32_t& k_begin,
+                                                     uint32_t& k_end) {
+    k_begin = 0;
+    k_end = n_inst;
+    if (!bins.enabled) return nullptr;
+    const uint32_t bin = ((uint32_t)py >> kBinShift) * bins.bins_x + ((uint32_t)px >> kBinShift);
+    const uint32_t cnt = __ldg(bins.count + bin);
+    if (cnt == 0xFFFFFFFFu) return nullptr;
+    k_begin = __ldg(bins.offset + bin);
+    k_end = k_begin + cnt;
+    return bins.list;
 }
 
 // -------------------------------------------------------------------------------------------
@@ -754,14 +769,10 @@ __global__ void __launch_bounds__(kBlockThreads) trace_primary_kernel(const __gr
             HitRecord rec{VT_MISS, 0u, VT_MISS, 0u};
             // draw order = instance order (lib/command.c:102); with bins, only the instances whose screen
             // rectangle touches this pixel's 16x16 bin are visited (same order, same results)
-            uint32_t k_begin = 0, k_end = fp.n_inst;
-            if (bins.enabled) {
-                const uint32_t bin = ((uint32_t)py >> kBinShift) * bins.bins_x + ((uint32_t)px >> kBinShift);
-                k_begin = __ldg(bins.offset + bin);
-                k_end = k_begin + __ldg(bins.count + bin);
-            }
+            uint32_t k_begin, k_end;
+            const uint32_t* bin_list = bin_range(bins, px, py, fp.n_inst, k_begin, k_end);
             for (uint32_t k = k_begin; k < k_end; ++k) {
-                const uint32_t i = bins.enabled ? __ldg(bins.list + k) : k;
+                const uint32_t i = bin_list ? __ldg(bin_list + k) : k;
                 Fragment f;
                 run_fragment<kSmem, kBricks>(fp, inst + i, mask_base, px, py, fx, fy, f);
                 if (!f.covered) continue;
@@ -1035,10 +1046,7 @@ __device__ void trace_world(const FrameParams& fp, const InstUniforms* __restric
         bool last_cell = true;
         const uint32_t* list = nullptr;
         if (binned) {
-            const uint32_t bin = ((uint32_t)py >> kBinShift) * bins.bins_x + ((uint32_t)px >> kBinShift);
-            k_begin = __ldg(bins.offset + bin);
-            k_end = k_begin + __ldg(bins.count + bin);
-            list = bins.list;
+            list = bin_range(bins, px, py, fp.n_inst, k_begin, k_end);
         } else if (gridded) {
             const uint32_t cell = world_walk_cell(walk, t_lim, last_cell);
             k_begin = __ldg(wg.offset + cell);
@@ -1211,7 +1219,7 @@ __global__ void __launch_bounds__(kBlockThreads) trace_paths_kernel(const __grid
         for (int c = 0; c < 3; ++c) sky_q[c] = __float2ull_rz((1.0f * sky[c]) * 16777216.0f);
     }
 
-    unsigned long long rays = 0, iters = 0;
+    unsigned long long rays = 0, iters = 0, analytic = 0;
     for (;;) {
         const int tile = claim_tiles(fb.stats + 2, lane, 1);
         if (tile >= n_tiles) break;
@@ -1222,14 +1230,10 @@ __global__ void __launch_bounds__(kBlockThreads) trace_paths_kernel(const __grid
         // the primary segment; their sum is known without tracing them (they still count as rays).
         bool may_hit = false;
         {
-            uint32_t k_begin = 0, k_end = fp.n_inst;
-            if (bins.enabled) {
-                const uint32_t bin = ((uint32_t)py >> kBinShift) * bins.bins_x + ((uint32_t)px >> kBinShift);
-                k_begin = __ldg(bins.offset + bin);
-                k_end = k_begin + __ldg(bins.count + bin);
-            }
+            uint32_t k_begin, k_end;
+            const uint32_t* bin_list = bin_range(bins, px, py, fp.n_inst, k_begin, k_end);
             for (uint32_t k = k_begin; k < k_end; ++k) {
-                const InstUniforms* Ip = inst + (bins.enabled ? __ldg(bins.list + k) : k);
+                const InstUniforms* Ip = inst + (bin_list ? __ldg(bin_list + k) : k);
                 may_hit = may_hit || !(px < Ip->bounds[0] || px > Ip->bounds[1] || py < Ip->bounds[2] || py > Ip->bounds[3]);
             }
         }
@@ -1238,6 +1242,7 @@ __global__ void __launch_bounds__(kBlockThreads) trace_paths_kernel(const __grid
 #pragma unroll
             for (int c = 0; c < 3; ++c) acc[c] = sky_q[c] * fp.spp;
             rays += fp.spp;
+            analytic += fp.spp;
         } else {
             for (uint32_t k = 0; k < fp.spp; ++k) {
                 float L[3];
@@ -1257,262 +1262,12 @@ __global__ void __launch_bounds__(kBlockThreads) trace_paths_kernel(const __grid
     for (int o = 16; o; o >>= 1) {
         rays += __shfl_xor_sync(0xffffffffu, rays, o);
         iters += __shfl_xor_sync(0xffffffffu, iters, o);
+        analytic += __shfl_xor_sync(0xffffffffu, analytic, o);
     }
     if (lane == 0) {
         if (rays) atomicAdd(fb.stats + 0, rays);
         if (iters) atomicAdd(fb.stats + 1, iters);
-    }
-}
-
-// -------------------------------------------------------------------------------------------
-// trace_paths_single_kernel: the path tracer for single-instance scenes (BASELINE configs[2]).
-//
-// Same paths, same arithmetic, same results as trace_path() above — but scheduled for SIMT
-// efficiency.  In the per-pixel kernel a warp's lanes spend most of the DDA loop masked off
-// (rays of one warp need 0..100+ iterations; ncu: 11.5 of 32 lanes active).  Here a warp owns an
-// 8x4 tile and a pool of jobs = (covered pixel, sample); lanes are persistent workers:
-//   * lanes whose ray stopped wait (masked) until fewer than `refill_threshold` lanes are still
-//     marching — i.e. until most of the warp is idle; then all stopped lanes shade, bounce or fetch their next job
-//     (ballot + popc hand out consecutive job numbers) and the warp re-enters the loop packed;
-//   * radiance goes to per-warp shared-memory accumulators with integer atomics — fixed point,
-//     so the order in which lanes finish cannot change a single bit of the result;
-//   * everything stays in the instance's voxel space (one instance: a ray that leaves the
-//     volume can only see the sky).
-// RNG streams are keyed by (pixel, sample) only, so results do not depend on which lane ran what.
-static constexpr uint32_t kSppChunk = 128;  // samples per pool: keeps 2^-24 fixed-point sums inside u32
-
-template <bool kSmem>
-__global__ void __launch_bounds__(kBlockThreads, 2) trace_paths_single_kernel(const __grid_constant__ FrameParams fp,
-                                                                            const InstUniforms* __restrict__ inst,
-                                                                            const uint32_t* __restrict__ mask_arena,
-                                                                            uint32_t arena_words, SrgbTables lut, FrameBuffers fb) {
-    stage_tables<kSmem>(mask_arena, arena_words, lut.decode);
-    const float* dec = reinterpret_cast<const float*>(vt_smem + kSmemLutOff);
-    const InstUniforms* Ip = inst; // the one instance
-    const Vol vol{Ip->w, Ip->h, Ip->d, Ip->xb, Ip->yb, Ip->mask_off, mask_arena};
-    const float size[3] = {(float)(int32_t)Ip->w, (float)(int32_t)Ip->h, (float)(int32_t)Ip->d};
-    const uint32_t xb = vol.xb, zb = vol.xb + vol.yb;
-
-    const int tiles_x = (fp.width + kTileW - 1) / kTileW;
-    const int tiles_y = (fp.height + kTileH - 1) / kTileH;
-    const int n_tiles = tiles_x * tiles_y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    uint32_t* wacc = reinterpret_cast<uint32_t*>(vt_smem + kSmemAccOff) + warp * 96;
-
-    const float sky[3] = {53.0f / 100.0f, 81.0f / 100.0f, 92.0f / 100.0f}; // lib/command.c:57-59
-    unsigned long long rays = 0, iters = 0;
-
-    for (;;) {
-        const int tile = claim_tiles(fb.stats + 2, lane, 1);
-        if (tile >= n_tiles) break;
-        const int tx0 = (tile % tiles_x) * kTileW, ty0 = (tile / tiles_x) * kTileH;
-        const int my_px = tx0 + (lane & 7), my_py = ty0 + (lane >> 3);
-        const bool in_frame = my_px < fp.width && my_py < fp.height;
-        const bool may_hit = in_frame && !(my_px < Ip->bounds[0] || my_px > Ip->bounds[1] || my_py < Ip->bounds[2] || my_py > Ip->bounds[3]);
-        const uint32_t cov = __ballot_sync(0xffffffffu, may_hit);
-        if (in_frame && !may_hit) { // sees only sky, for every sample
-            const size_t p = (size_t)my_py * (size_t)fp.width + (size_t)my_px;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) fb.accum[3 * p + c] += __float2ull_rz((1.0f * sky[c]) * 16777216.0f) * fp.spp;
-            rays += fp.spp;
-        }
-        if (!cov) continue;
-        const uint32_t ncov = __popc(cov);
-
-        for (uint32_t s0 = 0; s0 < fp.spp; s0 += kSppChunk) {
-            const uint32_t ns = fp.spp - s0 < kSppChunk ? fp.spp - s0 : kSppChunk;
-            const uint32_t njobs = ncov * ns;
-            uint32_t next = 0;
-            wacc[lane * 3 + 0] = 0; wacc[lane * 3 + 1] = 0; wacc[lane * 3 + 2] = 0;
-            __syncwarp();
-
-            // ---- per-lane worker state ----
-            bool has_path = false;   // a path is in flight on this lane
-            bool pending = false;    // its current ray has stopped (or never walked) and awaits shading
-            bool fast = false;       // ... and it stopped inside the fast walk (exit state still to be decoded)
-            bool walking = false;    // the fast walk is still going (the lane is NOT ready for shading)
-            uint32_t pix = 0;        // tile-local pixel (= lane that owns it) of the current path
-            Rng rng{0, 0};
-            float thr[3] = {1.0f, 1.0f, 1.0f};
-            uint32_t bounce = 0;
-            int entry_axis = 0;
-            Dda r;                   // ray state (registers)
-            r.hit = false; r.steps = 0; r.last_mask = 0; r.len = 1.0f;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { r.v[k] = 0; r.step[k] = 0; r.side[k] = r.delta[k] = r.dir[k] = r.pos[k] = 0.0f; }
-            // Walk registers.  idx == 0 is a border bit (always set), so a lane without a live ray can
-            // execute the step below as a no-op: the march loop needs no per-lane branch.
-            uint32_t idx = 0, prev = 0, steps = 0, ix = 0, iy = 0, iz = 0;
-            float sx = 0.0f, sy = 0.0f, sz = 0.0f;
-
-            for (;;) {
-                float npos[3] = {0.0f, 0.0f, 0.0f}, ndir[3] = {0.0f, 0.0f, 0.0f};
-                int32_t nsv[3] = {0, 0, 0};
-                bool new_ray = false, new_has_start = false;
-
-                // ---- (i) lanes whose ray stopped: shade, then bounce or end the path -------------
-                if (has_path && pending && !walking) {
-                    if (fast) {
-                        r.side[0] = sx; r.side[1] = sy; r.side[2] = sz;
-                        dda_finish_fast(vol, r, idx, prev, steps);
-                        iters += steps;
-                        idx = 0; // parks the lane on a stop bit
-                    }
-                    pending = false;
-                    if (!r.hit) {
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            const float q = (thr[c] * sky[c]) * 16777216.0f;
-                            if (q == q && q > 0.0f) atomicAdd(&wacc[pix * 3 + c], (uint32_t)__float2ull_rz(q));
-                        }
-                        has_path = false;
-                    } else {
-                        const uchar4 s = fetch_texel(Ip->rgba, Ip->w, Ip->h, Ip->d, Ip->remap_identity != 0, r.v);
-                        thr[0] = thr[0] * dec[s.x];
-                        thr[1] = thr[1] * dec[s.y];
-                        thr[2] = thr[2] * dec[s.z];
-                        if (bounce == fp.bounces) {
-                            has_path = false; // path length exhausted: contributes nothing
-                        } else {
-                            ++bounce;
-                            const uint32_t lm = r.steps ? r.last_mask : (1u << entry_axis);
-                            const int a = (lm & 1u) ? 0 : ((lm & 2u) ? 1 : 2);
-                            rng_sphere(rng, ndir);
-                            int nsign = 0;
-                            const float t = r.steps ? ((a == 0 ? r.side[0] : (a == 1 ? r.side[1] : r.side[2])) -
-                                                       (a == 0 ? r.delta[0] : (a == 1 ? r.delta[1] : r.delta[2])))
-                                                    : 0.0f;
-                            const float tl = t / r.len;
-#pragma unroll
-                            for (int k = 0; k < 3; ++k) {
-                                float p = r.pos[k] + r.dir[k] * tl;
-                                const float lo = (float)r.v[k], hi = (float)(r.v[k] + 1);
-                                p = p < lo ? lo : p;
-                                p = p > hi ? hi : p;
-                                npos[k] = p;
-                                nsv[k] = r.v[k];
-                                if (k == a) {
-                                    nsign = r.step[k] != 0 ? -r.step[k] : (r.pos[k] <= 0.5f * size[k] ? -1 : 1);
-                                    npos[k] = (float)(r.v[k] + (nsign > 0 ? 1 : 0));
-                                    nsv[k] += nsign;
-                                    ndir[k] += (float)nsign;
-                                }
-                            }
-                            const float l2 = (ndir[0] * ndir[0] + ndir[1] * ndir[1]) + ndir[2] * ndir[2];
-                            if (l2 < 1e-6f) {
-#pragma unroll
-                                for (int k = 0; k < 3; ++k) ndir[k] = (k == a) ? (float)nsign : 0.0f;
-                            } else {
-                                const float rl = 1.0f / sqrtf(l2);
-                                ndir[0] *= rl; ndir[1] *= rl; ndir[2] *= rl;
-                            }
-                            rays += 1;
-                            entry_axis = a;
-                            new_ray = true;
-                            new_has_start = true;
-                        }
-                    }
-                }
-                // ---- (ii) lanes without a path take the next jobs of the pool --------------------
-                for (;;) {
-                    const bool need = !has_path;
-                    const uint32_t m = __ballot_sync(0xffffffffu, need);
-                    if (!m || next >= njobs) break;
-                    const uint32_t avail = njobs - next;
-                    const uint32_t rank = __popc(m & lt_mask);
-                    if (need && rank < avail) {
-                        const uint32_t job = next + rank;          // sample-major: neighbouring lanes get neighbouring pixels
-                        const uint32_t si = job / ncov, ci = job - si * ncov;
-                        pix = __fns(cov, 0, ci + 1);                // ci-th covered pixel of the tile
-                        const int px = tx0 + (int)(pix & 7u), py = ty0 + (int)(pix >> 3);
-                        const uint32_t sample = fp.sample_first + (s0 + si) * fp.sample_stride;
-                        rng_init(rng, fp.seed, (uint32_t)py * (uint32_t)fp.width + (uint32_t)px, sample);
-                        const float jx = rng_u01(rng), jy = rng_u01(rng);
-                        const float fx = (float)px + jx, fy = (float)py + jy;
-                        rays += 1;
-                        // camera ray in the instance's model space: o = eye, d = dirm * (x_ndc, y_ndc, 1)
-                        const float x_ndc = fx * fp.sxn - 1.0f;
-                        const float y_ndc = fy * fp.syn - 1.0f;
-                        float d[3], o[3], lo3[3], hi3[3];
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) {
-                            d[k] = (Ip->dirm[0 * 3 + k] * x_ndc + Ip->dirm[1 * 3 + k] * y_ndc) + Ip->dirm[3 * 3 + k];
-                            o[k] = Ip->eye_m[k];
-                            lo3[k] = Ip->slab_lo[k];
-                            hi3[k] = Ip->slab_hi[k];
-                        }
-                        float tn;
-                        int axis;
-                        if (!slab_unit_cube(o, lo3, hi3, d, tn, axis)) { // leaves through the sky
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) atomicAdd(&wacc[pix * 3 + c], (uint32_t)__float2ull_rz((1.0f * sky[c]) * 16777216.0f));
-                        } else {
-                            float mp[3];
-                            entry_point(o, d, tn, axis, mp);
-#pragma unroll
-                            for (int k = 0; k < 3; ++k) {
-                                ndir[k] = d[k];
-                                npos[k] = (mp[k] + 0.5f) * size[k];
-                            }
-                            has_path = true;
-                            bounce = 0;
-                            thr[0] = thr[1] = thr[2] = 1.0f;
-                            entry_axis = axis;
-                            new_ray = true;
-                            new_has_start = false;
-                        }
-                    }
-                    next += __popc(m) < avail ? __popc(m) : avail;
-                }
-                // ---- (iii) bounce rays and new primaries start their walk together (trace.frag:63-71) ---
-                if (new_ray) {
-                    const DdaMode mode = dda_init(vol, npos, ndir, new_has_start, nsv, r, idx);
-                    prev = idx; steps = 0;
-                    sx = r.side[0]; sy = r.side[1]; sz = r.side[2];
-                    ix = (uint32_t)r.step[0]; iy = (uint32_t)r.step[1] << xb; iz = (uint32_t)r.step[2] << zb;
-                    pending = true;
-                    fast = mode == kDdaFast;
-                    walking = fast;
-                    if (mode == kDdaSlow) {
-                        dda_slow<kSmem>(vol, r); // rare: runs to completion here; r.hit / r.steps / r.last_mask final
-                        iters += r.steps;
-                    }
-                    if (!fast) idx = 0;
-                }
-                // ---- done when nobody holds a path (the pool is exhausted then) -------------------
-                if (!__ballot_sync(0xffffffffu, has_path)) break;
-                // ---- (iv) march: every lane executes the step; parked lanes sit on a stop bit --------
-                {
-                    const int n0 = __popc(__ballot_sync(0xffffffffu, walking));
-                    const int thresh = n0 < (int)fp.refill_threshold ? n0 : (int)fp.refill_threshold;
-                    if (n0) {
-                        do {
-#pragma unroll
-                            for (int u = 0; u < 4; ++u)
-                                walking = dda_step<kSmem>(vol, sx, sy, sz, r.delta[0], r.delta[1], r.delta[2], idx, prev, steps, ix, iy, iz);
-                        } while (__popc(__ballot_sync(0xffffffffu, walking)) >= thresh);
-                    }
-                }
-            }
-            // ---- pool drained: add the tile's sums to the frame accumulators ---------------------
-            __syncwarp();
-            if (may_hit) {
-                const size_t p = (size_t)my_py * (size_t)fp.width + (size_t)my_px;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) fb.accum[3 * p + c] += (unsigned long long)wacc[lane * 3 + c];
-            }
-            __syncwarp();
-        }
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        rays += __shfl_xor_sync(0xffffffffu, rays, o);
-        iters += __shfl_xor_sync(0xffffffffu, iters, o);
-    }
-    if (lane == 0) {
-        if (rays) atomicAdd(fb.stats + 0, rays);
-        if (iters) atomicAdd(fb.stats + 1, iters);
+        if (analytic) atomicAdd(fb.stats + 3, analytic);
     }
 }
 
@@ -1691,8 +1446,6 @@ cudaError_t configure_kernels(int max_smem_optin) {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(trace_paths_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(trace_paths_single_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
-    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(trace_paths_wave_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(trace_paths_wave_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
@@ -1745,7 +1498,7 @@ cudaError_t launch_trace_paths(const FrameParams& fp, const InstUniforms* inst, 
         }
         return cudaGetLastError();
     }
-    if (fp.n_inst == 1 && !(fp.flags & (VT_FLAG_PERSISTENT_LANES | VT_FLAG_PER_PIXEL_PATHS))) {
+    if (fp.n_inst == 1 && !(fp.flags & VT_FLAG_PER_PIXEL_PATHS)) {
         // single-instance scenes: warp-local wavefront engine (paths_wave.cuh)
         const size_t wsmem = wave_smem_bytes(arena_words, masks_in_smem);
         const int max_warps = 1 << 30; // persistent: one resident wave, work is claimed dynamically
@@ -1755,16 +1508,6 @@ cudaError_t launch_trace_paths(const FrameParams& fp, const InstUniforms* inst, 
         } else {
             int grid = persistent_grid(trace_paths_wave_kernel<false>, wsmem, sm_count, max_warps, kWaveThreads);
             trace_paths_wave_kernel<false><<<grid, kWaveThreads, wsmem, stream>>>(fp, inst, mask_arena, arena_words, lut, fb);
-        }
-        return cudaGetLastError();
-    }
-    if (fp.n_inst == 1 && (fp.flags & VT_FLAG_PERSISTENT_LANES)) { // opt-in persistent-lane schedule (single-instance scenes)
-        if (masks_in_smem) {
-            const int grid = persistent_grid(trace_paths_single_kernel<true>, smem, sm_count, n_tiles);
-            trace_paths_single_kernel<true><<<grid, kBlockThreads, smem, stream>>>(fp, inst, mask_arena, arena_words, lut, fb);
-        } else {
-            const int grid = persistent_grid(trace_paths_single_kernel<false>, smem, sm_count, n_tiles);
-            trace_paths_single_kernel<false><<<grid, kBlockThreads, smem, stream>>>(fp, inst, mask_arena, arena_words, lut, fb);
         }
         return cudaGetLastError();
     }

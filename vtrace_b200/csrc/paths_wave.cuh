@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
     unsigned long long sky_q[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) sky_q[c] = __float2ull_rz((1.0f * sky[c]) * 16777216.0f);
-    unsigned long long rays = 0, iters = 0;
+    unsigned long long rays = 0, iters = 0, analytic = 0;
 
     // ---- prologue: pixels outside the screen rectangle see only sky, for every sample.  No other
     // warp ever touches them, so a plain read-modify-write is enough (they still count as rays).
@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
                     for (int c = 0; c < 3; ++c) fb.accum[3 * p + c] += sky_q[c] * fp.sky_spp;
                 }
                 rays += fp.spp;
+                analytic += fp.spp;
             }
         }
     }
@@ -498,9 +499,11 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
     for (int o = 16; o; o >>= 1) {
         rays += __shfl_xor_sync(0xffffffffu, rays, o);
         iters += __shfl_xor_sync(0xffffffffu, iters, o);
+        analytic += __shfl_xor_sync(0xffffffffu, analytic, o);
     }
     if (lane == 0) {
         if (rays) atomicAdd(fb.stats + 0, rays);
         if (iters) atomicAdd(fb.stats + 1, iters);
+        if (analytic) atomicAdd(fb.stats + 3, analytic);
     }
 }

@@ -64,8 +64,6 @@ struct State {
     uint32_t* d_world_list = nullptr;
     uint32_t world_list_cap = 0;
     bool world_used = false;
-    float last_P[16] = {0}, last_V[16] = {0};
-    bool last_clear = false, last_resolve = false;
 
     // tables
     uint32_t clear_rgba = 0;
@@ -93,7 +91,7 @@ struct State {
     bool fused_sync = true;
     unsigned long long* fused_sum = nullptr; // root, on demand: materialised sums for vt_read_accum
     unsigned long long* d_stats = nullptr;
-    unsigned long long* h_stats = nullptr; // pinned: kRing slots of 2 counters
+    unsigned long long* h_stats = nullptr; // pinned: kRing slots of 4 counters (rays, iterations, work-claim counter, analytic rays)
     void* h_readback = nullptr;            // pinned staging for vt_read_*
     size_t readback_size = 0;
 
@@ -127,7 +125,10 @@ int fail(const char* fmt, ...) {
 #define CK(call)                                                                                   \
     do {                                                                                           \
         cudaError_t e_ = (call);                                                                   \
-        if (e_ != cudaSuccess) return fail("%s -> %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        if (e_ != cudaSuccess) {                                                                   \
+            (void)cudaGetLastError(); /* a recoverable failure must not poison the next launch's cudaGetLastError() */ \
+            return fail("%s -> %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);    \
+        }                                                                                          \
     } while (0)
 
 uint32_t env_u32(const char* name, uint32_t dflt) {
@@ -230,22 +231,17 @@ int finish_frame() {
     if (!g.frame_pending) return 0;
     CK(cudaStreamSynchronize(g.stream));
     g.frame_pending = false;
-    // the binner reports how many list entries it needed; if they did not fit, the frame is incomplete:
-    // grow the list and render it again
-    for (int attempt = 0; g.bins_used && *g.h_bin_cursor > g.bin_cap_list && attempt < 4; ++attempt) {
+    // the binner reports how many list entries it needed.  Bins whose segment did not fit made their pixels visit
+    // every instance (kernels.cu, bin_range) — exact, only slower, and free of side effects whoever owns the
+    // accumulator clear — so nothing is rendered again: the next frame simply gets a larger list.
+    if (g.bins_used && *g.h_bin_cursor > g.bin_cap_list) {
         const uint32_t need = *g.h_bin_cursor + *g.h_bin_cursor / 2;
         cudaFree(g.d_bin_list);
         g.d_bin_list = nullptr;
         g.bin_cap_list = 0;
         CK(cudaMalloc(&g.d_bin_list, (size_t)need * 4));
         g.bin_cap_list = need;
-        g.stats.frames -= 1;
-        float P[16], V[16];
-        memcpy(P, g.last_P, sizeof P);
-        memcpy(V, g.last_V, sizeof V);
-        if (render_async(P, V, g.last_clear, g.last_resolve)) return -1;
-        CK(cudaStreamSynchronize(g.stream));
-        g.frame_pending = false;
+        g.stats.bin_list_grown += 1;
     }
     if (g.fused_mode && g.d_fused_err) { // did a flag wait give up?  (the stream is idle here: a blocking 4-byte copy)
         CK(cudaMemcpy(g.h_fused_err, g.d_fused_err, 4, cudaMemcpyDeviceToHost));
@@ -274,14 +270,19 @@ int finish_frame() {
             g.stats.trace_frames += 1;
         }
         if (cudaEventElapsedTime(&ms, g.ev_begin[slot], g.ev_end[slot]) == cudaSuccess) g.stats.last_frame_ms = ms;
-        const unsigned long long* hs = g.h_stats + 2 * slot;
+        const unsigned long long* hs = g.h_stats + 4 * slot;
         if (g.cfg.mode == VT_MODE_PRIMARY || g.cfg.mode == VT_MODE_RAYS) {
             g.stats.rays = (uint64_t)g.cfg.width * g.cfg.height + hs[0]; // + shadow rays
             g.stats.iterations = hs[1];
+            g.stats.analytic_rays = 0;
         } else {
             g.stats.rays = hs[0];
             g.stats.iterations = hs[1];
+            g.stats.analytic_rays = hs[3];
         }
+        g.stats.rays_sum += g.stats.rays;
+        g.stats.iterations_sum += g.stats.iterations;
+        g.stats.analytic_rays_sum += g.stats.analytic_rays;
     }
     return 0;
 }
@@ -334,7 +335,7 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
     fp.clear_rgba = g.clear_rgba;
     fp.sky_spp = g.cfg.spp;
     if (g.fused_mode && g.cfg.mode == VT_MODE_PATHS) {
-        if (g.inst_count != 1 || g.any_bricks || (g.cfg.flags & (VT_FLAG_PERSISTENT_LANES | VT_FLAG_PER_PIXEL_PATHS)))
+        if (g.inst_count != 1 || g.any_bricks || (g.cfg.flags & VT_FLAG_PER_PIXEL_PATHS))
             return fail("fused cross-GPU accumulation needs the single-instance wavefront kernel");
         if (g.fused_pixels != (size_t)g.cfg.width * g.cfg.height) return fail("fused accumulation buffer does not match the framebuffer size");
         fp.sky_spp = 0u; // pixels outside the screen rectangle are resolved analytically on the root
@@ -352,11 +353,6 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
         g.vols_dirty = false;
     }
     if (ensure_instances(g.inst_count)) return -1;
-
-    memcpy(g.last_P, P, sizeof g.last_P);
-    memcpy(g.last_V, V, sizeof g.last_V);
-    g.last_clear = clear_accum;
-    g.last_resolve = resolve;
 
     CK(cudaEventRecord(g.ev_begin[slot], g.stream));
     uint32_t* consumed_flag = nullptr;
@@ -482,7 +478,7 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
             g.stats.launches += 1;
         }
     }
-    CK(cudaMemcpyAsync(g.h_stats + 2 * slot, g.d_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaMemcpyAsync(g.h_stats + 4 * slot, g.d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g.stream));
     CK(cudaEventRecord(g.ev_end[slot], g.stream));
     g.ring_head += 1;
     g.frame_pending = true;
@@ -501,8 +497,8 @@ int64_t read_back(const void* d_src, size_t bytes, void* out, size_t capacity) {
     if (!pinned) (void)cudaGetLastError();
     if (!pinned && ensure_readback(bytes)) return -1;
     void* dst = pinned ? out : g.h_readback;
+    if (finish_frame()) return -1; // (first: whatever finishing a frame may enqueue must precede the copy)
     if (cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, g.stream) != cudaSuccess) return fail("read-back copy failed");
-    if (finish_frame()) return -1;
     if (cudaStreamSynchronize(g.stream) != cudaSuccess) return fail("read-back sync failed");
     if (!pinned) memcpy(out, g.h_readback, bytes);
     return (int64_t)bytes;
@@ -522,12 +518,16 @@ extern "C" uint64_t entry(void) {
         fail("no CUDA device: %s", cudaGetErrorString(e));
         return ((uint64_t)(uint32_t)e << 32) | 1u;
     }
-    if (dev >= count) dev = 0;
+    if (dev >= count) { // (silently falling back to device 0 would stack several ranks on one GPU)
+        fail("device %d requested (VT_DEVICE / LOCAL_RANK) but only %d CUDA device(s) are visible", dev, count);
+        return 6u;
+    }
     g.device = dev;
 #define CKE(call)                                                                     \
     do {                                                                              \
         cudaError_t e_ = (call);                                                      \
         if (e_ != cudaSuccess) {                                                      \
+            (void)cudaGetLastError();                                                 \
             fail("%s -> %s", #call, cudaGetErrorString(e_));                          \
             return ((uint64_t)(uint32_t)e_ << 32) | 2u;                               \
         }                                                                             \
@@ -578,8 +578,8 @@ extern "C" uint64_t entry(void) {
     CKE(cudaMalloc(&g.d_bin_cursor, 4));
     CKE(cudaMallocHost(&g.h_bin_cursor, 4));
     *g.h_bin_cursor = 0;
-    CKE(cudaMallocHost(&g.h_stats, 2 * State::kRing * sizeof(unsigned long long)));
-    memset(g.h_stats, 0, 2 * State::kRing * sizeof(unsigned long long));
+    CKE(cudaMallocHost(&g.h_stats, 4 * State::kRing * sizeof(unsigned long long)));
+    memset(g.h_stats, 0, 4 * State::kRing * sizeof(unsigned long long));
 
     // defaults: the reference's fixed 1000x1000 window (lib/entry.c:62), overridable from the
     // environment so the unmodified Rust engine can be configured without new calls
@@ -600,6 +600,7 @@ extern "C" uint64_t entry(void) {
     g.refill_batch = env_u32("VT_REFILL_BATCH", 6);
     g.item_spp = env_u32("VT_ITEM_SPP", 16);
     if (g.item_spp < 1) g.item_spp = 1;
+    if (g.item_spp > 255) g.item_spp = 255; // an item's per-pixel sums live in 32-bit shared counters: 255 samples of < 2^24 each
     g.items_per_warp = env_u32("VT_ITEMS_PER_WARP", 6);
     if (g.items_per_warp < 1) g.items_per_warp = 1;
     if (g.refill_batch < 1) g.refill_batch = 1;
@@ -1110,6 +1111,7 @@ extern "C" int32_t vt_get_stats(vt_stats* out) {
     *out = g.stats;
     g.stats.trace_ms_sum = 0.0f; // the sums cover the frames since the previous call
     g.stats.trace_frames = 0;
+    g.stats.rays_sum = g.stats.iterations_sum = g.stats.analytic_rays_sum = 0;
     return 0;
 }
 
