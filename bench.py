@@ -378,6 +378,8 @@ def run_cuda(args):
     (t2, t2_trace), (rays2_all, iters2_all, analytic2_all) = reduce_over_ranks([sum(ms2), trace2_sum], [rays2, iters2, analytic2])
     cam["P"], cam["V"] = P, V
 
+    masks_in_smem = bool(r.stats().masks_in_smem)
+
     # ---- measured cache rooflines (plain streaming kernels of the library, untimed region) ----
     peaks = {}
     if rank == 0:
@@ -445,7 +447,7 @@ def run_cuda(args):
                         ("partial sums pushed into rank 0's memory over NVLink peer stores, ordered by " +
                          ("flags in peer memory" if fused_flags else "a 4-byte NCCL stream barrier")) if fused
                         else "NCCL all-reduce of 3*w*h int64")) if world > 1 else "single rank",
-                    "masks_in_smem": bool(r.stats().masks_in_smem), "ms_per_step_min": min(ms), "ms_per_step_median": statistics.median(ms)},
+                    "masks_in_smem": masks_in_smem, "ms_per_step_min": min(ms), "ms_per_step_median": statistics.median(ms)},
             "traced_rays_per_step": traced / steps, "traced_mrays_per_s": traced / (t_res * 1e-3) / 1e6,
             "analytic_sky_samples_per_step": analytic_all / steps,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(inst.nbytes + 128),
