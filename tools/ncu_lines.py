@@ -71,6 +71,7 @@ def main():
     ap.add_argument("--so", default=os.path.join(ROOT, "vtrace_b200", "librender.so"))
     ap.add_argument("--top", type=int, default=40)
     ap.add_argument("--regex", default=None, help="ncu -k regex when the report holds several kernels")
+    ap.add_argument("--sass", default=None, help="FILE:LINE — list every SASS instruction attributed to that source line with its counters")
     ap.add_argument("--buckets", action="store_true",
                     help="aggregate per code region: a region starts at a '// ----' banner comment or a function definition")
     args = ap.parse_args()
@@ -101,6 +102,20 @@ def main():
     print(f"kernel instructions: {n}; warp-inst executed {tot_inst:,}; thread-inst {tot_thr:,}; "
           f"SIMT efficiency {tot_thr / max(tot_inst, 1) / 32:.3f}; samples {tot_samp:,}")
     print("stall reasons (all samples):", ", ".join(f"{k[6:]}={v}" for k, v in stalls.most_common(8)))
+    if args.sass:
+        want_f, _, want_l = args.sass.partition(":")
+        print(f"{'offset':>8}{'inst%':>7}{'samp%':>7}{'lanes':>6}  top stall        sass")
+        for k in range(n):
+            off, text, f, line = sass[k]
+            if os.path.basename(f or "?") != want_f or (want_l and line != int(want_l)):
+                continue
+            r = body[k]
+            inst = int(r[col["Instructions Executed"]] or 0)
+            thr = int(r[col["Thread Instructions Executed"]] or 0)
+            samp = int(r[col["# Samples"]] or 0)
+            st = max(stall_cols, key=lambda h: int(r[col[h]] or 0)) if samp else ""
+            print(f"{off:8x}{100 * inst / max(tot_inst, 1):7.2f}{100 * samp / max(tot_samp, 1):7.2f}{thr / max(inst, 1):6.1f}  {st[6:]:<16} {text[:80]}")
+        return
     lines_cache = {}
 
     def text_of(fname, line):

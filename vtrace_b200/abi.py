@@ -87,7 +87,8 @@ _lib = None
 
 
 def library_path() -> str:
-    return _build.LIB
+    # VT_LIBRENDER: a side-by-side build of the same sources (python -m vtrace_b200.build --variant ...), for A/B timing
+    return os.environ.get("VT_LIBRENDER") or _build.LIB
 
 
 def load(build_if_missing: bool = True) -> C.CDLL:

@@ -108,5 +108,35 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(name: str, defs: list[str]) -> str:
+    """Side-by-side build with extra -D flags into variants/NAME/librender.so (git-ignored; for A/B timing via VT_LIBRENDER)."""
+    out_dir = os.path.join(ROOT, "variants", name)
+    os.makedirs(out_dir, exist_ok=True)
+    objs = []
+
+    def compile_one(src: str):
+        out = os.path.join(out_dir, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc(), *NVCC_FLAGS, *defs, "-ccbin", "/usr/bin/g++", "-c", "-o", out, os.path.join(CSRC, src)]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError(proc.stdout + proc.stderr)
+        return out, proc.stderr
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    objs = [o for o, _ in results]
+    with open(os.path.join(out_dir, "build.log"), "w") as f:
+        f.write("".join(t for _, t in results))
+    lib = os.path.join(out_dir, "librender.so")
+    subprocess.run([nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++", "-shared", "-o", lib, *objs], check=True)
+    for o in objs:
+        os.remove(o)
+    return lib
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv or "-v" in sys.argv))
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], [a for a in sys.argv[i + 2:] if a.startswith("-D")]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv or "-v" in sys.argv))

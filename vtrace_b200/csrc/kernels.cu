@@ -1498,7 +1498,7 @@ cudaError_t launch_trace_paths(const FrameParams& fp, const InstUniforms* inst, 
         }
         return cudaGetLastError();
     }
-    if (fp.n_inst == 1 && !(fp.flags & VT_FLAG_PER_PIXEL_PATHS)) {
+    if (fp.n_inst == 1 && !(fp.flags & VT_FLAG_PER_PIXEL_PATHS) && fp.max_idx_bits <= kWaveIdxBits) {
         // single-instance scenes: warp-local wavefront engine (paths_wave.cuh)
         const size_t wsmem = wave_smem_bytes(arena_words, masks_in_smem);
         const int max_warps = 1 << 30; // persistent: one resident wave, work is claimed dynamically
@@ -1520,6 +1520,15 @@ cudaError_t launch_trace_paths(const FrameParams& fp, const InstUniforms* inst, 
     }
     return cudaGetLastError();
 }
+
+#ifdef VT_WAVE_STATS
+cudaError_t read_wave_stats(unsigned long long* out16) {
+    cudaError_t e = cudaMemcpyFromSymbol(out16, vt_wave_stats, 32 * sizeof(unsigned long long));
+    if (e != cudaSuccess) return e;
+    unsigned long long zero[32] = {};
+    return cudaMemcpyToSymbol(vt_wave_stats, zero, sizeof zero);
+}
+#endif
 
 cudaError_t launch_resolve(const unsigned long long* accum, uint32_t n_pixels, uint32_t total_spp, SrgbTables lut, uchar4* color,
                            cudaStream_t stream) {

@@ -70,6 +70,7 @@ struct FrameParams {
     uint32_t items_per_warp;  // wavefront kernel: work items wanted per resident warp, VT_ITEMS_PER_WARP
     float sun[3];              // unit vector towards the sun, world space (shadow-ray extension)
     uint32_t any_bricks;       // the scene contains a procedural brick volume
+    uint32_t max_idx_bits;     // widest stop-mask bit index of the scene's dense volumes
     uint32_t clear_rgba;       // clear colour (lib/command.c:56-61) as stored by the sRGB target: r | g<<8 | b<<16 | a<<24
     uint32_t sky_spp;          // samples whose sky radiance this rank adds for pixels outside every screen
                                // rectangle (= spp normally; fused multi-GPU reduction: total on the root, 0 elsewhere)

@@ -2,20 +2,23 @@
 // (BASELINE configs[2]) as a warp-local wavefront engine.  Included from kernels.cu (namespace vt).
 //
 // Same paths, same arithmetic, same integer sums as trace_path() — only the schedule differs.
-// The per-pixel kernel runs at ~47 % SIMT efficiency (ncu: 15 of 32 lanes): rays of one warp need
-// 0..150 DDA iterations, paths end after 1..5 segments, and regenerating a ray (shade + bounce, or
-// a new camera ray) is as expensive as marching it.  Here every warp owns a pool of kSlots paths in
-// shared memory and only ever runs one kind of work at a time, on full batches:
+// Rays of one warp need 0..150 DDA iterations (16.5 on average in the bench scene), paths end after
+// 1..5 segments, and regenerating a ray (shade + bounce, or a new camera ray) costs as much as
+// marching it.  Every warp owns a pool of kSlots paths in shared memory and only ever runs one kind
+// of work at a time, on full batches:
 //
-//   classify : slot owners decode rays that stopped -> HIT (wait for a bounce batch) or MISS
-//              (sky radiance is added with integer atomics, slot freed);
-//   primary  : when >= 32 slots are free, 32 lanes start 32 new camera rays (jobs = covered
-//              pixel x sample, claimed per (tile, 16-sample) item from a global counter);
-//   bounce   : when >= 32 slots hold hits, 32 lanes shade and bounce them;
-//   march    : lanes pull READY rays from the pool, step them together (parked lanes sit on a
-//              stop bit, so the loop has no per-lane branch), write the exit state back when a
-//              ray stops and immediately pull the next one; when the READY list is empty and fewer
-//              than `refill_threshold` lanes still walk, the rest is parked back into the pool.
+//   primary : when >= 32 slots are free, 32 lanes start 32 new camera rays (jobs = covered
+//             pixel x sample, claimed per (tile, samples) item from a global counter);
+//   bounce  : when >= 32 slots hold hits, 32 lanes shade and bounce them;
+//   sky     : when >= 32 slots hold rays that left the volume, 32 lanes add their sky radiance
+//             (integer atomics) and free the slots;
+//   march   : lanes pull READY rays from the pool and step them together.  The stepping loop is one
+//             PTX block, fully predicated (a lane whose ray stopped — or that has no ray — keeps its
+//             "stopped" predicate and executes nothing): 16 SASS instructions per voxel step, no
+//             branch inside a burst of 4 steps, one vote per burst.  When `refill_batch` lanes have
+//             stopped they decode hit / miss, write their exit state and pull the next READY rays;
+//             when the READY list is empty and fewer than `refill_threshold` lanes still walk, the
+//             rest is parked back into the pool.
 //
 // Everything is warp-local (__syncwarp only): no inter-warp queues, no block barriers after the
 // prologue.  Radiance is 2^-24 fixed point added with integer atomics, RNG streams are keyed by
@@ -23,7 +26,8 @@
 //
 // Slot layout (96 bytes, 3 + 3 uint4; the 48-byte stride makes 128-bit accesses of consecutive
 // slots bank-conflict-free):
-//   ray  q0 = side.xyz, idx      q1 = delta.xyz, step signs      q2 = prev, steps, state, pixel
+//   ray  q0 = side.xyz, idx      q1 = signed delta.xyz (len / dir), step signs
+//        q2 = prev idx, steps | state << 24, -, pixel handle
 //   path p0 = thr.rgb, rng key   p1 = pos.xyz, len               p2 = dir.xyz, meta
 //
 // Multi-GPU: fb.accum may point at ANOTHER GPU's accumulation buffer (CUDA IPC mapping over NVLink,
@@ -31,14 +35,38 @@
 // and commute, so N ranks tracing disjoint samples add into one buffer with no separate all-reduce.
 #pragma once
 
-static constexpr int kWaveWarps = 12;
+// Shape of a CTA: warps, paths in flight per warp, CTAs per SM.  (Compile-time knobs so that variants can be
+// built side by side: python -m vtrace_b200.build --variant NAME -DVT_WAVE_WARPS=.. -DVT_WAVE_SLOTS=.. -DVT_WAVE_CTAS=..)
+#ifndef VT_WAVE_WARPS
+#define VT_WAVE_WARPS 12
+#endif
+#ifndef VT_WAVE_SLOTS
+#define VT_WAVE_SLOTS 64
+#endif
+#ifndef VT_WAVE_CTAS
+#define VT_WAVE_CTAS 2
+#endif
+static constexpr int kWaveWarps = VT_WAVE_WARPS;
 static constexpr int kWaveThreads = kWaveWarps * 32;
-static constexpr int kSlots = 64;        // paths in flight per warp
-static constexpr int kSlotGroups = kSlots / 32;
+static constexpr int kWaveCtas = VT_WAVE_CTAS;
+static constexpr int kSlots = VT_WAVE_SLOTS; // paths in flight per warp
+static constexpr int kSlotGroups = (kSlots + 31) / 32;
+static_assert(kSlots % 16 == 0 && kSlots >= 32 && kSlots <= 256, "slot ids travel as bytes; the pool is 16-byte granular");
 static constexpr uint32_t kPoolBytes = kSlots * 96 + kSlots + 32 + 32 * 3 * 4; // slots + byte list + covered-pixel table + tile accumulators
 static_assert(kPoolBytes % 16 == 0, "pool alignment");
+// The march keeps "previous index" and the step count modulo 4 in one register: bits 30-31 are the
+// position inside the burst, so a volume's stop-mask index must fit 30 bits (launch_trace_paths checks).
+static constexpr uint32_t kWaveIdxBits = 30;
 
-enum SlotState : uint32_t { kFree = 0, kReady = 1, kDone = 3, kHit = 4 };
+// -DVT_WAVE_STATS (variant builds only): per-phase counters, read with vt_debug_wave_stats()
+#ifdef VT_WAVE_STATS
+__device__ unsigned long long vt_wave_stats[32];
+#define VT_STAT(i, v) (wstat[i] += (v))
+#else
+#define VT_STAT(i, v) ((void)0)
+#endif
+
+enum SlotState : uint32_t { kFree = 0, kReady = 1, kMiss = 2, kHit = 4 };
 
 size_t wave_smem_bytes(uint32_t arena_words, bool masks_in_smem) {
     return trace_smem_bytes(arena_words, masks_in_smem) + size_t(kWaveWarps) * kPoolBytes;
@@ -48,8 +76,72 @@ __device__ __forceinline__ uint32_t pack_signs(const int32_t step[3]) {
     return (uint32_t)(step[0] + 1) | ((uint32_t)(step[1] + 1) << 2) | ((uint32_t)(step[2] + 1) << 4);
 }
 
+// ---- the stepping loop -------------------------------------------------------------------------
+// One voxel step (trace.frag:76-86) of a lane whose "stopped" predicate ps is false; a lane with ps
+// set executes nothing.  %0-%2 side, %3 idx, %4 rec (previous idx | burst position << 30),
+// %8-%10 delta, %11-%13 index increments, %14 mask base.  LD = the mask word load for word index t.
+#define VT_WAVE_SUB(LD, REC)                                                                        \
+    "shr.u32 t, %3, 5;\n" LD                                                                         \
+    "shf.l.wrap.b32 b, 0, 1, %3;\n"                                                                  \
+    "lop3.or.b32 b|ps, b, w, 0, 0xc0, ps;\n" /* :78 filled (or border): the walk ends here       */ \
+    "min.f32 m, %0, %1;\n"                                                                           \
+    "min.f32 m, m, %2;\n"                                                                            \
+    "setp.eq.and.f32 px, %0, m, !ps;\n"   /* :83 mask = side <= min(other two)                   */ \
+    "setp.eq.and.f32 py, %1, m, !ps;\n"                                                              \
+    "setp.eq.and.f32 pz, %2, m, !ps;\n" REC                                                          \
+    "@px add.rn.f32 %0, %0, %8;\n"        /* :84                                                 */ \
+    "@py add.rn.f32 %1, %1, %9;\n"                                                                   \
+    "@pz add.rn.f32 %2, %2, %10;\n"                                                                  \
+    "@px add.s32 %3, %3, %11;\n"          /* :85                                                 */ \
+    "@py add.s32 %3, %3, %12;\n"                                                                     \
+    "@pz add.s32 %3, %3, %13;\n"
+#define VT_WAVE_LD_SMEM "shl.b32 t, t, 2;\n" "add.u32 t, t, %14;\n" "ld.shared.u32 w, [t];\n"
+#define VT_WAVE_LD_GLOBAL "mad.wide.u32 ta, t, 4, %14;\n" "ld.global.nc.u32 w, [ta];\n"
+#define VT_WAVE_LOOP(LD)                                                                            \
+    "{\n"                                                                                            \
+    ".reg .pred ps, px, py, pz, pc;\n"                                                               \
+    ".reg .u32 t, w, b, n;\n"                                                                        \
+    ".reg .u64 ta;\n"                                                                                \
+    ".reg .f32 m;\n"                                                                                 \
+    "setp.ne.u32 ps, %6, 0;\n"                                                                       \
+    "WAVE_LOOP:\n"                                                                                   \
+    VT_WAVE_SUB(LD, "@!ps mov.u32 %4, %3;\n")                                                        \
+    VT_WAVE_SUB(LD, "@!ps add.u32 %4, %3, 0x40000000;\n")                                            \
+    VT_WAVE_SUB(LD, "@!ps add.u32 %4, %3, 0x80000000;\n")                                            \
+    VT_WAVE_SUB(LD, "@!ps add.u32 %4, %3, 0xc0000000;\n")                                            \
+    "@!ps add.u32 %5, %5, 4;\n"           /* :86, four at a time                                 */ \
+    "vote.sync.ballot.b32 %7, ps, 0xffffffff;\n"                                                     \
+    "popc.b32 n, %7;\n"                                                                              \
+    "setp.lt.u32 pc, n, %15;\n"                                                                      \
+    "@pc bra.uni WAVE_LOOP;\n"                                                                       \
+    "selp.u32 %6, 1, 0, ps;\n"                                                                       \
+    "}\n"
+
+// Steps the warp's rays in bursts of four iterations until at least `k_stop` lanes are stopped (lanes
+// without a ray count as stopped and sit on the border bit idx 0).  `rec` must enter with bits 30-31
+// set; afterwards a lane's ray has taken steps + ((rec >> 30) + 1 & 3) iterations and the index before
+// its last iteration is rec & 0x3fffffff.  Returns the ballot of stopped lanes.
 template <bool kSmem>
-__global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const __grid_constant__ FrameParams fp,
+__device__ __forceinline__ uint32_t wave_walk(const Vol& vol, float& sx, float& sy, float& sz, float dx, float dy, float dz,
+                                              uint32_t& idx, uint32_t& rec, uint32_t& steps, uint32_t& stopped, uint32_t ix,
+                                              uint32_t iy, uint32_t iz, uint32_t k_stop) {
+    uint32_t v;
+    if (kSmem) {
+        const uint32_t base = smem_u32(vt_smem + kSmemMaskOff) + vol.mask_off * 4u;
+        asm volatile(VT_WAVE_LOOP(VT_WAVE_LD_SMEM)
+                     : "+f"(sx), "+f"(sy), "+f"(sz), "+r"(idx), "+r"(rec), "+r"(steps), "+r"(stopped), "=r"(v)
+                     : "f"(dx), "f"(dy), "f"(dz), "r"(ix), "r"(iy), "r"(iz), "r"(base), "r"(k_stop));
+    } else {
+        const uint32_t* base = vol.arena + vol.mask_off;
+        asm volatile(VT_WAVE_LOOP(VT_WAVE_LD_GLOBAL)
+                     : "+f"(sx), "+f"(sy), "+f"(sz), "+r"(idx), "+r"(rec), "+r"(steps), "+r"(stopped), "=r"(v)
+                     : "f"(dx), "f"(dy), "f"(dz), "r"(ix), "r"(iy), "r"(iz), "l"(base), "r"(k_stop));
+    }
+    return v;
+}
+
+template <bool kSmem>
+__global__ void __launch_bounds__(kWaveThreads, kWaveCtas) trace_paths_wave_kernel(const __grid_constant__ FrameParams fp,
                                                                           const InstUniforms* __restrict__ inst,
                                                                           const uint32_t* __restrict__ mask_arena,
                                                                           uint32_t arena_words, SrgbTables lut, FrameBuffers fb) {
@@ -68,6 +160,10 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
     uint8_t* list = reinterpret_cast<uint8_t*>(path + kSlots * 3);
     uint8_t* cov_pix = list + kSlots; // cov_pix[c] = tile-local index of the item's c-th covered pixel
     uint32_t* wacc = reinterpret_cast<uint32_t*>(cov_pix + 32); // radiance sums of the current item's tile (2^-24 fixed point)
+    uint8_t* ray_bytes = reinterpret_cast<uint8_t*>(ray);
+    // a slot's state is the top byte of q2.y
+    auto state_of = [&](uint32_t slot) -> uint32_t { return ray_bytes[slot * 48u + 39u]; };
+    auto set_state = [&](uint32_t slot, uint32_t s) { ray_bytes[slot * 48u + 39u] = (uint8_t)s; };
 
     const int tiles_x = (fp.width + kTileW - 1) / kTileW;
     const int tiles_y = (fp.height + kTileH - 1) / kTileH;
@@ -106,6 +202,10 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
 #pragma unroll
     for (int c = 0; c < 3; ++c) sky_q[c] = __float2ull_rz((1.0f * sky[c]) * 16777216.0f);
     unsigned long long rays = 0, iters = 0, analytic = 0;
+#ifdef VT_WAVE_STATS
+    uint32_t wstat[32];
+    for (int i = 0; i < 32; ++i) wstat[i] = 0;
+#endif
 
     // ---- prologue: pixels outside the screen rectangle see only sky, for every sample.  No other
     // warp ever touches them, so a plain read-modify-write is enough (they still count as rays).
@@ -129,10 +229,11 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
     }
 
 #pragma unroll
-    for (int g = 0; g < kSlotGroups; ++g) ray[(lane + 32 * g) * 3 + 2] = make_uint4(0u, 0u, kFree, 0u);
+    for (int g = 0; g < kSlotGroups; ++g)
+        if (lane + 32 * g < kSlots) ray[(lane + 32 * g) * 3 + 2] = make_uint4(0u, kFree << 24, 0u, 0u);
     wacc[lane * 3 + 0] = 0u; wacc[lane * 3 + 1] = 0u; wacc[lane * 3 + 2] = 0u;
     __syncwarp();
-    int n_free = kSlots, n_ready = 0, n_hit = 0, n_done = 0; // n_done: rays that stopped in the last march, not yet classified
+    int n_free = kSlots, n_ready = 0, n_hit = 0, n_miss = 0;
 
     // current work item (warp-uniform)
     bool work_left = true;
@@ -178,9 +279,12 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
     };
     // writes a ray that is about to walk (or whose slow-path result is final) into its slot
     auto store_ray = [&](uint32_t slot, const Dda& r, uint32_t idx, uint32_t prev, uint32_t steps, uint32_t state, uint32_t pixel) {
+        // the sign of len / dir is the step direction (the march needs nothing else); step == 0 travels in the packed signs
+        const float raw[3] = {r.step[0] < 0 ? -r.delta[0] : r.delta[0], r.step[1] < 0 ? -r.delta[1] : r.delta[1],
+                              r.step[2] < 0 ? -r.delta[2] : r.delta[2]};
         ray[slot * 3 + 0] = make_uint4(__float_as_uint(r.side[0]), __float_as_uint(r.side[1]), __float_as_uint(r.side[2]), idx);
-        ray[slot * 3 + 1] = make_uint4(__float_as_uint(r.delta[0]), __float_as_uint(r.delta[1]), __float_as_uint(r.delta[2]), pack_signs(r.step));
-        ray[slot * 3 + 2] = make_uint4(prev, steps, state, pixel);
+        ray[slot * 3 + 1] = make_uint4(__float_as_uint(raw[0]), __float_as_uint(raw[1]), __float_as_uint(raw[2]), pack_signs(r.step));
+        ray[slot * 3 + 2] = make_uint4(prev, steps | state << 24, 0u, pixel);
     };
     // Starts the walk of a fresh ray (pos, dir[, start voxel]) that belongs to `slot`.
     // Returns the slot's new state: kReady (fast walk pending), kHit (slow path hit), kFree (slow path miss).
@@ -210,7 +314,7 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
             }
         }
         add_sky(pixel, thr[0], thr[1], thr[2]); // missed (or never entered the padded volume)
-        ray[slot * 3 + 2] = make_uint4(0u, 0u, kFree, pixel);
+        ray[slot * 3 + 2] = make_uint4(0u, kFree << 24, 0u, pixel);
         return kFree;
     };
     // compacts the slots in `state` into list[0..), returns how many there are
@@ -219,7 +323,7 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
 #pragma unroll
         for (int g = 0; g < kSlotGroups; ++g) {
             const uint32_t slot = lane + 32 * g;
-            const bool f = ray[slot * 3 + 2].z == state;
+            const bool f = (kSlots % 32 == 0 || slot < (uint32_t)kSlots) && state_of(slot) == state;
             const uint32_t m = __ballot_sync(0xffffffffu, f);
             if (f) list[base + __popc(m & lt_mask)] = (uint8_t)slot;
             base += __popc(m);
@@ -229,36 +333,6 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
     };
 
     for (;;) {
-        // ---- classify: owners decode the rays that stopped -------------------------------------
-        if (n_done) {
-        n_done = 0;
-#pragma unroll
-        for (int g = 0; g < kSlotGroups; ++g) {
-            const uint32_t slot = lane + 32 * g;
-            const uint4 q2 = ray[slot * 3 + 2];
-            const bool done = q2.z == kDone;
-            bool hit = false;
-            if (done) {
-                const uint32_t idx = ray[slot * 3 + 0].w;
-                const int32_t vx = (int32_t)(idx & ((1u << xb) - 1u)) - 1;
-                const int32_t vy = (int32_t)((idx >> xb) & ((1u << vol.yb) - 1u)) - 1;
-                const int32_t vz = (int32_t)(idx >> zb) - 1;
-                hit = vx >= 0 && vx < (int32_t)vol.w && vy >= 0 && vy < (int32_t)vol.h && vz >= 0 && vz < (int32_t)vol.d;
-                iters += q2.y;
-                if (hit) {
-                    ray[slot * 3 + 2].z = kHit;
-                } else {
-                    const uint4 p0 = path[slot * 3 + 0];
-                    add_sky(q2.w, __uint_as_float(p0.x), __uint_as_float(p0.y), __uint_as_float(p0.z));
-                    ray[slot * 3 + 2].z = kFree;
-                }
-            }
-            n_hit += __popc(__ballot_sync(0xffffffffu, done && hit));
-            n_free += __popc(__ballot_sync(0xffffffffu, done && !hit));
-        }
-        __syncwarp();
-        }
-
         // ---- make sure there is a work item with jobs (or learn that the frame is exhausted) ------
         while (work_left && it_next >= it_njobs) {
             const int item = claim_tiles(fb.stats + 2, lane, 1);
@@ -293,16 +367,19 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
         const bool jobs = work_left && it_next < it_njobs;
 
         // ---- pick the next full batch (or the best partial one when the pool runs dry) -----------
-        int action; // 0 primary, 1 bounce, 2 march, 3 stop
+        int action; // 0 primary, 1 bounce, 2 march, 3 stop, 4 sky
         const int low = (int)fp.refill_threshold;
         const int can_primary = jobs ? n_free : 0;
         if (n_hit >= 32) action = 1;                          // full bounce batch
+        else if (n_miss >= 32) action = 4;                    // full sky batch
         else if (can_primary >= 32) action = 0;               // full camera batch
         else if (n_ready >= 32) action = 2;                   // a full warp of rays is waiting
+        else if (n_miss > 0 && jobs && n_free + n_miss >= 32) action = 4; // frees the slots a full camera batch needs
         else if (n_hit >= low && n_hit >= can_primary) action = 1; // otherwise top the pool up with the better partial batch
         else if (can_primary >= low) action = 0;
         else if (n_ready > 0) action = 2;
         else if (n_hit > 0) action = 1;
+        else if (n_miss > 0) action = 4;
         else if (can_primary > 0) action = 0;
         else action = 3;
         if (action == 3) break;
@@ -354,6 +431,7 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
                 }
             }
             it_next += n;
+            VT_STAT(0, 1); VT_STAT(1, n);
             const int nr = __popc(__ballot_sync(0xffffffffu, st == kReady)), nh = __popc(__ballot_sync(0xffffffffu, st == kHit));
             n_ready += nr; n_hit += nh; n_free -= nr + nh;
             __syncwarp();
@@ -368,13 +446,13 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
                 const uint4 p0 = path[slot * 3 + 0], p1 = path[slot * 3 + 1], p2 = path[slot * 3 + 2];
                 Dda r;
                 r.side[0] = __uint_as_float(q0.x); r.side[1] = __uint_as_float(q0.y); r.side[2] = __uint_as_float(q0.z);
-                r.delta[0] = __uint_as_float(q1.x); r.delta[1] = __uint_as_float(q1.y); r.delta[2] = __uint_as_float(q1.z);
+                r.delta[0] = fabsf(__uint_as_float(q1.x)); r.delta[1] = fabsf(__uint_as_float(q1.y)); r.delta[2] = fabsf(__uint_as_float(q1.z));
 #pragma unroll
                 for (int k = 0; k < 3; ++k) r.step[k] = (int32_t)((q1.w >> (2 * k)) & 3u) - 1;
                 r.pos[0] = __uint_as_float(p1.x); r.pos[1] = __uint_as_float(p1.y); r.pos[2] = __uint_as_float(p1.z);
                 r.len = __uint_as_float(p1.w);
                 r.dir[0] = __uint_as_float(p2.x); r.dir[1] = __uint_as_float(p2.y); r.dir[2] = __uint_as_float(p2.z);
-                dda_finish_fast(vol, r, q0.w, q2.x, q2.y);
+                dda_finish_fast(vol, r, q0.w, q2.x, q2.y & 0xFFFFFFu);
                 const uint32_t pixel = q2.w;
                 uint32_t bounce = p2.w & 15u;
                 const int entry_axis = (int)((p2.w >> 4) & 3u);
@@ -385,7 +463,7 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
                 thr[1] = thr[1] * dec[s.y];
                 thr[2] = thr[2] * dec[s.z];
                 if (bounce == fp.bounces) {
-                    ray[slot * 3 + 2].z = kFree; // path length exhausted: contributes nothing
+                    set_state(slot, kFree); // path length exhausted: contributes nothing
                     st = kFree;
                 } else {
                     ++bounce;
@@ -427,34 +505,54 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
                 }
             }
             const int nr = __popc(__ballot_sync(0xffffffffu, st == kReady)), nf = __popc(__ballot_sync(0xffffffffu, st == kFree));
+            VT_STAT(2, 1); VT_STAT(3, n);
             n_ready += nr; n_free += nf; n_hit -= nr + nf;
+            __syncwarp();
+        } else if (action == 4) {
+            // ---- sky batch: rays that left the volume add throughput x clear colour, slots are freed --
+            const int have = build_list(kMiss);
+            const int n = have < 32 ? have : 32;
+            if (lane < n) {
+                const uint32_t slot = list[lane];
+                const uint4 p0 = path[slot * 3 + 0];
+                add_sky(ray[slot * 3 + 2].w, __uint_as_float(p0.x), __uint_as_float(p0.y), __uint_as_float(p0.z));
+                set_state(slot, kFree);
+            }
+            VT_STAT(4, 1); VT_STAT(5, n);
+            n_miss -= n; n_free += n;
             __syncwarp();
         } else {
             // ---- march: pull READY rays, step them packed, write exits back --------------------------
             const int total = build_list(kReady); // == n_ready
+            VT_STAT(6, 1); VT_STAT(7, total);
             int rc = 0;
             int my_slot = -1;
-            uint32_t my_pixel = 0;
-            uint32_t idx = 0, prev = 0, steps = 0, ix = 0, iy = 0, iz = 0; // idx 0 = border bit: a parked lane's step is a no-op
+            uint32_t idx = 0, rec = 3u << 30, steps = 0, ix = 0, iy = 0, iz = 0; // idx 0 = border bit, where lanes without a ray sit
             float sx = 0.0f, sy = 0.0f, sz = 0.0f, dx = 0.0f, dy = 0.0f, dz = 0.0f;
+            uint32_t stopped = 1u;              // this lane has no walking ray
+            uint32_t idle_mask = 0xffffffffu;   // lanes without a ray
+            uint32_t hits = 0, misses = 0, it32 = 0;
             int thresh = -1;
-            uint32_t idle_mask = 0xffffffffu; // lanes without a ray
             for (;;) {
-                if (idle_mask && rc < total) { // hand the next READY rays to the idle lanes
-                    const bool idle = (idle_mask >> lane) & 1u;
+                if (rc < total) { // hand the next READY rays to the idle lanes
                     const int rank = __popc(idle_mask & lt_mask);
-                    if (idle && rc + rank < total) {
+                    if (my_slot < 0 && rc + rank < total) {
                         my_slot = list[rc + rank];
-                        const uint4 q0 = ray[my_slot * 3 + 0], q1 = ray[my_slot * 3 + 1], q2 = ray[my_slot * 3 + 2];
+                        const uint4 q0 = ray[my_slot * 3 + 0], q1 = ray[my_slot * 3 + 1];
+                        const uint2 q2 = *reinterpret_cast<const uint2*>(&ray[my_slot * 3 + 2]);
                         sx = __uint_as_float(q0.x); sy = __uint_as_float(q0.y); sz = __uint_as_float(q0.z); idx = q0.w;
-                        dx = __uint_as_float(q1.x); dy = __uint_as_float(q1.y); dz = __uint_as_float(q1.z);
-                        ix = (uint32_t)((int32_t)(q1.w & 3u) - 1);
-                        iy = (uint32_t)((int32_t)((q1.w >> 2) & 3u) - 1) << xb;
-                        iz = (uint32_t)((int32_t)((q1.w >> 4) & 3u) - 1) << zb;
-                        prev = q2.x; steps = q2.y; my_pixel = q2.w;
+                        dx = fabsf(__uint_as_float(q1.x)); dy = fabsf(__uint_as_float(q1.y)); dz = fabsf(__uint_as_float(q1.z));
+                        // step direction = sign of len / dir (never 0 on the fast path): +-1 in the axis' field of the index
+                        ix = (uint32_t)(((int32_t)q1.x >> 31) * 2 + 1);
+                        iy = (uint32_t)(((int32_t)q1.y >> 31) * 2 + 1) << xb;
+                        iz = (uint32_t)(((int32_t)q1.z >> 31) * 2 + 1) << zb;
+                        rec = q2.x | 3u << 30;
+                        steps = q2.y & 0xFFFFFFu;
+                        stopped = 0u;
                     }
                     const int want = __popc(idle_mask);
-                    rc += want < total - rc ? want : total - rc;
+                    const int got = want < total - rc ? want : total - rc;
+                    rc += got;
                     idle_mask = __ballot_sync(0xffffffffu, my_slot < 0);
                 }
                 const int nact = 32 - __popc(idle_mask);
@@ -464,32 +562,45 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
                     // too few lanes left: park them back into the pool and go generate more rays
                     if (my_slot >= 0) {
                         ray[my_slot * 3 + 0] = make_uint4(__float_as_uint(sx), __float_as_uint(sy), __float_as_uint(sz), idx);
-                        ray[my_slot * 3 + 2] = make_uint4(prev, steps, kReady, my_pixel);
+                        *reinterpret_cast<uint2*>(&ray[my_slot * 3 + 2]) = make_uint2(rec & 0x3fffffffu, steps | kReady << 24);
                     }
                     n_ready = nact;
+                    VT_STAT(10, nact);
                     break;
                 }
-                // Step (4 iterations between checks; idle lanes sit on a stop bit) until it pays to look at the
-                // stopped lanes: while READY rays remain, once `refill_batch` lanes can be refilled together;
-                // afterwards, once fewer than `thresh` lanes are left and the rest gets parked.
-                bool walking;
-                int nwalk;
-                const bool can_refill = rc < total;
-                do {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) walking = dda_step<kSmem>(vol, sx, sy, sz, dx, dy, dz, idx, prev, steps, ix, iy, iz);
-                    nwalk = __popc(__ballot_sync(0xffffffffu, walking));
-                } while (nwalk > 0 && (can_refill ? (nact - nwalk < (int)fp.refill_batch) : (nwalk >= thresh)));
-                if (my_slot >= 0 && !walking) { // stopped: filled voxel or border
+                // Step until it pays to look at the stopped lanes: while READY rays remain, once `refill_batch`
+                // lanes can be refilled together; afterwards, once fewer than `thresh` lanes still walk (the rest
+                // is then parked).  Lanes without a ray count as stopped.
+                uint32_t k_stop = rc < total ? (uint32_t)(32 - nact) + fp.refill_batch : (uint32_t)(33 - thresh);
+                k_stop = k_stop > 32u ? 32u : k_stop;
+                const uint32_t v = wave_walk<kSmem>(vol, sx, sy, sz, dx, dy, dz, idx, rec, steps, stopped, ix, iy, iz, k_stop);
+                VT_STAT(8, 1); VT_STAT(9, __popc(v & ~idle_mask)); VT_STAT(11, nact);
+                if (stopped && my_slot >= 0) { // the ray ended: on a filled voxel (hit) or on the border (left the volume)
+                    const uint32_t st = steps + (((rec >> 30) + 1u) & 3u);
+                    const uint32_t vx = (idx & ((1u << xb) - 1u)) - 1u, vy = ((idx >> xb) & ((1u << vol.yb) - 1u)) - 1u, vz = (idx >> zb) - 1u;
+                    const bool hit = vx < vol.w && vy < vol.h && vz < vol.d;
                     ray[my_slot * 3 + 0] = make_uint4(__float_as_uint(sx), __float_as_uint(sy), __float_as_uint(sz), idx);
-                    ray[my_slot * 3 + 2] = make_uint4(prev, steps, kDone, my_pixel);
+                    *reinterpret_cast<uint2*>(&ray[my_slot * 3 + 2]) = make_uint2(rec & 0x3fffffffu, st | (hit ? kHit : kMiss) << 24);
+                    it32 += st;
+#ifdef VT_WAVE_STATS
+                    { // histogram of ray lengths: 0, 1, 2, 3, 4-7, 8-15, 16-31, 32-63, 64+; hits get +9
+                        const int b = st < 4 ? (int)st : (st < 8 ? 4 : (st < 16 ? 5 : (st < 32 ? 6 : (st < 64 ? 7 : 8))));
+                        for (int k = 0; k < 9; ++k) {
+                            const uint32_t m = __ballot_sync(__activemask(), b == k);
+                            wstat[12 + k] += (lane == (__ffs(__activemask()) - 1)) ? __popc(m) : 0;
+                        }
+                    }
+#endif
+                    hits += hit ? 1u : 0u;
+                    misses += hit ? 0u : 1u;
                     my_slot = -1;
                     idx = 0;
                 }
-                const uint32_t now_idle = __ballot_sync(0xffffffffu, my_slot < 0);
-                n_done += __popc(now_idle & ~idle_mask);
-                idle_mask = now_idle;
+                idle_mask = v; // every stopped lane is idle now
             }
+            n_hit += (int)__reduce_add_sync(0xffffffffu, hits);
+            n_miss += (int)__reduce_add_sync(0xffffffffu, misses);
+            iters += it32;
             __syncwarp();
         }
     }
@@ -501,6 +612,10 @@ __global__ void __launch_bounds__(kWaveThreads, 2) trace_paths_wave_kernel(const
         iters += __shfl_xor_sync(0xffffffffu, iters, o);
         analytic += __shfl_xor_sync(0xffffffffu, analytic, o);
     }
+#ifdef VT_WAVE_STATS
+    if (lane == 0)
+        for (int i = 0; i < 32; ++i) atomicAdd(&vt_wave_stats[i], (unsigned long long)wstat[i]);
+#endif
     if (lane == 0) {
         if (rays) atomicAdd(fb.stats + 0, rays);
         if (iters) atomicAdd(fb.stats + 1, iters);

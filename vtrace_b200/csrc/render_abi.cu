@@ -38,6 +38,7 @@ struct State {
     struct BrickAlloc { uint32_t* l1; uint32_t* table; uint32_t* pool; float* heights; uchar4* colors; BrickVolume* d_desc; };
     std::vector<BrickAlloc> brick_allocs; // procedural volumes (extension)
     bool any_bricks = false;
+    uint32_t max_idx_bits = 0; // widest stop-mask index of any dense volume (the wavefront kernel packs it into 30 bits)
     uint8_t* h_tex_staging = nullptr; // pinned; grows to the next power of two (lib/memory.c:297-302)
     size_t tex_staging_size = 0;
 
@@ -332,10 +333,11 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
         fp.sun[0] = sx / l; fp.sun[1] = sy / l; fp.sun[2] = sz / l;
     }
     fp.any_bricks = g.any_bricks ? 1u : 0u;
+    fp.max_idx_bits = g.max_idx_bits;
     fp.clear_rgba = g.clear_rgba;
     fp.sky_spp = g.cfg.spp;
     if (g.fused_mode && g.cfg.mode == VT_MODE_PATHS) {
-        if (g.inst_count != 1 || g.any_bricks || (g.cfg.flags & VT_FLAG_PER_PIXEL_PATHS))
+        if (g.inst_count != 1 || g.any_bricks || (g.cfg.flags & VT_FLAG_PER_PIXEL_PATHS) || g.max_idx_bits > 30)
             return fail("fused cross-GPU accumulation needs the single-instance wavefront kernel");
         if (g.fused_pixels != (size_t)g.cfg.width * g.cfg.height) return fail("fused accumulation buffer does not match the framebuffer size");
         fp.sky_spp = 0u; // pixels outside the screen rectangle are resolved analytically on the root
@@ -698,6 +700,7 @@ extern "C" int32_t add_texture(const uint8_t* data, uint32_t width, uint32_t hei
     g.stats.launches += 1;
     g.arena_words += mask_words_padded;
     g.vols.push_back(v);
+    if (xb + yb + zbits > g.max_idx_bits) g.max_idx_bits = xb + yb + zbits;
     g.vols_dirty = true;
     return (int32_t)(g.vols.size() - 1); // lib/memory.c:292,384
 }
@@ -1126,3 +1129,12 @@ extern "C" const char* vt_last_error(void) { return g.err; }
 static_assert(sizeof(user_input) == 40, "UserInput is 40 bytes (src/render.rs:37-51)");
 static_assert(sizeof(render_tick_info) == 2 * sizeof(void*), "RenderTickInfo is two pointers (src/render.rs:177-181)");
 static_assert(sizeof(vt_hit_record) == 16, "hit record is 16 bytes");
+
+#ifdef VT_WAVE_STATS
+// variant builds only (python -m vtrace_b200.build --variant stats -DVT_WAVE_STATS): per-phase counters of the wavefront kernel
+namespace vt { cudaError_t read_wave_stats(unsigned long long* out16); }
+extern "C" int vt_debug_wave_stats(uint64_t* out16) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    return vt::read_wave_stats(reinterpret_cast<unsigned long long*>(out16)) == cudaSuccess ? 0 : -1;
+}
+#endif
