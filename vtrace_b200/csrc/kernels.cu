@@ -1500,8 +1500,16 @@ cudaError_t launch_trace_paths(const FrameParams& fp, const InstUniforms* inst, 
     }
     if (fp.n_inst == 1 && !(fp.flags & VT_FLAG_PER_PIXEL_PATHS) && fp.max_idx_bits <= kWaveIdxBits) {
         // single-instance scenes: warp-local wavefront engine (paths_wave.cuh)
-        const size_t wsmem = wave_smem_bytes(arena_words, masks_in_smem);
         const int max_warps = 1 << 30; // persistent: one resident wave, work is claimed dynamically
+        // the masks share the SM's shared memory with the warps' pools: a large arena is read through L1 instead
+        int fits = 0;
+        if (masks_in_smem &&
+            (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fits, trace_paths_wave_kernel<true>, kWaveThreads,
+                                                           wave_smem_bytes(arena_words, true)) != cudaSuccess || fits < 1)) {
+            (void)cudaGetLastError();
+            masks_in_smem = false;
+        }
+        const size_t wsmem = wave_smem_bytes(arena_words, masks_in_smem);
         if (masks_in_smem) {
             int grid = persistent_grid(trace_paths_wave_kernel<true>, wsmem, sm_count, max_warps, kWaveThreads);
             trace_paths_wave_kernel<true><<<grid, kWaveThreads, wsmem, stream>>>(fp, inst, mask_arena, arena_words, lut, fb);

@@ -2,33 +2,37 @@
 // (BASELINE configs[2]) as a warp-local wavefront engine.  Included from kernels.cu (namespace vt).
 //
 // Same paths, same arithmetic, same integer sums as trace_path() — only the schedule differs.
-// Rays of one warp need 0..150 DDA iterations (16.5 on average in the bench scene), paths end after
-// 1..5 segments, and regenerating a ray (shade + bounce, or a new camera ray) costs as much as
-// marching it.  Every warp owns a pool of kSlots paths in shared memory and only ever runs one kind
-// of work at a time, on full batches:
+// Rays of one warp need 0..150 DDA iterations (22 on average in the bench scene, a fifth of them at
+// most 3), paths end after 1..5 segments, and regenerating a ray (shade + bounce, or a new camera
+// ray) costs more than marching it.  Every warp owns a pool of kSlots paths in shared memory and
+// alternates between two kinds of full-width work:
 //
-//   primary : when >= 32 slots are free, 32 lanes start 32 new camera rays (jobs = covered
-//             pixel x sample, claimed per (tile, samples) item from a global counter);
-//   bounce  : when >= 32 slots hold hits, 32 lanes shade and bounce them;
-//   sky     : when >= 32 slots hold rays that left the volume, 32 lanes add their sky radiance
-//             (integer atomics) and free the slots;
-//   march   : lanes pull READY rays from the pool and step them together.  The stepping loop is one
-//             PTX block, fully predicated (a lane whose ray stopped — or that has no ray — keeps its
-//             "stopped" predicate and executes nothing): 16 SASS instructions per voxel step, no
-//             branch inside a burst of 4 steps, one vote per burst.  When `refill_batch` lanes have
-//             stopped they decode hit / miss, write their exit state and pull the next READY rays;
-//             when the READY list is empty and fewer than `refill_threshold` lanes still walk, the
-//             rest is parked back into the pool.
+//   generate : 32 lanes shade and bounce 32 hits (taken from the warp's hit stack), or start 32 new
+//              camera rays (jobs = covered pixel x sample, claimed per (tile, samples) item from a
+//              global counter).  A lane that produced a ray keeps it in registers and walks it right
+//              away — a fresh ray never travels through shared memory.
+//   march    : the stepping loop is one PTX block, fully predicated (a lane whose ray stopped — or
+//              that has no ray — keeps its "stopped" predicate and executes nothing): 16 SASS
+//              instructions per voxel step, no branch inside a burst of 4 steps, one vote per burst.
+//              When `refill_batch` lanes have stopped they decode hit / miss and write their exit
+//              state: a hit goes on the hit stack, a ray that left the volume moves its throughput to
+//              the miss list and frees its slot at once; idle lanes pull the rays that the previous
+//              march parked.  When none are left and fewer than `refill_threshold` lanes still walk,
+//              the walkers are parked and the warp generates again.
+//   sky      : whenever the miss list holds 32 entries, 32 lanes add throughput x clear colour
+//              (integer atomics).
 //
-// Everything is warp-local (__syncwarp only): no inter-warp queues, no block barriers after the
-// prologue.  Radiance is 2^-24 fixed point added with integer atomics, RNG streams are keyed by
-// (pixel, sample): the result is bit-identical to the per-pixel kernel and to the CPU oracle.
+// Slots, hits, parked rays and misses are kept in small per-warp stacks that are pushed with
+// ballot / popc ranks — no state bytes, no compaction passes.  Everything is warp-local (__syncwarp
+// only): no inter-warp queues, no block barriers after the prologue.  Radiance is 2^-24 fixed point
+// added with integer atomics, RNG streams are keyed by (pixel, sample): the result is bit-identical to
+// the per-pixel kernel and to the CPU oracle.
 //
 // Slot layout (96 bytes, 3 + 3 uint4; the 48-byte stride makes 128-bit accesses of consecutive
 // slots bank-conflict-free):
 //   ray  q0 = side.xyz, idx      q1 = signed delta.xyz (len / dir), step signs
-//        q2 = prev idx, steps | state << 24, -, pixel handle
-//   path p0 = thr.rgb, rng key   p1 = pos.xyz, len               p2 = dir.xyz, meta
+//        q2 = prev idx, steps, rng key, -
+//   path p0 = thr.rgb, pixel handle   p1 = pos.xyz, len          p2 = dir.xyz, meta
 //
 // Multi-GPU: fb.accum may point at ANOTHER GPU's accumulation buffer (CUDA IPC mapping over NVLink,
 // see vt_fused_reduce_*): the per-tile flushes below are integer atomics, which work on peer memory
@@ -37,22 +41,25 @@
 
 // Shape of a CTA: warps, paths in flight per warp, CTAs per SM.  (Compile-time knobs so that variants can be
 // built side by side: python -m vtrace_b200.build --variant NAME -DVT_WAVE_WARPS=.. -DVT_WAVE_SLOTS=.. -DVT_WAVE_CTAS=..)
+// The kernel is bound by latency below ~24 warps per SM (12: 1.51 ms, 16: 1.25, 20: 1.11, 24: 1.08 on the bench frame).
 #ifndef VT_WAVE_WARPS
-#define VT_WAVE_WARPS 12
+#define VT_WAVE_WARPS 24
 #endif
 #ifndef VT_WAVE_SLOTS
 #define VT_WAVE_SLOTS 64
 #endif
 #ifndef VT_WAVE_CTAS
-#define VT_WAVE_CTAS 2
+#define VT_WAVE_CTAS 1
 #endif
 static constexpr int kWaveWarps = VT_WAVE_WARPS;
 static constexpr int kWaveThreads = kWaveWarps * 32;
 static constexpr int kWaveCtas = VT_WAVE_CTAS;
 static constexpr int kSlots = VT_WAVE_SLOTS; // paths in flight per warp
 static constexpr int kSlotGroups = (kSlots + 31) / 32;
+static constexpr int kMissCap = 64;          // miss list entries (drained in batches of 32 as soon as it holds 32)
 static_assert(kSlots % 16 == 0 && kSlots >= 32 && kSlots <= 256, "slot ids travel as bytes; the pool is 16-byte granular");
-static constexpr uint32_t kPoolBytes = kSlots * 96 + kSlots + 32 + 32 * 3 * 4; // slots + byte list + covered-pixel table + tile accumulators
+// slots + miss list + tile accumulators + free stack + hit stack + parked list + covered-pixel table
+static constexpr uint32_t kPoolBytes = kSlots * 96 + kMissCap * 16 + 32 * 3 * 4 + kSlots + kSlots + 32 + 32;
 static_assert(kPoolBytes % 16 == 0, "pool alignment");
 // The march keeps "previous index" and the step count modulo 4 in one register: bits 30-31 are the
 // position inside the burst, so a volume's stop-mask index must fit 30 bits (launch_trace_paths checks).
@@ -65,8 +72,6 @@ __device__ unsigned long long vt_wave_stats[32];
 #else
 #define VT_STAT(i, v) ((void)0)
 #endif
-
-enum SlotState : uint32_t { kFree = 0, kReady = 1, kMiss = 2, kHit = 4 };
 
 size_t wave_smem_bytes(uint32_t arena_words, bool masks_in_smem) {
     return trace_smem_bytes(arena_words, masks_in_smem) + size_t(kWaveWarps) * kPoolBytes;
@@ -157,13 +162,12 @@ __global__ void __launch_bounds__(kWaveThreads, kWaveCtas) trace_paths_wave_kern
     const uint32_t pool_off = kSmemMaskOff + (kSmem ? arena_words * 4u : 0u);
     uint4* ray = reinterpret_cast<uint4*>(vt_smem + pool_off + warp * kPoolBytes);
     uint4* path = ray + kSlots * 3;
-    uint8_t* list = reinterpret_cast<uint8_t*>(path + kSlots * 3);
-    uint8_t* cov_pix = list + kSlots; // cov_pix[c] = tile-local index of the item's c-th covered pixel
-    uint32_t* wacc = reinterpret_cast<uint32_t*>(cov_pix + 32); // radiance sums of the current item's tile (2^-24 fixed point)
-    uint8_t* ray_bytes = reinterpret_cast<uint8_t*>(ray);
-    // a slot's state is the top byte of q2.y
-    auto state_of = [&](uint32_t slot) -> uint32_t { return ray_bytes[slot * 48u + 39u]; };
-    auto set_state = [&](uint32_t slot, uint32_t s) { ray_bytes[slot * 48u + 39u] = (uint8_t)s; };
+    uint4* miss_list = path + kSlots * 3;                                 // (thr.rgb, pixel handle) of rays that left the volume
+    uint32_t* wacc = reinterpret_cast<uint32_t*>(miss_list + kMissCap);   // radiance sums of the current item's tile (2^-24 fixed point)
+    uint8_t* free_stack = reinterpret_cast<uint8_t*>(wacc + 32 * 3);      // slots without a path
+    uint8_t* hit_stack = free_stack + kSlots;                             // slots whose ray stopped on a filled voxel
+    uint8_t* parked = hit_stack + kSlots;                                 // slots whose ray is still walking (written when a march ends)
+    uint8_t* cov_pix = parked + 32; // cov_pix[c] = tile-local index of the item's c-th covered pixel
 
     const int tiles_x = (fp.width + kTileW - 1) / kTileW;
     const int tiles_y = (fp.height + kTileH - 1) / kTileH;
@@ -230,15 +234,21 @@ __global__ void __launch_bounds__(kWaveThreads, kWaveCtas) trace_paths_wave_kern
 
 #pragma unroll
     for (int g = 0; g < kSlotGroups; ++g)
-        if (lane + 32 * g < kSlots) ray[(lane + 32 * g) * 3 + 2] = make_uint4(0u, kFree << 24, 0u, 0u);
+        if (lane + 32 * g < kSlots) free_stack[lane + 32 * g] = (uint8_t)(lane + 32 * g);
     wacc[lane * 3 + 0] = 0u; wacc[lane * 3 + 1] = 0u; wacc[lane * 3 + 2] = 0u;
     __syncwarp();
-    int n_free = kSlots, n_ready = 0, n_hit = 0, n_miss = 0;
+    int n_free = kSlots, n_hit = 0, n_miss = 0, n_parked = 0; // warp-uniform stack heights
 
     // current work item (warp-uniform)
     bool work_left = true;
     int it_x0 = 0, it_y0 = 0;
     uint32_t it_tile = 0xFFFFFFFFu, it_ncov = 1, it_magic = 0, it_next = 0, it_njobs = 0, it_s0 = 0;
+
+    // the lane's walking ray (registers): side, delta, stop-mask index and its per-axis increments, rec = previous
+    // index | burst position << 30, steps, slot (-1: none); stopped != 0: nothing to step
+    float sx = 0.0f, sy = 0.0f, sz = 0.0f, dx = 0.0f, dy = 0.0f, dz = 0.0f;
+    uint32_t idx = 0, ix = 0, iy = 0, iz = 0, rec = 3u << 30, steps = 0, stopped = 1u; // idx 0 = border bit, where lanes without a ray sit
+    int my_slot = -1;
 
     // A path is identified by its pixel handle = tile << 5 | tile-local pixel.  Radiance of paths that
     // belong to the warp's current tile goes to shared-memory accumulators (flushed once per item);
@@ -277,28 +287,64 @@ __global__ void __launch_bounds__(kWaveThreads, kWaveCtas) trace_paths_wave_kern
         }
         __syncwarp();
     };
-    // writes a ray that is about to walk (or whose slow-path result is final) into its slot
-    auto store_ray = [&](uint32_t slot, const Dda& r, uint32_t idx, uint32_t prev, uint32_t steps, uint32_t state, uint32_t pixel) {
+    // ---- sky batch: up to 32 entries of the miss list add throughput x clear colour
+    auto sky_batch = [&]() {
+        __syncwarp();
+        const int n = n_miss < 32 ? n_miss : 32;
+        if (lane < n) {
+            const uint4 e = miss_list[n_miss - n + lane];
+            add_sky(e.w, __uint_as_float(e.x), __uint_as_float(e.y), __uint_as_float(e.z));
+        }
+        VT_STAT(4, 1); VT_STAT(5, n);
+        n_miss -= n;
+        __syncwarp();
+    };
+    // stack pushes (all lanes call; `mine` lanes push).  The miss list has room for 32 more entries whenever
+    // it holds fewer than 32, which every caller ensures (see sky_batch calls).
+    auto push_hit = [&](bool mine, uint32_t slot) {
+        const uint32_t m = __ballot_sync(0xffffffffu, mine);
+        if (mine) hit_stack[n_hit + __popc(m & lt_mask)] = (uint8_t)slot;
+        n_hit += __popc(m);
+    };
+    auto push_free = [&](bool mine, uint32_t slot) {
+        const uint32_t m = __ballot_sync(0xffffffffu, mine);
+        if (mine) free_stack[n_free + __popc(m & lt_mask)] = (uint8_t)slot;
+        n_free += __popc(m);
+    };
+    auto push_miss = [&](bool mine, uint32_t slot) { // the ray left the volume: its throughput waits in the miss list, the slot is free
+        const uint32_t m = __ballot_sync(0xffffffffu, mine);
+        if (mine) {
+            const int r = __popc(m & lt_mask);
+            miss_list[n_miss + r] = path[slot * 3 + 0];
+            free_stack[n_free + r] = (uint8_t)slot;
+        }
+        n_miss += __popc(m);
+        n_free += __popc(m);
+    };
+    // Starts the walk of a fresh ray (pos, dir[, start voxel]) that belongs to `slot`: the path part goes to the slot,
+    // the ray itself stays in this lane's registers.  Returns 1: walking, 2: the (rare) slow path ran to a hit,
+    // 0: it left the volume (or never entered the padded volume).
+    auto launch_ray = [&](uint32_t slot, uint32_t handle, const float pos[3], const float dir[3], bool has_start, const int32_t sv[3],
+                          const float thr[3], uint32_t key, uint32_t meta) -> uint32_t {
+        Dda r;
+        uint32_t i0;
+        const DdaMode mode = dda_init(vol, pos, dir, has_start, sv, r, i0);
         // the sign of len / dir is the step direction (the march needs nothing else); step == 0 travels in the packed signs
         const float raw[3] = {r.step[0] < 0 ? -r.delta[0] : r.delta[0], r.step[1] < 0 ? -r.delta[1] : r.delta[1],
                               r.step[2] < 0 ? -r.delta[2] : r.delta[2]};
-        ray[slot * 3 + 0] = make_uint4(__float_as_uint(r.side[0]), __float_as_uint(r.side[1]), __float_as_uint(r.side[2]), idx);
-        ray[slot * 3 + 1] = make_uint4(__float_as_uint(raw[0]), __float_as_uint(raw[1]), __float_as_uint(raw[2]), pack_signs(r.step));
-        ray[slot * 3 + 2] = make_uint4(prev, steps | state << 24, 0u, pixel);
-    };
-    // Starts the walk of a fresh ray (pos, dir[, start voxel]) that belongs to `slot`.
-    // Returns the slot's new state: kReady (fast walk pending), kHit (slow path hit), kFree (slow path miss).
-    auto launch_ray = [&](uint32_t slot, uint32_t pixel, const float pos[3], const float dir[3], bool has_start, const int32_t sv[3],
-                          const float thr[3], uint32_t key, uint32_t meta) -> uint32_t {
-        Dda r;
-        uint32_t idx;
-        const DdaMode mode = dda_init(vol, pos, dir, has_start, sv, r, idx);
-        path[slot * 3 + 0] = make_uint4(__float_as_uint(thr[0]), __float_as_uint(thr[1]), __float_as_uint(thr[2]), key);
+        path[slot * 3 + 0] = make_uint4(__float_as_uint(thr[0]), __float_as_uint(thr[1]), __float_as_uint(thr[2]), handle);
         path[slot * 3 + 1] = make_uint4(__float_as_uint(pos[0]), __float_as_uint(pos[1]), __float_as_uint(pos[2]), __float_as_uint(r.len));
         path[slot * 3 + 2] = make_uint4(__float_as_uint(dir[0]), __float_as_uint(dir[1]), __float_as_uint(dir[2]), meta);
+        ray[slot * 3 + 1] = make_uint4(__float_as_uint(raw[0]), __float_as_uint(raw[1]), __float_as_uint(raw[2]), pack_signs(r.step));
+        ray[slot * 3 + 2] = make_uint4(i0, 0u, key, 0u);
         if (mode == kDdaFast) {
-            store_ray(slot, r, idx, idx, 0u, kReady, pixel);
-            return kReady;
+            sx = r.side[0]; sy = r.side[1]; sz = r.side[2];
+            dx = r.delta[0]; dy = r.delta[1]; dz = r.delta[2];
+            ix = (uint32_t)r.step[0]; iy = (uint32_t)r.step[1] << xb; iz = (uint32_t)r.step[2] << zb;
+            idx = i0; rec = i0 | 3u << 30; steps = 0u;
+            my_slot = (int)slot;
+            stopped = 0u;
+            return 1u;
         }
         if (mode == kDdaSlow) {
             dda_slow<kSmem>(vol, r); // rare: a direction component is exactly 0; runs to completion here
@@ -306,30 +352,15 @@ __global__ void __launch_bounds__(kWaveThreads, kWaveCtas) trace_paths_wave_kern
             if (r.hit) {
                 // re-express the result in the fast walk's exit format (bit index, previous index, steps)
                 const uint32_t hidx = (uint32_t)(r.v[0] + 1) | ((uint32_t)(r.v[1] + 1) << xb) | ((uint32_t)(r.v[2] + 1) << zb);
-                const uint32_t ix = (uint32_t)r.step[0], iy = (uint32_t)r.step[1] << xb, iz = (uint32_t)r.step[2] << zb;
+                const uint32_t jx = (uint32_t)r.step[0], jy = (uint32_t)r.step[1] << xb, jz = (uint32_t)r.step[2] << zb;
                 const uint32_t lm = r.steps ? r.last_mask : 0u;
-                const uint32_t hprev = hidx - ((lm & 1u) ? ix : 0u) - ((lm & 2u) ? iy : 0u) - ((lm & 4u) ? iz : 0u);
-                store_ray(slot, r, hidx, hprev, r.steps, kHit, pixel);
-                return kHit;
+                const uint32_t hprev = hidx - ((lm & 1u) ? jx : 0u) - ((lm & 2u) ? jy : 0u) - ((lm & 4u) ? jz : 0u);
+                ray[slot * 3 + 0] = make_uint4(__float_as_uint(r.side[0]), __float_as_uint(r.side[1]), __float_as_uint(r.side[2]), hidx);
+                *reinterpret_cast<uint2*>(&ray[slot * 3 + 2]) = make_uint2(hprev, r.steps);
+                return 2u;
             }
         }
-        add_sky(pixel, thr[0], thr[1], thr[2]); // missed (or never entered the padded volume)
-        ray[slot * 3 + 2] = make_uint4(0u, kFree << 24, 0u, pixel);
-        return kFree;
-    };
-    // compacts the slots in `state` into list[0..), returns how many there are
-    auto build_list = [&](uint32_t state) -> int {
-        int base = 0;
-#pragma unroll
-        for (int g = 0; g < kSlotGroups; ++g) {
-            const uint32_t slot = lane + 32 * g;
-            const bool f = (kSlots % 32 == 0 || slot < (uint32_t)kSlots) && state_of(slot) == state;
-            const uint32_t m = __ballot_sync(0xffffffffu, f);
-            if (f) list[base + __popc(m & lt_mask)] = (uint8_t)slot;
-            base += __popc(m);
-        }
-        __syncwarp();
-        return base;
+        return 0u;
     };
 
     for (;;) {
@@ -365,34 +396,29 @@ __global__ void __launch_bounds__(kWaveThreads, kWaveCtas) trace_paths_wave_kern
             __syncwarp();
         }
         const bool jobs = work_left && it_next < it_njobs;
+        if (n_miss >= 32) sky_batch(); // (keeps room for 32 more entries)
 
-        // ---- pick the next full batch (or the best partial one when the pool runs dry) -----------
-        int action; // 0 primary, 1 bounce, 2 march, 3 stop, 4 sky
+        // ---- what to generate: a full batch if there is one; else march what is parked; else the better partial batch
         const int low = (int)fp.refill_threshold;
-        const int can_primary = jobs ? n_free : 0;
-        if (n_hit >= 32) action = 1;                          // full bounce batch
-        else if (n_miss >= 32) action = 4;                    // full sky batch
-        else if (can_primary >= 32) action = 0;               // full camera batch
-        else if (n_ready >= 32) action = 2;                   // a full warp of rays is waiting
-        else if (n_miss > 0 && jobs && n_free + n_miss >= 32) action = 4; // frees the slots a full camera batch needs
-        else if (n_hit >= low && n_hit >= can_primary) action = 1; // otherwise top the pool up with the better partial batch
-        else if (can_primary >= low) action = 0;
-        else if (n_ready > 0) action = 2;
-        else if (n_hit > 0) action = 1;
-        else if (n_miss > 0) action = 4;
-        else if (can_primary > 0) action = 0;
-        else action = 3;
-        if (action == 3) break;
+        const int avail = jobs ? (int)(it_njobs - it_next) : 0;
+        const int can_primary = n_free < avail ? n_free : avail;
+        int gen; // 0 nothing, 1 bounce, 2 primary
+        if (n_hit >= 32) gen = 1;
+        else if (can_primary >= 32 || (can_primary > 0 && can_primary == avail && n_free >= 32)) gen = 2; // (an item's last jobs count as a full batch)
+        else if (n_parked >= low) gen = 0;
+        else if (n_hit > 0 && n_hit >= can_primary) gen = 1;
+        else if (can_primary > 0) gen = 2;
+        else if (n_parked > 0) gen = 0;
+        else if (n_miss > 0) { sky_batch(); continue; }
+        else break;
 
-        if (action == 0) {
+        if (gen == 2) {
             // ---- primary batch: new camera rays --------------------------------------------------
-            build_list(kFree);
-            const uint32_t avail = it_njobs - it_next;
-            uint32_t n = n_free < 32 ? (uint32_t)n_free : 32u;
-            n = n < avail ? n : avail;
-            uint32_t st = kFree;
+            const uint32_t n = can_primary < 32 ? (uint32_t)can_primary : 32u;
+            bool enters = false;
+            uint32_t handle = 0, key = 0, meta = 0;
+            float d[3] = {0.0f, 0.0f, 0.0f}, pos[3] = {0.0f, 0.0f, 0.0f};
             if ((uint32_t)lane < n) {
-                const uint32_t slot = list[lane];
                 const uint32_t job = it_next + lane; // sample-major: neighbouring lanes get neighbouring pixels
                 const uint32_t si = __umulhi(job, it_magic), ci = job - si * it_ncov;
                 const uint32_t pix = cov_pix[ci];
@@ -402,12 +428,12 @@ __global__ void __launch_bounds__(kWaveThreads, kWaveCtas) trace_paths_wave_kern
                 rng_init(rng, fp.seed, pixel, fp.sample_first + (it_s0 + si) * fp.sample_stride);
                 const float jx = rng_u01(rng), jy = rng_u01(rng);
                 const float fx = (float)px + jx, fy = (float)py + jy;
-                const uint32_t handle = it_tile << 5 | pix;
+                handle = it_tile << 5 | pix;
                 rays += 1;
                 // camera ray in the instance's model space: o = eye, d = dirm * (x_ndc, y_ndc, 1)
                 const float x_ndc = fx * fp.sxn - 1.0f;
                 const float y_ndc = fy * fp.syn - 1.0f;
-                float d[3], o[3], lo3[3], hi3[3];
+                float o[3], lo3[3], hi3[3];
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     d[k] = (Ip->dirm[0 * 3 + k] * x_ndc + Ip->dirm[1 * 3 + k] * y_ndc) + Ip->dirm[3 * 3 + k];
@@ -417,31 +443,42 @@ __global__ void __launch_bounds__(kWaveThreads, kWaveCtas) trace_paths_wave_kern
                 }
                 float tn;
                 int axis;
-                if (!slab_unit_cube(o, lo3, hi3, d, tn, axis)) { // leaves through the sky; the slot stays free
+                if (!slab_unit_cube(o, lo3, hi3, d, tn, axis)) { // leaves through the sky: no slot needed
 #pragma unroll
                     for (int c = 0; c < 3; ++c) atomicAdd(&wacc[pix * 3 + c], (uint32_t)sky_q[c]);
                 } else {
-                    float mp[3], pos[3];
+                    float mp[3];
                     entry_point(o, d, tn, axis, mp);
 #pragma unroll
                     for (int k = 0; k < 3; ++k) pos[k] = (mp[k] + 0.5f) * size[k];
-                    const float one[3] = {1.0f, 1.0f, 1.0f};
-                    const int32_t none[3] = {0, 0, 0};
-                    st = launch_ray(slot, handle, pos, d, false, none, one, rng.key, (uint32_t)axis << 4 | rng.ctr << 8);
+                    enters = true;
+                    key = rng.key;
+                    meta = (uint32_t)axis << 4 | rng.ctr << 8;
                 }
             }
             it_next += n;
             VT_STAT(0, 1); VT_STAT(1, n);
-            const int nr = __popc(__ballot_sync(0xffffffffu, st == kReady)), nh = __popc(__ballot_sync(0xffffffffu, st == kHit));
-            n_ready += nr; n_hit += nh; n_free -= nr + nh;
+            // the rays that enter the cube pop a slot each
+            const uint32_t em = __ballot_sync(0xffffffffu, enters);
+            uint32_t res = 1u;
+            uint32_t slot = 0;
+            if (enters) {
+                slot = free_stack[n_free - 1 - __popc(em & lt_mask)];
+                const float one[3] = {1.0f, 1.0f, 1.0f};
+                const int32_t none[3] = {0, 0, 0};
+                res = launch_ray(slot, handle, pos, d, false, none, one, key, meta);
+            }
+            n_free -= __popc(em);
             __syncwarp();
-        } else if (action == 1) {
+            push_hit(enters && res == 2u, slot);
+            push_miss(enters && res == 0u, slot);
+        } else if (gen == 1) {
             // ---- bounce batch: shade the hits, start the next segment ---------------------------
-            const int have = build_list(kHit);
-            const int n = have < 32 ? have : 32;
-            uint32_t st = kHit; // lanes without work report "unchanged"
+            const int n = n_hit < 32 ? n_hit : 32;
+            uint32_t res = 1u; // 0 left the volume, 1 nothing to report (walking / no work), 2 slow-path hit, 3 path ended
+            uint32_t slot = 0;
             if (lane < n) {
-                const uint32_t slot = list[lane];
+                slot = hit_stack[n_hit - n + lane];
                 const uint4 q0 = ray[slot * 3 + 0], q1 = ray[slot * 3 + 1], q2 = ray[slot * 3 + 2];
                 const uint4 p0 = path[slot * 3 + 0], p1 = path[slot * 3 + 1], p2 = path[slot * 3 + 2];
                 Dda r;
@@ -452,19 +489,18 @@ __global__ void __launch_bounds__(kWaveThreads, kWaveCtas) trace_paths_wave_kern
                 r.pos[0] = __uint_as_float(p1.x); r.pos[1] = __uint_as_float(p1.y); r.pos[2] = __uint_as_float(p1.z);
                 r.len = __uint_as_float(p1.w);
                 r.dir[0] = __uint_as_float(p2.x); r.dir[1] = __uint_as_float(p2.y); r.dir[2] = __uint_as_float(p2.z);
-                dda_finish_fast(vol, r, q0.w, q2.x, q2.y & 0xFFFFFFu);
-                const uint32_t pixel = q2.w;
+                dda_finish_fast(vol, r, q0.w, q2.x, q2.y);
+                const uint32_t handle = p0.w;
                 uint32_t bounce = p2.w & 15u;
                 const int entry_axis = (int)((p2.w >> 4) & 3u);
-                Rng rng{p0.w, p2.w >> 8};
+                Rng rng{q2.z, p2.w >> 8};
                 float thr[3] = {__uint_as_float(p0.x), __uint_as_float(p0.y), __uint_as_float(p0.z)};
                 const uchar4 s = fetch_texel(Ip->rgba, Ip->w, Ip->h, Ip->d, Ip->remap_identity != 0, r.v);
                 thr[0] = thr[0] * dec[s.x];
                 thr[1] = thr[1] * dec[s.y];
                 thr[2] = thr[2] * dec[s.z];
                 if (bounce == fp.bounces) {
-                    set_state(slot, kFree); // path length exhausted: contributes nothing
-                    st = kFree;
+                    res = 3u; // path length exhausted: contributes nothing
                 } else {
                     ++bounce;
                     const uint32_t lm = r.steps ? r.last_mask : (1u << entry_axis);
@@ -501,43 +537,31 @@ __global__ void __launch_bounds__(kWaveThreads, kWaveCtas) trace_paths_wave_kern
                         ndir[0] *= rl; ndir[1] *= rl; ndir[2] *= rl;
                     }
                     rays += 1;
-                    st = launch_ray(slot, pixel, npos, ndir, true, nsv, thr, rng.key, bounce | (uint32_t)a << 4 | rng.ctr << 8);
+                    res = launch_ray(slot, handle, npos, ndir, true, nsv, thr, rng.key, bounce | (uint32_t)a << 4 | rng.ctr << 8);
                 }
             }
-            const int nr = __popc(__ballot_sync(0xffffffffu, st == kReady)), nf = __popc(__ballot_sync(0xffffffffu, st == kFree));
             VT_STAT(2, 1); VT_STAT(3, n);
-            n_ready += nr; n_free += nf; n_hit -= nr + nf;
-            __syncwarp();
-        } else if (action == 4) {
-            // ---- sky batch: rays that left the volume add throughput x clear colour, slots are freed --
-            const int have = build_list(kMiss);
-            const int n = have < 32 ? have : 32;
-            if (lane < n) {
-                const uint32_t slot = list[lane];
-                const uint4 p0 = path[slot * 3 + 0];
-                add_sky(ray[slot * 3 + 2].w, __uint_as_float(p0.x), __uint_as_float(p0.y), __uint_as_float(p0.z));
-                set_state(slot, kFree);
-            }
-            VT_STAT(4, 1); VT_STAT(5, n);
-            n_miss -= n; n_free += n;
-            __syncwarp();
-        } else {
-            // ---- march: pull READY rays, step them packed, write exits back --------------------------
-            const int total = build_list(kReady); // == n_ready
-            VT_STAT(6, 1); VT_STAT(7, total);
+            n_hit -= n;
+            __syncwarp(); // (the batch's reads of the hit stack precede the pushes below)
+            push_hit(res == 2u, slot);
+            push_free(res == 3u, slot);
+            push_miss(res == 0u, slot);
+        }
+
+        // ---- march: step the fresh rays, pull the parked ones into idle lanes, write exits back ------
+        {
+            if (n_miss >= 32) sky_batch(); // (the generation above may have pushed misses)
+            const int total = n_parked;
             int rc = 0;
-            int my_slot = -1;
-            uint32_t idx = 0, rec = 3u << 30, steps = 0, ix = 0, iy = 0, iz = 0; // idx 0 = border bit, where lanes without a ray sit
-            float sx = 0.0f, sy = 0.0f, sz = 0.0f, dx = 0.0f, dy = 0.0f, dz = 0.0f;
-            uint32_t stopped = 1u;              // this lane has no walking ray
-            uint32_t idle_mask = 0xffffffffu;   // lanes without a ray
-            uint32_t hits = 0, misses = 0, it32 = 0;
+            uint32_t idle_mask = __ballot_sync(0xffffffffu, my_slot < 0); // lanes without a ray
+            uint32_t it32 = 0;
             int thresh = -1;
+            VT_STAT(6, 1); VT_STAT(7, total + 32 - __popc(idle_mask));
             for (;;) {
-                if (rc < total) { // hand the next READY rays to the idle lanes
+                if (rc < total && idle_mask) { // hand the parked rays to the idle lanes
                     const int rank = __popc(idle_mask & lt_mask);
                     if (my_slot < 0 && rc + rank < total) {
-                        my_slot = list[rc + rank];
+                        my_slot = parked[rc + rank];
                         const uint4 q0 = ray[my_slot * 3 + 0], q1 = ray[my_slot * 3 + 1];
                         const uint2 q2 = *reinterpret_cast<const uint2*>(&ray[my_slot * 3 + 2]);
                         sx = __uint_as_float(q0.x); sy = __uint_as_float(q0.y); sz = __uint_as_float(q0.z); idx = q0.w;
@@ -547,43 +571,52 @@ __global__ void __launch_bounds__(kWaveThreads, kWaveCtas) trace_paths_wave_kern
                         iy = (uint32_t)(((int32_t)q1.y >> 31) * 2 + 1) << xb;
                         iz = (uint32_t)(((int32_t)q1.z >> 31) * 2 + 1) << zb;
                         rec = q2.x | 3u << 30;
-                        steps = q2.y & 0xFFFFFFu;
+                        steps = q2.y;
                         stopped = 0u;
                     }
                     const int want = __popc(idle_mask);
-                    const int got = want < total - rc ? want : total - rc;
-                    rc += got;
+                    rc += want < total - rc ? want : total - rc;
                     idle_mask = __ballot_sync(0xffffffffu, my_slot < 0);
                 }
                 const int nact = 32 - __popc(idle_mask);
-                if (!nact) { n_ready = 0; break; }
+                if (!nact) { n_parked = 0; break; }
                 if (thresh < 0) thresh = nact < low ? nact : low;
                 if (rc >= total && nact < thresh) {
-                    // too few lanes left: park them back into the pool and go generate more rays
+                    // too few lanes left: park them and go generate more rays
+                    __syncwarp(); // (every read of the parked list precedes its rewrite)
                     if (my_slot >= 0) {
                         ray[my_slot * 3 + 0] = make_uint4(__float_as_uint(sx), __float_as_uint(sy), __float_as_uint(sz), idx);
-                        *reinterpret_cast<uint2*>(&ray[my_slot * 3 + 2]) = make_uint2(rec & 0x3fffffffu, steps | kReady << 24);
+                        *reinterpret_cast<uint2*>(&ray[my_slot * 3 + 2]) = make_uint2(rec & 0x3fffffffu, steps);
+                        parked[__popc(~idle_mask & lt_mask)] = (uint8_t)my_slot;
+                        my_slot = -1;
+                        idx = 0;
+                        stopped = 1u;
                     }
-                    n_ready = nact;
+                    n_parked = nact;
                     VT_STAT(10, nact);
                     break;
                 }
-                // Step until it pays to look at the stopped lanes: while READY rays remain, once `refill_batch`
+                // Step until it pays to look at the stopped lanes: while parked rays remain, once `refill_batch`
                 // lanes can be refilled together; afterwards, once fewer than `thresh` lanes still walk (the rest
                 // is then parked).  Lanes without a ray count as stopped.
                 uint32_t k_stop = rc < total ? (uint32_t)(32 - nact) + fp.refill_batch : (uint32_t)(33 - thresh);
                 k_stop = k_stop > 32u ? 32u : k_stop;
                 const uint32_t v = wave_walk<kSmem>(vol, sx, sy, sz, dx, dy, dz, idx, rec, steps, stopped, ix, iy, iz, k_stop);
                 VT_STAT(8, 1); VT_STAT(9, __popc(v & ~idle_mask)); VT_STAT(11, nact);
-                if (stopped && my_slot >= 0) { // the ray ended: on a filled voxel (hit) or on the border (left the volume)
+                // the rays that ended: on a filled voxel (hit) or on the border (left the volume)
+                const bool fin = stopped && my_slot >= 0;
+                bool hit = false;
+                if (fin) {
                     const uint32_t st = steps + (((rec >> 30) + 1u) & 3u);
                     const uint32_t vx = (idx & ((1u << xb) - 1u)) - 1u, vy = ((idx >> xb) & ((1u << vol.yb) - 1u)) - 1u, vz = (idx >> zb) - 1u;
-                    const bool hit = vx < vol.w && vy < vol.h && vz < vol.d;
-                    ray[my_slot * 3 + 0] = make_uint4(__float_as_uint(sx), __float_as_uint(sy), __float_as_uint(sz), idx);
-                    *reinterpret_cast<uint2*>(&ray[my_slot * 3 + 2]) = make_uint2(rec & 0x3fffffffu, st | (hit ? kHit : kMiss) << 24);
+                    hit = vx < vol.w && vy < vol.h && vz < vol.d;
+                    if (hit) {
+                        ray[my_slot * 3 + 0] = make_uint4(__float_as_uint(sx), __float_as_uint(sy), __float_as_uint(sz), idx);
+                        *reinterpret_cast<uint2*>(&ray[my_slot * 3 + 2]) = make_uint2(rec & 0x3fffffffu, st);
+                    }
                     it32 += st;
 #ifdef VT_WAVE_STATS
-                    { // histogram of ray lengths: 0, 1, 2, 3, 4-7, 8-15, 16-31, 32-63, 64+; hits get +9
+                    { // histogram of ray lengths: 0, 1, 2, 3, 4-7, 8-15, 16-31, 32-63, 64+
                         const int b = st < 4 ? (int)st : (st < 8 ? 4 : (st < 16 ? 5 : (st < 32 ? 6 : (st < 64 ? 7 : 8))));
                         for (int k = 0; k < 9; ++k) {
                             const uint32_t m = __ballot_sync(__activemask(), b == k);
@@ -591,15 +624,13 @@ __global__ void __launch_bounds__(kWaveThreads, kWaveCtas) trace_paths_wave_kern
                         }
                     }
 #endif
-                    hits += hit ? 1u : 0u;
-                    misses += hit ? 0u : 1u;
-                    my_slot = -1;
-                    idx = 0;
                 }
+                push_hit(fin && hit, (uint32_t)my_slot);
+                push_miss(fin && !hit, (uint32_t)my_slot);
+                if (fin) { my_slot = -1; idx = 0; }
                 idle_mask = v; // every stopped lane is idle now
+                if (n_miss >= 32) sky_batch();
             }
-            n_hit += (int)__reduce_add_sync(0xffffffffu, hits);
-            n_miss += (int)__reduce_add_sync(0xffffffffu, misses);
             iters += it32;
             __syncwarp();
         }
