@@ -61,10 +61,6 @@ static_assert(kSlots % 16 == 0 && kSlots >= 32 && kSlots <= 256, "slot ids trave
 // slots + miss list + tile accumulators + free stack + hit stack + parked list + covered-pixel table
 static constexpr uint32_t kPoolBytes = kSlots * 96 + kMissCap * 16 + 32 * 3 * 4 + kSlots + kSlots + 32 + 32;
 static_assert(kPoolBytes % 16 == 0, "pool alignment");
-// The march keeps "previous index" and the step count modulo 4 in one register: bits 30-31 are the
-// position inside the burst, so a volume's stop-mask index must fit 30 bits (launch_trace_paths checks).
-static constexpr uint32_t kWaveIdxBits = 30;
-
 // -DVT_WAVE_STATS (variant builds only): per-phase counters, read with vt_debug_wave_stats()
 #ifdef VT_WAVE_STATS
 __device__ unsigned long long vt_wave_stats[32];
@@ -102,6 +98,34 @@ __device__ __forceinline__ uint32_t pack_signs(const int32_t step[3]) {
     "@pz add.s32 %3, %3, %13;\n"
 #define VT_WAVE_LD_SMEM "shl.b32 t, t, 2;\n" "add.u32 t, t, %14;\n" "ld.shared.u32 w, [t];\n"
 #define VT_WAVE_LD_GLOBAL "mad.wide.u32 ta, t, 4, %14;\n" "ld.global.nc.u32 w, [ta];\n"
+// Iterations per burst (between two votes): 4 or 8.  The position inside the burst lives in the top bits of rec.
+#ifndef VT_WAVE_BURST
+#define VT_WAVE_BURST 4
+#endif
+#if VT_WAVE_BURST == 8
+#define VT_WAVE_SUBS(LD)                                                                             \
+    VT_WAVE_SUB(LD, "@!ps mov.u32 %4, %3;\n")                                                        \
+    VT_WAVE_SUB(LD, "@!ps add.u32 %4, %3, 0x20000000;\n")                                            \
+    VT_WAVE_SUB(LD, "@!ps add.u32 %4, %3, 0x40000000;\n")                                            \
+    VT_WAVE_SUB(LD, "@!ps add.u32 %4, %3, 0x60000000;\n")                                            \
+    VT_WAVE_SUB(LD, "@!ps add.u32 %4, %3, 0x80000000;\n")                                            \
+    VT_WAVE_SUB(LD, "@!ps add.u32 %4, %3, 0xa0000000;\n")                                            \
+    VT_WAVE_SUB(LD, "@!ps add.u32 %4, %3, 0xc0000000;\n")                                            \
+    VT_WAVE_SUB(LD, "@!ps add.u32 %4, %3, 0xe0000000;\n")                                            \
+    "@!ps add.u32 %5, %5, 8;\n"          /* :86, eight at a time                                 */
+static constexpr uint32_t kWaveIdxBits = 29, kWaveBurst = 8;
+#else
+#define VT_WAVE_SUBS(LD)                                                                             \
+    VT_WAVE_SUB(LD, "@!ps mov.u32 %4, %3;\n")                                                        \
+    VT_WAVE_SUB(LD, "@!ps add.u32 %4, %3, 0x40000000;\n")                                            \
+    VT_WAVE_SUB(LD, "@!ps add.u32 %4, %3, 0x80000000;\n")                                            \
+    VT_WAVE_SUB(LD, "@!ps add.u32 %4, %3, 0xc0000000;\n")                                            \
+    "@!ps add.u32 %5, %5, 4;\n"          /* :86, four at a time                                  */
+static constexpr uint32_t kWaveIdxBits = 30, kWaveBurst = 4;
+#endif
+// The march keeps "previous index" and the step count modulo the burst length in one register (rec): the top bits are
+// the position inside the burst, so a volume's stop-mask index must fit kWaveIdxBits bits (launch_trace_paths checks).
+static constexpr uint32_t kRecIdxMask = (1u << kWaveIdxBits) - 1u, kRecFresh = (kWaveBurst - 1u) << kWaveIdxBits;
 #define VT_WAVE_LOOP(LD)                                                                            \
     "{\n"                                                                                            \
     ".reg .pred ps, px, py, pz, pc;\n"                                                               \
@@ -110,11 +134,7 @@ __device__ __forceinline__ uint32_t pack_signs(const int32_t step[3]) {
     ".reg .f32 m;\n"                                                                                 \
     "setp.ne.u32 ps, %6, 0;\n"                                                                       \
     "WAVE_LOOP:\n"                                                                                   \
-    VT_WAVE_SUB(LD, "@!ps mov.u32 %4, %3;\n")                                                        \
-    VT_WAVE_SUB(LD, "@!ps add.u32 %4, %3, 0x40000000;\n")                                            \
-    VT_WAVE_SUB(LD, "@!ps add.u32 %4, %3, 0x80000000;\n")                                            \
-    VT_WAVE_SUB(LD, "@!ps add.u32 %4, %3, 0xc0000000;\n")                                            \
-    "@!ps add.u32 %5, %5, 4;\n"           /* :86, four at a time                                 */ \
+    VT_WAVE_SUBS(LD)                                                                                 \
     "vote.sync.ballot.b32 %7, ps, 0xffffffff;\n"                                                     \
     "popc.b32 n, %7;\n"                                                                              \
     "setp.lt.u32 pc, n, %15;\n"                                                                      \
@@ -123,16 +143,16 @@ __device__ __forceinline__ uint32_t pack_signs(const int32_t step[3]) {
     "}\n"
 
 // Steps the warp's rays in bursts of four iterations until at least `k_stop` lanes are stopped (lanes
-// without a ray count as stopped and sit on the border bit idx 0).  `rec` must enter with bits 30-31
-// set; afterwards a lane's ray has taken steps + ((rec >> 30) + 1 & 3) iterations and the index before
-// its last iteration is rec & 0x3fffffff.  Returns the ballot of stopped lanes.
+// without a ray count as stopped and sit on the border bit idx 0).  `rec` must enter with its position bits
+// set (kRecFresh); afterwards a lane's ray has taken steps + ((rec >> kWaveIdxBits) + 1 & kWaveBurst - 1) iterations
+// and the index before its last iteration is rec & kRecIdxMask.  Returns the ballot of stopped lanes.
 template <bool kSmem>
 __device__ __forceinline__ uint32_t wave_walk(const Vol& vol, float& sx, float& sy, float& sz, float dx, float dy, float dz,
                                               uint32_t& idx, uint32_t& rec, uint32_t& steps, uint32_t& stopped, uint32_t ix,
-                                              uint32_t iy, uint32_t iz, uint32_t k_stop) {
+                                              uint32_t iy, uint32_t iz, uint32_t k_stop, uint32_t smem0) {
     uint32_t v;
     if (kSmem) {
-        const uint32_t base = smem_u32(vt_smem + kSmemMaskOff) + vol.mask_off * 4u;
+        const uint32_t base = smem0 + kSmemMaskOff + vol.mask_off * 4u;
         asm volatile(VT_WAVE_LOOP(VT_WAVE_LD_SMEM)
                      : "+f"(sx), "+f"(sy), "+f"(sz), "+r"(idx), "+r"(rec), "+r"(steps), "+r"(stopped), "=r"(v)
                      : "f"(dx), "f"(dy), "f"(dz), "r"(ix), "r"(iy), "r"(iz), "r"(base), "r"(k_stop));
@@ -151,7 +171,12 @@ __global__ void __launch_bounds__(kWaveThreads, kWaveCtas) trace_paths_wave_kern
                                                                           const uint32_t* __restrict__ mask_arena,
                                                                           uint32_t arena_words, SrgbTables lut, FrameBuffers fb) {
     stage_tables<kSmem>(mask_arena, arena_words, lut.decode);
-    const float* dec = reinterpret_cast<const float*>(vt_smem + kSmemLutOff);
+    // The shared-window address of the CTA's dynamic shared memory is pinned in one register (and every pool pointer
+    // derived from it): left alone, the compiler rebuilds it from %cluster_ctarank wherever a pointer is needed.
+    uint32_t smem0 = smem_u32(vt_smem);
+    asm volatile("" : "+r"(smem0));
+    unsigned char* const smem_base = static_cast<unsigned char*>(__cvta_shared_to_generic(smem0));
+    const float* dec = reinterpret_cast<const float*>(smem_base + kSmemLutOff);
     const InstUniforms* Ip = inst; // the one instance
     const Vol vol{Ip->w, Ip->h, Ip->d, Ip->xb, Ip->yb, Ip->mask_off, mask_arena};
     const float size[3] = {(float)(int32_t)Ip->w, (float)(int32_t)Ip->h, (float)(int32_t)Ip->d};
@@ -160,7 +185,7 @@ __global__ void __launch_bounds__(kWaveThreads, kWaveCtas) trace_paths_wave_kern
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t pool_off = kSmemMaskOff + (kSmem ? arena_words * 4u : 0u);
-    uint4* ray = reinterpret_cast<uint4*>(vt_smem + pool_off + warp * kPoolBytes);
+    uint4* ray = reinterpret_cast<uint4*>(smem_base + pool_off + warp * kPoolBytes);
     uint4* path = ray + kSlots * 3;
     uint4* miss_list = path + kSlots * 3;                                 // (thr.rgb, pixel handle) of rays that left the volume
     uint32_t* wacc = reinterpret_cast<uint32_t*>(miss_list + kMissCap);   // radiance sums of the current item's tile (2^-24 fixed point)
@@ -247,7 +272,7 @@ __global__ void __launch_bounds__(kWaveThreads, kWaveCtas) trace_paths_wave_kern
     // the lane's walking ray (registers): side, delta, stop-mask index and its per-axis increments, rec = previous
     // index | burst position << 30, steps, slot (-1: none); stopped != 0: nothing to step
     float sx = 0.0f, sy = 0.0f, sz = 0.0f, dx = 0.0f, dy = 0.0f, dz = 0.0f;
-    uint32_t idx = 0, ix = 0, iy = 0, iz = 0, rec = 3u << 30, steps = 0, stopped = 1u; // idx 0 = border bit, where lanes without a ray sit
+    uint32_t idx = 0, ix = 0, iy = 0, iz = 0, rec = kRecFresh, steps = 0, stopped = 1u; // idx 0 = border bit, where lanes without a ray sit
     int my_slot = -1;
 
     // A path is identified by its pixel handle = tile << 5 | tile-local pixel.  Radiance of paths that
@@ -341,7 +366,7 @@ __global__ void __launch_bounds__(kWaveThreads, kWaveCtas) trace_paths_wave_kern
             sx = r.side[0]; sy = r.side[1]; sz = r.side[2];
             dx = r.delta[0]; dy = r.delta[1]; dz = r.delta[2];
             ix = (uint32_t)r.step[0]; iy = (uint32_t)r.step[1] << xb; iz = (uint32_t)r.step[2] << zb;
-            idx = i0; rec = i0 | 3u << 30; steps = 0u;
+            idx = i0; rec = i0 | kRecFresh; steps = 0u;
             my_slot = (int)slot;
             stopped = 0u;
             return 1u;
@@ -570,7 +595,7 @@ __global__ void __launch_bounds__(kWaveThreads, kWaveCtas) trace_paths_wave_kern
                         ix = (uint32_t)(((int32_t)q1.x >> 31) * 2 + 1);
                         iy = (uint32_t)(((int32_t)q1.y >> 31) * 2 + 1) << xb;
                         iz = (uint32_t)(((int32_t)q1.z >> 31) * 2 + 1) << zb;
-                        rec = q2.x | 3u << 30;
+                        rec = q2.x | kRecFresh;
                         steps = q2.y;
                         stopped = 0u;
                     }
@@ -586,7 +611,7 @@ __global__ void __launch_bounds__(kWaveThreads, kWaveCtas) trace_paths_wave_kern
                     __syncwarp(); // (every read of the parked list precedes its rewrite)
                     if (my_slot >= 0) {
                         ray[my_slot * 3 + 0] = make_uint4(__float_as_uint(sx), __float_as_uint(sy), __float_as_uint(sz), idx);
-                        *reinterpret_cast<uint2*>(&ray[my_slot * 3 + 2]) = make_uint2(rec & 0x3fffffffu, steps);
+                        *reinterpret_cast<uint2*>(&ray[my_slot * 3 + 2]) = make_uint2(rec & kRecIdxMask, steps);
                         parked[__popc(~idle_mask & lt_mask)] = (uint8_t)my_slot;
                         my_slot = -1;
                         idx = 0;
@@ -601,18 +626,18 @@ __global__ void __launch_bounds__(kWaveThreads, kWaveCtas) trace_paths_wave_kern
                 // is then parked).  Lanes without a ray count as stopped.
                 uint32_t k_stop = rc < total ? (uint32_t)(32 - nact) + fp.refill_batch : (uint32_t)(33 - thresh);
                 k_stop = k_stop > 32u ? 32u : k_stop;
-                const uint32_t v = wave_walk<kSmem>(vol, sx, sy, sz, dx, dy, dz, idx, rec, steps, stopped, ix, iy, iz, k_stop);
+                const uint32_t v = wave_walk<kSmem>(vol, sx, sy, sz, dx, dy, dz, idx, rec, steps, stopped, ix, iy, iz, k_stop, smem0);
                 VT_STAT(8, 1); VT_STAT(9, __popc(v & ~idle_mask)); VT_STAT(11, nact);
                 // the rays that ended: on a filled voxel (hit) or on the border (left the volume)
                 const bool fin = stopped && my_slot >= 0;
                 bool hit = false;
                 if (fin) {
-                    const uint32_t st = steps + (((rec >> 30) + 1u) & 3u);
+                    const uint32_t st = steps + (((rec >> kWaveIdxBits) + 1u) & (kWaveBurst - 1u));
                     const uint32_t vx = (idx & ((1u << xb) - 1u)) - 1u, vy = ((idx >> xb) & ((1u << vol.yb) - 1u)) - 1u, vz = (idx >> zb) - 1u;
                     hit = vx < vol.w && vy < vol.h && vz < vol.d;
                     if (hit) {
                         ray[my_slot * 3 + 0] = make_uint4(__float_as_uint(sx), __float_as_uint(sy), __float_as_uint(sz), idx);
-                        *reinterpret_cast<uint2*>(&ray[my_slot * 3 + 2]) = make_uint2(rec & 0x3fffffffu, st);
+                        *reinterpret_cast<uint2*>(&ray[my_slot * 3 + 2]) = make_uint2(rec & kRecIdxMask, st);
                     }
                     it32 += st;
 #ifdef VT_WAVE_STATS

@@ -102,8 +102,8 @@ struct State {
     cudaEvent_t ev_begin[kRing] = {}, ev_trace0[kRing] = {}, ev_trace1[kRing] = {}, ev_end[kRing] = {};
     uint64_t ring_head = 0, ring_done = 0; // frames enqueued / frames folded into stats
     bool frame_pending = false;
-    uint32_t refill_threshold = 16; // tuning knob of the wavefront / persistent-lane kernels (VT_REFILL)
-    uint32_t refill_batch = 6;      // wavefront kernel: stopped lanes wait until this many can be refilled together (VT_REFILL_BATCH)
+    uint32_t refill_threshold = 12; // tuning knob of the wavefront / persistent-lane kernels (VT_REFILL)
+    uint32_t refill_batch = 10;     // wavefront kernel: stopped lanes wait until this many can be refilled together (VT_REFILL_BATCH)
     uint32_t item_spp = 16;         // wavefront kernel: most samples per work item (VT_ITEM_SPP)
     uint32_t items_per_warp = 6;    // wavefront kernel: work items wanted per resident warp (VT_ITEMS_PER_WARP)
 
@@ -337,7 +337,7 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
     fp.clear_rgba = g.clear_rgba;
     fp.sky_spp = g.cfg.spp;
     if (g.fused_mode && g.cfg.mode == VT_MODE_PATHS) {
-        if (g.inst_count != 1 || g.any_bricks || (g.cfg.flags & VT_FLAG_PER_PIXEL_PATHS) || g.max_idx_bits > 30)
+        if (g.inst_count != 1 || g.any_bricks || (g.cfg.flags & VT_FLAG_PER_PIXEL_PATHS) || g.max_idx_bits > 29)
             return fail("fused cross-GPU accumulation needs the single-instance wavefront kernel");
         if (g.fused_pixels != (size_t)g.cfg.width * g.cfg.height) return fail("fused accumulation buffer does not match the framebuffer size");
         fp.sky_spp = 0u; // pixels outside the screen rectangle are resolved analytically on the root
@@ -598,8 +598,8 @@ extern "C" uint64_t entry(void) {
     g.cfg.total_spp = env_u32("VT_TOTAL_SPP", 0);
     g.cfg.max_frames = (int32_t)env_u32("VT_MAX_FRAMES", 0);
     g.cfg.device = dev;
-    g.refill_threshold = env_u32("VT_REFILL", 16);
-    g.refill_batch = env_u32("VT_REFILL_BATCH", 6);
+    g.refill_threshold = env_u32("VT_REFILL", 12);
+    g.refill_batch = env_u32("VT_REFILL_BATCH", 10);
     g.item_spp = env_u32("VT_ITEM_SPP", 16);
     if (g.item_spp < 1) g.item_spp = 1;
     if (g.item_spp > 255) g.item_spp = 255; // an item's per-pixel sums live in 32-bit shared counters: 255 samples of < 2^24 each
