@@ -244,8 +244,9 @@ def run_cuda(args):
         accum = torch.zeros((HEIGHT, WIDTH, 3), dtype=torch.int64, device=dev)  # 2^-24 fixed-point radiance sums
         r.set_accum_buffer(accum.data_ptr())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    frame_pinned = torch.empty((HEIGHT, WIDTH, 4), dtype=torch.uint8, pin_memory=True)  # the host-side frame buffer
-    frame_host = frame_pinned.numpy()
+    frames_pinned = [torch.empty((HEIGHT, WIDTH, 4), dtype=torch.uint8, pin_memory=True) for _ in range(2)]  # host-side frame buffers
+    frame_host = frames_pinned[0].numpy()
+    frames_host = [f.numpy() for f in frames_pinned]
     lib = abi.load()
     cam = {"P": P, "V": V}
 
@@ -263,16 +264,14 @@ def run_cuda(args):
             reduce_accum(accum)
             r.resolve()
         else:
-            r.clear_accum()
-            r.render_async(cam["P"], cam["V"])
-            r.resolve()
+            r.render_frame_async(cam["P"], cam["V"])   # render_tick without the wait: clear + trace + resolve
 
     def step_resident():
         """One frame, everything device-resident, no host copies."""
         trace_and_reduce()
 
     def step_e2e():
-        """One frame through the reference-facing ABI with host buffers."""
+        """One frame through the reference-facing ABI with host buffers, host waiting for it (render_tick + vt_read_color)."""
         r.update_instances_raw(inst)          # host matrices -> pinned staging -> device
         if world == 1 and not fused:
             assert r.render_tick_raw(cam["P"], cam["V"])    # projection/camera by host pointer; clear + trace + resolve
@@ -281,6 +280,43 @@ def run_cuda(args):
         if rank == 0 or not fused:
             n = lib.vt_read_color(frame_host.ctypes.data, frame_host.nbytes)  # finished frame -> host
             assert n == frame_host.nbytes
+
+    def timed_e2e_pipelined(steps):
+        """The same per-step traffic (instance matrices host -> device, finished RGBA8 frame device -> pinned host), but the
+        host pipelines its frames the way a renderer with two frames in flight does: frame k+1 is traced while the copy
+        engine moves frame k over PCIe (vt_render_frame_async + vt_read_color_async, two colour buffers, two host buffers).
+        Step k's interval [e0, e1] on the launching stream covers its upload, its trace / reduce / resolve and the rest of
+        frame k-1's read-back (the stream waits for it before e1); the last read-back is timed on its own and added.  The L2
+        flush between steps stays outside the intervals."""
+        r.stats()
+        reads = rank == 0 or not fused
+        evs = []
+        for k in range(steps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            r.update_instances_raw(inst)
+            if world == 1 and not fused:
+                r.render_frame_async(cam["P"], cam["V"])
+            else:
+                trace_and_reduce()
+            if reads:
+                r.read_color_fence()          # (device-side) frame k-1 has landed in host memory
+            e1.record(stream)
+            if reads:
+                r.read_color_async(frames_host[k & 1])
+            evs.append((e0, e1))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        if reads:
+            r.read_color_fence()
+        e1.record(stream)
+        evs.append((e0, e1))
+        if reads:
+            r.read_color_wait()
+        torch.cuda.synchronize()
+        st = r.stats()
+        return [a.elapsed_time(b) for a, b in evs], st.rays_sum
 
     def barrier():
         if world > 1:
@@ -337,6 +373,7 @@ def run_cuda(args):
     for _ in range(max(args.warmup, 3)):
         step_resident()
         step_e2e()
+    timed_e2e_pipelined(max(args.warmup, 3))  # (untimed: the second colour buffer and the copy stream are created on first use)
     barrier()
     launches0 = r.stats().launches
     sampler = ClockSampler(local_rank)
@@ -352,8 +389,12 @@ def run_cuda(args):
     barrier()
     ms_e, rays_e = timed(step_e2e, steps)
     barrier()
-    (t_res, t_e2e, t_trace), (rays_all, rays_e_all, iters_all, analytic_all, launches_all) = reduce_over_ranks(
-        [sum(ms), sum(ms_e), trace_ms_sum], [rays, rays_e, iters, analytic, launches])
+    ms_p, rays_p = timed_e2e_pipelined(steps)
+    if rank == 0 or not fused:
+        assert np.array_equal(frames_host[0], frames_host[1]) and np.array_equal(frames_host[0], frame_host)  # same camera, same frame
+    barrier()
+    (t_res, t_e2e, t_e2e_pipe, t_trace), (rays_all, rays_e_all, rays_p_all, iters_all, analytic_all, launches_all) = reduce_over_ranks(
+        [sum(ms), sum(ms_e), sum(ms_p), trace_ms_sum], [rays, rays_e, rays_p, iters, analytic, launches])
 
     # ---- parity of the frame the timed configuration produces (all ranks' samples), against the CPU oracle ----
     trace_and_reduce()
@@ -398,7 +439,8 @@ def run_cuda(args):
 
     if rank == 0:
         value = rays_all / (t_res * 1e-3) / 1e6
-        e2e_value = rays_e_all / (t_e2e * 1e-3) / 1e6
+        e2e_serial = rays_e_all / (t_e2e * 1e-3) / 1e6
+        e2e_value = rays_p_all / (t_e2e_pipe * 1e-3) / 1e6
         traced = rays_all - analytic_all
         # roofline of the dominant kernel (trace_paths_wave_kernel), per launch on THIS rank:
         # algorithmic bytes = 4 B per DDA iteration (one RGBA8 voxel record, trace.frag:76) +
@@ -451,8 +493,13 @@ def run_cuda(args):
             "traced_rays_per_step": traced / steps, "traced_mrays_per_s": traced / (t_res * 1e-3) / 1e6,
             "analytic_sky_samples_per_step": analytic_all / steps,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(inst.nbytes + 128),
-                    "d2h_bytes_per_step": int(frame_host.nbytes + 32), "ms_per_step": t_e2e / steps,
-                    "traced_mrays_per_s": (rays_e_all - analytic_all) / (t_e2e * 1e-3) / 1e6},
+                    "d2h_bytes_per_step": int(frame_host.nbytes + 32), "ms_per_step": t_e2e_pipe / steps,
+                    "traced_mrays_per_s": (rays_p_all - analytic_all) / (t_e2e_pipe * 1e-3) / 1e6,
+                    "how": "every step: instance matrices from host memory -> device, trace (+ cross-GPU accumulation), resolve, "
+                           "RGBA8 frame -> pinned host memory; two frames in flight (vt_render_frame_async + vt_read_color_async: "
+                           "frame k+1 is traced while the copy engine moves frame k)",
+                    "host_waits_every_frame": {"value": e2e_serial, "ms_per_step": t_e2e / steps,
+                                               "how": "render_tick + vt_read_color, the host blocking on each"}},
             "gpu_launches": launches_all,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": recorded_traffic(), "kernel": "trace_paths_wave_kernel", "kernel_ms": kernel_s * 1e3,

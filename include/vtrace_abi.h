@@ -168,12 +168,24 @@ int32_t vt_configure(const vt_config* cfg);
  * projection / camera as in render_tick_info.  Up to 64 frames may be in flight; their counters and
  * kernel timings are folded into vt_stats at the next synchronising call.  0 = ok. */
 int32_t vt_render_async(const float* projection, const float* camera);
+/* render_tick without the wait: a whole frame (clear, trace, resolve into the colour buffer) enqueued on the
+ * library's stream, so that a host that pipelines its frames never stalls the device between them.  0 = ok. */
+int32_t vt_render_frame_async(const float* projection, const float* camera);
 /* Block until everything enqueued so far has finished.  0 = ok. */
 int32_t vt_synchronize(void);
 
 /* Read back the last frame.  `capacity` in bytes; returns bytes written or -1. */
 int64_t vt_read_hits(vt_hit_record* out, size_t capacity);
 int64_t vt_read_color(uint8_t* rgba8, size_t capacity); /* R,G,B,A bytes, sRGB-encoded         */
+/* Pipelined read-back: enqueue the copy of the frame enqueued last (vt_render_frame_async / render_tick / vt_resolve) into
+ * PAGE-LOCKED host memory on the library's copy stream and return at once; the next frame renders into a second colour
+ * buffer, so tracing frame k+1 overlaps the PCIe transfer of frame k.  The destination is valid after vt_read_color_wait
+ * (host blocks until every read-back issued so far has landed).  vt_read_color_fence makes the library's STREAM wait for
+ * them instead (no host wait), e.g. to time a pipelined loop with events.  Returns the byte count, -1 on error. */
+int64_t vt_read_color_async(uint8_t* pinned_rgba8, size_t capacity);
+int32_t vt_read_color_wait(void);
+int32_t vt_read_color_fence(void);
+
 /* The same frame in the reference swapchain's byte order, VK_FORMAT_B8G8R8A8_SRGB (lib/swapchain.c:88). */
 int64_t vt_read_color_bgra(uint8_t* bgra8, size_t capacity);
 /* Writes the last frame as a binary PPM (P6, RGB); 0 = ok.  For eyeballing / diffing against a real run of the reference. */

@@ -584,6 +584,64 @@ def test_paths_sample_sharding_is_exact(renderer, scene, assets):
     assert np.array_equal(total, whole)
 
 
+def test_paths_lean_frames_moving_camera(renderer, scene, assets):
+    """render_tick on a single-instance scene only clears / resolves the instance's screen rectangle; the sums outside it
+    are written when somebody asks (vt_read_accum), also after the rectangle moved and after other kinds of frames."""
+    t = scene.add(assets["AncientTemple"])
+    scene.set_instances([(glm.identity(), t)])
+    w, h, spp = 320, 200, 3
+    cams = [scenes.camera(w, h, eye=e, center=c) for e, c in (((1.6, -0.9, 1.2), (0.0, 0.0, 0.0)), ((2.2, -0.4, 0.3), (0.6, 0.2, 0.0)),
+                                                              ((0.9, -1.4, -1.1), (-0.3, 0.0, 0.2)))]
+    renderer.configure(width=w, height=h, mode=abi.MODE_PATHS, spp=spp, bounces=4, seed=0x5EED, sample_first=0, sample_stride=1,
+                       total_spp=spp, max_frames=0)
+    for P, V in cams:  # three frames, nothing read in between: stale sums of the earlier rectangles are lying around
+        assert renderer.render_tick_raw(P, V)
+    color = renderer.read_color()
+    want, _, _ = scene.o.render_paths(*cams[-1], w, h, spp=spp, bounces=4, seed=0x5EED, flags=0)
+    import oracle_lib
+    assert np.array_equal(color, oracle_lib.resolve(want, spp))
+    assert np.array_equal(renderer.read_accum(), want)
+    # a primary frame replaces the instance uniforms; the sums must have been completed before
+    assert renderer.render_tick_raw(*cams[0])
+    renderer.configure(width=w, height=h, mode=abi.MODE_PRIMARY, max_frames=0)
+    assert renderer.render_tick_raw(*cams[1])
+    want0, _, _ = scene.o.render_paths(*cams[0], w, h, spp=spp, bounces=4, seed=0x5EED, flags=0)
+    assert np.array_equal(renderer.read_accum(), want0)
+    # accumulating frames (the multi-GPU building block) on top of a lean frame
+    renderer.configure(width=w, height=h, mode=abi.MODE_PATHS, spp=spp, bounces=4, seed=0x5EED, sample_first=0, sample_stride=1,
+                       total_spp=spp, max_frames=0)
+    assert renderer.render_tick_raw(*cams[2])
+    renderer.render_async(*cams[2])
+    want2, _, _ = scene.o.render_paths(*cams[2], w, h, spp=spp, bounces=4, seed=0x5EED, flags=0)
+    assert np.array_equal(renderer.read_accum(), want2 * np.uint64(2))
+
+
+def test_pipelined_frames_and_async_readback(renderer, scene, assets):
+    """vt_render_frame_async + vt_read_color_async: three frames in flight with different cameras land in their own host
+    buffers, identical to what render_tick + vt_read_color give one by one; non-pinned destinations are refused."""
+    import torch
+    t = scene.add(assets["Treasure"])
+    scene.set_instances([(glm.identity(), t)])
+    w, h, spp = 256, 144, 2
+    cams = [scenes.camera(w, h, eye=e) for e in ((1.6, -0.9, 1.2), (0.8, -0.45, 0.6), (-1.2, -0.7, 1.5))]
+    renderer.configure(width=w, height=h, mode=abi.MODE_PATHS, spp=spp, bounces=3, seed=7, sample_first=0, sample_stride=1,
+                       total_spp=spp, max_frames=0)
+    want = []
+    for P, V in cams:
+        assert renderer.render_tick_raw(P, V)
+        want.append(renderer.read_color().copy())
+    bufs = [torch.zeros((h, w, 4), dtype=torch.uint8, pin_memory=True).numpy() for _ in cams]
+    for (P, V), b in zip(cams, bufs):
+        renderer.render_frame_async(P, V)
+        renderer.read_color_async(b)
+    renderer.read_color_wait()
+    for b, c in zip(bufs, want):
+        assert np.array_equal(b, c)
+    assert np.array_equal(renderer.read_color(), want[-1])  # the synchronous read still sees the newest frame
+    with pytest.raises(RuntimeError):
+        renderer.read_color_async(np.zeros((h, w, 4), dtype=np.uint8))
+
+
 def test_config2_full_size_exact(renderer, scene, assets):
     """configs[2] at full size (1080p, 64 spp, 4 bounces) — the bench workload itself — against the
     oracle bit for bit (radiance sums, ray and iteration counters, resolved colour), plus the

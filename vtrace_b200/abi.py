@@ -61,9 +61,13 @@ SYMBOLS = {
     "vt_get_config": (_i32, [C.POINTER(VtConfig)]),
     "vt_configure": (_i32, [C.POINTER(VtConfig)]),
     "vt_render_async": (_i32, [_vp, _vp]),
+    "vt_render_frame_async": (_i32, [_vp, _vp]),
     "vt_synchronize": (_i32, []),
     "vt_read_hits": (_i64, [_vp, _sz]),
     "vt_read_color": (_i64, [_vp, _sz]),
+    "vt_read_color_async": (_i64, [_vp, _sz]),
+    "vt_read_color_wait": (_i32, []),
+    "vt_read_color_fence": (_i32, []),
     "vt_read_color_bgra": (_i64, [_vp, _sz]),
     "vt_write_ppm": (_i32, [C.c_char_p]),
     "vt_read_depth": (_i64, [_vp, _sz]),

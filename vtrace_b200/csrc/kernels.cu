@@ -175,8 +175,12 @@ __host__ __device__ void mat4_inverse(const float* m, float* r) {
 
 __global__ void instance_setup_kernel(const float* __restrict__ instances, uint32_t n,
                                       const VolumeDesc* __restrict__ volumes, const FrameParams fp,
-                                      InstUniforms* __restrict__ out, uint32_t* flag, uint32_t flag_value) {
+                                      InstUniforms* __restrict__ out, uint32_t* flag, uint32_t flag_value,
+                                      unsigned long long* zero_stats) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && zero_stats) { // the frame's counters (rays, iterations, work-claim counter, analytic rays) start at 0
+        zero_stats[0] = 0ull; zero_stats[1] = 0ull; zero_stats[2] = 0ull; zero_stats[3] = 0ull;
+    }
     if (i == 0 && flag) { // fused multi-GPU accumulation, root: "the previous frame is consumed" (see flag_wait below)
         __threadfence_system();
         *reinterpret_cast<volatile uint32_t*>(flag) = flag_value;
@@ -258,9 +262,10 @@ __global__ void instance_setup_kernel(const float* __restrict__ instances, uint3
 }
 
 cudaError_t launch_instance_setup(const float* instances, uint32_t n, const VolumeDesc* volumes, FrameParams fp,
-                                  InstUniforms* out, uint32_t* flag, uint32_t flag_value, cudaStream_t stream) {
+                                  InstUniforms* out, uint32_t* flag, uint32_t flag_value, unsigned long long* zero_stats,
+                                  cudaStream_t stream) {
     const int threads = 64;
-    instance_setup_kernel<<<(n + threads - 1) / threads, threads, 0, stream>>>(instances, n, volumes, fp, out, flag, flag_value);
+    instance_setup_kernel<<<(n + threads - 1) / threads, threads, 0, stream>>>(instances, n, volumes, fp, out, flag, flag_value, zero_stats);
     return cudaGetLastError();
 }
 
@@ -1296,6 +1301,75 @@ __device__ __forceinline__ bool covered_region(const InstUniforms* __restrict__ 
     return !(px < Ip->bounds[0] || px > Ip->bounds[1] || py < Ip->bounds[2] || py > Ip->bounds[3]);
 }
 
+// -------------------------------------------------------------------------------------------
+// Single-instance frames through render_tick: only the instance's screen rectangle is ever accumulated.
+// The pixels outside it see nothing but sky for every sample, so the frame neither clears, nor adds to,
+// nor reads their accumulators: clear_rect zeroes the rectangle before the trace, resolve_rect encodes
+// it afterwards and writes the (constant) sky colour everywhere else, and fill_sky materialises
+// spp x sky in the outside accumulators only when somebody asks for them (vt_read_accum).
+__global__ void __launch_bounds__(256) clear_rect_kernel(const InstUniforms* __restrict__ inst, unsigned long long* __restrict__ accum,
+                                                         uint32_t width, uint32_t height) {
+    const int x0 = max(inst->bounds[0], 0), x1 = min(inst->bounds[1], (int)width - 1);
+    const int y0 = max(inst->bounds[2], 0), y1 = min(inst->bounds[3], (int)height - 1);
+    for (int py = y0 + (int)blockIdx.x; py <= y1; py += (int)gridDim.x)
+        for (int px = x0 + (int)threadIdx.x; px <= x1; px += (int)blockDim.x) {
+            const size_t p = (size_t)py * width + (size_t)px;
+            accum[3 * p + 0] = 0ull; accum[3 * p + 1] = 0ull; accum[3 * p + 2] = 0ull;
+        }
+}
+
+// sky_only != 0: touch nothing but the accumulators outside the rectangle (fill_sky)
+__global__ void __launch_bounds__(256) resolve_rect_kernel(const InstUniforms* __restrict__ inst, unsigned long long* __restrict__ accum,
+                                                           uint32_t width, uint32_t height, uint32_t spp, uint32_t total_spp, SrgbTables lut,
+                                                           uchar4* __restrict__ color, uint32_t sky_only,
+                                                           const unsigned long long* __restrict__ stats, unsigned long long* host_stats) {
+    if (host_stats && blockIdx.x == 0 && threadIdx.x == 0) { // the frame's counters go to (mapped, page-locked) host memory from here:
+        host_stats[0] = stats[0]; host_stats[1] = stats[1];  // no copy-engine operation on the frame's critical path
+        host_stats[2] = stats[2]; host_stats[3] = stats[3];
+        __threadfence_system();
+    }
+    const float scale = 1.0f / ((float)total_spp * 16777216.0f);
+    const float sky[3] = {53.0f / 100.0f, 81.0f / 100.0f, 92.0f / 100.0f};
+    unsigned long long sky_sum[3];
+    uint32_t sky_c[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        sky_sum[c] = __float2ull_rz((1.0f * sky[c]) * 16777216.0f) * spp;
+        sky_c[c] = srgb_encode(lut.threshold, __ull2float_rn(sky_sum[c]) * scale);
+    }
+    const uchar4 sky_px = make_uchar4((unsigned char)sky_c[0], (unsigned char)sky_c[1], (unsigned char)sky_c[2], 255);
+    for (uint32_t py = blockIdx.x; py < height; py += gridDim.x)
+        for (uint32_t px = threadIdx.x; px < width; px += blockDim.x) {
+            const size_t p = (size_t)py * width + px;
+            if (!covered_region(inst, (int)px, (int)py)) {
+                if (sky_only) { accum[3 * p + 0] = sky_sum[0]; accum[3 * p + 1] = sky_sum[1]; accum[3 * p + 2] = sky_sum[2]; }
+                else color[p] = sky_px;
+                continue;
+            }
+            if (sky_only) continue;
+            uint32_t c[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) c[k] = srgb_encode(lut.threshold, __ull2float_rn(accum[3 * p + k]) * scale);
+            color[p] = make_uchar4((unsigned char)c[0], (unsigned char)c[1], (unsigned char)c[2], 255);
+        }
+}
+
+cudaError_t launch_clear_rect(const InstUniforms* inst, unsigned long long* accum, uint32_t width, uint32_t height, int sm_count,
+                              cudaStream_t stream) {
+    const int grid = sm_count * 4 < (int)height ? sm_count * 4 : (int)height;
+    clear_rect_kernel<<<grid, 256, 0, stream>>>(inst, accum, width, height);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_resolve_rect(const InstUniforms* inst, unsigned long long* accum, uint32_t width, uint32_t height, uint32_t spp,
+                                uint32_t total_spp, SrgbTables lut, uchar4* color, bool sky_only, const unsigned long long* stats,
+                                unsigned long long* host_stats, int sm_count, cudaStream_t stream) {
+    const int grid = sm_count * 4 < (int)height ? sm_count * 4 : (int)height;
+    resolve_rect_kernel<<<grid, 256, 0, stream>>>(inst, accum, width, height, spp, total_spp, lut, color, sky_only ? 1u : 0u, stats, host_stats);
+    return cudaGetLastError();
+}
+
+
 // Cross-GPU ordering of the fused accumulation without a collective: sequence-number flags in the root's
 // memory.  A rank raises "my partial sums of frame s are in place" from the last block of its push kernel
 // (every block fences its stores at system scope before it counts itself done); the root's summation kernel
@@ -1483,6 +1557,11 @@ cudaError_t launch_trace_primary(const FrameParams& fp, const InstUniforms* inst
     return cudaGetLastError();
 }
 
+// true when launch_trace_paths runs the single-instance wavefront kernel for this frame
+bool paths_use_wave_kernel(const FrameParams& fp) {
+    return !fp.any_bricks && fp.n_inst == 1 && !(fp.flags & VT_FLAG_PER_PIXEL_PATHS) && fp.max_idx_bits <= kWaveIdxBits;
+}
+
 cudaError_t launch_trace_paths(const FrameParams& fp, const InstUniforms* inst, BinTable bins, WorldGridTable wg, const uint32_t* mask_arena,
                                uint32_t arena_words, bool masks_in_smem, SrgbTables lut, FrameBuffers fb, int sm_count,
                                cudaStream_t stream) {
@@ -1498,7 +1577,7 @@ cudaError_t launch_trace_paths(const FrameParams& fp, const InstUniforms* inst, 
         }
         return cudaGetLastError();
     }
-    if (fp.n_inst == 1 && !(fp.flags & VT_FLAG_PER_PIXEL_PATHS) && fp.max_idx_bits <= kWaveIdxBits) {
+    if (paths_use_wave_kernel(fp)) {
         // single-instance scenes: warp-local wavefront engine (paths_wave.cuh)
         const int max_warps = 1 << 30; // persistent: one resident wave, work is claimed dynamically
         // the masks share the SM's shared memory with the warps' pools: a large arena is read through L1 instead

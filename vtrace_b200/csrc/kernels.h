@@ -159,7 +159,8 @@ __host__ __device__ void mat4_inverse(const float* m, float* out);
 cudaError_t launch_build_mask(const uint8_t* rgba, uint32_t w, uint32_t h, uint32_t d, uint32_t xb, uint32_t yb,
                               uint32_t* mask, uint32_t mask_words, cudaStream_t stream);
 cudaError_t launch_instance_setup(const float* instances, uint32_t n, const VolumeDesc* volumes, FrameParams fp,
-                                  InstUniforms* out, uint32_t* flag, uint32_t flag_value, cudaStream_t stream);
+                                  InstUniforms* out, uint32_t* flag, uint32_t flag_value, unsigned long long* zero_stats,
+                                  cudaStream_t stream);
 // bins the instances' screen rectangles; *cursor (device) ends up holding the number of list entries
 // needed — if it exceeds `capacity` the lists are incomplete and the caller must retry with more room
 cudaError_t launch_bin_instances(const InstUniforms* inst, uint32_t n_inst, uint32_t bins_x, uint32_t bins_y, uint32_t* offset,
@@ -200,6 +201,14 @@ cudaError_t launch_push_partial(const InstUniforms* inst, unsigned long long* lo
 cudaError_t launch_resolve_partials(const InstUniforms* inst, const uint4* partials, uint32_t world, uint32_t width, uint32_t height,
                                     uint32_t total_spp, SrgbTables lut, uchar4* color, unsigned long long* accum_out, bool compact,
                                     FusedSync fs, int sm_count, cudaStream_t stream);
+// single-instance frames: zero / resolve only the instance's screen rectangle; sky_only: write spp x sky into the
+// accumulators outside it instead (they are not touched by such a frame otherwise)
+cudaError_t launch_clear_rect(const InstUniforms* inst, unsigned long long* accum, uint32_t width, uint32_t height, int sm_count,
+                              cudaStream_t stream);
+cudaError_t launch_resolve_rect(const InstUniforms* inst, unsigned long long* accum, uint32_t width, uint32_t height, uint32_t spp,
+                                uint32_t total_spp, SrgbTables lut, uchar4* color, bool sky_only, const unsigned long long* stats,
+                                unsigned long long* host_stats, int sm_count, cudaStream_t stream);
+bool paths_use_wave_kernel(const FrameParams& fp);
 cudaError_t launch_resolve(const unsigned long long* accum, uint32_t n_pixels, uint32_t total_spp, SrgbTables lut,
                            uchar4* color, cudaStream_t stream);
 // one-time: opt in to large dynamic shared memory

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <utility>
 #include <vector>
 
 namespace {
@@ -43,7 +44,14 @@ struct State {
     size_t tex_staging_size = 0;
 
     // instances
-    float* h_inst = nullptr; // pinned staging the engine writes into (lib/memory.c:245-247)
+    // pinned staging the engine writes into (lib/memory.c:245-247): a ring of kInstRing buffers, so that the host can fill the
+    // next frame's instances while earlier uploads are still queued (no host wait unless it runs kInstRing frames ahead)
+    static constexpr int kInstRing = 4;
+    float* h_inst = nullptr;       // kInstRing x inst_cap x 16 floats
+    int inst_slot = 0;             // the buffer handed out last
+    const float* inst_src = nullptr; // != nullptr: the instance-setup kernel reads the staging buffer itself (few instances)
+    cudaEvent_t ev_inst[kInstRing] = {nullptr, nullptr, nullptr, nullptr};
+    bool inst_busy[kInstRing] = {false, false, false, false};
     float* d_inst = nullptr;
     InstUniforms* d_iu = nullptr;
     uint32_t inst_cap = 0, inst_count = 1;
@@ -91,6 +99,12 @@ struct State {
     uint32_t* h_fused_err = nullptr; // pinned
     bool fused_sync = true;
     unsigned long long* fused_sum = nullptr; // root, on demand: materialised sums for vt_read_accum
+    // asynchronous colour read-back (vt_read_color_async): a second colour buffer, a copy stream, one event per buffer
+    uchar4* d_color_alt = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_color_ready = nullptr, ev_copy_done[2] = {nullptr, nullptr}; // [0] belongs to d_color, [1] to d_color_alt
+    bool copy_pending[2] = {false, false};
+    uint32_t sky_missing_spp = 0;            // != 0: the last frame left the accumulators outside the screen rectangle untouched (spp x sky missing)
     unsigned long long* d_stats = nullptr;
     unsigned long long* h_stats = nullptr; // pinned: kRing slots of 4 counters (rays, iterations, work-claim counter, analytic rays)
     void* h_readback = nullptr;            // pinned staging for vt_read_*
@@ -162,8 +176,10 @@ int alloc_framebuffer() {
     const uint32_t w = g.cfg.width, h = g.cfg.height;
     if (w == g.fb_w && h == g.fb_h && g.d_color) return 0;
     CK(cudaStreamSynchronize(g.stream));
-    cudaFree(g.d_rec); cudaFree(g.d_color); cudaFree(g.d_depth); cudaFree(g.d_accum_own);
-    g.d_rec = nullptr; g.d_color = nullptr; g.d_depth = nullptr; g.d_accum = nullptr; g.d_accum_own = nullptr;
+    if (g.copy_stream) CK(cudaStreamSynchronize(g.copy_stream));
+    cudaFree(g.d_rec); cudaFree(g.d_color); cudaFree(g.d_color_alt); cudaFree(g.d_depth); cudaFree(g.d_accum_own);
+    g.d_rec = nullptr; g.d_color = nullptr; g.d_color_alt = nullptr; g.d_depth = nullptr; g.d_accum = nullptr; g.d_accum_own = nullptr;
+    g.copy_pending[0] = g.copy_pending[1] = false;
     const size_t n = (size_t)w * h;
     CK(cudaMalloc(&g.d_rec, n * sizeof(HitRecord)));
     CK(cudaMalloc(&g.d_color, n * sizeof(uchar4)));
@@ -174,6 +190,7 @@ int alloc_framebuffer() {
     CK(cudaMemsetAsync(g.d_color, 0, n * sizeof(uchar4), g.stream));
     CK(cudaMemsetAsync(g.d_depth, 0, n * sizeof(float), g.stream));
     CK(cudaMemsetAsync(g.d_accum, 0, n * 3 * sizeof(unsigned long long), g.stream));
+    g.sky_missing_spp = 0;
     g.fb_w = w; g.fb_h = h;
     return 0;
 }
@@ -188,29 +205,65 @@ int ensure_readback(size_t bytes) {
     return 0;
 }
 
+constexpr uint32_t kDirectInstances = 64; // up to this many instances are read by the setup kernel straight from the staging buffer
+
+float* inst_staging(int slot) { return g.h_inst + (size_t)slot * g.inst_cap * 16; }
+
 int ensure_instances(uint32_t n) {
     if (n <= g.inst_cap) return 0;
     // lib/memory.c:239-243: the instance buffers are re-created at the next power of two
     const uint32_t cap = (uint32_t)round_up_p2(n);
     CK(cudaStreamSynchronize(g.stream));
     float* h_new = nullptr;
-    CK(cudaMallocHost(&h_new, (size_t)cap * 64));
-    memset(h_new, 0, (size_t)cap * 64);
+    CK(cudaMallocHost(&h_new, (size_t)State::kInstRing * cap * 64));
+    memset(h_new, 0, (size_t)State::kInstRing * cap * 64);
     if (g.h_inst) {
-        memcpy(h_new, g.h_inst, (size_t)g.inst_cap * 64);
+        memcpy(h_new, inst_staging(g.inst_slot), (size_t)g.inst_cap * 64); // the current contents survive, in slot 0
         cudaFreeHost(g.h_inst);
     }
     g.h_inst = h_new;
+    g.inst_slot = 0;
+    for (int i = 0; i < State::kInstRing; ++i) {
+        g.inst_busy[i] = false;
+        if (!g.ev_inst[i]) CK(cudaEventCreateWithFlags(&g.ev_inst[i], cudaEventDisableTiming));
+    }
     cudaFree(g.d_inst); cudaFree(g.d_iu);
     g.d_inst = nullptr; g.d_iu = nullptr;
     CK(cudaMalloc(&g.d_inst, (size_t)cap * 64));
     CK(cudaMalloc(&g.d_iu, (size_t)cap * sizeof(InstUniforms)));
-    CK(cudaMemcpyAsync(g.d_inst, g.h_inst, (size_t)cap * 64, cudaMemcpyHostToDevice, g.stream));
     g.inst_cap = cap;
+    CK(cudaMemcpyAsync(g.d_inst, g.h_inst, (size_t)cap * 64, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    if (g.inst_src) g.inst_src = inst_staging(0);
     return 0;
 }
 
 int render_async(const float* P, const float* V, bool clear_accum, bool resolve);
+
+// Called before anything writes the colour buffer: a buffer whose asynchronous read-back (vt_read_color_async) may still be
+// in flight is left alone — the frame goes to the other one, after (device-side) waiting for that one's own read-back.
+int prepare_color_target() {
+    if (!g.copy_pending[0]) return 0;
+    if (!g.d_color_alt) CK(cudaMalloc(&g.d_color_alt, (size_t)g.cfg.width * g.cfg.height * sizeof(uchar4)));
+    std::swap(g.d_color, g.d_color_alt);
+    std::swap(g.ev_copy_done[0], g.ev_copy_done[1]);
+    std::swap(g.copy_pending[0], g.copy_pending[1]);
+    if (g.copy_pending[0]) {
+        CK(cudaStreamWaitEvent(g.stream, g.ev_copy_done[0], 0));
+        g.copy_pending[0] = false;
+    }
+    return 0;
+}
+
+// After a lean frame (render_async) the accumulators outside the instance's screen rectangle hold stale data: write
+// spp x sky there before anybody reads or adds to them.
+int complete_accum() {
+    if (!g.sky_missing_spp) return 0;
+    SrgbTables lut{g.d_dec, g.d_thr};
+    CK(launch_resolve_rect(g.d_iu, g.d_accum, g.cfg.width, g.cfg.height, g.sky_missing_spp, 1u, lut, g.d_color, true, nullptr, nullptr, g.sm_count, g.stream));
+    g.sky_missing_spp = 0;
+    return 0;
+}
 
 static constexpr uint32_t kFusedMaxWorld = 64;
 static uint32_t* fused_arrive(uint32_t half) { return g.fused_flags + half * kFusedMaxWorld; }
@@ -356,6 +409,15 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
     }
     if (ensure_instances(g.inst_count)) return -1;
 
+    // render_tick on a single-instance scene: nothing outside the instance's screen rectangle is cleared, added to or
+    // read (kernels.cu, clear_rect / resolve_rect); the sums there are materialised on demand (complete_accum) — at the
+    // latest before another kind of frame replaces the instance uniforms the rectangle lives in.
+    static const bool lean_enabled = env_u32("VT_LEAN_FRAME", 1) != 0;
+    const bool lean = g.cfg.mode == VT_MODE_PATHS && clear_accum && resolve && !g.fused_mode && g.d_accum == g.d_accum_own &&
+                      paths_use_wave_kernel(fp) && lean_enabled;
+    if (lean) fp.sky_spp = 0u;
+    else if (complete_accum()) return -1;
+
     CK(cudaEventRecord(g.ev_begin[slot], g.stream));
     uint32_t* consumed_flag = nullptr;
     uint32_t consumed_value = 0;
@@ -368,8 +430,11 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
             consumed_value = g.fused_seq - 1;
         }
     }
-    CK(cudaMemsetAsync(g.d_stats, 0, 4 * sizeof(unsigned long long), g.stream));
-    CK(launch_instance_setup(g.d_inst, g.inst_count, g.d_vols, fp, g.d_iu, consumed_flag, consumed_value, g.stream));
+    // (the setup kernel also zeroes the frame's counters; a few instances are read straight from the page-locked staging
+    // buffer the engine wrote them into — neither costs the frame a copy-engine operation)
+    CK(launch_instance_setup(g.inst_src ? g.inst_src : g.d_inst, g.inst_count, g.d_vols, fp, g.d_iu, consumed_flag, consumed_value,
+                             g.d_stats, g.stream));
+    if (g.inst_src) CK(cudaEventRecord(g.ev_inst[g.inst_slot], g.stream)); // the staging buffer is in use until here
     g.stats.launches += 1;
 
     // many instances: bin their screen rectangles (16x16-pixel bins) so a pixel only visits its own
@@ -434,6 +499,7 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
     g.stats.masks_in_smem = in_smem ? 1u : 0u;
     FrameBuffers fb{};
     fb.records = (g.cfg.flags & VT_FLAG_NO_HIT_RECORDS) ? nullptr : g.d_rec;
+    if (prepare_color_target()) return -1;
     fb.color = g.d_color;
     fb.depth = g.d_depth;
     const bool fused = g.fused_mode && g.cfg.mode == VT_MODE_PATHS;
@@ -453,8 +519,13 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
         CK(cudaEventRecord(g.ev_trace1[slot], g.stream));
         g.stats.launches += 1;
     } else {
-        if (clear_accum)
+        if (lean) {
+            CK(launch_clear_rect(g.d_iu, g.d_accum, g.cfg.width, g.cfg.height, g.sm_count, g.stream));
+            g.stats.launches += 1;
+            g.sky_missing_spp = g.cfg.spp;
+        } else if (clear_accum) {
             CK(cudaMemsetAsync(g.d_accum, 0, (size_t)g.cfg.width * g.cfg.height * 3 * sizeof(unsigned long long), g.stream));
+        }
         CK(cudaEventRecord(g.ev_trace0[slot], g.stream));
         CK(launch_trace_paths(fp, g.d_iu, bins, wg, g.d_arena, g.arena_words, in_smem, lut, fb, g.sm_count, g.stream));
         CK(cudaEventRecord(g.ev_trace1[slot], g.stream));
@@ -476,11 +547,13 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
         }
         if (resolve && !fused) {
             const uint32_t total = g.cfg.total_spp ? g.cfg.total_spp : g.cfg.spp;
-            CK(launch_resolve(g.d_accum, g.cfg.width * g.cfg.height, total ? total : 1, lut, g.d_color, g.stream));
+            if (lean) CK(launch_resolve_rect(g.d_iu, g.d_accum, g.cfg.width, g.cfg.height, g.cfg.spp, total ? total : 1, lut, g.d_color, false,
+                                             g.d_stats, g.h_stats + 4 * slot, g.sm_count, g.stream));
+            else CK(launch_resolve(g.d_accum, g.cfg.width * g.cfg.height, total ? total : 1, lut, g.d_color, g.stream));
             g.stats.launches += 1;
         }
     }
-    CK(cudaMemcpyAsync(g.h_stats + 4 * slot, g.d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g.stream));
+    if (!lean) CK(cudaMemcpyAsync(g.h_stats + 4 * slot, g.d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g.stream));
     CK(cudaEventRecord(g.ev_end[slot], g.stream));
     g.ring_head += 1;
     g.frame_pending = true;
@@ -844,21 +917,35 @@ extern "C" float* start_update_instances(uint32_t instance_count) {
     if (!g.inited) { fail("start_update_instances before entry()"); return nullptr; }
     if (instance_count == 0) instance_count = 1; // lib/memory.c:236
     if (cudaSetDevice(g.device) != cudaSuccess) return nullptr;
-    // the previous frame's upload must have consumed the staging buffer before it is rewritten
-    if (cudaStreamSynchronize(g.stream) != cudaSuccess) return nullptr;
+    const uint32_t keep = g.inst_count < g.inst_cap ? g.inst_count : g.inst_cap;
     if (ensure_instances(instance_count)) return nullptr;
+    // the next staging buffer of the ring; its previous upload (kInstRing updates ago) must have been consumed
+    const int prev = g.inst_slot, slot = (g.inst_slot + 1) % State::kInstRing;
+    if (g.inst_busy[slot]) {
+        if (cudaEventSynchronize(g.ev_inst[slot]) != cudaSuccess) return nullptr;
+        g.inst_busy[slot] = false;
+    }
+    // the reference hands out one persistently mapped buffer (lib/memory.c:245-247): what was written before is still there
+    if (keep) memcpy(inst_staging(slot), inst_staging(prev), (size_t)keep * 64);
+    g.inst_slot = slot;
     g.inst_count = instance_count;
-    return g.h_inst;
+    return inst_staging(slot);
 }
-
 extern "C" int32_t end_update_instances(uint32_t instance_count) {
     if (!g.inited) return fail("end_update_instances before entry()");
     if (instance_count == 0) instance_count = 1; // lib/memory.c:251
     if (instance_count > g.inst_cap) return fail("end_update_instances: %u > capacity %u", instance_count, g.inst_cap);
     CK(cudaSetDevice(g.device));
     g.inst_count = instance_count;
-    // lib/memory.c:257-264: staging -> device copy
-    CK(cudaMemcpyAsync(g.d_inst, g.h_inst, (size_t)instance_count * 64, cudaMemcpyHostToDevice, g.stream));
+    if (instance_count <= kDirectInstances) {
+        g.inst_src = inst_staging(g.inst_slot); // page-locked memory is device-accessible (unified addressing): 64 bytes per instance over PCIe
+    } else {
+        g.inst_src = nullptr;
+        // lib/memory.c:257-264: staging -> device copy
+        CK(cudaMemcpyAsync(g.d_inst, inst_staging(g.inst_slot), (size_t)instance_count * 64, cudaMemcpyHostToDevice, g.stream));
+    }
+    CK(cudaEventRecord(g.ev_inst[g.inst_slot], g.stream));
+    g.inst_busy[g.inst_slot] = true;
     return 0;
 }
 
@@ -879,6 +966,8 @@ extern "C" void cleanup(void) {
     for (auto& b : g.brick_allocs) { cudaFree(b.l1); cudaFree(b.table); cudaFree(b.pool); cudaFree(b.heights); cudaFree(b.colors); cudaFree(b.d_desc); }
     g.brick_allocs.clear();
     cudaFree(g.d_vols); cudaFree(g.d_arena); cudaFree(g.d_inst); cudaFree(g.d_iu); cudaFree(g.d_dec); cudaFree(g.d_thr);
+    if (g.copy_stream) { cudaStreamSynchronize(g.copy_stream); cudaStreamDestroy(g.copy_stream); cudaEventDestroy(g.ev_color_ready); cudaEventDestroy(g.ev_copy_done[0]); cudaEventDestroy(g.ev_copy_done[1]); }
+    cudaFree(g.d_color_alt);
     cudaFree(g.d_rec); cudaFree(g.d_color); cudaFree(g.d_depth); cudaFree(g.d_accum_own); cudaFree(g.d_stats);
     cudaFree(g.d_bin_offset); cudaFree(g.d_bin_count); cudaFree(g.d_bin_list); cudaFree(g.d_bin_cursor);
     if (g.h_bin_cursor) cudaFreeHost(g.h_bin_cursor);
@@ -887,6 +976,7 @@ extern "C" void cleanup(void) {
     g.d_world_aabb = nullptr; g.d_world_hdr = nullptr; g.h_world_hdr = nullptr; g.d_world_cells = g.d_world_list = nullptr;
     g.world_aabb_cap = g.world_list_cap = 0; g.world_used = false;
     if (g.h_inst) cudaFreeHost(g.h_inst);
+    for (int i = 0; i < State::kInstRing; ++i) if (g.ev_inst[i]) cudaEventDestroy(g.ev_inst[i]);
     if (g.h_tex_staging) cudaFreeHost(g.h_tex_staging);
     if (g.h_stats) cudaFreeHost(g.h_stats);
     if (g.h_readback) cudaFreeHost(g.h_readback);
@@ -929,6 +1019,11 @@ extern "C" int32_t vt_render_async(const float* projection, const float* camera)
     return render_async(projection, camera, false, false);
 }
 
+extern "C" int32_t vt_render_frame_async(const float* projection, const float* camera) {
+    if (!projection || !camera) return -1;
+    return render_async(projection, camera, true, true);
+}
+
 extern "C" int32_t vt_synchronize(void) {
     if (!g.inited) return -1;
     CK(cudaSetDevice(g.device));
@@ -944,6 +1039,44 @@ extern "C" int64_t vt_read_hits(vt_hit_record* out, size_t capacity) {
 extern "C" int64_t vt_read_color(uint8_t* rgba8, size_t capacity) {
     return read_back(g.d_color, (size_t)g.cfg.width * g.cfg.height * 4, rgba8, capacity);
 }
+extern "C" int64_t vt_read_color_async(uint8_t* pinned_rgba8, size_t capacity) {
+    const size_t bytes = (size_t)g.cfg.width * g.cfg.height * 4;
+    if (!g.inited) return fail("read before entry()");
+    if (!pinned_rgba8 || capacity < bytes) return fail("read-back buffer too small: need %zu bytes, have %zu", bytes, capacity);
+    if (cudaSetDevice(g.device) != cudaSuccess) return fail("cudaSetDevice failed");
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, pinned_rgba8) != cudaSuccess || attr.type != cudaMemoryTypeHost) {
+        (void)cudaGetLastError();
+        return fail("vt_read_color_async: the destination must be page-locked host memory");
+    }
+    if (!g.copy_stream) {
+        CK(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&g.ev_color_ready, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&g.ev_copy_done[0], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&g.ev_copy_done[1], cudaEventDisableTiming));
+    }
+    CK(cudaEventRecord(g.ev_color_ready, g.stream)); // the frame enqueued last is complete
+    CK(cudaStreamWaitEvent(g.copy_stream, g.ev_color_ready, 0));
+    CK(cudaMemcpyAsync(pinned_rgba8, g.d_color, bytes, cudaMemcpyDeviceToHost, g.copy_stream));
+    CK(cudaEventRecord(g.ev_copy_done[0], g.copy_stream));
+    g.copy_pending[0] = true; // (the next frame renders into the other colour buffer: prepare_color_target)
+    return (int64_t)bytes;
+}
+
+extern "C" int32_t vt_read_color_wait(void) {
+    if (!g.inited) return -1;
+    if (g.copy_stream) CK(cudaStreamSynchronize(g.copy_stream));
+    return 0;
+}
+
+extern "C" int32_t vt_read_color_fence(void) {
+    if (!g.inited) return -1;
+    if (!g.copy_stream) return 0;
+    for (int i = 0; i < 2; ++i)
+        if (g.copy_pending[i]) CK(cudaStreamWaitEvent(g.stream, g.ev_copy_done[i], 0));
+    return 0;
+}
+
 extern "C" int64_t vt_read_color_bgra(uint8_t* bgra8, size_t capacity) {
     const int64_t n = read_back(g.d_color, (size_t)g.cfg.width * g.cfg.height * 4, bgra8, capacity);
     for (int64_t p = 0; p + 3 < n; p += 4) { const uint8_t r = bgra8[p]; bgra8[p] = bgra8[p + 2]; bgra8[p + 2] = r; }
@@ -980,15 +1113,23 @@ extern "C" int64_t vt_read_accum(uint64_t* accum, size_t capacity) {
             return fail("vt_read_accum: resolve failed");
         return read_back(g.fused_sum, g.fused_pixels * 24, accum, capacity);
     }
+    if (g.inited && g.sky_missing_spp) {
+        if (cudaSetDevice(g.device) != cudaSuccess || finish_frame() || complete_accum()) return -1;
+    }
     return read_back(g.d_accum, (size_t)g.cfg.width * g.cfg.height * 24, accum, capacity);
 }
 
-extern "C" void* vt_accum_device_ptr(void) { return g.inited ? (void*)g.d_accum : nullptr; }
+extern "C" void* vt_accum_device_ptr(void) {
+    if (!g.inited) return nullptr;
+    if (g.sky_missing_spp && (cudaSetDevice(g.device) != cudaSuccess || finish_frame() || complete_accum())) return nullptr;
+    return (void*)g.d_accum;
+}
 
 extern "C" int32_t vt_set_accum_buffer(void* device_ptr) {
     if (!g.inited) return -1;
     CK(cudaSetDevice(g.device));
     if (finish_frame()) return -1;
+    if (complete_accum()) return -1;
     CK(cudaStreamSynchronize(g.stream));
     g.d_accum = device_ptr ? (unsigned long long*)device_ptr : g.d_accum_own;
     return 0;
@@ -998,15 +1139,18 @@ extern "C" int32_t vt_clear_accum(void) {
     if (!g.inited) return -1;
     CK(cudaSetDevice(g.device));
     CK(cudaMemsetAsync(g.d_accum, 0, (size_t)g.cfg.width * g.cfg.height * 24, g.stream));
+    g.sky_missing_spp = 0;
     return 0;
 }
 
 extern "C" int32_t vt_resolve(void) {
     if (!g.inited) return -1;
     CK(cudaSetDevice(g.device));
+    if (complete_accum()) return -1;
     const uint32_t total = g.cfg.total_spp ? g.cfg.total_spp : g.cfg.spp;
     SrgbTables lut{g.d_dec, g.d_thr};
     if (g.fused_mode == 2) return fail("vt_resolve: only the root of a fused reduction holds the sums");
+    if (prepare_color_target()) return -1;
     if (g.fused_mode == 1) {
         const uint4* partials = g.fused_base + (size_t)g.fused_index * g.fused_world * g.fused_pixels * 2;
         CK(launch_resolve_partials(g.d_iu, partials, g.fused_world, g.cfg.width, g.cfg.height, total ? total : 1, lut, g.d_color, nullptr,

@@ -207,6 +207,26 @@ class Renderer:
         if self._lib.vt_render_async(P.ctypes.data, V.ctypes.data) != 0:
             raise RuntimeError("vt_render_async failed: " + abi.last_error())
 
+    def render_frame_async(self, perspective, camera):
+        """render_tick without the wait (clear + trace + resolve enqueued on the library's stream)."""
+        P = np.ascontiguousarray(perspective, dtype=np.float32).reshape(16)
+        V = np.ascontiguousarray(camera, dtype=np.float32).reshape(16)
+        if self._lib.vt_render_frame_async(P.ctypes.data, V.ctypes.data) != 0:
+            raise RuntimeError("vt_render_frame_async failed: " + abi.last_error())
+
+    def read_color_async(self, pinned: np.ndarray):
+        """Pipelined read-back of the frame enqueued last into page-locked memory (valid after read_color_wait)."""
+        if self._lib.vt_read_color_async(pinned.ctypes.data, pinned.nbytes) != pinned.nbytes:
+            raise RuntimeError("vt_read_color_async failed: " + abi.last_error())
+
+    def read_color_wait(self):
+        if self._lib.vt_read_color_wait() != 0:
+            raise RuntimeError("vt_read_color_wait failed: " + abi.last_error())
+
+    def read_color_fence(self):
+        if self._lib.vt_read_color_fence() != 0:
+            raise RuntimeError("vt_read_color_fence failed: " + abi.last_error())
+
     def synchronize(self):
         if self._lib.vt_synchronize() != 0:
             raise RuntimeError("vt_synchronize failed: " + abi.last_error())
