@@ -201,7 +201,7 @@ def run_cuda(args):
 
     from tools import scenes
     from vtrace_b200 import abi
-    from vtrace_b200.distributed import reduce_accum, setup_fused_reduce, shard_samples, stream_barrier
+    from vtrace_b200.distributed import reduce_accum, setup_fused_reduce, shard_samples, shard_samples_weighted, stream_barrier
     from vtrace_b200.renderer import Renderer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -243,6 +243,14 @@ def run_cuda(args):
     if not fused and world > 1:
         accum = torch.zeros((HEIGHT, WIDTH, 3), dtype=torch.int64, device=dev)  # 2^-24 fixed-point radiance sums
         r.set_accum_buffer(accum.data_ptr())
+    shares = [shard_samples(SPP, k, world) for k in range(world)]
+    if fused and world > 1:
+        # the root also sums the partial sums and encodes the frame (about two samples' worth of time): it traces fewer
+        relief = float(os.environ.get("VT_ROOT_RELIEF_SPP", "2"))
+        shares = [shard_samples_weighted(SPP, k, world, relief) for k in range(world)]
+        first, stride, count = shares[rank]
+        r.configure(width=WIDTH, height=HEIGHT, mode=abi.MODE_PATHS, flags=abi.FLAG_NO_HIT_RECORDS, spp=count,
+                    bounces=BOUNCES, seed=SEED, sample_first=first, sample_stride=stride, total_spp=SPP, max_frames=0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     frames_pinned = [torch.empty((HEIGHT, WIDTH, 4), dtype=torch.uint8, pin_memory=True) for _ in range(2)]  # host-side frame buffers
     frame_host = frames_pinned[0].numpy()
@@ -485,7 +493,7 @@ def run_cuda(args):
             "ms_per_step": t_res / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": DATA,
             "config": CONFIG,
-            "run": {"spp_per_rank": SPP // world, "partition": (f"spp sharded over {world} rank(s), " + (
+            "run": {"spp_per_rank": [c for _, _, c in shares], "partition": (f"spp sharded over {world} rank(s), " + (
                         ("partial sums pushed into rank 0's memory over NVLink peer stores, ordered by " +
                          ("flags in peer memory" if fused_flags else "a 4-byte NCCL stream barrier")) if fused
                         else "NCCL all-reduce of 3*w*h int64")) if world > 1 else "single rank",

@@ -6,7 +6,7 @@ import numpy as np
 
 from tools import scenes
 from vtrace_b200 import glm, voxel
-from vtrace_b200.distributed import shard_samples
+from vtrace_b200.distributed import shard_samples, shard_samples_weighted
 from vtrace_b200.renderer import TextureUploadQueue
 
 
@@ -72,3 +72,20 @@ def test_shard_samples_partitions_every_sample_once():
                 first, stride, count = shard_samples(total, rank, world)
                 seen += [first + k * stride for k in range(count)]
             assert sorted(seen) == list(range(total))
+
+
+def test_weighted_sharding_partitions_every_sample_once_and_relieves_the_root():
+    for total in (0, 1, 7, 64, 65, 256):
+        for world in (1, 2, 3, 4, 8):
+            for extra in (0.0, 2.0, 5.5, 1000.0):
+                seen, counts = [], []
+                for rank in range(world):
+                    first, stride, count = shard_samples_weighted(total, rank, world, extra)
+                    seen += [first + k * stride for k in range(count)]
+                    counts.append(count)
+                assert sorted(seen) == list(range(total))
+                if world > 1:
+                    assert counts[0] <= min(counts[1:]) + (1 if extra == 0.0 else 0)
+                    assert max(counts[1:]) - min(counts[1:]) <= 1
+    assert [shard_samples_weighted(64, r, 8)[2] for r in range(8)] == [6, 9, 9, 8, 8, 8, 8, 8]
+    assert [shard_samples_weighted(64, r, 2)[2] for r in range(2)] == [31, 33]

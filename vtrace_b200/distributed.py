@@ -20,6 +20,33 @@ def shard_samples(total_spp: int, rank: int, world: int) -> tuple[int, int, int]
     return rank, world, count
 
 
+def shard_samples_weighted(total_spp: int, rank: int, world: int, root_extra_spp: float = 2.0, root: int = 0) -> tuple[int, int, int]:
+    """(sample_first, sample_stride, sample_count) for the fused accumulation, where the root also sums every rank's
+    partial sums and encodes the frame: it traces fewer samples, so that all ranks finish a frame together.
+
+    `root_extra_spp` is the root's extra work per frame expressed in samples per pixel (summation + resolve take about as
+    long as tracing two samples of the bench frame).  Ranks take CONTIGUOUS sample ranges (stride 1): the root
+    round((S - (N-1) e) / N) samples, the others share the rest as evenly as possible.  Every sample is traced exactly
+    once, so the reduced image is the same bit pattern as for any other partition."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world of {world}")
+    if world == 1:
+        return 0, 1, total_spp
+    c_root = int(round((total_spp - (world - 1) * root_extra_spp) / world))
+    c_root = max(0, min(total_spp, c_root))
+    rest, others = total_spp - c_root, world - 1
+    counts = []
+    k = 0
+    for r in range(world):
+        if r == root:
+            counts.append(c_root)
+        else:
+            counts.append(rest // others + (1 if k < rest % others else 0))
+            k += 1
+    first = sum(counts[:rank])
+    return first, 1, counts[rank]
+
+
 def reduce_accum(accum, group=None):
     """Sum the (h, w, 3) int64 accumulation tensor over all ranks, in place; returns it."""
     import torch.distributed as dist
