@@ -4,7 +4,9 @@
 // A 1024^3 or 4096^3 volume cannot be a dense RGBA8 texture (the reference's own add_texture
 // overflows its u32 byte count at 1024^3, lib/memory.c:297).  Such volumes are generated on the
 // device from a procedural definition and stored as occupancy only:
-//   l1 bit per 8^3 brick  ->  table[brick] = pool slot  ->  16 words (512 bits) per non-empty brick.
+//   l1: two bits per 8^3 brick, a tiny distance field — 3: the brick has voxels or lies in the border, 2: a brick next to it
+//   does, 1: a brick two away does, 0: nothing within two bricks  ->  table[brick] = pool slot  ->  16 words (512 bits) per
+//   non-empty brick.
 // The brick grid carries a one-brick border on every side whose entries say "outside" (kSlotExit), so
 // the walk needs no coordinate compares: leaving the volume is found by the same lookup as entering
 // a brick.
@@ -15,7 +17,14 @@
 #pragma once
 
 static constexpr uint32_t kSlotEmpty = 0xFFFFFFFFu; // brick without voxels
-static constexpr uint32_t kSlotExit = 0xFFFFFFFEu;  // border brick: outside the volume
+static constexpr uint32_t kSlotFree = 0xFFFFFFFEu;  // brick without voxels whose 26 neighbours have none either (and are inside)
+static constexpr uint32_t kSlotFree2 = 0xFFFFFFFDu; // the same for all 124 bricks within two bricks: two bursts without a lookup
+static constexpr uint32_t kSlotExit = 0xFFFFFFFCu;  // border brick: outside the volume.  Anything below is a pool slot.
+
+// l1 holds two bits per padded brick
+__host__ __device__ __forceinline__ size_t l1_words(size_t padded_bricks) { return (padded_bricks + 15) / 16; }
+__device__ __forceinline__ uint32_t l1_pair(const uint32_t* __restrict__ l1, uint32_t bi) { return (__ldg(l1 + (bi >> 4)) >> ((bi & 15u) * 2u)) & 3u; }
+__device__ __forceinline__ void l1_set(uint32_t* __restrict__ l1, size_t bi, uint32_t bit) { atomicOr(l1 + (bi >> 4), (1u << bit) << ((bi & 15u) * 2u)); }
 
 // index of brick (x, y, z) in the padded grid (pbx, pby = brick counts + 2)
 __host__ __device__ __forceinline__ uint32_t brick_index(uint32_t pbx, uint32_t pby, uint32_t x, uint32_t y, uint32_t z) {
@@ -127,7 +136,7 @@ __global__ void brick_build_kernel(uint32_t kind, uint32_t seed, uint32_t w, uin
     for (uint32_t wi = 0; wi < 16; ++wi) pool[(size_t)slot * 16 + wi] = words[wi];
     const uint32_t pb = brick_index(bxn + 2, byn + 2, bx, by, bz);
     table[pb] = slot;
-    atomicOr(l1 + (pb >> 5), 1u << (pb & 31));
+    l1_set(l1, pb, 0);
 }
 
 // border of the padded brick grid: l1 bit set, table = kSlotExit.  One thread per padded brick.
@@ -137,8 +146,65 @@ __global__ void brick_border_kernel(uint32_t pbx, uint32_t pby, uint32_t pbz, ui
     const uint32_t x = (uint32_t)(i % pbx), y = (uint32_t)((i / pbx) % pby), z = (uint32_t)(i / ((size_t)pbx * pby));
     if (x == 0 || y == 0 || z == 0 || x == pbx - 1 || y == pby - 1 || z == pbz - 1) {
         table[i] = kSlotExit;
-        atomicOr(l1 + (i >> 5), 1u << (i & 31));
+        l1_set(l1, i, 0);
     }
+}
+
+// The distance field is built in three passes after every occupied / border brick has its bit 0.
+// 1. scatter: bit 1 of every brick in the 3x3x3 neighbourhood of a set brick (one thread per padded brick; only the few
+//    per cent that are set scatter);
+__global__ void brick_dilate_kernel(uint32_t pbx, uint32_t pby, uint32_t pbz, uint32_t* __restrict__ l1) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)pbx * pby * pbz) return;
+    if (!((l1[i >> 4] >> ((i & 15u) * 2u)) & 1u)) return;
+    const int x = (int)(i % pbx), y = (int)((i / pbx) % pby), z = (int)(i / ((size_t)pbx * pby));
+    for (int dz = -1; dz <= 1; ++dz)
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int nx = x + dx, ny = y + dy, nz = z + dz;
+                if (nx < 0 || ny < 0 || nz < 0 || nx >= (int)pbx || ny >= (int)pby || nz >= (int)pbz) continue;
+                l1_set(l1, ((size_t)nz * pby + ny) * pbx + nx, 1);
+            }
+}
+// 2. gather: a brick with neither bit is "two away" if one of its 26 neighbours has bit 1 (one bit per brick in `far2`);
+__global__ void brick_dilate2_kernel(uint32_t pbx, uint32_t pby, uint32_t pbz, const uint32_t* __restrict__ l1, uint32_t* __restrict__ far2) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)pbx * pby * pbz) return;
+    if ((l1[i >> 4] >> ((i & 15u) * 2u)) & 3u) return;
+    const int x = (int)(i % pbx), y = (int)((i / pbx) % pby), z = (int)(i / ((size_t)pbx * pby));
+    bool near = false;
+    for (int dz = -1; dz <= 1 && !near; ++dz)
+        for (int dy = -1; dy <= 1 && !near; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int nx = x + dx, ny = y + dy, nz = z + dz;
+                if (nx < 0 || ny < 0 || nz < 0 || nx >= (int)pbx || ny >= (int)pby || nz >= (int)pbz) continue;
+                const size_t j = ((size_t)nz * pby + ny) * pbx + nx;
+                if ((l1[j >> 4] >> ((j & 15u) * 2u)) & 2u) { near = true; break; }
+            }
+    if (near) atomicOr(far2 + (i >> 5), 1u << (i & 31));
+}
+// 3. re-encode, one thread per l1 word: (bit 0, bit 1, far2) -> 3 occupied, 2 next to one, 1 two away, 0 farther.
+__global__ void brick_encode_kernel(size_t words, uint32_t* __restrict__ l1, const uint32_t* __restrict__ far2) {
+    const size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= words) return;
+    const uint32_t v = l1[w], f = (far2[w >> 1] >> ((w & 1u) * 16u)) & 0xFFFFu;
+    uint32_t out = 0;
+    for (uint32_t k = 0; k < 16; ++k) {
+        const uint32_t p = (v >> (2 * k)) & 3u;
+        const uint32_t q = (p & 1u) ? 3u : ((p & 2u) ? 2u : ((f >> k) & 1u));
+        out |= q << (2 * k);
+    }
+    l1[w] = out;
+}
+
+// `scratch`: (padded bricks + 31) / 32 words, zeroed
+cudaError_t launch_brick_dilate(uint32_t pbx, uint32_t pby, uint32_t pbz, uint32_t* l1, uint32_t* scratch, cudaStream_t stream) {
+    const size_t n = (size_t)pbx * pby * pbz;
+    brick_dilate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(pbx, pby, pbz, l1);
+    brick_dilate2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(pbx, pby, pbz, l1, scratch);
+    const size_t words = l1_words(n);
+    brick_encode_kernel<<<(unsigned)((words + 255) / 256), 256, 0, stream>>>(words, l1, scratch);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_brick_border(uint32_t pbx, uint32_t pby, uint32_t pbz, uint32_t* l1, uint32_t* table, cudaStream_t stream) {
@@ -165,7 +231,7 @@ __global__ void brick_index_kernel(const uint32_t* __restrict__ coords, uint32_t
     if (x >= bx || y >= by || z >= bz) { atomicAdd(bad, 1u); return; }
     const uint32_t b = brick_index(bx + 2, by + 2, x, y, z);
     table[b] = i;
-    atomicOr(l1 + (b >> 5), 1u << (b & 31));
+    l1_set(l1, b, 0);
 }
 
 cudaError_t launch_brick_index(const uint32_t* coords, uint32_t n, uint32_t bx, uint32_t by, uint32_t bz, uint32_t* l1, uint32_t* table,
@@ -193,14 +259,18 @@ struct BrickWalk {
     uint32_t pa, pb;       // (a, b) before the last iteration
     uint32_t ix, iy, iz;   // packed per-axis increments
     uint32_t ref_a, ref_b;
+    uint32_t mask;         // kBrickMaskA: stop at the brick's faces; 0 (kSlotFree bricks): walk on, nothing is near
     uint32_t slot;
     uint32_t steps, last;
 };
+#ifndef VT_BRICK_PREFETCH
+#define VT_BRICK_PREFETCH 0 // (measured: 4 % slower on configs[3] and configs[4] — the l1 words are not what the lookups wait for)
+#endif
 #ifndef VT_MARCH_BURST
-#define VT_MARCH_BURST 4 // DDA iterations between brick lookups, coherent rays (primary / shadow); 3, 6, 8 measured slower
+#define VT_MARCH_BURST 8 // DDA iterations between brick lookups, coherent rays (primary / shadow); with kSlotFree bricks: 4: 1.99 ms, 6: 1.79, 8: 1.74 (configs[3])
 #endif
 #ifndef VT_RAY_BURST
-#define VT_RAY_BURST 6   // same, incoherent rays (trace_rays_kernel); 4 and 8 measured 5 % slower
+#define VT_RAY_BURST 8   // same, incoherent rays (trace_rays_kernel); with kSlotFree bricks: 6: 44.0 ms, 8: 42.2 (configs[4])
 #endif
 static constexpr uint32_t kBrickMaskA = 0xFFF8FFF8u; // brick part of both packed words
 
@@ -221,7 +291,7 @@ __device__ __noinline__ int brick_walk_slow(const uint32_t* __restrict__ l1, con
     int status = 2;
     while (steps < W + H + D && (uint32_t)vx < W && (uint32_t)vy < H && (uint32_t)vz < D) { // :74-75
         const uint32_t bi = brick_index(pbx, pby, (uint32_t)vx >> 3, (uint32_t)vy >> 3, (uint32_t)vz >> 3);
-        if ((__ldg(l1 + (bi >> 5)) >> (bi & 31)) & 1u) {
+        if (l1_pair(l1, bi) == 3u) {
             const uint32_t wv = __ldg(pool + ((size_t)__ldg(table + bi) << 4) + ((((uint32_t)vz & 7u) << 1) | (((uint32_t)vy & 7u) >> 2)));
             if ((wv >> (((uint32_t)vx & 7u) | (((uint32_t)vy & 3u) << 3))) & 1u) { status = 1; break; } // :78-80
         }
@@ -247,16 +317,18 @@ __device__ __noinline__ int brick_walk_slow(const uint32_t* __restrict__ l1, con
 // voxel.  0 = empty, keep walking; 1 = filled (:78-80); 2 = outside the volume (:75).
 __device__ __forceinline__ int brick_walk_lookup(const BrickVolume& bv, BrickWalk& k) {
     // ref is stored complemented (flip = ~0) while the current brick has voxels
-    const uint32_t flip = k.slot != kSlotEmpty ? 0xFFFFFFFFu : 0u;
-    if ((((k.a ^ k.ref_a ^ flip) | (k.b ^ k.ref_b ^ flip)) & kBrickMaskA) != 0u) { // entered another brick: one l1 bit, and the slot if it is set
+    const uint32_t flip = k.slot < kSlotExit ? 0xFFFFFFFFu : 0u;
+    if ((((k.a ^ k.ref_a ^ flip) | (k.b ^ k.ref_b ^ flip)) & kBrickMaskA) != 0u) { // entered another brick: its l1 pair, and the slot if it has voxels
         const uint32_t bi = ((k.b >> 3) * bv.by + (k.a >> 19)) * bv.bx + ((k.a >> 3) & 0x1FFFu);
-        const uint32_t bit = (__ldg(bv.l1 + (bi >> 5)) >> (bi & 31)) & 1u;
-        k.slot = bit ? __ldg(bv.table + bi) : kSlotEmpty;
-        k.ref_a = bit ? ~k.a : k.a;
-        k.ref_b = bit ? ~k.b : k.b;
+        const uint32_t pr = l1_pair(bv.l1, bi);
+        const bool occ = pr == 3u;
+        k.slot = occ ? __ldg(bv.table + bi) : (kSlotFree2 + pr); // 0 -> kSlotFree2, 1 -> kSlotFree, 2 -> kSlotEmpty
+        k.ref_a = occ ? ~k.a : k.a;
+        k.ref_b = occ ? ~k.b : k.b;
+        k.mask = pr >= 2u ? kBrickMaskA : 0u;
         if (k.slot == kSlotExit) return 2;
     }
-    if (k.slot != kSlotEmpty) {
+    if (k.slot < kSlotExit) {
         const uint32_t wv = __ldg(bv.pool + ((size_t)k.slot << 4) + (((k.b & 7u) << 1) | ((k.a >> 18) & 1u)));
         if ((wv >> ((k.a & 7u) | (((k.a >> 16) & 3u) << 3))) & 1u) {
             // axes advanced by the last iteration (:83), from the voxel it started at
@@ -312,6 +384,7 @@ __device__ __forceinline__ int brick_walk_begin(const BrickVolume& bv, uint32_t 
     k.sx = r.side[0]; k.sy = r.side[1]; k.sz = r.side[2];
     k.pa = k.a; k.pb = k.b;
     k.slot = kSlotEmpty;
+    k.mask = kBrickMaskA;
     k.ref_a = ~k.a; k.ref_b = ~k.b; // no current brick: the first test looks one up
     if (status == 0) status = brick_walk_lookup(bv, k);
     return status;
@@ -326,7 +399,8 @@ __device__ __forceinline__ int brick_walk_begin(const BrickVolume& bv, uint32_t 
 // still inside the brick it knows to be empty"; a lane that has left idles through the rest of the
 // burst, predicated off, instead of jumping ahead to a lookup of its own.
 //   %0-2 side, %3-4 packed voxel, %5-6 voxel before the iteration, %7 steps, %8 left (out),
-//   %9-11 delta, %12-14 packed increments, %15-16 reference brick
+//   %9-11 delta, %12-14 packed increments, %15-16 reference brick, %17 brick mask (0 in a kSlotFree brick: the lane does not
+//   stop at its faces — within the 8 iterations of a burst it cannot get past the empty neighbours)
 #define VT_BRICK_STEP_PTX                        \
     "min.f32 m, %0, %1;\n"                       \
     "min.f32 m, m, %2;\n"                        \
@@ -345,7 +419,7 @@ __device__ __forceinline__ int brick_walk_begin(const BrickVolume& bv, uint32_t 
     "xor.b32 t, %3, %15;\n"                      \
     "xor.b32 u, %4, %16;\n"                      \
     "or.b32 t, t, u;\n"                          \
-    "and.b32 t, t, 0xFFF8FFF8;\n"                \
+    "and.b32 t, t, %17;\n"                       \
     "setp.eq.and.u32 g, t, 0, g;\n"
 #define VT_BRICK_BURST_ASM(STEPS)                                                                                         \
     asm volatile("{\n"                                                                                                    \
@@ -355,11 +429,11 @@ __device__ __forceinline__ int brick_walk_begin(const BrickVolume& bv, uint32_t 
                  "setp.eq.u32 g, 0, 0;\n" STEPS "selp.u32 %8, 0, 1, g;\n"                                                 \
                  "}\n"                                                                                                    \
                  : "+f"(k.sx), "+f"(k.sy), "+f"(k.sz), "+r"(k.a), "+r"(k.b), "+r"(k.pa), "+r"(k.pb), "+r"(k.steps), "=r"(left) \
-                 : "f"(r.delta[0]), "f"(r.delta[1]), "f"(r.delta[2]), "r"(k.ix), "r"(k.iy), "r"(k.iz), "r"(k.ref_a), "r"(k.ref_b))
+                 : "f"(r.delta[0]), "f"(r.delta[1]), "f"(r.delta[2]), "r"(k.ix), "r"(k.iy), "r"(k.iz), "r"(k.ref_a), "r"(k.ref_b), "r"(k.mask))
 
 template <int kBurst>
 __device__ __forceinline__ int brick_walk_burst(const BrickVolume& bv, const Dda& r, BrickWalk& k) {
-    static_assert(kBurst == 3 || kBurst == 4 || kBurst == 6 || kBurst == 8, "burst lengths with a PTX body");
+    static_assert(kBurst == 3 || kBurst == 4 || kBurst == 6 || kBurst == 8, "burst lengths with a PTX body (at most 8: see kSlotFree)");
     // Per iteration (trace.frag:83-86), no NaN: side <= min(other two) is side == min(all three);
     // vec3(mask) * delta is a predicated add; bits 16-18 of b are always 0, so one mask serves both words:
     //     m = min(sx, sy, sz); m0 = go && sx == m; ...; if (go) { pa = a; pb = b; }
@@ -375,6 +449,12 @@ __device__ __forceinline__ int brick_walk_burst(const BrickVolume& bv, const Dda
     if (kBurst == 8)
         VT_BRICK_BURST_ASM(VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX
                                VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX);
+    // a lane that walked on through the faces of a kSlotFree brick looks up where it is now — after its second burst if
+    // nothing lies within two bricks of where it started (kSlotFree2)
+    if ((((k.a ^ k.ref_a) | (k.b ^ k.ref_b)) & kBrickMaskA & ~k.mask) != 0u) {
+        if (k.slot == kSlotFree2) k.slot = kSlotFree;
+        else left = 1u;
+    }
     return left ? brick_walk_lookup(bv, k) : 0;
 }
 

@@ -34,7 +34,8 @@ struct VolumeDesc {
 
 // Large procedural volumes (extension; §8f rank 2): occupancy only, as a
 // two-level sparse structure; colours are a function of the voxel position.
-//   l1    : one bit per 8^3 brick (set = the brick has at least one filled voxel, or lies in the border)
+//   l1    : two bits per 8^3 brick: 3 = the brick has at least one filled voxel, or lies in the border; 2 = a neighbour does;
+//           1 = a brick two away does; 0 = nothing within two bricks (1 / 0: the walk needs no lookup for one / two bursts)
 //   table : per brick, its slot in `pool` (only meaningful where the l1 bit is set); 0xFFFFFFFE in the border
 // The brick grid is stored padded by one brick on every side; the border says "outside the volume".
 //   pool  : 16 words per non-empty brick; voxel (x,y,z) of a brick is bit (x | (y&3) << 3) of
@@ -179,6 +180,8 @@ cudaError_t launch_brick_build(uint32_t kind, uint32_t seed, uint32_t w, uint32_
                                uint32_t* table, uint32_t* pool, uint32_t pool_capacity, uint32_t* counter, cudaStream_t stream);
 // caller-supplied bricks: coords (n x 3) -> table / l1 entries (the masks are already the pool)
 cudaError_t launch_brick_border(uint32_t pbx, uint32_t pby, uint32_t pbz, uint32_t* l1, uint32_t* table, cudaStream_t stream);
+// after every occupied / border brick has its bit 0: bit 1 of the 3x3x3 neighbourhoods
+cudaError_t launch_brick_dilate(uint32_t pbx, uint32_t pby, uint32_t pbz, uint32_t* l1, uint32_t* scratch, cudaStream_t stream);
 cudaError_t launch_brick_index(const uint32_t* coords, uint32_t n, uint32_t bx, uint32_t by, uint32_t bz, uint32_t* l1, uint32_t* table,
                                uint32_t* bad, cudaStream_t stream);
 // incoherent-ray mode: rays [first, first + n) through instance 0's volume

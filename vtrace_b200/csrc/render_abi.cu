@@ -809,9 +809,9 @@ extern "C" int32_t vt_add_volume_procedural(uint32_t kind, uint32_t width, uint3
     // the brick grid is stored with a one-brick border that marks "outside" (kernels.h, BrickVolume)
     const uint32_t pbx = (width >> 3) + 2, pby = (height >> 3) + 2, pbz = (depth >> 3) + 2;
     const size_t padded = (size_t)pbx * pby * pbz;
-    CK(cudaMalloc(&a.l1, ((padded + 31) / 32) * 4));
+    CK(cudaMalloc(&a.l1, ((padded + 15) / 16) * 4)); // two bits per brick
     CK(cudaMalloc(&a.table, padded * 4));
-    CK(cudaMemsetAsync(a.l1, 0, ((padded + 31) / 32) * 4, g.stream));
+    CK(cudaMemsetAsync(a.l1, 0, ((padded + 15) / 16) * 4, g.stream));
     CK(launch_brick_border(pbx, pby, pbz, a.l1, a.table, g.stream));
     g.stats.launches += 1;
     // pass 1 counts the non-empty bricks, pass 2 fills the pool
@@ -822,7 +822,15 @@ extern "C" int32_t vt_add_volume_procedural(uint32_t kind, uint32_t width, uint3
     CK(cudaMalloc(&a.pool, (size_t)(n ? n : 1) * 64));
     CK(cudaMemsetAsync(d_counter, 0, 4, g.stream));
     CK(launch_brick_build(kind, seed, width, height, depth, a.heights, a.l1, a.table, a.pool, n, d_counter, g.stream));
-    g.stats.launches += 2;
+    {
+        uint32_t* scratch = nullptr;
+        CK(cudaMalloc(&scratch, ((padded + 31) / 32) * 4));
+        CK(cudaMemsetAsync(scratch, 0, ((padded + 31) / 32) * 4, g.stream));
+        CK(launch_brick_dilate(pbx, pby, pbz, a.l1, scratch, g.stream));
+        CK(cudaStreamSynchronize(g.stream));
+        cudaFree(scratch);
+    }
+    g.stats.launches += 5;
     BrickVolume bv{};
     bv.l1 = a.l1; bv.table = a.table; bv.pool = a.pool; bv.heights = a.heights; bv.colors = nullptr;
     bv.kind = kind; bv.seed = seed;
@@ -871,13 +879,13 @@ extern "C" int32_t vt_add_volume_bricks(const uint32_t* brick_coords, const uint
     uint32_t bad = 0;
     const uint32_t pbx = (width >> 3) + 2, pby = (height >> 3) + 2, pbz = (depth >> 3) + 2;
     const size_t padded = (size_t)pbx * pby * pbz;
-    CK(cudaMalloc(&a.l1, ((padded + 31) / 32) * 4));
+    CK(cudaMalloc(&a.l1, ((padded + 15) / 16) * 4)); // two bits per brick
     CK(cudaMalloc(&a.table, padded * 4));
     CK(cudaMalloc(&a.pool, n1 * 64));
     CK(cudaMalloc(&a.colors, n1 * 4));
     CK(cudaMalloc(&d_coords, n1 * 12));
     CK(cudaMalloc(&d_bad, 4));
-    CK(cudaMemsetAsync(a.l1, 0, ((padded + 31) / 32) * 4, g.stream));
+    CK(cudaMemsetAsync(a.l1, 0, ((padded + 15) / 16) * 4, g.stream));
     CK(launch_brick_border(pbx, pby, pbz, a.l1, a.table, g.stream));
     CK(cudaMemsetAsync(d_bad, 0, 4, g.stream));
     // the inputs are only borrowed for the call (like add_texture's): synchronous copies
@@ -885,6 +893,14 @@ extern "C" int32_t vt_add_volume_bricks(const uint32_t* brick_coords, const uint
     CK(cudaMemcpy(a.colors, colors, n_bricks * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_coords, brick_coords, n_bricks * 12, cudaMemcpyHostToDevice));
     CK(launch_brick_index(d_coords, (uint32_t)n_bricks, width >> 3, height >> 3, depth >> 3, a.l1, a.table, d_bad, g.stream));
+    {
+        uint32_t* scratch = nullptr;
+        CK(cudaMalloc(&scratch, ((padded + 31) / 32) * 4));
+        CK(cudaMemsetAsync(scratch, 0, ((padded + 31) / 32) * 4, g.stream));
+        CK(launch_brick_dilate(pbx, pby, pbz, a.l1, scratch, g.stream));
+        CK(cudaStreamSynchronize(g.stream));
+        cudaFree(scratch);
+    }
     CK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
     cudaFree(d_coords);
