@@ -5,7 +5,8 @@
 // overflows its u32 byte count at 1024^3, lib/memory.c:297).  Such volumes are generated on the
 // device from a procedural definition and stored as occupancy only:
 //   l1: two bits per 8^3 brick, a tiny distance field — 3: the brick has voxels or lies in the border, 2: a brick next to it
-//   does, 1: a brick two away does, 0: nothing within two bricks  ->  table[brick] = pool slot  ->  16 words (512 bits) per
+//   does, 1: a brick two away does, 0: nothing within two bricks (the walk treats 1 and 0 alike: a second burst without a
+//   lookup for 0 was measured and bought nothing)  ->  table[brick] = pool slot  ->  16 words (512 bits) per
 //   non-empty brick.
 // The brick grid carries a one-brick border on every side whose entries say "outside" (kSlotExit), so
 // the walk needs no coordinate compares: leaving the volume is found by the same lookup as entering
@@ -18,7 +19,6 @@
 
 static constexpr uint32_t kSlotEmpty = 0xFFFFFFFFu; // brick without voxels
 static constexpr uint32_t kSlotFree = 0xFFFFFFFEu;  // brick without voxels whose 26 neighbours have none either (and are inside)
-static constexpr uint32_t kSlotFree2 = 0xFFFFFFFDu; // the same for all 124 bricks within two bricks: two bursts without a lookup
 static constexpr uint32_t kSlotExit = 0xFFFFFFFCu;  // border brick: outside the volume.  Anything below is a pool slot.
 
 // l1 holds two bits per padded brick
@@ -242,37 +242,37 @@ cudaError_t launch_brick_index(const uint32_t* coords, uint32_t n, uint32_t bx, 
 
 // The reference's DDA (trace.frag:63-89) over a brick volume, as a resumable walk: same state, same
 // float operations in the same order as dda_init / dda_step / dda_slow_impl — only the occupancy
-// test differs.  brick_walk_step() runs ONE loop iteration; the persistent-lane ray kernel interleaves
+// test differs.  brick_walk_burst() runs up to 8 loop iterations; the persistent-lane ray kernel interleaves
 // the walks of 32 lanes and refills lanes whose ray ended.
 //
-// Fast path (no NaN/inf in side/delta): the voxel is kept packed in two words, a = (x+8) | (y+8) << 16
-// and b = z+8 (the bias of one brick keeps the border positive), so a step is three predicated adds
-// and "still in the same empty brick?" is three LOP3s against the reference pair (ref_a, ref_b).  Only
-// when that test fails is anything looked up: the l1 bit of the new brick, its slot if the bit is
-// set (kSlotExit in the border = the ray left the volume), one pool word per step inside a brick
-// that has voxels.  For such a brick the reference pair is stored complemented, which makes the test
-// fail on every step without a second compare.  Every fast-path iteration advances >= 1 voxel, so the
-// steps < W+H+D bound of :74 cannot bind before the ray is outside.
+// Fast path (no NaN/inf in side/delta): the voxel is kept as a brick (padded brick coordinates, `cell`) plus its
+// position INSIDE the brick, three 5-bit fields of one word (`loc` = fx | fy << 8 | fz << 16, field = local
+// coordinate + 8).  A step is three predicated adds on `loc`; a field that leaves 8..15 has crossed a face of the
+// brick, and bit 3 of a field is set exactly while it is inside, so "did this lane leave its brick?" is ONE
+// instruction (LOP3 with predicate output: ~loc & stop != 0) instead of compares on absolute coordinates.
+// `stop` = 0x080808 in an empty brick; 0x202020 (bits that are never set: the test always fires) in a brick with
+// voxels, where every step needs its pool word; 0 in a brick whose neighbourhood is empty too (kSlotFree): such a
+// lane walks a whole burst through brick faces — the fields then range over 0..23 and say how many bricks it moved.
+// Only when the test fires is anything looked up: the brick's l1 pair, its slot if it has voxels (kSlotExit in the
+// border = the ray left the volume), one pool word per step inside such a brick.  Every fast-path iteration advances
+// >= 1 voxel, so the steps < W+H+D bound of :74 cannot bind before the ray is outside.
 struct BrickWalk {
     float sx, sy, sz;
-    uint32_t a, b;
-    uint32_t pa, pb;       // (a, b) before the last iteration
-    uint32_t ix, iy, iz;   // packed per-axis increments
-    uint32_t ref_a, ref_b;
-    uint32_t mask;         // kBrickMaskA: stop at the brick's faces; 0 (kSlotFree bricks): walk on, nothing is near
+    uint32_t loc;          // position inside the brick: (x & 7) + 8 | ((y & 7) + 8) << 8 | ((z & 7) + 8) << 16
+    uint32_t ploc;         // loc before the last iteration | iterations run by the current burst << 24
+    uint32_t cell;         // padded brick coordinates cx | cy << 10 | cz << 20
+    uint32_t ix, iy, iz;   // per-axis increments of loc: +-1, +-1 << 8, +-1 << 16
+    uint32_t stop;         // see above
     uint32_t slot;
     uint32_t steps, last;
 };
-#ifndef VT_BRICK_PREFETCH
-#define VT_BRICK_PREFETCH 0 // (measured: 4 % slower on configs[3] and configs[4] — the l1 words are not what the lookups wait for)
-#endif
+static constexpr uint32_t kLocInside = 0x00080808u, kLocAlways = 0x00202020u, kLocFields = 0x001F1F1Fu, kLocLow = 0x00070707u;
 #ifndef VT_MARCH_BURST
-#define VT_MARCH_BURST 8 // DDA iterations between brick lookups, coherent rays (primary / shadow); with kSlotFree bricks: 4: 1.99 ms, 6: 1.79, 8: 1.74 (configs[3])
+#define VT_MARCH_BURST 8 // DDA iterations between brick lookups, coherent rays (primary / shadow); 4: 1.99 ms, 6: 1.79, 8: 1.74 (configs[3])
 #endif
 #ifndef VT_RAY_BURST
-#define VT_RAY_BURST 8   // same, incoherent rays (trace_rays_kernel); with kSlotFree bricks: 6: 44.0 ms, 8: 42.2 (configs[4])
+#define VT_RAY_BURST 8   // same, incoherent rays (trace_rays_kernel); 6: 44.0 ms, 8: 42.2 (configs[4])
 #endif
-static constexpr uint32_t kBrickMaskA = 0xFFF8FFF8u; // brick part of both packed words
 
 // literal transcription of the loop for rays with a zero direction component (0 * inf = NaN, :84), run to
 // the end.  Out of line and fed by value, so the callers' ray state stays in registers.
@@ -316,24 +316,22 @@ __device__ __noinline__ int brick_walk_slow(const uint32_t* __restrict__ l1, con
 // The walk left the brick it knew to be empty (or stands in one that has voxels): look at the current
 // voxel.  0 = empty, keep walking; 1 = filled (:78-80); 2 = outside the volume (:75).
 __device__ __forceinline__ int brick_walk_lookup(const BrickVolume& bv, BrickWalk& k) {
-    // ref is stored complemented (flip = ~0) while the current brick has voxels
-    const uint32_t flip = k.slot < kSlotExit ? 0xFFFFFFFFu : 0u;
-    if ((((k.a ^ k.ref_a ^ flip) | (k.b ^ k.ref_b ^ flip)) & kBrickMaskA) != 0u) { // entered another brick: its l1 pair, and the slot if it has voxels
-        const uint32_t bi = ((k.b >> 3) * bv.by + (k.a >> 19)) * bv.bx + ((k.a >> 3) & 0x1FFFu);
+    const uint32_t moved = (k.loc ^ k.ploc) & kLocFields; // fields the last iteration changed (:83), before loc is re-based
+    if ((~k.loc & kLocInside) != 0u) { // crossed at least one face: field >> 3 = 0 / 1 / 2 -> one brick down / same / up
+        k.cell = k.cell + ((k.loc >> 3) & 0x3u) + (((k.loc >> 11) & 0x3u) << 10) + (((k.loc >> 19) & 0x3u) << 20) - 0x00100401u;
+        k.loc = (k.loc & kLocLow) | kLocInside;
+        const uint32_t bi = ((k.cell >> 20) * bv.by + ((k.cell >> 10) & 0x3FFu)) * bv.bx + (k.cell & 0x3FFu);
         const uint32_t pr = l1_pair(bv.l1, bi);
         const bool occ = pr == 3u;
-        k.slot = occ ? __ldg(bv.table + bi) : (kSlotFree2 + pr); // 0 -> kSlotFree2, 1 -> kSlotFree, 2 -> kSlotEmpty
-        k.ref_a = occ ? ~k.a : k.a;
-        k.ref_b = occ ? ~k.b : k.b;
-        k.mask = pr >= 2u ? kBrickMaskA : 0u;
+        k.slot = occ ? __ldg(bv.table + bi) : (pr == 2u ? kSlotEmpty : kSlotFree);
+        k.stop = occ ? kLocAlways : (pr == 2u ? kLocInside : 0u);
         if (k.slot == kSlotExit) return 2;
     }
     if (k.slot < kSlotExit) {
-        const uint32_t wv = __ldg(bv.pool + ((size_t)k.slot << 4) + (((k.b & 7u) << 1) | ((k.a >> 18) & 1u)));
-        if ((wv >> ((k.a & 7u) | (((k.a >> 16) & 3u) << 3))) & 1u) {
-            // axes advanced by the last iteration (:83), from the voxel it started at
-            const uint32_t da = k.a ^ k.pa;
-            k.last = ((da & 0xFFFFu) ? 1u : 0u) | ((da >> 16) ? 2u : 0u) | (k.b != k.pb ? 4u : 0u);
+        const uint32_t lx = k.loc & 7u, ly = (k.loc >> 8) & 7u, lz = (k.loc >> 16) & 7u;
+        const uint32_t wv = __ldg(bv.pool + ((size_t)k.slot << 4) + ((lz << 1) | (ly >> 2)));
+        if ((wv >> (lx | ((ly & 3u) << 3))) & 1u) {
+            k.last = ((moved & 0x1Fu) ? 1u : 0u) | ((moved & 0x1F00u) ? 2u : 0u) | ((moved & 0x1F0000u) ? 4u : 0u);
             return 1;
         }
     }
@@ -378,88 +376,85 @@ __device__ __forceinline__ int brick_walk_begin(const BrickVolume& bv, uint32_t 
         r.side[0] = io.side[0]; r.side[1] = io.side[1]; r.side[2] = io.side[2];
         k.steps = io.steps; k.last = io.last;
     }
-    k.a = (uint32_t)(r.v[0] + 8) | ((uint32_t)(r.v[1] + 8) << 16);
-    k.b = (uint32_t)(r.v[2] + 8);
-    k.ix = (uint32_t)r.step[0]; k.iy = (uint32_t)r.step[1] << 16; k.iz = (uint32_t)r.step[2];
+    // padded brick = (v + 8) >> 3, position inside = (v + 8) & 7
+    const uint32_t ux = (uint32_t)(r.v[0] + 8), uy = (uint32_t)(r.v[1] + 8), uz = (uint32_t)(r.v[2] + 8);
+    k.cell = (ux >> 3) | ((uy >> 3) << 10) | ((uz >> 3) << 20);
+    k.loc = ((ux & 7u) | ((uy & 7u) << 8) | ((uz & 7u) << 16)) | kLocInside;
+    k.ix = (uint32_t)r.step[0]; k.iy = (uint32_t)r.step[1] << 8; k.iz = (uint32_t)r.step[2] << 16;
     k.sx = r.side[0]; k.sy = r.side[1]; k.sz = r.side[2];
-    k.pa = k.a; k.pb = k.b;
-    k.slot = kSlotEmpty;
-    k.mask = kBrickMaskA;
-    k.ref_a = ~k.a; k.ref_b = ~k.b; // no current brick: the first test looks one up
-    if (status == 0) status = brick_walk_lookup(bv, k);
+    k.ploc = k.loc;
+    // no current brick yet: look the start brick up (the same code as after crossing a face, with no face crossed)
+    if (status == 0) {
+        const uint32_t bi = ((k.cell >> 20) * bv.by + ((k.cell >> 10) & 0x3FFu)) * bv.bx + (k.cell & 0x3FFu);
+        const uint32_t pr = l1_pair(bv.l1, bi);
+        const bool occ = pr == 3u;
+        k.slot = occ ? __ldg(bv.table + bi) : (pr == 2u ? kSlotEmpty : kSlotFree);
+        k.stop = occ ? kLocAlways : (pr == 2u ? kLocInside : 0u);
+        status = k.slot == kSlotExit ? 2 : brick_walk_lookup(bv, k);
+    } else {
+        k.slot = kSlotEmpty;
+        k.stop = kLocInside;
+    }
     return status;
 }
 
-// Up to kBurst iterations of the while loop of trace.frag:75-87 through the current empty brick, then
-// ONE lookup if the walk left it.  The lanes of a warp run the burst together and meet again for the
-// lookup, so its loads are issued by many lanes at once instead of by whichever lane happens to cross
-// a brick face in a given iteration.
-// One iteration in PTX (the selection the compiler makes from the C++ below it costs five more
-// instructions per iteration: selects + 3-input adds instead of predicated adds).  g = "this lane is
-// still inside the brick it knows to be empty"; a lane that has left idles through the rest of the
-// burst, predicated off, instead of jumping ahead to a lookup of its own.
-//   %0-2 side, %3-4 packed voxel, %5-6 voxel before the iteration, %7 steps, %8 left (out),
-//   %9-11 delta, %12-14 packed increments, %15-16 reference brick, %17 brick mask (0 in a kSlotFree brick: the lane does not
-//   stop at its faces — within the 8 iterations of a burst it cannot get past the empty neighbours)
-#define VT_BRICK_STEP_PTX                        \
+// Up to kBurst iterations of the while loop of trace.frag:75-87 through the current brick, then ONE lookup if
+// the walk left it.  The lanes of a warp run the burst together and meet again for the lookup, so its loads are
+// issued by many lanes at once instead of by whichever lane happens to cross a brick face in a given iteration.
+// One iteration in PTX: 12 SASS instructions (FMNMX3, 3 FSETP, the record of the previous position, 3 + 3
+// predicated adds, the face test).  lf = "this lane has left its brick"; such a lane idles through the rest of
+// the burst, predicated off, instead of jumping ahead to a lookup of its own.
+//   %0-2 side, %3 loc, %4 ploc (written with the iteration's number in bits 24+), %5 left (out),
+//   %6-8 delta, %9-11 increments of loc, %12 stop bits
+#define VT_BRICK_STEP_PTX(CODE)                  \
     "min.f32 m, %0, %1;\n"                       \
     "min.f32 m, m, %2;\n"                        \
-    "setp.eq.and.f32 px, %0, m, g;\n"            \
-    "setp.eq.and.f32 py, %1, m, g;\n"            \
-    "setp.eq.and.f32 pz, %2, m, g;\n"            \
-    "@g mov.u32 %5, %3;\n"                       \
-    "@g mov.u32 %6, %4;\n"                       \
-    "@px add.rn.f32 %0, %0, %9;\n"               \
-    "@py add.rn.f32 %1, %1, %10;\n"              \
-    "@pz add.rn.f32 %2, %2, %11;\n"              \
-    "@px add.u32 %3, %3, %12;\n"                 \
-    "@py add.u32 %3, %3, %13;\n"                 \
-    "@pz add.u32 %4, %4, %14;\n"                 \
-    "@g add.u32 %7, %7, 1;\n"                    \
-    "xor.b32 t, %3, %15;\n"                      \
-    "xor.b32 u, %4, %16;\n"                      \
-    "or.b32 t, t, u;\n"                          \
-    "and.b32 t, t, %17;\n"                       \
-    "setp.eq.and.u32 g, t, 0, g;\n"
+    "setp.eq.and.f32 px, %0, m, !lf;\n"          \
+    "setp.eq.and.f32 py, %1, m, !lf;\n"          \
+    "setp.eq.and.f32 pz, %2, m, !lf;\n"          \
+    "@!lf add.u32 %4, %3, " CODE ";\n"           \
+    "@px add.rn.f32 %0, %0, %6;\n"               \
+    "@py add.rn.f32 %1, %1, %7;\n"               \
+    "@pz add.rn.f32 %2, %2, %8;\n"               \
+    "@px add.u32 %3, %3, %9;\n"                  \
+    "@py add.u32 %3, %3, %10;\n"                 \
+    "@pz add.u32 %3, %3, %11;\n"                 \
+    "lop3.or.b32 t|lf, %3, %12, 0, 0x0C, lf;\n"  /* ~loc & stop != 0: a field left 8..15 */
 #define VT_BRICK_BURST_ASM(STEPS)                                                                                         \
     asm volatile("{\n"                                                                                                    \
-                 ".reg .pred g, px, py, pz;\n"                                                                            \
+                 ".reg .pred lf, px, py, pz;\n"                                                                           \
                  ".reg .f32 m;\n"                                                                                         \
-                 ".reg .u32 t, u;\n"                                                                                      \
-                 "setp.eq.u32 g, 0, 0;\n" STEPS "selp.u32 %8, 0, 1, g;\n"                                                 \
+                 ".reg .u32 t;\n"                                                                                         \
+                 "setp.ne.u32 lf, 0, 0;\n" STEPS "selp.u32 %5, 1, 0, lf;\n"                                              \
                  "}\n"                                                                                                    \
-                 : "+f"(k.sx), "+f"(k.sy), "+f"(k.sz), "+r"(k.a), "+r"(k.b), "+r"(k.pa), "+r"(k.pb), "+r"(k.steps), "=r"(left) \
-                 : "f"(r.delta[0]), "f"(r.delta[1]), "f"(r.delta[2]), "r"(k.ix), "r"(k.iy), "r"(k.iz), "r"(k.ref_a), "r"(k.ref_b), "r"(k.mask))
+                 : "+f"(k.sx), "+f"(k.sy), "+f"(k.sz), "+r"(k.loc), "+r"(k.ploc), "=r"(left)                                \
+                 : "f"(r.delta[0]), "f"(r.delta[1]), "f"(r.delta[2]), "r"(k.ix), "r"(k.iy), "r"(k.iz), "r"(k.stop))
+#define VT_BRICK_STEPS_4 VT_BRICK_STEP_PTX("0x01000000") VT_BRICK_STEP_PTX("0x02000000") VT_BRICK_STEP_PTX("0x03000000") VT_BRICK_STEP_PTX("0x04000000")
+#define VT_BRICK_STEPS_6 VT_BRICK_STEPS_4 VT_BRICK_STEP_PTX("0x05000000") VT_BRICK_STEP_PTX("0x06000000")
+#define VT_BRICK_STEPS_8 VT_BRICK_STEPS_6 VT_BRICK_STEP_PTX("0x07000000") VT_BRICK_STEP_PTX("0x08000000")
 
 template <int kBurst>
 __device__ __forceinline__ int brick_walk_burst(const BrickVolume& bv, const Dda& r, BrickWalk& k) {
-    static_assert(kBurst == 3 || kBurst == 4 || kBurst == 6 || kBurst == 8, "burst lengths with a PTX body (at most 8: see kSlotFree)");
-    // Per iteration (trace.frag:83-86), no NaN: side <= min(other two) is side == min(all three);
-    // vec3(mask) * delta is a predicated add; bits 16-18 of b are always 0, so one mask serves both words:
-    //     m = min(sx, sy, sz); m0 = go && sx == m; ...; if (go) { pa = a; pb = b; }
-    //     if (m0) { sx += delta[0]; a += ix; } ...; steps += go;
-    //     go = go && (((a ^ ref_a) | (b ^ ref_b)) & kBrickMaskA) == 0;
-    // The asm is volatile and `left` comes out of it, so the lookup is reached from ONE branch by all
+    static_assert(kBurst == 4 || kBurst == 6 || kBurst == 8, "burst lengths with a PTX body (at most 8: see kSlotFree)");
+    // Per iteration (trace.frag:83-86), no NaN: side <= min(other two) is side == min(all three); vec3(mask) * delta is
+    // a predicated add.  The asm is volatile and `left` comes out of it, so the lookup is reached from ONE branch by all
     // lanes that need it together.
     uint32_t left;
-    if (kBurst == 3) VT_BRICK_BURST_ASM(VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX);
-    if (kBurst == 4) VT_BRICK_BURST_ASM(VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX);
-    if (kBurst == 6)
-        VT_BRICK_BURST_ASM(VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX);
-    if (kBurst == 8)
-        VT_BRICK_BURST_ASM(VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX
-                               VT_BRICK_STEP_PTX VT_BRICK_STEP_PTX);
-    // a lane that walked on through the faces of a kSlotFree brick looks up where it is now — after its second burst if
-    // nothing lies within two bricks of where it started (kSlotFree2)
-    if ((((k.a ^ k.ref_a) | (k.b ^ k.ref_b)) & kBrickMaskA & ~k.mask) != 0u) {
-        if (k.slot == kSlotFree2) k.slot = kSlotFree;
-        else left = 1u;
-    }
+    if (kBurst == 4) VT_BRICK_BURST_ASM(VT_BRICK_STEPS_4);
+    if (kBurst == 6) VT_BRICK_BURST_ASM(VT_BRICK_STEPS_6);
+    if (kBurst == 8) VT_BRICK_BURST_ASM(VT_BRICK_STEPS_8);
+    k.steps += k.ploc >> 24; // :86, the iterations this burst ran
+    k.ploc &= 0x00FFFFFFu;
+    // a lane that walked on through the faces of a kSlotFree brick looks up where it is now (branch-free: every lane
+    // that needs the lookup reaches it together)
+    left |= (k.stop == 0u ? 1u : 0u) & ((~k.loc & kLocInside) != 0u ? 1u : 0u);
     return left ? brick_walk_lookup(bv, k) : 0;
 }
 
 __device__ __forceinline__ void brick_walk_finish(const BrickWalk& k, bool hit, Dda& r) {
-    r.v[0] = (int32_t)(k.a & 0xFFFFu) - 8; r.v[1] = (int32_t)(k.a >> 16) - 8; r.v[2] = (int32_t)k.b - 8;
+    r.v[0] = (int32_t)(((k.cell & 0x3FFu) << 3) + (k.loc & 7u)) - 8;
+    r.v[1] = (int32_t)((((k.cell >> 10) & 0x3FFu) << 3) + ((k.loc >> 8) & 7u)) - 8;
+    r.v[2] = (int32_t)(((k.cell >> 20) << 3) + ((k.loc >> 16) & 7u)) - 8;
     r.side[0] = k.sx; r.side[1] = k.sy; r.side[2] = k.sz;
     r.steps = k.steps;
     r.last_mask = k.last;

@@ -945,7 +945,7 @@ __global__ void __launch_bounds__(kBlockThreads) trace_rays_kernel(const __grid_
         r.hit = false; r.steps = 0; r.last_mask = 0; r.len = 1.0f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) { r.v[c] = 0; r.step[c] = 0; r.side[c] = r.delta[c] = r.dir[c] = r.pos[c] = 0.0f; }
-        k.a = k.b = k.pa = k.pb = k.ix = k.iy = k.iz = 0; k.sx = k.sy = k.sz = 0.0f; k.steps = k.last = 0; k.ref_a = k.ref_b = 0; k.mask = kBrickMaskA; k.slot = kSlotEmpty;
+        k.loc = k.ploc = kLocInside; k.cell = 0; k.ix = k.iy = k.iz = 0; k.sx = k.sy = k.sz = 0.0f; k.steps = k.last = 0; k.stop = kLocInside; k.slot = kSlotEmpty;
         for (;;) {
             // ---- refill idle lanes ----
             uint32_t idle = __ballot_sync(0xffffffffu, !active);
