@@ -260,7 +260,7 @@ struct BrickWalk {
     float sx, sy, sz;
     uint32_t loc;          // position inside the brick: (x & 7) + 8 | ((y & 7) + 8) << 8 | ((z & 7) + 8) << 16
     uint32_t ploc;         // loc before the last iteration | iterations run by the current burst << 24
-    uint32_t cell;         // padded brick coordinates cx | cy << 10 | cz << 20
+    uint32_t cell;         // index of the brick in the padded brick grid, (cz * pby + cy) * pbx + cx
     uint32_t ix, iy, iz;   // per-axis increments of loc: +-1, +-1 << 8, +-1 << 16
     uint32_t stop;         // see above
     uint32_t slot;
@@ -318,9 +318,10 @@ __device__ __noinline__ int brick_walk_slow(const uint32_t* __restrict__ l1, con
 __device__ __forceinline__ int brick_walk_lookup(const BrickVolume& bv, BrickWalk& k) {
     const uint32_t moved = (k.loc ^ k.ploc) & kLocFields; // fields the last iteration changed (:83), before loc is re-based
     if ((~k.loc & kLocInside) != 0u) { // crossed at least one face: field >> 3 = 0 / 1 / 2 -> one brick down / same / up
-        k.cell = k.cell + ((k.loc >> 3) & 0x3u) + (((k.loc >> 11) & 0x3u) << 10) + (((k.loc >> 19) & 0x3u) << 20) - 0x00100401u;
+        const uint32_t row = bv.bx, plane = bv.bx * bv.by;
+        k.cell = k.cell + ((k.loc >> 3) & 0x3u) + ((k.loc >> 11) & 0x3u) * row + ((k.loc >> 19) & 0x3u) * plane - (1u + row + plane);
         k.loc = (k.loc & kLocLow) | kLocInside;
-        const uint32_t bi = ((k.cell >> 20) * bv.by + ((k.cell >> 10) & 0x3FFu)) * bv.bx + (k.cell & 0x3FFu);
+        const uint32_t bi = k.cell;
         const uint32_t pr = l1_pair(bv.l1, bi);
         const bool occ = pr == 3u;
         k.slot = occ ? __ldg(bv.table + bi) : (pr == 2u ? kSlotEmpty : kSlotFree);
@@ -378,14 +379,14 @@ __device__ __forceinline__ int brick_walk_begin(const BrickVolume& bv, uint32_t 
     }
     // padded brick = (v + 8) >> 3, position inside = (v + 8) & 7
     const uint32_t ux = (uint32_t)(r.v[0] + 8), uy = (uint32_t)(r.v[1] + 8), uz = (uint32_t)(r.v[2] + 8);
-    k.cell = (ux >> 3) | ((uy >> 3) << 10) | ((uz >> 3) << 20);
+    k.cell = ((uz >> 3) * bv.by + (uy >> 3)) * bv.bx + (ux >> 3);
     k.loc = ((ux & 7u) | ((uy & 7u) << 8) | ((uz & 7u) << 16)) | kLocInside;
     k.ix = (uint32_t)r.step[0]; k.iy = (uint32_t)r.step[1] << 8; k.iz = (uint32_t)r.step[2] << 16;
     k.sx = r.side[0]; k.sy = r.side[1]; k.sz = r.side[2];
     k.ploc = k.loc;
     // no current brick yet: look the start brick up (the same code as after crossing a face, with no face crossed)
     if (status == 0) {
-        const uint32_t bi = ((k.cell >> 20) * bv.by + ((k.cell >> 10) & 0x3FFu)) * bv.bx + (k.cell & 0x3FFu);
+        const uint32_t bi = k.cell;
         const uint32_t pr = l1_pair(bv.l1, bi);
         const bool occ = pr == 3u;
         k.slot = occ ? __ldg(bv.table + bi) : (pr == 2u ? kSlotEmpty : kSlotFree);
@@ -451,10 +452,11 @@ __device__ __forceinline__ int brick_walk_burst(const BrickVolume& bv, const Dda
     return left ? brick_walk_lookup(bv, k) : 0;
 }
 
-__device__ __forceinline__ void brick_walk_finish(const BrickWalk& k, bool hit, Dda& r) {
-    r.v[0] = (int32_t)(((k.cell & 0x3FFu) << 3) + (k.loc & 7u)) - 8;
-    r.v[1] = (int32_t)((((k.cell >> 10) & 0x3FFu) << 3) + ((k.loc >> 8) & 7u)) - 8;
-    r.v[2] = (int32_t)(((k.cell >> 20) << 3) + ((k.loc >> 16) & 7u)) - 8;
+__device__ __forceinline__ void brick_walk_finish(const BrickVolume& bv, const BrickWalk& k, bool hit, Dda& r) {
+    const uint32_t cz = k.cell / (bv.bx * bv.by), rem = k.cell - cz * (bv.bx * bv.by), cy = rem / bv.bx, cx = rem - cy * bv.bx;
+    r.v[0] = (int32_t)((cx << 3) + (k.loc & 7u)) - 8;
+    r.v[1] = (int32_t)((cy << 3) + ((k.loc >> 8) & 7u)) - 8;
+    r.v[2] = (int32_t)((cz << 3) + ((k.loc >> 16) & 7u)) - 8;
     r.side[0] = k.sx; r.side[1] = k.sy; r.side[2] = k.sz;
     r.steps = k.steps;
     r.last_mask = k.last;
@@ -466,5 +468,5 @@ __device__ __forceinline__ void dda_march_bricks(const BrickVolume& bv, uint32_t
     BrickWalk k;
     int status = brick_walk_begin(bv, W, H, D, pos, dir, has_start, sv, r, k);
     while (status == 0) status = brick_walk_burst<VT_MARCH_BURST>(bv, r, k);
-    brick_walk_finish(k, status == 1, r);
+    brick_walk_finish(bv, k, status == 1, r);
 }

@@ -882,7 +882,10 @@ __device__ __forceinline__ void rng_sphere(Rng& r, float s[3]) {
 // RNG stream keyed (seed, i).  One thread per ray, grid-stride; masks of dense volumes stay in global
 // memory here (the mode exists for volumes far larger than shared memory).
 // Record: hit_voxel = x | y << 16, instance = z, packed = steps | face bits << 16, iters = steps.
-__global__ void __launch_bounds__(kBlockThreads) trace_rays_kernel(const __grid_constant__ FrameParams fp,
+#ifndef VT_RAYS_MIN_BLOCKS
+#define VT_RAYS_MIN_BLOCKS 5 // 48 registers (a few spills) for 5 CTAs per SM: the walk waits on l1 / table / pool loads (configs[4]: 36.3 -> 34.0 ms)
+#endif
+__global__ void __launch_bounds__(kBlockThreads, VT_RAYS_MIN_BLOCKS) trace_rays_kernel(const __grid_constant__ FrameParams fp,
                                                                    const InstUniforms* __restrict__ inst,
                                                                    const uint32_t* __restrict__ mask_arena, unsigned long long n,
                                                                    unsigned long long first, FrameBuffers fb) {
@@ -987,7 +990,7 @@ __global__ void __launch_bounds__(kBlockThreads) trace_rays_kernel(const __grid_
             }
             // ---- ended rays write their record ----
             if (active && status != 0) {
-                brick_walk_finish(k, status == 1, r);
+                brick_walk_finish(bv, k, status == 1, r);
                 iter_sum += r.steps;
                 write_ray(my_ray, r);
                 active = false;
