@@ -117,7 +117,24 @@ inline std::vector<RawDynamicChunk> load_magica_voxel(const std::string& filepat
         else if (!std::memcmp(&buf[off], "RGBA", 4) && !rgba) rgba = body;
         off = body + n + m;
     }
-    if (!rgba) throw std::runtime_error("RGBA chunk missing (default palette not restated)");
+    // no RGBA chunk: MagicaVoxel's published default palette (index 0 unused, 6x6x6 colour cube without black, ramps of
+    // red / green / blue / grey), laid out like an RGBA chunk (entry k = colour of file index k + 1); dot_vox's own copy of
+    // the table is not available offline, so this is an unpinned restatement
+    std::vector<uint32_t> palette(256, 0);
+    if (rgba) {
+        for (size_t k = 0; k < 256; ++k) palette[k] = u32(rgba + 4 * k);
+    } else {
+        static const uint32_t lv[6] = {0xff, 0xcc, 0x99, 0x66, 0x33, 0x00}, ramp[10] = {0xee, 0xdd, 0xbb, 0xaa, 0x88, 0x77, 0x55, 0x44, 0x22, 0x11};
+        uint32_t t[257] = {};
+        for (uint32_t k = 0; k < 215; ++k) t[k + 1] = 0xff000000u | lv[k % 6] << 16 | lv[(k / 6) % 6] << 8 | lv[k / 36];
+        for (uint32_t j = 0; j < 10; ++j) {
+            t[216 + j] = 0xff000000u | ramp[j];
+            t[226 + j] = 0xff000000u | ramp[j] << 8;
+            t[236 + j] = 0xff000000u | ramp[j] << 16;
+            t[246 + j] = 0xff000000u | ramp[j] * 0x010101u;
+        }
+        for (size_t k = 0; k < 256; ++k) palette[k] = t[k + 1];
+    }
     std::vector<RawDynamicChunk> chunks;
     for (const Model& md : models) {
         RawDynamicChunk chunk(md.sx, md.sy, md.sz, Color::from_uint(0));
@@ -127,7 +144,7 @@ inline std::vector<RawDynamicChunk> load_magica_voxel(const std::string& filepat
             Color* c = chunk.at_mut(q[0], int(md.sy) - int(q[2]) - 1, q[1]);
             if (!c) throw std::runtime_error("voxel outside chunk");
             const uint32_t i = q[3] ? q[3] - 1u : 0u;
-            *c = Color::from_uint(u32(rgba + 4 * size_t(i)));
+            *c = Color::from_uint(palette[i]);
         }
         chunks.push_back(std::move(chunk));
     }

@@ -961,7 +961,32 @@ void vo_resolve(const uint64_t* accum, int width, int height, uint32_t total_spp
 
 static uint32_t rd_u32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 
-int vo_load_vox(const char* path, uint32_t dims[3], uint8_t* out, uint64_t out_capacity) {
+/* MagicaVoxel's default palette (the table published with the .vox format: index 0 unused, a 6x6x6 colour cube without
+ * black, then ramps of red, green, blue and grey), laid out like an RGBA chunk: entry k is the colour of file index k + 1.
+ * dot_vox 4.1.0 supplies its copy of this table when a file has no RGBA chunk; that copy (resources/default_palette.bytes
+ * of the crate) is not available offline, so this restatement is unpinned. */
+static void vox_default_palette(uint8_t pal[1024]) {
+    static const uint8_t lv[6] = {0xff, 0xcc, 0x99, 0x66, 0x33, 0x00};
+    static const uint8_t ramp[10] = {0xee, 0xdd, 0xbb, 0xaa, 0x88, 0x77, 0x55, 0x44, 0x22, 0x11};
+    uint32_t t[257];
+    t[0] = 0;
+    for (uint32_t k = 0; k < 215; ++k) /* 0xAABBGGRR: blue runs fastest, red slowest */
+        t[k + 1] = 0xff000000u | ((uint32_t)lv[k % 6] << 16) | ((uint32_t)lv[(k / 6) % 6] << 8) | (uint32_t)lv[k / 36];
+    for (uint32_t j = 0; j < 10; ++j) {
+        t[216 + j] = 0xff000000u | ramp[j];
+        t[226 + j] = 0xff000000u | ((uint32_t)ramp[j] << 8);
+        t[236 + j] = 0xff000000u | ((uint32_t)ramp[j] << 16);
+        t[246 + j] = 0xff000000u | ((uint32_t)ramp[j] * 0x010101u);
+    }
+    t[256] = 0;
+    for (uint32_t k = 0; k < 256; ++k) {
+        const uint32_t c = t[k + 1];
+        pal[4 * k + 0] = (uint8_t)c; pal[4 * k + 1] = (uint8_t)(c >> 8); pal[4 * k + 2] = (uint8_t)(c >> 16); pal[4 * k + 3] = (uint8_t)(c >> 24);
+    }
+}
+
+/* model `model` of the file (dot_vox: one model per SIZE / XYZI pair, in file order); -6 when the file has fewer */
+int vo_load_vox_model(const char* path, uint32_t model, uint32_t dims[3], uint8_t* out, uint64_t out_capacity) {
     FILE* f = fopen(path, "rb");
     if (!f) return -1;
     fseek(f, 0, SEEK_END);
@@ -976,18 +1001,25 @@ int vo_load_vox(const char* path, uint32_t dims[3], uint8_t* out, uint64_t out_c
         const uint8_t* size_chunk = NULL;
         const uint8_t* xyzi_chunk = NULL;
         const uint8_t* rgba_chunk = NULL;
+        const uint8_t* pending_size = NULL;
+        uint32_t seen = 0;
+        uint8_t default_pal[1024];
         size_t off = 20; /* "VOX " ver "MAIN" n m */
         while (off + 12 <= (size_t)n) {
             const uint8_t* id = buf + off;
             uint32_t cn = rd_u32(buf + off + 4), cm = rd_u32(buf + off + 8);
             const uint8_t* body = buf + off + 12;
             if (off + 12 + (size_t)cn + (size_t)cm > (size_t)n) break;
-            if (!memcmp(id, "SIZE", 4) && !size_chunk) size_chunk = body;
-            else if (!memcmp(id, "XYZI", 4) && !xyzi_chunk) xyzi_chunk = body;
-            else if (!memcmp(id, "RGBA", 4) && !rgba_chunk) rgba_chunk = body;
+            if (!memcmp(id, "SIZE", 4)) pending_size = body;
+            else if (!memcmp(id, "XYZI", 4) && pending_size) {
+                if (seen == model) { size_chunk = pending_size; xyzi_chunk = body; }
+                ++seen;
+                pending_size = NULL;
+            } else if (!memcmp(id, "RGBA", 4) && !rgba_chunk) rgba_chunk = body;
             off += 12 + (size_t)cn + (size_t)cm;
         }
-        if (!size_chunk || !xyzi_chunk || !rgba_chunk) goto done;
+        if (!size_chunk || !xyzi_chunk) { rc = seen ? -6 : -3; goto done; }
+        if (!rgba_chunk) { vox_default_palette(default_pal); rgba_chunk = default_pal; }
         uint32_t sx = rd_u32(size_chunk), sy = rd_u32(size_chunk + 4), sz = rd_u32(size_chunk + 8);
         dims[0] = sx; dims[1] = sy; dims[2] = sz; /* RawDynamicChunk::new(size.x, size.y, size.z), :23-28 */
         rc = 0;
@@ -1014,6 +1046,10 @@ int vo_load_vox(const char* path, uint32_t dims[3], uint8_t* out, uint64_t out_c
 done:
     free(buf);
     return rc;
+}
+
+int vo_load_vox(const char* path, uint32_t dims[3], uint8_t* out, uint64_t out_capacity) {
+    return vo_load_vox_model(path, 0, dims, out, out_capacity);
 }
 
 /* texels of volume `tex` (any kind) in the box [x0,x0+nx) x [y0,y0+ny) x [z0,z0+nz), x fastest: lets the tests turn a

@@ -113,6 +113,9 @@ void vo_mat4_mul(const float* a, const float* b, float* out);
  * src/voxel/rawchunk.rs:292) = exactly what add_texture receives.  Returns 0 on success.
  * Call with out == NULL to query dims only. */
 int vo_load_vox(const char* path, uint32_t dims[3], uint8_t* out, uint64_t out_capacity);
+/* the same for model `model` of a multi-model file (one per SIZE / XYZI pair, file order; -6: no such model).  A file
+ * without RGBA chunk gets MagicaVoxel's published default palette (unpinned: dot_vox's own copy is not available offline). */
+int vo_load_vox_model(const char* path, uint32_t model, uint32_t dims[3], uint8_t* out, uint64_t out_capacity);
 
 /* sRGB helpers shared by resolve and blend (exposed for tests) */
 float vo_srgb_decode(uint8_t c);

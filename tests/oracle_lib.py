@@ -63,6 +63,8 @@ def lib() -> C.CDLL:
         L.vo_mat4_mul.argtypes = [vp, vp, vp]
         L.vo_load_vox.argtypes = [C.c_char_p, vp, vp, u64]
         L.vo_load_vox.restype = C.c_int
+        L.vo_load_vox_model.argtypes = [C.c_char_p, C.c_uint32, vp, vp, u64]
+        L.vo_load_vox_model.restype = C.c_int
         L.vo_srgb_decode.argtypes = [C.c_uint8]
         L.vo_srgb_decode.restype = C.c_float
         L.vo_srgb_encode.argtypes = [C.c_float]
@@ -171,6 +173,21 @@ def frag_main(P, V, M, sp, mp, rgba, w, h, d):
     rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
     lib().vo_frag_main(_p(P), _p(V), _p(M), _p(sp), _p(mp), _p(rgba), w, h, d, _p(out), _p(color), _p(depth))
     return out, color, float(depth[0])
+
+
+def load_vox_model(path: str, model: int):
+    """(raw RGBA bytes as n x 4, dims) of one model of a .vox file; None when the file has fewer models."""
+    dims = np.zeros(3, dtype=np.uint32)
+    rc = lib().vo_load_vox_model(path.encode(), model, _p(dims), None, 0)
+    if rc == -6:
+        return None
+    if rc != 0:
+        raise RuntimeError(f"vo_load_vox_model({path}, {model}) failed: {rc}")
+    out = np.zeros(4 * int(dims.prod()), dtype=np.uint8)
+    rc = lib().vo_load_vox_model(path.encode(), model, _p(dims), _p(out), out.size)
+    if rc != 0:
+        raise RuntimeError(f"vo_load_vox_model({path}, {model}) failed: {rc}")
+    return out.reshape(-1, 4), tuple(int(d) for d in dims)
 
 
 def load_vox(path: str):

@@ -3,6 +3,7 @@ texture upload queue, scene helpers)."""
 import os
 
 import numpy as np
+import pytest
 
 from tools import scenes
 from vtrace_b200 import glm, voxel
@@ -89,3 +90,46 @@ def test_weighted_sharding_partitions_every_sample_once_and_relieves_the_root():
                     assert max(counts[1:]) - min(counts[1:]) <= 1
     assert [shard_samples_weighted(64, r, 8)[2] for r in range(8)] == [6, 9, 9, 8, 8, 8, 8, 8]
     assert [shard_samples_weighted(64, r, 2)[2] for r in range(2)] == [31, 33]
+
+
+def _fnv1a64(b: bytes) -> int:
+    h = 1469598103934665603
+    for x in b:
+        h = ((h ^ x) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+@pytest.mark.parametrize("name,with_rgba", [("three_models_rgba", True), ("three_models_default_palette", False)])
+def test_multi_model_vox_and_default_palette_across_the_three_loaders(oracle, tmp_path, name, with_rgba):
+    """dot_vox semantics the two reference assets do not exercise: one chunk per SIZE / XYZI pair, and
+    the default palette when the file has no RGBA chunk.  The C oracle loader, the Python loader and the C++ host's loader
+    must produce the same bytes — and those bytes must be what an independent construction from the fixture's voxel list
+    gives.  (The default palette itself is restated from the published .vox format, not from the crate: unpinned.)"""
+    import subprocess
+
+    from tools import gen_vox_fixtures as gen
+    path = os.path.join(scenes.ASSETS, f"{name}.vox")
+    pal = gen.palette() if with_rgba else voxel.default_palette()
+    if not with_rgba:  # spot values of the published table: index 1 white, 2 = 0xffccffff, 216 = darkest-but-one... red ramp
+        assert tuple(pal[0]) == (255, 255, 255, 255) and tuple(pal[1]) == (255, 255, 204, 255)
+        assert tuple(pal[215]) == (238, 0, 0, 255) and tuple(pal[254]) == (17, 17, 17, 255) and tuple(pal[255]) == (0, 0, 0, 0)
+        assert len({tuple(c) for c in pal[:255]}) == 255
+    chunks = voxel.load_magica_voxel(path)
+    ms = gen.models()
+    assert len(chunks) == len(ms) == 3
+    exe = tmp_path / "vox_dump"
+    host = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "host")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-I", os.path.join(host, "..", "include"), "-o", str(exe), os.path.join(host, "vox_dump.cpp")],
+                   check=True)
+    dumped = subprocess.run([str(exe), path], check=True, capture_output=True, text=True).stdout.splitlines()
+    assert len(dumped) == 3
+    for m, ((sx, sy, sz), vox) in enumerate(ms):
+        want = np.zeros((sx, sy, sz, 4), dtype=np.uint8)  # chunk (x, size.y - z - 1, y), magica_voxel.rs:31-37
+        for x, y, z, i in vox:
+            want[x, sy - int(z) - 1, y] = pal[int(i) - 1]
+        raw, dims = oracle.load_vox_model(path, m)
+        assert dims == (sx, sy, sz) == chunks[m].dims()
+        assert np.array_equal(raw.reshape(-1), want.reshape(-1))
+        assert np.array_equal(chunks[m].get_raw(), want.reshape(-1))
+        assert dumped[m] == f"model {m} dims {sx} {sy} {sz} fnv1a {_fnv1a64(want.tobytes()):016x}"
+    assert oracle.load_vox_model(path, 3) is None

@@ -44,23 +44,42 @@ def _chunks(buf: bytes, off: int, end: int):
         off += 12 + n + m
 
 
+def default_palette() -> np.ndarray:
+    """MagicaVoxel's default palette (published with the .vox format: index 0 unused, a 6x6x6 colour cube without black,
+    then ramps of red, green, blue, grey), laid out like an RGBA chunk: row k = colour of file index k + 1.  dot_vox 4.1.0
+    supplies its copy when a file has no RGBA chunk; that copy is not available offline — unpinned restatement."""
+    lv = [0xFF, 0xCC, 0x99, 0x66, 0x33, 0x00]
+    ramp = [0xEE, 0xDD, 0xBB, 0xAA, 0x88, 0x77, 0x55, 0x44, 0x22, 0x11]
+    t = [0] * 257
+    for k in range(215):  # 0xAABBGGRR: blue runs fastest, red slowest
+        t[k + 1] = 0xFF000000 | lv[k % 6] << 16 | lv[(k // 6) % 6] << 8 | lv[k // 36]
+    for j in range(10):
+        t[216 + j] = 0xFF000000 | ramp[j]
+        t[226 + j] = 0xFF000000 | ramp[j] << 8
+        t[236 + j] = 0xFF000000 | ramp[j] << 16
+        t[246 + j] = 0xFF000000 | ramp[j] * 0x010101
+    return np.array(t[1:], dtype="<u4").view(np.uint8).reshape(256, 4)
+
+
 def load_magica_voxel(path: str) -> list[RawDynamicChunk]:
     """One RawDynamicChunk per model, axes remapped as magica_voxel.rs:31-37 does."""
     with open(path, "rb") as f:
         buf = f.read()
     if buf[:4] != b"VOX " or buf[8:12] != b"MAIN":
         raise ValueError("not a MagicaVoxel file")
-    sizes, xyzis, palette = [], [], None
+    sizes, xyzis, palette, pending = [], [], None, None
     for cid, body in _chunks(buf, 20, len(buf)):
         if cid == b"SIZE":
-            sizes.append(struct.unpack_from("<III", body))
-        elif cid == b"XYZI":
+            pending = struct.unpack_from("<III", body)
+        elif cid == b"XYZI" and pending is not None:  # one model per SIZE / XYZI pair, in file order
             n = struct.unpack_from("<I", body)[0]
+            sizes.append(pending)
             xyzis.append(np.frombuffer(body, dtype=np.uint8, count=4 * n, offset=4).reshape(n, 4))
+            pending = None
         elif cid == b"RGBA" and palette is None:
             palette = np.frombuffer(body, dtype=np.uint8, count=1024).reshape(256, 4)
     if palette is None:
-        raise ValueError("RGBA chunk missing (default palette not restated)")
+        palette = default_palette()
     out = []
     for (sx, sy, sz), vox in zip(sizes, xyzis):
         chunk = RawDynamicChunk(sx, sy, sz)
