@@ -461,6 +461,23 @@ def _grid_models(a, b):
     return models
 
 
+def test_default_world_primary_and_paths(scene):
+    """The reference's default world (src/world.rs:143-198): the 11x11 entity grid plus every non-empty 16^3 chunk of the
+    paged terrain (tools/scenes.default_world: 343 instances, 224 textures, masks read from global memory) — primary
+    frame and path-traced frame against the oracle, from outside and from the reference's start position inside chunk 0."""
+    textures, inst = scenes.default_world()
+    ids = [scene.add(c) for c in textures]
+    scene.set_instances([(m, ids[t]) for m, t in inst])
+    for eye, center in (((9.0, -9.0, 7.0), (0.0, -2.0, 0.0)), ((0.0, 0.0, 0.0), (1.0, 0.0, 0.0))):
+        P, V = scenes.camera(400, 400, eye=eye, center=center)
+        got, st = scene.check_primary(P, V, 400, 400, what=f"default world from {eye}")
+        assert st.masks_in_smem == 0
+        if eye[0] > 1.0:
+            assert len(np.unique(got["instance"][got["hit_voxel"] != abi.VT_MISS])) > 150
+    P, V = scenes.camera(200, 200, eye=(9.0, -9.0, 7.0), center=(0.0, -2.0, 0.0))
+    scene.check_paths(P, V, 200, 200, spp=2, bounces=3, what="default world paths")
+
+
 def test_paths_world_grid_entity_grid(scene, assets):
     """Bounce rays over the 11x11 entity grid go through the world-space instance grid (world_grid.cuh): the
     result must be what the oracle's loop over every instance gives, and what the same kernel gives with the

@@ -33,6 +33,9 @@ CONFIGS = {
     "heightmap_4k": ("heightmap1024", 3840, 2160, abi.MODE_PRIMARY, 0),        # configs[3]: primary + shadow rays
     "sparse_rays": ("sparse4096", 8192, 8192, abi.MODE_RAYS, 0),               # configs[4]: 2^26 incoherent rays
     "heightmap_paths": ("heightmap1024", 1920, 1080, abi.MODE_PATHS, 8),       # the configs[3] volume, path traced
+    # the reference's default world (src/world.rs:143-198): 121 entities + the paged terrain chunks, 1000x1000 window
+    "world_primary": ("world", 1000, 1000, abi.MODE_PRIMARY, 0),
+    "world_paths": ("world", 1000, 1000, abi.MODE_PATHS, 8),
 }
 
 
@@ -57,6 +60,12 @@ def main():
             from vtrace_b200 import glm
             P = glm.perspective(glm.REFERENCE_FOV, np.float32(w) / np.float32(h), glm.REFERENCE_NEAR, glm.REFERENCE_FAR)
             V = glm.look_at((0.0, -2.0, 0.0), (3.0, -5.0, 2.0), (0.0, 1.0, 0.0))
+        elif asset == "world":
+            textures, inst = scenes.default_world()
+            ids = [r.add_texture(c) for c in textures]
+            from vtrace_b200 import glm
+            r.update_instances_raw(np.stack([glm.with_texture_id(m, ids[t]).reshape(16) for m, t in inst]))
+            P, V = scenes.camera(w, h, eye=(9.0, -9.0, 7.0), center=(0.0, -2.0, 0.0))
         elif asset == "heightmap1024":
             r.add_volume_procedural(abi.VOLUME_HEIGHTMAP, 1024, 1024, 1024, 1)
             r.update_instances_raw(scenes.single_instance(0))
