@@ -202,7 +202,8 @@ __global__ void instance_setup_kernel(const float* __restrict__ instances, uint3
         I.rgba = nullptr;
         for (int k = 0; k < 16; ++k) I.MVP[k] = 0.0f;
         for (int k = 0; k < 12; ++k) I.Mi[k] = I.M[k] = I.dirm[k] = 0.0f;
-        for (int k = 0; k < 3; ++k) I.eye_m[k] = I.slab_lo[k] = I.slab_hi[k] = 0.0f;
+        for (int k = 0; k < 3; ++k) I.eye_m[k] = I.slab_lo[k] = I.slab_hi[k] = I.lin[k] = I.ilin[k] = 0.0f;
+        I.pad1[0] = I.pad1[1] = 0;
         I.bounds[0] = 1; I.bounds[1] = 0; I.bounds[2] = 1; I.bounds[3] = 0; // empty
         out[i] = I;
         return;
@@ -228,6 +229,20 @@ __global__ void instance_setup_kernel(const float* __restrict__ instances, uint3
         I.slab_lo[r] = -0.5f - I.eye_m[r];
         I.slab_hi[r] = 0.5f - I.eye_m[r];
         I.sun_m[r] = (Mi[0 * 4 + r] * fp.sun[0] + Mi[1 * 4 + r] * fp.sun[1]) + Mi[2 * 4 + r] * fp.sun[2];
+    }
+    {   // is inverse(M)'s linear part diagonal with powers of two?  (see InstUniforms::lin)
+        bool ok = true;
+        for (int c = 0; c < 3; ++c)
+            for (int r = 0; r < 3; ++r) {
+                const uint32_t bits = __float_as_uint(Mi[c * 4 + r]);
+                if (c != r) ok = ok && (bits << 1) == 0u; // +-0
+                else ok = ok && (bits & 0x007FFFFFu) == 0u && ((bits >> 23) & 0xFFu) >= 64u && ((bits >> 23) & 0xFFu) <= 190u; // +-2^e, |e| <= 63
+            }
+        for (int k = 0; k < 3; ++k) {
+            I.lin[k] = ok ? Mi[k * 4 + k] : 0.0f;
+            I.ilin[k] = ok ? 1.0f / Mi[k * 4 + k] : 0.0f;
+        }
+        I.pad1[0] = I.pad1[1] = 0;
     }
     // Conservative screen rectangle of the proxy cube (what the rasteriser would bin): project the 8
     // corners, +-2 pixels of slack.  Any corner at or behind the eye plane -> whole screen.  A pixel
@@ -360,6 +375,32 @@ __device__ __forceinline__ bool slab_unit_cube(const float o[3], const float lo3
     if (axis < 0) return false;
     if (!(tn <= tf)) return false;
     if (!(tn > 0.0f)) return false; // inside / behind: only back faces -> culled (lib/pipeline.c:120-121)
+    tn_out = tn;
+    axis_out = axis;
+    return true;
+}
+
+// the same with 1 / d[k] supplied (bit-identical when inv[k] == 1.0f / d[k])
+__device__ __forceinline__ bool slab_unit_cube_inv(const float o[3], const float lo3[3], const float hi3[3], const float d[3],
+                                                   const float inv3[3], float& tn_out, int& axis_out) {
+    float tn = -INFINITY, tf = INFINITY;
+    int axis = -1;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (d[k] == 0.0f) {
+            if (o[k] < -0.5f || o[k] > 0.5f) return false;
+            continue;
+        }
+        const float t1 = lo3[k] * inv3[k];
+        const float t2 = hi3[k] * inv3[k];
+        const float lo = t1 < t2 ? t1 : t2;
+        const float hi = t1 < t2 ? t2 : t1;
+        if (lo > tn) { tn = lo; axis = k; }
+        if (hi < tf) tf = hi;
+    }
+    if (axis < 0) return false;
+    if (!(tn <= tf)) return false;
+    if (!(tn > 0.0f)) return false;
     tn_out = tn;
     axis_out = axis;
     return true;
@@ -1043,6 +1084,42 @@ __device__ void trace_world(const FrameParams& fp, const InstUniforms* __restric
         const WorldGrid g = *wg.hdr;
         world_walk_begin(g, ow, dw, walk);
     }
+    // The ray's direction as an instance with inverse(M) = identity would see it, and its reciprocal: instances whose
+    // inverse(M) is a diagonal of powers of two (InstUniforms::lin) scale both exactly, so they cost no division.
+    float d0[3], inv0[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        d0[k] = cam ? (fp.RD[0 * 4 + k] * cam[0] + fp.RD[1 * 4 + k] * cam[1]) + fp.RD[3 * 4 + k] : dw[k];
+        inv0[k] = 1.0f / d0[k];
+    }
+    // the ray in the space of instance j, and the box test of trace.frag's proxy cube
+    auto candidate = [&](uint32_t j, float o[3], float d[3], float& tn, int& axis) -> bool {
+        const InstUniforms* J = inst + j;
+        float inv3[3];
+        const bool lin = J->lin[0] != 0.0f;
+        if (cam) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) o[k] = J->eye_m[k];
+            if (!lin) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) d[k] = (J->dirm[0 * 3 + k] * cam[0] + J->dirm[1 * 3 + k] * cam[1]) + J->dirm[3 * 3 + k];
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                o[k] = ((J->Mi[0 * 3 + k] * ow[0] + J->Mi[1 * 3 + k] * ow[1]) + J->Mi[2 * 3 + k] * ow[2]) + J->Mi[3 * 3 + k];
+                if (!lin) d[k] = (J->Mi[0 * 3 + k] * dw[0] + J->Mi[1 * 3 + k] * dw[1]) + J->Mi[2 * 3 + k] * dw[2];
+            }
+        }
+        const float lo3[3] = {-0.5f - o[0], -0.5f - o[1], -0.5f - o[2]};
+        const float hi3[3] = {0.5f - o[0], 0.5f - o[1], 0.5f - o[2]};
+        if (lin) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { d[k] = J->lin[k] * d0[k]; inv3[k] = J->ilin[k] * inv0[k]; }
+            return slab_unit_cube_inv(o, lo3, hi3, d, inv3, tn, axis);
+        }
+        return slab_unit_cube(o, lo3, hi3, d, tn, axis);
+    };
     for (;;) {
         bool found = false;
         float best_t = 0.0f;
@@ -1065,27 +1142,11 @@ __device__ void trace_world(const FrameParams& fp, const InstUniforms* __restric
             const uint32_t j = list ? __ldg(list + k) : k;
             const InstUniforms* J = inst + j;
             if (j == skip || !J->valid) continue;
-            float o[3], d[3];
-            if (cam) {
-                // camera rays: the conservative screen rectangle rejects most instances without arithmetic
-                if (px < J->bounds[0] || px > J->bounds[1] || py < J->bounds[2] || py > J->bounds[3]) continue;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    o[k] = J->eye_m[k];
-                    d[k] = (J->dirm[0 * 3 + k] * cam[0] + J->dirm[1 * 3 + k] * cam[1]) + J->dirm[3 * 3 + k];
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    o[k] = ((J->Mi[0 * 3 + k] * ow[0] + J->Mi[1 * 3 + k] * ow[1]) + J->Mi[2 * 3 + k] * ow[2]) + J->Mi[3 * 3 + k];
-                    d[k] = (J->Mi[0 * 3 + k] * dw[0] + J->Mi[1 * 3 + k] * dw[1]) + J->Mi[2 * 3 + k] * dw[2];
-                }
-            }
-            const float lo3[3] = {-0.5f - o[0], -0.5f - o[1], -0.5f - o[2]};
-            const float hi3[3] = {0.5f - o[0], 0.5f - o[1], 0.5f - o[2]};
-            float tn;
+            // camera rays: the conservative screen rectangle rejects most instances without arithmetic
+            if (cam && (px < J->bounds[0] || px > J->bounds[1] || py < J->bounds[2] || py > J->bounds[3])) continue;
+            float o[3], d[3], tn;
             int axis;
-            if (!slab_unit_cube(o, lo3, hi3, d, tn, axis)) continue;
+            if (!candidate(j, o, d, tn, axis)) continue;
             if (have_last && !(tn > last_t || (tn == last_t && j > last_j))) continue;
             if (tn > t_lim) continue;
             if (!found || tn < best_t || (tn == best_t && j < best_j)) { // (grid lists are unordered)

@@ -98,6 +98,12 @@ struct __align__(16) InstUniforms {
     uint32_t pad;
     const uint8_t* rgba;
     const BrickVolume* bricks; // non-null: procedural brick volume
+    // lin[k] != 0: inverse(M)'s 3x3 part is diagonal with (signed) powers of two, lin = its diagonal, ilin = 1 / lin.  The
+    // instance's ray direction is then lin * (world direction) EXACTLY, and 1 / d = ilin * (1 / world direction) exactly:
+    // the path tracer divides once per ray instead of once per instance it tests (every instance of the reference's
+    // default world — translations, and chunks scaled by 2 — is of this kind).
+    float lin[3], ilin[3];
+    uint32_t pad1[2];
 };
 
 static_assert(offsetof(InstUniforms, bounds) % 16 == 0, "bounds are loaded as one int4");
