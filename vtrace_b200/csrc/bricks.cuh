@@ -4,11 +4,13 @@
 // A 1024^3 or 4096^3 volume cannot be a dense RGBA8 texture (the reference's own add_texture
 // overflows its u32 byte count at 1024^3, lib/memory.c:297).  Such volumes are generated on the
 // device from a procedural definition and stored as occupancy only:
-//   l1: two bits per 8^3 brick, a tiny distance field — 3: the brick has voxels or lies in the border, 2: a brick next to it
-//   does, 1: a brick two away does, 0: nothing within two bricks (the walk treats 1 and 0 alike: a second burst without a
-//   lookup for 0 was measured and bought nothing)  ->  table[brick] = pool slot  ->  16 words (512 bits) per
-//   non-empty brick.
-// The brick grid carries a one-brick border on every side whose entries say "outside" (kSlotExit), so
+//   directory: per 16 consecutive bricks of the padded brick grid one word of two-bit codes (3: the brick has voxels,
+//   2: it has none but a brick of its 3x3x3 neighbourhood has some or is outside, 1: the brick lies in the one-brick border =
+//   outside the volume, 0: nothing within one brick) and one word with the number of bricks with voxels in all earlier
+//   entries.  The pool holds the 16 words (512 bits) of the bricks with voxels in grid order, so a brick's slot is that
+//   base + the number of 3-codes before it in its entry (no per-brick slot table: at 4096^3 that table was 543 MB, codes and
+//   bases are 34 MB each and stay in L2).
+// The brick grid carries a one-brick border on every side whose codes say "outside", so
 // the walk needs no coordinate compares: leaving the volume is found by the same lookup as entering
 // a brick.
 // Traversal keeps the reference's per-voxel float DDA (trace.frag:73-87) bit for bit — same steps,
@@ -18,13 +20,24 @@
 #pragma once
 
 static constexpr uint32_t kSlotEmpty = 0xFFFFFFFFu; // brick without voxels
-static constexpr uint32_t kSlotFree = 0xFFFFFFFEu;  // brick without voxels whose 26 neighbours have none either (and are inside)
-static constexpr uint32_t kSlotExit = 0xFFFFFFFCu;  // border brick: outside the volume.  Anything below is a pool slot.
+static constexpr uint32_t kSlotFree = 0xFFFFFFFEu;  // brick without voxels whose 26 neighbours have none either (and are inside).  Anything below is a pool slot.
 
-// l1 holds two bits per padded brick
-__host__ __device__ __forceinline__ size_t l1_words(size_t padded_bricks) { return (padded_bricks + 15) / 16; }
-__device__ __forceinline__ uint32_t l1_pair(const uint32_t* __restrict__ l1, uint32_t bi) { return (__ldg(l1 + (bi >> 4)) >> ((bi & 15u) * 2u)) & 3u; }
-__device__ __forceinline__ void l1_set(uint32_t* __restrict__ l1, size_t bi, uint32_t bit) { atomicOr(l1 + (bi >> 4), (1u << bit) << ((bi & 15u) * 2u)); }
+// directory entries: 16 bricks each.  Codes and slot bases live in two arrays of one word per entry: the base is only
+// needed for a brick with voxels, and the codes alone (34 MB at 4096^3) stay L2-resident (an interleaved 8-byte entry
+// was measured 9 % slower on configs[4]).
+__host__ __device__ __forceinline__ size_t dir_entries(size_t padded_bricks) { return (padded_bricks + 15) / 16; }
+__device__ __forceinline__ void dir_set(uint32_t* __restrict__ codes, size_t bi, uint32_t bit) {
+    atomicOr(codes + (bi >> 4), (1u << bit) << ((bi & 15u) * 2u));
+}
+// code of brick bi: 0 free, 1 outside, 2 empty, 3 has voxels
+__device__ __forceinline__ uint32_t dir_code(const uint32_t* __restrict__ codes, uint32_t bi, uint32_t& entry) {
+    entry = __ldg(codes + (bi >> 4));
+    return (entry >> ((bi & 15u) * 2u)) & 3u;
+}
+// pool slot of a brick with voxels: its entry's base + the 3-codes before it in the entry
+__device__ __forceinline__ uint32_t dir_slot(const uint32_t* __restrict__ base, uint32_t bi, uint32_t entry) {
+    return __ldg(base + (bi >> 4)) + __popc(entry & (entry >> 1) & 0x55555555u & ((1u << ((bi & 15u) * 2u)) - 1u));
+}
 
 // index of brick (x, y, z) in the padded grid (pbx, pby = brick counts + 2)
 __host__ __device__ __forceinline__ uint32_t brick_index(uint32_t pbx, uint32_t pby, uint32_t x, uint32_t y, uint32_t z) {
@@ -87,7 +100,10 @@ __device__ __forceinline__ bool proc_filled(uint32_t kind, uint32_t seed, const 
 __device__ __forceinline__ uchar4 proc_color(const BrickVolume* __restrict__ bv, uint32_t h, uint32_t x, uint32_t y, uint32_t z) {
     const uint32_t kind = bv->kind, seed = bv->seed;
     if (kind == kVolumeUploadedBricks) { // one colour per brick, found through the table again (once per ray)
-        const uchar4 c = __ldg(bv->colors + __ldg(bv->table + brick_index(bv->bx, bv->by, x >> 3, y >> 3, z >> 3)));
+        const uint32_t bi = brick_index(bv->bx, bv->by, x >> 3, y >> 3, z >> 3);
+        uint32_t entry;
+        dir_code(bv->codes, bi, entry);
+        const uchar4 c = __ldg(bv->colors + dir_slot(bv->base, bi, entry));
         return make_uchar4(c.x, c.y, c.z, 255);
     }
     if (kind == kVolumeHeightmap) {
@@ -100,10 +116,11 @@ __device__ __forceinline__ uchar4 proc_color(const BrickVolume* __restrict__ bv,
     return make_uchar4((unsigned char)(c | 0x40u), (unsigned char)((c >> 8) | 0x40u), (unsigned char)((c >> 16) | 0x40u), 255);
 }
 
-// One thread per brick.  pool == nullptr: count the non-empty bricks (*counter); otherwise fill.
+// One thread per brick.  pool == nullptr: mark the bricks with voxels (bit 0 of their code) and count them (*counter);
+// otherwise (after brick_finalize) write each one's 16 words to its slot.
 __global__ void brick_build_kernel(uint32_t kind, uint32_t seed, uint32_t w, uint32_t h, uint32_t d, const float* __restrict__ heights,
-                                   uint32_t* __restrict__ l1, uint32_t* __restrict__ table, uint32_t* __restrict__ pool,
-                                   uint32_t pool_capacity, uint32_t* __restrict__ counter) {
+                                   uint32_t* __restrict__ codes, const uint32_t* __restrict__ base, uint32_t* __restrict__ pool,
+                                   uint32_t* __restrict__ counter) {
     const uint32_t bxn = w >> 3, byn = h >> 3, bzn = d >> 3;
     const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= (size_t)bxn * byn * bzn) return;
@@ -131,112 +148,150 @@ __global__ void brick_build_kernel(uint32_t kind, uint32_t seed, uint32_t w, uin
         any |= bits;
     }
     if (!any) return;
-    const uint32_t slot = atomicAdd(counter, 1u);
-    if (!pool || slot >= pool_capacity) return;
-    for (uint32_t wi = 0; wi < 16; ++wi) pool[(size_t)slot * 16 + wi] = words[wi];
     const uint32_t pb = brick_index(bxn + 2, byn + 2, bx, by, bz);
-    table[pb] = slot;
-    l1_set(l1, pb, 0);
-}
-
-// border of the padded brick grid: l1 bit set, table = kSlotExit.  One thread per padded brick.
-__global__ void brick_border_kernel(uint32_t pbx, uint32_t pby, uint32_t pbz, uint32_t* __restrict__ l1, uint32_t* __restrict__ table) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)pbx * pby * pbz) return;
-    const uint32_t x = (uint32_t)(i % pbx), y = (uint32_t)((i / pbx) % pby), z = (uint32_t)(i / ((size_t)pbx * pby));
-    if (x == 0 || y == 0 || z == 0 || x == pbx - 1 || y == pby - 1 || z == pbz - 1) {
-        table[i] = kSlotExit;
-        l1_set(l1, i, 0);
+    if (!pool) {
+        dir_set(codes, pb, 0);
+        atomicAdd(counter, 1u);
+        return;
     }
+    uint32_t entry;
+    dir_code(codes, pb, entry);
+    const uint32_t slot = dir_slot(base, pb, entry);
+    for (uint32_t wi = 0; wi < 16; ++wi) pool[(size_t)slot * 16 + wi] = words[wi];
 }
 
-// The distance field is built in three passes after every occupied / border brick has its bit 0.
-// 1. scatter: bit 1 of every brick in the 3x3x3 neighbourhood of a set brick (one thread per padded brick; only the few
-//    per cent that are set scatter);
-__global__ void brick_dilate_kernel(uint32_t pbx, uint32_t pby, uint32_t pbz, uint32_t* __restrict__ l1) {
+// The directory is finished in four passes after every brick with voxels has bit 0 of its code set:
+// 1. scatter: bit 1 of every brick in the 3x3x3 neighbourhood of a brick with voxels or of a border brick (one thread per
+//    padded brick; only the few per cent that qualify scatter);
+__global__ void brick_dilate_kernel(uint32_t pbx, uint32_t pby, uint32_t pbz, uint32_t* __restrict__ codes) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)pbx * pby * pbz) return;
-    if (!((l1[i >> 4] >> ((i & 15u) * 2u)) & 1u)) return;
     const int x = (int)(i % pbx), y = (int)((i / pbx) % pby), z = (int)(i / ((size_t)pbx * pby));
+    const bool border = x == 0 || y == 0 || z == 0 || x == (int)pbx - 1 || y == (int)pby - 1 || z == (int)pbz - 1;
+    if (!border && !((codes[i >> 4] >> ((i & 15u) * 2u)) & 1u)) return;
     for (int dz = -1; dz <= 1; ++dz)
         for (int dy = -1; dy <= 1; ++dy)
             for (int dx = -1; dx <= 1; ++dx) {
                 const int nx = x + dx, ny = y + dy, nz = z + dz;
                 if (nx < 0 || ny < 0 || nz < 0 || nx >= (int)pbx || ny >= (int)pby || nz >= (int)pbz) continue;
-                l1_set(l1, ((size_t)nz * pby + ny) * pbx + nx, 1);
+                dir_set(codes, ((size_t)nz * pby + ny) * pbx + nx, 1);
             }
 }
-// 2. gather: a brick with neither bit is "two away" if one of its 26 neighbours has bit 1 (one bit per brick in `far2`);
-__global__ void brick_dilate2_kernel(uint32_t pbx, uint32_t pby, uint32_t pbz, const uint32_t* __restrict__ l1, uint32_t* __restrict__ far2) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)pbx * pby * pbz) return;
-    if ((l1[i >> 4] >> ((i & 15u) * 2u)) & 3u) return;
-    const int x = (int)(i % pbx), y = (int)((i / pbx) % pby), z = (int)(i / ((size_t)pbx * pby));
-    bool near = false;
-    for (int dz = -1; dz <= 1 && !near; ++dz)
-        for (int dy = -1; dy <= 1 && !near; ++dy)
-            for (int dx = -1; dx <= 1; ++dx) {
-                const int nx = x + dx, ny = y + dy, nz = z + dz;
-                if (nx < 0 || ny < 0 || nz < 0 || nx >= (int)pbx || ny >= (int)pby || nz >= (int)pbz) continue;
-                const size_t j = ((size_t)nz * pby + ny) * pbx + nx;
-                if ((l1[j >> 4] >> ((j & 15u) * 2u)) & 2u) { near = true; break; }
-            }
-    if (near) atomicOr(far2 + (i >> 5), 1u << (i & 31));
-}
-// 3. re-encode, one thread per l1 word: (bit 0, bit 1, far2) -> 3 occupied, 2 next to one, 1 two away, 0 farther.
-__global__ void brick_encode_kernel(size_t words, uint32_t* __restrict__ l1, const uint32_t* __restrict__ far2) {
+// 2. encode, one thread per entry: (bit 0, bit 1, border) -> 3 has voxels, 1 outside, 2 near something, 0 free; the entry's
+//    count of 3-codes goes to base[] for the scan;
+__global__ void brick_encode_kernel(uint32_t pbx, uint32_t pby, uint32_t pbz, size_t entries, uint32_t* __restrict__ codes,
+                                    uint32_t* __restrict__ base) {
     const size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= words) return;
-    const uint32_t v = l1[w], f = (far2[w >> 1] >> ((w & 1u) * 16u)) & 0xFFFFu;
-    uint32_t out = 0;
+    if (w >= entries) return;
+    const uint32_t v = codes[w];
+    const size_t n = (size_t)pbx * pby * pbz;
+    uint32_t out = 0, cnt = 0;
     for (uint32_t k = 0; k < 16; ++k) {
+        const size_t i = w * 16 + k;
+        if (i >= n) break;
+        const uint32_t x = (uint32_t)(i % pbx), y = (uint32_t)((i / pbx) % pby), z = (uint32_t)(i / ((size_t)pbx * pby));
+        const bool border = x == 0 || y == 0 || z == 0 || x == pbx - 1 || y == pby - 1 || z == pbz - 1;
         const uint32_t p = (v >> (2 * k)) & 3u;
-        const uint32_t q = (p & 1u) ? 3u : ((p & 2u) ? 2u : ((f >> k) & 1u));
+        const uint32_t q = border ? 1u : ((p & 1u) ? 3u : ((p & 2u) ? 2u : 0u));
+        cnt += q == 3u ? 1u : 0u;
         out |= q << (2 * k);
     }
-    l1[w] = out;
+    codes[w] = out;
+    base[w] = cnt;
+}
+// 3./4. exclusive scan of the counts (1024 entries per block: block sums, their scan by one block, then the entries).
+__global__ void __launch_bounds__(256) brick_scan_sums_kernel(size_t entries, const uint32_t* __restrict__ base, uint32_t* __restrict__ sums) {
+    __shared__ uint32_t part[8];
+    const size_t first = (size_t)blockIdx.x * 1024 + threadIdx.x * 4;
+    uint32_t s = 0;
+    for (int k = 0; k < 4; ++k)
+        if (first + k < entries) s += base[first + k];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int k = 0; k < 8; ++k) t += part[k];
+        sums[blockIdx.x] = t;
+    }
+}
+__global__ void brick_scan_top_kernel(uint32_t n_blocks, uint32_t* __restrict__ sums, uint32_t* __restrict__ total) {
+    if (blockIdx.x || threadIdx.x) return;
+    uint32_t run = 0;
+    for (uint32_t b = 0; b < n_blocks; ++b) { const uint32_t v = sums[b]; sums[b] = run; run += v; }
+    *total = run;
+}
+__global__ void __launch_bounds__(256) brick_scan_apply_kernel(size_t entries, uint32_t* __restrict__ base, const uint32_t* __restrict__ sums) {
+    __shared__ uint32_t part[256];
+    const size_t first = (size_t)blockIdx.x * 1024 + threadIdx.x * 4;
+    uint32_t c[4] = {0, 0, 0, 0};
+    for (int k = 0; k < 4; ++k)
+        if (first + k < entries) c[k] = base[first + k];
+    part[threadIdx.x] = c[0] + c[1] + c[2] + c[3];
+    __syncthreads();
+    if (threadIdx.x == 0) { // 256 partial sums: a serial exclusive scan by one thread is a few hundred cycles
+        uint32_t run = sums[blockIdx.x];
+        for (int k = 0; k < 256; ++k) { const uint32_t v = part[k]; part[k] = run; run += v; }
+    }
+    __syncthreads();
+    uint32_t run = part[threadIdx.x];
+    for (int k = 0; k < 4; ++k)
+        if (first + k < entries) { base[first + k] = run; run += c[k]; }
 }
 
-// `scratch`: (padded bricks + 31) / 32 words, zeroed
-cudaError_t launch_brick_dilate(uint32_t pbx, uint32_t pby, uint32_t pbz, uint32_t* l1, uint32_t* scratch, cudaStream_t stream) {
+// `scratch`: (entries + 1023) / 1024 + 1 words.  *total (device, scratch's last word) = number of bricks with voxels.
+cudaError_t launch_brick_finalize(uint32_t pbx, uint32_t pby, uint32_t pbz, uint32_t* codes, uint32_t* base, uint32_t* scratch,
+                                  cudaStream_t stream) {
     const size_t n = (size_t)pbx * pby * pbz;
-    brick_dilate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(pbx, pby, pbz, l1);
-    brick_dilate2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(pbx, pby, pbz, l1, scratch);
-    const size_t words = l1_words(n);
-    brick_encode_kernel<<<(unsigned)((words + 255) / 256), 256, 0, stream>>>(words, l1, scratch);
+    const size_t entries = dir_entries(n);
+    const uint32_t n_blocks = (uint32_t)((entries + 1023) / 1024);
+    brick_dilate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(pbx, pby, pbz, codes);
+    brick_encode_kernel<<<(unsigned)((entries + 255) / 256), 256, 0, stream>>>(pbx, pby, pbz, entries, codes, base);
+    brick_scan_sums_kernel<<<n_blocks, 256, 0, stream>>>(entries, base, scratch);
+    brick_scan_top_kernel<<<1, 32, 0, stream>>>(n_blocks, scratch, scratch + n_blocks);
+    brick_scan_apply_kernel<<<n_blocks, 256, 0, stream>>>(entries, base, scratch);
     return cudaGetLastError();
 }
 
-cudaError_t launch_brick_border(uint32_t pbx, uint32_t pby, uint32_t pbz, uint32_t* l1, uint32_t* table, cudaStream_t stream) {
-    const size_t n = (size_t)pbx * pby * pbz;
-    brick_border_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(pbx, pby, pbz, l1, table);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_brick_build(uint32_t kind, uint32_t seed, uint32_t w, uint32_t h, uint32_t d, const float* heights, uint32_t* l1,
-                               uint32_t* table, uint32_t* pool, uint32_t pool_capacity, uint32_t* counter, cudaStream_t stream) {
+cudaError_t launch_brick_build(uint32_t kind, uint32_t seed, uint32_t w, uint32_t h, uint32_t d, const float* heights, uint32_t* codes,
+                               const uint32_t* base, uint32_t* pool, uint32_t* counter, cudaStream_t stream) {
     const size_t bricks = (size_t)(w >> 3) * (h >> 3) * (d >> 3);
     const int threads = 128;
-    brick_build_kernel<<<(unsigned)((bricks + threads - 1) / threads), threads, 0, stream>>>(kind, seed, w, h, d, heights, l1, table, pool,
-                                                                                          pool_capacity, counter);
+    brick_build_kernel<<<(unsigned)((bricks + threads - 1) / threads), threads, 0, stream>>>(kind, seed, w, h, d, heights, codes, base, pool, counter);
     return cudaGetLastError();
 }
 
-// caller-supplied bricks: one thread per brick writes its table entry and l1 bit
+// caller-supplied bricks, pass 1: one thread per brick marks its code (bit 0); coordinates outside the volume are counted in *bad
 __global__ void brick_index_kernel(const uint32_t* __restrict__ coords, uint32_t n, uint32_t bx, uint32_t by, uint32_t bz,
-                                   uint32_t* __restrict__ l1, uint32_t* __restrict__ table, uint32_t* __restrict__ bad) {
+                                   uint32_t* __restrict__ codes, uint32_t* __restrict__ bad) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t x = coords[3 * i], y = coords[3 * i + 1], z = coords[3 * i + 2];
     if (x >= bx || y >= by || z >= bz) { atomicAdd(bad, 1u); return; }
-    const uint32_t b = brick_index(bx + 2, by + 2, x, y, z);
-    table[b] = i;
-    l1_set(l1, b, 0);
+    dir_set(codes, brick_index(bx + 2, by + 2, x, y, z), 0);
+}
+// pass 2 (after brick_finalize): the caller's occupancy words and colour move to the brick's slot (grid order)
+__global__ void brick_place_kernel(const uint32_t* __restrict__ coords, uint32_t n, uint32_t bx, uint32_t by,
+                                   const uint32_t* __restrict__ codes, const uint32_t* __restrict__ base, const uint32_t* __restrict__ masks, const uchar4* __restrict__ colors, uint32_t* __restrict__ pool,
+                                   uchar4* __restrict__ colors_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t bi = brick_index(bx + 2, by + 2, coords[3 * i], coords[3 * i + 1], coords[3 * i + 2]);
+    uint32_t entry;
+    dir_code(codes, bi, entry);
+    const uint32_t slot = dir_slot(base, bi, entry);
+    for (uint32_t wi = 0; wi < 16; ++wi) pool[(size_t)slot * 16 + wi] = masks[(size_t)i * 16 + wi];
+    colors_out[slot] = colors[i];
 }
 
-cudaError_t launch_brick_index(const uint32_t* coords, uint32_t n, uint32_t bx, uint32_t by, uint32_t bz, uint32_t* l1, uint32_t* table,
-                               uint32_t* bad, cudaStream_t stream) {
-    if (n) brick_index_kernel<<<(n + 127) / 128, 128, 0, stream>>>(coords, n, bx, by, bz, l1, table, bad);
+cudaError_t launch_brick_index(const uint32_t* coords, uint32_t n, uint32_t bx, uint32_t by, uint32_t bz, uint32_t* codes, uint32_t* bad,
+                               cudaStream_t stream) {
+    if (n) brick_index_kernel<<<(n + 127) / 128, 128, 0, stream>>>(coords, n, bx, by, bz, codes, bad);
+    return cudaGetLastError();
+}
+cudaError_t launch_brick_place(const uint32_t* coords, uint32_t n, uint32_t bx, uint32_t by, const uint32_t* codes, const uint32_t* base,
+                               const uint32_t* masks, const uchar4* colors, uint32_t* pool, uchar4* colors_out, cudaStream_t stream) {
+    if (n) brick_place_kernel<<<(n + 127) / 128, 128, 0, stream>>>(coords, n, bx, by, codes, base, masks, colors, pool, colors_out);
     return cudaGetLastError();
 }
 
@@ -253,8 +308,8 @@ cudaError_t launch_brick_index(const uint32_t* coords, uint32_t n, uint32_t bx, 
 // `stop` = 0x080808 in an empty brick; 0x202020 (bits that are never set: the test always fires) in a brick with
 // voxels, where every step needs its pool word; 0 in a brick whose neighbourhood is empty too (kSlotFree): such a
 // lane walks a whole burst through brick faces — the fields then range over 0..23 and say how many bricks it moved.
-// Only when the test fires is anything looked up: the brick's l1 pair, its slot if it has voxels (kSlotExit in the
-// border = the ray left the volume), one pool word per step inside such a brick.  Every fast-path iteration advances
+// Only when the test fires is anything looked up: the brick's directory entry (code 1, the border = the ray left the
+// volume; code 3 comes with the brick's pool slot), one pool word per step inside a brick with voxels.  Every fast-path iteration advances
 // >= 1 voxel, so the steps < W+H+D bound of :74 cannot bind before the ray is outside.
 struct BrickWalk {
     float sx, sy, sz;
@@ -281,7 +336,7 @@ struct BrickSlowState {
     float side[3];
     uint32_t steps, last;
 };
-__device__ __noinline__ int brick_walk_slow(const uint32_t* __restrict__ l1, const uint32_t* __restrict__ table,
+__device__ __noinline__ int brick_walk_slow(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ base,
                                             const uint32_t* __restrict__ pool, uint32_t pbx, uint32_t pby, uint32_t W, uint32_t H,
                                             uint32_t D, float d0, float d1, float d2, int32_t s0, int32_t s1, int32_t s2,
                                             BrickSlowState* io) {
@@ -291,8 +346,9 @@ __device__ __noinline__ int brick_walk_slow(const uint32_t* __restrict__ l1, con
     int status = 2;
     while (steps < W + H + D && (uint32_t)vx < W && (uint32_t)vy < H && (uint32_t)vz < D) { // :74-75
         const uint32_t bi = brick_index(pbx, pby, (uint32_t)vx >> 3, (uint32_t)vy >> 3, (uint32_t)vz >> 3);
-        if (l1_pair(l1, bi) == 3u) {
-            const uint32_t wv = __ldg(pool + ((size_t)__ldg(table + bi) << 4) + ((((uint32_t)vz & 7u) << 1) | (((uint32_t)vy & 7u) >> 2)));
+        uint32_t entry;
+        if (dir_code(codes, bi, entry) == 3u) {
+            const uint32_t wv = __ldg(pool + ((size_t)dir_slot(base, bi, entry) << 4) + ((((uint32_t)vz & 7u) << 1) | (((uint32_t)vy & 7u) >> 2)));
             if ((wv >> (((uint32_t)vx & 7u) | (((uint32_t)vy & 3u) << 3))) & 1u) { status = 1; break; } // :78-80
         }
         const bool m0 = sx <= vt_fmin(sy, sz); // :83
@@ -322,13 +378,13 @@ __device__ __forceinline__ int brick_walk_lookup(const BrickVolume& bv, BrickWal
         k.cell = k.cell + ((k.loc >> 3) & 0x3u) + ((k.loc >> 11) & 0x3u) * row + ((k.loc >> 19) & 0x3u) * plane - (1u + row + plane);
         k.loc = (k.loc & kLocLow) | kLocInside;
         const uint32_t bi = k.cell;
-        const uint32_t pr = l1_pair(bv.l1, bi);
-        const bool occ = pr == 3u;
-        k.slot = occ ? __ldg(bv.table + bi) : (pr == 2u ? kSlotEmpty : kSlotFree);
-        k.stop = occ ? kLocAlways : (pr == 2u ? kLocInside : 0u);
-        if (k.slot == kSlotExit) return 2;
+        uint32_t entry;
+        const uint32_t code = dir_code(bv.codes, bi, entry);
+        k.slot = code == 3u ? dir_slot(bv.base, bi, entry) : (code == 0u ? kSlotFree : kSlotEmpty);
+        k.stop = code == 3u ? kLocAlways : (code == 0u ? 0u : kLocInside);
+        if (code == 1u) return 2; // the border: outside the volume
     }
-    if (k.slot < kSlotExit) {
+    if (k.slot < kSlotFree) {
         const uint32_t lx = k.loc & 7u, ly = (k.loc >> 8) & 7u, lz = (k.loc >> 16) & 7u;
         const uint32_t wv = __ldg(bv.pool + ((size_t)k.slot << 4) + ((lz << 1) | (ly >> 2)));
         if ((wv >> (lx | ((ly & 3u) << 3))) & 1u) {
@@ -370,7 +426,7 @@ __device__ __forceinline__ int brick_walk_begin(const BrickVolume& bv, uint32_t 
         BrickSlowState io;
 #pragma unroll
         for (int c = 0; c < 3; ++c) { io.v[c] = r.v[c]; io.side[c] = r.side[c]; }
-        status = brick_walk_slow(bv.l1, bv.table, bv.pool, bv.bx, bv.by, W, H, D, r.delta[0], r.delta[1], r.delta[2], r.step[0],
+        status = brick_walk_slow(bv.codes, bv.base, bv.pool, bv.bx, bv.by, W, H, D, r.delta[0], r.delta[1], r.delta[2], r.step[0],
                                  r.step[1], r.step[2], &io);
         // park the finished ray in the packed state (clamped: the voxel of a miss is never read)
         r.v[0] = max(-8, min(io.v[0], (int32_t)W + 7)); r.v[1] = max(-8, min(io.v[1], (int32_t)H + 7)); r.v[2] = max(-8, min(io.v[2], (int32_t)D + 7));
@@ -387,11 +443,11 @@ __device__ __forceinline__ int brick_walk_begin(const BrickVolume& bv, uint32_t 
     // no current brick yet: look the start brick up (the same code as after crossing a face, with no face crossed)
     if (status == 0) {
         const uint32_t bi = k.cell;
-        const uint32_t pr = l1_pair(bv.l1, bi);
-        const bool occ = pr == 3u;
-        k.slot = occ ? __ldg(bv.table + bi) : (pr == 2u ? kSlotEmpty : kSlotFree);
-        k.stop = occ ? kLocAlways : (pr == 2u ? kLocInside : 0u);
-        status = k.slot == kSlotExit ? 2 : brick_walk_lookup(bv, k);
+        uint32_t entry;
+        const uint32_t code = dir_code(bv.codes, bi, entry);
+        k.slot = code == 3u ? dir_slot(bv.base, bi, entry) : (code == 0u ? kSlotFree : kSlotEmpty);
+        k.stop = code == 3u ? kLocAlways : (code == 0u ? 0u : kLocInside);
+        status = code == 1u ? 2 : brick_walk_lookup(bv, k);
     } else {
         k.slot = kSlotEmpty;
         k.stop = kLocInside;

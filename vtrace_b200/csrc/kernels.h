@@ -34,15 +34,15 @@ struct VolumeDesc {
 
 // Large procedural volumes (extension; §8f rank 2): occupancy only, as a
 // two-level sparse structure; colours are a function of the voxel position.
-//   l1    : two bits per 8^3 brick: 3 = the brick has at least one filled voxel, or lies in the border; 2 = a neighbour does;
-//           1 = a brick two away does; 0 = nothing within two bricks (1 / 0: the walk needs no lookup for one / two bursts)
-//   table : per brick, its slot in `pool` (only meaningful where the l1 bit is set); 0xFFFFFFFE in the border
-// The brick grid is stored padded by one brick on every side; the border says "outside the volume".
-//   pool  : 16 words per non-empty brick; voxel (x,y,z) of a brick is bit (x | (y&3) << 3) of
-//           word ((z&7) << 1 | (y&7) >> 2)
+//   codes : one word per 16 consecutive bricks of the padded brick grid = 16 two-bit codes (3 = the brick has at least one
+//           filled voxel, 2 = it has none but a brick of its 3x3x3 neighbourhood has or is outside, 1 = the brick lies in the
+//           one-brick border = outside the volume, 0 = nothing within one brick: the walk needs no lookup for a whole burst)
+//   base  : per such entry, the number of 3-codes in all earlier entries
+//   pool  : 16 words per non-empty brick, in grid order (slot = base + number of 3-codes before the brick in its entry); voxel (x,y,z) of a brick is bit (x | (y&3) << 3) of word ((z&7) << 1 | (y&7) >> 2)
+// The brick grid is stored padded by one brick on every side.
 struct BrickVolume {
-    const uint32_t* l1;
-    const uint32_t* table;
+    const uint32_t* codes;
+    const uint32_t* base;
     const uint32_t* pool;
     const float* heights;  // heightmap kind: w*d column heights
     const uchar4* colors;  // uploaded bricks: one RGBA colour per pool slot
@@ -180,16 +180,19 @@ cudaError_t launch_world_grid(const InstUniforms* inst, uint32_t n_inst, float* 
 cudaError_t launch_trace_paths(const FrameParams& fp, const InstUniforms* inst, BinTable bins, WorldGridTable wg, const uint32_t* mask_arena,
                                uint32_t arena_words, bool masks_in_smem, SrgbTables lut, FrameBuffers fb,
                                int sm_count, cudaStream_t stream);
-// procedural brick volumes: column heights, then count / fill passes over all bricks
+// procedural brick volumes: column heights; mark + count the bricks with voxels (pool == nullptr); finish the directory
+// (launch_brick_finalize: neighbourhood codes, border, slot bases; scratch = entries / 1024 + 2 words, its last used word
+// receives the number of bricks with voxels); then fill the pool
 cudaError_t launch_heightmap(float* heights, uint32_t w, uint32_t h, uint32_t d, uint32_t seed, cudaStream_t stream);
-cudaError_t launch_brick_build(uint32_t kind, uint32_t seed, uint32_t w, uint32_t h, uint32_t d, const float* heights, uint32_t* l1,
-                               uint32_t* table, uint32_t* pool, uint32_t pool_capacity, uint32_t* counter, cudaStream_t stream);
-// caller-supplied bricks: coords (n x 3) -> table / l1 entries (the masks are already the pool)
-cudaError_t launch_brick_border(uint32_t pbx, uint32_t pby, uint32_t pbz, uint32_t* l1, uint32_t* table, cudaStream_t stream);
-// after every occupied / border brick has its bit 0: bit 1 of the 3x3x3 neighbourhoods
-cudaError_t launch_brick_dilate(uint32_t pbx, uint32_t pby, uint32_t pbz, uint32_t* l1, uint32_t* scratch, cudaStream_t stream);
-cudaError_t launch_brick_index(const uint32_t* coords, uint32_t n, uint32_t bx, uint32_t by, uint32_t bz, uint32_t* l1, uint32_t* table,
-                               uint32_t* bad, cudaStream_t stream);
+cudaError_t launch_brick_build(uint32_t kind, uint32_t seed, uint32_t w, uint32_t h, uint32_t d, const float* heights, uint32_t* codes,
+                               const uint32_t* base, uint32_t* pool, uint32_t* counter, cudaStream_t stream);
+cudaError_t launch_brick_finalize(uint32_t pbx, uint32_t pby, uint32_t pbz, uint32_t* codes, uint32_t* base, uint32_t* scratch,
+                                  cudaStream_t stream);
+// caller-supplied bricks: coords (n x 3) -> codes; after launch_brick_finalize the masks / colours move to their slots
+cudaError_t launch_brick_index(const uint32_t* coords, uint32_t n, uint32_t bx, uint32_t by, uint32_t bz, uint32_t* codes, uint32_t* bad,
+                               cudaStream_t stream);
+cudaError_t launch_brick_place(const uint32_t* coords, uint32_t n, uint32_t bx, uint32_t by, const uint32_t* codes, const uint32_t* base,
+                               const uint32_t* masks, const uchar4* colors, uint32_t* pool, uchar4* colors_out, cudaStream_t stream);
 // incoherent-ray mode: rays [first, first + n) through instance 0's volume
 cudaError_t launch_trace_rays(const FrameParams& fp, const InstUniforms* inst, const uint32_t* mask_arena, unsigned long long n,
                               unsigned long long first, FrameBuffers fb, int sm_count, cudaStream_t stream);

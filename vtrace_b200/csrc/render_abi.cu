@@ -36,7 +36,7 @@ struct State {
     bool vols_dirty = false;
     uint32_t* d_arena = nullptr; // all stop masks, contiguous
     uint32_t arena_words = 0, arena_cap = 0;
-    struct BrickAlloc { uint32_t* l1; uint32_t* table; uint32_t* pool; float* heights; uchar4* colors; BrickVolume* d_desc; };
+    struct BrickAlloc { uint32_t* codes; uint32_t* base; uint32_t* pool; float* heights; uchar4* colors; BrickVolume* d_desc; };
     std::vector<BrickAlloc> brick_allocs; // procedural volumes (extension)
     bool any_bricks = false;
     uint32_t max_idx_bits = 0; // widest stop-mask index of any dense volume (the wavefront kernel packs it into 30 bits)
@@ -809,30 +809,25 @@ extern "C" int32_t vt_add_volume_procedural(uint32_t kind, uint32_t width, uint3
     // the brick grid is stored with a one-brick border that marks "outside" (kernels.h, BrickVolume)
     const uint32_t pbx = (width >> 3) + 2, pby = (height >> 3) + 2, pbz = (depth >> 3) + 2;
     const size_t padded = (size_t)pbx * pby * pbz;
-    CK(cudaMalloc(&a.l1, ((padded + 15) / 16) * 4)); // two bits per brick
-    CK(cudaMalloc(&a.table, padded * 4));
-    CK(cudaMemsetAsync(a.l1, 0, ((padded + 15) / 16) * 4, g.stream));
-    CK(launch_brick_border(pbx, pby, pbz, a.l1, a.table, g.stream));
-    g.stats.launches += 1;
-    // pass 1 counts the non-empty bricks, pass 2 fills the pool
+    const size_t entries = (padded + 15) / 16, scan_words = (entries + 1023) / 1024 + 2;
+    uint32_t* scratch = nullptr;
+    CK(cudaMalloc(&a.codes, entries * 4));
+    CK(cudaMalloc(&a.base, entries * 4));
+    CK(cudaMalloc(&scratch, scan_words * 4));
+    CK(cudaMemsetAsync(a.codes, 0, entries * 4, g.stream));
+    // pass 1 marks and counts the bricks with voxels, the directory is finished, pass 2 fills the pool in grid order
     CK(cudaMemsetAsync(d_counter, 0, 4, g.stream));
-    CK(launch_brick_build(kind, seed, width, height, depth, a.heights, a.l1, a.table, nullptr, 0, d_counter, g.stream));
+    CK(launch_brick_build(kind, seed, width, height, depth, a.heights, a.codes, a.base, nullptr, d_counter, g.stream));
     CK(cudaMemcpyAsync(&n, d_counter, 4, cudaMemcpyDeviceToHost, g.stream));
+    CK(launch_brick_finalize(pbx, pby, pbz, a.codes, a.base, scratch, g.stream));
     CK(cudaStreamSynchronize(g.stream));
     CK(cudaMalloc(&a.pool, (size_t)(n ? n : 1) * 64));
-    CK(cudaMemsetAsync(d_counter, 0, 4, g.stream));
-    CK(launch_brick_build(kind, seed, width, height, depth, a.heights, a.l1, a.table, a.pool, n, d_counter, g.stream));
-    {
-        uint32_t* scratch = nullptr;
-        CK(cudaMalloc(&scratch, ((padded + 31) / 32) * 4));
-        CK(cudaMemsetAsync(scratch, 0, ((padded + 31) / 32) * 4, g.stream));
-        CK(launch_brick_dilate(pbx, pby, pbz, a.l1, scratch, g.stream));
-        CK(cudaStreamSynchronize(g.stream));
-        cudaFree(scratch);
-    }
-    g.stats.launches += 5;
+    CK(launch_brick_build(kind, seed, width, height, depth, a.heights, a.codes, a.base, a.pool, d_counter, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    cudaFree(scratch);
+    g.stats.launches += 7;
     BrickVolume bv{};
-    bv.l1 = a.l1; bv.table = a.table; bv.pool = a.pool; bv.heights = a.heights; bv.colors = nullptr;
+    bv.codes = a.codes; bv.base = a.base; bv.pool = a.pool; bv.heights = a.heights; bv.colors = nullptr;
     bv.kind = kind; bv.seed = seed;
     bv.bx = pbx; bv.by = pby; bv.bz = pbz;
     bv.n_bricks = n;
@@ -879,39 +874,42 @@ extern "C" int32_t vt_add_volume_bricks(const uint32_t* brick_coords, const uint
     uint32_t bad = 0;
     const uint32_t pbx = (width >> 3) + 2, pby = (height >> 3) + 2, pbz = (depth >> 3) + 2;
     const size_t padded = (size_t)pbx * pby * pbz;
-    CK(cudaMalloc(&a.l1, ((padded + 15) / 16) * 4)); // two bits per brick
-    CK(cudaMalloc(&a.table, padded * 4));
+    const size_t entries = (padded + 15) / 16, scan_words = (entries + 1023) / 1024 + 2;
+    uint32_t* scratch = nullptr;
+    uint32_t* d_masks = nullptr;
+    uchar4* d_colors = nullptr;
+    CK(cudaMalloc(&a.codes, entries * 4));
+    CK(cudaMalloc(&a.base, entries * 4));
+    CK(cudaMalloc(&scratch, scan_words * 4));
     CK(cudaMalloc(&a.pool, n1 * 64));
     CK(cudaMalloc(&a.colors, n1 * 4));
+    CK(cudaMalloc(&d_masks, n1 * 64));
+    CK(cudaMalloc(&d_colors, n1 * 4));
     CK(cudaMalloc(&d_coords, n1 * 12));
     CK(cudaMalloc(&d_bad, 4));
-    CK(cudaMemsetAsync(a.l1, 0, ((padded + 15) / 16) * 4, g.stream));
-    CK(launch_brick_border(pbx, pby, pbz, a.l1, a.table, g.stream));
+    CK(cudaMemsetAsync(a.codes, 0, entries * 4, g.stream));
     CK(cudaMemsetAsync(d_bad, 0, 4, g.stream));
     // the inputs are only borrowed for the call (like add_texture's): synchronous copies
-    CK(cudaMemcpy(a.pool, masks, n_bricks * 64, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(a.colors, colors, n_bricks * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_masks, masks, n_bricks * 64, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_colors, colors, n_bricks * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_coords, brick_coords, n_bricks * 12, cudaMemcpyHostToDevice));
-    CK(launch_brick_index(d_coords, (uint32_t)n_bricks, width >> 3, height >> 3, depth >> 3, a.l1, a.table, d_bad, g.stream));
-    {
-        uint32_t* scratch = nullptr;
-        CK(cudaMalloc(&scratch, ((padded + 31) / 32) * 4));
-        CK(cudaMemsetAsync(scratch, 0, ((padded + 31) / 32) * 4, g.stream));
-        CK(launch_brick_dilate(pbx, pby, pbz, a.l1, scratch, g.stream));
-        CK(cudaStreamSynchronize(g.stream));
-        cudaFree(scratch);
-    }
+    // mark the bricks, finish the directory, then move every brick's words and colour to its slot (grid order)
+    CK(launch_brick_index(d_coords, (uint32_t)n_bricks, width >> 3, height >> 3, depth >> 3, a.codes, d_bad, g.stream));
     CK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
-    cudaFree(d_coords);
-    cudaFree(d_bad);
-    g.stats.launches += 2;
+    if (!bad) {
+        CK(launch_brick_finalize(pbx, pby, pbz, a.codes, a.base, scratch, g.stream));
+        CK(launch_brick_place(d_coords, (uint32_t)n_bricks, width >> 3, height >> 3, a.codes, a.base, d_masks, d_colors, a.pool, a.colors, g.stream));
+        CK(cudaStreamSynchronize(g.stream));
+    }
+    cudaFree(d_coords); cudaFree(d_bad); cudaFree(d_masks); cudaFree(d_colors); cudaFree(scratch);
+    g.stats.launches += 7;
     if (bad) {
-        cudaFree(a.l1); cudaFree(a.table); cudaFree(a.pool); cudaFree(a.colors);
+        cudaFree(a.codes); cudaFree(a.base); cudaFree(a.pool); cudaFree(a.colors);
         return fail("vt_add_volume_bricks: %u brick coordinates outside the volume", bad);
     }
     BrickVolume bv{};
-    bv.l1 = a.l1; bv.table = a.table; bv.pool = a.pool; bv.heights = nullptr; bv.colors = a.colors;
+    bv.codes = a.codes; bv.base = a.base; bv.pool = a.pool; bv.heights = nullptr; bv.colors = a.colors;
     bv.kind = kVolumeUploadedBricks; bv.seed = 0;
     bv.bx = pbx; bv.by = pby; bv.bz = pbz;
     bv.n_bricks = (uint32_t)n_bricks;
@@ -979,7 +977,7 @@ extern "C" void cleanup(void) {
     g.fused_mode = 0;
     for (auto& v : g.vols) cudaFree(const_cast<uint8_t*>(v.rgba));
     g.vols.clear();
-    for (auto& b : g.brick_allocs) { cudaFree(b.l1); cudaFree(b.table); cudaFree(b.pool); cudaFree(b.heights); cudaFree(b.colors); cudaFree(b.d_desc); }
+    for (auto& b : g.brick_allocs) { cudaFree(b.codes); cudaFree(b.base); cudaFree(b.pool); cudaFree(b.heights); cudaFree(b.colors); cudaFree(b.d_desc); }
     g.brick_allocs.clear();
     cudaFree(g.d_vols); cudaFree(g.d_arena); cudaFree(g.d_inst); cudaFree(g.d_iu); cudaFree(g.d_dec); cudaFree(g.d_thr);
     if (g.copy_stream) { cudaStreamSynchronize(g.copy_stream); cudaStreamDestroy(g.copy_stream); cudaEventDestroy(g.ev_color_ready); cudaEventDestroy(g.ev_copy_done[0]); cudaEventDestroy(g.ev_copy_done[1]); }
