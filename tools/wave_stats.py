@@ -27,8 +27,12 @@ with Renderer() as r:
     fn = lib.vt_debug_wave_stats
     fn.restype, fn.argtypes = C.c_int, [C.c_void_p]
     out = np.zeros(32, dtype=np.uint64)
+    ft = lib.vt_debug_wave_times
+    ft.restype, ft.argtypes = C.c_int, [C.c_void_p]
+    times = np.zeros(192, dtype=np.uint32)
     assert r.render_tick_raw(P, V)
     fn(out.ctypes.data)  # (drop the first frame)
+    ft(times.ctypes.data)
     assert r.render_tick_raw(P, V)
     assert fn(out.ctypes.data) == 0
     s = [int(x) for x in out]
@@ -41,3 +45,8 @@ with Renderer() as r:
     tot = sum(s[12:21])
     print("ray length histogram (fast-path rays that ended in a march):", ", ".join(
         f"{n}: {100 * s[12 + k] / max(tot, 1):.1f}%" for k, n in enumerate(["0", "1", "2", "3", "4-7", "8-15", "16-31", "32-63", "64+"])))
+    assert ft(times.ctypes.data) == 0
+    for name, h in (("first item claimed", times[128:192]), ("work exhausted", times[0:64]), ("warp finished", times[64:128])):
+        nz = np.nonzero(h)[0]
+        print(f"{name:18s} (5 us buckets since the warp started, warps):", " ".join(f"{5 * b}us:{h[b]}" for b in nz))
+    print("kernel ms", r.stats().last_trace_ms)

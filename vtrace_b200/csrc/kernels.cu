@@ -1679,6 +1679,12 @@ cudaError_t read_wave_stats(unsigned long long* out16) {
     unsigned long long zero[32] = {};
     return cudaMemcpyToSymbol(vt_wave_stats, zero, sizeof zero);
 }
+cudaError_t read_wave_times(unsigned int* out192) {
+    cudaError_t e = cudaMemcpyFromSymbol(out192, vt_wave_times, 192 * sizeof(unsigned int));
+    if (e != cudaSuccess) return e;
+    unsigned int zero[192] = {};
+    return cudaMemcpyToSymbol(vt_wave_times, zero, sizeof zero);
+}
 #endif
 
 cudaError_t launch_resolve(const unsigned long long* accum, uint32_t n_pixels, uint32_t total_spp, SrgbTables lut, uchar4* color,

@@ -64,7 +64,13 @@ static_assert(kPoolBytes % 16 == 0, "pool alignment");
 // -DVT_WAVE_STATS (variant builds only): per-phase counters, read with vt_debug_wave_stats()
 #ifdef VT_WAVE_STATS
 __device__ unsigned long long vt_wave_stats[32];
+__device__ unsigned int vt_wave_times[3 * 64]; // histograms (5 us buckets since the warp started): work exhausted, finished, first item claimed
 #define VT_STAT(i, v) (wstat[i] += (v))
+__device__ __forceinline__ unsigned long long wave_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 #else
 #define VT_STAT(i, v) ((void)0)
 #endif
@@ -232,6 +238,8 @@ __global__ void __launch_bounds__(kWaveThreads, kWaveCtas) trace_paths_wave_kern
     for (int c = 0; c < 3; ++c) sky_q[c] = __float2ull_rz((1.0f * sky[c]) * 16777216.0f);
     unsigned long long rays = 0, iters = 0, analytic = 0;
 #ifdef VT_WAVE_STATS
+    const unsigned long long t_start = wave_timer_ns();
+    unsigned long long t_exhausted = 0, t_first = 0;
     uint32_t wstat[32];
     for (int i = 0; i < 32; ++i) wstat[i] = 0;
 #endif
@@ -392,6 +400,10 @@ __global__ void __launch_bounds__(kWaveThreads, kWaveCtas) trace_paths_wave_kern
         // ---- make sure there is a work item with jobs (or learn that the frame is exhausted) ------
         while (work_left && it_next >= it_njobs) {
             const int item = claim_tiles(fb.stats + 2, lane, 1);
+#ifdef VT_WAVE_STATS
+            if (item >= n_items && !t_exhausted) t_exhausted = wave_timer_ns();
+            if (item < n_items && !t_first) t_first = wave_timer_ns();
+#endif
             if (item >= n_items) { work_left = false; break; }
             flush_tile();
             const int chunk = item / cov_tiles, ct = item - chunk * cov_tiles; // chunk-major: a tile's chunks are spread in time
@@ -669,8 +681,14 @@ __global__ void __launch_bounds__(kWaveThreads, kWaveCtas) trace_paths_wave_kern
         analytic += __shfl_xor_sync(0xffffffffu, analytic, o);
     }
 #ifdef VT_WAVE_STATS
-    if (lane == 0)
+    if (lane == 0) {
         for (int i = 0; i < 32; ++i) atomicAdd(&vt_wave_stats[i], (unsigned long long)wstat[i]);
+        const unsigned long long t_end = wave_timer_ns();
+        auto bucket = [&](unsigned long long t) { const unsigned long long b = (t - t_start) / 5000ull; return (int)(b > 63 ? 63 : b); };
+        atomicAdd(&vt_wave_times[bucket(t_exhausted ? t_exhausted : t_end)], 1u);
+        atomicAdd(&vt_wave_times[64 + bucket(t_end)], 1u);
+        atomicAdd(&vt_wave_times[128 + bucket(t_first ? t_first : t_end)], 1u);
+    }
 #endif
     if (lane == 0) {
         if (rays) atomicAdd(fb.stats + 0, rays);
