@@ -183,7 +183,7 @@ __global__ void instance_setup_kernel(const float* __restrict__ instances, uint3
     }
     if (i == 0 && flag) { // fused multi-GPU accumulation, root: "the previous frame is consumed" (see flag_wait below)
         __threadfence_system();
-        *reinterpret_cast<volatile uint32_t*>(flag) = flag_value;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(flag_value) : "memory");
     }
     if (i >= n) return;
     float M[16], Mi[16];
@@ -1449,11 +1449,19 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 }
 
 // spins until *flag has reached `target` (sequence numbers compared modulo 2^32)
+// (acquire / release at system scope: the flags live in another GPU's memory, the data they guard travels over NVLink)
+__device__ __forceinline__ uint32_t flag_load_acquire(const uint32_t* flag) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    return v;
+}
+__device__ __forceinline__ void flag_store_release(uint32_t* flag, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(v) : "memory");
+}
 __device__ __forceinline__ void flag_wait(const uint32_t* flag, uint32_t target, uint32_t* err) {
-    const volatile uint32_t* f = flag;
-    if ((int32_t)(*f - target) >= 0) return;
+    if ((int32_t)(flag_load_acquire(flag) - target) >= 0) return;
     const unsigned long long t0 = global_timer_ns();
-    while ((int32_t)(*f - target) < 0) {
+    while ((int32_t)(flag_load_acquire(flag) - target) < 0) {
         __nanosleep(256);
         if (global_timer_ns() - t0 > kFlagWaitLimitNs) { atomicExch(err, 1u); break; }
     }
@@ -1462,6 +1470,7 @@ __device__ __forceinline__ void flag_wait(const uint32_t* flag, uint32_t target,
 __device__ __forceinline__ void fused_sync_begin(const FusedSync& fs) {
     if (fs.wait_flags) {
         if (threadIdx.x < fs.wait_count) flag_wait(fs.wait_flags + threadIdx.x, fs.wait_target, fs.err);
+        __threadfence_system(); // the waiting threads' acquire, made cumulative for the block by the barrier
         __syncthreads();
     }
 }
@@ -1473,7 +1482,7 @@ __device__ __forceinline__ void fused_sync_end(const FusedSync& fs) {
             if (atomicAdd(fs.done_counter, 1u) == gridDim.x - 1) { // last block
                 *fs.done_counter = 0u;
                 __threadfence_system();
-                *reinterpret_cast<volatile uint32_t*>(fs.signal_flag) = fs.signal_value;
+                flag_store_release(fs.signal_flag, fs.signal_value);
             }
         }
     }
