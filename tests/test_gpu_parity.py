@@ -263,6 +263,30 @@ def test_rotated_scaled_instances(scene, assets):
     scene.check_primary(P, V, 512, 384, what="rotated/scaled")
 
 
+def test_instances_straddling_the_eye_plane(scene, assets):
+    """Screen rectangles of proxy cubes that reach behind the eye plane (instance_setup_kernel cuts them at w = eps instead
+    of giving up on the whole screen): cameras in the middle of the entity grid, next to a cube face (whole-screen
+    fallback), below the grid looking up, and a rotated / stretched instance that passes the camera on one side.  Primary
+    records, depth and colour as well as path-traced radiance sums must still be the oracle's, bit for bit."""
+    a = scene.add(assets["Treasure"])
+    b = scene.add(assets["AncientTemple"])
+    models = _grid_models(a, b)
+    long_box = glm.scale(glm.rotate(glm.translate(glm.identity(), (0.6, -3.2, 0.4)), 0.5, (0.2, 1.0, 0.3)), (9.0, 0.8, 0.6))
+    models.append((long_box, b))
+    scene.set_instances(models)
+    w, h = 320, 200
+    P = glm.perspective(glm.REFERENCE_FOV, w / h, glm.REFERENCE_NEAR, glm.REFERENCE_FAR)
+    cams = [((0.0, -4.2, 0.0), (4.0, -5.2, 3.0)),      # just above the cubes, grazing view across the grid
+            ((0.75, -5.0, 0.75), (6.0, -5.0, 0.8)),    # between four cubes, at their height
+            ((0.0, -5.0, 0.52), (0.0, -5.0, 3.0)),     # 0.02 in front of a cube face
+            ((2.0, -8.0, 1.0), (0.0, -3.0, 0.0)),      # on the other side of the grid, looking back through it
+            ((0.6, -3.2, 1.2), (0.7, -3.1, -4.0))]     # the long box passes on both sides of the camera
+    for i, (eye, center) in enumerate(cams):
+        V = glm.look_at(eye, center, (0.0, 1.0, 0.0))
+        scene.check_primary(P, V, w, h, what=f"straddling cubes, camera {i}, primary")
+        scene.check_paths(P, V, w, h, spp=2, bounces=3, what=f"straddling cubes, camera {i}, paths")
+
+
 # ---- large-scene extension: shadow rays, procedural brick volumes, incoherent rays --------------
 
 def test_shadow_rays_on_dense_volumes(scene, assets):

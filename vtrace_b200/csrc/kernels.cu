@@ -244,30 +244,85 @@ __global__ void instance_setup_kernel(const float* __restrict__ instances, uint3
         }
         I.pad1[0] = I.pad1[1] = 0;
     }
-    // Conservative screen rectangle of the proxy cube (what the rasteriser would bin): project the 8
-    // corners, +-2 pixels of slack.  Any corner at or behind the eye plane -> whole screen.  A pixel
-    // outside the rectangle cannot be covered for any sample position inside it, so the trace kernels
-    // may skip the instance (and, when no instance remains, the pixel) without changing any result.
+    // Conservative screen rectangle of the proxy cube (what the rasteriser would bin): project the 8 corners, +-2 pixels of
+    // slack.  A pixel outside the rectangle cannot be covered for any sample position inside it, so the trace kernels may
+    // skip the instance (and, when no instance remains, the pixel) without changing any result.
+    // A cube that reaches behind the eye plane (w <= 0) is first cut at w = eps: what lies in 0 < w < eps can only be seen
+    // by an on-screen pixel if |x|, |y| <= w < eps in clip space, i.e. within |A^-1|_inf * eps of the centre of projection
+    // e (A = rows x, y, w of MVP, A e = -t) — and eps is chosen as half of what the cube's distance from e allows.  Eye
+    // inside or next to the cube, or no centre of projection (singular A): whole screen.
     float minx = INFINITY, maxx = -INFINITY, miny = INFINITY, maxy = -INFINITY;
-    bool whole = false;
+    bool whole = false, cut = false;
+    float cX[8], cY[8], cW[8], wmin = INFINITY;
     for (int c = 0; c < 8; ++c) {
         const float cx = (c & 1) ? 0.5f : -0.5f, cy = (c & 2) ? 0.5f : -0.5f, cz = (c & 4) ? 0.5f : -0.5f;
-        const float X = ((I.MVP[0] * cx + I.MVP[4] * cy) + I.MVP[8] * cz) + I.MVP[12];
-        const float Y = ((I.MVP[1] * cx + I.MVP[5] * cy) + I.MVP[9] * cz) + I.MVP[13];
-        const float W = ((I.MVP[3] * cx + I.MVP[7] * cy) + I.MVP[11] * cz) + I.MVP[15];
-        if (!(W > 1e-6f)) { whole = true; break; }
-        const float fx = (X / W + 1.0f) / fp.sxn, fy = (Y / W + 1.0f) / fp.syn;
-        if (!(fx == fx) || !(fy == fy)) { whole = true; break; }
-        minx = fminf(minx, fx); maxx = fmaxf(maxx, fx);
-        miny = fminf(miny, fy); maxy = fmaxf(maxy, fy);
+        cX[c] = ((I.MVP[0] * cx + I.MVP[4] * cy) + I.MVP[8] * cz) + I.MVP[12];
+        cY[c] = ((I.MVP[1] * cx + I.MVP[5] * cy) + I.MVP[9] * cz) + I.MVP[13];
+        cW[c] = ((I.MVP[3] * cx + I.MVP[7] * cy) + I.MVP[11] * cz) + I.MVP[15];
+        wmin = fminf(wmin, cW[c]);
+        if (!(cW[c] == cW[c])) whole = true;
+    }
+    float eps = 1e-6f, slack = 2.0f;
+    if (!whole && !(wmin > 1e-6f)) {
+        const float a00 = I.MVP[0], a01 = I.MVP[4], a02 = I.MVP[8], a10 = I.MVP[1], a11 = I.MVP[5], a12 = I.MVP[9];
+        const float a20 = I.MVP[3], a21 = I.MVP[7], a22 = I.MVP[11];
+        const float c00 = a11 * a22 - a12 * a21, c01 = a12 * a20 - a10 * a22, c02 = a10 * a21 - a11 * a20;
+        const float det = (a00 * c00 + a01 * c01) + a02 * c02;
+        const float id = 1.0f / det;
+        // rows of A^-1
+        const float r0[3] = {c00 * id, (a02 * a21 - a01 * a22) * id, (a01 * a12 - a02 * a11) * id};
+        const float r1[3] = {c01 * id, (a00 * a22 - a02 * a20) * id, (a02 * a10 - a00 * a12) * id};
+        const float r2[3] = {c02 * id, (a01 * a20 - a00 * a21) * id, (a00 * a11 - a01 * a10) * id};
+        const float t[3] = {I.MVP[12], I.MVP[13], I.MVP[15]};
+        const float e0 = -((r0[0] * t[0] + r0[1] * t[1]) + r0[2] * t[2]);
+        const float e1 = -((r1[0] * t[0] + r1[1] * t[1]) + r1[2] * t[2]);
+        const float e2 = -((r2[0] * t[0] + r2[1] * t[1]) + r2[2] * t[2]);
+        const float dinf = fmaxf(fmaxf(fabsf(e0), fabsf(e1)), fabsf(e2)) - 0.5f;
+        const float n0 = (fabsf(r0[0]) + fabsf(r0[1])) + fabsf(r0[2]);
+        const float n1 = (fabsf(r1[0]) + fabsf(r1[1])) + fabsf(r1[2]);
+        const float n2 = (fabsf(r2[0]) + fabsf(r2[1])) + fabsf(r2[2]);
+        eps = 0.5f * dinf / fmaxf(fmaxf(n0, n1), n2);
+        if (!(eps >= 1e-2f) || !(eps < INFINITY)) {
+            whole = true;
+        } else {
+            cut = true;
+            // rounding of a cut point's x and y, magnified by 1 / eps, in pixels (generous)
+            const float sx = ((fabsf(a00) + fabsf(a01)) + fabsf(a02)) + fabsf(t[0]);
+            const float sy = ((fabsf(a10) + fabsf(a11)) + fabsf(a12)) + fabsf(t[1]);
+            slack += 16.0f * 1.1920929e-7f * fmaxf(sx / fp.sxn, sy / fp.syn) / eps;
+        }
+    }
+    bool any = false;
+    if (!whole) {
+        auto add = [&](float X, float Y, float W) {
+            const float fx = (X / W + 1.0f) / fp.sxn, fy = (Y / W + 1.0f) / fp.syn;
+            if (!(fx == fx) || !(fy == fy)) { whole = true; return; }
+            minx = fminf(minx, fx); maxx = fmaxf(maxx, fx);
+            miny = fminf(miny, fy); maxy = fmaxf(maxy, fy);
+            any = true;
+        };
+        for (int c = 0; c < 8; ++c)
+            if (!cut || cW[c] >= eps) add(cX[c], cY[c], cW[c]);
+        if (cut) {
+            for (int c = 0; c < 8; ++c)
+                for (int ax = 1; ax < 8; ax <<= 1) {
+                    if (c & ax) continue;
+                    const int d = c | ax;
+                    if ((cW[c] >= eps) == (cW[d] >= eps)) continue;
+                    const float sp = (eps - cW[c]) / (cW[d] - cW[c]);
+                    add(cX[c] + sp * (cX[d] - cX[c]), cY[c] + sp * (cY[d] - cY[c]), eps);
+                }
+        }
     }
     if (whole) {
         I.bounds[0] = 0; I.bounds[1] = fp.width - 1; I.bounds[2] = 0; I.bounds[3] = fp.height - 1;
+    } else if (!any) { // entirely behind the eye plane
+        I.bounds[0] = 1; I.bounds[1] = 0; I.bounds[2] = 1; I.bounds[3] = 0;
     } else {
         const float lim = 1.0e9f;
-        minx = fmaxf(minx, -lim); maxx = fminf(maxx, lim); miny = fmaxf(miny, -lim); maxy = fminf(maxy, lim);
-        int x0 = __float2int_rd(minx) - 2, x1 = __float2int_rd(maxx) + 2;
-        int y0 = __float2int_rd(miny) - 2, y1 = __float2int_rd(maxy) + 2;
+        minx = fmaxf(minx - slack, -lim); maxx = fminf(maxx + slack, lim); miny = fmaxf(miny - slack, -lim); maxy = fminf(maxy + slack, lim);
+        int x0 = __float2int_rd(minx), x1 = __float2int_rd(maxx);
+        int y0 = __float2int_rd(miny), y1 = __float2int_rd(maxy);
         I.bounds[0] = x0 < 0 ? 0 : x0;
         I.bounds[1] = x1 > fp.width - 1 ? fp.width - 1 : x1;
         I.bounds[2] = y0 < 0 ? 0 : y0;
