@@ -244,7 +244,15 @@ def run_cuda(args):
         accum = torch.zeros((HEIGHT, WIDTH, 3), dtype=torch.int64, device=dev)  # 2^-24 fixed-point radiance sums
         r.set_accum_buffer(accum.data_ptr())
     shares = [shard_samples(SPP, k, world) for k in range(world)]
-    if fused and world > 1:
+    by_rows = fused and world > 1 and args.partition == "rows"
+    if by_rows:
+        # the frame is shared out by rows of 8x4 tiles: rank k traces all 64 samples of the tile rows ty = k (mod world), so
+        # per-pixel work (camera set-up, accumulator and NVLink traffic, the root's pass over the slots) is divided too
+        shares = [(0, 1, SPP) for _ in range(world)]
+        r.configure(width=WIDTH, height=HEIGHT, mode=abi.MODE_PATHS, flags=abi.FLAG_NO_HIT_RECORDS, spp=SPP,
+                    bounces=BOUNCES, seed=SEED, sample_first=0, sample_stride=1, total_spp=SPP, max_frames=0)
+        r.fused_reduce_partition(True)
+    elif fused and world > 1:
         # the root also sums the partial sums and encodes the frame (about two samples' worth of time): it traces fewer
         relief = float(os.environ.get("VT_ROOT_RELIEF_SPP", "2"))
         shares = [shard_samples_weighted(SPP, k, world, relief) for k in range(world)]
@@ -493,7 +501,9 @@ def run_cuda(args):
             "ms_per_step": t_res / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": DATA,
             "config": CONFIG,
-            "run": {"spp_per_rank": [c for _, _, c in shares], "partition": (f"spp sharded over {world} rank(s), " + (
+            "run": {"spp_per_rank": [c for _, _, c in shares], "partition": ((
+                        f"rows of 8x4-pixel tiles dealt round-robin to {world} rank(s), every rank tracing all {SPP} samples of its rows, "
+                        if by_rows else f"spp sharded over {world} rank(s), ") + (
                         ("partial sums pushed into rank 0's memory over NVLink peer stores, ordered by " +
                          ("flags in peer memory" if fused_flags else "a 4-byte NCCL stream barrier")) if fused
                         else "NCCL all-reduce of 3*w*h int64")) if world > 1 else "single rank",
@@ -639,6 +649,8 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE.json configurations")
     ap.add_argument("--force-fused", action="store_true", help="N=1 only: run the fused multi-GPU data path with one rank (profiling aid)")
     ap.add_argument("--reduce", default="fused", choices=["fused", "allreduce"], help="cross-GPU accumulation for N > 1")
+    ap.add_argument("--partition", default="rows", choices=["rows", "samples"],
+                    help="N > 1, fused: share a frame by rows of tiles (each rank traces all samples of its rows) or by samples")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

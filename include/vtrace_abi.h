@@ -222,6 +222,13 @@ int32_t vt_fused_reduce_export(uint8_t handle[64], uint32_t world);
 int32_t vt_fused_reduce_import(const uint8_t handle[64], uint32_t rank, uint32_t world);
 int32_t vt_fused_reduce_next_frame(void);
 int32_t vt_fused_reduce_disable(void);
+/* How the ranks of a fused reduction share a frame.  0 (default): by samples — rank r traces samples
+ * sample_first + k * sample_stride of every pixel, and the root adds the slots up.  1: by rows of 8x4-pixel tiles —
+ * rank r traces EVERY sample (configure sample_first 0, sample_stride 1, spp = total_spp) of the tile rows
+ * ty = r (mod world), pushes only those rows, and the root takes each pixel from its owner's slot: per-pixel work
+ * (camera set-up, accumulator traffic, NVLink bytes, the root's summation) is divided by the number of ranks instead
+ * of being repeated on each.  The image is the same, bit for bit.  Call on every rank after export / import. */
+int32_t vt_fused_reduce_partition(uint32_t by_tile_rows);
 
 /* Run on a caller-provided cudaStream_t (e.g. the launcher's current stream); NULL = own. */
 int32_t vt_set_stream(void* cuda_stream);

@@ -111,8 +111,60 @@ def main():
             assert np.array_equal(r.read_accum(), whole2), f"fused accumulation, wide layout, differs (frame {frame})"
     r.synchronize()
     dist.barrier()
+    # (f) the frame shared out by rows of tiles instead of by samples (vt_fused_reduce_partition): every rank traces all
+    # samples of the tile rows ty = rank (mod world); wide layout first (264 samples), then the compact one with the
+    # camera moving from frame to frame (the screen rectangle, and with it the first owned row, changes)
+    r.fused_reduce_disable()
+    r.configure(width=w2, height=h2, mode=abi.MODE_PATHS, spp=spp2, bounces=4, seed=0x5EED, sample_first=0, sample_stride=1, total_spp=spp2)
+    assert setup_fused_reduce(r, rank, world, dev)
+    r.fused_reduce_partition(True)
+    for frame in range(3):
+        r.fused_reduce_next_frame()
+        r.render_async(P2, V2)
+        if rank == 0:
+            assert np.array_equal(r.read_accum(), whole2), f"fused accumulation by tile rows, wide layout, differs (frame {frame})"
+    r.synchronize()
+    dist.barrier()
+    r.fused_reduce_disable()
+    eyes = [(0.8, -0.45, 0.6), (1.6, -0.9, 1.2), (2.4, -1.3, 1.9), (0.5, -0.2, 0.35), (1.1, 0.4, -0.9)]
+    wholes = []
     if rank == 0:
-        print(f"multi-GPU check ok: {world} ranks, all-reduce and fused NVLink accumulation (flags, external barrier) bit-identical to one rank")
+        r.configure(width=w, height=h, mode=abi.MODE_PATHS, spp=spp, bounces=4, seed=0x5EED, sample_first=0, sample_stride=1, total_spp=spp)
+        for eye in eyes:
+            Pm, Vm = scenes.camera(w, h, eye=eye)
+            assert r.render_tick_raw(Pm, Vm)
+            wholes.append((r.read_accum(), r.read_color()))
+    r.configure(width=w, height=h, mode=abi.MODE_PATHS, spp=spp, bounces=4, seed=0x5EED, sample_first=0, sample_stride=1, total_spp=spp)
+    assert setup_fused_reduce(r, rank, world, dev)
+    r.fused_reduce_partition(True)
+    rays_rows = 0
+    for frame, eye in enumerate(eyes + eyes):
+        Pm, Vm = scenes.camera(w, h, eye=eye)
+        r.fused_reduce_next_frame()
+        r.render_async(Pm, Vm)
+        if rank == 0:
+            r.resolve()
+            for name, got, want in (("colour", r.read_color(), wholes[frame % len(eyes)][1]), ("sums", r.read_accum(), wholes[frame % len(eyes)][0])):
+                if not np.array_equal(got, want):
+                    bad = np.argwhere((got != want).reshape(h, w, -1).any(axis=2))
+                    raise AssertionError(f"fused accumulation by tile rows: {name} differ (frame {frame}) at {len(bad)} pixels, rows "
+                                         f"{bad[:, 0].min()}..{bad[:, 0].max()}, columns {bad[:, 1].min()}..{bad[:, 1].max()}; first {bad[0]}: "
+                                         f"{got.reshape(h, w, -1)[bad[0][0], bad[0][1]]} != {want.reshape(h, w, -1)[bad[0][0], bad[0][1]]}")
+        r.synchronize()
+        if frame == 0:
+            rays_rows = r.stats().rays
+    # every path of the frame is traced by exactly one rank: the ray counters add up to the single-rank frame's
+    t = torch.tensor([rays_rows], dtype=torch.int64, device=dev)
+    dist.all_reduce(t)
+    if rank == 0:
+        r.fused_reduce_disable()
+        r.configure(width=w, height=h, mode=abi.MODE_PATHS, spp=spp, bounces=4, seed=0x5EED, sample_first=0, sample_stride=1, total_spp=spp)
+        Pm, Vm = scenes.camera(w, h, eye=eyes[0])
+        assert r.render_tick_raw(Pm, Vm)
+        assert r.stats().rays == int(t.item()), f"rays over the ranks {int(t.item())} != single-rank frame {r.stats().rays}"
+    dist.barrier()
+    if rank == 0:
+        print(f"multi-GPU check ok: {world} ranks, all-reduce and fused NVLink accumulation (flags, external barrier, by samples and by tile rows) bit-identical to one rank")
     r.close()
     dist.destroy_process_group()
 

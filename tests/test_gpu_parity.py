@@ -657,6 +657,22 @@ def test_paths_lean_frames_moving_camera(renderer, scene, assets):
     assert np.array_equal(renderer.read_accum(), want2 * np.uint64(2))
 
 
+def test_paths_tiles_with_a_single_covered_pixel(scene, assets):
+    """A screen rectangle whose corner is the last pixel of an 8x4 tile leaves that tile with ONE covered pixel: the
+    wavefront kernel's job -> (sample, pixel) split divides by the number of covered pixels with a 32-bit magic number,
+    and the magic number of 1 does not fit (found by tests/multi_gpu_check.py; every sample became sample 0).  The first
+    camera puts the rectangle's corner at pixel (199, 23) of a 640x360 frame; the sweep covers other corner alignments."""
+    t = scene.add(assets["AncientTemple"])
+    scene.set_instances([(glm.identity(), t)])
+    P, V = scenes.camera(640, 360, eye=(1.1, 0.4, -0.9))
+    scene.check_paths(P, V, 640, 360, spp=5, bounces=4, what="corner tile with one covered pixel")
+    for i in range(24):
+        a = 0.26 * i
+        eye = (1.9 * np.cos(a) + 0.013 * i, -0.7 + 0.05 * i, 1.9 * np.sin(a))
+        P, V = scenes.camera(168, 100, eye=eye)
+        scene.check_paths(P, V, 168, 100, spp=3, bounces=3, what=f"corner alignment sweep, camera {i}")
+
+
 def test_pipelined_frames_and_async_readback(renderer, scene, assets):
     """vt_render_frame_async + vt_read_color_async: three frames in flight with different cameras land in their own host
     buffers, identical to what render_tick + vt_read_color give one by one; non-pinned destinations are refused."""

@@ -1550,11 +1550,12 @@ __device__ __forceinline__ void fused_sync_end(const FusedSync& fs) {
 // rectangle only (the other pixels are sky for every rank and never travel).
 template <bool kCompact>
 __global__ void __launch_bounds__(256) push_partial_kernel(const InstUniforms* __restrict__ inst, unsigned long long* __restrict__ local_accum,
-                                                           uint4* __restrict__ slot, uint32_t width, uint32_t height, FusedSync fs) {
+                                                           uint4* __restrict__ slot, uint32_t width, uint32_t height,
+                                                           uint32_t row_first, uint32_t row_stride, FusedSync fs) {
     fused_sync_begin(fs);
     const int x0 = max(inst->bounds[0], 0), x1 = min(inst->bounds[1], (int)width - 1);
     const int y0 = max(inst->bounds[2], 0), y1 = min(inst->bounds[3], (int)height - 1);
-    for (int py = y0 + (int)blockIdx.x; py <= y1; py += (int)gridDim.x)
+    auto push_row = [&](int py) {
         for (int px = x0 + (int)threadIdx.x; px <= x1; px += (int)blockDim.x) {
             const size_t p = (size_t)py * width + (size_t)px;
             const unsigned long long r = local_accum[3 * p + 0], g = local_accum[3 * p + 1], b = local_accum[3 * p + 2];
@@ -1566,6 +1567,20 @@ __global__ void __launch_bounds__(256) push_partial_kernel(const InstUniforms* _
                 slot[2 * p + 1] = make_uint4((uint32_t)b, (uint32_t)(b >> 32), 0u, 0u);
             }
         }
+    };
+    if (row_stride <= 1) {
+        for (int py = y0 + (int)blockIdx.x; py <= y1; py += (int)gridDim.x) push_row(py);
+    } else if (y0 <= y1) {
+        // the lines of the tile rows this rank owns, numbered consecutively so that the blocks share them evenly
+        const int t0 = y0 / kTileH, t1 = y1 / kTileH;
+        const int ty0 = t0 + (int)((row_first + row_stride - (uint32_t)t0 % row_stride) % row_stride);
+        for (int k = (int)blockIdx.x;; k += (int)gridDim.x) {
+            const int ty = ty0 + (k / kTileH) * (int)row_stride;
+            if (ty > t1) break;
+            const int py = ty * kTileH + k % kTileH;
+            if (py >= y0 && py <= y1) push_row(py);
+        }
+    }
     fused_sync_end(fs);
 }
 
@@ -1573,7 +1588,8 @@ template <bool kCompact>
 __global__ void __launch_bounds__(256) resolve_partials_kernel(const InstUniforms* __restrict__ inst, const uint4* __restrict__ partials,
                                                                uint32_t world, uint32_t width, uint32_t height, uint32_t total_spp,
                                                                SrgbTables lut, uchar4* __restrict__ color,
-                                                               unsigned long long* __restrict__ accum_out, FusedSync fs) {
+                                                               unsigned long long* __restrict__ accum_out, uint32_t row_stride,
+                                                               FusedSync fs) {
     fused_sync_begin(fs);
     const size_t n_pix = (size_t)width * height;
     const float scale = 1.0f / ((float)total_spp * 16777216.0f);
@@ -1595,7 +1611,10 @@ __global__ void __launch_bounds__(256) resolve_partials_kernel(const InstUniform
                 continue;
             }
             unsigned long long sum[3] = {0ull, 0ull, 0ull};
-            for (uint32_t r = 0; r < world; ++r) { // (a slot is n_pix * 32 bytes whatever the layout; L1 is bypassed: peers wrote these lines)
+            // shared out by tile rows: the owner's slot holds the pixel's complete sums
+            const uint32_t r_begin = row_stride > 1 ? (py / (uint32_t)kTileH) % row_stride : 0u;
+            const uint32_t r_end = row_stride > 1 ? r_begin + 1u : world;
+            for (uint32_t r = r_begin; r < r_end; ++r) { // (a slot is n_pix * 32 bytes whatever the layout; L1 is bypassed: peers wrote these lines)
                 if (kCompact) {
                     const uint4 a = __ldcg(partials + r * n_pix * 2 + p);
                     sum[0] += a.x; sum[1] += a.y; sum[2] += a.z;
@@ -1616,19 +1635,23 @@ __global__ void __launch_bounds__(256) resolve_partials_kernel(const InstUniform
 }
 
 cudaError_t launch_push_partial(const InstUniforms* inst, unsigned long long* local_accum, uint4* slot, uint32_t width, uint32_t height,
-                                bool compact, FusedSync fs, int sm_count, cudaStream_t stream) {
-    const int grid = sm_count * 4 < (int)height ? sm_count * 4 : (int)height;
-    if (compact) push_partial_kernel<true><<<grid, 256, 0, stream>>>(inst, local_accum, slot, width, height, fs);
-    else push_partial_kernel<false><<<grid, 256, 0, stream>>>(inst, local_accum, slot, width, height, fs);
+                                bool compact, uint32_t row_first, uint32_t row_stride, FusedSync fs, int sm_count, cudaStream_t stream) {
+    int grid = sm_count * 4 < (int)height ? sm_count * 4 : (int)height;
+    if (row_stride > 1) { // about height / row_stride rows to move
+        const int own = (int)(height / row_stride) + kTileH;
+        if (grid > own) grid = own;
+    }
+    if (compact) push_partial_kernel<true><<<grid, 256, 0, stream>>>(inst, local_accum, slot, width, height, row_first, row_stride, fs);
+    else push_partial_kernel<false><<<grid, 256, 0, stream>>>(inst, local_accum, slot, width, height, row_first, row_stride, fs);
     return cudaGetLastError();
 }
 
 cudaError_t launch_resolve_partials(const InstUniforms* inst, const uint4* partials, uint32_t world, uint32_t width, uint32_t height,
                                     uint32_t total_spp, SrgbTables lut, uchar4* color, unsigned long long* accum_out, bool compact,
-                                    FusedSync fs, int sm_count, cudaStream_t stream) {
+                                    uint32_t row_stride, FusedSync fs, int sm_count, cudaStream_t stream) {
     const int grid = sm_count * 4 < (int)height ? sm_count * 4 : (int)height;
-    if (compact) resolve_partials_kernel<true><<<grid, 256, 0, stream>>>(inst, partials, world, width, height, total_spp, lut, color, accum_out, fs);
-    else resolve_partials_kernel<false><<<grid, 256, 0, stream>>>(inst, partials, world, width, height, total_spp, lut, color, accum_out, fs);
+    if (compact) resolve_partials_kernel<true><<<grid, 256, 0, stream>>>(inst, partials, world, width, height, total_spp, lut, color, accum_out, row_stride, fs);
+    else resolve_partials_kernel<false><<<grid, 256, 0, stream>>>(inst, partials, world, width, height, total_spp, lut, color, accum_out, row_stride, fs);
     return cudaGetLastError();
 }
 

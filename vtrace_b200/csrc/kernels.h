@@ -75,6 +75,8 @@ struct FrameParams {
     uint32_t clear_rgba;       // clear colour (lib/command.c:56-61) as stored by the sRGB target: r | g<<8 | b<<16 | a<<24
     uint32_t sky_spp;          // samples whose sky radiance this rank adds for pixels outside every screen
                                // rectangle (= spp normally; fused multi-GPU reduction: total on the root, 0 elsewhere)
+    uint32_t row_first, row_stride; // wavefront kernel: this rank traces the tile rows ty = row_first (mod row_stride)
+                                    // (0, 1 = all of them; vt_fused_reduce_partition)
 };
 
 // Per-instance uniforms (trace.vert outputs that are flat per instance + derived matrices).
@@ -208,11 +210,13 @@ struct FusedSync {
     uint32_t* err;
 };
 
+// row_stride > 1: the frame is shared out by rows of tiles (rank r traces every sample of the tile rows ty = r mod
+// row_stride): a rank pushes only its own rows, and the root takes a pixel from its owner's slot instead of summing all
 cudaError_t launch_push_partial(const InstUniforms* inst, unsigned long long* local_accum, uint4* slot, uint32_t width, uint32_t height,
-                                bool compact, FusedSync fs, int sm_count, cudaStream_t stream);
+                                bool compact, uint32_t row_first, uint32_t row_stride, FusedSync fs, int sm_count, cudaStream_t stream);
 cudaError_t launch_resolve_partials(const InstUniforms* inst, const uint4* partials, uint32_t world, uint32_t width, uint32_t height,
                                     uint32_t total_spp, SrgbTables lut, uchar4* color, unsigned long long* accum_out, bool compact,
-                                    FusedSync fs, int sm_count, cudaStream_t stream);
+                                    uint32_t row_stride, FusedSync fs, int sm_count, cudaStream_t stream);
 // single-instance frames: zero / resolve only the instance's screen rectangle; sky_only: write spp x sky into the
 // accumulators outside it instead (they are not touched by such a frame otherwise)
 cudaError_t launch_clear_rect(const InstUniforms* inst, unsigned long long* accum, uint32_t width, uint32_t height, int sm_count,

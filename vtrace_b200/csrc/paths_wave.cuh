@@ -208,7 +208,11 @@ __global__ void __launch_bounds__(kWaveThreads, kWaveCtas) trace_paths_wave_kern
     const bool any_cov = Ip->bounds[0] <= Ip->bounds[1] && Ip->bounds[2] <= Ip->bounds[3];
     const int ctx0 = any_cov ? Ip->bounds[0] / kTileW : 0, ctx1 = any_cov ? Ip->bounds[1] / kTileW : -1;
     const int cty0 = any_cov ? Ip->bounds[2] / kTileH : 0, cty1 = any_cov ? Ip->bounds[3] / kTileH : -1;
-    const int cov_w = ctx1 - ctx0 + 1, cov_tiles = cov_w * (cty1 - cty0 + 1);
+    // multi-GPU, frame shared out by rows of tiles: this rank's rows are own_y0, own_y0 + rs, ...
+    const int rs = fp.row_stride > 1u ? (int)fp.row_stride : 1;
+    const int own_y0 = cty0 + (int)((fp.row_first + (uint32_t)rs - (uint32_t)cty0 % (uint32_t)rs) % (uint32_t)rs);
+    const int own_rows = cty1 >= own_y0 ? (cty1 - own_y0) / rs + 1 : 0;
+    const int cov_w = ctx1 - ctx0 + 1, cov_tiles = cov_w * own_rows;
     // Work item = one tile x `item_spp` samples.  Items are sized so that there are several per resident
     // warp even when a rank only has a few samples per pixel (multi-GPU), otherwise the tail dominates.
     const uint32_t kItemSpp = fp.item_spp; // most samples per work item
@@ -251,7 +255,7 @@ __global__ void __launch_bounds__(kWaveThreads, kWaveCtas) trace_paths_wave_kern
         for (int tile = gw; tile < n_tiles; tile += nw) {
             const int tx = tile % tiles_x, ty = tile / tiles_x;
             const int px = tx * kTileW + (lane & 7), py = ty * kTileH + (lane >> 3);
-            const bool in_frame = px < fp.width && py < fp.height;
+            const bool in_frame = px < fp.width && py < fp.height && (uint32_t)ty % (uint32_t)rs == fp.row_first % (uint32_t)rs;
             const bool may_hit = !(px < Ip->bounds[0] || px > Ip->bounds[1] || py < Ip->bounds[2] || py > Ip->bounds[3]);
             if (in_frame && !may_hit) {
                 const size_t p = (size_t)py * (size_t)fp.width + (size_t)px;
@@ -408,10 +412,10 @@ __global__ void __launch_bounds__(kWaveThreads, kWaveCtas) trace_paths_wave_kern
             flush_tile();
             const int chunk = item / cov_tiles, ct = item - chunk * cov_tiles; // chunk-major: a tile's chunks are spread in time
             const int cy = ct / cov_w, cx = ct - cy * cov_w;
-            const int tile = (cty0 + cy) * tiles_x + (ctx0 + cx);
+            const int tile = (own_y0 + cy * rs) * tiles_x + (ctx0 + cx);
             it_tile = (uint32_t)tile;
             it_x0 = (ctx0 + cx) * kTileW;
-            it_y0 = (cty0 + cy) * kTileH;
+            it_y0 = (own_y0 + cy * rs) * kTileH;
             const int my_px = it_x0 + (lane & 7), my_py = it_y0 + (lane >> 3);
             const bool in_frame = my_px < fp.width && my_py < fp.height;
             const bool may_hit = in_frame && !(my_px < Ip->bounds[0] || my_px > Ip->bounds[1] || my_py < Ip->bounds[2] || my_py > Ip->bounds[3]);
@@ -457,7 +461,7 @@ __global__ void __launch_bounds__(kWaveThreads, kWaveCtas) trace_paths_wave_kern
             float d[3] = {0.0f, 0.0f, 0.0f}, pos[3] = {0.0f, 0.0f, 0.0f};
             if ((uint32_t)lane < n) {
                 const uint32_t job = it_next + lane; // sample-major: neighbouring lanes get neighbouring pixels
-                const uint32_t si = __umulhi(job, it_magic), ci = job - si * it_ncov;
+                const uint32_t si = it_ncov == 1u ? job : __umulhi(job, it_magic), ci = job - si * it_ncov; // (the magic number of 1 is 2^32)
                 const uint32_t pix = cov_pix[ci];
                 const int px = it_x0 + (int)(pix & 7u), py = it_y0 + (int)(pix >> 3);
                 const uint32_t pixel = (uint32_t)py * (uint32_t)fp.width + (uint32_t)px;

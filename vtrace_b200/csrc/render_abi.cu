@@ -98,6 +98,7 @@ struct State {
     uint32_t* d_fused_err = nullptr;
     uint32_t* h_fused_err = nullptr; // pinned
     bool fused_sync = true;
+    bool fused_rows = false;         // vt_fused_reduce_partition(1): the frame is shared out by rows of tiles, not by samples
     unsigned long long* fused_sum = nullptr; // root, on demand: materialised sums for vt_read_accum
     // asynchronous colour read-back (vt_read_color_async): a second colour buffer, a copy stream, one event per buffer
     uchar4* d_color_alt = nullptr;
@@ -394,6 +395,12 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
             return fail("fused cross-GPU accumulation needs the single-instance wavefront kernel");
         if (g.fused_pixels != (size_t)g.cfg.width * g.cfg.height) return fail("fused accumulation buffer does not match the framebuffer size");
         fp.sky_spp = 0u; // pixels outside the screen rectangle are resolved analytically on the root
+        if (g.fused_rows) {
+            if (g.cfg.sample_first != 0 || g.cfg.sample_stride > 1 || (g.cfg.total_spp && g.cfg.total_spp != g.cfg.spp))
+                return fail("fused accumulation by tile rows: every rank traces all samples (sample_first 0, sample_stride 1, spp = total_spp)");
+            fp.row_first = g.fused_rank;
+            fp.row_stride = g.fused_world;
+        }
     }
 
     if (g.vols_dirty) {
@@ -542,7 +549,8 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
                 fs.done_counter = g.d_fused_err + 1;
                 fs.err = g.d_fused_err;
             }
-            CK(launch_push_partial(g.d_iu, g.d_accum_own, slot, g.cfg.width, g.cfg.height, fused_compact(), fs, g.sm_count, g.stream));
+            CK(launch_push_partial(g.d_iu, g.d_accum_own, slot, g.cfg.width, g.cfg.height, fused_compact(), g.fused_rank,
+                                   g.fused_rows ? g.fused_world : 1u, fs, g.sm_count, g.stream));
             g.stats.launches += 1;
         }
         if (resolve && !fused) {
@@ -971,6 +979,7 @@ extern "C" void cleanup(void) {
     if (g.fused_mode == 2) cudaIpcCloseMemHandle(g.fused_base);
     g.fused_base = nullptr;
     g.fused_flags = nullptr;
+    g.fused_rows = false;
     cudaFree(g.d_fused_err);
     if (g.h_fused_err) cudaFreeHost(g.h_fused_err);
     g.d_fused_err = g.h_fused_err = nullptr;
@@ -1123,7 +1132,7 @@ extern "C" int64_t vt_read_accum(uint64_t* accum, size_t capacity) {
         SrgbTables lut{g.d_dec, g.d_thr};
         const uint4* partials = g.fused_base + (size_t)g.fused_index * g.fused_world * g.fused_pixels * 2;
         if (launch_resolve_partials(g.d_iu, partials, g.fused_world, g.cfg.width, g.cfg.height, total ? total : 1, lut, g.d_color, g.fused_sum,
-                                    fused_compact(), fused_wait_all(), g.sm_count, g.stream) != cudaSuccess)
+                                    fused_compact(), g.fused_rows ? g.fused_world : 1u, fused_wait_all(), g.sm_count, g.stream) != cudaSuccess)
             return fail("vt_read_accum: resolve failed");
         return read_back(g.fused_sum, g.fused_pixels * 24, accum, capacity);
     }
@@ -1168,7 +1177,7 @@ extern "C" int32_t vt_resolve(void) {
     if (g.fused_mode == 1) {
         const uint4* partials = g.fused_base + (size_t)g.fused_index * g.fused_world * g.fused_pixels * 2;
         CK(launch_resolve_partials(g.d_iu, partials, g.fused_world, g.cfg.width, g.cfg.height, total ? total : 1, lut, g.d_color, nullptr,
-                                   fused_compact(), fused_wait_all(), g.sm_count, g.stream));
+                                   fused_compact(), g.fused_rows ? g.fused_world : 1u, fused_wait_all(), g.sm_count, g.stream));
     } else {
         CK(launch_resolve(g.d_accum, g.cfg.width * g.cfg.height, total ? total : 1, lut, g.d_color, g.stream));
     }
@@ -1231,6 +1240,14 @@ extern "C" int32_t vt_fused_reduce_import(const uint8_t handle[64], uint32_t ran
     g.fused_base = (uint4*)p;
     g.fused_flags = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p) + 2 * (size_t)world * g.fused_pixels * 2 * sizeof(uint4));
     g.fused_mode = 2;
+    return 0;
+}
+
+extern "C" int32_t vt_fused_reduce_partition(uint32_t by_tile_rows) {
+    if (!g.inited || !g.fused_mode) return fail("vt_fused_reduce_partition: no fused reduction set up");
+    CK(cudaSetDevice(g.device));
+    if (finish_frame()) return -1;
+    g.fused_rows = by_tile_rows != 0;
     return 0;
 }
 

@@ -262,6 +262,11 @@ class Renderer:
         if self._lib.vt_fused_reduce_disable() != 0:
             raise RuntimeError("vt_fused_reduce_disable failed: " + abi.last_error())
 
+    def fused_reduce_partition(self, by_tile_rows: bool):
+        """False: ranks share a frame by samples; True: by rows of 8x4 tiles, every rank tracing all samples of its rows."""
+        if self._lib.vt_fused_reduce_partition(1 if by_tile_rows else 0) != 0:
+            raise RuntimeError("vt_fused_reduce_partition failed: " + abi.last_error())
+
     def set_accum_buffer(self, device_ptr: int | None):
         if self._lib.vt_set_accum_buffer(C.c_void_p(device_ptr or 0)) != 0:
             raise RuntimeError("vt_set_accum_buffer failed: " + abi.last_error())
