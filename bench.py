@@ -244,7 +244,7 @@ def run_cuda(args):
         accum = torch.zeros((HEIGHT, WIDTH, 3), dtype=torch.int64, device=dev)  # 2^-24 fixed-point radiance sums
         r.set_accum_buffer(accum.data_ptr())
     shares = [shard_samples(SPP, k, world) for k in range(world)]
-    by_rows = fused and world > 1 and args.partition == "rows"
+    by_rows = fused and args.partition == "rows" and (world > 1 or bool(os.environ.get("VT_FUSED_ROWS_AS_WORLD")))  # (env: profiling aid)
     if by_rows:
         # the frame is shared out by rows of 8x4 tiles: rank k traces all 64 samples of the tile rows ty = k (mod world), so
         # per-pixel work (camera set-up, accumulator and NVLink traffic, the root's pass over the slots) is divided too

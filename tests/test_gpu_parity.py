@@ -673,6 +673,45 @@ def test_paths_tiles_with_a_single_covered_pixel(scene, assets):
         scene.check_paths(P, V, 168, 100, spp=3, bounces=3, what=f"corner alignment sweep, camera {i}")
 
 
+def test_fused_accumulation_data_path_with_one_rank(renderer, scene, assets):
+    """The multi-GPU data path (vt_fused_reduce_*) with a world of one rank: the root's sums never travel — its summation
+    kernel takes them from the local accumulators, parks them in its slot for later calls on the same frame and clears
+    them — for both ways of sharing a frame, compact and wide layout, with the camera moving between frames.  (Several
+    ranks: tests/multi_gpu_check.py under torchrun.)"""
+    import oracle_lib
+    t = scene.add(assets["AncientTemple"])
+    scene.set_instances([(glm.identity(), t)])
+    w, h = 320, 200
+    cams = [scenes.camera(w, h, eye=e) for e in ((1.6, -0.9, 1.2), (0.8, -0.45, 0.6), (1.1, 0.4, -0.9))]
+    for spp in (3, 260):
+        renderer.configure(width=w, height=h, mode=abi.MODE_PATHS, spp=spp, bounces=3, seed=0x5EED, sample_first=0, sample_stride=1,
+                           total_spp=spp, max_frames=0)
+        wants = [scene.o.render_paths(P, V, w, h, spp=spp, bounces=3, seed=0x5EED, flags=0) for P, V in (cams if spp == 3 else cams[:1])]
+        renderer.fused_reduce_export(1)
+        try:
+            for by_rows in (False, True):
+                renderer.fused_reduce_partition(by_rows)
+                for (P, V), (want, rays, iters) in zip(cams, wants):
+                    renderer.fused_reduce_next_frame()
+                    renderer.render_async(P, V)
+                    renderer.resolve()
+                    assert np.array_equal(renderer.read_color(), oracle_lib.resolve(want, spp))
+                    assert np.array_equal(renderer.read_accum(), want)   # second summation of the frame: from the slot
+                    renderer.resolve()
+                    assert np.array_equal(renderer.read_color(), oracle_lib.resolve(want, spp))
+                    st = renderer.stats()
+                    assert (st.rays, st.iterations) == (rays, iters)
+            # the protocol: the root sums every frame before it starts the next
+            renderer.fused_reduce_next_frame()
+            renderer.render_async(*cams[0])
+            renderer.fused_reduce_next_frame()
+            with pytest.raises(RuntimeError, match="for every frame"):
+                renderer.render_async(*cams[0])
+            renderer.resolve()
+        finally:
+            renderer.fused_reduce_disable()
+
+
 def test_pipelined_frames_and_async_readback(renderer, scene, assets):
     """vt_render_frame_async + vt_read_color_async: three frames in flight with different cameras land in their own host
     buffers, identical to what render_tick + vt_read_color give one by one; non-pinned destinations are refused."""

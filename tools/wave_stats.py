@@ -30,10 +30,23 @@ with Renderer() as r:
     ft = lib.vt_debug_wave_times
     ft.restype, ft.argtypes = C.c_int, [C.c_void_p]
     times = np.zeros(192, dtype=np.uint32)
-    assert r.render_tick_raw(P, V)
+    rows_as = os.environ.get("VT_FUSED_ROWS_AS_WORLD")  # one rank of an N-rank job that shares frames by tile rows
+
+    def frame():
+        if rows_as:
+            r.fused_reduce_next_frame()
+            r.render_async(P, V)
+            r.synchronize()
+        else:
+            assert r.render_tick_raw(P, V)
+
+    if rows_as:
+        r.fused_reduce_export(1)
+        r.fused_reduce_partition(True)
+    frame()
     fn(out.ctypes.data)  # (drop the first frame)
     ft(times.ctypes.data)
-    assert r.render_tick_raw(P, V)
+    frame()
     assert fn(out.ctypes.data) == 0
     s = [int(x) for x in out]
     st = r.stats()

@@ -1525,17 +1525,25 @@ __device__ __forceinline__ void flag_wait(const uint32_t* flag, uint32_t target,
 }
 
 __device__ __forceinline__ void fused_sync_begin(const FusedSync& fs) {
+    if (fs.host_stats && blockIdx.x == 0 && threadIdx.x == 0) {
+        fs.host_stats[0] = fs.stats[0]; fs.host_stats[1] = fs.stats[1]; fs.host_stats[2] = fs.stats[2]; fs.host_stats[3] = fs.stats[3];
+    }
     if (fs.wait_flags) {
-        if (threadIdx.x < fs.wait_count) flag_wait(fs.wait_flags + threadIdx.x, fs.wait_target, fs.err);
-        __threadfence_system(); // the waiting threads' acquire, made cumulative for the block by the barrier
+        if (threadIdx.x < fs.wait_count) {
+            flag_wait(fs.wait_flags + threadIdx.x, fs.wait_target, fs.err);
+            __threadfence_system(); // the waiting threads' acquire; the barrier extends it to the block (fences are cumulative)
+        }
         __syncthreads();
     }
 }
 __device__ __forceinline__ void fused_sync_end(const FusedSync& fs) {
     if (fs.signal_flag) {
-        __threadfence_system(); // this thread's stores to the root's memory are visible before the flag can be
+        // The block's stores to the root's memory must be visible there before the flag can be: the barrier orders them before
+        // thread 0's system-scope fence, which is cumulative (one fence per block instead of one per thread: a MEMBAR.SYS
+        // waits for every store the SM has in flight).
         __syncthreads();
         if (threadIdx.x == 0) {
+            __threadfence_system();
             if (atomicAdd(fs.done_counter, 1u) == gridDim.x - 1) { // last block
                 *fs.done_counter = 0u;
                 __threadfence_system();
@@ -1555,30 +1563,25 @@ __global__ void __launch_bounds__(256) push_partial_kernel(const InstUniforms* _
     fused_sync_begin(fs);
     const int x0 = max(inst->bounds[0], 0), x1 = min(inst->bounds[1], (int)width - 1);
     const int y0 = max(inst->bounds[2], 0), y1 = min(inst->bounds[3], (int)height - 1);
-    auto push_row = [&](int py) {
-        for (int px = x0 + (int)threadIdx.x; px <= x1; px += (int)blockDim.x) {
-            const size_t p = (size_t)py * width + (size_t)px;
-            const unsigned long long r = local_accum[3 * p + 0], g = local_accum[3 * p + 1], b = local_accum[3 * p + 2];
-            local_accum[3 * p + 0] = 0ull; local_accum[3 * p + 1] = 0ull; local_accum[3 * p + 2] = 0ull;
-            if (kCompact) {
-                slot[p] = make_uint4((uint32_t)r, (uint32_t)g, (uint32_t)b, 0u);
-            } else {
-                slot[2 * p + 0] = make_uint4((uint32_t)r, (uint32_t)(r >> 32), (uint32_t)g, (uint32_t)(g >> 32));
-                slot[2 * p + 1] = make_uint4((uint32_t)b, (uint32_t)(b >> 32), 0u, 0u);
-            }
-        }
-    };
-    if (row_stride <= 1) {
-        for (int py = y0 + (int)blockIdx.x; py <= y1; py += (int)gridDim.x) push_row(py);
-    } else if (y0 <= y1) {
-        // the lines of the tile rows this rank owns, numbered consecutively so that the blocks share them evenly
-        const int t0 = y0 / kTileH, t1 = y1 / kTileH;
-        const int ty0 = t0 + (int)((row_first + row_stride - (uint32_t)t0 % row_stride) % row_stride);
-        for (int k = (int)blockIdx.x;; k += (int)gridDim.x) {
-            const int ty = ty0 + (k / kTileH) * (int)row_stride;
-            if (ty > t1) break;
-            const int py = ty * kTileH + k % kTileH;
-            if (py >= y0 && py <= y1) push_row(py);
+    // the pixels of the rectangle's lines this rank owns, numbered consecutively: one grid-stride loop over all of them
+    const int rect_w = x1 - x0 + 1;
+    const int rs = row_stride > 1 ? (int)row_stride : 1;
+    const int t0 = y0 / kTileH, t1 = y1 / kTileH;
+    const int ty0 = t0 + (int)((row_first + (uint32_t)rs - (uint32_t)t0 % (uint32_t)rs) % (uint32_t)rs); // first owned tile row
+    const int own_tile_rows = (y0 <= y1 && rect_w > 0 && ty0 <= t1) ? (t1 - ty0) / rs + 1 : 0;
+    const long long total = (long long)own_tile_rows * kTileH * rect_w;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int line = (int)(i / rect_w), px = x0 + (int)(i - (long long)line * rect_w);
+        const int py = (ty0 + (line / kTileH) * rs) * kTileH + line % kTileH;
+        if (py < y0 || py > y1) continue; // (the first and last tile row may be cut by the rectangle)
+        const size_t p = (size_t)py * width + (size_t)px;
+        const unsigned long long r = local_accum[3 * p + 0], g = local_accum[3 * p + 1], b = local_accum[3 * p + 2];
+        local_accum[3 * p + 0] = 0ull; local_accum[3 * p + 1] = 0ull; local_accum[3 * p + 2] = 0ull;
+        if (kCompact) {
+            slot[p] = make_uint4((uint32_t)r, (uint32_t)g, (uint32_t)b, 0u);
+        } else {
+            slot[2 * p + 0] = make_uint4((uint32_t)r, (uint32_t)(r >> 32), (uint32_t)g, (uint32_t)(g >> 32));
+            slot[2 * p + 1] = make_uint4((uint32_t)b, (uint32_t)(b >> 32), 0u, 0u);
         }
     }
     fused_sync_end(fs);
@@ -1589,6 +1592,7 @@ __global__ void __launch_bounds__(256) resolve_partials_kernel(const InstUniform
                                                                uint32_t world, uint32_t width, uint32_t height, uint32_t total_spp,
                                                                SrgbTables lut, uchar4* __restrict__ color,
                                                                unsigned long long* __restrict__ accum_out, uint32_t row_stride,
+                                                               unsigned long long* __restrict__ root_local, uint4* __restrict__ root_slot,
                                                                FusedSync fs) {
     fused_sync_begin(fs);
     const size_t n_pix = (size_t)width * height;
@@ -1615,6 +1619,18 @@ __global__ void __launch_bounds__(256) resolve_partials_kernel(const InstUniform
             const uint32_t r_begin = row_stride > 1 ? (py / (uint32_t)kTileH) % row_stride : 0u;
             const uint32_t r_end = row_stride > 1 ? r_begin + 1u : world;
             for (uint32_t r = r_begin; r < r_end; ++r) { // (a slot is n_pix * 32 bytes whatever the layout; L1 is bypassed: peers wrote these lines)
+                if (r == 0u && root_local) { // the root's own sums never travelled: take them from its accumulators
+                    const unsigned long long lr = root_local[3 * p + 0], lg = root_local[3 * p + 1], lb = root_local[3 * p + 2];
+                    root_local[3 * p + 0] = 0ull; root_local[3 * p + 1] = 0ull; root_local[3 * p + 2] = 0ull;
+                    if (kCompact) {
+                        root_slot[p] = make_uint4((uint32_t)lr, (uint32_t)lg, (uint32_t)lb, 0u);
+                    } else {
+                        root_slot[2 * p + 0] = make_uint4((uint32_t)lr, (uint32_t)(lr >> 32), (uint32_t)lg, (uint32_t)(lg >> 32));
+                        root_slot[2 * p + 1] = make_uint4((uint32_t)lb, (uint32_t)(lb >> 32), 0u, 0u);
+                    }
+                    sum[0] += lr; sum[1] += lg; sum[2] += lb;
+                    continue;
+                }
                 if (kCompact) {
                     const uint4 a = __ldcg(partials + r * n_pix * 2 + p);
                     sum[0] += a.x; sum[1] += a.y; sum[2] += a.z;
@@ -1636,11 +1652,7 @@ __global__ void __launch_bounds__(256) resolve_partials_kernel(const InstUniform
 
 cudaError_t launch_push_partial(const InstUniforms* inst, unsigned long long* local_accum, uint4* slot, uint32_t width, uint32_t height,
                                 bool compact, uint32_t row_first, uint32_t row_stride, FusedSync fs, int sm_count, cudaStream_t stream) {
-    int grid = sm_count * 4 < (int)height ? sm_count * 4 : (int)height;
-    if (row_stride > 1) { // about height / row_stride rows to move
-        const int own = (int)(height / row_stride) + kTileH;
-        if (grid > own) grid = own;
-    }
+    const int grid = sm_count * 4; // grid-stride over the owned pixels
     if (compact) push_partial_kernel<true><<<grid, 256, 0, stream>>>(inst, local_accum, slot, width, height, row_first, row_stride, fs);
     else push_partial_kernel<false><<<grid, 256, 0, stream>>>(inst, local_accum, slot, width, height, row_first, row_stride, fs);
     return cudaGetLastError();
@@ -1648,10 +1660,11 @@ cudaError_t launch_push_partial(const InstUniforms* inst, unsigned long long* lo
 
 cudaError_t launch_resolve_partials(const InstUniforms* inst, const uint4* partials, uint32_t world, uint32_t width, uint32_t height,
                                     uint32_t total_spp, SrgbTables lut, uchar4* color, unsigned long long* accum_out, bool compact,
-                                    uint32_t row_stride, FusedSync fs, int sm_count, cudaStream_t stream) {
+                                    uint32_t row_stride, unsigned long long* root_local, uint4* root_slot, FusedSync fs, int sm_count,
+                                    cudaStream_t stream) {
     const int grid = sm_count * 4 < (int)height ? sm_count * 4 : (int)height;
-    if (compact) resolve_partials_kernel<true><<<grid, 256, 0, stream>>>(inst, partials, world, width, height, total_spp, lut, color, accum_out, row_stride, fs);
-    else resolve_partials_kernel<false><<<grid, 256, 0, stream>>>(inst, partials, world, width, height, total_spp, lut, color, accum_out, row_stride, fs);
+    if (compact) resolve_partials_kernel<true><<<grid, 256, 0, stream>>>(inst, partials, world, width, height, total_spp, lut, color, accum_out, row_stride, root_local, root_slot, fs);
+    else resolve_partials_kernel<false><<<grid, 256, 0, stream>>>(inst, partials, world, width, height, total_spp, lut, color, accum_out, row_stride, root_local, root_slot, fs);
     return cudaGetLastError();
 }
 

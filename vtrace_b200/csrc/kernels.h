@@ -208,15 +208,22 @@ struct FusedSync {
     uint32_t signal_value;
     uint32_t* done_counter;     // device word, 0 between launches
     uint32_t* err;
+    // the frame's counters (4 x u64, device) are published to mapped page-locked host memory by block 0 (no copy-engine
+    // operation on the frame's stream: it would queue behind the previous frame's colour read-back)
+    const unsigned long long* stats;
+    unsigned long long* host_stats;
 };
 
 // row_stride > 1: the frame is shared out by rows of tiles (rank r traces every sample of the tile rows ty = r mod
 // row_stride): a rank pushes only its own rows, and the root takes a pixel from its owner's slot instead of summing all
 cudaError_t launch_push_partial(const InstUniforms* inst, unsigned long long* local_accum, uint4* slot, uint32_t width, uint32_t height,
                                 bool compact, uint32_t row_first, uint32_t row_stride, FusedSync fs, int sm_count, cudaStream_t stream);
+// root_local != nullptr: the root's own sums are still in its local accumulators (it does not push): they are taken from
+// there, cleared, and parked in the root's slot (root_slot) for later calls on the same frame
 cudaError_t launch_resolve_partials(const InstUniforms* inst, const uint4* partials, uint32_t world, uint32_t width, uint32_t height,
                                     uint32_t total_spp, SrgbTables lut, uchar4* color, unsigned long long* accum_out, bool compact,
-                                    uint32_t row_stride, FusedSync fs, int sm_count, cudaStream_t stream);
+                                    uint32_t row_stride, unsigned long long* root_local, uint4* root_slot, FusedSync fs, int sm_count,
+                                    cudaStream_t stream);
 // single-instance frames: zero / resolve only the instance's screen rectangle; sky_only: write spp x sky into the
 // accumulators outside it instead (they are not touched by such a frame otherwise)
 cudaError_t launch_clear_rect(const InstUniforms* inst, unsigned long long* accum, uint32_t width, uint32_t height, int sm_count,

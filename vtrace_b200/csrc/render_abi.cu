@@ -99,6 +99,10 @@ struct State {
     uint32_t* h_fused_err = nullptr; // pinned
     bool fused_sync = true;
     bool fused_rows = false;         // vt_fused_reduce_partition(1): the frame is shared out by rows of tiles, not by samples
+    // root: the last frame's own sums are still in d_accum_own (the root does not push; its first vt_resolve / vt_read_accum
+    // of the frame takes them from there) and its counters in d_stats (published by the same kernel), ring slot below
+    bool fused_root_live = false;
+    uint32_t fused_root_slot = 0;
     unsigned long long* fused_sum = nullptr; // root, on demand: materialised sums for vt_read_accum
     // asynchronous colour read-back (vt_read_color_async): a second colour buffer, a copy stream, one event per buffer
     uchar4* d_color_alt = nullptr;
@@ -274,18 +278,37 @@ static uint32_t* fused_consumed(uint32_t half) { return g.fused_flags + 2 * kFus
 // the root's summation first waits for every rank's "sums of this frame are in place" flag
 static FusedSync fused_wait_all() {
     FusedSync fs{};
-    if (g.fused_sync) {
-        fs.wait_flags = fused_arrive(g.fused_index); fs.wait_count = g.fused_world; fs.wait_target = g.fused_seq;
+    if (g.fused_sync && g.fused_world > 1) { // (the root's own sums do not travel: ranks 1 .. world - 1)
+        fs.wait_flags = fused_arrive(g.fused_index) + 1; fs.wait_count = g.fused_world - 1; fs.wait_target = g.fused_seq;
         fs.err = g.d_fused_err;
     }
     return fs;
 }
 static bool fused_compact() { return (g.cfg.total_spp ? g.cfg.total_spp : g.cfg.spp) <= 255u; }
+// The root's summation (vt_resolve / vt_read_accum).  The first one of a frame also collects the root's own sums from its
+// local accumulators and publishes the frame's counters, so the frame's end event is recorded again behind it.
+static cudaError_t fused_root_sum(unsigned long long* accum_out) {
+    const uint32_t total = g.cfg.total_spp ? g.cfg.total_spp : g.cfg.spp;
+    SrgbTables lut{g.d_dec, g.d_thr};
+    uint4* half = g.fused_base + (size_t)g.fused_index * g.fused_world * g.fused_pixels * 2;
+    FusedSync fs = fused_wait_all();
+    if (g.fused_root_live) { fs.stats = g.d_stats; fs.host_stats = g.h_stats + 4 * g.fused_root_slot; }
+    cudaError_t e = launch_resolve_partials(g.d_iu, half, g.fused_world, g.cfg.width, g.cfg.height, total ? total : 1, lut, g.d_color, accum_out,
+                                            fused_compact(), g.fused_rows ? g.fused_world : 1u, g.fused_root_live ? g.d_accum_own : nullptr, half,
+                                            fs, g.sm_count, g.stream);
+    if (e == cudaSuccess && g.fused_root_live) {
+        g.fused_root_live = false;
+        e = cudaEventRecord(g.ev_end[g.fused_root_slot], g.stream);
+    }
+    return e;
+}
 
 int finish_frame() {
     if (!g.frame_pending) return 0;
     CK(cudaStreamSynchronize(g.stream));
     g.frame_pending = false;
+    if (g.fused_mode == 1 && g.fused_root_live) // counters of a root frame that was not summed yet (normally vt_resolve's kernel publishes them)
+        CK(cudaMemcpy(g.h_stats + 4 * g.fused_root_slot, g.d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     // the binner reports how many list entries it needed.  Bins whose segment did not fit made their pixels visit
     // every instance (kernels.cu, bin_range) — exact, only slower, and free of side effects whoever owns the
     // accumulator clear — so nothing is rendered again: the next frame simply gets a larger list.
@@ -394,12 +417,16 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
         if (g.inst_count != 1 || g.any_bricks || (g.cfg.flags & VT_FLAG_PER_PIXEL_PATHS) || g.max_idx_bits > 29)
             return fail("fused cross-GPU accumulation needs the single-instance wavefront kernel");
         if (g.fused_pixels != (size_t)g.cfg.width * g.cfg.height) return fail("fused accumulation buffer does not match the framebuffer size");
+        if (g.fused_mode == 1 && g.fused_root_live)
+            return fail("fused cross-GPU accumulation: the root must call vt_resolve (or vt_read_accum) for every frame before it starts the next");
         fp.sky_spp = 0u; // pixels outside the screen rectangle are resolved analytically on the root
         if (g.fused_rows) {
             if (g.cfg.sample_first != 0 || g.cfg.sample_stride > 1 || (g.cfg.total_spp && g.cfg.total_spp != g.cfg.spp))
                 return fail("fused accumulation by tile rows: every rank traces all samples (sample_first 0, sample_stride 1, spp = total_spp)");
             fp.row_first = g.fused_rank;
             fp.row_stride = g.fused_world;
+            // (profiling aid: one rank of an N-rank job on its own — VT_FUSED_ROWS_AS_WORLD=N traces rank 0's rows only)
+            if (const uint32_t as_world = env_u32("VT_FUSED_ROWS_AS_WORLD", 0)) fp.row_stride = as_world;
         }
     }
 
@@ -537,9 +564,12 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
         CK(launch_trace_paths(fp, g.d_iu, bins, wg, g.d_arena, g.arena_words, in_smem, lut, fb, g.sm_count, g.stream));
         CK(cudaEventRecord(g.ev_trace1[slot], g.stream));
         g.stats.launches += 1;
-        if (fused) { // stream this rank's sums of the covered rectangle into its slot in the root's memory
+        if (fused && g.fused_mode == 1) { // the root's sums stay where they are until its summation kernel collects them
+            g.fused_root_live = true;
+            g.fused_root_slot = slot;
+        } else if (fused) { // stream this rank's sums of the covered rectangle into its slot in the root's memory
             const uint32_t half = g.fused_index, seq = g.fused_seq;
-            uint4* slot = g.fused_base + ((size_t)half * g.fused_world + g.fused_rank) * g.fused_pixels * 2;
+            uint4* peer_slot = g.fused_base + ((size_t)half * g.fused_world + g.fused_rank) * g.fused_pixels * 2;
             FusedSync fs{};
             if (g.fused_sync) {
                 if (g.fused_rank != 0 && seq > 2) { // the root must be done with the frame that used this half before
@@ -549,7 +579,8 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
                 fs.done_counter = g.d_fused_err + 1;
                 fs.err = g.d_fused_err;
             }
-            CK(launch_push_partial(g.d_iu, g.d_accum_own, slot, g.cfg.width, g.cfg.height, fused_compact(), g.fused_rank,
+            fs.stats = g.d_stats; fs.host_stats = g.h_stats + 4 * slot; // (the frame's counters travel with this kernel)
+            CK(launch_push_partial(g.d_iu, g.d_accum_own, peer_slot, g.cfg.width, g.cfg.height, fused_compact(), g.fused_rank,
                                    g.fused_rows ? g.fused_world : 1u, fs, g.sm_count, g.stream));
             g.stats.launches += 1;
         }
@@ -561,7 +592,8 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
             g.stats.launches += 1;
         }
     }
-    if (!lean) CK(cudaMemcpyAsync(g.h_stats + 4 * slot, g.d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g.stream));
+    if (!lean && !(g.fused_mode && g.cfg.mode == VT_MODE_PATHS))
+        CK(cudaMemcpyAsync(g.h_stats + 4 * slot, g.d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g.stream));
     CK(cudaEventRecord(g.ev_end[slot], g.stream));
     g.ring_head += 1;
     g.frame_pending = true;
@@ -980,6 +1012,7 @@ extern "C" void cleanup(void) {
     g.fused_base = nullptr;
     g.fused_flags = nullptr;
     g.fused_rows = false;
+    g.fused_root_live = false;
     cudaFree(g.d_fused_err);
     if (g.h_fused_err) cudaFreeHost(g.h_fused_err);
     g.d_fused_err = g.h_fused_err = nullptr;
@@ -1128,12 +1161,7 @@ extern "C" int64_t vt_read_accum(uint64_t* accum, size_t capacity) {
     if (g.inited && g.fused_mode == 1) { // materialise the sum of all ranks' partial sums
         if (cudaSetDevice(g.device) != cudaSuccess) return -1;
         if (!g.fused_sum && cudaMalloc(&g.fused_sum, g.fused_pixels * 24) != cudaSuccess) return fail("vt_read_accum: out of memory");
-        const uint32_t total = g.cfg.total_spp ? g.cfg.total_spp : g.cfg.spp;
-        SrgbTables lut{g.d_dec, g.d_thr};
-        const uint4* partials = g.fused_base + (size_t)g.fused_index * g.fused_world * g.fused_pixels * 2;
-        if (launch_resolve_partials(g.d_iu, partials, g.fused_world, g.cfg.width, g.cfg.height, total ? total : 1, lut, g.d_color, g.fused_sum,
-                                    fused_compact(), g.fused_rows ? g.fused_world : 1u, fused_wait_all(), g.sm_count, g.stream) != cudaSuccess)
-            return fail("vt_read_accum: resolve failed");
+        if (fused_root_sum(g.fused_sum) != cudaSuccess) return fail("vt_read_accum: resolve failed");
         return read_back(g.fused_sum, g.fused_pixels * 24, accum, capacity);
     }
     if (g.inited && g.sky_missing_spp) {
@@ -1175,9 +1203,7 @@ extern "C" int32_t vt_resolve(void) {
     if (g.fused_mode == 2) return fail("vt_resolve: only the root of a fused reduction holds the sums");
     if (prepare_color_target()) return -1;
     if (g.fused_mode == 1) {
-        const uint4* partials = g.fused_base + (size_t)g.fused_index * g.fused_world * g.fused_pixels * 2;
-        CK(launch_resolve_partials(g.d_iu, partials, g.fused_world, g.cfg.width, g.cfg.height, total ? total : 1, lut, g.d_color, nullptr,
-                                   fused_compact(), g.fused_rows ? g.fused_world : 1u, fused_wait_all(), g.sm_count, g.stream));
+        CK(fused_root_sum(nullptr));
     } else {
         CK(launch_resolve(g.d_accum, g.cfg.width * g.cfg.height, total ? total : 1, lut, g.d_color, g.stream));
     }
@@ -1311,5 +1337,11 @@ namespace vt { cudaError_t read_wave_stats(unsigned long long* out16); }
 extern "C" int vt_debug_wave_stats(uint64_t* out16) {
     if (cudaDeviceSynchronize() != cudaSuccess) return -1;
     return vt::read_wave_stats(reinterpret_cast<unsigned long long*>(out16)) == cudaSuccess ? 0 : -1;
+}
+// histograms in 5 us buckets since each warp started: [0,64) work exhausted, [64,128) warp finished, [128,192) first item claimed
+namespace vt { cudaError_t read_wave_times(unsigned int* out192); }
+extern "C" int vt_debug_wave_times(uint32_t* out192) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    return vt::read_wave_times(out192) == cudaSuccess ? 0 : -1;
 }
 #endif
