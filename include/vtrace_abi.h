@@ -227,8 +227,10 @@ int32_t vt_fused_reduce_disable(void);
  * rank r traces EVERY sample (configure sample_first 0, sample_stride 1, spp = total_spp) of the tile rows
  * ty = r (mod world), pushes only those rows, and the root takes each pixel from its owner's slot: per-pixel work
  * (camera set-up, accumulator traffic, NVLink bytes, the root's summation) is divided by the number of ranks instead
- * of being repeated on each.  The image is the same, bit for bit.  Call on every rank after export / import. */
-int32_t vt_fused_reduce_partition(uint32_t by_tile_rows);
+ * of being repeated on each.  The image is the same, bit for bit.  root_relief_num / root_relief_den (den 1 .. 64,
+ * num < den, the same on every rank): the root, which also sums the slots and encodes the frame, is dealt den - num tile
+ * rows for every den of another rank.  Call on every rank after export / import. */
+int32_t vt_fused_reduce_partition(uint32_t by_tile_rows, uint32_t root_relief_num, uint32_t root_relief_den);
 
 /* Run on a caller-provided cudaStream_t (e.g. the launcher's current stream); NULL = own. */
 int32_t vt_set_stream(void* cuda_stream);

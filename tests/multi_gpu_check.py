@@ -117,7 +117,7 @@ def main():
     r.fused_reduce_disable()
     r.configure(width=w2, height=h2, mode=abi.MODE_PATHS, spp=spp2, bounces=4, seed=0x5EED, sample_first=0, sample_stride=1, total_spp=spp2)
     assert setup_fused_reduce(r, rank, world, dev)
-    r.fused_reduce_partition(True)
+    r.fused_reduce_partition(True, 1, 16)
     for frame in range(3):
         r.fused_reduce_next_frame()
         r.render_async(P2, V2)
@@ -136,7 +136,7 @@ def main():
             wholes.append((r.read_accum(), r.read_color()))
     r.configure(width=w, height=h, mode=abi.MODE_PATHS, spp=spp, bounces=4, seed=0x5EED, sample_first=0, sample_stride=1, total_spp=spp)
     assert setup_fused_reduce(r, rank, world, dev)
-    r.fused_reduce_partition(True)
+    r.fused_reduce_partition(True, 3, 8)   # the root is dealt 5 tile rows for every 8 of another rank
     rays_rows = 0
     for frame, eye in enumerate(eyes + eyes):
         Pm, Vm = scenes.camera(w, h, eye=eye)

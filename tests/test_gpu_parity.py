@@ -690,7 +690,7 @@ def test_fused_accumulation_data_path_with_one_rank(renderer, scene, assets):
         renderer.fused_reduce_export(1)
         try:
             for by_rows in (False, True):
-                renderer.fused_reduce_partition(by_rows)
+                renderer.fused_reduce_partition(by_rows, 2 if by_rows else 0, 8)
                 for (P, V), (want, rays, iters) in zip(cams, wants):
                     renderer.fused_reduce_next_frame()
                     renderer.render_async(P, V)

@@ -133,3 +133,20 @@ def test_multi_model_vox_and_default_palette_across_the_three_loaders(oracle, tm
         assert np.array_equal(chunks[m].get_raw(), want.reshape(-1))
         assert dumped[m] == f"model {m} dims {sx} {sy} {sz} fnv1a {_fnv1a64(want.tobytes()):016x}"
     assert oracle.load_vox_model(path, 3) is None
+
+
+def test_tile_row_ownership_of_the_fused_reduction():
+    """vt_fused_reduce_partition shares a frame by rows of tiles; the host-side mirror of the device rule: every row has one
+    owner, the root's share shrinks by eighths, the other ranks' shares stay equal."""
+    from vtrace_b200.distributed import row_owner, rows_per_rank
+    assert [row_owner(t, 1) for t in range(5)] == [0] * 5
+    assert [row_owner(t, 4) for t in range(8)] == [0, 1, 2, 3, 0, 1, 2, 3]
+    for world in (2, 4, 8):
+        for relief in range(8):
+            cycle = relief * (world - 1) + (8 - relief) * world
+            counts = rows_per_rank(cycle * 3, world, relief)
+            assert counts[0] == 3 * (8 - relief) and all(c == 24 for c in counts[1:]), (world, relief, counts)
+            assert sum(counts) == cycle * 3
+    # 270 tile rows of a 1080p frame over 8 ranks, the root relieved by 2/8
+    counts = rows_per_rank(270, 8, 2)
+    assert sum(counts) == 270 and counts[0] < min(counts[1:]) and max(counts[1:]) - min(counts[1:]) <= 2

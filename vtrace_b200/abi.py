@@ -80,7 +80,7 @@ SYMBOLS = {
     "vt_fused_reduce_import": (_i32, [_vp, _u32, _u32]),
     "vt_fused_reduce_next_frame": (_i32, []),
     "vt_fused_reduce_disable": (_i32, []),
-    "vt_fused_reduce_partition": (_i32, [_u32]),
+    "vt_fused_reduce_partition": (_i32, [_u32, _u32, _u32]),
     "vt_set_stream": (_i32, [_vp]),
     "vt_get_stats": (_i32, [C.POINTER(VtStats)]),
     "vt_measure_peak": (_i32, [_u32, C.POINTER(C.c_double)]),

@@ -1559,21 +1559,19 @@ __device__ __forceinline__ void fused_sync_end(const FusedSync& fs) {
 template <bool kCompact>
 __global__ void __launch_bounds__(256) push_partial_kernel(const InstUniforms* __restrict__ inst, unsigned long long* __restrict__ local_accum,
                                                            uint4* __restrict__ slot, uint32_t width, uint32_t height,
-                                                           uint32_t row_first, uint32_t row_stride, FusedSync fs) {
+                                                           RowShare rows, FusedSync fs) {
     fused_sync_begin(fs);
     const int x0 = max(inst->bounds[0], 0), x1 = min(inst->bounds[1], (int)width - 1);
     const int y0 = max(inst->bounds[2], 0), y1 = min(inst->bounds[3], (int)height - 1);
     // the pixels of the rectangle's lines this rank owns, numbered consecutively: one grid-stride loop over all of them
     const int rect_w = x1 - x0 + 1;
-    const int rs = row_stride > 1 ? (int)row_stride : 1;
     const int t0 = y0 / kTileH, t1 = y1 / kTileH;
-    const int ty0 = t0 + (int)((row_first + (uint32_t)rs - (uint32_t)t0 % (uint32_t)rs) % (uint32_t)rs); // first owned tile row
-    const int own_tile_rows = (y0 <= y1 && rect_w > 0 && ty0 <= t1) ? (t1 - ty0) / rs + 1 : 0;
+    const int own_tile_rows = (y0 <= y1 && rect_w > 0) ? (int)rows.rows_in((uint32_t)t0, (uint32_t)t1) : 0;
     const long long total = (long long)own_tile_rows * kTileH * rect_w;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int line = (int)(i / rect_w), px = x0 + (int)(i - (long long)line * rect_w);
-        const int py = (ty0 + (line / kTileH) * rs) * kTileH + line % kTileH;
-        if (py < y0 || py > y1) continue; // (the first and last tile row may be cut by the rectangle)
+        const int py = (int)rows.row((uint32_t)t0, (uint32_t)(line / kTileH)) * kTileH + line % kTileH;
+        if (py < y0 || py > y1) continue; // (enumerated rows may lie outside the rectangle; the first and last may be cut by it)
         const size_t p = (size_t)py * width + (size_t)px;
         const unsigned long long r = local_accum[3 * p + 0], g = local_accum[3 * p + 1], b = local_accum[3 * p + 2];
         local_accum[3 * p + 0] = 0ull; local_accum[3 * p + 1] = 0ull; local_accum[3 * p + 2] = 0ull;
@@ -1591,7 +1589,7 @@ template <bool kCompact>
 __global__ void __launch_bounds__(256) resolve_partials_kernel(const InstUniforms* __restrict__ inst, const uint4* __restrict__ partials,
                                                                uint32_t world, uint32_t width, uint32_t height, uint32_t total_spp,
                                                                SrgbTables lut, uchar4* __restrict__ color,
-                                                               unsigned long long* __restrict__ accum_out, uint32_t row_stride,
+                                                               unsigned long long* __restrict__ accum_out, RowShare rows,
                                                                unsigned long long* __restrict__ root_local, uint4* __restrict__ root_slot,
                                                                FusedSync fs) {
     fused_sync_begin(fs);
@@ -1616,8 +1614,8 @@ __global__ void __launch_bounds__(256) resolve_partials_kernel(const InstUniform
             }
             unsigned long long sum[3] = {0ull, 0ull, 0ull};
             // shared out by tile rows: the owner's slot holds the pixel's complete sums
-            const uint32_t r_begin = row_stride > 1 ? (py / (uint32_t)kTileH) % row_stride : 0u;
-            const uint32_t r_end = row_stride > 1 ? r_begin + 1u : world;
+            const uint32_t r_begin = rows.world > 1u ? rows.owner(py / (uint32_t)kTileH) : 0u;
+            const uint32_t r_end = rows.world > 1u ? r_begin + 1u : world;
             for (uint32_t r = r_begin; r < r_end; ++r) { // (a slot is n_pix * 32 bytes whatever the layout; L1 is bypassed: peers wrote these lines)
                 if (r == 0u && root_local) { // the root's own sums never travelled: take them from its accumulators
                     const unsigned long long lr = root_local[3 * p + 0], lg = root_local[3 * p + 1], lb = root_local[3 * p + 2];
@@ -1651,20 +1649,20 @@ __global__ void __launch_bounds__(256) resolve_partials_kernel(const InstUniform
 }
 
 cudaError_t launch_push_partial(const InstUniforms* inst, unsigned long long* local_accum, uint4* slot, uint32_t width, uint32_t height,
-                                bool compact, uint32_t row_first, uint32_t row_stride, FusedSync fs, int sm_count, cudaStream_t stream) {
+                                bool compact, RowShare rows, FusedSync fs, int sm_count, cudaStream_t stream) {
     const int grid = sm_count * 4; // grid-stride over the owned pixels
-    if (compact) push_partial_kernel<true><<<grid, 256, 0, stream>>>(inst, local_accum, slot, width, height, row_first, row_stride, fs);
-    else push_partial_kernel<false><<<grid, 256, 0, stream>>>(inst, local_accum, slot, width, height, row_first, row_stride, fs);
+    if (compact) push_partial_kernel<true><<<grid, 256, 0, stream>>>(inst, local_accum, slot, width, height, rows, fs);
+    else push_partial_kernel<false><<<grid, 256, 0, stream>>>(inst, local_accum, slot, width, height, rows, fs);
     return cudaGetLastError();
 }
 
 cudaError_t launch_resolve_partials(const InstUniforms* inst, const uint4* partials, uint32_t world, uint32_t width, uint32_t height,
                                     uint32_t total_spp, SrgbTables lut, uchar4* color, unsigned long long* accum_out, bool compact,
-                                    uint32_t row_stride, unsigned long long* root_local, uint4* root_slot, FusedSync fs, int sm_count,
+                                    RowShare rows, unsigned long long* root_local, uint4* root_slot, FusedSync fs, int sm_count,
                                     cudaStream_t stream) {
     const int grid = sm_count * 4 < (int)height ? sm_count * 4 : (int)height;
-    if (compact) resolve_partials_kernel<true><<<grid, 256, 0, stream>>>(inst, partials, world, width, height, total_spp, lut, color, accum_out, row_stride, root_local, root_slot, fs);
-    else resolve_partials_kernel<false><<<grid, 256, 0, stream>>>(inst, partials, world, width, height, total_spp, lut, color, accum_out, row_stride, root_local, root_slot, fs);
+    if (compact) resolve_partials_kernel<true><<<grid, 256, 0, stream>>>(inst, partials, world, width, height, total_spp, lut, color, accum_out, rows, root_local, root_slot, fs);
+    else resolve_partials_kernel<false><<<grid, 256, 0, stream>>>(inst, partials, world, width, height, total_spp, lut, color, accum_out, rows, root_local, root_slot, fs);
     return cudaGetLastError();
 }
 

@@ -53,6 +53,40 @@ struct BrickVolume {
 static constexpr uint32_t kVolumeDense = 0, kVolumeHeightmap = 1, kVolumeSparseBricks = 2, kVolumeUploadedBricks = 3;
 
 // Per-frame uniforms, passed by value as a kernel parameter (constant bank, no loads).
+// How the ranks of a fused multi-GPU reduction share a frame by rows of 8x4-pixel tiles.  Tile rows are dealt in cycles of
+// c * (world - 1) + (k - c) * world rows: the first c rounds of a cycle go to ranks 1 .. world - 1 only, the remaining k - c
+// rounds to every rank in turn, so the root (rank 0), which also sums the slots and encodes the frame, owns (k - c) rows of a
+// cycle and everybody else k.  world <= 1: one rank owns everything.
+struct RowShare {
+    uint32_t rank, world, k, c;
+#ifdef __CUDACC__
+    __host__ __device__ uint32_t cycle() const { return c * (world - 1u) + (k - c) * world; }
+    __host__ __device__ uint32_t own_per_cycle() const { return rank == 0u ? k - c : k; }
+    __host__ __device__ uint32_t owner(uint32_t ty) const {
+        if (world <= 1u) return 0u;
+        const uint32_t q = ty % cycle(), skip = c * (world - 1u);
+        return q < skip ? 1u + q % (world - 1u) : (q - skip) % world;
+    }
+    // position inside a cycle of this rank's j-th row of the cycle (j < own_per_cycle())
+    __host__ __device__ uint32_t own_pos(uint32_t j) const {
+        const uint32_t skip = c * (world - 1u);
+        if (rank == 0u) return skip + j * world;
+        return j < c ? (rank - 1u) + j * (world - 1u) : skip + rank + (j - c) * world;
+    }
+    // this rank's rows among the tile rows [t0, t1], enumerated by cycle (a superset: rows_in() entries, of which row(i) may
+    // fall outside [t0, t1] — callers skip those)
+    __host__ __device__ uint32_t rows_in(uint32_t t0, uint32_t t1) const {
+        if (world <= 1u) return t1 - t0 + 1u;
+        return (t1 / cycle() - t0 / cycle() + 1u) * own_per_cycle();
+    }
+    __host__ __device__ uint32_t row(uint32_t t0, uint32_t i) const {
+        if (world <= 1u) return t0 + i;
+        const uint32_t n = own_per_cycle();
+        return (t0 / cycle() + i / n) * cycle() + own_pos(i % n);
+    }
+#endif
+};
+
 struct FrameParams {
     float RD[16]; // inverse(centered camera) * inverse(projection), trace.frag:59
     float PV[16]; // projection * camera, trace.vert:45
@@ -75,8 +109,9 @@ struct FrameParams {
     uint32_t clear_rgba;       // clear colour (lib/command.c:56-61) as stored by the sRGB target: r | g<<8 | b<<16 | a<<24
     uint32_t sky_spp;          // samples whose sky radiance this rank adds for pixels outside every screen
                                // rectangle (= spp normally; fused multi-GPU reduction: total on the root, 0 elsewhere)
-    uint32_t row_first, row_stride; // wavefront kernel: this rank traces the tile rows ty = row_first (mod row_stride)
-                                    // (0, 1 = all of them; vt_fused_reduce_partition)
+    uint32_t item_order;       // wavefront kernel: 0 = chunk-major over tiles in row order, 1 = tile-major from the centre of the
+                               // rectangle outwards, 2 = chunk-major, every pass from the centre outwards (VT_ITEM_ORDER)
+    RowShare rows;             // wavefront kernel: the tile rows this rank traces (world <= 1: all; vt_fused_reduce_partition)
 };
 
 // Per-instance uniforms (trace.vert outputs that are flat per instance + derived matrices).
@@ -214,15 +249,15 @@ struct FusedSync {
     unsigned long long* host_stats;
 };
 
-// row_stride > 1: the frame is shared out by rows of tiles (rank r traces every sample of the tile rows ty = r mod
-// row_stride): a rank pushes only its own rows, and the root takes a pixel from its owner's slot instead of summing all
+// rows.world > 1: the frame is shared out by rows of tiles (RowShare): a rank pushes only its own rows, and the root takes a
+// pixel from its owner's slot instead of summing all
 cudaError_t launch_push_partial(const InstUniforms* inst, unsigned long long* local_accum, uint4* slot, uint32_t width, uint32_t height,
-                                bool compact, uint32_t row_first, uint32_t row_stride, FusedSync fs, int sm_count, cudaStream_t stream);
+                                bool compact, RowShare rows, FusedSync fs, int sm_count, cudaStream_t stream);
 // root_local != nullptr: the root's own sums are still in its local accumulators (it does not push): they are taken from
 // there, cleared, and parked in the root's slot (root_slot) for later calls on the same frame
 cudaError_t launch_resolve_partials(const InstUniforms* inst, const uint4* partials, uint32_t world, uint32_t width, uint32_t height,
                                     uint32_t total_spp, SrgbTables lut, uchar4* color, unsigned long long* accum_out, bool compact,
-                                    uint32_t row_stride, unsigned long long* root_local, uint4* root_slot, FusedSync fs, int sm_count,
+                                    RowShare rows, unsigned long long* root_local, uint4* root_slot, FusedSync fs, int sm_count,
                                     cudaStream_t stream);
 // single-instance frames: zero / resolve only the instance's screen rectangle; sky_only: write spp x sky into the
 // accumulators outside it instead (they are not touched by such a frame otherwise)

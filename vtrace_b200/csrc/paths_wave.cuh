@@ -208,10 +208,10 @@ __global__ void __launch_bounds__(kWaveThreads, kWaveCtas) trace_paths_wave_kern
     const bool any_cov = Ip->bounds[0] <= Ip->bounds[1] && Ip->bounds[2] <= Ip->bounds[3];
     const int ctx0 = any_cov ? Ip->bounds[0] / kTileW : 0, ctx1 = any_cov ? Ip->bounds[1] / kTileW : -1;
     const int cty0 = any_cov ? Ip->bounds[2] / kTileH : 0, cty1 = any_cov ? Ip->bounds[3] / kTileH : -1;
-    // multi-GPU, frame shared out by rows of tiles: this rank's rows are own_y0, own_y0 + rs, ...
-    const int rs = fp.row_stride > 1u ? (int)fp.row_stride : 1;
-    const int own_y0 = cty0 + (int)((fp.row_first + (uint32_t)rs - (uint32_t)cty0 % (uint32_t)rs) % (uint32_t)rs);
-    const int own_rows = cty1 >= own_y0 ? (cty1 - own_y0) / rs + 1 : 0;
+    // multi-GPU, frame shared out by rows of tiles: this rank's rows (RowShare; a few of the enumerated rows may lie outside
+    // the rectangle: their tiles have no covered pixel and cost one claim)
+    const RowShare rows = fp.rows;
+    const int own_rows = any_cov ? (int)rows.rows_in((uint32_t)cty0, (uint32_t)cty1) : 0;
     const int cov_w = ctx1 - ctx0 + 1, cov_tiles = cov_w * own_rows;
     // Work item = one tile x `item_spp` samples.  Items are sized so that there are several per resident
     // warp even when a rank only has a few samples per pixel (multi-GPU), otherwise the tail dominates.
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(kWaveThreads, kWaveCtas) trace_paths_wave_kern
         for (int tile = gw; tile < n_tiles; tile += nw) {
             const int tx = tile % tiles_x, ty = tile / tiles_x;
             const int px = tx * kTileW + (lane & 7), py = ty * kTileH + (lane >> 3);
-            const bool in_frame = px < fp.width && py < fp.height && (uint32_t)ty % (uint32_t)rs == fp.row_first % (uint32_t)rs;
+            const bool in_frame = px < fp.width && py < fp.height && rows.owner((uint32_t)ty) == rows.rank;
             const bool may_hit = !(px < Ip->bounds[0] || px > Ip->bounds[1] || py < Ip->bounds[2] || py > Ip->bounds[3]);
             if (in_frame && !may_hit) {
                 const size_t p = (size_t)py * (size_t)fp.width + (size_t)px;
@@ -410,12 +410,40 @@ __global__ void __launch_bounds__(kWaveThreads, kWaveCtas) trace_paths_wave_kern
 #endif
             if (item >= n_items) { work_left = false; break; }
             flush_tile();
-            const int chunk = item / cov_tiles, ct = item - chunk * cov_tiles; // chunk-major: a tile's chunks are spread in time
-            const int cy = ct / cov_w, cx = ct - cy * cov_w;
-            const int tile = (own_y0 + cy * rs) * tiles_x + (ctx0 + cx);
+            int chunk, cy, cx;
+            if (fp.item_order == 0u) { // chunk-major over the tiles in row order: a tile's chunks are spread in time
+                chunk = item / cov_tiles;
+                const int ct = item - chunk * cov_tiles;
+                cy = ct / cov_w; cx = ct - cy * cov_w;
+            } else {
+                // Tile-major, from the centre of the rectangle outwards: the instance fills the middle of its screen rectangle,
+                // so the tiles whose paths bounce longest are started first and the frame ends on border tiles, whose paths
+                // mostly leave through the sky after one segment — the drain of the last paths is short.  Rings are counted from
+                // the outside (ring r = tiles r away from the nearest edge); q counts tiles from the END of the order.
+                int ct;
+                if (fp.item_order == 1u) { ct = item / n_chunks; chunk = item - ct * n_chunks; }
+                else { chunk = item / cov_tiles; ct = item - chunk * cov_tiles; } // (2: chunk-major, every pass from the centre outwards)
+                const int q = cov_tiles - 1 - ct;
+                int r = 0, before = 0; // tiles in the rings outside ring r
+                for (;;) {
+                    const int w_in = cov_w - 2 * (r + 1), h_in = own_rows - 2 * (r + 1);
+                    const int upto = cov_tiles - (w_in > 0 && h_in > 0 ? w_in * h_in : 0); // tiles in rings 0 .. r
+                    if (q < upto) break;
+                    before = upto;
+                    ++r;
+                }
+                const int w_r = cov_w - 2 * r, h_r = own_rows - 2 * r; // ring r is the border of a w_r x h_r box at (r, r)
+                int k = q - before;
+                if (w_r == 1) { cy = r + k; cx = r; }                                          // a single column
+                else if (h_r == 1 || k < w_r) { cy = r; cx = r + k; }                          // top edge (or the single row)
+                else if (k < 2 * w_r) { cy = r + h_r - 1; cx = r + (k - w_r); }                // bottom edge
+                else { k -= 2 * w_r; cy = r + 1 + (k >> 1); cx = (k & 1) ? r + w_r - 1 : r; }  // left / right columns in between
+            }
+            const int ty = (int)rows.row((uint32_t)cty0, (uint32_t)cy);
+            const int tile = ty * tiles_x + (ctx0 + cx);
             it_tile = (uint32_t)tile;
             it_x0 = (ctx0 + cx) * kTileW;
-            it_y0 = (own_y0 + cy * rs) * kTileH;
+            it_y0 = ty * kTileH;
             const int my_px = it_x0 + (lane & 7), my_py = it_y0 + (lane >> 3);
             const bool in_frame = my_px < fp.width && my_py < fp.height;
             const bool may_hit = in_frame && !(my_px < Ip->bounds[0] || my_px > Ip->bounds[1] || my_py < Ip->bounds[2] || my_py > Ip->bounds[3]);

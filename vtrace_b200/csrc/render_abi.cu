@@ -98,7 +98,8 @@ struct State {
     uint32_t* d_fused_err = nullptr;
     uint32_t* h_fused_err = nullptr; // pinned
     bool fused_sync = true;
-    bool fused_rows = false;         // vt_fused_reduce_partition(1): the frame is shared out by rows of tiles, not by samples
+    bool fused_rows = false;         // vt_fused_reduce_partition(1, ...): the frame is shared out by rows of tiles, not by samples
+    uint32_t fused_relief = 0, fused_relief_den = 8; // ... of which the root owns (den - relief) for every den of another rank (RowShare)
     // root: the last frame's own sums are still in d_accum_own (the root does not push; its first vt_resolve / vt_read_accum
     // of the frame takes them from there) and its counters in d_stats (published by the same kernel), ring slot below
     bool fused_root_live = false;
@@ -125,6 +126,7 @@ struct State {
     uint32_t refill_batch = 10;     // wavefront kernel: stopped lanes wait until this many can be refilled together (VT_REFILL_BATCH)
     uint32_t item_spp = 16;         // wavefront kernel: most samples per work item (VT_ITEM_SPP)
     uint32_t items_per_warp = 6;    // wavefront kernel: work items wanted per resident warp (VT_ITEMS_PER_WARP)
+    uint32_t item_order = 0;        // wavefront kernel: order of the work items (VT_ITEM_ORDER, FrameParams::item_order)
 
     vt_stats stats{};
     user_input input{};
@@ -284,6 +286,17 @@ static FusedSync fused_wait_all() {
     }
     return fs;
 }
+// rows of tiles per rank (vt_fused_reduce_partition); world 1 = every rank holds every row (frames shared by samples)
+static RowShare fused_row_share() {
+    RowShare rs{0u, 1u, g.fused_relief_den, 0u};
+    if (g.fused_rows) {
+        rs.rank = g.fused_rank; rs.world = g.fused_world; rs.c = g.fused_world > 1 ? g.fused_relief : 0u;
+        // (profiling aid: one rank of an N-rank job on its own — VT_FUSED_ROWS_AS_WORLD=N traces and moves rank 0's rows only)
+        static const uint32_t as_world = env_u32("VT_FUSED_ROWS_AS_WORLD", 0);
+        if (as_world && g.fused_world == 1) { rs.world = as_world; rs.c = g.fused_relief; }
+    }
+    return rs;
+}
 static bool fused_compact() { return (g.cfg.total_spp ? g.cfg.total_spp : g.cfg.spp) <= 255u; }
 // The root's summation (vt_resolve / vt_read_accum).  The first one of a frame also collects the root's own sums from its
 // local accumulators and publishes the frame's counters, so the frame's end event is recorded again behind it.
@@ -294,7 +307,7 @@ static cudaError_t fused_root_sum(unsigned long long* accum_out) {
     FusedSync fs = fused_wait_all();
     if (g.fused_root_live) { fs.stats = g.d_stats; fs.host_stats = g.h_stats + 4 * g.fused_root_slot; }
     cudaError_t e = launch_resolve_partials(g.d_iu, half, g.fused_world, g.cfg.width, g.cfg.height, total ? total : 1, lut, g.d_color, accum_out,
-                                            fused_compact(), g.fused_rows ? g.fused_world : 1u, g.fused_root_live ? g.d_accum_own : nullptr, half,
+                                            fused_compact(), fused_row_share(), g.fused_root_live ? g.d_accum_own : nullptr, half,
                                             fs, g.sm_count, g.stream);
     if (e == cudaSuccess && g.fused_root_live) {
         g.fused_root_live = false;
@@ -404,6 +417,7 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
     fp.refill_batch = g.refill_batch;
     fp.item_spp = g.item_spp;
     fp.items_per_warp = g.items_per_warp;
+    fp.item_order = g.item_order;
     {   // sun direction (0.4, -0.8, 0.45), normalised (same float operations as the oracle)
         const float sx = 0.4f, sy = -0.8f, sz = 0.45f;
         const float l = sqrtf((sx * sx + sy * sy) + sz * sz);
@@ -423,10 +437,7 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
         if (g.fused_rows) {
             if (g.cfg.sample_first != 0 || g.cfg.sample_stride > 1 || (g.cfg.total_spp && g.cfg.total_spp != g.cfg.spp))
                 return fail("fused accumulation by tile rows: every rank traces all samples (sample_first 0, sample_stride 1, spp = total_spp)");
-            fp.row_first = g.fused_rank;
-            fp.row_stride = g.fused_world;
-            // (profiling aid: one rank of an N-rank job on its own — VT_FUSED_ROWS_AS_WORLD=N traces rank 0's rows only)
-            if (const uint32_t as_world = env_u32("VT_FUSED_ROWS_AS_WORLD", 0)) fp.row_stride = as_world;
+            fp.rows = fused_row_share();
         }
     }
 
@@ -580,8 +591,8 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
                 fs.err = g.d_fused_err;
             }
             fs.stats = g.d_stats; fs.host_stats = g.h_stats + 4 * slot; // (the frame's counters travel with this kernel)
-            CK(launch_push_partial(g.d_iu, g.d_accum_own, peer_slot, g.cfg.width, g.cfg.height, fused_compact(), g.fused_rank,
-                                   g.fused_rows ? g.fused_world : 1u, fs, g.sm_count, g.stream));
+            CK(launch_push_partial(g.d_iu, g.d_accum_own, peer_slot, g.cfg.width, g.cfg.height, fused_compact(), fused_row_share(), fs,
+                                   g.sm_count, g.stream));
             g.stats.launches += 1;
         }
         if (resolve && !fused) {
@@ -716,6 +727,8 @@ extern "C" uint64_t entry(void) {
     g.item_spp = env_u32("VT_ITEM_SPP", 16);
     if (g.item_spp < 1) g.item_spp = 1;
     if (g.item_spp > 255) g.item_spp = 255; // an item's per-pixel sums live in 32-bit shared counters: 255 samples of < 2^24 each
+    g.item_order = env_u32("VT_ITEM_ORDER", 0); // (1 and 2 measured: whole frame +6 % / +1 %; a rank's tile rows -4 % .. +8 %, box to box)
+    if (g.item_order > 2u) g.item_order = 0;
     g.items_per_warp = env_u32("VT_ITEMS_PER_WARP", 6);
     if (g.items_per_warp < 1) g.items_per_warp = 1;
     if (g.refill_batch < 1) g.refill_batch = 1;
@@ -1269,11 +1282,15 @@ extern "C" int32_t vt_fused_reduce_import(const uint8_t handle[64], uint32_t ran
     return 0;
 }
 
-extern "C" int32_t vt_fused_reduce_partition(uint32_t by_tile_rows) {
+extern "C" int32_t vt_fused_reduce_partition(uint32_t by_tile_rows, uint32_t root_relief_num, uint32_t root_relief_den) {
     if (!g.inited || !g.fused_mode) return fail("vt_fused_reduce_partition: no fused reduction set up");
+    if (root_relief_den < 1u || root_relief_den > 64u || root_relief_num >= root_relief_den)
+        return fail("vt_fused_reduce_partition: the root's relief is num / den with den in 1 .. 64 and num < den");
     CK(cudaSetDevice(g.device));
     if (finish_frame()) return -1;
     g.fused_rows = by_tile_rows != 0;
+    g.fused_relief = root_relief_num;
+    g.fused_relief_den = root_relief_den;
     return 0;
 }
 

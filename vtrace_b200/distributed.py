@@ -100,3 +100,22 @@ def stream_barrier(flag):
     import torch.distributed as dist
 
     dist.all_reduce(flag)
+
+
+def row_owner(tile_row: int, world: int, relief_num: int = 0, relief_den: int = 8) -> int:
+    """Owner of a row of 8x4-pixel tiles when a fused reduction shares frames by tile rows (vt_fused_reduce_partition; the
+    device-side rule is RowShare in csrc/kernels.h).  Rows are dealt in cycles of c*(world-1) + (k-c)*world: the first c
+    rounds of a cycle skip the root, the other k-c include it — the root owns k-c rows of a cycle, every other rank k."""
+    if world <= 1:
+        return 0
+    c, k = relief_num, relief_den
+    skip = c * (world - 1)
+    q = tile_row % (skip + (k - c) * world)
+    return 1 + q % (world - 1) if q < skip else (q - skip) % world
+
+
+def rows_per_rank(n_tile_rows: int, world: int, relief_num: int = 0, relief_den: int = 8) -> list[int]:
+    counts = [0] * max(world, 1)
+    for ty in range(n_tile_rows):
+        counts[row_owner(ty, world, relief_num, relief_den)] += 1
+    return counts

@@ -262,9 +262,10 @@ class Renderer:
         if self._lib.vt_fused_reduce_disable() != 0:
             raise RuntimeError("vt_fused_reduce_disable failed: " + abi.last_error())
 
-    def fused_reduce_partition(self, by_tile_rows: bool):
-        """False: ranks share a frame by samples; True: by rows of 8x4 tiles, every rank tracing all samples of its rows."""
-        if self._lib.vt_fused_reduce_partition(1 if by_tile_rows else 0) != 0:
+    def fused_reduce_partition(self, by_tile_rows: bool, relief_num: int = 0, relief_den: int = 8):
+        """False: ranks share a frame by samples; True: by rows of 8x4 tiles, every rank tracing all samples of its rows (the
+        root relief_den - relief_num rows for every relief_den of another rank)."""
+        if self._lib.vt_fused_reduce_partition(1 if by_tile_rows else 0, relief_num, relief_den) != 0:
             raise RuntimeError("vt_fused_reduce_partition failed: " + abi.last_error())
 
     def set_accum_buffer(self, device_ptr: int | None):
