@@ -24,3 +24,4 @@ timeout 600 $NCU -k regex:trace_primary_kernel -s 5 -o $O/prof_primary python to
 timeout 600 $NCU -k regex:trace_primary_kernel -s 3 -o $O/prof_heightmap python tools/run_config.py --config heightmap_4k --frames 3 --warmup 1 > $O/ncu_heightmap.log 2>&1
 timeout 600 $NCU -k regex:trace_rays_kernel -s 2 -o $O/prof_rays python tools/run_config.py --config sparse_rays --frames 2 --warmup 1 > $O/ncu_rays.log 2>&1
 timeout 600 $NCU -k regex:trace_paths_kernel -s 2 -o $O/prof_world python tools/run_config.py --config world_paths --frames 3 --warmup 1 > $O/ncu_world.log 2>&1
+timeout 600 $NCU -k regex:trace_paths_kernel -s 2 -o $O/prof_grid python tools/run_config.py --config temple_paths --grid --spp 8 --frames 3 --warmup 1 > $O/ncu_grid.log 2>&1
