@@ -708,6 +708,13 @@ def test_fused_accumulation_data_path_with_one_rank(renderer, scene, assets):
             with pytest.raises(RuntimeError, match="for every frame"):
                 renderer.render_async(*cams[0])
             renderer.resolve()
+            # ... and every frame has its own sequence number
+            renderer.render_async(*cams[0])      # (uses the number the refused frame did not consume)
+            renderer.resolve()
+            with pytest.raises(RuntimeError, match="vt_fused_reduce_next_frame"):
+                renderer.render_async(*cams[0])
+            with pytest.raises(RuntimeError, match="own buffer"):
+                renderer.set_accum_buffer(1 << 20)   # (any non-null pointer: refused before it is ever used)
         finally:
             renderer.fused_reduce_disable()
 

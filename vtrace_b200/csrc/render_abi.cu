@@ -104,6 +104,7 @@ struct State {
     // of the frame takes them from there) and its counters in d_stats (published by the same kernel), ring slot below
     bool fused_root_live = false;
     uint32_t fused_root_slot = 0;
+    uint32_t fused_seq_rendered = 0; // sequence number of the last frame rendered: every frame needs its own (vt_fused_reduce_next_frame)
     unsigned long long* fused_sum = nullptr; // root, on demand: materialised sums for vt_read_accum
     // asynchronous colour read-back (vt_read_color_async): a second colour buffer, a copy stream, one event per buffer
     uchar4* d_color_alt = nullptr;
@@ -433,6 +434,8 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
         if (g.fused_pixels != (size_t)g.cfg.width * g.cfg.height) return fail("fused accumulation buffer does not match the framebuffer size");
         if (g.fused_mode == 1 && g.fused_root_live)
             return fail("fused cross-GPU accumulation: the root must call vt_resolve (or vt_read_accum) for every frame before it starts the next");
+        if (g.fused_seq != 0 && g.fused_seq == g.fused_seq_rendered) // (the flags of this sequence number are already up: the root would not wait)
+            return fail("fused cross-GPU accumulation: vt_fused_reduce_next_frame must be called before every frame");
         fp.sky_spp = 0u; // pixels outside the screen rectangle are resolved analytically on the root
         if (g.fused_rows) {
             if (g.cfg.sample_first != 0 || g.cfg.sample_stride > 1 || (g.cfg.total_spp && g.cfg.total_spp != g.cfg.spp))
@@ -468,6 +471,7 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
     uint32_t consumed_value = 0;
     if (g.fused_mode && g.cfg.mode == VT_MODE_PATHS) {
         if (g.fused_seq == 0) { g.fused_seq = 1; g.fused_index = 1; } // (vt_fused_reduce_next_frame was not called yet)
+        g.fused_seq_rendered = g.fused_seq;
         // the root is done with the previous frame once it starts this one: its half may be refilled
         // (raised by the instance-setup kernel below, the first kernel of the frame)
         if (g.fused_sync && g.fused_mode == 1 && g.fused_seq > 1) {
@@ -1194,6 +1198,7 @@ extern "C" int32_t vt_set_accum_buffer(void* device_ptr) {
     CK(cudaSetDevice(g.device));
     if (finish_frame()) return -1;
     if (complete_accum()) return -1;
+    if (g.fused_mode && device_ptr) return fail("vt_set_accum_buffer: a fused reduction accumulates in the library's own buffer (vt_fused_reduce_disable first)");
     CK(cudaStreamSynchronize(g.stream));
     g.d_accum = device_ptr ? (unsigned long long*)device_ptr : g.d_accum_own;
     return 0;
@@ -1232,6 +1237,9 @@ static int fused_common(uint32_t rank, uint32_t world) {
     g.fused_world = world;
     g.fused_index = 0;
     g.fused_seq = 0;
+    g.fused_seq_rendered = 0;
+    g.fused_root_live = false;
+    g.fused_rows = false;
     g.fused_sync = env_u32("VT_FUSED_SYNC", 1) != 0; // 0: the caller orders the ranks itself (a stream barrier per frame)
     if (world > kFusedMaxWorld) return fail("fused reduction: at most %u ranks", kFusedMaxWorld);
     if (!g.d_fused_err) {
