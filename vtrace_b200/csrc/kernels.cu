@@ -1160,10 +1160,18 @@ __device__ void trace_world(const FrameParams& fp, const InstUniforms* __restric
                 for (int k = 0; k < 3; ++k) d[k] = (J->dirm[0 * 3 + k] * cam[0] + J->dirm[1 * 3 + k] * cam[1]) + J->dirm[3 * 3 + k];
             }
         } else {
+            if (lin) {
+                // inverse(M)'s off-diagonal entries are +-0: the general sum below adds +-0 to lin[k] * ow[k], which changes
+                // nothing but, possibly, the sign of an exact zero — and o[k] = +-0 gives the same slab bounds, the same
+                // comparisons and the same entry point (its sign can only survive into mp[k] + 0.5)
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                o[k] = ((J->Mi[0 * 3 + k] * ow[0] + J->Mi[1 * 3 + k] * ow[1]) + J->Mi[2 * 3 + k] * ow[2]) + J->Mi[3 * 3 + k];
-                if (!lin) d[k] = (J->Mi[0 * 3 + k] * dw[0] + J->Mi[1 * 3 + k] * dw[1]) + J->Mi[2 * 3 + k] * dw[2];
+                for (int k = 0; k < 3; ++k) o[k] = J->lin[k] * ow[k] + J->Mi[3 * 3 + k];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    o[k] = ((J->Mi[0 * 3 + k] * ow[0] + J->Mi[1 * 3 + k] * ow[1]) + J->Mi[2 * 3 + k] * ow[2]) + J->Mi[3 * 3 + k];
+                    d[k] = (J->Mi[0 * 3 + k] * dw[0] + J->Mi[1 * 3 + k] * dw[1]) + J->Mi[2 * 3 + k] * dw[2];
+                }
             }
         }
         const float lo3[3] = {-0.5f - o[0], -0.5f - o[1], -0.5f - o[2]};
