@@ -14,7 +14,7 @@
 // the walk needs no coordinate compares: leaving the volume is found by the same lookup as entering
 // a brick.
 // Traversal keeps the reference's per-voxel float DDA (trace.frag:73-87) bit for bit — same steps,
-// same ties — but touches memory only when the ray enters a new brick (l1 bit, then the slot) and,
+// same ties — but touches memory only when the ray enters a new brick (its two-bit code, then the slot base) and,
 // inside non-empty bricks, one word per step; empty bricks are walked with arithmetic alone.
 // Colour is a function of the voxel position, evaluated at the hit.
 #pragma once

@@ -979,7 +979,7 @@ __device__ __forceinline__ void rng_sphere(Rng& r, float s[3]) {
 // memory here (the mode exists for volumes far larger than shared memory).
 // Record: hit_voxel = x | y << 16, instance = z, packed = steps | face bits << 16, iters = steps.
 #ifndef VT_RAYS_MIN_BLOCKS
-#define VT_RAYS_MIN_BLOCKS 5 // 48 registers (a few spills) for 5 CTAs per SM: the walk waits on l1 / table / pool loads (configs[4]: 36.3 -> 34.0 ms)
+#define VT_RAYS_MIN_BLOCKS 5 // 48 registers (a few spills) for 5 CTAs per SM: the walk waits on directory / pool loads (configs[4]: 36.3 -> 34.0 ms)
 #endif
 __global__ void __launch_bounds__(kBlockThreads, VT_RAYS_MIN_BLOCKS) trace_rays_kernel(const __grid_constant__ FrameParams fp,
                                                                    const InstUniforms* __restrict__ inst,

@@ -34,9 +34,10 @@
 //        q2 = prev idx, steps, rng key, -
 //   path p0 = thr.rgb, pixel handle   p1 = pos.xyz, len          p2 = dir.xyz, meta
 //
-// Multi-GPU: fb.accum may point at ANOTHER GPU's accumulation buffer (CUDA IPC mapping over NVLink,
-// see vt_fused_reduce_*): the per-tile flushes below are integer atomics, which work on peer memory
-// and commute, so N ranks tracing disjoint samples add into one buffer with no separate all-reduce.
+// Multi-GPU: every rank accumulates in its OWN buffer (remote atomics from inside this kernel were tried and
+// dropped) and a separate kernel moves the sums to the root.  A rank traces either a subset of
+// the samples of every pixel (fp.sample_first / sample_stride) or every sample of the tile rows fp.rows
+// deals to it (RowShare); the per-tile flushes are integer adds, so the image is the same either way.
 #pragma once
 
 // Shape of a CTA: warps, paths in flight per warp, CTAs per SM.  (Compile-time knobs so that variants can be
