@@ -181,7 +181,11 @@ int64_t vt_read_color(uint8_t* rgba8, size_t capacity); /* R,G,B,A bytes, sRGB-e
  * PAGE-LOCKED host memory on the library's copy stream and return at once; the next frame renders into a second colour
  * buffer, so tracing frame k+1 overlaps the PCIe transfer of frame k.  The destination is valid after vt_read_color_wait
  * (host blocks until every read-back issued so far has landed).  vt_read_color_fence makes the library's STREAM wait for
- * them instead (no host wait), e.g. to time a pipelined loop with events.  Returns the byte count, -1 on error. */
+ * them instead (no host wait), e.g. to time a pipelined loop with events.  The transfer itself starts when the next
+ * frame's trace kernel starts, or at the next vt_read_color_wait / _fence / _async, whichever comes first: while a
+ * device-to-host copy saturates PCIe the GPU's command fetches queue behind it, so a copy that runs under the set-up
+ * kernels of the next frame delays them, and one that runs under its long trace kernel delays nothing
+ * (VT_DEFER_READBACK=0 starts it at once).  Returns the byte count, -1 on error. */
 int64_t vt_read_color_async(uint8_t* pinned_rgba8, size_t capacity);
 int32_t vt_read_color_wait(void);
 int32_t vt_read_color_fence(void);

@@ -111,6 +111,11 @@ struct State {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_color_ready = nullptr, ev_copy_done[2] = {nullptr, nullptr}; // [0] belongs to d_color, [1] to d_color_alt
     bool copy_pending[2] = {false, false};
+    // A read-back is not started when it is asked for but when the NEXT frame's trace kernel starts (or when somebody waits
+    // for it): while a device->host copy saturates PCIe, the GPU's command fetches queue behind it, and the small kernels at
+    // the start of a frame (set-up, clear) were measured 30-70 us slower.  Under the long trace kernel nothing is fetched.
+    struct { bool armed = false; uint8_t* dst = nullptr; const uchar4* src = nullptr; size_t bytes = 0; cudaEvent_t done = nullptr; } deferred_copy;
+    bool defer_readback = true; // VT_DEFER_READBACK
     uint32_t sky_missing_spp = 0;            // != 0: the last frame left the accumulators outside the screen rectangle untouched (spp x sky missing)
     unsigned long long* d_stats = nullptr;
     unsigned long long* h_stats = nullptr; // pinned: kRing slots of 4 counters (rays, iterations, work-claim counter, analytic rays)
@@ -180,9 +185,12 @@ void mat4_mul(const float* a, const float* b, float* r) {
 
 double srgb_to_linear(double c) { return c <= 0.04045 ? c / 12.92 : pow((c + 0.055) / 1.055, 2.4); }
 
+int issue_deferred_copy(cudaEvent_t after);
+
 int alloc_framebuffer() {
     const uint32_t w = g.cfg.width, h = g.cfg.height;
     if (w == g.fb_w && h == g.fb_h && g.d_color) return 0;
+    if (issue_deferred_copy(nullptr)) return -1; // (a read-back of the old buffers that no frame has started yet)
     CK(cudaStreamSynchronize(g.stream));
     if (g.copy_stream) CK(cudaStreamSynchronize(g.copy_stream));
     cudaFree(g.d_rec); cudaFree(g.d_color); cudaFree(g.d_color_alt); cudaFree(g.d_depth); cudaFree(g.d_accum_own);
@@ -213,7 +221,8 @@ int ensure_readback(size_t bytes) {
     return 0;
 }
 
-constexpr uint32_t kDirectInstances = 64; // up to this many instances are read by the setup kernel straight from the staging buffer
+// up to this many instances are read by the setup kernel straight from the staging buffer (VT_DIRECT_INSTANCES)
+static uint32_t direct_instances() { static const uint32_t n = env_u32("VT_DIRECT_INSTANCES", 64); return n; }
 
 float* inst_staging(int slot) { return g.h_inst + (size_t)slot * g.inst_cap * 16; }
 
@@ -247,6 +256,17 @@ int ensure_instances(uint32_t n) {
 }
 
 int render_async(const float* P, const float* V, bool clear_accum, bool resolve);
+
+// starts the read-back that vt_read_color_async armed; `after` (optional): not before this event of the render stream
+int issue_deferred_copy(cudaEvent_t after) {
+    if (!g.deferred_copy.armed) return 0;
+    g.deferred_copy.armed = false;
+    CK(cudaStreamWaitEvent(g.copy_stream, g.ev_color_ready, 0)); // its frame is complete
+    if (after) CK(cudaStreamWaitEvent(g.copy_stream, after, 0));
+    CK(cudaMemcpyAsync(g.deferred_copy.dst, g.deferred_copy.src, g.deferred_copy.bytes, cudaMemcpyDeviceToHost, g.copy_stream));
+    CK(cudaEventRecord(g.deferred_copy.done, g.copy_stream));
+    return 0;
+}
 
 // Called before anything writes the colour buffer: a buffer whose asynchronous read-back (vt_read_color_async) may still be
 // in flight is left alone — the frame goes to the other one, after (device-side) waiting for that one's own read-back.
@@ -559,11 +579,13 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
     if (g.cfg.mode == VT_MODE_RAYS) {
         const unsigned long long n = (unsigned long long)g.cfg.width * g.cfg.height;
         CK(cudaEventRecord(g.ev_trace0[slot], g.stream));
+        if (issue_deferred_copy(g.ev_trace0[slot])) return -1;
         CK(launch_trace_rays(fp, g.d_iu, g.d_arena, n, (unsigned long long)g.cfg.sample_first * n, fb, g.sm_count, g.stream));
         CK(cudaEventRecord(g.ev_trace1[slot], g.stream));
         g.stats.launches += 1;
     } else if (g.cfg.mode == VT_MODE_PRIMARY) {
         CK(cudaEventRecord(g.ev_trace0[slot], g.stream));
+        if (issue_deferred_copy(g.ev_trace0[slot])) return -1;
         CK(launch_trace_primary(fp, g.d_iu, bins, g.d_arena, g.arena_words, in_smem, lut, fb, g.sm_count, g.stream));
         CK(cudaEventRecord(g.ev_trace1[slot], g.stream));
         g.stats.launches += 1;
@@ -576,6 +598,7 @@ int render_async(const float* P, const float* V, bool clear_accum, bool resolve)
             CK(cudaMemsetAsync(g.d_accum, 0, (size_t)g.cfg.width * g.cfg.height * 3 * sizeof(unsigned long long), g.stream));
         }
         CK(cudaEventRecord(g.ev_trace0[slot], g.stream));
+        if (issue_deferred_copy(g.ev_trace0[slot])) return -1;
         CK(launch_trace_paths(fp, g.d_iu, bins, wg, g.d_arena, g.arena_words, in_smem, lut, fb, g.sm_count, g.stream));
         CK(cudaEventRecord(g.ev_trace1[slot], g.stream));
         g.stats.launches += 1;
@@ -731,6 +754,8 @@ extern "C" uint64_t entry(void) {
     g.item_spp = env_u32("VT_ITEM_SPP", 16);
     if (g.item_spp < 1) g.item_spp = 1;
     if (g.item_spp > 255) g.item_spp = 255; // an item's per-pixel sums live in 32-bit shared counters: 255 samples of < 2^24 each
+    g.defer_readback = env_u32("VT_DEFER_READBACK", 1) != 0;
+    g.deferred_copy.armed = false;
     g.item_order = env_u32("VT_ITEM_ORDER", 0); // (1 and 2 measured: whole frame +6 % / +1 %; a rank's tile rows -4 % .. +8 %, box to box)
     if (g.item_order > 2u) g.item_order = 0;
     g.items_per_warp = env_u32("VT_ITEMS_PER_WARP", 6);
@@ -1008,7 +1033,7 @@ extern "C" int32_t end_update_instances(uint32_t instance_count) {
     if (instance_count > g.inst_cap) return fail("end_update_instances: %u > capacity %u", instance_count, g.inst_cap);
     CK(cudaSetDevice(g.device));
     g.inst_count = instance_count;
-    if (instance_count <= kDirectInstances) {
+    if (instance_count <= direct_instances()) {
         g.inst_src = inst_staging(g.inst_slot); // page-locked memory is device-accessible (unified addressing): 64 bytes per instance over PCIe
     } else {
         g.inst_src = nullptr;
@@ -1039,6 +1064,7 @@ extern "C" void cleanup(void) {
     for (auto& b : g.brick_allocs) { cudaFree(b.codes); cudaFree(b.base); cudaFree(b.pool); cudaFree(b.heights); cudaFree(b.colors); cudaFree(b.d_desc); }
     g.brick_allocs.clear();
     cudaFree(g.d_vols); cudaFree(g.d_arena); cudaFree(g.d_inst); cudaFree(g.d_iu); cudaFree(g.d_dec); cudaFree(g.d_thr);
+    g.deferred_copy.armed = false;
     if (g.copy_stream) { cudaStreamSynchronize(g.copy_stream); cudaStreamDestroy(g.copy_stream); cudaEventDestroy(g.ev_color_ready); cudaEventDestroy(g.ev_copy_done[0]); cudaEventDestroy(g.ev_copy_done[1]); }
     cudaFree(g.d_color_alt);
     cudaFree(g.d_rec); cudaFree(g.d_color); cudaFree(g.d_depth); cudaFree(g.d_accum_own); cudaFree(g.d_stats);
@@ -1128,16 +1154,18 @@ extern "C" int64_t vt_read_color_async(uint8_t* pinned_rgba8, size_t capacity) {
         CK(cudaEventCreateWithFlags(&g.ev_copy_done[0], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&g.ev_copy_done[1], cudaEventDisableTiming));
     }
+    if (issue_deferred_copy(nullptr)) return -1;     // (an earlier read-back that no frame has started yet)
     CK(cudaEventRecord(g.ev_color_ready, g.stream)); // the frame enqueued last is complete
-    CK(cudaStreamWaitEvent(g.copy_stream, g.ev_color_ready, 0));
-    CK(cudaMemcpyAsync(pinned_rgba8, g.d_color, bytes, cudaMemcpyDeviceToHost, g.copy_stream));
-    CK(cudaEventRecord(g.ev_copy_done[0], g.copy_stream));
+    g.deferred_copy.armed = true;
+    g.deferred_copy.dst = pinned_rgba8; g.deferred_copy.src = g.d_color; g.deferred_copy.bytes = bytes; g.deferred_copy.done = g.ev_copy_done[0];
     g.copy_pending[0] = true; // (the next frame renders into the other colour buffer: prepare_color_target)
+    if (!g.defer_readback && issue_deferred_copy(nullptr)) return -1;
     return (int64_t)bytes;
 }
 
 extern "C" int32_t vt_read_color_wait(void) {
     if (!g.inited) return -1;
+    if (issue_deferred_copy(nullptr)) return -1;
     if (g.copy_stream) CK(cudaStreamSynchronize(g.copy_stream));
     return 0;
 }
@@ -1145,6 +1173,7 @@ extern "C" int32_t vt_read_color_wait(void) {
 extern "C" int32_t vt_read_color_fence(void) {
     if (!g.inited) return -1;
     if (!g.copy_stream) return 0;
+    if (issue_deferred_copy(nullptr)) return -1;
     for (int i = 0; i < 2; ++i)
         if (g.copy_pending[i]) CK(cudaStreamWaitEvent(g.stream, g.ev_copy_done[i], 0));
     return 0;
