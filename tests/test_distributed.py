@@ -124,3 +124,50 @@ def test_fused_setup_handshake_all_ranks_or_none(tmp_path):
     assert not any(x["ok"] for x in res)
     assert res[0]["calls"] == ["export", "disable"]   # the root had succeeded: it backs out
     assert res[1]["calls"] == ["import"]              # the failing rank has nothing to undo
+
+
+def _rows_worker(rank, world, port, w, h, spp, relief, out_path):
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+
+    import oracle_lib
+    from tools import scenes
+    from vtrace_b200.distributed import reduce_accum, row_owner
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    chunk = scenes.load_asset("AncientTemple")
+    sc = oracle_lib.OracleScene()
+    sc.add_texture(chunk.get_raw(), *chunk.dims())
+    sc.set_instances(scenes.single_instance(0))
+    P, V = scenes.camera(w, h, eye=(0.8, -0.45, 0.6))
+    # frames shared by rows of 8x4-pixel tiles (vt_fused_reduce_partition): a rank keeps every sample of the rows it owns
+    acc, _, _ = sc.render_paths(P, V, w, h, spp=spp, threads=2)
+    acc = acc.reshape(h, w, 3).copy()
+    for y in range(h):
+        if row_owner(y // 4, world, *relief) != rank:
+            acc[y] = 0
+    t = torch.from_numpy(acc.view(np.int64).copy())
+    reduce_accum(t)
+    np.save(f"{out_path}.{rank}.npy", t.numpy())
+    dist.destroy_process_group()
+
+
+def test_two_ranks_sharing_a_frame_by_tile_rows(tmp_path, oracle, assets):
+    """The other way of sharing a frame: every pixel is traced (all samples) by exactly one rank — the owner of its row of
+    tiles, the root relieved by 3/8 — so the sum over the ranks is the single-rank image."""
+    from tools import scenes
+    w, h, spp, world = 80, 45, 3, 2
+    out = str(tmp_path / "rows")
+    mp.spawn(_rows_worker, args=(world, _free_port(), w, h, spp, (3, 8), out), nprocs=world, join=True)
+    sc = oracle.OracleScene()
+    sc.add_texture(assets["AncientTemple"].get_raw(), *assets["AncientTemple"].dims())
+    sc.set_instances(scenes.single_instance(0))
+    P, V = scenes.camera(w, h, eye=(0.8, -0.45, 0.6))
+    whole, _, _ = sc.render_paths(P, V, w, h, spp=spp)
+    for rank in range(world):
+        assert np.array_equal(np.load(f"{out}.{rank}.npy").view(np.uint64).reshape(whole.shape), whole)
